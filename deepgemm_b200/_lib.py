@@ -1,0 +1,98 @@
+"""ctypes binding of the dgb200 C ABI (include/dgb200.h).
+
+The CUDA library is the product: there is no CPU or eager-PyTorch fallback. If ``libdgb200.so`` is missing
+or a call fails, the error is raised to the caller (the reference raises RuntimeError from DG_HOST_ASSERT,
+csrc/utils/exception.hpp:12-40).
+"""
+import ctypes
+import os
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_REPO = os.path.dirname(_HERE)
+LIB_PATH = os.path.join(_HERE, 'lib', 'libdgb200.so')
+SOURCES = [os.path.join(_HERE, 'csrc', f) for f in
+           ('dgb200_api.cu', 'fp8_gemm_kernel.cuh', 'ptx.cuh', 'sf_layout.cuh')] + [os.path.join(_REPO, 'include', 'dgb200.h')]
+
+NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
+              '--expt-relaxed-constexpr', '-shared', '-Xcompiler', '-fPIC']
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile the AOT library for sm_100a with nvcc (cross-compiles without a GPU)."""
+    if not force and os.path.exists(LIB_PATH):
+        newest = max(os.path.getmtime(s) for s in SOURCES if os.path.exists(s))
+        if os.path.getmtime(LIB_PATH) >= newest:
+            return LIB_PATH
+    os.makedirs(os.path.dirname(LIB_PATH), exist_ok=True)
+    nvcc = os.path.join(os.environ.get('CUDA_HOME', '/usr/local/cuda'), 'bin', 'nvcc')
+    cmd = [nvcc] + NVCC_FLAGS + (['-Xptxas', '-v'] if verbose else []) + ['-o', LIB_PATH, SOURCES[0], '-lcudart']
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError(f'nvcc failed:\n{" ".join(cmd)}\n{res.stdout}\n{res.stderr}')
+    if verbose:
+        print(res.stderr)
+    return LIB_PATH
+
+
+class _Config(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_int) for n in ('block_m', 'cluster', 'num_stages', 'num_sms', 'smem_bytes', 'num_tiles')]
+
+
+_P, _I, _L = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64
+
+# name -> (restype, argtypes); must list every symbol include/dgb200.h declares (tests check this)
+SIGNATURES = {
+    'dgb200_last_error': (ctypes.c_char_p, []),
+    'dgb200_version': (_I, []),
+    'dgb200_set_num_sms': (_I, [_I]),
+    'dgb200_get_num_sms': (_I, []),
+    'dgb200_set_tc_util': (_I, [_I]),
+    'dgb200_get_tc_util': (_I, []),
+    'dgb200_set_pdl': (_I, [_I]),
+    'dgb200_get_pdl': (_I, []),
+    'dgb200_set_mk_alignment_for_contiguous_layout': (_I, [_I]),
+    'dgb200_get_mk_alignment_for_contiguous_layout': (_I, []),
+    'dgb200_get_theoretical_mk_alignment_for_contiguous_layout': (_I, [_I]),
+    'dgb200_get_tma_aligned_size': (_I, [_I, _I]),
+    'dgb200_pack_sf_ue8m0': (_I, [_P, _P, _I, _I, _I, _I, _L, _L, _L, _P, _I, _I, _P]),
+    'dgb200_transpose_sf_fp32': (_I, [_P, _P, _I, _I, _I, _L, _L, _L, _P]),
+    'dgb200_pack_sf_ue8m0_k_grouped': (_I, [_P, _P, _I, _P, _I, _I, _P]),
+    'dgb200_fp8_gemm_nt': (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _L, _L, _L, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
+    'dgb200_m_grouped_fp8_gemm_nt_contiguous': (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _L, _L, _L, _I, _I, _I,
+                                                     _I, _I, _I, _I, _I, _P]),
+    'dgb200_m_grouped_fp8_gemm_nt_masked': (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
+    'dgb200_k_grouped_fp8_gemm_tn_contiguous': (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
+    'dgb200_last_config': (_I, [ctypes.POINTER(_Config)]),
+    'dgb200_launch_count': (_L, []),
+}
+
+_lib = None
+
+
+def lib() -> ctypes.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(f'{LIB_PATH} is missing: run `python -c "import __graft_entry__ as g; g.build()"` '
+                               f'(there is no CPU fallback for the FP8 GEMM path)')
+        _lib = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(_lib, name)
+            fn.restype, fn.argtypes = res, args
+    return _lib
+
+
+def check(code: int) -> None:
+    if code != 0:
+        raise RuntimeError(lib().dgb200_last_error().decode())
+
+
+def last_config() -> dict:
+    cfg = _Config()
+    check(lib().dgb200_last_config(ctypes.byref(cfg)))
+    return {n: getattr(cfg, n) for n, _ in _Config._fields_}
+
+
+def launch_count() -> int:
+    return int(lib().dgb200_launch_count())

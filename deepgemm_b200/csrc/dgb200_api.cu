@@ -1,0 +1,571 @@
+// Host side of the dgb200 C ABI (include/dgb200.h): argument checks, tile/pipeline heuristics, tensor-map
+// construction and kernel launch. No torch, no JIT: the kernels in this translation unit are compiled ahead of
+// time for sm_100a and every shape parameter is a run-time argument.
+//
+// Replaces (reference file:line): csrc/apis/gemm.hpp:73-346 (checks), csrc/jit_kernels/heuristics/sm100.hpp
+// (config choice), csrc/jit_kernels/impls/runtime_utils.hpp:113-267 (CUtensorMap builders),
+// csrc/jit_kernels/impls/sm100_fp8_fp4_gemm_1d1d.hpp:93-391 (launchers), csrc/jit/handle.hpp:174-219 (launch attrs),
+// csrc/jit/device_runtime.hpp:14-134 (device property cache + knobs).
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/dgb200.h"
+#include "fp8_gemm_kernel.cuh"
+#include "sf_layout.cuh"
+
+namespace dgb200 {
+namespace {
+
+// ------------------------------------------------------------------------------------------------ errors
+thread_local std::string g_last_error;
+thread_local dgb200_config g_last_config = {0, 0, 0, 0, 0, 0};
+std::atomic<int64_t> g_launch_count{0};
+
+int fail(int code, const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+    return code;
+}
+
+#define DGB_REQUIRE(cond)                                                                                     \
+    do {                                                                                                      \
+        if (!(cond))                                                                                          \
+            return fail(DGB200_ERR_INVALID_ARGUMENT, "Assertion error (%s:%d): %s", __FILE__, __LINE__, #cond); \
+    } while (0)
+
+#define DGB_CUDA(call)                                                                                          \
+    do {                                                                                                        \
+        cudaError_t e_ = (call);                                                                                \
+        if (e_ != cudaSuccess)                                                                                  \
+            return fail(DGB200_ERR_CUDA, "CUDA runtime error (%s:%d): %s", __FILE__, __LINE__, cudaGetErrorString(e_)); \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------------ runtime state
+using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+struct Runtime {
+    std::mutex mu;
+    bool device_ready = false;
+    int device = -1;
+    int sm_count = 0;
+    int smem_optin = 0;
+    int num_sms = 0;  // user override (0 = all)
+    int tc_util = 100;
+    int pdl = 0;
+    int mk_alignment = 128;  // HeuristicsRuntime::kLegacyMKAlignmentForContiguousLayout
+    EncodeTiledFn encode = nullptr;
+};
+Runtime& rt() {
+    static Runtime r;
+    return r;
+}
+
+int ensure_device() {
+    Runtime& r = rt();
+    std::lock_guard<std::mutex> lock(r.mu);
+    int dev = 0;
+    DGB_CUDA(cudaGetDevice(&dev));
+    if (r.device_ready && dev == r.device) return DGB200_OK;
+    cudaDeviceProp prop;
+    DGB_CUDA(cudaGetDeviceProperties(&prop, dev));
+    if (prop.major != 10)
+        return fail(DGB200_ERR_UNSUPPORTED, "dgb200 kernels are built for sm_100a only; device %d is sm_%d%d", dev,
+                    prop.major, prop.minor);
+    r.device = dev;
+    r.sm_count = prop.multiProcessorCount;
+    r.smem_optin = static_cast<int>(prop.sharedMemPerBlockOptin);
+    if (!r.encode) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        DGB_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+        if (qres != cudaDriverEntryPointSuccess || fn == nullptr)
+            return fail(DGB200_ERR_CUDA, "cuTensorMapEncodeTiled is not available in this driver");
+        r.encode = reinterpret_cast<EncodeTiledFn>(fn);
+    }
+    r.device_ready = true;
+    return DGB200_OK;
+}
+
+int effective_num_sms() {
+    Runtime& r = rt();
+    int n = r.num_sms > 0 ? std::min(r.num_sms, r.sm_count) : r.sm_count;
+    return n & ~1;  // CTA pairs need an even grid
+}
+
+inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+inline int align_up(int a, int b) { return ceil_div(a, b) * b; }
+inline int env_int(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return v && *v ? atoi(v) : dflt;
+}
+
+// ------------------------------------------------------------------------------------------------ tensor maps
+struct MapKey {
+    const void* ptr;
+    uint64_t d0, d1, stride;
+    uint32_t b0, b1, dtype, swizzle;
+    bool operator==(const MapKey& o) const {
+        return ptr == o.ptr && d0 == o.d0 && d1 == o.d1 && stride == o.stride && b0 == o.b0 && b1 == o.b1 &&
+               dtype == o.dtype && swizzle == o.swizzle;
+    }
+};
+struct MapKeyHash {
+    size_t operator()(const MapKey& k) const {
+        uint64_t h = reinterpret_cast<uint64_t>(k.ptr);
+        auto mix = [&](uint64_t v) { h ^= v + 0x9e3779b97f4a7c15ull + (h << 6) + (h >> 2); };
+        mix(k.d0), mix(k.d1), mix(k.stride), mix(k.b0), mix(k.b1), mix(k.dtype), mix(k.swizzle);
+        return static_cast<size_t>(h);
+    }
+};
+
+// 2-D tiled map: inner dim d0 contiguous, outer dim d1 with `stride_bytes` pitch; box b0 x b1.
+// Encoding is a pure function of its arguments, so maps are memoised per thread (the reference re-encodes five
+// maps on every call, impls/sm100_fp8_fp4_gemm_1d1d.hpp:117-135).
+int make_map_2d(CUtensorMap* out, const void* ptr, CUtensorMapDataType dtype, uint64_t d0, uint64_t d1,
+                uint64_t stride_bytes, uint32_t b0, uint32_t b1, CUtensorMapSwizzle swizzle) {
+    thread_local std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
+    const MapKey key{ptr, d0, d1, stride_bytes, b0, b1, static_cast<uint32_t>(dtype), static_cast<uint32_t>(swizzle)};
+    auto it = cache.find(key);
+    if (it != cache.end()) {
+        *out = it->second;
+        return DGB200_OK;
+    }
+    const cuuint64_t dims[2] = {d0, d1};
+    const cuuint64_t strides[1] = {stride_bytes};
+    const cuuint32_t box[2] = {b0, b1};
+    const cuuint32_t elem_strides[2] = {1, 1};
+    CUresult res = rt().encode(out, dtype, 2, const_cast<void*>(ptr), dims, strides, box, elem_strides,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (res != CUDA_SUCCESS)
+        return fail(DGB200_ERR_CUDA,
+                    "cuTensorMapEncodeTiled failed (%d): ptr=%p dims={%llu,%llu} stride=%llu box={%u,%u} swizzle=%d",
+                    static_cast<int>(res), ptr, (unsigned long long)d0, (unsigned long long)d1,
+                    (unsigned long long)stride_bytes, b0, b1, static_cast<int>(swizzle));
+    if (cache.size() > 4096) cache.clear();
+    cache.emplace(key, *out);
+    return DGB200_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ heuristics
+struct Problem {
+    int type;          // GemmType
+    int m;             // dense M | contiguous total M | masked M_max
+    int expected_m;    // rows per group the caller expects (== m for dense)
+    int n, k, groups;
+    int alignment;     // contiguous layouts: group start alignment
+};
+struct Config {
+    int block_m, cluster, stages, num_sms, smem_bytes, swizzle_group;
+};
+
+constexpr int kSmemCapacity = 232448;  // 227 KB usable per CTA on sm_100 (heuristics/sm100.hpp:15)
+
+int stage_bytes(int block_m, int cluster) {
+    return kWTileBytes + (block_m / cluster) * kBlockK + 512 + ceil_div(block_m, 128) * 512;
+}
+int smem_bytes_for(int block_m, int cluster, int stages) {
+    return stages * stage_bytes(block_m, cluster) + (3 * stages + 4) * 8 + 16;
+}
+
+// Estimated cycles for the whole problem with a given tile height. Two resources:
+//   tensor pipe : a K=32 UMMA of a CTA pair costs block_m/2 cycles (1 CTA: block_m/... same per-SM rate),
+//   memory      : every CTA pulls (128 + block_m/cluster) x 128 B per k-block; per-SM ingest is capped, and
+//                 unique bytes are bounded by HBM.
+// The tile order walks all m-blocks of a few weight panels, so weights come from HBM once and tokens hit L2.
+double estimate_cycles(const Problem& pb, int block_m, int cluster, int num_sms) {
+    const int num_units = num_sms / cluster;
+    const int n_units = ceil_div(pb.n, (int)kBlockN * cluster);
+    const int num_kb = ceil_div(pb.k, (int)kBlockK);
+    double tiles;
+    if (pb.type == kDense)
+        tiles = (double)ceil_div(pb.m, block_m) * n_units;
+    else if (pb.type == kMMasked)
+        tiles = (double)pb.groups * ceil_div(std::max(pb.expected_m, 1), block_m) * n_units;
+    else
+        tiles = (double)ceil_div(pb.m, block_m) * n_units;
+    const double waves = std::ceil(tiles / num_units);
+    const double busy_ctas = std::min<double>(tiles, num_units) * cluster;
+    const double mma_cycles = 4.0 * block_m / 2.0;                               // per k-block
+    const double cta_bytes = (128.0 + (double)block_m / cluster) * kBlockK;      // per k-block per CTA
+    const double sm_ingest = 56.0;                                               // B/cycle one SM can pull from L2
+    const double hbm_rate = 3400.0;                                              // B/cycle chip-wide (6.5 TB/s @ 1.9 GHz)
+    // unique bytes: each weight tile is new; token tiles are shared by the n-units of a wave
+    const double uniq_bytes = 128.0 * kBlockK + (double)block_m / cluster * kBlockK / std::max(1.0, std::min<double>(n_units, num_units));
+    const double mem_cycles = std::max(cta_bytes / sm_ingest, uniq_bytes * busy_ctas / hbm_rate);
+    const double per_tile = num_kb * std::max(mma_cycles, mem_cycles) + 1500.0 + 6.0 * block_m;
+    return waves * per_tile;
+}
+
+Config choose_config(const Problem& pb) {
+    Config c{};
+    c.num_sms = effective_num_sms();
+    c.cluster = c.num_sms >= 2 ? 2 : 1;
+    std::vector<int> candidates;
+    if (pb.type == kDense) {
+        for (int bm = 16; bm <= (int)kMaxBlockM; bm += 16) candidates.push_back(bm);
+    } else if (pb.type == kMMasked) {
+        for (int bm = 16; bm <= (int)kMaxBlockM; bm += 16) candidates.push_back(bm);
+    } else {
+        // a tile must not straddle two groups: block_m has to divide the group alignment
+        for (int bm = 16; bm <= (int)kMaxBlockM; bm += 16)
+            if (pb.alignment % bm == 0) candidates.push_back(bm);
+        if (candidates.empty()) candidates.push_back(16);
+    }
+    double best = 1e300;
+    c.block_m = candidates[0];
+    for (int bm : candidates) {
+        if (pb.type == kDense && bm - 16 >= align_up(pb.m, 16)) continue;  // taller than the whole problem
+        if (pb.type == kMMasked && bm - 16 >= align_up(pb.m, 16)) continue;
+        const double t = estimate_cycles(pb, bm, c.cluster, c.num_sms);
+        if (t < best * 0.999) best = t, c.block_m = bm;  // ties -> smaller tile (finer tail)
+    }
+    if (int v = env_int("DGB200_BLOCK_M", 0)) c.block_m = v;
+    if (int v = env_int("DGB200_CLUSTER", 0)) c.cluster = v;
+    const int num_kb = ceil_div(pb.k, (int)kBlockK);
+    int stages = (kSmemCapacity - 64) / stage_bytes(c.block_m, c.cluster);
+    while (stages > 1 && smem_bytes_for(c.block_m, c.cluster, stages) > kSmemCapacity) --stages;
+    stages = std::min(stages, 32);
+    (void)num_kb;
+    if (int v = env_int("DGB200_STAGES", 0)) stages = std::min(v, stages);
+    c.stages = std::max(stages, 1);
+    c.smem_bytes = smem_bytes_for(c.block_m, c.cluster, c.stages);
+    c.swizzle_group = env_int("DGB200_SWIZZLE_GROUP", 8);
+    return c;
+}
+
+// ------------------------------------------------------------------------------------------------ launch
+struct GemmCall {
+    int type;
+    const void* a;
+    const void* b;
+    const int32_t* sfa;
+    const int32_t* sfb;
+    void* d;
+    const int32_t* grouped_layout;
+    int m, n, k, groups;
+    int a_rows;  // total rows of the flattened A
+    int64_t lda, ldb, ldd;
+    int sfa_stride, sfb_stride, sfa_cols, sfb_cols;
+    int gran_k_a, gran_k_b;
+    int d_dtype, accumulate;
+    int expected_m, alignment, zero_padding;
+    cudaStream_t stream;
+};
+
+template <typename Kernel>
+int launch_kernel(Kernel kernel, const Config& cfg, cudaStream_t stream, const CUtensorMap& mx, const CUtensorMap& mw,
+                  const CUtensorMap& msfx, const CUtensorMap& msfw, const GemmParams& p) {
+    // Opt in to > 48 KB dynamic smem once per instantiation and device
+    static thread_local std::unordered_map<int, int> configured;  // device -> max smem configured
+    int& cur = configured[rt().device];
+    if (cur < cfg.smem_bytes) {
+        DGB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemCapacity));
+        cur = kSmemCapacity;
+    }
+    cudaLaunchConfig_t lc{};
+    lc.gridDim = dim3(cfg.num_sms, 1, 1);
+    lc.blockDim = dim3(kNumThreads, 1, 1);
+    lc.dynamicSmemBytes = cfg.smem_bytes;
+    lc.stream = stream;
+    cudaLaunchAttribute attrs[2];
+    int na = 0;
+    if (cfg.cluster > 1) {
+        attrs[na].id = cudaLaunchAttributeClusterDimension;
+        attrs[na].val.clusterDim.x = cfg.cluster;
+        attrs[na].val.clusterDim.y = 1;
+        attrs[na].val.clusterDim.z = 1;
+        ++na;
+    }
+    if (rt().pdl) {
+        attrs[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attrs[na].val.programmaticStreamSerializationAllowed = 1;
+        ++na;
+    }
+    lc.attrs = attrs;
+    lc.numAttrs = na;
+    DGB_CUDA(cudaLaunchKernelEx(&lc, kernel, mx, mw, msfx, msfw, p));
+    g_launch_count.fetch_add(1, std::memory_order_relaxed);
+    return DGB200_OK;
+}
+
+template <int kType, int kCluster>
+int dispatch_out(const GemmCall& c, const Config& cfg, const CUtensorMap& mx, const CUtensorMap& mw,
+                 const CUtensorMap& msfx, const CUtensorMap& msfw, const GemmParams& p) {
+    if (c.d_dtype == DGB200_BF16) {
+        if (c.accumulate)
+            return launch_kernel(fp8_gemm_kernel<kType, kCluster, __nv_bfloat16, true>, cfg, c.stream, mx, mw, msfx, msfw, p);
+        return launch_kernel(fp8_gemm_kernel<kType, kCluster, __nv_bfloat16, false>, cfg, c.stream, mx, mw, msfx, msfw, p);
+    }
+    if (c.accumulate)
+        return launch_kernel(fp8_gemm_kernel<kType, kCluster, float, true>, cfg, c.stream, mx, mw, msfx, msfw, p);
+    return launch_kernel(fp8_gemm_kernel<kType, kCluster, float, false>, cfg, c.stream, mx, mw, msfx, msfw, p);
+}
+
+template <int kType>
+int dispatch_cluster(const GemmCall& c, const Config& cfg, const CUtensorMap& mx, const CUtensorMap& mw,
+                     const CUtensorMap& msfx, const CUtensorMap& msfw, const GemmParams& p) {
+    if (cfg.cluster == 2) return dispatch_out<kType, 2>(c, cfg, mx, mw, msfx, msfw, p);
+    return dispatch_out<kType, 1>(c, cfg, mx, mw, msfx, msfw, p);
+}
+
+int run_gemm(const GemmCall& c) {
+    if (int e = ensure_device()) return e;
+    DGB_REQUIRE(c.gran_k_a == 32 || c.gran_k_a == 128);
+    DGB_REQUIRE(c.gran_k_b == 32 || c.gran_k_b == 128);
+    DGB_REQUIRE(c.lda % 16 == 0 && c.ldb % 16 == 0);  // TMA: 16-byte pitch
+    DGB_REQUIRE((reinterpret_cast<uintptr_t>(c.a) & 15) == 0 && (reinterpret_cast<uintptr_t>(c.b) & 15) == 0);
+    DGB_REQUIRE((reinterpret_cast<uintptr_t>(c.sfa) & 15) == 0 && (reinterpret_cast<uintptr_t>(c.sfb) & 15) == 0);
+    DGB_REQUIRE(c.sfa_stride % 4 == 0 && c.sfb_stride % 4 == 0);
+
+    Problem pb{c.type, c.m, c.expected_m, c.n, c.k, c.groups, c.alignment};
+    const Config cfg = choose_config(pb);
+    DGB_REQUIRE(cfg.block_m % 16 == 0 && cfg.block_m >= 16 && cfg.block_m <= (int)kMaxBlockM);
+    DGB_REQUIRE(cfg.cluster == 1 || cfg.cluster == 2);
+    if (c.type == kMContiguous || c.type == kMContiguousPsum) DGB_REQUIRE(c.alignment % cfg.block_m == 0);
+
+    const int num_kp_a = ceil_div(c.k, c.gran_k_a * 4), num_kp_b = ceil_div(c.k, c.gran_k_b * 4);
+    const int b_groups = c.type == kDense ? 1 : c.groups;
+    const int sfa_groups = c.type == kMMasked ? c.groups : 1;
+
+    CUtensorMap mx, mw, msfx, msfw;
+    if (int e = make_map_2d(&mx, c.a, CU_TENSOR_MAP_DATA_TYPE_UINT8, c.k, c.a_rows, c.lda, kBlockK,
+                            cfg.block_m / cfg.cluster, CU_TENSOR_MAP_SWIZZLE_128B)) return e;
+    if (int e = make_map_2d(&mw, c.b, CU_TENSOR_MAP_DATA_TYPE_UINT8, c.k, (uint64_t)c.n * b_groups, c.ldb, kBlockK,
+                            kBlockN, CU_TENSOR_MAP_SWIZZLE_128B)) return e;
+    if (int e = make_map_2d(&msfx, c.sfa, CU_TENSOR_MAP_DATA_TYPE_INT32, c.sfa_cols, (uint64_t)num_kp_a * sfa_groups,
+                            (uint64_t)c.sfa_stride * 4, cfg.block_m, 1, CU_TENSOR_MAP_SWIZZLE_NONE)) return e;
+    if (int e = make_map_2d(&msfw, c.sfb, CU_TENSOR_MAP_DATA_TYPE_INT32, c.sfb_cols, (uint64_t)num_kp_b * b_groups,
+                            (uint64_t)c.sfb_stride * 4, kBlockN, 1, CU_TENSOR_MAP_SWIZZLE_NONE)) return e;
+
+    GemmParams p{};
+    p.d = c.d;
+    p.grouped_layout = c.grouped_layout;
+    p.m = c.m, p.n = c.n, p.k = c.k;
+    p.num_groups = c.groups;
+    p.block_m = cfg.block_m;
+    p.num_stages = cfg.stages;
+    p.ld_d = static_cast<uint32_t>(c.ldd);
+    p.num_kp_x = num_kp_a, p.num_kp_w = num_kp_b;
+    p.kb_per_sf_x = c.gran_k_a == 128 ? 4 : 1;
+    p.kb_per_sf_w = c.gran_k_b == 128 ? 4 : 1;
+    p.swizzle_group = std::max(1, cfg.swizzle_group);
+    p.m_alignment = std::max(1, c.alignment);
+    p.zero_padding = c.zero_padding;
+
+    g_last_config = dgb200_config{cfg.block_m, cfg.cluster, cfg.stages, cfg.num_sms, cfg.smem_bytes, 0};
+    if (env_int("DGB200_PRINT_CONFIGS", 0))
+        fprintf(stderr, "dgb200 config: type=%d m=%d n=%d k=%d groups=%d -> block_m=%d cluster=%d stages=%d sms=%d smem=%d\n",
+                c.type, c.m, c.n, c.k, c.groups, cfg.block_m, cfg.cluster, cfg.stages, cfg.num_sms, cfg.smem_bytes);
+
+    switch (c.type) {
+        case kDense: return dispatch_cluster<kDense>(c, cfg, mx, mw, msfx, msfw, p);
+        case kMContiguous: return dispatch_cluster<kMContiguous>(c, cfg, mx, mw, msfx, msfw, p);
+        case kMMasked: return dispatch_cluster<kMMasked>(c, cfg, mx, mw, msfx, msfw, p);
+        case kMContiguousPsum: return dispatch_cluster<kMContiguousPsum>(c, cfg, mx, mw, msfx, msfw, p);
+        default: return fail(DGB200_ERR_INVALID_ARGUMENT, "unknown gemm type %d", c.type);
+    }
+}
+
+}  // namespace
+}  // namespace dgb200
+
+// ================================================================================================ C ABI
+using namespace dgb200;
+
+extern "C" {
+
+const char* dgb200_last_error(void) { return g_last_error.c_str(); }
+int dgb200_version(void) { return DGB200_VERSION; }
+
+int dgb200_set_num_sms(int num_sms) {
+    DGB_REQUIRE(num_sms > 0 && num_sms % 2 == 0);
+    if (rt().device_ready) DGB_REQUIRE(num_sms <= rt().sm_count);
+    rt().num_sms = num_sms;
+    return DGB200_OK;
+}
+int dgb200_get_num_sms(void) {
+    if (!rt().device_ready) return rt().num_sms;
+    return effective_num_sms();
+}
+int dgb200_set_tc_util(int percent) {
+    DGB_REQUIRE(percent > 0 && percent <= 100);
+    rt().tc_util = percent;
+    return DGB200_OK;
+}
+int dgb200_get_tc_util(void) { return rt().tc_util; }
+int dgb200_set_pdl(int enabled) {
+    rt().pdl = enabled != 0;
+    return DGB200_OK;
+}
+int dgb200_get_pdl(void) { return rt().pdl; }
+int dgb200_set_mk_alignment_for_contiguous_layout(int alignment) {
+    DGB_REQUIRE(alignment > 0 && alignment % 16 == 0);
+    rt().mk_alignment = alignment;
+    return DGB200_OK;
+}
+int dgb200_get_mk_alignment_for_contiguous_layout(void) { return rt().mk_alignment; }
+int dgb200_get_theoretical_mk_alignment_for_contiguous_layout(int expected_m) {
+    // Largest tile height this kernel supports, shrunk while it still covers `expected_m`
+    // (the reference returns 224 on SM100 and shrinks in steps of 32, heuristics/runtime.hpp:47-57).
+    int block_m = 224;
+    if (expected_m > 0)
+        for (; block_m > 32 && block_m - 32 >= expected_m; block_m -= 32) {
+        }
+    return block_m;
+}
+int dgb200_get_tma_aligned_size(int x, int element_size) {
+    if (element_size <= 0 || 16 % element_size != 0) return -1;
+    return align_up(x, 16 / element_size);
+}
+
+int dgb200_pack_sf_ue8m0(const float* sf, int32_t* out, int mn, int sf_k, int num_groups, int gran_mn,
+                         int64_t stride_g, int64_t stride_mn, int64_t stride_k, const int32_t* psum_layout,
+                         int num_psum_groups, int m_alignment, void* stream) {
+    if (int e = ensure_device()) return e;
+    DGB_REQUIRE(mn > 0 && sf_k > 0 && num_groups > 0 && gran_mn > 0);
+    const int aligned_mn = align_up(mn, 4), num_kp = ceil_div(sf_k, 4);
+    const dim3 grid(ceil_div(aligned_mn, 128), num_kp, num_groups);
+    DGB_REQUIRE(num_kp <= 65535 && num_groups <= 65535);
+    if (psum_layout != nullptr) {
+        DGB_REQUIRE(num_psum_groups > 0 && m_alignment > 0);
+        pack_sf_ue8m0_kernel<true><<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+            sf, reinterpret_cast<uint32_t*>(out), mn, aligned_mn, sf_k, num_kp, gran_mn, stride_g, stride_mn, stride_k,
+            psum_layout, num_psum_groups, m_alignment);
+    } else {
+        pack_sf_ue8m0_kernel<false><<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+            sf, reinterpret_cast<uint32_t*>(out), mn, aligned_mn, sf_k, num_kp, gran_mn, stride_g, stride_mn, stride_k,
+            nullptr, 0, 1);
+    }
+    DGB_CUDA(cudaGetLastError());
+    g_launch_count.fetch_add(1, std::memory_order_relaxed);
+    return DGB200_OK;
+}
+
+int dgb200_transpose_sf_fp32(const float* sf, float* out, int mn, int sf_k, int num_groups, int64_t stride_g,
+                             int64_t stride_mn, int64_t stride_k, void* stream) {
+    if (int e = ensure_device()) return e;
+    DGB_REQUIRE(mn > 0 && sf_k > 0 && num_groups > 0);
+    DGB_REQUIRE(sf_k <= 65535 && num_groups <= 65535);
+    const int aligned_mn = align_up(mn, 4);
+    const dim3 grid(ceil_div(mn, 128), sf_k, num_groups);
+    transpose_sf_fp32_kernel<<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(sf, out, mn, aligned_mn, sf_k, stride_g,
+                                                                                  stride_mn, stride_k);
+    DGB_CUDA(cudaGetLastError());
+    g_launch_count.fetch_add(1, std::memory_order_relaxed);
+    return DGB200_OK;
+}
+
+int dgb200_pack_sf_ue8m0_k_grouped(const float* sf, int32_t* out, int mn, const int32_t* ks_host, int num_groups,
+                                   int gran_k, void* stream) {
+    (void)sf, (void)out, (void)mn, (void)ks_host, (void)num_groups, (void)gran_k, (void)stream;
+    return fail(DGB200_ERR_UNSUPPORTED, "k-grouped SF packing is not built yet");
+}
+
+int dgb200_fp8_gemm_nt(const void* a, const int32_t* sfa, const void* b, const int32_t* sfb, void* d, int m, int n,
+                       int k, int64_t lda, int64_t ldb, int64_t ldd, int major_a, int major_b, int sfa_stride,
+                       int sfb_stride, int gran_k_a, int gran_k_b, int d_dtype, int accumulate, void* stream) {
+    DGB_REQUIRE(m >= 0 && n >= 0 && k >= 0);
+    if (m == 0 || n == 0) return DGB200_OK;  // gemm.hpp:22-23
+    DGB_REQUIRE(k > 0);                      // k == 0 (D = C or 0) is handled by the host wrapper, gemm.hpp:36-40
+    DGB_REQUIRE(d_dtype == DGB200_BF16 || d_dtype == DGB200_FP32);
+    if (major_a != DGB200_K_MAJOR || major_b != DGB200_K_MAJOR)
+        return fail(DGB200_ERR_UNSUPPORTED, "MN-major FP8 operands are not built yet");
+    DGB_REQUIRE(lda >= k && ldb >= k && ldd >= n);
+    DGB_REQUIRE(sfa_stride >= align_up(m, 4) && sfb_stride >= align_up(n, 4));
+    GemmCall c{};
+    c.type = kDense;
+    c.a = a, c.b = b, c.sfa = sfa, c.sfb = sfb, c.d = d, c.grouped_layout = nullptr;
+    c.m = m, c.n = n, c.k = k, c.groups = 1, c.a_rows = m;
+    c.lda = lda, c.ldb = ldb, c.ldd = ldd;
+    c.sfa_stride = sfa_stride, c.sfb_stride = sfb_stride;
+    c.sfa_cols = align_up(m, 4), c.sfb_cols = align_up(n, 4);
+    c.gran_k_a = gran_k_a, c.gran_k_b = gran_k_b;
+    c.d_dtype = d_dtype, c.accumulate = accumulate != 0;
+    c.expected_m = m, c.alignment = 1, c.zero_padding = 0;
+    c.stream = static_cast<cudaStream_t>(stream);
+    return run_gemm(c);
+}
+
+int dgb200_m_grouped_fp8_gemm_nt_contiguous(const void* a, const int32_t* sfa, const void* b, const int32_t* sfb,
+                                            void* d, const int32_t* grouped_layout, int num_groups, int m, int n,
+                                            int k, int64_t lda, int64_t ldb, int64_t ldd, int major_b, int sfa_stride,
+                                            int sfb_stride, int gran_k_a, int gran_k_b, int use_psum_layout,
+                                            int ensure_zero_padding, int expected_m_for_psum_layout, void* stream) {
+    DGB_REQUIRE(m >= 0);
+    DGB_REQUIRE(n > 0 && k > 0 && num_groups > 0);  // gemm.hpp:192
+    if (m == 0) return DGB200_OK;                    // gemm.hpp:210-211
+    DGB_REQUIRE(grouped_layout != nullptr);
+    if (major_b != DGB200_K_MAJOR) return fail(DGB200_ERR_UNSUPPORTED, "MN-major FP8 operands are not built yet");
+    DGB_REQUIRE(lda >= k && ldb >= k && ldd >= n);
+    DGB_REQUIRE(sfa_stride >= align_up(m, 4) && sfb_stride >= align_up(n, 4));
+    GemmCall c{};
+    c.type = use_psum_layout ? kMContiguousPsum : kMContiguous;
+    c.a = a, c.b = b, c.sfa = sfa, c.sfb = sfb, c.d = d, c.grouped_layout = grouped_layout;
+    c.m = m, c.n = n, c.k = k, c.groups = num_groups, c.a_rows = m;
+    c.lda = lda, c.ldb = ldb, c.ldd = ldd;
+    c.sfa_stride = sfa_stride, c.sfb_stride = sfb_stride;
+    c.sfa_cols = align_up(m, 4), c.sfb_cols = align_up(n, 4);
+    c.gran_k_a = gran_k_a, c.gran_k_b = gran_k_b;
+    c.d_dtype = DGB200_BF16, c.accumulate = 0;
+    c.expected_m = expected_m_for_psum_layout > 0 ? expected_m_for_psum_layout : ceil_div(m, num_groups);
+    c.alignment = rt().mk_alignment;
+    c.zero_padding = use_psum_layout && ensure_zero_padding;
+    c.stream = static_cast<cudaStream_t>(stream);
+    return run_gemm(c);
+}
+
+int dgb200_m_grouped_fp8_gemm_nt_masked(const void* a, const int32_t* sfa, const void* b, const int32_t* sfb, void* d,
+                                        const int32_t* masked_m, int num_groups, int m_max, int n, int k,
+                                        int expected_m, int sfa_stride, int sfb_stride, int gran_k_a, int gran_k_b,
+                                        void* stream) {
+    DGB_REQUIRE(expected_m > 0 && m_max > 0 && n > 0 && k > 0 && num_groups > 0);  // gemm.hpp:274
+    DGB_REQUIRE(masked_m != nullptr);
+    DGB_REQUIRE(sfa_stride >= align_up(m_max, 4) && sfb_stride >= align_up(n, 4));
+    GemmCall c{};
+    c.type = kMMasked;
+    c.a = a, c.b = b, c.sfa = sfa, c.sfb = sfb, c.d = d, c.grouped_layout = masked_m;
+    c.m = m_max, c.n = n, c.k = k, c.groups = num_groups, c.a_rows = num_groups * m_max;
+    c.lda = k, c.ldb = k, c.ldd = n;
+    c.sfa_stride = sfa_stride, c.sfb_stride = sfb_stride;
+    c.sfa_cols = align_up(m_max, 4), c.sfb_cols = align_up(n, 4);
+    c.gran_k_a = gran_k_a, c.gran_k_b = gran_k_b;
+    c.d_dtype = DGB200_BF16, c.accumulate = 0;
+    c.expected_m = std::min(expected_m, m_max), c.alignment = 1, c.zero_padding = 0;
+    c.stream = static_cast<cudaStream_t>(stream);
+    return run_gemm(c);
+}
+
+int dgb200_k_grouped_fp8_gemm_tn_contiguous(const void* a, const int32_t* sfa, const void* b, const int32_t* sfb,
+                                            float* d, const int32_t* ks_host, int num_groups, int m, int n, int gran_k,
+                                            void* stream) {
+    (void)a, (void)sfa, (void)b, (void)sfb, (void)d, (void)ks_host, (void)num_groups, (void)m, (void)n, (void)gran_k,
+        (void)stream;
+    return fail(DGB200_ERR_UNSUPPORTED, "k-grouped FP8 GEMM is not built yet");
+}
+
+int dgb200_last_config(dgb200_config* out) {
+    if (!out) return DGB200_ERR_INVALID_ARGUMENT;
+    *out = g_last_config;
+    return DGB200_OK;
+}
+int64_t dgb200_launch_count(void) { return g_launch_count.load(); }
+
+}  // extern "C"

@@ -1,0 +1,428 @@
+// FP8 (E4M3) x FP8 blockwise-scaled GEMM for sm_100a -- the one hot kernel of this library.
+//
+//   D[m, n] (+)= sum_k  A[m, k] * 2^(sfa[m, k/g]-127)  *  B[n, k] * 2^(sfb[n, k/g]-127)        (FP32 accumulate)
+//
+// Replaces the reference's `sm100_fp8_fp4_gemm_1d1d_impl`
+// (deep_gemm/include/deep_gemm/impls/sm100_fp8_fp4_gemm_1d1d.cuh:33-534) together with its scheduler
+// (scheduler/gemm.cuh:39-325) and epilogues (epilogue/sm100_store_cd*.cuh), but it is a different program:
+//
+//  * AOT + runtime shapes. M/N/K, group count, tile height `block_m`, pipeline depth and SM count are kernel
+//    *arguments* (the reference bakes all of them into a JIT-compiled template instance per shape).
+//  * One orientation only: the weight operand B always sits on the 128 TMEM lanes (UMMA "A" side), the token
+//    operand A on the TMEM columns (UMMA "N" side, any multiple of 16 up to 240). A CTA pair (cta_group::2) owns
+//    256 weight rows x block_m tokens and shares the token tile, half of it in each CTA's shared memory.
+//  * No shared-memory staging of the output and no TMA store: with tokens on TMEM columns every warp-level
+//    `tcgen05.ld` hands each lane one output column n and consecutive rows m, so a plain store instruction
+//    writes 32 consecutive n of one row (64 B bf16 / 128 B fp32, sector aligned). All 227 KB of smem feed the
+//    TMA->MMA ring instead, rows are predicated exactly (masked / psum layouts never write invalid rows).
+//  * Scale factors arrive in the reference's documented wire format (packed UE8M0 int32, MN-major,
+//    csrc/utils/layout.hpp:100-107) so user-packed tensors keep working; a helper warp re-tiles each 128-word
+//    group into the `tcgen05.cp` 32x128b layout before the MMA warp copies it into TMEM.
+//
+// Warp roles (256 threads): w0 TMA producer | w1 MMA issuer (leader CTA) | w2 TMEM alloc + SF re-tiler |
+//                           w3 idle | w4-7 epilogue (TMEM -> registers -> global).
+#pragma once
+#include <cuda_bf16.h>
+
+#include "ptx.cuh"
+
+namespace dgb200 {
+
+enum GemmType : int {
+    kDense = 0,         // D[M,N] = A[M,K] B[N,K]^T
+    kMContiguous = 1,   // rows of A grouped, grouped_layout[r] = group id (-1 = padding)      (gemm.hpp:166)
+    kMMasked = 2,       // A[G,Mmax,K], rows < masked_m[g] valid                                 (gemm.hpp:250)
+    kMContiguousPsum = 3,  // grouped_layout[g] = end row of group g, starts aligned              (scheduler/gemm.cuh:217-237)
+};
+
+constexpr uint32_t kBlockN = 128;        // weight rows per CTA == TMEM lanes
+constexpr uint32_t kBlockK = 128;        // K bytes per pipeline stage == one 128B swizzle atom
+constexpr uint32_t kUmmaK = 32;          // K per tcgen05.mma for 8-bit operands
+constexpr uint32_t kMaxBlockM = 240;     // 2 accumulator buffers + SF columns must fit 512 TMEM columns
+constexpr uint32_t kAccumColStride = 256;
+constexpr uint32_t kTmemColSFW = 496;    // weight scale factors: 4 columns
+constexpr uint32_t kTmemColSFX = 500;    // token scale factors: up to 8 columns
+constexpr uint32_t kTmemCols = 512;
+constexpr uint32_t kNumThreads = 256;
+constexpr uint32_t kNumEpilogueThreads = 128;
+constexpr uint32_t kWTileBytes = kBlockN * kBlockK;  // 16 KB
+
+struct GemmParams {
+    void* d;                    // output (bf16 or fp32), row stride ld_d elements
+    const int* grouped_layout;  // see GemmType
+    uint32_t m;                 // dense: M | contiguous: sum of aligned M | masked: M_max
+    uint32_t n, k;
+    uint32_t num_groups;
+    uint32_t block_m;           // token rows per tile, multiple of 16, <= 240
+    uint32_t num_stages;        // TMA->MMA ring depth
+    uint32_t ld_d;
+    uint32_t num_kp_x;          // packed SF words along K per group (tokens)
+    uint32_t num_kp_w;          // packed SF words along K per group (weights)
+    uint32_t kb_per_sf_x;       // k-blocks covered by one packed SF word: 4 (gran_k 128) or 1 (gran_k 32)
+    uint32_t kb_per_sf_w;
+    uint32_t swizzle_group;     // L2 tile-order group width (in n-units)
+    uint32_t m_alignment;       // contiguous layouts: group start alignment
+    uint32_t zero_padding;      // psum: write zeros to [end, aligned end)
+};
+
+// ------------------------------------------------------------------------------------------------ scheduler
+struct Tile {
+    uint32_t x_row;     // first token row of the tile in the (group-flattened) A / SFA-column space
+    uint32_t d_row;     // first output row
+    uint32_t sfx_col;   // column (mn index) in the token SF map
+    uint32_t sfx_row;   // first k-row in the token SF map
+    uint32_t w_row;     // first weight row of THIS CTA in the group-flattened B
+    uint32_t sfw_col;
+    uint32_t sfw_row;
+    uint32_t n0;        // first output column of THIS CTA
+    uint32_t valid_m;   // rows [0, valid_m) of the tile are real outputs
+    uint32_t store_m;   // rows [0, store_m) are written (>= valid_m only when zero padding is requested)
+};
+
+template <int kGemmType, int kCluster>
+struct Scheduler {
+    const GemmParams& p;
+    uint32_t cta_rank, cluster_id, num_clusters;
+    uint32_t num_n_units;
+    uint32_t iter = 0;
+    // grouped walk state
+    uint32_t g = 0, unit_cum = 0, row_start = 0, row_end = 0;
+
+    __device__ Scheduler(const GemmParams& p_, uint32_t rank) : p(p_), cta_rank(rank) {
+        cluster_id = blockIdx.x / kCluster;
+        num_clusters = gridDim.x / kCluster;
+        num_n_units = (p.n + kBlockN * kCluster - 1) / (kBlockN * kCluster);
+        if constexpr (kGemmType == kMContiguousPsum) row_end = static_cast<uint32_t>(__ldg(p.grouped_layout));
+    }
+
+    // L2-friendly order inside one problem of `num_m` m-blocks: walk `swizzle_group` n-units at a time.
+    __device__ void split(uint32_t local, uint32_t num_m, uint32_t& m_blk, uint32_t& n_unit) const {
+        const uint32_t gw = p.swizzle_group;
+        const uint32_t per_group = gw * num_m;
+        const uint32_t grp = local / per_group;
+        const uint32_t first = grp * gw;
+        const uint32_t in = local - grp * per_group;
+        const uint32_t width = min(gw, num_n_units - first);
+        m_blk = in / width;
+        n_unit = first + in - m_blk * width;
+    }
+
+    __device__ bool next(Tile& t) {
+        const uint32_t idx = cluster_id + (iter++) * num_clusters;
+        uint32_t m_blk, n_unit, group = 0;
+        if constexpr (kGemmType == kDense || kGemmType == kMContiguous) {
+            const uint32_t num_m = (p.m + p.block_m - 1) / p.block_m;
+            if (idx >= num_m * num_n_units) return false;
+            split(idx, num_m, m_blk, n_unit);
+            t.x_row = m_blk * p.block_m;
+            t.d_row = t.x_row;
+            t.sfx_col = t.x_row;
+            t.sfx_row = 0;
+            t.valid_m = min(p.block_m, p.m - t.x_row);
+            t.store_m = t.valid_m;
+            if constexpr (kGemmType == kMContiguous) group = static_cast<uint32_t>(max(0, __ldg(p.grouped_layout + t.x_row)));
+        } else if constexpr (kGemmType == kMMasked) {
+            uint32_t num_m;
+            while (true) {
+                if (g >= p.num_groups) return false;
+                const uint32_t mg = min(static_cast<uint32_t>(max(0, __ldg(p.grouped_layout + g))), p.m);
+                num_m = (mg + p.block_m - 1) / p.block_m;
+                if (idx < (unit_cum + num_m) * num_n_units) {
+                    row_end = mg;
+                    break;
+                }
+                unit_cum += num_m, ++g;
+            }
+            split(idx - unit_cum * num_n_units, num_m, m_blk, n_unit);
+            group = g;
+            const uint32_t m0 = m_blk * p.block_m;
+            t.x_row = g * p.m + m0;
+            t.d_row = t.x_row;
+            t.sfx_col = m0;
+            t.sfx_row = g * p.num_kp_x;
+            t.valid_m = min(p.block_m, row_end - m0);
+            t.store_m = t.valid_m;
+        } else {  // kMContiguousPsum
+            uint32_t num_m;
+            while (true) {
+                num_m = (row_end - row_start + p.block_m - 1) / p.block_m;
+                if (idx < (unit_cum + num_m) * num_n_units) break;
+                unit_cum += num_m;
+                if (++g >= p.num_groups) return false;
+                row_start = (row_end + p.m_alignment - 1) / p.m_alignment * p.m_alignment;
+                row_end = max(row_start, static_cast<uint32_t>(__ldg(p.grouped_layout + g)));
+            }
+            split(idx - unit_cum * num_n_units, num_m, m_blk, n_unit);
+            group = g;
+            t.x_row = row_start + m_blk * p.block_m;
+            t.d_row = t.x_row;
+            t.sfx_col = t.x_row;
+            t.sfx_row = 0;
+            t.valid_m = min(p.block_m, row_end - t.x_row);
+            const uint32_t aligned_end = min(p.m, (row_end + p.m_alignment - 1) / p.m_alignment * p.m_alignment);
+            t.store_m = p.zero_padding ? min(p.block_m, aligned_end - t.x_row) : t.valid_m;
+        }
+        t.n0 = (n_unit * kCluster + cta_rank) * kBlockN;
+        t.w_row = group * p.n + t.n0;
+        t.sfw_col = t.n0;
+        t.sfw_row = group * p.num_kp_w;
+        return true;
+    }
+};
+
+// ------------------------------------------------------------------------------------------------ epilogue helpers
+template <typename out_t>
+__device__ __forceinline__ void store_out(out_t* ptr, float v, bool accumulate);
+
+template <>
+__device__ __forceinline__ void store_out<float>(float* ptr, float v, bool accumulate) {
+    if (accumulate) v += *ptr;
+    *ptr = v;
+}
+template <>
+__device__ __forceinline__ void store_out<__nv_bfloat16>(__nv_bfloat16* ptr, float v, bool accumulate) {
+    __nv_bfloat16 r = __float2bfloat16_rn(v);
+    // Same arithmetic as the reference's memory-side `cp.reduce.async.bulk ... add` on a BF16 tile
+    // (epilogue/sm100_store_cd.cuh:126-128): round the accumulator to BF16 first, then one BF16 add.
+    if (accumulate) r = __hadd(r, *ptr);
+    *ptr = r;
+}
+
+// ------------------------------------------------------------------------------------------------ the kernel
+template <int kGemmType, int kCluster, typename out_t, bool kAccumulate>
+__global__ void __launch_bounds__(kNumThreads, 1)
+fp8_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
+                const __grid_constant__ CUtensorMap map_sfx, const __grid_constant__ CUtensorMap map_sfw,
+                const __grid_constant__ GemmParams p) {
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ >= 1000)
+    using namespace ptx;
+    extern __shared__ __align__(1024) uint8_t smem[];
+
+    const uint32_t warp_idx = __shfl_sync(0xffffffffu, threadIdx.x / 32, 0);
+    const uint32_t lane = lane_id();
+    const uint32_t cta_rank = kCluster == 1 ? 0u : cluster_ctarank();
+    const bool is_leader = cta_rank == 0;
+
+    // ---- shared memory carve-up (all sizes are runtime values)
+    const uint32_t num_stages = p.num_stages;
+    const uint32_t load_m = p.block_m / kCluster;                           // token rows this CTA loads per stage
+    const uint32_t x_tile_bytes = load_m * kBlockK;                         // multiple of 1024 (load_m % 8 == 0)
+    const uint32_t num_sfx_groups = (p.block_m + 127) / 128;                // 128-row UTCCP groups of token SFs
+    const uint32_t sfx_bytes = num_sfx_groups * 512;
+    uint8_t* smem_w = smem;
+    uint8_t* smem_x = smem_w + num_stages * kWTileBytes;
+    uint8_t* smem_sfw = smem_x + num_stages * x_tile_bytes;
+    uint8_t* smem_sfx = smem_sfw + num_stages * 512;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_sfx + num_stages * sfx_bytes);
+    uint64_t* full_bar = bars;                         // TMA bytes landed (per CTA)
+    uint64_t* empty_bar = bars + num_stages;           // MMAs that read the stage retired (per CTA, via commit)
+    uint64_t* ready_bar = bars + 2 * num_stages;       // stage landed in every CTA + SFs re-tiled (leader only)
+    uint64_t* tmem_full_bar = bars + 3 * num_stages;   // [2] accumulator complete (per CTA, via commit)
+    uint64_t* tmem_empty_bar = tmem_full_bar + 2;      // [2] accumulator drained by all epilogue threads (leader only)
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+
+    if (warp_idx == 0 && elect_one()) {
+        prefetch_tensormap(&map_x);
+        prefetch_tensormap(&map_w);
+        prefetch_tensormap(&map_sfx);
+        prefetch_tensormap(&map_sfw);
+    }
+    if (warp_idx == 1 && elect_one()) {
+        for (uint32_t i = 0; i < num_stages; ++i) {
+            mbar_init(full_bar + i, 1);
+            mbar_init(empty_bar + i, 1);
+            mbar_init(ready_bar + i, 32 * kCluster);
+        }
+        for (uint32_t i = 0; i < 2; ++i) {
+            mbar_init(tmem_full_bar + i, 1);
+            mbar_init(tmem_empty_bar + i, kNumEpilogueThreads * kCluster);
+        }
+        fence_mbar_init();
+    }
+    if constexpr (kCluster > 1) {
+        // Both CTAs must be resident before a cta_group::2 allocation
+        cluster_arrive_relaxed();
+        cluster_wait();
+    }
+    if (warp_idx == 2) tmem_alloc<kCluster>(tmem_ptr_smem, kTmemCols);
+    tcgen05_fence_before();
+    if constexpr (kCluster > 1) {
+        cluster_arrive();
+        cluster_wait();
+    } else {
+        __syncthreads();
+    }
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+
+    // Programmatic dependent launch: everything above overlaps the previous kernel's tail
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+
+    const uint32_t num_kb = (p.k + kBlockK - 1) / kBlockK;
+    uint32_t stage = 0, phase = 0;
+    auto advance = [&]() {
+        stage = stage + 1 == num_stages ? 0 : stage + 1;
+        phase ^= (stage == 0);
+    };
+
+    if (warp_idx == 0) {
+        // =================================================================== TMA producer (one lane, every CTA)
+        if (elect_one()) {
+            Scheduler<kGemmType, kCluster> sched(p, cta_rank);
+            Tile t;
+            const uint32_t ab_bytes = kWTileBytes + x_tile_bytes;
+            while (sched.next(t)) {
+                const uint32_t x_row = t.x_row + cta_rank * load_m;
+                for (uint32_t kb = 0; kb < num_kb; ++kb, advance()) {
+                    mbar_wait(empty_bar + stage, phase ^ 1);
+                    const bool load_sfw = kb % p.kb_per_sf_w == 0;
+                    const bool load_sfx = kb % p.kb_per_sf_x == 0;
+                    const uint32_t bytes = ab_bytes + (load_sfw ? kBlockN * 4 : 0) + (load_sfx ? p.block_m * 4 : 0);
+                    mbar_arrive_expect_tx(full_bar + stage, bytes);
+                    // weights are streamed once per m-block; tokens are re-read by every n-unit
+                    tma_load_2d(&map_w, full_bar + stage, smem_w + stage * kWTileBytes, kb * kBlockK, t.w_row, kEvictNormal);
+                    tma_load_2d(&map_x, full_bar + stage, smem_x + stage * x_tile_bytes, kb * kBlockK, x_row, kEvictNormal);
+                    if (load_sfw)
+                        tma_load_2d(&map_sfw, full_bar + stage, smem_sfw + stage * 512, t.sfw_col,
+                                    t.sfw_row + kb / p.kb_per_sf_w, kEvictNormal);
+                    if (load_sfx)
+                        tma_load_2d(&map_sfx, full_bar + stage, smem_sfx + stage * sfx_bytes, t.sfx_col,
+                                    t.sfx_row + kb / p.kb_per_sf_x, kEvictNormal);
+                }
+            }
+        }
+    } else if (warp_idx == 1) {
+        // =================================================================== MMA issuer (leader CTA only)
+        if (is_leader) {
+            Scheduler<kGemmType, kCluster> sched(p, cta_rank);
+            Tile t;
+            const uint32_t idesc_base = make_idesc(128 * kCluster, p.block_m, 0, 0);
+            const uint64_t w_desc0 = make_smem_desc(smem_u32(smem_w), 0, 1024, kLayoutSwizzle128B);
+            const uint64_t x_desc0 = make_smem_desc(smem_u32(smem_x), 0, 1024, kLayoutSwizzle128B);
+            const uint64_t sfw_desc0 = make_smem_desc(smem_u32(smem_sfw), 0, 128, kLayoutNoSwizzle);
+            const uint64_t sfx_desc0 = make_smem_desc(smem_u32(smem_sfx), 0, 128, kLayoutNoSwizzle);
+            uint32_t tile_iter = 0;
+            while (sched.next(t)) {
+                const uint32_t as = tile_iter & 1, aphase = (tile_iter >> 1) & 1;
+                ++tile_iter;
+                mbar_wait_cluster(tmem_empty_bar + as, aphase ^ 1);
+                tcgen05_fence_after();
+                const uint32_t tmem_d = tmem_base + as * kAccumColStride;
+                for (uint32_t kb = 0; kb < num_kb; ++kb, advance()) {
+                    mbar_wait_cluster(ready_bar + stage, phase);
+                    tcgen05_fence_after();
+                    if (elect_one()) {
+                        const uint32_t sfw_sub = kb % p.kb_per_sf_w, sfx_sub = kb % p.kb_per_sf_x;
+                        if (sfw_sub == 0)
+                            tmem_cp_sf<kCluster>(tmem_base + kTmemColSFW, sfw_desc0 + ((stage * 512) >> 4));
+                        if (sfx_sub == 0)
+                            for (uint32_t i = 0; i < num_sfx_groups; ++i)
+                                tmem_cp_sf<kCluster>(tmem_base + kTmemColSFX + i * 4,
+                                                     sfx_desc0 + ((stage * sfx_bytes + i * 512) >> 4));
+                        const uint64_t w_desc = w_desc0 + ((stage * kWTileBytes) >> 4);
+                        const uint64_t x_desc = x_desc0 + ((stage * x_tile_bytes) >> 4);
+#pragma unroll
+                        for (uint32_t j = 0; j < kBlockK / kUmmaK; ++j) {
+                            // one UE8M0 byte per 32 K-elements: byte id inside the packed word
+                            const uint32_t w_id = p.kb_per_sf_w == 1 ? j : sfw_sub;
+                            const uint32_t x_id = p.kb_per_sf_x == 1 ? j : sfx_sub;
+                            mma_mxf8_block_scale<kCluster>(tmem_d, w_desc + j * (kUmmaK >> 4), x_desc + j * (kUmmaK >> 4),
+                                                           idesc_with_sf_ids(idesc_base, w_id, x_id),
+                                                           tmem_base + kTmemColSFW, tmem_base + kTmemColSFX,
+                                                           (kb | j) != 0 ? 1u : 0u);
+                        }
+                        // retire -> the smem stage may be overwritten (signals every CTA of the pair)
+                        mma_commit<kCluster>(empty_bar + stage);
+                        if (kb + 1 == num_kb) mma_commit<kCluster>(tmem_full_bar + as);
+                    }
+                    __syncwarp();
+                }
+            }
+            // Drain: nobody may tear the CTA pair down while epilogue threads of the peer still arrive here
+            if (tile_iter > 0) {
+                const uint32_t last = tile_iter - 1;
+                mbar_wait_cluster(tmem_empty_bar + (last & 1), (last >> 1) & 1);
+            }
+        }
+    } else if (warp_idx == 2) {
+        // =================================================================== SF re-tiler / stage forwarder
+        Scheduler<kGemmType, kCluster> sched(p, cta_rank);
+        Tile t;
+        // tcgen05.cp 32x128b wants word (row r of the 128-group) at [r % 32][r / 32]; TMA delivered it at [r]
+        auto retile = [&](uint8_t* base) {
+            uint32_t* w = reinterpret_cast<uint32_t*>(base);
+            const uint32_t v0 = ld_shared_u32(w + lane), v1 = ld_shared_u32(w + 32 + lane),
+                           v2 = ld_shared_u32(w + 64 + lane), v3 = ld_shared_u32(w + 96 + lane);
+            __syncwarp();
+            st_shared_v4(w + lane * 4, v0, v1, v2, v3);
+        };
+        while (sched.next(t)) {
+            for (uint32_t kb = 0; kb < num_kb; ++kb, advance()) {
+                mbar_wait(full_bar + stage, phase);
+                bool touched = false;
+                if (kb % p.kb_per_sf_w == 0) retile(smem_sfw + stage * 512), touched = true;
+                if (kb % p.kb_per_sf_x == 0) {
+                    for (uint32_t i = 0; i < num_sfx_groups; ++i) retile(smem_sfx + stage * sfx_bytes + i * 512);
+                    touched = true;
+                }
+                if (touched) fence_proxy_async_smem();   // generic-proxy writes -> visible to tcgen05.cp
+                if constexpr (kCluster > 1)
+                    mbar_arrive_cluster(ready_bar + stage, 0);
+                else
+                    mbar_arrive(ready_bar + stage);
+            }
+        }
+    } else if (warp_idx >= 4) {
+        // =================================================================== epilogue: TMEM -> registers -> global
+        Scheduler<kGemmType, kCluster> sched(p, cta_rank);
+        Tile t;
+        const uint32_t quad = warp_idx & 3;                 // TMEM lane quadrant this warp may read
+        out_t* d = reinterpret_cast<out_t*>(p.d);
+        uint32_t tile_iter = 0;
+        while (sched.next(t)) {
+            const uint32_t as = tile_iter & 1, aphase = (tile_iter >> 1) & 1;
+            ++tile_iter;
+            mbar_wait(tmem_full_bar + as, aphase);
+            tcgen05_fence_after();
+            const uint32_t taddr = tmem_base + ((quad * 32) << 16) + as * kAccumColStride;
+            const uint32_t n = t.n0 + quad * 32 + lane;
+            const bool n_ok = n < p.n;
+            out_t* d_col = d + static_cast<size_t>(t.d_row) * p.ld_d + n;
+            const uint32_t load_cols = (max(t.valid_m, 1u) + 15) / 16 * 16;
+            for (uint32_t c0 = 0; c0 < load_cols; c0 += 16) {
+                uint32_t v[16];
+                tmem_ld_32x32b_x16(taddr + c0, v);
+                tmem_ld_wait();
+#pragma unroll
+                for (uint32_t j = 0; j < 16; ++j) {
+                    const uint32_t r = c0 + j;
+                    if (r < t.valid_m && n_ok)
+                        store_out<out_t>(d_col + static_cast<size_t>(r) * p.ld_d, __uint_as_float(v[j]), kAccumulate);
+                }
+            }
+            // accumulator buffer may be overwritten by the tile after next
+            tcgen05_fence_before();
+            if constexpr (kCluster > 1)
+                mbar_arrive_cluster(tmem_empty_bar + as, 0);
+            else
+                mbar_arrive(tmem_empty_bar + as);
+            // psum layout with zero padding: rows between the group's end and its aligned end are defined to be 0
+            if (n_ok)
+                for (uint32_t r = t.valid_m; r < t.store_m; ++r)
+                    store_out<out_t>(d_col + static_cast<size_t>(r) * p.ld_d, 0.0f, false);
+        }
+    }
+
+    // ---- teardown
+    tcgen05_fence_before();
+    if constexpr (kCluster > 1) {
+        cluster_arrive();
+        cluster_wait();
+    } else {
+        __syncthreads();
+    }
+    if (warp_idx == 2) tmem_dealloc<kCluster>(tmem_base, kTmemCols);
+#endif
+}
+
+}  // namespace dgb200

@@ -1,0 +1,212 @@
+"""Python face of the FP8 GEMM path -- same names, argument meaning and error behaviour as the reference's
+``deep_gemm`` module (csrc/apis/gemm.hpp:73-400, signatures registered at :649-717).
+
+Every function validates like the reference (RuntimeError on violation), converts scale factors to the packed
+UE8M0 wire format when FP32 ones are given, and forwards raw device pointers to the C ABI (include/dgb200.h) on the
+current torch CUDA stream. Nothing here computes: without the CUDA library the call fails.
+"""
+from typing import List, Optional, Tuple
+
+import torch
+
+from . import layout as _layout
+from ._lib import check, lib
+from .runtime import get_mk_alignment_for_contiguous_layout
+
+_K_MAJOR, _MN_MAJOR = 0, 1
+_BF16, _FP32 = 0, 1
+
+TensorPair = Tuple[torch.Tensor, torch.Tensor]
+
+
+def _require(cond: bool, what: str) -> None:
+    if not cond:
+        raise RuntimeError(f'Assertion error (deepgemm_b200/gemm.py): {what}')
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _major_check(t: torch.Tensor) -> None:
+    """csrc/utils/layout.hpp:13-19."""
+    _require(t.dim() in (2, 3), 'dim == 2 or dim == 3')
+    if t.dim() == 3:
+        _require(t.stride(0) == t.size(-2) * t.size(-1), 't.stride(0) == t.size(-2) * t.size(-1)')
+    _require(t.stride(-2) == 1 or t.stride(-1) == 1, 't.stride(-2) == 1 or t.stride(-1) == 1')
+
+
+def _major_ab(t: torch.Tensor) -> int:
+    _major_check(t)
+    return _K_MAJOR if t.stride(-1) == 1 else _MN_MAJOR
+
+
+def _check_cd(t: torch.Tensor) -> None:
+    _major_check(t)
+    _require(t.stride(-1) == 1, 'C/D must be row-major (stride(-1) == 1)')
+
+
+def _check_fp8(t: torch.Tensor) -> None:
+    if t.dtype != torch.float8_e4m3fn:
+        if t.dtype == torch.int8:
+            raise RuntimeError('FP4 (int8-packed) operands are outside this library\'s FP8xFP8 scope')
+        raise RuntimeError(f'Assertion error (deepgemm_b200/gemm.py): operand dtype must be torch.float8_e4m3fn, got {t.dtype}')
+
+
+def _d_dtype(d: torch.Tensor) -> int:
+    _require(d.dtype in (torch.bfloat16, torch.float32), 'd.dtype is bfloat16 or float')
+    return _BF16 if d.dtype == torch.bfloat16 else _FP32
+
+
+def _early_return(m: int, n: int, k: int, d: torch.Tensor, c: Optional[torch.Tensor]) -> bool:
+    """csrc/apis/gemm.hpp:19-46."""
+    if m == 0 or n == 0:
+        return True
+    same = c is not None and c.data_ptr() == d.data_ptr()
+    if same:
+        _require(c.shape == d.shape and c.stride() == d.stride(), 'c and d alias with different layouts')
+    _d_dtype(d)
+    if c is not None:
+        _check_cd(c)
+        _require(d.dtype == c.dtype, 'd.dtype == c.dtype')
+    if k == 0:
+        if not same:
+            d.copy_(c) if c is not None else d.zero_()
+        return True
+    if c is not None and not same:
+        d.copy_(c)
+    return False
+
+
+# ------------------------------------------------------------------------------------------------ dense
+def fp8_gemm_nt(a: TensorPair, b: TensorPair, d: torch.Tensor, c: Optional[torch.Tensor] = None,
+                recipe: Optional[Tuple[int, int, int]] = None, recipe_a: Optional[Tuple[int, int]] = None,
+                recipe_b: Optional[Tuple[int, int]] = None, compiled_dims: str = 'nk',
+                disable_ue8m0_cast: bool = False) -> None:
+    """D = (C +) A @ B.T with A [M,K], B [N,K] FP8 E4M3 and per-(1 x gran_k | 128 x 128) scale factors.
+    Reference: fp8_fp4_gemm_nt, csrc/apis/gemm.hpp:73-124. `compiled_dims` is a JIT hint there; ignored here."""
+    (a_t, sfa), (b_t, sfb) = a, b
+    _check_fp8(a_t), _check_fp8(b_t)
+    major_a, major_b = _major_ab(a_t), _major_ab(b_t)
+    _check_cd(d)
+    _require(a_t.dim() == 2 and b_t.dim() == 2 and d.dim() == 2, 'a, b, d are 2-D')
+    (m, k), (n, k_), (m_, n_) = a_t.shape, b_t.shape, d.shape
+    _require(m == m_ and n == n_ and k == k_, 'm == m_ and n == n_ and k == k_')
+    _d_dtype(d)
+    if _early_return(m, n, k, d, c):
+        return
+    sfa_t, sfb_t, gran_k_a, gran_k_b = _layout.transform_sf_pair_into_required_layout(
+        sfa, sfb, m, n, k, recipe, recipe_a, recipe_b, None, None, disable_ue8m0_cast)
+    _require(sfa_t.dtype == torch.int32 and sfb_t.dtype == torch.int32, 'Unsupported architecture or scaling factor types')
+    lda = a_t.stride(0) if major_a == _K_MAJOR else a_t.stride(1)
+    ldb = b_t.stride(0) if major_b == _K_MAJOR else b_t.stride(1)
+    check(lib().dgb200_fp8_gemm_nt(a_t.data_ptr(), sfa_t.data_ptr(), b_t.data_ptr(), sfb_t.data_ptr(), d.data_ptr(),
+                                   m, n, k, lda, ldb, d.stride(0), major_a, major_b,
+                                   sfa_t.stride(-1), sfb_t.stride(-1), gran_k_a, gran_k_b, _d_dtype(d),
+                                   int(c is not None), _stream()))
+
+
+def _t(pair: TensorPair, d0: int = 0, d1: int = 1) -> TensorPair:
+    return pair[0].transpose(d0, d1), pair[1].transpose(d0, d1)
+
+
+def fp8_gemm_nn(a, b, d, c=None, recipe=None, recipe_a=None, recipe_b=None, compiled_dims='nk', disable_ue8m0_cast=False):
+    """B given as [K,N] (gemm.hpp:126-137)."""
+    fp8_gemm_nt(a, _t(b), d, c, recipe, recipe_a, recipe_b, compiled_dims, disable_ue8m0_cast)
+
+
+def fp8_gemm_tn(a, b, d, c=None, recipe=None, recipe_a=None, recipe_b=None, compiled_dims='mn', disable_ue8m0_cast=False):
+    """A given as [K,M], B as [K,N] (gemm.hpp:139-151)."""
+    fp8_gemm_nt(_t(a), _t(b), d, c, recipe, recipe_a, recipe_b, compiled_dims, disable_ue8m0_cast)
+
+
+def fp8_gemm_tt(a, b, d, c=None, recipe=None, recipe_a=None, recipe_b=None, compiled_dims='mn', disable_ue8m0_cast=False):
+    """A given as [K,M], B as [N,K] (gemm.hpp:153-164)."""
+    fp8_gemm_nt(_t(a), b, d, c, recipe, recipe_a, recipe_b, compiled_dims, disable_ue8m0_cast)
+
+
+# ------------------------------------------------------------------------------------------------ M-grouped
+def m_grouped_fp8_gemm_nt_contiguous(a: TensorPair, b: TensorPair, d: torch.Tensor, grouped_layout: torch.Tensor,
+                                     recipe=None, recipe_a=None, recipe_b=None, compiled_dims: str = 'nk',
+                                     disable_ue8m0_cast: bool = False, use_psum_layout: bool = False,
+                                     ensure_zero_padding: bool = True,
+                                     expected_m_for_psum_layout: Optional[int] = None) -> None:
+    """A [M_sum,K] rows grouped by expert, B [G,N,K], D [M_sum,N] BF16 (gemm.hpp:166-232)."""
+    (a_t, sfa), (b_t, sfb) = a, b
+    _check_fp8(a_t), _check_fp8(b_t)
+    major_a, major_b = _major_ab(a_t), _major_ab(b_t)
+    _require(major_a == _K_MAJOR, 'major_a == K (m-grouped GEMMs need K-major A)')
+    _require(grouped_layout.is_contiguous(), 'grouped_layout.is_contiguous()')
+    _require(a_t.dim() == 2 and b_t.dim() == 3 and d.dim() == 2, 'a 2-D, b 3-D, d 2-D')
+    (m, k), (num_groups, n, k_), (m_, n_) = a_t.shape, b_t.shape, d.shape
+    _require(m == m_ and n == n_ and k == k_, 'm == m_ and n == n_ and k == k_')
+    _require(n > 0 and k > 0 and num_groups > 0, 'n > 0 and k > 0 and num_groups > 0')
+    _require(d.dtype == torch.bfloat16, 'd.dtype == bfloat16')
+    _require(grouped_layout.dtype == torch.int32, 'grouped_layout.dtype == int32')
+    if use_psum_layout:
+        _require(grouped_layout.dim() == 1 and grouped_layout.numel() == num_groups, 'grouped_layout is [num_groups]')
+    else:
+        _require(grouped_layout.dim() == 1 and grouped_layout.numel() == m, 'grouped_layout is [m]')
+        _require(expected_m_for_psum_layout is None, 'expected_m_for_psum_layout needs use_psum_layout')
+    _check_cd(d)
+    if m == 0:
+        return
+    sfa_t, sfb_t, gran_k_a, gran_k_b = _layout.transform_sf_pair_into_required_layout(
+        sfa, sfb, m, n, k, recipe, recipe_a, recipe_b, None, num_groups, disable_ue8m0_cast,
+        grouped_layout if use_psum_layout else None)
+    _require(sfa_t.dtype == torch.int32 and sfb_t.dtype == torch.int32, 'Unsupported architecture or scaling factor types')
+    ldb = b_t.stride(1) if major_b == _K_MAJOR else b_t.stride(2)
+    check(lib().dgb200_m_grouped_fp8_gemm_nt_contiguous(
+        a_t.data_ptr(), sfa_t.data_ptr(), b_t.data_ptr(), sfb_t.data_ptr(), d.data_ptr(), grouped_layout.data_ptr(),
+        num_groups, m, n, k, a_t.stride(0), ldb, d.stride(0), major_b, sfa_t.stride(-1), sfb_t.stride(-1),
+        gran_k_a, gran_k_b, int(use_psum_layout), int(ensure_zero_padding),
+        -1 if expected_m_for_psum_layout is None else int(expected_m_for_psum_layout), _stream()))
+
+
+def m_grouped_fp8_gemm_nn_contiguous(a, b, d, grouped_layout, recipe=None, recipe_a=None, recipe_b=None,
+                                     compiled_dims='nk', disable_ue8m0_cast=False, use_psum_layout=False,
+                                     ensure_zero_padding=True) -> None:
+    """B given as [G,K,N] (gemm.hpp:234-248)."""
+    m_grouped_fp8_gemm_nt_contiguous(a, _t(b, 1, 2), d, grouped_layout, recipe, recipe_a, recipe_b, compiled_dims,
+                                     disable_ue8m0_cast, use_psum_layout, ensure_zero_padding, None)
+
+
+def m_grouped_fp8_gemm_nt_masked(a: TensorPair, b: TensorPair, d: torch.Tensor, masked_m: torch.Tensor,
+                                 expected_m: int, recipe=None, recipe_a=None, recipe_b=None,
+                                 compiled_dims: str = 'nk', disable_ue8m0_cast: bool = False) -> None:
+    """A [G,M_max,K], B [G,N,K], D [G,M_max,N] BF16; rows >= masked_m[g] are ignored. `masked_m` stays on the device
+    (CUDA-graph safe). Reference: gemm.hpp:250-297."""
+    (a_t, sfa), (b_t, sfb) = a, b
+    _check_fp8(a_t), _check_fp8(b_t)
+    _require(_major_ab(a_t) == _K_MAJOR and _major_ab(b_t) == _K_MAJOR, 'major_a == K and major_b == K')
+    _require(masked_m.is_contiguous(), 'masked_m.is_contiguous()')
+    _require(a_t.dim() == 3 and b_t.dim() == 3 and d.dim() == 3, 'a, b, d are 3-D')
+    (g, m, k), (g_, n, k_), (g__, m_, n_) = a_t.shape, b_t.shape, d.shape
+    _require(g == g_ == g__ == masked_m.numel(), 'group counts agree')
+    _require(m == m_ and n == n_ and k == k_, 'm == m_ and n == n_ and k == k_')
+    _require(expected_m > 0 and m > 0 and n > 0 and k > 0 and g > 0, 'positive sizes')
+    _require(d.dtype == torch.bfloat16, 'd.dtype == bfloat16')
+    _require(masked_m.dtype == torch.int32, 'masked_m.dtype == int32')
+    _check_cd(d)
+    _require(d.stride(1) == n, 'd is densely batched')
+    sfa_t, sfb_t, gran_k_a, gran_k_b = _layout.transform_sf_pair_into_required_layout(
+        sfa, sfb, m, n, k, recipe, recipe_a, recipe_b, g, g, disable_ue8m0_cast)
+    _require(sfa_t.dtype == torch.int32 and sfb_t.dtype == torch.int32, 'Unsupported architecture or scaling factor types')
+    check(lib().dgb200_m_grouped_fp8_gemm_nt_masked(
+        a_t.data_ptr(), sfa_t.data_ptr(), b_t.data_ptr(), sfb_t.data_ptr(), d.data_ptr(), masked_m.data_ptr(),
+        g, m, n, k, int(expected_m), sfa_t.stride(-1), sfb_t.stride(-1), gran_k_a, gran_k_b, _stream()))
+
+
+# ------------------------------------------------------------------------------------------------ K-grouped
+def k_grouped_fp8_gemm_tn_contiguous(a: TensorPair, b: TensorPair, d: torch.Tensor, ks_cpu: Optional[List[int]],
+                                     grouped_layout: torch.Tensor, c: Optional[torch.Tensor] = None,
+                                     recipe: Tuple[int, int, int] = (1, 1, 128), compiled_dims: str = 'mn',
+                                     use_psum_layout: bool = False) -> None:
+    """Weight gradient D[g] = C[g] + A[k_g,:M].T @ B[k_g,:N] (gemm.hpp:299-346)."""
+    raise RuntimeError('k_grouped_fp8_gemm_tn_contiguous is not built yet (deepgemm_b200)')
+
+
+def k_grouped_fp8_gemm_nt_contiguous(a, b, d, ks_cpu, grouped_layout, c=None, recipe=(1, 1, 128), compiled_dims='mn',
+                                     use_psum_layout=False) -> None:
+    """SM90-only in the reference (gemm.hpp:393-399 -> 'Unsupported architecture' on SM100)."""
+    raise RuntimeError('Unsupported architecture')

@@ -1,0 +1,146 @@
+"""Scale-factor layout API (reference: csrc/apis/layout.hpp:14-122, csrc/jit_kernels/impls/smxx_layout.hpp:120-353).
+
+The GEMM kernel consumes one wire format only -- the reference's SM100 format: UE8M0 exponent bytes, four consecutive
+K granules packed into one int32, MN-major with the MN extent padded to 16 bytes:
+``shape [.., mn, ceil(sf_k/4)]``, ``strides (.., 1, align(mn, 4))``.
+"""
+from typing import Optional, Sequence, Tuple, Union
+
+import torch
+
+from ._lib import check, lib
+from .runtime import get_mk_alignment_for_contiguous_layout, get_tma_aligned_size
+
+
+def _require(cond: bool, what: str) -> None:
+    if not cond:
+        raise RuntimeError(f'Assertion error (deepgemm_b200/layout.py): {what}')
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ceil_div(a: int, b: int) -> int:
+    return -(-a // b)
+
+
+def _empty_mn_major(num_batches: int, mn: int, cols: int, dtype, device) -> torch.Tensor:
+    aligned_mn = get_tma_aligned_size(mn, 4)
+    return torch.empty_strided((num_batches, mn, cols), (cols * aligned_mn, 1, aligned_mn), dtype=dtype, device=device)
+
+
+def get_mn_major_tma_aligned_tensor(sf: torch.Tensor) -> torch.Tensor:
+    """FP32 SFs -> MN-major, TMA-aligned FP32 (smxx_layout.hpp:120-153). Exported utility; the SM100 GEMM path does
+    not consume FP32 scale factors (csrc/apis/gemm.hpp:118-122)."""
+    _require(sf.dim() in (2, 3) and sf.dtype == torch.float32, 'sf must be a 2-D/3-D float tensor')
+    batched = sf.unsqueeze(0) if sf.dim() == 2 else sf
+    b, mn, sf_k = batched.shape
+    aligned_mn = get_tma_aligned_size(mn, 4)
+    if (batched.stride(0) == aligned_mn * sf_k or sf.dim() == 2) and batched.stride(1) == 1 and batched.stride(2) == aligned_mn:
+        return sf
+    out = _empty_mn_major(b, mn, sf_k, torch.float32, sf.device)
+    check(lib().dgb200_transpose_sf_fp32(batched.data_ptr(), out.data_ptr(), mn, sf_k, b, batched.stride(0),
+                                         batched.stride(1), batched.stride(2), _stream()))
+    return out.squeeze(0) if sf.dim() == 2 else out
+
+
+def _pack(sf: torch.Tensor, mn: int, gran_mn: int, psum_layout: Optional[torch.Tensor]) -> torch.Tensor:
+    """Shared body: FP32 [.., ceil(mn/gran_mn), sf_k] (any strides) -> packed [.., mn, ceil(sf_k/4)]."""
+    batched = sf.unsqueeze(0) if sf.dim() == 2 else sf
+    b, rows, sf_k = batched.shape
+    _require(rows == _ceil_div(mn, gran_mn), 'sf.size(-2) == ceil_div(mn, gran_mn)')
+    out = _empty_mn_major(b, mn, _ceil_div(sf_k, 4), torch.int32, sf.device)
+    if psum_layout is not None:
+        _require(b == 1 and batched.is_contiguous(), 'psum layout needs one contiguous SF batch')
+        _require(psum_layout.dtype == torch.int32 and psum_layout.is_contiguous() and psum_layout.numel() > 0,
+                 'psum_layout must be a non-empty contiguous int tensor')
+        check(lib().dgb200_pack_sf_ue8m0(batched.data_ptr(), out.data_ptr(), mn, sf_k, b, gran_mn, batched.stride(0),
+                                         batched.stride(1), batched.stride(2), psum_layout.data_ptr(),
+                                         psum_layout.numel(), get_mk_alignment_for_contiguous_layout(), _stream()))
+    else:
+        check(lib().dgb200_pack_sf_ue8m0(batched.data_ptr(), out.data_ptr(), mn, sf_k, b, gran_mn, batched.stride(0),
+                                         batched.stride(1), batched.stride(2), None, 0, 1, _stream()))
+    return out.squeeze(0) if sf.dim() == 2 else out
+
+
+def get_mn_major_tma_aligned_packed_ue8m0_tensor(sf: torch.Tensor, psum_layout: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """FP32 power-of-two SFs [.., mn, sf_k] -> packed UE8M0 int32 [.., mn, ceil(sf_k/4)], strides (.., 1, align(mn,4))
+    (smxx_layout.hpp:180-253; bit-exact contract pinned by the reference's tests/test_layout.py:20-42)."""
+    _require(sf.dim() in (2, 3) and sf.dtype == torch.float32, 'sf must be a 2-D/3-D float tensor')
+    return _pack(sf, sf.size(-2), 1, psum_layout)
+
+
+def get_k_grouped_mn_major_tma_aligned_packed_ue8m0_tensor(sf: torch.Tensor, grouped_layout: torch.Tensor,
+                                                           ks_cpu: Optional[Sequence[int]], gran_k: int, k_alignment: int,
+                                                           use_psum_layout: bool = False) -> torch.Tensor:
+    raise RuntimeError('k-grouped SF packing is not built yet (deepgemm_b200)')
+
+
+def check_sf_layout(sf: torch.Tensor, mn: int, k: int, gran_mn: int, gran_k: int, num_groups: Optional[int],
+                    tma_stride_check: bool = False, type_check: Optional[torch.dtype] = None) -> torch.Tensor:
+    """csrc/utils/layout.hpp:80-117."""
+    if type_check is not None:
+        _require(sf.dtype == type_check, f'sf.dtype == {type_check}')
+    _require(sf.dtype in (torch.float32, torch.int32), 'sf must be float or int')
+    _require(sf.dim() == (3 if num_groups is not None else 2), 'sf.dim() == num_groups.has_value() + 2')
+    if num_groups is not None:
+        _require(sf.size(-3) == num_groups, 'sf.size(-3) == num_groups')
+    _require(sf.size(-2) == _ceil_div(mn, gran_mn), 'sf.size(-2) == ceil_div(mn, gran_mn)')
+    _require(sf.size(-1) == _ceil_div(k, gran_k * (1 if sf.dtype == torch.float32 else 4)),
+             'sf.size(-1) == ceil_div(k, gran_k * (1 or 4))')
+    if tma_stride_check:
+        if num_groups is not None:
+            _require(sf.stride(-3) == sf.stride(-1) * sf.size(-1), 'sf.stride(-3) == sf.stride(-1) * sf.size(-1)')
+        _require(sf.stride(-2) == 1 or mn == 1, 'sf must be MN-major')
+        _require(sf.stride(-1) == get_tma_aligned_size(mn, sf.element_size()), 'sf.stride(-1) == tma_aligned(mn)')
+    return sf
+
+
+Recipe = Union[Tuple[int, int, int], Tuple[int, int]]
+
+
+def transform_sf_into_required_layout(sf: torch.Tensor, mn: int, k: int, recipe: Recipe,
+                                      num_groups: Optional[int] = None, is_sfa: Optional[bool] = None,
+                                      disable_ue8m0_cast: bool = False,
+                                      psum_layout: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """csrc/apis/layout.hpp:14-61, SM100 branch only (this library is sm_100a-only)."""
+    recipe = tuple(recipe)
+    if len(recipe) == 3:
+        _require(is_sfa is not None, 'is_sfa must be given with a 3-tuple recipe')
+        gran_mn, gran_k = (recipe[0] if is_sfa else recipe[1]), recipe[2]
+    else:
+        _require(len(recipe) == 2 and is_sfa is None, 'invalid recipe')
+        gran_mn, gran_k = recipe
+    check_sf_layout(sf, mn, k, gran_mn, gran_k, num_groups)
+
+    if sf.dtype == torch.float32 and gran_k in (32, 128):
+        # The SM100 kernel needs power-of-two scales (hardware block scaling); the reference asserts the same
+        # (layout.hpp:49-50) and leaves `disable_ue8m0_cast=True` without an SM100 kernel (gemm.hpp:118-122).
+        _require(not disable_ue8m0_cast, 'not disable_ue8m0_cast (FP32 scale factors are cast to UE8M0 on SM100)')
+        return _pack(sf, mn, gran_mn, psum_layout)
+    if sf.dtype == torch.int32 and gran_mn == 1 and gran_k in (32, 128):
+        return check_sf_layout(sf, mn, k, gran_mn, gran_k, num_groups, tma_stride_check=True, type_check=torch.int32)
+    raise RuntimeError('Unknown SF transformation')
+
+
+def get_default_recipe(sfa_dtype: torch.dtype, sfb_dtype: torch.dtype) -> Tuple[int, int, int]:
+    """csrc/utils/layout.hpp:64-77 (arch 10 branch)."""
+    _require(sfb_dtype in (torch.float32, torch.int32), 'sfb must be float or int')
+    return (1, 128, 128) if sfb_dtype == torch.float32 else (1, 1, 128)
+
+
+def transform_sf_pair_into_required_layout(sfa, sfb, m, n, k, recipe, recipe_a, recipe_b, num_groups_a, num_groups_b,
+                                           disable_ue8m0_cast=False, psum_layout=None):
+    """csrc/apis/layout.hpp:63-90. Returns (sfa, sfb, gran_k_a, gran_k_b)."""
+    if recipe_a is None and recipe is None:
+        recipe = get_default_recipe(sfa.dtype, sfb.dtype)
+    _require((recipe_a is None) == (recipe_b is None), 'recipe_a and recipe_b come as a pair')
+    _require((recipe_a is None) != (recipe is None), "either 'recipe' or the 'recipe_a' + 'recipe_b' pair")
+    if recipe is not None:
+        tsfa = transform_sf_into_required_layout(sfa, m, k, recipe, num_groups_a, True, disable_ue8m0_cast, psum_layout)
+        tsfb = transform_sf_into_required_layout(sfb, n, k, recipe, num_groups_b, False, disable_ue8m0_cast)
+        return tsfa, tsfb, recipe[2], recipe[2]
+    tsfa = transform_sf_into_required_layout(sfa, m, k, recipe_a, num_groups_a, None, disable_ue8m0_cast, psum_layout)
+    tsfb = transform_sf_into_required_layout(sfb, n, k, recipe_b, num_groups_b, None, disable_ue8m0_cast)
+    return tsfa, tsfb, recipe_a[1], recipe_b[1]

@@ -1,0 +1,135 @@
+/*
+ * dgb200 -- C ABI of the B200-native FP8 blockwise-scaled GEMM library.
+ *
+ * This is the drop-in boundary for the FP8 GEMM hot path of deepseek-ai/DeepGEMM. The reference has no C ABI:
+ * its boundary is the pybind11 module `deep_gemm._C` (csrc/python_api.cpp:17-28) whose functions take
+ * torch.Tensors. Every entry point below is the torch-free core of one of those functions; the comment on each
+ * names the reference function it replaces (file:line in the reference tree). `deepgemm_b200/` binds them with
+ * ctypes; INTEGRATION.md shows the pybind/ctypes stub a reference maintainer would add.
+ *
+ * Conventions
+ *   - all data pointers are DEVICE pointers unless the name ends in `_host`; sizes are element counts
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream); all work is enqueued, nothing syncs
+ *   - A ("tokens", M side) and B ("weights", N side) are FP8 E4M3; D is BF16 (DGB200_BF16) or FP32 (DGB200_FP32)
+ *   - scale factors are the reference's SM100 wire format: UE8M0 bytes, 4 consecutive K-granules packed in one
+ *     int32, MN-major (element (mn, kp) at  sf[kp * sf_stride + mn],  sf_stride >= align(mn, 4);
+ *     batched/grouped: group g starts at  g * num_kp * sf_stride)   (csrc/utils/layout.hpp:100-107)
+ *   - return value: 0 on success, otherwise a DGB200_ERR_* code; dgb200_last_error() gives the message
+ *     (the reference throws DGException -> Python RuntimeError, csrc/utils/exception.hpp:12-40)
+ *   - no function reads device memory on the host: every call is CUDA-graph capturable
+ */
+#ifndef DGB200_H_
+#define DGB200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DGB200_VERSION 100
+
+enum { DGB200_BF16 = 0, DGB200_FP32 = 1 };
+enum { DGB200_K_MAJOR = 0, DGB200_MN_MAJOR = 1 };
+enum {
+    DGB200_OK = 0,
+    DGB200_ERR_INVALID_ARGUMENT = 1, /* host-side contract violation (DG_HOST_ASSERT in the reference) */
+    DGB200_ERR_CUDA = 2,             /* CUDA runtime / driver failure */
+    DGB200_ERR_UNSUPPORTED = 3       /* valid in the reference, not built here (FP4 operands, SM90-only paths) */
+};
+
+/* Message of the last failing call on this thread. */
+const char* dgb200_last_error(void);
+int dgb200_version(void);
+
+/* ---- runtime knobs: csrc/apis/runtime.hpp:11-49, csrc/apis/layout.hpp:142-150 --------------------------- */
+int dgb200_set_num_sms(int num_sms);      /* must be even and <= device SM count (heuristics/config.hpp:47) */
+int dgb200_get_num_sms(void);             /* 0 until a device is first used, then the value in effect */
+int dgb200_set_tc_util(int percent);      /* accepted for API parity; only the reference's BF16 kernel consumes it */
+int dgb200_get_tc_util(void);
+int dgb200_set_pdl(int enabled);          /* programmatic dependent launch attribute on every kernel launch */
+int dgb200_get_pdl(void);
+int dgb200_set_mk_alignment_for_contiguous_layout(int alignment);
+int dgb200_get_mk_alignment_for_contiguous_layout(void);
+int dgb200_get_theoretical_mk_alignment_for_contiguous_layout(int expected_m /* <=0: none */);
+int dgb200_get_tma_aligned_size(int x, int element_size);  /* csrc/utils/math.hpp:23-27 */
+
+/* ---- scale-factor layout transforms: csrc/jit_kernels/impls/smxx_layout.hpp:120-316 ------------------------ */
+
+/* FP32 power-of-two scale factors -> packed UE8M0 int32, MN-major, TMA aligned.
+ * Replaces get_mn_major_tma_aligned_packed_ue8m0_tensor (smxx_layout.hpp:180-253) fused with the
+ * `index_select` row broadcast of csrc/apis/layout.hpp:48-54 (gran_mn = 128 means one input row per 128 outputs).
+ *   sf        : fp32 [num_groups, ceil(mn/gran_mn), sf_k] with element strides (stride_g, stride_mn, stride_k)
+ *   out       : int32, num_groups * ceil(sf_k/4) * align(mn,4) words
+ *   psum_layout: optional int32[num_psum_groups] end rows; rows in alignment gaps are written as 0 (safe, finite)
+ * Scale factors that are not exact powers of two trap on the device, as in the reference (smxx_layout.cuh:131). */
+int dgb200_pack_sf_ue8m0(const float* sf, int32_t* out, int mn, int sf_k, int num_groups, int gran_mn,
+                         int64_t stride_g, int64_t stride_mn, int64_t stride_k,
+                         const int32_t* psum_layout, int num_psum_groups, int m_alignment, void* stream);
+
+/* FP32 scale factors -> FP32 MN-major TMA-aligned copy (get_mn_major_tma_aligned_tensor, smxx_layout.hpp:120-178).
+ *   out: fp32, num_groups * sf_k * align(mn,4) elements, element (g, mn, k) at out[(g*sf_k + k)*align(mn,4) + mn] */
+int dgb200_transpose_sf_fp32(const float* sf, float* out, int mn, int sf_k, int num_groups,
+                             int64_t stride_g, int64_t stride_mn, int64_t stride_k, void* stream);
+
+/* K-grouped variant (get_k_grouped_mn_major_tma_aligned_packed_ue8m0_tensor, smxx_layout.hpp:255-316):
+ *   sf  : fp32 [sum_g ceil(k_g/gran_k), mn] contiguous;  out: int32 [sum_g ceil(k_g/(4*gran_k)), mn] contiguous.
+ *   ks_host: per-group K (host array, as the reference's `ks_cpu`). */
+int dgb200_pack_sf_ue8m0_k_grouped(const float* sf, int32_t* out, int mn, const int32_t* ks_host, int num_groups,
+                                   int gran_k, void* stream);
+
+/* ---- GEMMs ------------------------------------------------------------------------------------------------ */
+
+/* D[m,n] (= C +) sum_k A[m,k] B[n,k]          -- fp8_fp4_gemm_nt, csrc/apis/gemm.hpp:73-124 (+ nn/tn/tt :126-164
+ * through the major flags: K_MAJOR means the K extent is contiguous, lda/ldb are the strides of the other extent).
+ * accumulate != 0: D holds C on entry (the host wrapper copies C into D first, gemm.hpp:42-44). */
+int dgb200_fp8_gemm_nt(const void* a, const int32_t* sfa, const void* b, const int32_t* sfb, void* d,
+                       int m, int n, int k, int64_t lda, int64_t ldb, int64_t ldd,
+                       int major_a, int major_b, int sfa_stride, int sfb_stride, int gran_k_a, int gran_k_b,
+                       int d_dtype, int accumulate, void* stream);
+
+/* Rows of A grouped by expert          -- m_grouped_fp8_fp4_gemm_nt_contiguous, csrc/apis/gemm.hpp:166-232.
+ *   a [m, k], b [num_groups, n, k], d [m, n] bf16
+ *   use_psum_layout == 0: grouped_layout int32[m], expert id per row, -1 for padding rows
+ *   use_psum_layout != 0: grouped_layout int32[num_groups], (unaligned) end row of each expert; expert g+1 starts
+ *                         at align(end_g, mk_alignment); ensure_zero_padding writes zeros to the gap rows of D */
+int dgb200_m_grouped_fp8_gemm_nt_contiguous(const void* a, const int32_t* sfa, const void* b, const int32_t* sfb,
+                                            void* d, const int32_t* grouped_layout, int num_groups,
+                                            int m, int n, int k, int64_t lda, int64_t ldb, int64_t ldd, int major_b,
+                                            int sfa_stride, int sfb_stride, int gran_k_a, int gran_k_b,
+                                            int use_psum_layout, int ensure_zero_padding,
+                                            int expected_m_for_psum_layout, void* stream);
+
+/* Per-expert fixed slots, device-side counts   -- m_grouped_fp8_fp4_gemm_nt_masked, csrc/apis/gemm.hpp:250-297.
+ *   a [num_groups, m_max, k], b [num_groups, n, k], d [num_groups, m_max, n] bf16, masked_m int32[num_groups]
+ *   (device; never read by the host). Only rows < masked_m[g] of each group are written. */
+int dgb200_m_grouped_fp8_gemm_nt_masked(const void* a, const int32_t* sfa, const void* b, const int32_t* sfb,
+                                        void* d, const int32_t* masked_m, int num_groups,
+                                        int m_max, int n, int k, int expected_m,
+                                        int sfa_stride, int sfb_stride, int gran_k_a, int gran_k_b, void* stream);
+
+/* Weight gradient, K grouped           -- k_grouped_fp8_gemm_tn_contiguous, csrc/apis/gemm.hpp:299-346.
+ *   a [sum_k, m], b [sum_k, n] (both MN-major), d [num_groups, m, n] fp32 accumulated in place (D holds C),
+ *   ks_host int32[num_groups] per-group K (multiples of the mk alignment), sfa/sfb k-grouped packed layouts. */
+int dgb200_k_grouped_fp8_gemm_tn_contiguous(const void* a, const int32_t* sfa, const void* b, const int32_t* sfb,
+                                            float* d, const int32_t* ks_host, int num_groups, int m, int n,
+                                            int gran_k, void* stream);
+
+/* ---- introspection (bench / tests) -------------------------------------------------------------------------- */
+typedef struct dgb200_config {
+    int block_m;     /* token rows per tile */
+    int cluster;     /* CTAs per MMA (1 or 2) */
+    int num_stages;  /* TMA->MMA ring depth */
+    int num_sms;     /* grid size */
+    int smem_bytes;  /* dynamic shared memory per CTA */
+    int num_tiles;   /* upper bound on (cluster) tiles */
+} dgb200_config;
+/* Configuration the last GEMM call on this thread used (DG_PRINT_CONFIGS analogue, heuristics/common.hpp:39-50). */
+int dgb200_last_config(dgb200_config* out);
+/* Number of kernels launched by this library since process start (all threads). */
+int64_t dgb200_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DGB200_H_ */
