@@ -63,6 +63,7 @@ SIGNATURES = {
                                                      _I, _I, _I, _I, _I, _P]),
     'dgb200_m_grouped_fp8_gemm_nt_masked': (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
     'dgb200_k_grouped_fp8_gemm_tn_contiguous': (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
+    'dgb200_plan': (_I, [_I, _I, _I, _I, _I, _I, _I, _I, ctypes.POINTER(_Config)]),
     'dgb200_last_config': (_I, [ctypes.POINTER(_Config)]),
     'dgb200_launch_count': (_L, []),
 }
@@ -92,6 +93,13 @@ def last_config() -> dict:
     cfg = _Config()
     check(lib().dgb200_last_config(ctypes.byref(cfg)))
     return {n: getattr(cfg, n) for n, _ in _Config._fields_}
+
+
+def plan(gemm_type: int, m: int, n: int, k: int, num_groups: int = 1, expected_m: int = 0, alignment: int = 1,
+         num_sms: int = 148) -> dict:
+    cfg = _Config()
+    check(lib().dgb200_plan(gemm_type, m, n, k, num_groups, expected_m, alignment, num_sms, ctypes.byref(cfg)))
+    return {n_: getattr(cfg, n_) for n_, _ in _Config._fields_}
 
 
 def launch_count() -> int:

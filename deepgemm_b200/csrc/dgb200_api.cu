@@ -185,38 +185,47 @@ int smem_bytes_for(int block_m, int cluster, int stages) {
     return stages * stage_bytes(block_m, cluster) + (3 * stages + 4) * 8 + 16;
 }
 
-// Estimated cycles for the whole problem with a given tile height. Two resources:
-//   tensor pipe : a K=32 UMMA of a CTA pair costs block_m/2 cycles (1 CTA: block_m/... same per-SM rate),
-//   memory      : every CTA pulls (128 + block_m/cluster) x 128 B per k-block; per-SM ingest is capped, and
-//                 unique bytes are bounded by HBM.
-// The tile order walks all m-blocks of a few weight panels, so weights come from HBM once and tokens hit L2.
+// Estimated cycles for the whole problem with a given tile height. All busy CTAs advance one k-block per "step";
+// a step is bounded by the slowest of four resources (constants are B200 measurements / fits):
+//   tensor pipe : a K=32 UMMA of a CTA pair retires in block_m/2 cycles -> 2*block_m cycles per 128-K block
+//   SM ingest   : one SM pulls at most ~kSmIngest B/cycle through TMA
+//   L2          : all busy CTAs together pull at most ~kL2Rate B/cycle
+//   HBM         : bytes that are new to the chip in this step (weight tiles are shared by the m-blocks in flight,
+//                 token tiles by the n-units in flight) at ~kHbmRate B/cycle
+constexpr double kSmIngest = 56.0, kL2Rate = 8000.0, kHbmRate = 3400.0, kTileOverhead = 1500.0;
+
 double estimate_cycles(const Problem& pb, int block_m, int cluster, int num_sms) {
     const int num_units = num_sms / cluster;
     const int n_units = ceil_div(pb.n, (int)kBlockN * cluster);
     const int num_kb = ceil_div(pb.k, (int)kBlockK);
+    int m_blocks;  // m-blocks that share one weight panel
     double tiles;
-    if (pb.type == kDense)
+    if (pb.type == kMMasked) {
+        m_blocks = ceil_div(std::max(pb.expected_m, 1), block_m);
+        tiles = (double)pb.groups * m_blocks * n_units;
+    } else if (pb.type == kDense) {
+        m_blocks = ceil_div(pb.m, block_m);
+        tiles = (double)m_blocks * n_units;
+    } else {
+        m_blocks = ceil_div(std::max(pb.expected_m, 1), block_m);
         tiles = (double)ceil_div(pb.m, block_m) * n_units;
-    else if (pb.type == kMMasked)
-        tiles = (double)pb.groups * ceil_div(std::max(pb.expected_m, 1), block_m) * n_units;
-    else
-        tiles = (double)ceil_div(pb.m, block_m) * n_units;
+    }
     const double waves = std::ceil(tiles / num_units);
-    const double busy_ctas = std::min<double>(tiles, num_units) * cluster;
-    const double mma_cycles = 4.0 * block_m / 2.0;                               // per k-block
-    const double cta_bytes = (128.0 + (double)block_m / cluster) * kBlockK;      // per k-block per CTA
-    const double sm_ingest = 56.0;                                               // B/cycle one SM can pull from L2
-    const double hbm_rate = 3400.0;                                              // B/cycle chip-wide (6.5 TB/s @ 1.9 GHz)
-    // unique bytes: each weight tile is new; token tiles are shared by the n-units of a wave
-    const double uniq_bytes = 128.0 * kBlockK + (double)block_m / cluster * kBlockK / std::max(1.0, std::min<double>(n_units, num_units));
-    const double mem_cycles = std::max(cta_bytes / sm_ingest, uniq_bytes * busy_ctas / hbm_rate);
-    const double per_tile = num_kb * std::max(mma_cycles, mem_cycles) + 1500.0 + 6.0 * block_m;
-    return waves * per_tile;
+    const double busy_units = std::min<double>(tiles, num_units);
+    const double busy_ctas = busy_units * cluster;
+    const double cta_bytes = (128.0 + (double)block_m / cluster) * kBlockK;
+    const double distinct_n = std::min<double>(n_units, busy_units);
+    const double distinct_m = std::max(1.0, busy_units / distinct_n);
+    const double shared_m = std::min<double>(distinct_m, m_blocks);  // m-blocks in flight that reuse a weight tile
+    const double new_bytes = (busy_ctas * 128.0 / shared_m + distinct_m * block_m) * kBlockK;
+    const double step = std::max(std::max(2.0 * block_m, cta_bytes / kSmIngest),
+                                 std::max(busy_ctas * cta_bytes / kL2Rate, new_bytes / kHbmRate));
+    return waves * (num_kb * step + kTileOverhead + 6.0 * block_m);
 }
 
-Config choose_config(const Problem& pb) {
+Config choose_config(const Problem& pb, int num_sms_override = 0) {
     Config c{};
-    c.num_sms = effective_num_sms();
+    c.num_sms = num_sms_override > 0 ? (num_sms_override & ~1) : effective_num_sms();
     c.cluster = c.num_sms >= 2 ? 2 : 1;
     std::vector<int> candidates;
     if (pb.type == kDense) {
@@ -274,11 +283,16 @@ template <typename Kernel>
 int launch_kernel(Kernel kernel, const Config& cfg, cudaStream_t stream, const CUtensorMap& mx, const CUtensorMap& mw,
                   const CUtensorMap& msfx, const CUtensorMap& msfw, const GemmParams& p) {
     // Opt in to > 48 KB dynamic smem once per instantiation and device
-    static thread_local std::unordered_map<int, int> configured;  // device -> max smem configured
-    int& cur = configured[rt().device];
-    if (cur < cfg.smem_bytes) {
-        DGB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemCapacity));
-        cur = kSmemCapacity;
+    // (all instantiations share one function-pointer type, so the memo is keyed by the kernel address)
+    static std::mutex mu;
+    static std::unordered_map<const void*, int> configured;  // kernel -> device it was configured on
+    {
+        std::lock_guard<std::mutex> lock(mu);
+        auto it = configured.find(reinterpret_cast<const void*>(kernel));
+        if (it == configured.end() || it->second != rt().device) {
+            DGB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemCapacity));
+            configured[reinterpret_cast<const void*>(kernel)] = rt().device;
+        }
     }
     cudaLaunchConfig_t lc{};
     lc.gridDim = dim3(cfg.num_sms, 1, 1);
@@ -364,8 +378,8 @@ int run_gemm(const GemmCall& c) {
     p.num_stages = cfg.stages;
     p.ld_d = static_cast<uint32_t>(c.ldd);
     p.num_kp_x = num_kp_a, p.num_kp_w = num_kp_b;
-    p.kb_per_sf_x = c.gran_k_a == 128 ? 4 : 1;
-    p.kb_per_sf_w = c.gran_k_b == 128 ? 4 : 1;
+    p.sf_shift_x = c.gran_k_a == 128 ? 2 : 0;
+    p.sf_shift_w = c.gran_k_b == 128 ? 2 : 0;
     p.swizzle_group = std::max(1, cfg.swizzle_group);
     p.m_alignment = std::max(1, c.alignment);
     p.zero_padding = c.zero_padding;
@@ -559,6 +573,19 @@ int dgb200_k_grouped_fp8_gemm_tn_contiguous(const void* a, const int32_t* sfa, c
     (void)a, (void)sfa, (void)b, (void)sfb, (void)d, (void)ks_host, (void)num_groups, (void)m, (void)n, (void)gran_k,
         (void)stream;
     return fail(DGB200_ERR_UNSUPPORTED, "k-grouped FP8 GEMM is not built yet");
+}
+
+int dgb200_plan(int gemm_type, int m, int n, int k, int num_groups, int expected_m, int alignment, int num_sms,
+                dgb200_config* out) {
+    DGB_REQUIRE(out != nullptr && num_sms >= 2);
+    DGB_REQUIRE(gemm_type >= kDense && gemm_type <= kMContiguousPsum);
+    DGB_REQUIRE(m > 0 && n > 0 && k > 0 && num_groups > 0);
+    Problem pb{gemm_type, m, expected_m > 0 ? expected_m : m, n, k, num_groups, std::max(alignment, 1)};
+    const Config cfg = choose_config(pb, num_sms);
+    const int n_units = ceil_div(n, (int)kBlockN * cfg.cluster);
+    const int m_blocks = gemm_type == kMMasked ? num_groups * ceil_div(pb.expected_m, cfg.block_m) : ceil_div(m, cfg.block_m);
+    *out = dgb200_config{cfg.block_m, cfg.cluster, cfg.stages, cfg.num_sms, cfg.smem_bytes, m_blocks * n_units};
+    return DGB200_OK;
 }
 
 int dgb200_last_config(dgb200_config* out) {

@@ -58,8 +58,8 @@ struct GemmParams {
     uint32_t ld_d;
     uint32_t num_kp_x;          // packed SF words along K per group (tokens)
     uint32_t num_kp_w;          // packed SF words along K per group (weights)
-    uint32_t kb_per_sf_x;       // k-blocks covered by one packed SF word: 4 (gran_k 128) or 1 (gran_k 32)
-    uint32_t kb_per_sf_w;
+    uint32_t sf_shift_x;        // log2(k-blocks covered by one packed SF word): 2 (gran_k 128) or 0 (gran_k 32)
+    uint32_t sf_shift_w;
     uint32_t swizzle_group;     // L2 tile-order group width (in n-units)
     uint32_t m_alignment;       // contiguous layouts: group start alignment
     uint32_t zero_padding;      // psum: write zeros to [end, aligned end)
@@ -259,6 +259,7 @@ fp8_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
     asm volatile("griddepcontrol.wait;" ::: "memory");
 
     const uint32_t num_kb = (p.k + kBlockK - 1) / kBlockK;
+    const uint32_t sfw_mask = (1u << p.sf_shift_w) - 1, sfx_mask = (1u << p.sf_shift_x) - 1;
     uint32_t stage = 0, phase = 0;
     auto advance = [&]() {
         stage = stage + 1 == num_stages ? 0 : stage + 1;
@@ -275,8 +276,8 @@ fp8_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
                 const uint32_t x_row = t.x_row + cta_rank * load_m;
                 for (uint32_t kb = 0; kb < num_kb; ++kb, advance()) {
                     mbar_wait(empty_bar + stage, phase ^ 1);
-                    const bool load_sfw = kb % p.kb_per_sf_w == 0;
-                    const bool load_sfx = kb % p.kb_per_sf_x == 0;
+                    const bool load_sfw = (kb & sfw_mask) == 0;
+                    const bool load_sfx = (kb & sfx_mask) == 0;
                     const uint32_t bytes = ab_bytes + (load_sfw ? kBlockN * 4 : 0) + (load_sfx ? p.block_m * 4 : 0);
                     mbar_arrive_expect_tx(full_bar + stage, bytes);
                     // weights are streamed once per m-block; tokens are re-read by every n-unit
@@ -284,10 +285,10 @@ fp8_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
                     tma_load_2d(&map_x, full_bar + stage, smem_x + stage * x_tile_bytes, kb * kBlockK, x_row, kEvictNormal);
                     if (load_sfw)
                         tma_load_2d(&map_sfw, full_bar + stage, smem_sfw + stage * 512, t.sfw_col,
-                                    t.sfw_row + kb / p.kb_per_sf_w, kEvictNormal);
+                                    t.sfw_row + (kb >> p.sf_shift_w), kEvictNormal);
                     if (load_sfx)
                         tma_load_2d(&map_sfx, full_bar + stage, smem_sfx + stage * sfx_bytes, t.sfx_col,
-                                    t.sfx_row + kb / p.kb_per_sf_x, kEvictNormal);
+                                    t.sfx_row + (kb >> p.sf_shift_x), kEvictNormal);
                 }
             }
         }
@@ -305,14 +306,14 @@ fp8_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
             while (sched.next(t)) {
                 const uint32_t as = tile_iter & 1, aphase = (tile_iter >> 1) & 1;
                 ++tile_iter;
-                mbar_wait_cluster(tmem_empty_bar + as, aphase ^ 1);
+                mbar_wait(tmem_empty_bar + as, aphase ^ 1);
                 tcgen05_fence_after();
                 const uint32_t tmem_d = tmem_base + as * kAccumColStride;
                 for (uint32_t kb = 0; kb < num_kb; ++kb, advance()) {
-                    mbar_wait_cluster(ready_bar + stage, phase);
+                    mbar_wait(ready_bar + stage, phase);
                     tcgen05_fence_after();
                     if (elect_one()) {
-                        const uint32_t sfw_sub = kb % p.kb_per_sf_w, sfx_sub = kb % p.kb_per_sf_x;
+                        const uint32_t sfw_sub = kb & sfw_mask, sfx_sub = kb & sfx_mask;
                         if (sfw_sub == 0)
                             tmem_cp_sf<kCluster>(tmem_base + kTmemColSFW, sfw_desc0 + ((stage * 512) >> 4));
                         if (sfx_sub == 0)
@@ -324,8 +325,8 @@ fp8_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
 #pragma unroll
                         for (uint32_t j = 0; j < kBlockK / kUmmaK; ++j) {
                             // one UE8M0 byte per 32 K-elements: byte id inside the packed word
-                            const uint32_t w_id = p.kb_per_sf_w == 1 ? j : sfw_sub;
-                            const uint32_t x_id = p.kb_per_sf_x == 1 ? j : sfx_sub;
+                            const uint32_t w_id = sfw_mask == 0 ? j : sfw_sub;
+                            const uint32_t x_id = sfx_mask == 0 ? j : sfx_sub;
                             mma_mxf8_block_scale<kCluster>(tmem_d, w_desc + j * (kUmmaK >> 4), x_desc + j * (kUmmaK >> 4),
                                                            idesc_with_sf_ids(idesc_base, w_id, x_id),
                                                            tmem_base + kTmemColSFW, tmem_base + kTmemColSFX,
@@ -341,7 +342,7 @@ fp8_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
             // Drain: nobody may tear the CTA pair down while epilogue threads of the peer still arrive here
             if (tile_iter > 0) {
                 const uint32_t last = tile_iter - 1;
-                mbar_wait_cluster(tmem_empty_bar + (last & 1), (last >> 1) & 1);
+                mbar_wait(tmem_empty_bar + (last & 1), (last >> 1) & 1);
             }
         }
     } else if (warp_idx == 2) {
@@ -360,8 +361,8 @@ fp8_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
             for (uint32_t kb = 0; kb < num_kb; ++kb, advance()) {
                 mbar_wait(full_bar + stage, phase);
                 bool touched = false;
-                if (kb % p.kb_per_sf_w == 0) retile(smem_sfw + stage * 512), touched = true;
-                if (kb % p.kb_per_sf_x == 0) {
+                if ((kb & sfw_mask) == 0) retile(smem_sfw + stage * 512), touched = true;
+                if ((kb & sfx_mask) == 0) {
                     for (uint32_t i = 0; i < num_sfx_groups; ++i) retile(smem_sfx + stage * sfx_bytes + i * 512);
                     touched = true;
                 }
@@ -393,6 +394,14 @@ fp8_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
                 uint32_t v[16];
                 tmem_ld_32x32b_x16(taddr + c0, v);
                 tmem_ld_wait();
+                if (c0 + 16 >= load_cols) {
+                    // last read of this accumulator buffer: hand it back to the MMA warp before the stores drain
+                    tcgen05_fence_before();
+                    if constexpr (kCluster > 1)
+                        mbar_arrive_cluster(tmem_empty_bar + as, 0);
+                    else
+                        mbar_arrive(tmem_empty_bar + as);
+                }
 #pragma unroll
                 for (uint32_t j = 0; j < 16; ++j) {
                     const uint32_t r = c0 + j;
@@ -400,12 +409,6 @@ fp8_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
                         store_out<out_t>(d_col + static_cast<size_t>(r) * p.ld_d, __uint_as_float(v[j]), kAccumulate);
                 }
             }
-            // accumulator buffer may be overwritten by the tile after next
-            tcgen05_fence_before();
-            if constexpr (kCluster > 1)
-                mbar_arrive_cluster(tmem_empty_bar + as, 0);
-            else
-                mbar_arrive(tmem_empty_bar + as);
             // psum layout with zero padding: rows between the group's end and its aligned end are defined to be 0
             if (n_ok)
                 for (uint32_t r = t.valid_m; r < t.store_m; ++r)

@@ -72,12 +72,15 @@ DGB_DEVICE void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 // Arrive on the barrier that lives at the same smem offset in CTA `cta` of this cluster.
+// NOTE: default (.release.cta) semantics on purpose. Explicit `.release.cluster` / `.acquire.cluster` qualifiers make
+// ptxas emit MEMBAR.ALL.GPU + CCTL.IVALL around every barrier operation, which serialised the whole k-loop
+// (measured: 2.3x slower kernel). mbarrier objects in shared::cluster are coherent across the CTA pair.
 DGB_DEVICE void mbar_arrive_cluster(uint64_t* bar, uint32_t cta) {
     asm volatile(
         "{\n"
         ".reg .b32 raddr;\n"
         "mapa.shared::cluster.u32 raddr, %0, %1;\n"
-        "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [raddr];\n"
+        "mbarrier.arrive.shared::cluster.b64 _, [raddr];\n"
         "}\n" ::"r"(smem_u32(bar)),
         "r"(cta)
         : "memory");
@@ -88,20 +91,6 @@ DGB_DEVICE bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
         "{\n"
         ".reg .pred p;\n"
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-        "selp.u32 %0, 1, 0, p;\n"
-        "}\n"
-        : "=r"(done)
-        : "r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-    return done != 0;
-}
-// Cluster-scope acquire variant: used when the arrivals may come from the peer CTA.
-DGB_DEVICE bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
-    uint32_t done;
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n"
         "selp.u32 %0, 1, 0, p;\n"
         "}\n"
         : "=r"(done)
@@ -130,13 +119,6 @@ DGB_DEVICE void mbar_wait(uint64_t* bar, uint32_t parity) {
     uint64_t t0 = 0;
     while (!mbar_try_wait(bar, parity)) spin_guard(spins, t0);
 }
-DGB_DEVICE void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
-    if (mbar_try_wait_cluster(bar, parity)) return;
-    uint32_t spins = 0;
-    uint64_t t0 = 0;
-    while (!mbar_try_wait_cluster(bar, parity)) spin_guard(spins, t0);
-}
-
 // ---------------------------------------------------------------- proxies / fences
 DGB_DEVICE void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 DGB_DEVICE void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }

@@ -124,6 +124,11 @@ typedef struct dgb200_config {
     int smem_bytes;  /* dynamic shared memory per CTA */
     int num_tiles;   /* upper bound on (cluster) tiles */
 } dgb200_config;
+/* Pure function (no CUDA): the configuration the heuristics pick for a problem on `num_sms` SMs.
+ * gemm_type: 0 dense, 1 m-grouped contiguous, 2 m-grouped masked, 3 m-grouped contiguous psum.
+ * Replaces get_best_config<SM100ArchSpec> (csrc/jit_kernels/heuristics/common.hpp:13-52). */
+int dgb200_plan(int gemm_type, int m, int n, int k, int num_groups, int expected_m, int alignment, int num_sms,
+                dgb200_config* out);
 /* Configuration the last GEMM call on this thread used (DG_PRINT_CONFIGS analogue, heuristics/common.hpp:39-50). */
 int dgb200_last_config(dgb200_config* out);
 /* Number of kernels launched by this library since process start (all threads). */

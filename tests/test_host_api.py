@@ -1,0 +1,141 @@
+"""CPU: the C-ABI library loads and exports every symbol include/dgb200.h declares; host-side logic (knobs,
+heuristics, argument validation, error behaviour) works without a GPU. No compute calls here."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+import torch
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope='module')
+def lib():
+    from deepgemm_b200 import _lib
+    _lib.build()
+    return _lib
+
+
+def _declared_symbols():
+    text = open(os.path.join(REPO, 'include', 'dgb200.h')).read()
+    text = re.sub(r'/\*.*?\*/', '', text, flags=re.S)
+    return sorted(set(re.findall(r'\b(dgb200_[a-z0-9_]+)\s*\(', text)))
+
+
+def test_library_exports_every_declared_symbol(lib):
+    handle = ctypes.CDLL(lib.LIB_PATH)
+    declared = _declared_symbols()
+    assert len(declared) >= 20
+    for name in declared:
+        assert hasattr(handle, name), f'{name} declared in include/dgb200.h but not exported'
+    assert sorted(lib.SIGNATURES) == declared, 'python binding table and header disagree'
+
+
+def test_version_and_knobs_roundtrip(lib):
+    import deepgemm_b200 as dg
+    assert lib.lib().dgb200_version() == 100
+    dg.set_tc_util(80)
+    assert dg.get_tc_util() == 80
+    dg.set_tc_util(100)
+    dg.set_pdl(True)
+    assert dg.get_pdl() is True
+    dg.set_pdl(False)
+    assert dg.get_mk_alignment_for_contiguous_layout() == 128  # legacy default, heuristics/runtime.hpp:10
+    dg.set_mk_alignment_for_contiguous_layout(224)
+    assert dg.get_mk_alignment_for_contiguous_layout() == 224
+    dg.set_mk_alignment_for_contiguous_layout(128)
+    with pytest.raises(RuntimeError):
+        dg.set_num_sms(147)  # must be even (heuristics/config.hpp:47)
+    with pytest.raises(RuntimeError):
+        dg.set_mk_alignment_for_contiguous_layout(100)
+
+
+def test_alignment_helpers_match_reference_formulas(lib):
+    import deepgemm_b200 as dg
+    # csrc/utils/math.hpp:23-27
+    assert [dg.get_tma_aligned_size(x, 4) for x in (1, 4, 5, 4097)] == [4, 4, 8, 4100]
+    assert dg.get_tma_aligned_size(17, 1) == 32
+    # heuristics/runtime.hpp:47-57 (arch 10)
+    assert dg.get_theoretical_mk_alignment_for_contiguous_layout() == 224
+    assert dg.get_theoretical_mk_alignment_for_contiguous_layout(1000) == 224
+    assert dg.get_theoretical_mk_alignment_for_contiguous_layout(100) == 128
+    assert dg.get_theoretical_mk_alignment_for_contiguous_layout(20) == 32
+
+
+def test_heuristics_baseline_shapes(lib):
+    """Plan for the BASELINE.json shapes: valid tile heights, pipelines that fit 227 KB, CTA pairs."""
+    for m in (1, 64, 128, 512, 4096):
+        cfg = lib.plan(0, m, 4096, 7168)
+        assert cfg['block_m'] % 16 == 0 and 16 <= cfg['block_m'] <= 240
+        assert cfg['cluster'] == 2 and cfg['num_sms'] == 148
+        assert cfg['smem_bytes'] <= 232448 and cfg['num_stages'] >= 4
+        assert cfg['block_m'] - 16 < max(m, 16)
+    big = lib.plan(0, 4096, 4096, 7168)
+    assert big['block_m'] >= 192                      # compute-bound shape wants tall tiles
+    cont = lib.plan(1, 32768, 4096, 7168, 256, 128, 128)
+    assert 128 % cont['block_m'] == 0                 # a tile never straddles two experts
+    masked = lib.plan(2, 128, 7168, 2048, 256, 64)
+    assert masked['block_m'] <= 128
+
+
+def test_python_api_validation_errors_without_gpu(lib):
+    """Contract violations raise RuntimeError before anything touches CUDA (DG_HOST_ASSERT -> RuntimeError)."""
+    import deepgemm_b200 as dg
+    a = torch.zeros((8, 128), dtype=torch.float8_e4m3fn)
+    b = torch.zeros((16, 128), dtype=torch.float8_e4m3fn)
+    sfa, sfb = torch.ones((8, 1)), torch.ones((1, 1))
+    with pytest.raises(RuntimeError, match='m == m_'):
+        dg.fp8_gemm_nt((a, sfa), (b, sfb), torch.zeros((8, 32), dtype=torch.bfloat16))
+    with pytest.raises(RuntimeError, match='bfloat16 or float'):
+        dg.fp8_gemm_nt((a, sfa), (b, sfb), torch.zeros((8, 16), dtype=torch.float16))
+    with pytest.raises(RuntimeError, match='FP4'):
+        dg.fp8_gemm_nt((a.view(torch.int8), sfa), (b, sfb), torch.zeros((8, 16), dtype=torch.bfloat16))
+    with pytest.raises(RuntimeError, match='row-major'):
+        dg.fp8_gemm_nt((a, sfa), (b, sfb), torch.zeros((16, 8), dtype=torch.bfloat16).t())
+    # empty problems return before any device work (gemm.hpp:22-23)
+    dg.fp8_gemm_nt((a[:0], sfa[:0]), (b, sfb), torch.zeros((0, 16), dtype=torch.bfloat16))
+    # k == 0 -> D = C (gemm.hpp:36-40)
+    d = torch.ones((8, 16), dtype=torch.bfloat16)
+    c = torch.full((8, 16), 3.0, dtype=torch.bfloat16)
+    dg.fp8_gemm_nt((a[:, :0], sfa[:, :0]), (b[:, :0], sfb[:, :0]), d, c=c)
+    assert torch.equal(d, c)
+    with pytest.raises(RuntimeError, match='grouped_layout'):
+        dg.m_grouped_fp8_gemm_nt_contiguous((a, sfa), (b.view(1, 16, 128), sfb.view(1, 1, 1)),
+                                            torch.zeros((8, 16), dtype=torch.bfloat16),
+                                            torch.zeros(3, dtype=torch.int32))
+    with pytest.raises(RuntimeError, match='Unsupported architecture'):
+        dg.k_grouped_fp8_gemm_nt_contiguous(None, None, None, None, None)
+
+
+def test_aliases_and_dropin_module(lib):
+    import deep_gemm
+    import deepgemm_b200 as dg
+    assert deep_gemm.fp8_gemm_nt is dg.fp8_gemm_nt
+    assert deep_gemm.fp8_fp4_gemm_nt is dg.fp8_gemm_nt
+    assert deep_gemm.fp8_m_grouped_gemm_nt_masked is dg.m_grouped_fp8_gemm_nt_masked
+    from deep_gemm.utils import per_token_cast_to_fp8  # noqa: F401
+    from deep_gemm.testing import calc_diff  # noqa: F401
+    for name in ('fp8_gemm_nt', 'fp8_gemm_nn', 'fp8_gemm_tn', 'fp8_gemm_tt', 'm_grouped_fp8_gemm_nt_contiguous',
+                 'm_grouped_fp8_gemm_nn_contiguous', 'm_grouped_fp8_gemm_nt_masked', 'k_grouped_fp8_gemm_tn_contiguous',
+                 'transform_sf_into_required_layout', 'get_mn_major_tma_aligned_packed_ue8m0_tensor', 'set_num_sms',
+                 'get_num_sms', 'set_tc_util', 'set_pdl', 'get_mk_alignment_for_contiguous_layout'):
+        assert hasattr(deep_gemm, name), name
+
+
+def test_import_does_not_touch_cuda():
+    """The reference guarantees import-then-fork safety (tests/test_lazy_init.py); so do we."""
+    code = ('import torch, deepgemm_b200, deep_gemm; from deepgemm_b200 import _lib; _lib.lib(); '
+            'assert not torch.cuda.is_initialized(); print("ok")')
+    out = subprocess.run([sys.executable, '-c', code], cwd=REPO, capture_output=True, text=True)
+    assert out.returncode == 0 and 'ok' in out.stdout, out.stderr
+
+
+def test_product_path_never_imports_the_oracle():
+    for root, _, files in os.walk(os.path.join(REPO, 'deepgemm_b200')):
+        for f in files:
+            if f.endswith(('.py', '.cu', '.cuh', '.h')):
+                text = open(os.path.join(root, f)).read()
+                assert 'import oracle' not in text and 'from oracle' not in text, f
