@@ -178,9 +178,7 @@ struct Config {
 
 constexpr int kSmemCapacity = 232448;  // 227 KB usable per CTA on sm_100 (heuristics/sm100.hpp:15)
 
-int stage_bytes(int block_m, int cluster) {
-    return kWTileBytes + (block_m / cluster) * kBlockK + 512 + ceil_div(block_m, 128) * 512;
-}
+int stage_bytes(int block_m, int cluster) { return static_cast<int>(slot_bytes(block_m, cluster)); }
 int smem_bytes_for(int block_m, int cluster, int stages) {
     return stages * stage_bytes(block_m, cluster) + (3 * stages + 4) * 8 + 16;
 }
@@ -381,6 +379,8 @@ int run_gemm(const GemmCall& c) {
     p.sf_shift_x = c.gran_k_a == 128 ? 2 : 0;
     p.sf_shift_w = c.gran_k_b == 128 ? 2 : 0;
     p.swizzle_group = std::max(1, cfg.swizzle_group);
+    p.num_n_units = ceil_div(c.n, (int)kBlockN * cfg.cluster);
+    p.num_m_blocks = ceil_div(c.m, cfg.block_m);
     p.m_alignment = std::max(1, c.alignment);
     p.zero_padding = c.zero_padding;
 

@@ -19,8 +19,9 @@
 //    csrc/utils/layout.hpp:100-107) so user-packed tensors keep working; a helper warp re-tiles each 128-word
 //    group into the `tcgen05.cp` 32x128b layout before the MMA warp copies it into TMEM.
 //
-// Warp roles (256 threads): w0 TMA producer | w1 MMA issuer (leader CTA) | w2 TMEM alloc + SF re-tiler |
-//                           w3 idle | w4-7 epilogue (TMEM -> registers -> global).
+// Warp roles (384 threads): w0 TMA producer | w1 MMA issuer (leader CTA) | w2 TMEM alloc + SF re-tiler |
+//                           w3 idle | w4-11 epilogue (TMEM -> registers -> global; two warps per lane quadrant,
+//                           interleaved over 32-row chunks so the exposed tail of the last tile is halved).
 #pragma once
 #include <cuda_bf16.h>
 
@@ -43,8 +44,8 @@ constexpr uint32_t kAccumColStride = 256;
 constexpr uint32_t kTmemColSFW = 496;    // weight scale factors: 4 columns
 constexpr uint32_t kTmemColSFX = 500;    // token scale factors: up to 8 columns
 constexpr uint32_t kTmemCols = 512;
-constexpr uint32_t kNumThreads = 256;
-constexpr uint32_t kNumEpilogueThreads = 128;
+constexpr uint32_t kNumThreads = 384;
+constexpr uint32_t kNumEpilogueThreads = 256;   // two warps per TMEM lane quadrant
 constexpr uint32_t kWTileBytes = kBlockN * kBlockK;  // 16 KB
 
 struct GemmParams {
@@ -61,6 +62,8 @@ struct GemmParams {
     uint32_t sf_shift_x;        // log2(k-blocks covered by one packed SF word): 2 (gran_k 128) or 0 (gran_k 32)
     uint32_t sf_shift_w;
     uint32_t swizzle_group;     // L2 tile-order group width (in n-units)
+    uint32_t num_n_units;       // ceil(n / (128 * cluster))
+    uint32_t num_m_blocks;      // dense / contiguous: ceil(m / block_m)
     uint32_t m_alignment;       // contiguous layouts: group start alignment
     uint32_t zero_padding;      // psum: write zeros to [end, aligned end)
 };
@@ -91,7 +94,7 @@ struct Scheduler {
     __device__ Scheduler(const GemmParams& p_, uint32_t rank) : p(p_), cta_rank(rank) {
         cluster_id = blockIdx.x / kCluster;
         num_clusters = gridDim.x / kCluster;
-        num_n_units = (p.n + kBlockN * kCluster - 1) / (kBlockN * kCluster);
+        num_n_units = p.num_n_units;
         if constexpr (kGemmType == kMContiguousPsum) row_end = static_cast<uint32_t>(__ldg(p.grouped_layout));
     }
 
@@ -111,7 +114,7 @@ struct Scheduler {
         const uint32_t idx = cluster_id + (iter++) * num_clusters;
         uint32_t m_blk, n_unit, group = 0;
         if constexpr (kGemmType == kDense || kGemmType == kMContiguous) {
-            const uint32_t num_m = (p.m + p.block_m - 1) / p.block_m;
+            const uint32_t num_m = p.num_m_blocks;
             if (idx >= num_m * num_n_units) return false;
             split(idx, num_m, m_blk, n_unit);
             t.x_row = m_blk * p.block_m;
@@ -143,9 +146,11 @@ struct Scheduler {
             t.valid_m = min(p.block_m, row_end - m0);
             t.store_m = t.valid_m;
         } else {  // kMContiguousPsum
-            uint32_t num_m;
+            uint32_t num_m, cover_end;
             while (true) {
-                num_m = (row_end - row_start + p.block_m - 1) / p.block_m;
+                // rows [row_start, row_end) are real; with zero padding the gap up to the aligned end is written too
+                cover_end = p.zero_padding ? min(p.m, (row_end + p.m_alignment - 1) / p.m_alignment * p.m_alignment) : row_end;
+                num_m = (cover_end - row_start + p.block_m - 1) / p.block_m;
                 if (idx < (unit_cum + num_m) * num_n_units) break;
                 unit_cum += num_m;
                 if (++g >= p.num_groups) return false;
@@ -158,9 +163,8 @@ struct Scheduler {
             t.d_row = t.x_row;
             t.sfx_col = t.x_row;
             t.sfx_row = 0;
-            t.valid_m = min(p.block_m, row_end - t.x_row);
-            const uint32_t aligned_end = min(p.m, (row_end + p.m_alignment - 1) / p.m_alignment * p.m_alignment);
-            t.store_m = p.zero_padding ? min(p.block_m, aligned_end - t.x_row) : t.valid_m;
+            t.valid_m = t.x_row < row_end ? min(p.block_m, row_end - t.x_row) : 0u;   // 0: a pure padding tile
+            t.store_m = min(p.block_m, cover_end - t.x_row);
         }
         t.n0 = (n_unit * kCluster + cta_rank) * kBlockN;
         t.w_row = group * p.n + t.n0;
@@ -189,6 +193,26 @@ __device__ __forceinline__ void store_out<__nv_bfloat16>(__nv_bfloat16* ptr, flo
 }
 
 // ------------------------------------------------------------------------------------------------ the kernel
+// Shared memory: `num_stages` contiguous stage slots, then the barriers.
+//   slot  = [ W 128x128 B | X load_m x 128 B | SFW 512 B | SFX groups x 512 B | pad to 1 KB ]
+// Every role walks the ring with two running offsets (slot byte offset, barrier byte offset): the k-loops contain no
+// multiplications, no generic->shared conversions and no 64-bit address arithmetic. (With runtime shapes the naive
+// form cost ~450 cycles per k-block in the single-thread TMA producer and capped the small-M shapes.)
+struct Ring {
+    uint32_t slot, bar, phase;       // byte offset of the current slot, byte offset of its barrier, phase bit
+    uint32_t slot_stride, bar_end;
+    __device__ __forceinline__ Ring(uint32_t slot_stride_, uint32_t num_stages)
+        : slot(0), bar(0), phase(0), slot_stride(slot_stride_), bar_end(num_stages * 8) {}
+    __device__ __forceinline__ void advance() {
+        slot += slot_stride, bar += 8;
+        if (bar == bar_end) slot = 0, bar = 0, phase ^= 1;
+    }
+};
+
+__host__ __device__ constexpr uint32_t slot_bytes(uint32_t block_m, uint32_t cluster) {
+    return (kWTileBytes + (block_m / cluster) * kBlockK + 512 + ((block_m + 127) / 128) * 512 + 1023) / 1024 * 1024;
+}
+
 template <int kGemmType, int kCluster, typename out_t, bool kAccumulate>
 __global__ void __launch_bounds__(kNumThreads, 1)
 fp8_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
@@ -203,23 +227,21 @@ fp8_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
     const uint32_t cta_rank = kCluster == 1 ? 0u : cluster_ctarank();
     const bool is_leader = cta_rank == 0;
 
-    // ---- shared memory carve-up (all sizes are runtime values)
+    // ---- shared memory carve-up (all sizes are runtime values), as 32-bit shared::cta addresses
     const uint32_t num_stages = p.num_stages;
     const uint32_t load_m = p.block_m / kCluster;                           // token rows this CTA loads per stage
     const uint32_t x_tile_bytes = load_m * kBlockK;                         // multiple of 1024 (load_m % 8 == 0)
     const uint32_t num_sfx_groups = (p.block_m + 127) / 128;                // 128-row UTCCP groups of token SFs
-    const uint32_t sfx_bytes = num_sfx_groups * 512;
-    uint8_t* smem_w = smem;
-    uint8_t* smem_x = smem_w + num_stages * kWTileBytes;
-    uint8_t* smem_sfw = smem_x + num_stages * x_tile_bytes;
-    uint8_t* smem_sfx = smem_sfw + num_stages * 512;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_sfx + num_stages * sfx_bytes);
-    uint64_t* full_bar = bars;                         // TMA bytes landed (per CTA)
-    uint64_t* empty_bar = bars + num_stages;           // MMAs that read the stage retired (per CTA, via commit)
-    uint64_t* ready_bar = bars + 2 * num_stages;       // stage landed in every CTA + SFs re-tiled (leader only)
-    uint64_t* tmem_full_bar = bars + 3 * num_stages;   // [2] accumulator complete (per CTA, via commit)
-    uint64_t* tmem_empty_bar = tmem_full_bar + 2;      // [2] accumulator drained by all epilogue threads (leader only)
-    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+    const uint32_t slot_stride = slot_bytes(p.block_m, kCluster);
+    const uint32_t smem_base = smem_u32(smem);
+    const uint32_t off_x = kWTileBytes, off_sfw = off_x + x_tile_bytes, off_sfx = off_sfw + 512;
+    const uint32_t bars = smem_base + num_stages * slot_stride;
+    const uint32_t full_bar = bars;                            // TMA bytes landed (per CTA)
+    const uint32_t empty_bar = bars + num_stages * 8;          // MMAs that read the slot retired (per CTA, via commit)
+    const uint32_t ready_bar = bars + num_stages * 16;         // slot landed in every CTA + SFs re-tiled (leader only)
+    const uint32_t tmem_full_bar = bars + num_stages * 24;     // [2] accumulator complete (per CTA, via commit)
+    const uint32_t tmem_empty_bar = tmem_full_bar + 16;        // [2] accumulator drained by all epilogue threads (leader)
+    const uint32_t tmem_ptr_smem = tmem_empty_bar + 16;
 
     if (warp_idx == 0 && elect_one()) {
         prefetch_tensormap(&map_x);
@@ -229,13 +251,13 @@ fp8_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
     }
     if (warp_idx == 1 && elect_one()) {
         for (uint32_t i = 0; i < num_stages; ++i) {
-            mbar_init(full_bar + i, 1);
-            mbar_init(empty_bar + i, 1);
-            mbar_init(ready_bar + i, 32 * kCluster);
+            mbar_init(full_bar + i * 8, 1);
+            mbar_init(empty_bar + i * 8, 1);
+            mbar_init(ready_bar + i * 8, 32 * kCluster);
         }
         for (uint32_t i = 0; i < 2; ++i) {
-            mbar_init(tmem_full_bar + i, 1);
-            mbar_init(tmem_empty_bar + i, kNumEpilogueThreads * kCluster);
+            mbar_init(tmem_full_bar + i * 8, 1);
+            mbar_init(tmem_empty_bar + i * 8, kNumEpilogueThreads * kCluster);
         }
         fence_mbar_init();
     }
@@ -247,24 +269,22 @@ fp8_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
     if (warp_idx == 2) tmem_alloc<kCluster>(tmem_ptr_smem, kTmemCols);
     tcgen05_fence_before();
     if constexpr (kCluster > 1) {
-        cluster_arrive();
+        // relaxed arrive: `fence.mbarrier_init.release.cluster` above already publishes the barrier inits, and a
+        // release-arrive would cost a MEMBAR.ALL.GPU
+        cluster_arrive_relaxed();
         cluster_wait();
     } else {
         __syncthreads();
     }
     tcgen05_fence_after();
-    const uint32_t tmem_base = *tmem_ptr_smem;
+    const uint32_t tmem_base = ld_shared_u32(tmem_ptr_smem);
 
     // Programmatic dependent launch: everything above overlaps the previous kernel's tail
     asm volatile("griddepcontrol.wait;" ::: "memory");
 
     const uint32_t num_kb = (p.k + kBlockK - 1) / kBlockK;
     const uint32_t sfw_mask = (1u << p.sf_shift_w) - 1, sfx_mask = (1u << p.sf_shift_x) - 1;
-    uint32_t stage = 0, phase = 0;
-    auto advance = [&]() {
-        stage = stage + 1 == num_stages ? 0 : stage + 1;
-        phase ^= (stage == 0);
-    };
+    Ring ring(slot_stride, num_stages);
 
     if (warp_idx == 0) {
         // =================================================================== TMA producer (one lane, every CTA)
@@ -272,23 +292,20 @@ fp8_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
             Scheduler<kGemmType, kCluster> sched(p, cta_rank);
             Tile t;
             const uint32_t ab_bytes = kWTileBytes + x_tile_bytes;
+            const uint32_t sfw_tx = kBlockN * 4, sfx_tx = p.block_m * 4;
             while (sched.next(t)) {
+                if (kGemmType == kMContiguousPsum && t.valid_m == 0) continue;   // padding-only tile: nothing to load
                 const uint32_t x_row = t.x_row + cta_rank * load_m;
-                for (uint32_t kb = 0; kb < num_kb; ++kb, advance()) {
-                    mbar_wait(empty_bar + stage, phase ^ 1);
-                    const bool load_sfw = (kb & sfw_mask) == 0;
-                    const bool load_sfx = (kb & sfx_mask) == 0;
-                    const uint32_t bytes = ab_bytes + (load_sfw ? kBlockN * 4 : 0) + (load_sfx ? p.block_m * 4 : 0);
-                    mbar_arrive_expect_tx(full_bar + stage, bytes);
-                    // weights are streamed once per m-block; tokens are re-read by every n-unit
-                    tma_load_2d(&map_w, full_bar + stage, smem_w + stage * kWTileBytes, kb * kBlockK, t.w_row, kEvictNormal);
-                    tma_load_2d(&map_x, full_bar + stage, smem_x + stage * x_tile_bytes, kb * kBlockK, x_row, kEvictNormal);
-                    if (load_sfw)
-                        tma_load_2d(&map_sfw, full_bar + stage, smem_sfw + stage * 512, t.sfw_col,
-                                    t.sfw_row + (kb >> p.sf_shift_w), kEvictNormal);
-                    if (load_sfx)
-                        tma_load_2d(&map_sfx, full_bar + stage, smem_sfx + stage * sfx_bytes, t.sfx_col,
-                                    t.sfx_row + (kb >> p.sf_shift_x), kEvictNormal);
+                uint32_t k0 = 0;
+                for (uint32_t kb = 0; kb < num_kb; ++kb, k0 += kBlockK, ring.advance()) {
+                    const uint32_t full = full_bar + ring.bar, slot = smem_base + ring.slot;
+                    mbar_wait(empty_bar + ring.bar, ring.phase ^ 1);
+                    const bool load_sfw = (kb & sfw_mask) == 0, load_sfx = (kb & sfx_mask) == 0;
+                    mbar_arrive_expect_tx(full, ab_bytes + (load_sfw ? sfw_tx : 0u) + (load_sfx ? sfx_tx : 0u));
+                    tma_load_2d(&map_w, full, slot, k0, t.w_row, kEvictNormal);
+                    tma_load_2d(&map_x, full, slot + off_x, k0, x_row, kEvictNormal);
+                    if (load_sfw) tma_load_2d(&map_sfw, full, slot + off_sfw, t.sfw_col, t.sfw_row + (kb >> p.sf_shift_w), kEvictNormal);
+                    if (load_sfx) tma_load_2d(&map_sfx, full, slot + off_sfx, t.sfx_col, t.sfx_row + (kb >> p.sf_shift_x), kEvictNormal);
                 }
             }
         }
@@ -298,43 +315,42 @@ fp8_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
             Scheduler<kGemmType, kCluster> sched(p, cta_rank);
             Tile t;
             const uint32_t idesc_base = make_idesc(128 * kCluster, p.block_m, 0, 0);
-            const uint64_t w_desc0 = make_smem_desc(smem_u32(smem_w), 0, 1024, kLayoutSwizzle128B);
-            const uint64_t x_desc0 = make_smem_desc(smem_u32(smem_x), 0, 1024, kLayoutSwizzle128B);
-            const uint64_t sfw_desc0 = make_smem_desc(smem_u32(smem_sfw), 0, 128, kLayoutNoSwizzle);
-            const uint64_t sfx_desc0 = make_smem_desc(smem_u32(smem_sfx), 0, 128, kLayoutNoSwizzle);
+            // descriptors of slot 0; a slot offset adds (bytes >> 4) to the 14-bit start-address field
+            const uint64_t w_desc0 = make_smem_desc(smem_base, 0, 1024, kLayoutSwizzle128B);
+            const uint64_t x_desc0 = make_smem_desc(smem_base + off_x, 0, 1024, kLayoutSwizzle128B);
+            const uint64_t sfw_desc0 = make_smem_desc(smem_base + off_sfw, 0, 128, kLayoutNoSwizzle);
+            const uint64_t sfx_desc0 = make_smem_desc(smem_base + off_sfx, 0, 128, kLayoutNoSwizzle);
+            const uint32_t tmem_sfw = tmem_base + kTmemColSFW, tmem_sfx = tmem_base + kTmemColSFX;
             uint32_t tile_iter = 0;
             while (sched.next(t)) {
+                if (kGemmType == kMContiguousPsum && t.valid_m == 0) continue;
                 const uint32_t as = tile_iter & 1, aphase = (tile_iter >> 1) & 1;
                 ++tile_iter;
-                mbar_wait(tmem_empty_bar + as, aphase ^ 1);
+                mbar_wait(tmem_empty_bar + as * 8, aphase ^ 1);
                 tcgen05_fence_after();
                 const uint32_t tmem_d = tmem_base + as * kAccumColStride;
-                for (uint32_t kb = 0; kb < num_kb; ++kb, advance()) {
-                    mbar_wait(ready_bar + stage, phase);
+                for (uint32_t kb = 0; kb < num_kb; ++kb, ring.advance()) {
+                    mbar_wait(ready_bar + ring.bar, ring.phase);
                     tcgen05_fence_after();
                     if (elect_one()) {
+                        const uint32_t slot16 = ring.slot >> 4;
                         const uint32_t sfw_sub = kb & sfw_mask, sfx_sub = kb & sfx_mask;
-                        if (sfw_sub == 0)
-                            tmem_cp_sf<kCluster>(tmem_base + kTmemColSFW, sfw_desc0 + ((stage * 512) >> 4));
-                        if (sfx_sub == 0)
-                            for (uint32_t i = 0; i < num_sfx_groups; ++i)
-                                tmem_cp_sf<kCluster>(tmem_base + kTmemColSFX + i * 4,
-                                                     sfx_desc0 + ((stage * sfx_bytes + i * 512) >> 4));
-                        const uint64_t w_desc = w_desc0 + ((stage * kWTileBytes) >> 4);
-                        const uint64_t x_desc = x_desc0 + ((stage * x_tile_bytes) >> 4);
-#pragma unroll
-                        for (uint32_t j = 0; j < kBlockK / kUmmaK; ++j) {
-                            // one UE8M0 byte per 32 K-elements: byte id inside the packed word
-                            const uint32_t w_id = sfw_mask == 0 ? j : sfw_sub;
-                            const uint32_t x_id = sfx_mask == 0 ? j : sfx_sub;
-                            mma_mxf8_block_scale<kCluster>(tmem_d, w_desc + j * (kUmmaK >> 4), x_desc + j * (kUmmaK >> 4),
-                                                           idesc_with_sf_ids(idesc_base, w_id, x_id),
-                                                           tmem_base + kTmemColSFW, tmem_base + kTmemColSFX,
-                                                           (kb | j) != 0 ? 1u : 0u);
+                        if (sfw_sub == 0) tmem_cp_sf<kCluster>(tmem_sfw, sfw_desc0 + slot16);
+                        if (sfx_sub == 0) {
+                            tmem_cp_sf<kCluster>(tmem_sfx, sfx_desc0 + slot16);
+                            if (num_sfx_groups > 1) tmem_cp_sf<kCluster>(tmem_sfx + 4, sfx_desc0 + slot16 + 32);
                         }
-                        // retire -> the smem stage may be overwritten (signals every CTA of the pair)
-                        mma_commit<kCluster>(empty_bar + stage);
-                        if (kb + 1 == num_kb) mma_commit<kCluster>(tmem_full_bar + as);
+                        const uint64_t w_desc = w_desc0 + slot16, x_desc = x_desc0 + slot16;
+                        // one UE8M0 byte per 32 K-elements: byte id inside the packed word
+                        const uint32_t idesc = idesc_with_sf_ids(idesc_base, sfw_mask ? sfw_sub : 0u, sfx_mask ? sfx_sub : 0u);
+                        const uint32_t id_step = (sfw_mask ? 0u : (1u << 29)) | (sfx_mask ? 0u : (1u << 4));  // gran_k 32
+#pragma unroll
+                        for (uint32_t j = 0; j < kBlockK / kUmmaK; ++j)
+                            mma_mxf8_block_scale<kCluster>(tmem_d, w_desc + j * (kUmmaK >> 4), x_desc + j * (kUmmaK >> 4),
+                                                           idesc + j * id_step, tmem_sfw, tmem_sfx, (kb | j) != 0 ? 1u : 0u);
+                        // retire -> the smem slot may be overwritten (signals every CTA of the pair)
+                        mma_commit<kCluster>(empty_bar + ring.bar);
+                        if (kb + 1 == num_kb) mma_commit<kCluster>(tmem_full_bar + as * 8);
                     }
                     __syncwarp();
                 }
@@ -342,35 +358,41 @@ fp8_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
             // Drain: nobody may tear the CTA pair down while epilogue threads of the peer still arrive here
             if (tile_iter > 0) {
                 const uint32_t last = tile_iter - 1;
-                mbar_wait(tmem_empty_bar + (last & 1), (last >> 1) & 1);
+                mbar_wait(tmem_empty_bar + (last & 1) * 8, (last >> 1) & 1);
             }
         }
     } else if (warp_idx == 2) {
-        // =================================================================== SF re-tiler / stage forwarder
+        // =================================================================== SF re-tiler / slot forwarder
         Scheduler<kGemmType, kCluster> sched(p, cta_rank);
         Tile t;
         // tcgen05.cp 32x128b wants word (row r of the 128-group) at [r % 32][r / 32]; TMA delivered it at [r]
-        auto retile = [&](uint8_t* base) {
-            uint32_t* w = reinterpret_cast<uint32_t*>(base);
-            const uint32_t v0 = ld_shared_u32(w + lane), v1 = ld_shared_u32(w + 32 + lane),
-                           v2 = ld_shared_u32(w + 64 + lane), v3 = ld_shared_u32(w + 96 + lane);
+        auto retile = [&](uint32_t base) {
+            const uint32_t src = base + lane * 4;
+            const uint32_t v0 = ld_shared_u32(src), v1 = ld_shared_u32(src + 128), v2 = ld_shared_u32(src + 256),
+                           v3 = ld_shared_u32(src + 384);
             __syncwarp();
-            st_shared_v4(w + lane * 4, v0, v1, v2, v3);
+            st_shared_v4(base + lane * 16, v0, v1, v2, v3);
         };
+        // barrier of the pair's leader CTA, as a shared::cluster address
+        const uint32_t ready_dst = kCluster > 1 ? mapa(ready_bar, 0) : ready_bar;
         while (sched.next(t)) {
-            for (uint32_t kb = 0; kb < num_kb; ++kb, advance()) {
-                mbar_wait(full_bar + stage, phase);
-                bool touched = false;
-                if ((kb & sfw_mask) == 0) retile(smem_sfw + stage * 512), touched = true;
-                if ((kb & sfx_mask) == 0) {
-                    for (uint32_t i = 0; i < num_sfx_groups; ++i) retile(smem_sfx + stage * sfx_bytes + i * 512);
-                    touched = true;
+            if (kGemmType == kMContiguousPsum && t.valid_m == 0) continue;
+            for (uint32_t kb = 0; kb < num_kb; ++kb, ring.advance()) {
+                mbar_wait(full_bar + ring.bar, ring.phase);
+                const bool do_w = (kb & sfw_mask) == 0, do_x = (kb & sfx_mask) == 0;
+                if (do_w | do_x) {
+                    const uint32_t slot = smem_base + ring.slot;
+                    if (do_w) retile(slot + off_sfw);
+                    if (do_x) {
+                        retile(slot + off_sfx);
+                        if (num_sfx_groups > 1) retile(slot + off_sfx + 512);
+                    }
+                    fence_proxy_async_smem();   // generic-proxy writes -> visible to tcgen05.cp
                 }
-                if (touched) fence_proxy_async_smem();   // generic-proxy writes -> visible to tcgen05.cp
                 if constexpr (kCluster > 1)
-                    mbar_arrive_cluster(ready_bar + stage, 0);
+                    mbar_arrive_remote(ready_dst + ring.bar);
                 else
-                    mbar_arrive(ready_bar + stage);
+                    mbar_arrive(ready_dst + ring.bar);
             }
         }
     } else if (warp_idx >= 4) {
@@ -378,48 +400,69 @@ fp8_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
         Scheduler<kGemmType, kCluster> sched(p, cta_rank);
         Tile t;
         const uint32_t quad = warp_idx & 3;                 // TMEM lane quadrant this warp may read
+        const uint32_t half = (warp_idx - 4) >> 2;          // 0: chunks 0,2,4.. | 1: chunks 1,3,5..
         out_t* d = reinterpret_cast<out_t*>(p.d);
+        const uint32_t tmem_empty_dst = kCluster > 1 ? mapa(tmem_empty_bar, 0) : tmem_empty_bar;
+        const size_t row_bytes = static_cast<size_t>(p.ld_d) * sizeof(out_t);
         uint32_t tile_iter = 0;
         while (sched.next(t)) {
-            const uint32_t as = tile_iter & 1, aphase = (tile_iter >> 1) & 1;
-            ++tile_iter;
-            mbar_wait(tmem_full_bar + as, aphase);
-            tcgen05_fence_after();
-            const uint32_t taddr = tmem_base + ((quad * 32) << 16) + as * kAccumColStride;
             const uint32_t n = t.n0 + quad * 32 + lane;
             const bool n_ok = n < p.n;
-            out_t* d_col = d + static_cast<size_t>(t.d_row) * p.ld_d + n;
+            char* d_col = reinterpret_cast<char*>(d + static_cast<size_t>(t.d_row) * p.ld_d + n);
+            if (kGemmType == kMContiguousPsum && t.valid_m == 0) {
+                if (n_ok && half == 0)
+                    for (uint32_t r = 0; r < t.store_m; ++r) store_out<out_t>(reinterpret_cast<out_t*>(d_col + r * row_bytes), 0.0f, false);
+                continue;
+            }
+            const uint32_t as = tile_iter & 1, aphase = (tile_iter >> 1) & 1;
+            ++tile_iter;
+            mbar_wait(tmem_full_bar + as * 8, aphase);
+            tcgen05_fence_after();
+            const uint32_t taddr = tmem_base + ((quad * 32) << 16) + as * kAccumColStride;
             const uint32_t load_cols = (max(t.valid_m, 1u) + 15) / 16 * 16;
-            for (uint32_t c0 = 0; c0 < load_cols; c0 += 16) {
-                uint32_t v[16];
-                tmem_ld_32x32b_x16(taddr + c0, v);
+            auto release_accumulator = [&]() {
+                // last read of this accumulator buffer by this warp: hand it back before the stores drain
+                tcgen05_fence_before();
+                if constexpr (kCluster > 1)
+                    mbar_arrive_remote(tmem_empty_dst + as * 8);
+                else
+                    mbar_arrive(tmem_empty_dst + as * 8);
+            };
+            if (half * 32 >= load_cols) release_accumulator();   // nothing to read for this warp
+            // 32 token rows per iteration: two TMEM loads in flight, then 32 row stores (one instruction each,
+            // 32 consecutive columns per warp). Full chunks take the branch-free path.
+            for (uint32_t c0 = half * 32; c0 < load_cols; c0 += 64) {
+                uint32_t v[32];
+                const bool second = c0 + 16 < load_cols;
+                tmem_ld_32x32b_x16(taddr + c0, *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
+                if (second) tmem_ld_32x32b_x16(taddr + c0 + 16, *reinterpret_cast<uint32_t(*)[16]>(&v[16]));
                 tmem_ld_wait();
-                if (c0 + 16 >= load_cols) {
-                    // last read of this accumulator buffer: hand it back to the MMA warp before the stores drain
-                    tcgen05_fence_before();
-                    if constexpr (kCluster > 1)
-                        mbar_arrive_cluster(tmem_empty_bar + as, 0);
-                    else
-                        mbar_arrive(tmem_empty_bar + as);
-                }
+                if (c0 + 64 >= load_cols) release_accumulator();
+                char* row = d_col + static_cast<size_t>(c0) * row_bytes;
+                if (n_ok) {
+                    if (c0 + 32 <= t.valid_m) {
 #pragma unroll
-                for (uint32_t j = 0; j < 16; ++j) {
-                    const uint32_t r = c0 + j;
-                    if (r < t.valid_m && n_ok)
-                        store_out<out_t>(d_col + static_cast<size_t>(r) * p.ld_d, __uint_as_float(v[j]), kAccumulate);
+                        for (uint32_t j = 0; j < 32; ++j)
+                            store_out<out_t>(reinterpret_cast<out_t*>(row + j * row_bytes), __uint_as_float(v[j]), kAccumulate);
+                    } else {
+#pragma unroll
+                        for (uint32_t j = 0; j < 32; ++j)
+                            if (c0 + j < t.valid_m)
+                                store_out<out_t>(reinterpret_cast<out_t*>(row + j * row_bytes), __uint_as_float(v[j]), kAccumulate);
+                    }
                 }
             }
             // psum layout with zero padding: rows between the group's end and its aligned end are defined to be 0
-            if (n_ok)
+            if (n_ok && half == 0)
                 for (uint32_t r = t.valid_m; r < t.store_m; ++r)
-                    store_out<out_t>(d_col + static_cast<size_t>(r) * p.ld_d, 0.0f, false);
+                    store_out<out_t>(reinterpret_cast<out_t*>(d_col + r * row_bytes), 0.0f, false);
         }
     }
 
     // ---- teardown
     tcgen05_fence_before();
     if constexpr (kCluster > 1) {
-        cluster_arrive();
+        cluster_arrive_relaxed();   // (a release-arrive here would wait for every output store to become visible)
         cluster_wait();
     } else {
         __syncthreads();

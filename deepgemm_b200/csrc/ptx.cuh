@@ -59,42 +59,41 @@ DGB_DEVICE void cluster_arrive_relaxed() { asm volatile("barrier.cluster.arrive.
 DGB_DEVICE void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
 DGB_DEVICE void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
 
-// ---------------------------------------------------------------- mbarrier
-DGB_DEVICE void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+// ---------------------------------------------------------------- mbarrier (all addresses are 32-bit shared::cta)
+DGB_DEVICE void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
 DGB_DEVICE void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 
-DGB_DEVICE void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+DGB_DEVICE void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-DGB_DEVICE void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+DGB_DEVICE void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-// Arrive on the barrier that lives at the same smem offset in CTA `cta` of this cluster.
+// shared::cluster address of `addr` (a shared::cta address of this CTA) as seen in CTA `cta` of the cluster
+DGB_DEVICE uint32_t mapa(uint32_t addr, uint32_t cta) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(cta));
+    return r;
+}
+// Arrive on a barrier of another CTA of the cluster (`bar` is a shared::cluster address from mapa()).
 // NOTE: default (.release.cta) semantics on purpose. Explicit `.release.cluster` / `.acquire.cluster` qualifiers make
 // ptxas emit MEMBAR.ALL.GPU + CCTL.IVALL around every barrier operation, which serialised the whole k-loop
 // (measured: 2.3x slower kernel). mbarrier objects in shared::cluster are coherent across the CTA pair.
-DGB_DEVICE void mbar_arrive_cluster(uint64_t* bar, uint32_t cta) {
-    asm volatile(
-        "{\n"
-        ".reg .b32 raddr;\n"
-        "mapa.shared::cluster.u32 raddr, %0, %1;\n"
-        "mbarrier.arrive.shared::cluster.b64 _, [raddr];\n"
-        "}\n" ::"r"(smem_u32(bar)),
-        "r"(cta)
-        : "memory");
+DGB_DEVICE void mbar_arrive_remote(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-DGB_DEVICE bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+DGB_DEVICE bool mbar_try_wait(uint32_t bar, uint32_t parity) {
     uint32_t done;
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, 0x989680;\n"   // hardware-suspended wait, bounded
         "selp.u32 %0, 1, 0, p;\n"
         "}\n"
         : "=r"(done)
-        : "r"(smem_u32(bar)), "r"(parity)
+        : "r"(bar), "r"(parity)
         : "memory");
     return done != 0;
 }
@@ -106,19 +105,19 @@ DGB_DEVICE uint64_t globaltimer_ns() {
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     return t;
 }
-DGB_DEVICE void spin_guard(uint32_t& spins, uint64_t& t0) {
-    if ((++spins & 0x3FFF) == 0) {
-        const uint64_t now = globaltimer_ns();
-        if (t0 == 0) t0 = now;
-        if (now - t0 > kSpinTimeoutNs) asm volatile("trap;");
-    }
-}
-DGB_DEVICE void mbar_wait(uint64_t* bar, uint32_t parity) {
+DGB_DEVICE void mbar_wait(uint32_t bar, uint32_t parity) {
     if (mbar_try_wait(bar, parity)) return;
     uint32_t spins = 0;
     uint64_t t0 = 0;
-    while (!mbar_try_wait(bar, parity)) spin_guard(spins, t0);
+    while (!mbar_try_wait(bar, parity)) {
+        if ((++spins & 0xFF) == 0) {
+            const uint64_t now = globaltimer_ns();
+            if (t0 == 0) t0 = now;
+            if (now - t0 > kSpinTimeoutNs) asm volatile("trap;");
+        }
+    }
 }
+
 // ---------------------------------------------------------------- proxies / fences
 DGB_DEVICE void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 DGB_DEVICE void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -134,24 +133,24 @@ DGB_DEVICE void prefetch_tensormap(const CUtensorMap* map) {
 }
 
 // 2-D tiled load: global (via tensor map) -> this CTA's shared memory, completion counted on `bar`.
-DGB_DEVICE void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* smem_dst, uint32_t c0, uint32_t c1,
+DGB_DEVICE void tma_load_2d(const CUtensorMap* map, uint32_t bar, uint32_t smem_dst, uint32_t c0, uint32_t c1,
                             uint64_t hint) {
     asm volatile(
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
-        " [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(smem_u32(smem_dst)),
-        "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "l"(hint)
+        " [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(smem_dst),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "l"(hint)
         : "memory");
 }
 
 // ---------------------------------------------------------------- tensor memory
 template <int kCtaGroup>
-DGB_DEVICE void tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {
+DGB_DEVICE void tmem_alloc(uint32_t smem_dst, uint32_t ncols) {
     if constexpr (kCtaGroup == 1)
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)),
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst),
                      "r"(ncols)
                      : "memory");
     else
-        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)),
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst),
                      "r"(ncols)
                      : "memory");
 }
@@ -206,15 +205,15 @@ DGB_DEVICE void mma_mxf8_block_scale(uint32_t tmem_d, uint64_t adesc, uint64_t b
 // Make all previously issued tcgen05 ops of this thread arrive on an mbarrier when they retire.
 // cta_group::2 form multicasts the arrival to the barrier at the same offset in both CTAs of the pair.
 template <int kCtaGroup>
-DGB_DEVICE void mma_commit(uint64_t* bar) {
+DGB_DEVICE void mma_commit(uint32_t bar) {
     if constexpr (kCtaGroup == 1) {
-        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
                      : "memory");
     } else {
         const uint16_t mask = 0b11;
         asm volatile(
             "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
-                smem_u32(bar)),
+                bar),
             "h"(mask)
             : "memory");
     }
@@ -258,12 +257,12 @@ DGB_DEVICE uint32_t idesc_with_sf_ids(uint32_t idesc, uint32_t a_sf_id, uint32_t
 }
 
 // ---------------------------------------------------------------- misc
-DGB_DEVICE void st_shared_v4(void* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
-    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(smem_u32(p)), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+DGB_DEVICE void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
-DGB_DEVICE uint32_t ld_shared_u32(const void* p) {
+DGB_DEVICE uint32_t ld_shared_u32(uint32_t addr) {
     uint32_t v;
-    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory");
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
     return v;
 }
 DGB_DEVICE void named_bar_sync(uint32_t id, uint32_t nthreads) {

@@ -4,8 +4,9 @@ by the reference's own SM100 kernel (tests/golden/gpu_golden.pt), and -- at BASE
 size-independent properties (linearity in the power-of-two scales, row/column permutation equivariance, zero rows).
 
 Tolerance: every e4m3 x e4m3 product and every UE8M0 scale is exact, so the only freedom versus the oracle is the
-FP32 accumulation order inside the tensor core. FP32 outputs: |d - oracle| <= 2^-20 * sum_k |a_k b_k| (a handful of
-FP32 roundings); BF16 outputs: at most 1 BF16 ulp on at most 1% of the elements, calc_diff < 1e-6 (the reference's own
+FP32 accumulation order inside the tensor core. FP32 outputs: |d - oracle| <= 1e-5 * max|oracle| (a handful of FP32
+roundings of the accumulator); BF16 outputs: differ on at most 1% of the elements, each by at most one BF16 rounding
+step of the value plus that FP32 noise, and calc_diff < 1e-6 (the reference's own
 test bound is 1e-3 against unquantised inputs, tests/test_fp8_fp4.py:53-55). Versus the reference's SM100 kernel on
 identical inputs the match is BITWISE (golden fixtures).
 """
@@ -50,9 +51,11 @@ def _assert_close_to_oracle(d, want, what=''):
     if d.dtype == torch.bfloat16:
         mism = d != want
         assert mism.float().mean() <= 0.01, f'{what}: {int(mism.sum())} mismatches'
-        # mismatches are single-ulp: neighbouring BF16 values
-        di, wi = d.view(torch.int16).int(), want.view(torch.int16).int()
-        assert (di - wi).abs().max() <= 1, what
+        # a mismatch is one BF16 rounding step of the value (2^-7 relative) plus FP32 accumulation noise, which is
+        # absolute (it scales with sum_k |a_k b_k|, not with the possibly cancelled result)
+        err = (d.float() - want.float()).abs()
+        tol = want.float().abs() * 2.0 ** -7 + 1e-5 * want.float().abs().max()
+        assert bool((err <= tol).all()), f'{what}: max excess {float((err - tol).max())}'
     else:
         scale = want.abs().max().clamp(min=1.0)
         assert ((d - want).abs().max() / scale) < 1e-5, what
