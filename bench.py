@@ -116,14 +116,17 @@ def run_dense(args, rank, world, device):
                 record[i][1].record()
 
     # ---- kernel-only (inputs resident) ------------------------------------------------------------
-    for _ in range(args.warmup):
-        step_kernel_only()
-    torch.cuda.synchronize()
-    barrier(world)
-    events = [[(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in probs]
-              for _ in range(args.steps)]
-    launches0 = _lib.launch_count()
+    # The clock sampler (a thread that forks nvidia-smi) starts before the warm-up so that its start-up noise and the
+    # GPU's idle->busy clock ramp fall outside the timed region.
     with ClockSampler(torch.cuda.current_device()) as clocks:
+        for _ in range(args.warmup):
+            step_kernel_only()
+        torch.cuda.synchronize()
+        barrier(world)
+        events = [[(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in probs]
+                  for _ in range(args.steps)]
+        launches0 = _lib.launch_count()
+        clocks.rows.clear()
         t_wall0 = time.perf_counter()
         for s in range(args.steps):
             step_kernel_only(events[s])
@@ -131,7 +134,8 @@ def run_dense(args, rank, world, device):
         t_wall = time.perf_counter() - t_wall0
     launches = _lib.launch_count() - launches0
     barrier(world)
-    per_shape_ms = [sum(e[i][0].elapsed_time(e[i][1]) for e in events) / args.steps for i in range(len(probs))]
+    per_step_ms = [[e[i][0].elapsed_time(e[i][1]) for i in range(len(probs))] for e in events]
+    per_shape_ms = [sum(st[i] for st in per_step_ms) / args.steps for i in range(len(probs))]
     step_ms = sum(per_shape_ms)
     step_ms = allreduce_max(step_ms, world, device)
     flops = sum(2.0 * p['m'] * p['n'] * p['k'] for p in probs)
@@ -207,6 +211,7 @@ def run_dense(args, rank, world, device):
         'e2e': {'value': round(e2e_value, 3), 'unit': 'TFLOPS', 'ms_per_step': round(e2e_ms, 4),
                 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h)},
         'gpu_launches': int(launches), 'wall_ms_per_step_incl_flush': round(t_wall * 1e3 / args.steps, 3),
+        'per_step_us': [[round(x * 1e3, 1) for x in st] for st in per_step_ms[:8]],
     }
     return out
 

@@ -36,7 +36,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
 
 class _Config(ctypes.Structure):
-    _fields_ = [(n, ctypes.c_int) for n in ('block_m', 'cluster', 'num_stages', 'num_sms', 'smem_bytes', 'num_tiles')]
+    _fields_ = [(n, ctypes.c_int) for n in ('block_m', 'cluster', 'num_stages', 'num_sms', 'smem_bytes', 'num_tiles',
+                                            'num_splits')]
 
 
 _P, _I, _L = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64
@@ -58,13 +59,15 @@ SIGNATURES = {
     'dgb200_pack_sf_ue8m0': (_I, [_P, _P, _I, _I, _I, _I, _L, _L, _L, _P, _I, _I, _P]),
     'dgb200_transpose_sf_fp32': (_I, [_P, _P, _I, _I, _I, _L, _L, _L, _P]),
     'dgb200_pack_sf_ue8m0_k_grouped': (_I, [_P, _P, _I, _P, _I, _I, _P]),
-    'dgb200_fp8_gemm_nt': (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _L, _L, _L, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
+    'dgb200_fp8_gemm_nt': (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _L, _L, _L, _I, _I, _I, _I, _I, _I, _I, _I, _P, _L, _P]),
+    'dgb200_workspace_bytes': (_L, [_I, _I]),
     'dgb200_m_grouped_fp8_gemm_nt_contiguous': (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _L, _L, _L, _I, _I, _I,
                                                      _I, _I, _I, _I, _I, _P]),
     'dgb200_m_grouped_fp8_gemm_nt_masked': (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
     'dgb200_k_grouped_fp8_gemm_tn_contiguous': (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
     'dgb200_plan': (_I, [_I, _I, _I, _I, _I, _I, _I, _I, ctypes.POINTER(_Config)]),
     'dgb200_last_config': (_I, [ctypes.POINTER(_Config)]),
+    'dgb200_debug_set_timestamps': (_I, [_P]),
     'dgb200_launch_count': (_L, []),
 }
 

@@ -29,8 +29,9 @@ namespace {
 
 // ------------------------------------------------------------------------------------------------ errors
 thread_local std::string g_last_error;
-thread_local dgb200_config g_last_config = {0, 0, 0, 0, 0, 0};
+thread_local dgb200_config g_last_config = {0, 0, 0, 0, 0, 0, 0};
 std::atomic<int64_t> g_launch_count{0};
+std::atomic<long long*> g_debug_ts{nullptr};
 
 int fail(int code, const char* fmt, ...) {
     char buf[1024];
@@ -171,9 +172,11 @@ struct Problem {
     int expected_m;    // rows per group the caller expects (== m for dense)
     int n, k, groups;
     int alignment;     // contiguous layouts: group start alignment
+    int max_splits = 1;  // > 1 only for dense problems whose caller supplied a split-K workspace
 };
 struct Config {
     int block_m, cluster, stages, num_sms, smem_bytes, swizzle_group;
+    int num_splits, kb_per_split;   // split-K (dense, small problems): K cut into num_splits ranges
 };
 
 constexpr int kSmemCapacity = 232448;  // 227 KB usable per CTA on sm_100 (heuristics/sm100.hpp:15)
@@ -190,12 +193,16 @@ int smem_bytes_for(int block_m, int cluster, int stages) {
 //   L2          : all busy CTAs together pull at most ~kL2Rate B/cycle
 //   HBM         : bytes that are new to the chip in this step (weight tiles are shared by the m-blocks in flight,
 //                 token tiles by the n-units in flight) at ~kHbmRate B/cycle
-constexpr double kSmIngest = 56.0, kL2Rate = 8000.0, kHbmRate = 3400.0, kTileOverhead = 1500.0;
+constexpr double kSmIngest = 45.0, kL2Rate = 8000.0, kHbmRate = 3400.0, kTileOverhead = 1500.0, kSplitOverhead = 2500.0;
+constexpr int kMaxSplits = 8;
+constexpr int kSplitKCounters = 4096;                 // ints at the start of the workspace
+constexpr size_t kSplitKHeaderBytes = kSplitKCounters * sizeof(int);
 
-double estimate_cycles(const Problem& pb, int block_m, int cluster, int num_sms) {
+double estimate_cycles(const Problem& pb, int block_m, int cluster_total, int num_sms, int splits) {
+    const int cluster = std::min(cluster_total, 2);
     const int num_units = num_sms / cluster;
     const int n_units = ceil_div(pb.n, (int)kBlockN * cluster);
-    const int num_kb = ceil_div(pb.k, (int)kBlockK);
+    const int num_kb = ceil_div(ceil_div(pb.k, (int)kBlockK), splits);
     int m_blocks;  // m-blocks that share one weight panel
     double tiles;
     if (pb.type == kMMasked) {
@@ -203,7 +210,7 @@ double estimate_cycles(const Problem& pb, int block_m, int cluster, int num_sms)
         tiles = (double)pb.groups * m_blocks * n_units;
     } else if (pb.type == kDense) {
         m_blocks = ceil_div(pb.m, block_m);
-        tiles = (double)m_blocks * n_units;
+        tiles = (double)m_blocks * n_units * splits;
     } else {
         m_blocks = ceil_div(std::max(pb.expected_m, 1), block_m);
         tiles = (double)ceil_div(pb.m, block_m) * n_units;
@@ -212,23 +219,22 @@ double estimate_cycles(const Problem& pb, int block_m, int cluster, int num_sms)
     const double busy_units = std::min<double>(tiles, num_units);
     const double busy_ctas = busy_units * cluster;
     const double cta_bytes = (128.0 + (double)block_m / cluster) * kBlockK;
-    const double distinct_n = std::min<double>(n_units, busy_units);
+    const double distinct_n = std::min<double>((double)n_units * splits, busy_units);   // distinct weight panels in flight
     const double distinct_m = std::max(1.0, busy_units / distinct_n);
     const double shared_m = std::min<double>(distinct_m, m_blocks);  // m-blocks in flight that reuse a weight tile
     const double new_bytes = (busy_ctas * 128.0 / shared_m + distinct_m * block_m) * kBlockK;
     const double step = std::max(std::max(2.0 * block_m, cta_bytes / kSmIngest),
                                  std::max(busy_ctas * cta_bytes / kL2Rate, new_bytes / kHbmRate));
-    return waves * (num_kb * step + kTileOverhead + 6.0 * block_m);
+    return waves * (num_kb * step + kTileOverhead + 6.0 * block_m) + (splits > 1 ? kSplitOverhead : 0.0);
 }
 
 Config choose_config(const Problem& pb, int num_sms_override = 0) {
     Config c{};
     c.num_sms = num_sms_override > 0 ? (num_sms_override & ~1) : effective_num_sms();
     c.cluster = c.num_sms >= 2 ? 2 : 1;
+    if (int v = env_int("DGB200_CLUSTER", 0)) c.cluster = v;
     std::vector<int> candidates;
-    if (pb.type == kDense) {
-        for (int bm = 16; bm <= (int)kMaxBlockM; bm += 16) candidates.push_back(bm);
-    } else if (pb.type == kMMasked) {
+    if (pb.type == kDense || pb.type == kMMasked) {
         for (int bm = 16; bm <= (int)kMaxBlockM; bm += 16) candidates.push_back(bm);
     } else {
         // a tile must not straddle two groups: block_m has to divide the group alignment
@@ -236,24 +242,38 @@ Config choose_config(const Problem& pb, int num_sms_override = 0) {
             if (pb.alignment % bm == 0) candidates.push_back(bm);
         if (candidates.empty()) candidates.push_back(16);
     }
+    const int num_kb = ceil_div(pb.k, (int)kBlockK);
+    const int max_splits = std::min({pb.max_splits, kMaxSplits, std::max(1, num_kb / 4)});
     double best = 1e300;
     c.block_m = candidates[0];
+    c.num_splits = 1;
     for (int bm : candidates) {
-        if (pb.type == kDense && bm - 16 >= align_up(pb.m, 16)) continue;  // taller than the whole problem
-        if (pb.type == kMMasked && bm - 16 >= align_up(pb.m, 16)) continue;
-        const double t = estimate_cycles(pb, bm, c.cluster, c.num_sms);
-        if (t < best * 0.999) best = t, c.block_m = bm;  // ties -> smaller tile (finer tail)
+        if ((pb.type == kDense || pb.type == kMMasked) && bm - 16 >= align_up(pb.m, 16)) continue;  // taller than the problem
+        for (int sp = 1; sp <= max_splits; ++sp) {
+            if (sp > 1) {
+                // split-K only pays for very small problems: the finalising pass costs ~3 us (measured), so it is used
+                // when a handful of short tiles would otherwise leave most SMs idle (e.g. M=1, N=2112: 15 -> 10.8 us)
+                if (c.cluster > 2 || bm > 32) break;
+                if (ceil_div(pb.m, bm) * ceil_div(pb.n, (int)kBlockN * c.cluster) * 4 > c.num_sms / c.cluster) break;
+                const int tiles = ceil_div(pb.m, bm) * ceil_div(pb.n, (int)kBlockN * c.cluster);
+                if (tiles * sp > c.num_sms / c.cluster) break;
+                if (ceil_div(num_kb, sp) * (sp - 1) >= num_kb) continue;    // an empty slice
+            }
+            const double t = estimate_cycles(pb, bm, c.cluster, c.num_sms, sp);
+            if (t < best * 0.999) best = t, c.block_m = bm, c.num_splits = sp;  // ties -> smaller tile, fewer slices
+        }
     }
     if (int v = env_int("DGB200_BLOCK_M", 0)) c.block_m = v;
-    if (int v = env_int("DGB200_CLUSTER", 0)) c.cluster = v;
-    const int num_kb = ceil_div(pb.k, (int)kBlockK);
-    int stages = (kSmemCapacity - 64) / stage_bytes(c.block_m, c.cluster);
-    while (stages > 1 && smem_bytes_for(c.block_m, c.cluster, stages) > kSmemCapacity) --stages;
+    if (const char* v = getenv("DGB200_SPLITS")) c.num_splits = std::max(1, std::min(atoi(v), max_splits));
+    c.kb_per_split = ceil_div(num_kb, c.num_splits);
+    c.num_splits = ceil_div(num_kb, c.kb_per_split);
+    const int cta_group = std::min(c.cluster, 2);
+    int stages = (kSmemCapacity - 64) / stage_bytes(c.block_m, cta_group);
+    while (stages > 1 && smem_bytes_for(c.block_m, cta_group, stages) > kSmemCapacity) --stages;
     stages = std::min(stages, 32);
-    (void)num_kb;
     if (int v = env_int("DGB200_STAGES", 0)) stages = std::min(v, stages);
     c.stages = std::max(stages, 1);
-    c.smem_bytes = smem_bytes_for(c.block_m, c.cluster, c.stages);
+    c.smem_bytes = smem_bytes_for(c.block_m, cta_group, c.stages);
     c.swizzle_group = env_int("DGB200_SWIZZLE_GROUP", 8);
     return c;
 }
@@ -274,6 +294,8 @@ struct GemmCall {
     int gran_k_a, gran_k_b;
     int d_dtype, accumulate;
     int expected_m, alignment, zero_padding;
+    void* workspace;
+    size_t workspace_bytes;
     cudaStream_t stream;
 };
 
@@ -293,7 +315,7 @@ int launch_kernel(Kernel kernel, const Config& cfg, cudaStream_t stream, const C
         }
     }
     cudaLaunchConfig_t lc{};
-    lc.gridDim = dim3(cfg.num_sms, 1, 1);
+    lc.gridDim = dim3(cfg.num_sms / cfg.cluster * cfg.cluster, 1, 1);
     lc.blockDim = dim3(kNumThreads, 1, 1);
     lc.dynamicSmemBytes = cfg.smem_bytes;
     lc.stream = stream;
@@ -305,6 +327,22 @@ int launch_kernel(Kernel kernel, const Config& cfg, cudaStream_t stream, const C
         attrs[na].val.clusterDim.y = 1;
         attrs[na].val.clusterDim.z = 1;
         ++na;
+    }
+    if (cfg.cluster > 2) {
+        // 4/8-CTA clusters must sit inside one GPC: ask how many fit at once and size the persistent grid to that
+        static std::mutex occ_mu;
+        static std::unordered_map<const void*, int> resident;   // kernel (x cluster size, implied) -> clusters
+        std::lock_guard<std::mutex> lock(occ_mu);
+        auto it = resident.find(reinterpret_cast<const void*>(kernel));
+        if (it == resident.end()) {
+            lc.attrs = attrs, lc.numAttrs = na;
+            int n = 0;
+            cudaError_t e = cudaOccupancyMaxActiveClusters(&n, kernel, &lc);
+            if (e != cudaSuccess || n <= 0) n = cfg.num_sms / cfg.cluster;
+            it = resident.emplace(reinterpret_cast<const void*>(kernel), n).first;
+        }
+        const int clusters = std::min(it->second, cfg.num_sms / cfg.cluster);
+        lc.gridDim = dim3(clusters * cfg.cluster, 1, 1);
     }
     if (rt().pdl) {
         attrs[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -334,8 +372,13 @@ int dispatch_out(const GemmCall& c, const Config& cfg, const CUtensorMap& mx, co
 template <int kType>
 int dispatch_cluster(const GemmCall& c, const Config& cfg, const CUtensorMap& mx, const CUtensorMap& mw,
                      const CUtensorMap& msfx, const CUtensorMap& msfw, const GemmParams& p) {
+    if constexpr (kType == kDense) {
+        if (cfg.cluster == 8) return dispatch_out<kType, 8>(c, cfg, mx, mw, msfx, msfw, p);
+        if (cfg.cluster == 4) return dispatch_out<kType, 4>(c, cfg, mx, mw, msfx, msfw, p);
+    }
     if (cfg.cluster == 2) return dispatch_out<kType, 2>(c, cfg, mx, mw, msfx, msfw, p);
-    return dispatch_out<kType, 1>(c, cfg, mx, mw, msfx, msfw, p);
+    if (cfg.cluster == 1) return dispatch_out<kType, 1>(c, cfg, mx, mw, msfx, msfw, p);
+    return fail(DGB200_ERR_INVALID_ARGUMENT, "unsupported cluster size %d for gemm type %d", cfg.cluster, (int)kType);
 }
 
 int run_gemm(const GemmCall& c) {
@@ -348,9 +391,18 @@ int run_gemm(const GemmCall& c) {
     DGB_REQUIRE(c.sfa_stride % 4 == 0 && c.sfb_stride % 4 == 0);
 
     Problem pb{c.type, c.m, c.expected_m, c.n, c.k, c.groups, c.alignment};
-    const Config cfg = choose_config(pb);
+    // split-K needs scratch: [4096 arrival counters][num_splits x m x n fp32 partial tiles]
+    if (c.type == kDense && c.workspace != nullptr && c.n % 4 == 0 && c.workspace_bytes > kSplitKHeaderBytes &&
+        (reinterpret_cast<uintptr_t>(c.workspace) & 15) == 0) {
+        const size_t per_split = static_cast<size_t>(c.m) * c.n * sizeof(float);
+        pb.max_splits = static_cast<int>(std::min<size_t>(kMaxSplits, (c.workspace_bytes - kSplitKHeaderBytes) / per_split));
+    }
+    Config cfg = choose_config(pb);
+    if (cfg.num_splits > 1 && ceil_div(c.m, cfg.block_m) * ceil_div(c.n, (int)kBlockN) > kSplitKCounters)
+        cfg.num_splits = 1, cfg.kb_per_split = ceil_div(c.k, (int)kBlockK);
     DGB_REQUIRE(cfg.block_m % 16 == 0 && cfg.block_m >= 16 && cfg.block_m <= (int)kMaxBlockM);
-    DGB_REQUIRE(cfg.cluster == 1 || cfg.cluster == 2);
+    DGB_REQUIRE(cfg.cluster == 1 || cfg.cluster == 2 || (c.type == kDense && (cfg.cluster == 4 || cfg.cluster == 8)));
+    DGB_REQUIRE(cfg.cluster <= 2 || cfg.num_splits == 1);
     if (c.type == kMContiguous || c.type == kMContiguousPsum) DGB_REQUIRE(c.alignment % cfg.block_m == 0);
 
     const int num_kp_a = ceil_div(c.k, c.gran_k_a * 4), num_kp_b = ceil_div(c.k, c.gran_k_b * 4);
@@ -359,9 +411,10 @@ int run_gemm(const GemmCall& c) {
 
     CUtensorMap mx, mw, msfx, msfw;
     if (int e = make_map_2d(&mx, c.a, CU_TENSOR_MAP_DATA_TYPE_UINT8, c.k, c.a_rows, c.lda, kBlockK,
-                            cfg.block_m / cfg.cluster, CU_TENSOR_MAP_SWIZZLE_128B)) return e;
+                            cfg.block_m / std::min(cfg.cluster, 2), CU_TENSOR_MAP_SWIZZLE_128B)) return e;
+    const int cta_group = cfg.cluster >= 2 ? 2 : 1, pairs = cfg.cluster >= 2 ? cfg.cluster / 2 : 1;
     if (int e = make_map_2d(&mw, c.b, CU_TENSOR_MAP_DATA_TYPE_UINT8, c.k, (uint64_t)c.n * b_groups, c.ldb, kBlockK,
-                            kBlockN, CU_TENSOR_MAP_SWIZZLE_128B)) return e;
+                            kBlockN / pairs, CU_TENSOR_MAP_SWIZZLE_128B)) return e;
     if (int e = make_map_2d(&msfx, c.sfa, CU_TENSOR_MAP_DATA_TYPE_INT32, c.sfa_cols, (uint64_t)num_kp_a * sfa_groups,
                             (uint64_t)c.sfa_stride * 4, cfg.block_m, 1, CU_TENSOR_MAP_SWIZZLE_NONE)) return e;
     if (int e = make_map_2d(&msfw, c.sfb, CU_TENSOR_MAP_DATA_TYPE_INT32, c.sfb_cols, (uint64_t)num_kp_b * b_groups,
@@ -379,15 +432,20 @@ int run_gemm(const GemmCall& c) {
     p.sf_shift_x = c.gran_k_a == 128 ? 2 : 0;
     p.sf_shift_w = c.gran_k_b == 128 ? 2 : 0;
     p.swizzle_group = std::max(1, cfg.swizzle_group);
-    p.num_n_units = ceil_div(c.n, (int)kBlockN * cfg.cluster);
+    p.num_splits = cfg.num_splits;
+    p.kb_per_split = cfg.kb_per_split;
+    p.splitk_counters = cfg.num_splits > 1 ? static_cast<int*>(c.workspace) : nullptr;
+    p.splitk_ws = cfg.num_splits > 1 ? reinterpret_cast<float*>(static_cast<char*>(c.workspace) + kSplitKHeaderBytes) : nullptr;
+    p.debug_ts = g_debug_ts.load();
+    p.num_n_units = ceil_div(c.n, (int)kBlockN * cta_group);
     p.num_m_blocks = ceil_div(c.m, cfg.block_m);
     p.m_alignment = std::max(1, c.alignment);
     p.zero_padding = c.zero_padding;
 
-    g_last_config = dgb200_config{cfg.block_m, cfg.cluster, cfg.stages, cfg.num_sms, cfg.smem_bytes, 0};
+    g_last_config = dgb200_config{cfg.block_m, cfg.cluster, cfg.stages, cfg.num_sms, cfg.smem_bytes, 0, cfg.num_splits};
     if (env_int("DGB200_PRINT_CONFIGS", 0))
-        fprintf(stderr, "dgb200 config: type=%d m=%d n=%d k=%d groups=%d -> block_m=%d cluster=%d stages=%d sms=%d smem=%d\n",
-                c.type, c.m, c.n, c.k, c.groups, cfg.block_m, cfg.cluster, cfg.stages, cfg.num_sms, cfg.smem_bytes);
+        fprintf(stderr, "dgb200 config: type=%d m=%d n=%d k=%d groups=%d -> block_m=%d cluster=%d stages=%d sms=%d smem=%d splits=%d\n",
+                c.type, c.m, c.n, c.k, c.groups, cfg.block_m, cfg.cluster, cfg.stages, cfg.num_sms, cfg.smem_bytes, cfg.num_splits);
 
     switch (c.type) {
         case kDense: return dispatch_cluster<kDense>(c, cfg, mx, mw, msfx, msfw, p);
@@ -495,7 +553,8 @@ int dgb200_pack_sf_ue8m0_k_grouped(const float* sf, int32_t* out, int mn, const 
 
 int dgb200_fp8_gemm_nt(const void* a, const int32_t* sfa, const void* b, const int32_t* sfb, void* d, int m, int n,
                        int k, int64_t lda, int64_t ldb, int64_t ldd, int major_a, int major_b, int sfa_stride,
-                       int sfb_stride, int gran_k_a, int gran_k_b, int d_dtype, int accumulate, void* stream) {
+                       int sfb_stride, int gran_k_a, int gran_k_b, int d_dtype, int accumulate, void* workspace,
+                       int64_t workspace_bytes, void* stream) {
     DGB_REQUIRE(m >= 0 && n >= 0 && k >= 0);
     if (m == 0 || n == 0) return DGB200_OK;  // gemm.hpp:22-23
     DGB_REQUIRE(k > 0);                      // k == 0 (D = C or 0) is handled by the host wrapper, gemm.hpp:36-40
@@ -514,6 +573,7 @@ int dgb200_fp8_gemm_nt(const void* a, const int32_t* sfa, const void* b, const i
     c.gran_k_a = gran_k_a, c.gran_k_b = gran_k_b;
     c.d_dtype = d_dtype, c.accumulate = accumulate != 0;
     c.expected_m = m, c.alignment = 1, c.zero_padding = 0;
+    c.workspace = workspace, c.workspace_bytes = workspace_bytes > 0 ? static_cast<size_t>(workspace_bytes) : 0;
     c.stream = static_cast<cudaStream_t>(stream);
     return run_gemm(c);
 }
@@ -581,11 +641,23 @@ int dgb200_plan(int gemm_type, int m, int n, int k, int num_groups, int expected
     DGB_REQUIRE(gemm_type >= kDense && gemm_type <= kMContiguousPsum);
     DGB_REQUIRE(m > 0 && n > 0 && k > 0 && num_groups > 0);
     Problem pb{gemm_type, m, expected_m > 0 ? expected_m : m, n, k, num_groups, std::max(alignment, 1)};
+    if (gemm_type == kDense && n % 4 == 0) pb.max_splits = kMaxSplits;   // as if a workspace were supplied
     const Config cfg = choose_config(pb, num_sms);
-    const int n_units = ceil_div(n, (int)kBlockN * cfg.cluster);
+    const int n_units = ceil_div(n, (int)kBlockN * std::min(cfg.cluster, 2));
     const int m_blocks = gemm_type == kMMasked ? num_groups * ceil_div(pb.expected_m, cfg.block_m) : ceil_div(m, cfg.block_m);
-    *out = dgb200_config{cfg.block_m, cfg.cluster, cfg.stages, cfg.num_sms, cfg.smem_bytes, m_blocks * n_units};
+    *out = dgb200_config{cfg.block_m, cfg.cluster, cfg.stages, cfg.num_sms, cfg.smem_bytes, m_blocks * n_units * cfg.num_splits,
+                         cfg.num_splits};
     return DGB200_OK;
+}
+
+int dgb200_debug_set_timestamps(void* device_int64_buffer) {
+    g_debug_ts.store(static_cast<long long*>(device_int64_buffer));
+    return DGB200_OK;
+}
+
+int64_t dgb200_workspace_bytes(int m, int n) {
+    if (m <= 0 || n <= 0) return 0;
+    return static_cast<int64_t>(kSplitKHeaderBytes) + static_cast<int64_t>(kMaxSplits) * m * n * sizeof(float);
 }
 
 int dgb200_last_config(dgb200_config* out) {

@@ -62,6 +62,11 @@ struct GemmParams {
     uint32_t sf_shift_x;        // log2(k-blocks covered by one packed SF word): 2 (gran_k 128) or 0 (gran_k 32)
     uint32_t sf_shift_w;
     uint32_t swizzle_group;     // L2 tile-order group width (in n-units)
+    float* splitk_ws;           // split-K: fp32 partial tiles [num_splits][m][n]   (dense only, else nullptr)
+    int* splitk_counters;       // split-K: one arrival counter per (m-block, 128-column block), zero between launches
+    uint32_t num_splits;        // K is cut into this many ranges of `kb_per_split` k-blocks (1 = no split)
+    uint32_t kb_per_split;
+    long long* debug_ts;        // optional (development): CTA 0 stamps clock64() at 10 points of its life
     uint32_t num_n_units;       // ceil(n / (128 * cluster))
     uint32_t num_m_blocks;      // dense / contiguous: ceil(m / block_m)
     uint32_t m_alignment;       // contiguous layouts: group start alignment
@@ -80,10 +85,17 @@ struct Tile {
     uint32_t n0;        // first output column of THIS CTA
     uint32_t valid_m;   // rows [0, valid_m) of the tile are real outputs
     uint32_t store_m;   // rows [0, store_m) are written (>= valid_m only when zero padding is requested)
+    uint32_t kb_begin, kb_end;  // k-blocks this tile accumulates (a sub-range only under split-K)
+    uint32_t split;             // split-K slice index
+    uint32_t counter_idx;       // split-K arrival counter of this CTA's output block
 };
 
+// kCluster = CTAs per cluster: 1 (single CTA MMA), 2 (one cta_group::2 pair) or 4 / 8 (2 / 4 pairs that work on
+// consecutive m-blocks of the SAME weight panel and share its TMA loads by multicast; dense only).
 template <int kGemmType, int kCluster>
 struct Scheduler {
+    static constexpr uint32_t kPairs = kCluster >= 2 ? kCluster / 2 : 1;
+    static constexpr uint32_t kCtaGroup = kCluster >= 2 ? 2 : 1;
     const GemmParams& p;
     uint32_t cta_rank, cluster_id, num_clusters;
     uint32_t num_n_units;
@@ -102,27 +114,42 @@ struct Scheduler {
     __device__ void split(uint32_t local, uint32_t num_m, uint32_t& m_blk, uint32_t& n_unit) const {
         const uint32_t gw = p.swizzle_group;
         const uint32_t per_group = gw * num_m;
-        const uint32_t grp = local / per_group;
+        const uint32_t grp = local < per_group ? 0u : local / per_group;     // (integer division is ~25 instructions)
         const uint32_t first = grp * gw;
         const uint32_t in = local - grp * per_group;
         const uint32_t width = min(gw, num_n_units - first);
-        m_blk = in / width;
+        m_blk = in < width ? 0u : in / width;
         n_unit = first + in - m_blk * width;
     }
 
     __device__ bool next(Tile& t) {
         const uint32_t idx = cluster_id + (iter++) * num_clusters;
         uint32_t m_blk, n_unit, group = 0;
+        const uint32_t num_kb_total = (p.k + kBlockK - 1) / kBlockK;
+        t.kb_begin = 0, t.kb_end = num_kb_total, t.split = 0, t.counter_idx = 0;
         if constexpr (kGemmType == kDense || kGemmType == kMContiguous) {
-            const uint32_t num_m = p.num_m_blocks;
-            if (idx >= num_m * num_n_units) return false;
-            split(idx, num_m, m_blk, n_unit);
+            const uint32_t num_m = (p.num_m_blocks + kPairs - 1) / kPairs;   // m-blocks are handed out kPairs at a time
+            uint32_t local = idx;
+            if (kGemmType == kDense && p.num_splits > 1) {
+                // split-K: slice index varies slowest, so the CTAs of one slice stream disjoint weight panels
+                const uint32_t per_split = num_m * num_n_units;
+                if (idx >= per_split * p.num_splits) return false;
+                t.split = idx / per_split;
+                local = idx - t.split * per_split;
+                t.kb_begin = t.split * p.kb_per_split;
+                t.kb_end = min(num_kb_total, t.kb_begin + p.kb_per_split);
+            } else if (idx >= num_m * num_n_units) {
+                return false;
+            }
+            split(local, num_m, m_blk, n_unit);
+            m_blk = m_blk * kPairs + (cta_rank >> 1);                        // this pair's m-block inside the group
             t.x_row = m_blk * p.block_m;
             t.d_row = t.x_row;
             t.sfx_col = t.x_row;
             t.sfx_row = 0;
-            t.valid_m = min(p.block_m, p.m - t.x_row);
+            t.valid_m = t.x_row < p.m ? min(p.block_m, p.m - t.x_row) : 0u;  // 0: a pair past the last m-block idles along
             t.store_m = t.valid_m;
+            t.counter_idx = m_blk * (num_n_units * kCtaGroup) + n_unit * kCtaGroup + (cta_rank & 1);
             if constexpr (kGemmType == kMContiguous) group = static_cast<uint32_t>(max(0, __ldg(p.grouped_layout + t.x_row)));
         } else if constexpr (kGemmType == kMMasked) {
             uint32_t num_m;
@@ -166,7 +193,7 @@ struct Scheduler {
             t.valid_m = t.x_row < row_end ? min(p.block_m, row_end - t.x_row) : 0u;   // 0: a pure padding tile
             t.store_m = min(p.block_m, cover_end - t.x_row);
         }
-        t.n0 = (n_unit * kCluster + cta_rank) * kBlockN;
+        t.n0 = (n_unit * kCtaGroup + (cta_rank & 1)) * kBlockN;
         t.w_row = group * p.n + t.n0;
         t.sfw_col = t.n0;
         t.sfw_row = group * p.num_kp_w;
@@ -213,6 +240,40 @@ __host__ __device__ constexpr uint32_t slot_bytes(uint32_t block_m, uint32_t clu
     return (kWTileBytes + (block_m / cluster) * kBlockK + 512 + ((block_m + 127) / 128) * 512 + 1023) / 1024 * 1024;
 }
 
+// Split-K finalisation by the last slice to arrive: D rows = sum over slices (in slice order) of the FP32 partials.
+// All kRows x kSplits 16-byte loads of a batch are issued before the first add, so a batch costs one L2 round trip.
+template <uint32_t kSplits, uint32_t kRows, typename out_t, bool kAccumulate>
+__device__ __forceinline__ void splitk_finalize(const float* ws, size_t slice_elems, uint32_t n, out_t* d, uint32_t ld_d,
+                                                uint32_t row0, uint32_t valid_m, uint32_t nc, uint32_t warp, uint32_t num_warps) {
+    for (uint32_t r0 = warp * kRows; r0 < valid_m; r0 += num_warps * kRows) {
+        float4 x[kRows][kSplits];
+        const float* src = ws + static_cast<size_t>(row0 + r0) * n + nc;
+#pragma unroll
+        for (uint32_t i = 0; i < kRows; ++i)
+#pragma unroll
+            for (uint32_t sl = 0; sl < kSplits; ++sl)
+                x[i][sl] = r0 + i < valid_m ? __ldcg(reinterpret_cast<const float4*>(src + static_cast<size_t>(i) * n + sl * slice_elems))
+                                            : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (uint32_t i = 0; i < kRows; ++i) {
+            if (r0 + i >= valid_m) break;
+            float4 acc = x[i][0];
+#pragma unroll
+            for (uint32_t sl = 1; sl < kSplits; ++sl) acc.x += x[i][sl].x, acc.y += x[i][sl].y, acc.z += x[i][sl].z, acc.w += x[i][sl].w;
+            out_t* dst = d + static_cast<size_t>(row0 + r0 + i) * ld_d + nc;
+            store_out<out_t>(dst + 0, acc.x, kAccumulate);
+            store_out<out_t>(dst + 1, acc.y, kAccumulate);
+            store_out<out_t>(dst + 2, acc.z, kAccumulate);
+            store_out<out_t>(dst + 3, acc.w, kAccumulate);
+        }
+    }
+}
+
+#define DGB_STAMP(i)                                                            \
+    do {                                                                        \
+        if (p.debug_ts != nullptr && blockIdx.x == 0) p.debug_ts[i] = clock64(); \
+    } while (0)
+
 template <int kGemmType, int kCluster, typename out_t, bool kAccumulate>
 __global__ void __launch_bounds__(kNumThreads, 1)
 fp8_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
@@ -224,15 +285,20 @@ fp8_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
 
     const uint32_t warp_idx = __shfl_sync(0xffffffffu, threadIdx.x / 32, 0);
     const uint32_t lane = lane_id();
+    if (threadIdx.x == 0) DGB_STAMP(0);
+    if (threadIdx.x == 0 && p.debug_ts != nullptr) p.debug_ts[16 + 2 * blockIdx.x] = globaltimer_ns();   // per-CTA entry
+    constexpr int kCtaGroup = kCluster >= 2 ? 2 : 1;          // CTAs per UMMA (cta_group)
+    constexpr uint32_t kPairs = kCluster >= 2 ? kCluster / 2 : 1;   // CTA pairs per cluster (share the weight loads)
     const uint32_t cta_rank = kCluster == 1 ? 0u : cluster_ctarank();
-    const bool is_leader = cta_rank == 0;
+    const uint32_t pair_idx = cta_rank >> 1, leader_rank = cta_rank & ~1u;
+    const bool is_leader = (cta_rank & 1) == 0;
 
     // ---- shared memory carve-up (all sizes are runtime values), as 32-bit shared::cta addresses
     const uint32_t num_stages = p.num_stages;
-    const uint32_t load_m = p.block_m / kCluster;                           // token rows this CTA loads per stage
+    const uint32_t load_m = p.block_m / kCtaGroup;                          // token rows this CTA loads per stage
     const uint32_t x_tile_bytes = load_m * kBlockK;                         // multiple of 1024 (load_m % 8 == 0)
     const uint32_t num_sfx_groups = (p.block_m + 127) / 128;                // 128-row UTCCP groups of token SFs
-    const uint32_t slot_stride = slot_bytes(p.block_m, kCluster);
+    const uint32_t slot_stride = slot_bytes(p.block_m, kCtaGroup);
     const uint32_t smem_base = smem_u32(smem);
     const uint32_t off_x = kWTileBytes, off_sfw = off_x + x_tile_bytes, off_sfx = off_sfw + 512;
     const uint32_t bars = smem_base + num_stages * slot_stride;
@@ -242,31 +308,32 @@ fp8_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
     const uint32_t tmem_full_bar = bars + num_stages * 24;     // [2] accumulator complete (per CTA, via commit)
     const uint32_t tmem_empty_bar = tmem_full_bar + 16;        // [2] accumulator drained by all epilogue threads (leader)
     const uint32_t tmem_ptr_smem = tmem_empty_bar + 16;
+    const uint32_t splitk_flag_smem = tmem_ptr_smem + 4;
 
+    // Setup, arranged so that the independent pieces overlap: the first cluster barrier (both CTAs of a pair must be
+    // resident before a cta_group::2 TMEM allocation) is split-phase around the barrier initialisation, which is
+    // spread over the lanes of warp 1; warp 2 allocates tensor memory as soon as the cluster is known to be up.
+    if constexpr (kCluster > 1) cluster_arrive_relaxed();
     if (warp_idx == 0 && elect_one()) {
         prefetch_tensormap(&map_x);
         prefetch_tensormap(&map_w);
         prefetch_tensormap(&map_sfx);
         prefetch_tensormap(&map_sfw);
     }
-    if (warp_idx == 1 && elect_one()) {
-        for (uint32_t i = 0; i < num_stages; ++i) {
+    if (warp_idx == 1) {
+        for (uint32_t i = lane; i < num_stages; i += 32) {
             mbar_init(full_bar + i * 8, 1);
-            mbar_init(empty_bar + i * 8, 1);
-            mbar_init(ready_bar + i * 8, 32 * kCluster);
+            mbar_init(empty_bar + i * 8, kPairs);      // one commit per pair: peers multicast weights into this slot too
+            mbar_init(ready_bar + i * 8, 32 * kCtaGroup);
         }
-        for (uint32_t i = 0; i < 2; ++i) {
-            mbar_init(tmem_full_bar + i * 8, 1);
-            mbar_init(tmem_empty_bar + i * 8, kNumEpilogueThreads * kCluster);
+        if (lane < 2) {
+            mbar_init(tmem_full_bar + lane * 8, 1);
+            mbar_init(tmem_empty_bar + lane * 8, kNumEpilogueThreads * kCtaGroup);
         }
         fence_mbar_init();
     }
-    if constexpr (kCluster > 1) {
-        // Both CTAs must be resident before a cta_group::2 allocation
-        cluster_arrive_relaxed();
-        cluster_wait();
-    }
-    if (warp_idx == 2) tmem_alloc<kCluster>(tmem_ptr_smem, kTmemCols);
+    if constexpr (kCluster > 1) cluster_wait();
+    if (warp_idx == 2) tmem_alloc<kCtaGroup>(tmem_ptr_smem, kTmemCols);
     tcgen05_fence_before();
     if constexpr (kCluster > 1) {
         // relaxed arrive: `fence.mbarrier_init.release.cluster` above already publishes the barrier inits, and a
@@ -281,8 +348,8 @@ fp8_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
 
     // Programmatic dependent launch: everything above overlaps the previous kernel's tail
     asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (threadIdx.x == 0) DGB_STAMP(1);
 
-    const uint32_t num_kb = (p.k + kBlockK - 1) / kBlockK;
     const uint32_t sfw_mask = (1u << p.sf_shift_w) - 1, sfx_mask = (1u << p.sf_shift_x) - 1;
     Ring ring(slot_stride, num_stages);
 
@@ -293,19 +360,31 @@ fp8_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
             Tile t;
             const uint32_t ab_bytes = kWTileBytes + x_tile_bytes;
             const uint32_t sfw_tx = kBlockN * 4, sfx_tx = p.block_m * 4;
+            // multi-pair clusters: this CTA fetches 1/kPairs of its weight tile and multicasts it to the CTAs of the
+            // same parity in every pair (they need the same 128 weight rows for their own m-blocks)
+            constexpr uint32_t kWRows = kBlockN / kPairs;
+            uint16_t w_mask = 0;
+            for (uint32_t q = 0; q < kPairs; ++q) w_mask |= static_cast<uint16_t>(1u << (2 * q + (cta_rank & 1)));
             while (sched.next(t)) {
                 if (kGemmType == kMContiguousPsum && t.valid_m == 0) continue;   // padding-only tile: nothing to load
-                const uint32_t x_row = t.x_row + cta_rank * load_m;
-                uint32_t k0 = 0;
-                for (uint32_t kb = 0; kb < num_kb; ++kb, k0 += kBlockK, ring.advance()) {
+                const uint32_t x_row = t.x_row + (cta_rank & 1) * load_m;
+                uint32_t k0 = t.kb_begin * kBlockK;
+                for (uint32_t kb = t.kb_begin; kb < t.kb_end; ++kb, k0 += kBlockK, ring.advance()) {
                     const uint32_t full = full_bar + ring.bar, slot = smem_base + ring.slot;
                     mbar_wait(empty_bar + ring.bar, ring.phase ^ 1);
-                    const bool load_sfw = (kb & sfw_mask) == 0, load_sfx = (kb & sfx_mask) == 0;
+                    // a packed SF word covers 4 k-blocks (gran_k 128); a split-K slice may start inside one
+                    const bool first = kb == t.kb_begin;
+                    const bool load_sfw = (kb & sfw_mask) == 0 || first, load_sfx = (kb & sfx_mask) == 0 || first;
                     mbar_arrive_expect_tx(full, ab_bytes + (load_sfw ? sfw_tx : 0u) + (load_sfx ? sfx_tx : 0u));
-                    tma_load_2d(&map_w, full, slot, k0, t.w_row, kEvictNormal);
+                    if constexpr (kPairs == 1)
+                        tma_load_2d(&map_w, full, slot, k0, t.w_row, kEvictNormal);
+                    else
+                        tma_load_2d_multicast(&map_w, full, slot + pair_idx * (kWRows * kBlockK), k0, t.w_row + pair_idx * kWRows,
+                                              w_mask, kEvictNormal);
                     tma_load_2d(&map_x, full, slot + off_x, k0, x_row, kEvictNormal);
                     if (load_sfw) tma_load_2d(&map_sfw, full, slot + off_sfw, t.sfw_col, t.sfw_row + (kb >> p.sf_shift_w), kEvictNormal);
                     if (load_sfx) tma_load_2d(&map_sfx, full, slot + off_sfx, t.sfx_col, t.sfx_row + (kb >> p.sf_shift_x), kEvictNormal);
+                    if (first) DGB_STAMP(2);
                 }
             }
         }
@@ -314,13 +393,15 @@ fp8_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
         if (is_leader) {
             Scheduler<kGemmType, kCluster> sched(p, cta_rank);
             Tile t;
-            const uint32_t idesc_base = make_idesc(128 * kCluster, p.block_m, 0, 0);
+            const uint32_t idesc_base = make_idesc(128 * kCtaGroup, p.block_m, 0, 0);
             // descriptors of slot 0; a slot offset adds (bytes >> 4) to the 14-bit start-address field
             const uint64_t w_desc0 = make_smem_desc(smem_base, 0, 1024, kLayoutSwizzle128B);
             const uint64_t x_desc0 = make_smem_desc(smem_base + off_x, 0, 1024, kLayoutSwizzle128B);
             const uint64_t sfw_desc0 = make_smem_desc(smem_base + off_sfw, 0, 128, kLayoutNoSwizzle);
             const uint64_t sfx_desc0 = make_smem_desc(smem_base + off_sfx, 0, 128, kLayoutNoSwizzle);
             const uint32_t tmem_sfw = tmem_base + kTmemColSFW, tmem_sfx = tmem_base + kTmemColSFX;
+            constexpr uint16_t kEmptyMask = static_cast<uint16_t>((1u << kCluster) - 1);   // every CTA's `empty` barrier
+            const uint16_t pair_mask = static_cast<uint16_t>(0b11u << leader_rank);           // this pair only
             uint32_t tile_iter = 0;
             while (sched.next(t)) {
                 if (kGemmType == kMContiguousPsum && t.valid_m == 0) continue;
@@ -329,16 +410,17 @@ fp8_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
                 mbar_wait(tmem_empty_bar + as * 8, aphase ^ 1);
                 tcgen05_fence_after();
                 const uint32_t tmem_d = tmem_base + as * kAccumColStride;
-                for (uint32_t kb = 0; kb < num_kb; ++kb, ring.advance()) {
+                for (uint32_t kb = t.kb_begin; kb < t.kb_end; ++kb, ring.advance()) {
                     mbar_wait(ready_bar + ring.bar, ring.phase);
                     tcgen05_fence_after();
                     if (elect_one()) {
                         const uint32_t slot16 = ring.slot >> 4;
                         const uint32_t sfw_sub = kb & sfw_mask, sfx_sub = kb & sfx_mask;
-                        if (sfw_sub == 0) tmem_cp_sf<kCluster>(tmem_sfw, sfw_desc0 + slot16);
-                        if (sfx_sub == 0) {
-                            tmem_cp_sf<kCluster>(tmem_sfx, sfx_desc0 + slot16);
-                            if (num_sfx_groups > 1) tmem_cp_sf<kCluster>(tmem_sfx + 4, sfx_desc0 + slot16 + 32);
+                        const bool first = kb == t.kb_begin;
+                        if (sfw_sub == 0 || first) tmem_cp_sf<kCtaGroup>(tmem_sfw, sfw_desc0 + slot16);
+                        if (sfx_sub == 0 || first) {
+                            tmem_cp_sf<kCtaGroup>(tmem_sfx, sfx_desc0 + slot16);
+                            if (num_sfx_groups > 1) tmem_cp_sf<kCtaGroup>(tmem_sfx + 4, sfx_desc0 + slot16 + 32);
                         }
                         const uint64_t w_desc = w_desc0 + slot16, x_desc = x_desc0 + slot16;
                         // one UE8M0 byte per 32 K-elements: byte id inside the packed word
@@ -346,11 +428,15 @@ fp8_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
                         const uint32_t id_step = (sfw_mask ? 0u : (1u << 29)) | (sfx_mask ? 0u : (1u << 4));  // gran_k 32
 #pragma unroll
                         for (uint32_t j = 0; j < kBlockK / kUmmaK; ++j)
-                            mma_mxf8_block_scale<kCluster>(tmem_d, w_desc + j * (kUmmaK >> 4), x_desc + j * (kUmmaK >> 4),
-                                                           idesc + j * id_step, tmem_sfw, tmem_sfx, (kb | j) != 0 ? 1u : 0u);
+                            mma_mxf8_block_scale<kCtaGroup>(tmem_d, w_desc + j * (kUmmaK >> 4), x_desc + j * (kUmmaK >> 4),
+                                                           idesc + j * id_step, tmem_sfw, tmem_sfx, (!first || j != 0) ? 1u : 0u);
                         // retire -> the smem slot may be overwritten (signals every CTA of the pair)
-                        mma_commit<kCluster>(empty_bar + ring.bar);
-                        if (kb + 1 == num_kb) mma_commit<kCluster>(tmem_full_bar + as * 8);
+                        mma_commit<kCtaGroup>(empty_bar + ring.bar, kEmptyMask);
+                        if (first) DGB_STAMP(4);
+                        if (kb + 1 == t.kb_end) {
+                            mma_commit<kCtaGroup>(tmem_full_bar + as * 8, pair_mask);
+                            DGB_STAMP(5);
+                        }
                     }
                     __syncwarp();
                 }
@@ -374,12 +460,14 @@ fp8_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
             st_shared_v4(base + lane * 16, v0, v1, v2, v3);
         };
         // barrier of the pair's leader CTA, as a shared::cluster address
-        const uint32_t ready_dst = kCluster > 1 ? mapa(ready_bar, 0) : ready_bar;
+        const uint32_t ready_dst = kCluster > 1 ? mapa(ready_bar, leader_rank) : ready_bar;
         while (sched.next(t)) {
             if (kGemmType == kMContiguousPsum && t.valid_m == 0) continue;
-            for (uint32_t kb = 0; kb < num_kb; ++kb, ring.advance()) {
+            for (uint32_t kb = t.kb_begin; kb < t.kb_end; ++kb, ring.advance()) {
                 mbar_wait(full_bar + ring.bar, ring.phase);
-                const bool do_w = (kb & sfw_mask) == 0, do_x = (kb & sfx_mask) == 0;
+                const bool first = kb == t.kb_begin;
+                if (first && lane == 0) DGB_STAMP(3);
+                const bool do_w = (kb & sfw_mask) == 0 || first, do_x = (kb & sfx_mask) == 0 || first;
                 if (do_w | do_x) {
                     const uint32_t slot = smem_base + ring.slot;
                     if (do_w) retile(slot + off_sfw);
@@ -402,7 +490,7 @@ fp8_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
         const uint32_t quad = warp_idx & 3;                 // TMEM lane quadrant this warp may read
         const uint32_t half = (warp_idx - 4) >> 2;          // 0: chunks 0,2,4.. | 1: chunks 1,3,5..
         out_t* d = reinterpret_cast<out_t*>(p.d);
-        const uint32_t tmem_empty_dst = kCluster > 1 ? mapa(tmem_empty_bar, 0) : tmem_empty_bar;
+        const uint32_t tmem_empty_dst = kCluster > 1 ? mapa(tmem_empty_bar, leader_rank) : tmem_empty_bar;
         const size_t row_bytes = static_cast<size_t>(p.ld_d) * sizeof(out_t);
         uint32_t tile_iter = 0;
         while (sched.next(t)) {
@@ -418,8 +506,80 @@ fp8_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
             ++tile_iter;
             mbar_wait(tmem_full_bar + as * 8, aphase);
             tcgen05_fence_after();
+            if (threadIdx.x == 128) DGB_STAMP(6);
             const uint32_t taddr = tmem_base + ((quad * 32) << 16) + as * kAccumColStride;
             const uint32_t load_cols = (max(t.valid_m, 1u) + 15) / 16 * 16;
+            if (kGemmType == kDense && p.num_splits > 1) {
+                // ---------------------------------------------------------------- split-K epilogue
+                // (1) park this slice's FP32 partial tile in the workspace, (2) count arrivals per output block,
+                // (3) the last slice to arrive adds the partials in slice order (deterministic) and writes D.
+                float* ws_col = p.splitk_ws + (static_cast<size_t>(t.split) * p.m + t.d_row) * p.n + n;
+                auto release = [&]() {
+                    tcgen05_fence_before();
+                    if constexpr (kCluster > 1)
+                        mbar_arrive_remote(tmem_empty_dst + as * 8);
+                    else
+                        mbar_arrive(tmem_empty_dst + as * 8);
+                };
+                if (half * 32 >= load_cols) release();
+                for (uint32_t c0 = half * 32; c0 < load_cols; c0 += 64) {
+                    uint32_t v[32];
+                    const bool second = c0 + 16 < load_cols;
+                    tmem_ld_32x32b_x16(taddr + c0, *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
+                    if (second) tmem_ld_32x32b_x16(taddr + c0 + 16, *reinterpret_cast<uint32_t(*)[16]>(&v[16]));
+                    tmem_ld_wait();
+                    if (c0 + 64 >= load_cols) release();
+                    if (n_ok) {
+                        float* wrow = ws_col + static_cast<size_t>(c0) * p.n;
+#pragma unroll
+                        for (uint32_t h = 0; h < 2; ++h) {
+                            const uint32_t r0 = c0 + h * 16;
+                            if (r0 + 16 <= t.valid_m) {
+#pragma unroll
+                                for (uint32_t j = 0; j < 16; ++j) wrow[static_cast<size_t>(h * 16 + j) * p.n] = __uint_as_float(v[h * 16 + j]);
+                            } else if (r0 < t.valid_m) {
+#pragma unroll
+                                for (uint32_t j = 0; j < 16; ++j)
+                                    if (r0 + j < t.valid_m) wrow[static_cast<size_t>(h * 16 + j) * p.n] = __uint_as_float(v[h * 16 + j]);
+                            }
+                        }
+                    }
+                }
+                // Publish: the CTA barrier orders every thread's partial stores before thread 0, whose gpu-scope fence
+                // (cumulative) + counter increment release them; the increment's result tells who arrived last.
+                const uint32_t et = threadIdx.x - 4 * 32;          // index among the epilogue threads
+                named_bar_sync(1, kNumEpilogueThreads);
+                if (et == 0) {
+                    asm volatile("fence.acq_rel.gpu;" ::: "memory");
+                    const int prev = atomicAdd(p.splitk_counters + t.counter_idx, 1);
+                    asm volatile("fence.acq_rel.gpu;" ::: "memory");
+                    asm volatile("st.shared.b32 [%0], %1;" ::"r"(splitk_flag_smem), "r"(prev) : "memory");
+                }
+                named_bar_sync(1, kNumEpilogueThreads);
+                const uint32_t prev = ld_shared_u32(splitk_flag_smem);
+                if (prev == p.num_splits - 1) {
+                    const uint32_t nc = t.n0 + lane * 4;           // 4 consecutive columns per lane, one row per warp
+                    if (nc < p.n) {
+                        const size_t slice = static_cast<size_t>(p.m) * p.n;
+                        constexpr uint32_t kWarps = kNumEpilogueThreads / 32;
+#define DGB_FINALIZE(S, R) \
+    splitk_finalize<S, R, out_t, kAccumulate>(p.splitk_ws, slice, p.n, d, p.ld_d, t.d_row, t.valid_m, nc, et >> 5, kWarps)
+                        switch (p.num_splits) {
+                            case 2: DGB_FINALIZE(2, 4); break;
+                            case 3: DGB_FINALIZE(3, 4); break;
+                            case 4: DGB_FINALIZE(4, 4); break;
+                            case 5: DGB_FINALIZE(5, 2); break;
+                            case 6: DGB_FINALIZE(6, 2); break;
+                            case 7: DGB_FINALIZE(7, 2); break;
+                            default: DGB_FINALIZE(8, 2); break;
+                        }
+#undef DGB_FINALIZE
+                    }
+                    if (et == 0) p.splitk_counters[t.counter_idx] = 0;   // leave the counters clean for the next launch
+                }
+                named_bar_sync(1, kNumEpilogueThreads);                   // the flag word is reused by the next tile
+                continue;
+            }
             auto release_accumulator = [&]() {
                 // last read of this accumulator buffer by this warp: hand it back before the stores drain
                 tcgen05_fence_before();
@@ -440,15 +600,21 @@ fp8_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
                 if (c0 + 64 >= load_cols) release_accumulator();
                 char* row = d_col + static_cast<size_t>(c0) * row_bytes;
                 if (n_ok) {
-                    if (c0 + 32 <= t.valid_m) {
 #pragma unroll
-                        for (uint32_t j = 0; j < 32; ++j)
-                            store_out<out_t>(reinterpret_cast<out_t*>(row + j * row_bytes), __uint_as_float(v[j]), kAccumulate);
-                    } else {
+                    for (uint32_t h = 0; h < 2; ++h) {
+                        const uint32_t r0 = c0 + h * 16;
+                        if (r0 + 16 <= t.valid_m) {          // full 16-row half: no per-row predicates
 #pragma unroll
-                        for (uint32_t j = 0; j < 32; ++j)
-                            if (c0 + j < t.valid_m)
-                                store_out<out_t>(reinterpret_cast<out_t*>(row + j * row_bytes), __uint_as_float(v[j]), kAccumulate);
+                            for (uint32_t j = 0; j < 16; ++j)
+                                store_out<out_t>(reinterpret_cast<out_t*>(row + (h * 16 + j) * row_bytes),
+                                                 __uint_as_float(v[h * 16 + j]), kAccumulate);
+                        } else if (r0 < t.valid_m) {
+#pragma unroll
+                            for (uint32_t j = 0; j < 16; ++j)
+                                if (r0 + j < t.valid_m)
+                                    store_out<out_t>(reinterpret_cast<out_t*>(row + (h * 16 + j) * row_bytes),
+                                                     __uint_as_float(v[h * 16 + j]), kAccumulate);
+                        }
                     }
                 }
             }
@@ -460,6 +626,8 @@ fp8_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
     }
 
     // ---- teardown
+    if (threadIdx.x == 128) DGB_STAMP(7);
+    if (threadIdx.x == 0) DGB_STAMP(8);
     tcgen05_fence_before();
     if constexpr (kCluster > 1) {
         cluster_arrive_relaxed();   // (a release-arrive here would wait for every output store to become visible)
@@ -467,7 +635,9 @@ fp8_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
     } else {
         __syncthreads();
     }
-    if (warp_idx == 2) tmem_dealloc<kCluster>(tmem_base, kTmemCols);
+    if (warp_idx == 2) tmem_dealloc<kCtaGroup>(tmem_base, kTmemCols);
+    if (threadIdx.x == 0) DGB_STAMP(9);
+    if (threadIdx.x == 0 && p.debug_ts != nullptr) p.debug_ts[16 + 2 * blockIdx.x + 1] = globaltimer_ns();  // per-CTA exit
 #endif
 }
 

@@ -142,6 +142,16 @@ DGB_DEVICE void tma_load_2d(const CUtensorMap* map, uint32_t bar, uint32_t smem_
         : "memory");
 }
 
+// Same, delivered to the same shared-memory offset of every CTA in `cta_mask` (and counted on each one's barrier).
+DGB_DEVICE void tma_load_2d_multicast(const CUtensorMap* map, uint32_t bar, uint32_t smem_dst, uint32_t c0, uint32_t c1,
+                                      uint16_t cta_mask, uint64_t hint) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster.L2::cache_hint"
+        " [%0], [%1, {%3, %4}], [%2], %5, %6;" ::"r"(smem_dst),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "h"(cta_mask), "l"(hint)
+        : "memory");
+}
+
 // ---------------------------------------------------------------- tensor memory
 template <int kCtaGroup>
 DGB_DEVICE void tmem_alloc(uint32_t smem_dst, uint32_t ncols) {
@@ -205,12 +215,11 @@ DGB_DEVICE void mma_mxf8_block_scale(uint32_t tmem_d, uint64_t adesc, uint64_t b
 // Make all previously issued tcgen05 ops of this thread arrive on an mbarrier when they retire.
 // cta_group::2 form multicasts the arrival to the barrier at the same offset in both CTAs of the pair.
 template <int kCtaGroup>
-DGB_DEVICE void mma_commit(uint32_t bar) {
+DGB_DEVICE void mma_commit(uint32_t bar, uint16_t mask = 0b11) {
     if constexpr (kCtaGroup == 1) {
         asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
                      : "memory");
     } else {
-        const uint16_t mask = 0b11;
         asm volatile(
             "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
                 bar),

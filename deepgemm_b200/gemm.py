@@ -28,6 +28,26 @@ def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
+# Split-K scratch (include/dgb200.h, `workspace`): one zero-initialised buffer per (device, stream), so GEMMs that may
+# run concurrently never share it. Only small problems use it (fewer output tiles than SM pairs).
+_WORKSPACE_CAP = 64 << 20
+_workspaces = {}
+
+
+def _workspace(m: int, n: int, device: torch.device, stream: int):
+    need = 16384 + 32 * m * n
+    if need > _WORKSPACE_CAP:
+        return None, 0
+    key = (device.index, stream)
+    ws = _workspaces.get(key)
+    if ws is None or ws.numel() < need:
+        if torch.cuda.is_current_stream_capturing():
+            return None, 0                      # never allocate inside a CUDA-graph capture
+        ws = torch.zeros(max(need, 8 << 20), dtype=torch.uint8, device=device)
+        _workspaces[key] = ws
+    return ws.data_ptr(), ws.numel()
+
+
 def _major_check(t: torch.Tensor) -> None:
     """csrc/utils/layout.hpp:13-19."""
     _require(t.dim() in (2, 3), 'dim == 2 or dim == 3')
@@ -100,10 +120,12 @@ def fp8_gemm_nt(a: TensorPair, b: TensorPair, d: torch.Tensor, c: Optional[torch
     _require(sfa_t.dtype == torch.int32 and sfb_t.dtype == torch.int32, 'Unsupported architecture or scaling factor types')
     lda = a_t.stride(0) if major_a == _K_MAJOR else a_t.stride(1)
     ldb = b_t.stride(0) if major_b == _K_MAJOR else b_t.stride(1)
+    stream = _stream()
+    ws_ptr, ws_bytes = _workspace(m, n, d.device, stream)
     check(lib().dgb200_fp8_gemm_nt(a_t.data_ptr(), sfa_t.data_ptr(), b_t.data_ptr(), sfb_t.data_ptr(), d.data_ptr(),
                                    m, n, k, lda, ldb, d.stride(0), major_a, major_b,
                                    sfa_t.stride(-1), sfb_t.stride(-1), gran_k_a, gran_k_b, _d_dtype(d),
-                                   int(c is not None), _stream()))
+                                   int(c is not None), ws_ptr, ws_bytes, stream))
 
 
 def _t(pair: TensorPair, d0: int = 0, d1: int = 1) -> TensorPair:

@@ -86,7 +86,14 @@ int dgb200_pack_sf_ue8m0_k_grouped(const float* sf, int32_t* out, int mn, const 
 int dgb200_fp8_gemm_nt(const void* a, const int32_t* sfa, const void* b, const int32_t* sfb, void* d,
                        int m, int n, int k, int64_t lda, int64_t ldb, int64_t ldd,
                        int major_a, int major_b, int sfa_stride, int sfb_stride, int gran_k_a, int gran_k_b,
-                       int d_dtype, int accumulate, void* stream);
+                       int d_dtype, int accumulate, void* workspace, int64_t workspace_bytes, void* stream);
+/* `workspace` (optional, may be NULL): device scratch that lets small problems (fewer output tiles than SM pairs) cut K
+ * into slices so that every SM streams its own part of B ("split-K"). Contract: 16-byte aligned, its first
+ * DGB200_WORKSPACE_HEADER_BYTES are zero before the first use (the kernel leaves them zero again), and it is not
+ * shared by GEMMs that may run concurrently (use one per stream). Results stay deterministic: partial sums are added
+ * in slice order. dgb200_workspace_bytes() gives a size that is always sufficient for an (m, n) problem. */
+#define DGB200_WORKSPACE_HEADER_BYTES 16384
+int64_t dgb200_workspace_bytes(int m, int n);
 
 /* Rows of A grouped by expert          -- m_grouped_fp8_fp4_gemm_nt_contiguous, csrc/apis/gemm.hpp:166-232.
  *   a [m, k], b [num_groups, n, k], d [m, n] bf16
@@ -123,6 +130,7 @@ typedef struct dgb200_config {
     int num_sms;     /* grid size */
     int smem_bytes;  /* dynamic shared memory per CTA */
     int num_tiles;   /* upper bound on (cluster) tiles */
+    int num_splits;  /* split-K slices (1 = none) */
 } dgb200_config;
 /* Pure function (no CUDA): the configuration the heuristics pick for a problem on `num_sms` SMs.
  * gemm_type: 0 dense, 1 m-grouped contiguous, 2 m-grouped masked, 3 m-grouped contiguous psum.
@@ -131,6 +139,11 @@ int dgb200_plan(int gemm_type, int m, int n, int k, int num_groups, int expected
                 dgb200_config* out);
 /* Configuration the last GEMM call on this thread used (DG_PRINT_CONFIGS analogue, heuristics/common.hpp:39-50). */
 int dgb200_last_config(dgb200_config* out);
+/* Development aid: when set to a device buffer of (16 + 2 * grid) int64, CTA 0 of every GEMM launch stamps clock64()
+ * at ten points of its life (entry, setup done, first TMA, first data, first MMA, last MMA, accumulator ready, stores
+ * issued, teardown begin/end) into [0,10), and every CTA b stamps %globaltimer (ns) at entry / exit into
+ * [16 + 2b], [17 + 2b]. NULL (default) disables it. */
+int dgb200_debug_set_timestamps(void* device_int64_buffer);
 /* Number of kernels launched by this library since process start (all threads). */
 int64_t dgb200_launch_count(void);
 

@@ -42,18 +42,20 @@ def main():
         out['dense'].append({'name': f'dense_{m}x{n}x{k}_{dtype}_{acc}', 'a': u8(qa[0]), 'sfa': qa[1].cpu(), 'b': u8(qb[0]),
                              'sfb': qb[1].cpu(), 'c': None if c is None else c.cpu(), 'd': d.cpu()})
 
-    g, m_max, n, k = 4, 96, 256, 512
+    # NOTE: M_max must be a multiple of the reference's BLOCK_M (128 here): its masked kernel stores whole tiles, so with
+    # M_max=96 a tile of group g spills over the first rows of group g+1 (SURVEY Appendix E pitfall 1) -- not golden.
+    g, m_max, n, k = 4, 128, 256, 512
     a = torch.randn((g, m_max, k), device='cuda', dtype=torch.bfloat16)
     b = torch.randn((g, n, k), device='cuda', dtype=torch.bfloat16)
     qa_l = [per_token_cast_to_fp8(a[i], True) for i in range(g)]
     qb_l = [per_block_cast_to_fp8(b[i], True) for i in range(g)]
     qa = (torch.stack([x[0] for x in qa_l]), torch.stack([x[1] for x in qa_l]))
     qb = (torch.stack([x[0] for x in qb_l]), torch.stack([x[1] for x in qb_l]))
-    masked_m = torch.tensor([17, 96, 0, 50], device='cuda', dtype=torch.int32)
+    masked_m = torch.tensor([17, 128, 0, 50], device='cuda', dtype=torch.int32)
     d = torch.zeros((g, m_max, n), device='cuda', dtype=torch.bfloat16)
     ref.m_grouped_fp8_gemm_nt_masked(qa, qb, d, masked_m, 48)
     torch.cuda.synchronize()
-    out['masked'].append({'name': 'masked_4x96x256x512', 'a': u8(qa[0]), 'sfa': qa[1].cpu(), 'b': u8(qb[0]), 'sfb': qb[1].cpu(),
+    out['masked'].append({'name': 'masked_4x128x256x512', 'a': u8(qa[0]), 'sfa': qa[1].cpu(), 'b': u8(qb[0]), 'sfb': qb[1].cpu(),
                           'masked_m': masked_m.cpu(), 'expected_m': 48, 'd': d.cpu()})
 
     for psum in (False, True):

@@ -34,8 +34,9 @@ def dequant_ref(qa, qb, m, n, k):
     return (qa[0].float() * sfa) @ (qb[0].float() * sfb).t()
 
 
-def set_cfg(block_m=0, cluster=0, stages=0):
-    for name, v in (('DGB200_BLOCK_M', block_m), ('DGB200_CLUSTER', cluster), ('DGB200_STAGES', stages)):
+def set_cfg(block_m=0, cluster=0, stages=0, splits=0):
+    for name, v in (('DGB200_BLOCK_M', block_m), ('DGB200_CLUSTER', cluster), ('DGB200_STAGES', stages),
+                    ('DGB200_SPLITS', splits)):
         if v:
             os.environ[name] = str(v)
         else:
@@ -122,6 +123,7 @@ def run_ref():
         torch.cuda.synchronize()
         same = bool(torch.equal(d_ref, d_our))
         nmis = int((d_ref != d_our).sum())
+        cfg_used = __import__('deepgemm_b200')._lib.last_config()
         # pre-packed SFs for both (kernel-only comparison)
         sfa = dg.transform_sf_into_required_layout(qa[1], m, k, (1, 128, 128), None, True)
         sfb = dg.transform_sf_into_required_layout(qb[1], n, k, (1, 128, 128), None, False)
@@ -133,7 +135,7 @@ def run_ref():
         e_ref, _ = time_fn(lambda: ref.fp8_gemm_nt(qa, qb, d_ref))
         e_our, _ = time_fn(lambda: dg.fp8_gemm_nt(qa, qb, d_our))
         fl = 2.0 * m * n * k
-        log(test='ref_vs_ours', m=m, n=n, k=k, bitwise_equal=same, mismatches=nmis, pack_equal=pack_equal,
+        log(test='ref_vs_ours', m=m, n=n, k=k, bitwise_equal=same, mismatches=nmis, pack_equal=pack_equal, cfg=cfg_used,
             ref_us=round(t_ref * 1e6, 2), our_us=round(t_our * 1e6, 2), ref_tflops=round(fl / t_ref / 1e12, 1) if t_ref else None,
             our_tflops=round(fl / t_our / 1e12, 1) if t_our else None, ref_e2e_us=round(e_ref * 1e6, 2),
             our_e2e_us=round(e_our * 1e6, 2), ref_jit_s=round(jit_s, 1))
@@ -164,6 +166,135 @@ def run_sweep():
     set_cfg()
 
 
+def make_grouped_weights(g, n, k, seed=0):
+    """[G,N,K] FP8 weights + [G,N/128,K/128] scales, generated expert by expert to bound memory."""
+    from deepgemm_b200.utils import per_block_cast_to_fp8
+    gen = torch.Generator(device='cuda').manual_seed(seed)
+    b = torch.empty((g, n, k), device='cuda', dtype=torch.float8_e4m3fn)
+    sfb = torch.empty((g, (n + 127) // 128, (k + 127) // 128), device='cuda', dtype=torch.float32)
+    for i in range(g):
+        w = torch.randn((n, k), device='cuda', dtype=torch.bfloat16, generator=gen)
+        b[i], sfb[i] = per_block_cast_to_fp8(w, True)
+    return b, sfb
+
+
+def run_grouped():
+    """BASELINE configs 3 and 4 at full size, ours vs the reference kernel (kernel-only, cold L2)."""
+    import random
+    ref = import_reference()
+    import deepgemm_b200 as dg
+    from deepgemm_b200 import _lib
+    from deepgemm_b200.testing import bench_kineto
+    from deepgemm_b200.utils import per_token_cast_to_fp8
+    set_cfg()
+    random.seed(0)
+    # ---- config 3: contiguous, 256 experts, N=4096, K=7168
+    g, n, k = 256, 4096, 7168
+    b, sfb = make_grouped_weights(g, n, k)
+    sfb_p = dg.transform_sf_into_required_layout(sfb, n, k, (1, 128, 128), g, False)
+    sfb_r = ref.transform_sf_into_required_layout(sfb, n, k, (1, 128, 128), g, False)
+    log(test='grouped_sfb_pack_equal', equal=bool(torch.equal(sfb_p, sfb_r)))
+    for mean_m in (64, 128, 256):
+        for alignment in (128,):
+            dg.set_mk_alignment_for_contiguous_layout(alignment)
+            ref.set_mk_alignment_for_contiguous_layout(alignment)
+            ms = [int(mean_m * random.uniform(0.7, 1.3)) for _ in range(g)]
+            aligned = [(x + alignment - 1) // alignment * alignment for x in ms]
+            m = sum(aligned)
+            a = torch.randn((m, k), device='cuda', dtype=torch.bfloat16)
+            layout = torch.empty(m, device='cuda', dtype=torch.int32)
+            s0 = 0
+            for i, (mi, ai) in enumerate(zip(ms, aligned)):
+                layout[s0:s0 + mi] = i
+                layout[s0 + mi:s0 + ai] = -1
+                a[s0 + mi:s0 + ai] = 0
+                s0 += ai
+            qa = per_token_cast_to_fp8(a, True)
+            sfa = dg.transform_sf_into_required_layout(qa[1], m, k, (1, 128, 128), None, True)
+            d_ref = torch.empty((m, n), device='cuda', dtype=torch.bfloat16)
+            d_our = torch.empty_like(d_ref)
+            ref.m_grouped_fp8_gemm_nt_contiguous((qa[0], sfa), (b, sfb_r), d_ref, layout)
+            dg.m_grouped_fp8_gemm_nt_contiguous((qa[0], sfa), (b, sfb_p), d_our, layout)
+            torch.cuda.synchronize()
+            eq = bool(torch.equal(d_ref, d_our))
+            cfg = _lib.last_config()
+            t_ref = bench_kineto(lambda: ref.m_grouped_fp8_gemm_nt_contiguous((qa[0], sfa), (b, sfb_r), d_ref, layout), 'gemm_', num_tests=5)
+            t_our = bench_kineto(lambda: dg.m_grouped_fp8_gemm_nt_contiguous((qa[0], sfa), (b, sfb_p), d_our, layout), 'fp8_gemm_kernel', num_tests=5)
+            valid = sum(ms)
+            byts = m * k + g * n * k + m * n * 2
+            log(test='contiguous', groups=g, mean_m=mean_m, m=m, valid_m=valid, n=n, k=k, alignment=alignment, cfg=cfg,
+                bitwise_equal=eq, ref_us=round(t_ref * 1e6, 1), our_us=round(t_our * 1e6, 1),
+                ref_tflops=round(2.0 * valid * n * k / t_ref / 1e12, 1), our_tflops=round(2.0 * valid * n * k / t_our / 1e12, 1),
+                ref_gbs=round(byts / t_ref / 1e9), our_gbs=round(byts / t_our / 1e9))
+            del a, qa, sfa, d_ref, d_our, layout
+    del b, sfb, sfb_p, sfb_r
+    torch.cuda.empty_cache()
+    # ---- config 4: masked, 256 experts, M_max=128, N=7168, K=2048
+    g, m_max, n, k = 256, 128, 7168, 2048
+    b, sfb = make_grouped_weights(g, n, k, seed=1)
+    sfb_p = dg.transform_sf_into_required_layout(sfb, n, k, (1, 128, 128), g, False)
+    a = torch.randn((g, m_max, k), device='cuda', dtype=torch.bfloat16)
+    qs = [per_token_cast_to_fp8(a[i], True) for i in range(g)]
+    qa = (torch.stack([q[0] for q in qs]), torch.stack([q[1] for q in qs]))
+    sfa = dg.transform_sf_into_required_layout(qa[1], m_max, k, (1, 128, 128), g, True)
+    for mean_m in (16, 64, 96):
+        masked = torch.tensor([min(m_max, int(mean_m * random.uniform(0.7, 1.3))) for _ in range(g)], device='cuda', dtype=torch.int32)
+        expected_m = int(1.2 * mean_m)
+        d_ref = torch.zeros((g, m_max, n), device='cuda', dtype=torch.bfloat16)
+        d_our = torch.zeros_like(d_ref)
+        ref.m_grouped_fp8_gemm_nt_masked((qa[0], sfa), (b, sfb_p), d_ref, masked, expected_m)
+        dg.m_grouped_fp8_gemm_nt_masked((qa[0], sfa), (b, sfb_p), d_our, masked, expected_m)
+        torch.cuda.synchronize()
+        cfg = _lib.last_config()
+        eq = all(bool(torch.equal(d_ref[i, :mm], d_our[i, :mm])) for i, mm in enumerate(masked.tolist()))
+        t_ref = bench_kineto(lambda: ref.m_grouped_fp8_gemm_nt_masked((qa[0], sfa), (b, sfb_p), d_ref, masked, expected_m), 'gemm_', num_tests=5)
+        t_our = bench_kineto(lambda: dg.m_grouped_fp8_gemm_nt_masked((qa[0], sfa), (b, sfb_p), d_our, masked, expected_m), 'fp8_gemm_kernel', num_tests=5)
+        # CUDA-graph replay of ours
+        graph = torch.cuda.CUDAGraph()
+        side = torch.cuda.Stream()
+        with torch.cuda.stream(side):
+            with torch.cuda.graph(graph, stream=side):
+                dg.m_grouped_fp8_gemm_nt_masked((qa[0], sfa), (b, sfb_p), d_our, masked, expected_m)
+        t_graph, _ = time_fn(lambda: graph.replay(), iters=8)
+        valid = int(masked.sum())
+        byts = valid * k + g * n * k + valid * n * 2
+        log(test='masked', groups=g, mean_m=mean_m, valid_m=valid, n=n, k=k, cfg=cfg, valid_rows_bitwise_equal=eq,
+            ref_us=round(t_ref * 1e6, 1), our_us=round(t_our * 1e6, 1), our_graph_us=round(t_graph * 1e6, 1),
+            ref_tflops=round(2.0 * valid * n * k / t_ref / 1e12, 1), our_tflops=round(2.0 * valid * n * k / t_our / 1e12, 1),
+            ref_gbs=round(byts / t_ref / 1e9), our_gbs=round(byts / t_our / 1e9))
+
+
+def run_mcast():
+    """Weight-multicast clusters (4 / 8 CTAs) vs plain pairs: bitwise check + kernel time."""
+    import deepgemm_b200 as dg
+    from deepgemm_b200 import _lib
+    from deepgemm_b200.testing import bench_kineto
+    for (m, n, k, bms) in [(64, 4096, 7168, (16, 32, 64)), (128, 4096, 7168, (32, 64, 128)), (512, 4096, 7168, (64, 128)),
+                           (4096, 4096, 7168, (128, 192, 240)), (4096, 7168, 2048, (128, 240)), (1024, 2112, 7168, (128, 240))]:
+        a, b, qa, qb = make_inputs(m, n, k)
+        sfa = dg.transform_sf_into_required_layout(qa[1], m, k, (1, 128, 128), None, True)
+        sfb = dg.transform_sf_into_required_layout(qb[1], n, k, (1, 128, 128), None, False)
+        base = torch.empty((m, n), device='cuda', dtype=torch.bfloat16)
+        set_cfg(bms[-1], 2, 0, 1)
+        dg.fp8_gemm_nt((qa[0], sfa), (qb[0], sfb), base)
+        for bm in bms:
+            for cl in (2, 4, 8):
+                if cl // 2 * bm > max(m, bm) * 2 and cl > 2 and (m + bm - 1) // bm < cl // 2:
+                    continue
+                set_cfg(bm, cl, 0, 1)
+                d = torch.full((m, n), float('nan'), device='cuda', dtype=torch.bfloat16)
+                try:
+                    dg.fp8_gemm_nt((qa[0], sfa), (qb[0], sfb), d)
+                    torch.cuda.synchronize()
+                    t = bench_kineto(lambda: dg.fp8_gemm_nt((qa[0], sfa), (qb[0], sfb), d), 'fp8_gemm_kernel', num_tests=10)
+                except Exception as e:  # noqa: BLE001
+                    log(test='mcast', m=m, n=n, k=k, bm=bm, cluster=cl, error=str(e)[:200])
+                    raise
+                log(test='mcast', m=m, n=n, k=k, cfg=_lib.last_config(), equal=bool(torch.equal(d, base)),
+                    us=round(t * 1e6, 2), tflops=round(2.0 * m * n * k / t / 1e12, 1))
+    set_cfg()
+
+
 if __name__ == '__main__':
     mode = sys.argv[1]
     torch.manual_seed(0)
@@ -174,4 +305,8 @@ if __name__ == '__main__':
         run_ref()
     elif mode == 'sweep':
         run_sweep()
+    elif mode == 'grouped':
+        run_grouped()
+    elif mode == 'mcast':
+        run_mcast()
     log(mode=mode, done=True)
