@@ -58,13 +58,13 @@ SIGNATURES = {
     'dgb200_get_tma_aligned_size': (_I, [_I, _I]),
     'dgb200_pack_sf_ue8m0': (_I, [_P, _P, _I, _I, _I, _I, _L, _L, _L, _P, _I, _I, _P]),
     'dgb200_transpose_sf_fp32': (_I, [_P, _P, _I, _I, _I, _L, _L, _L, _P]),
-    'dgb200_pack_sf_ue8m0_k_grouped': (_I, [_P, _P, _I, _P, _I, _I, _P]),
+    'dgb200_pack_sf_ue8m0_k_grouped': (_I, [_P, _P, _I, _P, _I, _I, _I, _I, _P]),
     'dgb200_fp8_gemm_nt': (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _L, _L, _L, _I, _I, _I, _I, _I, _I, _I, _I, _P, _L, _P]),
     'dgb200_workspace_bytes': (_L, [_I, _I]),
     'dgb200_m_grouped_fp8_gemm_nt_contiguous': (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _L, _L, _L, _I, _I, _I,
                                                      _I, _I, _I, _I, _I, _P]),
     'dgb200_m_grouped_fp8_gemm_nt_masked': (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
-    'dgb200_k_grouped_fp8_gemm_tn_contiguous': (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
+    'dgb200_k_grouped_fp8_gemm_tn_contiguous': (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
     'dgb200_plan': (_I, [_I, _I, _I, _I, _I, _I, _I, _I, ctypes.POINTER(_Config)]),
     'dgb200_last_config': (_I, [ctypes.POINTER(_Config)]),
     'dgb200_debug_set_timestamps': (_I, [_P]),

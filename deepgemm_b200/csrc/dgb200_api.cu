@@ -173,6 +173,8 @@ struct Problem {
     int n, k, groups;
     int alignment;     // contiguous layouts: group start alignment
     int max_splits = 1;  // > 1 only for dense problems whose caller supplied a split-K workspace
+    bool x_mn = false;   // MN-major tokens: the token tile is loaded in 32/64/128-row swizzle atoms
+    bool any_mn = false; // any MN-major operand: no weight multicast
 };
 struct Config {
     int block_m, cluster, stages, num_sms, smem_bytes, swizzle_group;
@@ -234,8 +236,9 @@ Config choose_config(const Problem& pb, int num_sms_override = 0) {
     c.cluster = c.num_sms >= 2 ? 2 : 1;
     if (int v = env_int("DGB200_CLUSTER", 0)) c.cluster = v;
     std::vector<int> candidates;
-    if (pb.type == kDense || pb.type == kMMasked) {
-        for (int bm = 16; bm <= (int)kMaxBlockM; bm += 16) candidates.push_back(bm);
+    if (pb.type == kDense || pb.type == kMMasked || pb.type == kKGrouped || pb.type == kKGroupedPsum) {
+        const int step = pb.x_mn ? 32 * std::min(c.cluster, 2) : 16;   // MN-major tokens: load_m is a multiple of 32
+        for (int bm = step; bm <= (int)kMaxBlockM; bm += step) candidates.push_back(bm);
     } else {
         // a tile must not straddle two groups: block_m has to divide the group alignment
         for (int bm = 16; bm <= (int)kMaxBlockM; bm += 16)
@@ -248,7 +251,8 @@ Config choose_config(const Problem& pb, int num_sms_override = 0) {
     c.block_m = candidates[0];
     c.num_splits = 1;
     for (int bm : candidates) {
-        if ((pb.type == kDense || pb.type == kMMasked) && bm - 16 >= align_up(pb.m, 16)) continue;  // taller than the problem
+        if (pb.type != kMContiguous && pb.type != kMContiguousPsum && bm != candidates[0] && bm - 16 >= align_up(pb.m, 16))
+            continue;  // taller than the problem
         for (int sp = 1; sp <= max_splits; ++sp) {
             if (sp > 1) {
                 // split-K only pays for very small problems: the finalising pass costs ~3 us (measured), so it is used
@@ -290,6 +294,8 @@ struct GemmCall {
     int m, n, k, groups;
     int a_rows;  // total rows of the flattened A
     int64_t lda, ldb, ldd;
+    bool x_mn = false, w_mn = false;  // operand is MN-major (M / N contiguous, K strided by lda / ldb)
+    int sfa_krows = 0, sfb_krows = 0; // k-grouped: total packed SF rows (0: derive from k)
     int sfa_stride, sfb_stride, sfa_cols, sfb_cols;
     int gran_k_a, gran_k_b;
     int d_dtype, accumulate;
@@ -356,29 +362,58 @@ int launch_kernel(Kernel kernel, const Config& cfg, cudaStream_t stream, const C
     return DGB200_OK;
 }
 
-template <int kType, int kCluster>
+// Instantiation menu (everything is compiled ahead of time; keep it to what the API can reach):
+//   dense          : out {bf16, fp32} x accumulate {0,1} x majors {KK: clusters 1,2,4,8 | KM, MK, MM: clusters 1,2}
+//   contiguous/psum: bf16, no C, tokens K-major, weights {K, MN}, clusters 1,2        (gemm.hpp:181,193)
+//   masked         : bf16, no C, both K-major, clusters 1,2                             (gemm.hpp:263,275)
+//   k-grouped(+psum): fp32, accumulate into D, both MN-major, clusters 1,2             (gemm.hpp:325-328)
+#define DGB_LAUNCH(TYPE, CL, OUT, ACC, XMN, WMN) \
+    launch_kernel(fp8_gemm_kernel<TYPE, CL, OUT, ACC, XMN, WMN>, cfg, c.stream, mx, mw, msfx, msfw, p)
+
+template <int kType, int kCluster, bool kXMn, bool kWMn>
 int dispatch_out(const GemmCall& c, const Config& cfg, const CUtensorMap& mx, const CUtensorMap& mw,
                  const CUtensorMap& msfx, const CUtensorMap& msfw, const GemmParams& p) {
-    if (c.d_dtype == DGB200_BF16) {
-        if (c.accumulate)
-            return launch_kernel(fp8_gemm_kernel<kType, kCluster, __nv_bfloat16, true>, cfg, c.stream, mx, mw, msfx, msfw, p);
-        return launch_kernel(fp8_gemm_kernel<kType, kCluster, __nv_bfloat16, false>, cfg, c.stream, mx, mw, msfx, msfw, p);
+    if constexpr (kType == kDense) {
+        if (c.d_dtype == DGB200_BF16)
+            return c.accumulate ? DGB_LAUNCH(kType, kCluster, __nv_bfloat16, true, kXMn, kWMn)
+                                : DGB_LAUNCH(kType, kCluster, __nv_bfloat16, false, kXMn, kWMn);
+        return c.accumulate ? DGB_LAUNCH(kType, kCluster, float, true, kXMn, kWMn)
+                            : DGB_LAUNCH(kType, kCluster, float, false, kXMn, kWMn);
+    } else if constexpr (kType == kKGrouped || kType == kKGroupedPsum) {
+        return DGB_LAUNCH(kType, kCluster, float, true, true, true);
+    } else {
+        return DGB_LAUNCH(kType, kCluster, __nv_bfloat16, false, false, kWMn);
     }
-    if (c.accumulate)
-        return launch_kernel(fp8_gemm_kernel<kType, kCluster, float, true>, cfg, c.stream, mx, mw, msfx, msfw, p);
-    return launch_kernel(fp8_gemm_kernel<kType, kCluster, float, false>, cfg, c.stream, mx, mw, msfx, msfw, p);
+}
+
+template <int kType, bool kXMn, bool kWMn>
+int dispatch_cluster(const GemmCall& c, const Config& cfg, const CUtensorMap& mx, const CUtensorMap& mw,
+                     const CUtensorMap& msfx, const CUtensorMap& msfw, const GemmParams& p) {
+    if constexpr (kType == kDense && !kXMn && !kWMn) {
+        if (cfg.cluster == 8) return dispatch_out<kType, 8, kXMn, kWMn>(c, cfg, mx, mw, msfx, msfw, p);
+        if (cfg.cluster == 4) return dispatch_out<kType, 4, kXMn, kWMn>(c, cfg, mx, mw, msfx, msfw, p);
+    }
+    if (cfg.cluster == 2) return dispatch_out<kType, 2, kXMn, kWMn>(c, cfg, mx, mw, msfx, msfw, p);
+    if (cfg.cluster == 1) return dispatch_out<kType, 1, kXMn, kWMn>(c, cfg, mx, mw, msfx, msfw, p);
+    return fail(DGB200_ERR_INVALID_ARGUMENT, "unsupported cluster size %d for gemm type %d", cfg.cluster, (int)kType);
 }
 
 template <int kType>
-int dispatch_cluster(const GemmCall& c, const Config& cfg, const CUtensorMap& mx, const CUtensorMap& mw,
-                     const CUtensorMap& msfx, const CUtensorMap& msfw, const GemmParams& p) {
+int dispatch_majors(const GemmCall& c, const Config& cfg, const CUtensorMap& mx, const CUtensorMap& mw,
+                    const CUtensorMap& msfx, const CUtensorMap& msfw, const GemmParams& p) {
     if constexpr (kType == kDense) {
-        if (cfg.cluster == 8) return dispatch_out<kType, 8>(c, cfg, mx, mw, msfx, msfw, p);
-        if (cfg.cluster == 4) return dispatch_out<kType, 4>(c, cfg, mx, mw, msfx, msfw, p);
+        if (c.x_mn && c.w_mn) return dispatch_cluster<kType, true, true>(c, cfg, mx, mw, msfx, msfw, p);
+        if (c.x_mn) return dispatch_cluster<kType, true, false>(c, cfg, mx, mw, msfx, msfw, p);
+        if (c.w_mn) return dispatch_cluster<kType, false, true>(c, cfg, mx, mw, msfx, msfw, p);
+        return dispatch_cluster<kType, false, false>(c, cfg, mx, mw, msfx, msfw, p);
+    } else if constexpr (kType == kKGrouped || kType == kKGroupedPsum) {
+        return dispatch_cluster<kType, true, true>(c, cfg, mx, mw, msfx, msfw, p);
+    } else if constexpr (kType == kMMasked) {
+        return dispatch_cluster<kType, false, false>(c, cfg, mx, mw, msfx, msfw, p);
+    } else {
+        if (c.w_mn) return dispatch_cluster<kType, false, true>(c, cfg, mx, mw, msfx, msfw, p);
+        return dispatch_cluster<kType, false, false>(c, cfg, mx, mw, msfx, msfw, p);
     }
-    if (cfg.cluster == 2) return dispatch_out<kType, 2>(c, cfg, mx, mw, msfx, msfw, p);
-    if (cfg.cluster == 1) return dispatch_out<kType, 1>(c, cfg, mx, mw, msfx, msfw, p);
-    return fail(DGB200_ERR_INVALID_ARGUMENT, "unsupported cluster size %d for gemm type %d", cfg.cluster, (int)kType);
 }
 
 int run_gemm(const GemmCall& c) {
@@ -389,8 +424,10 @@ int run_gemm(const GemmCall& c) {
     DGB_REQUIRE((reinterpret_cast<uintptr_t>(c.a) & 15) == 0 && (reinterpret_cast<uintptr_t>(c.b) & 15) == 0);
     DGB_REQUIRE((reinterpret_cast<uintptr_t>(c.sfa) & 15) == 0 && (reinterpret_cast<uintptr_t>(c.sfb) & 15) == 0);
     DGB_REQUIRE(c.sfa_stride % 4 == 0 && c.sfb_stride % 4 == 0);
+    const bool k_grouped = c.type == kKGrouped || c.type == kKGroupedPsum;
 
     Problem pb{c.type, c.m, c.expected_m, c.n, c.k, c.groups, c.alignment};
+    pb.x_mn = c.x_mn, pb.any_mn = c.x_mn || c.w_mn;
     // split-K needs scratch: [4096 arrival counters][num_splits x m x n fp32 partial tiles]
     if (c.type == kDense && c.workspace != nullptr && c.n % 4 == 0 && c.workspace_bytes > kSplitKHeaderBytes &&
         (reinterpret_cast<uintptr_t>(c.workspace) & 15) == 0) {
@@ -400,25 +437,46 @@ int run_gemm(const GemmCall& c) {
     Config cfg = choose_config(pb);
     if (cfg.num_splits > 1 && ceil_div(c.m, cfg.block_m) * ceil_div(c.n, (int)kBlockN) > kSplitKCounters)
         cfg.num_splits = 1, cfg.kb_per_split = ceil_div(c.k, (int)kBlockK);
+    if (pb.any_mn && cfg.cluster > 2) cfg.cluster = 2;            // weight multicast is built for K-major tiles only
+    const int cta_group = cfg.cluster >= 2 ? 2 : 1, pairs = cfg.cluster >= 2 ? cfg.cluster / 2 : 1;
+    const int load_m = cfg.block_m / cta_group;
     DGB_REQUIRE(cfg.block_m % 16 == 0 && cfg.block_m >= 16 && cfg.block_m <= (int)kMaxBlockM);
     DGB_REQUIRE(cfg.cluster == 1 || cfg.cluster == 2 || (c.type == kDense && (cfg.cluster == 4 || cfg.cluster == 8)));
     DGB_REQUIRE(cfg.cluster <= 2 || cfg.num_splits == 1);
     if (c.type == kMContiguous || c.type == kMContiguousPsum) DGB_REQUIRE(c.alignment % cfg.block_m == 0);
+    if (c.x_mn) DGB_REQUIRE(load_m % 32 == 0);
 
     const int num_kp_a = ceil_div(c.k, c.gran_k_a * 4), num_kp_b = ceil_div(c.k, c.gran_k_b * 4);
-    const int b_groups = c.type == kDense ? 1 : c.groups;
+    const int b_groups = (c.type == kDense || k_grouped) ? 1 : c.groups;
     const int sfa_groups = c.type == kMMasked ? c.groups : 1;
+    const uint64_t sfa_krows = c.sfa_krows > 0 ? (uint64_t)c.sfa_krows : (uint64_t)num_kp_a * sfa_groups;
+    const uint64_t sfb_krows = c.sfb_krows > 0 ? (uint64_t)c.sfb_krows : (uint64_t)num_kp_b * b_groups;
 
+    // Tensor maps. K-major operand [rows, K]: box 128 K-bytes x rows. MN-major operand [K rows, MN]: box S MN-bytes x
+    // 128 K-rows, S = one swizzle atom (128 for the weights; the widest of 128/64/32 that divides load_m for tokens).
     CUtensorMap mx, mw, msfx, msfw;
-    if (int e = make_map_2d(&mx, c.a, CU_TENSOR_MAP_DATA_TYPE_UINT8, c.k, c.a_rows, c.lda, kBlockK,
-                            cfg.block_m / std::min(cfg.cluster, 2), CU_TENSOR_MAP_SWIZZLE_128B)) return e;
-    const int cta_group = cfg.cluster >= 2 ? 2 : 1, pairs = cfg.cluster >= 2 ? cfg.cluster / 2 : 1;
-    if (int e = make_map_2d(&mw, c.b, CU_TENSOR_MAP_DATA_TYPE_UINT8, c.k, (uint64_t)c.n * b_groups, c.ldb, kBlockK,
-                            kBlockN / pairs, CU_TENSOR_MAP_SWIZZLE_128B)) return e;
-    if (int e = make_map_2d(&msfx, c.sfa, CU_TENSOR_MAP_DATA_TYPE_INT32, c.sfa_cols, (uint64_t)num_kp_a * sfa_groups,
-                            (uint64_t)c.sfa_stride * 4, cfg.block_m, 1, CU_TENSOR_MAP_SWIZZLE_NONE)) return e;
-    if (int e = make_map_2d(&msfw, c.sfb, CU_TENSOR_MAP_DATA_TYPE_INT32, c.sfb_cols, (uint64_t)num_kp_b * b_groups,
-                            (uint64_t)c.sfb_stride * 4, kBlockN, 1, CU_TENSOR_MAP_SWIZZLE_NONE)) return e;
+    int x_swizzle = 128;
+    if (c.x_mn) {
+        x_swizzle = load_m % 128 == 0 ? 128 : (load_m % 64 == 0 ? 64 : 32);
+        const CUtensorMapSwizzle sw = x_swizzle == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                      : (x_swizzle == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+        if (int e = make_map_2d(&mx, c.a, CU_TENSOR_MAP_DATA_TYPE_UINT8, c.m, c.a_rows, c.lda, x_swizzle, kBlockK, sw)) return e;
+    } else {
+        if (int e = make_map_2d(&mx, c.a, CU_TENSOR_MAP_DATA_TYPE_UINT8, c.k, c.a_rows, c.lda, kBlockK, load_m,
+                                CU_TENSOR_MAP_SWIZZLE_128B)) return e;
+    }
+    if (c.w_mn) {
+        const uint64_t k_rows = k_grouped ? (uint64_t)c.a_rows : (uint64_t)c.k * b_groups;
+        if (int e = make_map_2d(&mw, c.b, CU_TENSOR_MAP_DATA_TYPE_UINT8, c.n, k_rows, c.ldb, kBlockN, kBlockK,
+                                CU_TENSOR_MAP_SWIZZLE_128B)) return e;
+    } else {
+        if (int e = make_map_2d(&mw, c.b, CU_TENSOR_MAP_DATA_TYPE_UINT8, c.k, (uint64_t)c.n * b_groups, c.ldb, kBlockK,
+                                kBlockN / pairs, CU_TENSOR_MAP_SWIZZLE_128B)) return e;
+    }
+    if (int e = make_map_2d(&msfx, c.sfa, CU_TENSOR_MAP_DATA_TYPE_INT32, c.sfa_cols, sfa_krows, (uint64_t)c.sfa_stride * 4,
+                            cfg.block_m, 1, CU_TENSOR_MAP_SWIZZLE_NONE)) return e;
+    if (int e = make_map_2d(&msfw, c.sfb, CU_TENSOR_MAP_DATA_TYPE_INT32, c.sfb_cols, sfb_krows, (uint64_t)c.sfb_stride * 4,
+                            kBlockN, 1, CU_TENSOR_MAP_SWIZZLE_NONE)) return e;
 
     GemmParams p{};
     p.d = c.d;
@@ -441,17 +499,22 @@ int run_gemm(const GemmCall& c) {
     p.num_m_blocks = ceil_div(c.m, cfg.block_m);
     p.m_alignment = std::max(1, c.alignment);
     p.zero_padding = c.zero_padding;
+    p.x_swizzle = x_swizzle;
+    p.sf_k_span = 4 * c.gran_k_a;
 
     g_last_config = dgb200_config{cfg.block_m, cfg.cluster, cfg.stages, cfg.num_sms, cfg.smem_bytes, 0, cfg.num_splits};
     if (env_int("DGB200_PRINT_CONFIGS", 0))
-        fprintf(stderr, "dgb200 config: type=%d m=%d n=%d k=%d groups=%d -> block_m=%d cluster=%d stages=%d sms=%d smem=%d splits=%d\n",
-                c.type, c.m, c.n, c.k, c.groups, cfg.block_m, cfg.cluster, cfg.stages, cfg.num_sms, cfg.smem_bytes, cfg.num_splits);
+        fprintf(stderr, "dgb200 config: type=%d m=%d n=%d k=%d groups=%d majors=%d%d -> block_m=%d cluster=%d stages=%d sms=%d smem=%d splits=%d\n",
+                c.type, c.m, c.n, c.k, c.groups, (int)c.x_mn, (int)c.w_mn, cfg.block_m, cfg.cluster, cfg.stages, cfg.num_sms,
+                cfg.smem_bytes, cfg.num_splits);
 
     switch (c.type) {
-        case kDense: return dispatch_cluster<kDense>(c, cfg, mx, mw, msfx, msfw, p);
-        case kMContiguous: return dispatch_cluster<kMContiguous>(c, cfg, mx, mw, msfx, msfw, p);
-        case kMMasked: return dispatch_cluster<kMMasked>(c, cfg, mx, mw, msfx, msfw, p);
-        case kMContiguousPsum: return dispatch_cluster<kMContiguousPsum>(c, cfg, mx, mw, msfx, msfw, p);
+        case kDense: return dispatch_majors<kDense>(c, cfg, mx, mw, msfx, msfw, p);
+        case kMContiguous: return dispatch_majors<kMContiguous>(c, cfg, mx, mw, msfx, msfw, p);
+        case kMMasked: return dispatch_majors<kMMasked>(c, cfg, mx, mw, msfx, msfw, p);
+        case kMContiguousPsum: return dispatch_majors<kMContiguousPsum>(c, cfg, mx, mw, msfx, msfw, p);
+        case kKGrouped: return dispatch_majors<kKGrouped>(c, cfg, mx, mw, msfx, msfw, p);
+        case kKGroupedPsum: return dispatch_majors<kKGroupedPsum>(c, cfg, mx, mw, msfx, msfw, p);
         default: return fail(DGB200_ERR_INVALID_ARGUMENT, "unknown gemm type %d", c.type);
     }
 }
@@ -545,10 +608,18 @@ int dgb200_transpose_sf_fp32(const float* sf, float* out, int mn, int sf_k, int 
     return DGB200_OK;
 }
 
-int dgb200_pack_sf_ue8m0_k_grouped(const float* sf, int32_t* out, int mn, const int32_t* ks_host, int num_groups,
-                                   int gran_k, void* stream) {
-    (void)sf, (void)out, (void)mn, (void)ks_host, (void)num_groups, (void)gran_k, (void)stream;
-    return fail(DGB200_ERR_UNSUPPORTED, "k-grouped SF packing is not built yet");
+int dgb200_pack_sf_ue8m0_k_grouped(const float* sf, int32_t* out, int mn, const int32_t* ks_device, int num_groups,
+                                   int packed_rows, int gran_k, int psum_alignment, void* stream) {
+    if (int e = ensure_device()) return e;
+    DGB_REQUIRE(mn > 0 && num_groups > 0 && (gran_k == 32 || gran_k == 128));
+    if (packed_rows <= 0) return DGB200_OK;
+    DGB_REQUIRE(packed_rows <= 65535);
+    const dim3 grid(ceil_div(mn, 128), packed_rows);
+    pack_sf_ue8m0_k_grouped_kernel<<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+        sf, reinterpret_cast<uint32_t*>(out), mn, ks_device, num_groups, gran_k, psum_alignment > 0 ? psum_alignment : 0);
+    DGB_CUDA(cudaGetLastError());
+    g_launch_count.fetch_add(1, std::memory_order_relaxed);
+    return DGB200_OK;
 }
 
 int dgb200_fp8_gemm_nt(const void* a, const int32_t* sfa, const void* b, const int32_t* sfb, void* d, int m, int n,
@@ -559,14 +630,15 @@ int dgb200_fp8_gemm_nt(const void* a, const int32_t* sfa, const void* b, const i
     if (m == 0 || n == 0) return DGB200_OK;  // gemm.hpp:22-23
     DGB_REQUIRE(k > 0);                      // k == 0 (D = C or 0) is handled by the host wrapper, gemm.hpp:36-40
     DGB_REQUIRE(d_dtype == DGB200_BF16 || d_dtype == DGB200_FP32);
-    if (major_a != DGB200_K_MAJOR || major_b != DGB200_K_MAJOR)
-        return fail(DGB200_ERR_UNSUPPORTED, "MN-major FP8 operands are not built yet");
-    DGB_REQUIRE(lda >= k && ldb >= k && ldd >= n);
+    DGB_REQUIRE(major_a == DGB200_K_MAJOR || major_a == DGB200_MN_MAJOR);
+    DGB_REQUIRE(major_b == DGB200_K_MAJOR || major_b == DGB200_MN_MAJOR);
+    DGB_REQUIRE(lda >= (major_a == DGB200_K_MAJOR ? k : m) && ldb >= (major_b == DGB200_K_MAJOR ? k : n) && ldd >= n);
     DGB_REQUIRE(sfa_stride >= align_up(m, 4) && sfb_stride >= align_up(n, 4));
     GemmCall c{};
     c.type = kDense;
     c.a = a, c.b = b, c.sfa = sfa, c.sfb = sfb, c.d = d, c.grouped_layout = nullptr;
-    c.m = m, c.n = n, c.k = k, c.groups = 1, c.a_rows = m;
+    c.x_mn = major_a == DGB200_MN_MAJOR, c.w_mn = major_b == DGB200_MN_MAJOR;
+    c.m = m, c.n = n, c.k = k, c.groups = 1, c.a_rows = c.x_mn ? k : m;   // rows of the A tensor map's outer extent
     c.lda = lda, c.ldb = ldb, c.ldd = ldd;
     c.sfa_stride = sfa_stride, c.sfb_stride = sfb_stride;
     c.sfa_cols = align_up(m, 4), c.sfb_cols = align_up(n, 4);
@@ -587,11 +659,12 @@ int dgb200_m_grouped_fp8_gemm_nt_contiguous(const void* a, const int32_t* sfa, c
     DGB_REQUIRE(n > 0 && k > 0 && num_groups > 0);  // gemm.hpp:192
     if (m == 0) return DGB200_OK;                    // gemm.hpp:210-211
     DGB_REQUIRE(grouped_layout != nullptr);
-    if (major_b != DGB200_K_MAJOR) return fail(DGB200_ERR_UNSUPPORTED, "MN-major FP8 operands are not built yet");
-    DGB_REQUIRE(lda >= k && ldb >= k && ldd >= n);
+    DGB_REQUIRE(major_b == DGB200_K_MAJOR || major_b == DGB200_MN_MAJOR);
+    DGB_REQUIRE(lda >= k && ldb >= (major_b == DGB200_K_MAJOR ? k : n) && ldd >= n);
     DGB_REQUIRE(sfa_stride >= align_up(m, 4) && sfb_stride >= align_up(n, 4));
     GemmCall c{};
     c.type = use_psum_layout ? kMContiguousPsum : kMContiguous;
+    c.w_mn = major_b == DGB200_MN_MAJOR;
     c.a = a, c.b = b, c.sfa = sfa, c.sfb = sfb, c.d = d, c.grouped_layout = grouped_layout;
     c.m = m, c.n = n, c.k = k, c.groups = num_groups, c.a_rows = m;
     c.lda = lda, c.ldb = ldb, c.ldd = ldd;
@@ -628,11 +701,29 @@ int dgb200_m_grouped_fp8_gemm_nt_masked(const void* a, const int32_t* sfa, const
 }
 
 int dgb200_k_grouped_fp8_gemm_tn_contiguous(const void* a, const int32_t* sfa, const void* b, const int32_t* sfb,
-                                            float* d, const int32_t* ks_host, int num_groups, int m, int n, int gran_k,
-                                            void* stream) {
-    (void)a, (void)sfa, (void)b, (void)sfb, (void)d, (void)ks_host, (void)num_groups, (void)m, (void)n, (void)gran_k,
-        (void)stream;
-    return fail(DGB200_ERR_UNSUPPORTED, "k-grouped FP8 GEMM is not built yet");
+                                            float* d, const int32_t* grouped_layout, int num_groups, int m, int n,
+                                            int sum_k, int sf_rows, int gran_k, int use_psum_layout, void* stream) {
+    DGB_REQUIRE(gran_k == 32 || gran_k == 128);                      // gemm.hpp:313
+    DGB_REQUIRE(num_groups > 0 && m >= 0 && n >= 0 && sum_k >= 0);
+    if (m == 0 || n == 0 || sum_k == 0) return DGB200_OK;            // D already holds C (gemm.hpp:334-335)
+    DGB_REQUIRE(grouped_layout != nullptr && sf_rows > 0);
+    DGB_REQUIRE(m % 4 == 0 && n % 4 == 0);                           // packed k-grouped SFs are [rows, mn] contiguous
+    const int k_alignment = rt().mk_alignment;
+    DGB_REQUIRE(k_alignment % 32 == 0);                              // gemm.hpp:315
+    GemmCall c{};
+    c.type = use_psum_layout ? kKGroupedPsum : kKGrouped;
+    c.x_mn = c.w_mn = true;
+    c.a = a, c.b = b, c.sfa = sfa, c.sfb = sfb, c.d = d, c.grouped_layout = grouped_layout;
+    c.m = m, c.n = n, c.k = sum_k, c.groups = num_groups, c.a_rows = sum_k;
+    c.lda = m, c.ldb = n, c.ldd = n;
+    c.sfa_stride = m, c.sfb_stride = n, c.sfa_cols = m, c.sfb_cols = n;
+    c.sfa_krows = sf_rows, c.sfb_krows = sf_rows;
+    c.gran_k_a = gran_k, c.gran_k_b = gran_k;
+    c.d_dtype = DGB200_FP32, c.accumulate = 1;
+    c.expected_m = m, c.alignment = k_alignment, c.zero_padding = 0;
+    c.workspace = nullptr, c.workspace_bytes = 0;
+    c.stream = static_cast<cudaStream_t>(stream);
+    return run_gemm(c);
 }
 
 int dgb200_plan(int gemm_type, int m, int n, int k, int num_groups, int expected_m, int alignment, int num_sms,

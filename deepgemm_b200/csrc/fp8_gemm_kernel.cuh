@@ -34,6 +34,8 @@ enum GemmType : int {
     kMContiguous = 1,   // rows of A grouped, grouped_layout[r] = group id (-1 = padding)      (gemm.hpp:166)
     kMMasked = 2,       // A[G,Mmax,K], rows < masked_m[g] valid                                 (gemm.hpp:250)
     kMContiguousPsum = 3,  // grouped_layout[g] = end row of group g, starts aligned              (scheduler/gemm.cuh:217-237)
+    kKGrouped = 4,      // D[g] += A[k_g, :M]^T B[k_g, :N], grouped_layout[g] = K of group g        (gemm.hpp:299, sched :259-283)
+    kKGroupedPsum = 5,  // same, grouped_layout[g] = end K of group g, starts aligned to m_alignment
 };
 
 constexpr uint32_t kBlockN = 128;        // weight rows per CTA == TMEM lanes
@@ -69,8 +71,10 @@ struct GemmParams {
     long long* debug_ts;        // optional (development): CTA 0 stamps clock64() at 10 points of its life
     uint32_t num_n_units;       // ceil(n / (128 * cluster))
     uint32_t num_m_blocks;      // dense / contiguous: ceil(m / block_m)
-    uint32_t m_alignment;       // contiguous layouts: group start alignment
+    uint32_t m_alignment;       // contiguous layouts: group start alignment (K alignment for k-grouped psum)
     uint32_t zero_padding;      // psum: write zeros to [end, aligned end)
+    uint32_t x_swizzle;         // MN-major tokens: swizzle width in bytes (128 / 64 / 32) = rows of one TMA box
+    uint32_t sf_k_span;         // k-grouped: K elements covered by one packed SF word (4 * gran_k)
 };
 
 // ------------------------------------------------------------------------------------------------ scheduler
@@ -88,6 +92,9 @@ struct Tile {
     uint32_t kb_begin, kb_end;  // k-blocks this tile accumulates (a sub-range only under split-K)
     uint32_t split;             // split-K slice index
     uint32_t counter_idx;       // split-K arrival counter of this CTA's output block
+    uint32_t k_base;            // K offset of the tile's group in A / B (k-grouped), else 0
+    uint32_t wk_base;           // K-row offset of the tile's group in an MN-major grouped B ([G,K,N] flattened), else 0
+    uint32_t last_umma;         // UMMAs (32 K-elements each) to issue in the last k-block (4 unless K ends inside it)
 };
 
 // kCluster = CTAs per cluster: 1 (single CTA MMA), 2 (one cta_group::2 pair) or 4 / 8 (2 / 4 pairs that work on
@@ -102,6 +109,9 @@ struct Scheduler {
     uint32_t iter = 0;
     // grouped walk state
     uint32_t g = 0, unit_cum = 0, row_start = 0, row_end = 0;
+    // k-grouped walk state: K range of the current group, packed-SF rows before it, non-empty groups before it
+    uint32_t k_start = 0, k_end = 0, sf_rows_before = 0;
+    bool kg_loaded = false;
 
     __device__ Scheduler(const GemmParams& p_, uint32_t rank) : p(p_), cta_rank(rank) {
         cluster_id = blockIdx.x / kCluster;
@@ -127,6 +137,53 @@ struct Scheduler {
         uint32_t m_blk, n_unit, group = 0;
         const uint32_t num_kb_total = (p.k + kBlockK - 1) / kBlockK;
         t.kb_begin = 0, t.kb_end = num_kb_total, t.split = 0, t.counter_idx = 0;
+        t.k_base = 0, t.wk_base = 0;
+        t.last_umma = ((p.k - (num_kb_total - 1) * kBlockK) + kUmmaK - 1) / kUmmaK;
+        if constexpr (kGemmType == kKGrouped || kGemmType == kKGroupedPsum) {
+            // groups are walked in order; every non-empty group contributes num_m_blocks * num_n_units tiles
+            const uint32_t per_group = p.num_m_blocks * num_n_units;
+            auto load_group = [&]() {
+                const uint32_t v = static_cast<uint32_t>(max(0, __ldg(p.grouped_layout + g)));
+                if constexpr (kGemmType == kKGroupedPsum) {
+                    k_start = (k_end + p.m_alignment - 1) / p.m_alignment * p.m_alignment;
+                    k_end = max(k_start, v);
+                } else {
+                    k_start = k_end;
+                    k_end = k_start + v;
+                }
+            };
+            if (!kg_loaded) {
+                if (p.num_groups == 0) return false;
+                load_group();
+                kg_loaded = true;
+            }
+            while (true) {
+                const bool empty = k_end == k_start;
+                if (!empty && idx < (unit_cum + 1) * per_group) break;
+                if (!empty) {
+                    unit_cum += 1;
+                    sf_rows_before += (k_end - k_start + p.sf_k_span - 1) / p.sf_k_span;
+                }
+                if (++g >= p.num_groups) return false;
+                load_group();
+            }
+            split(idx - unit_cum * per_group, p.num_m_blocks, m_blk, n_unit);
+            const uint32_t kg = k_end - k_start;
+            t.kb_end = (kg + kBlockK - 1) / kBlockK;
+            t.last_umma = ((kg - (t.kb_end - 1) * kBlockK) + kUmmaK - 1) / kUmmaK;
+            t.k_base = k_start;
+            t.x_row = m_blk * p.block_m;
+            t.d_row = g * p.m + t.x_row;
+            t.sfx_col = t.x_row;
+            t.sfx_row = sf_rows_before;
+            t.valid_m = min(p.block_m, p.m - t.x_row);
+            t.store_m = t.valid_m;
+            t.n0 = (n_unit * kCtaGroup + (cta_rank & 1)) * kBlockN;
+            t.w_row = t.n0;
+            t.sfw_col = t.n0;
+            t.sfw_row = sf_rows_before;
+            return true;
+        }
         if constexpr (kGemmType == kDense || kGemmType == kMContiguous) {
             const uint32_t num_m = (p.num_m_blocks + kPairs - 1) / kPairs;   // m-blocks are handed out kPairs at a time
             uint32_t local = idx;
@@ -138,6 +195,7 @@ struct Scheduler {
                 local = idx - t.split * per_split;
                 t.kb_begin = t.split * p.kb_per_split;
                 t.kb_end = min(num_kb_total, t.kb_begin + p.kb_per_split);
+                if (t.kb_end != num_kb_total) t.last_umma = kBlockK / kUmmaK;
             } else if (idx >= num_m * num_n_units) {
                 return false;
             }
@@ -195,6 +253,7 @@ struct Scheduler {
         }
         t.n0 = (n_unit * kCtaGroup + (cta_rank & 1)) * kBlockN;
         t.w_row = group * p.n + t.n0;
+        t.wk_base = group * p.k;
         t.sfw_col = t.n0;
         t.sfw_row = group * p.num_kp_w;
         return true;
@@ -274,7 +333,9 @@ __device__ __forceinline__ void splitk_finalize(const float* ws, size_t slice_el
         if (p.debug_ts != nullptr && blockIdx.x == 0) p.debug_ts[i] = clock64(); \
     } while (0)
 
-template <int kGemmType, int kCluster, typename out_t, bool kAccumulate>
+// kXMn / kWMn: the token / weight operand is MN-major in global memory (its M / N extent is contiguous, K strided):
+// fp8_gemm_{nn,tn,tt}, m_grouped nn, and both operands of the K-grouped weight-gradient GEMM.
+template <int kGemmType, int kCluster, typename out_t, bool kAccumulate, bool kXMn = false, bool kWMn = false>
 __global__ void __launch_bounds__(kNumThreads, 1)
 fp8_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
                 const __grid_constant__ CUtensorMap map_sfx, const __grid_constant__ CUtensorMap map_sfw,
@@ -376,12 +437,23 @@ fp8_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
                     const bool first = kb == t.kb_begin;
                     const bool load_sfw = (kb & sfw_mask) == 0 || first, load_sfx = (kb & sfx_mask) == 0 || first;
                     mbar_arrive_expect_tx(full, ab_bytes + (load_sfw ? sfw_tx : 0u) + (load_sfx ? sfx_tx : 0u));
-                    if constexpr (kPairs == 1)
-                        tma_load_2d(&map_w, full, slot, k0, t.w_row, kEvictNormal);
-                    else
+                    // K-major operand: box = 128 K-bytes x rows, coordinates (k, row).
+                    // MN-major operand: box = S contiguous MN-bytes x 128 K-rows, coordinates (mn, k row); S = 128 for the
+                    // weights (one swizzle atom), p.x_swizzle for the tokens (load_m / S atoms side by side).
+                    if constexpr (kWMn) {
+                        tma_load_2d(&map_w, full, slot, t.n0, t.wk_base + t.k_base + k0, kEvictNormal);
+                    } else if constexpr (kPairs == 1) {
+                        tma_load_2d(&map_w, full, slot, t.k_base + k0, t.w_row, kEvictNormal);
+                    } else {
                         tma_load_2d_multicast(&map_w, full, slot + pair_idx * (kWRows * kBlockK), k0, t.w_row + pair_idx * kWRows,
                                               w_mask, kEvictNormal);
-                    tma_load_2d(&map_x, full, slot + off_x, k0, x_row, kEvictNormal);
+                    }
+                    if constexpr (kXMn) {
+                        for (uint32_t i = 0, off = 0; i < load_m; i += p.x_swizzle, off += p.x_swizzle * kBlockK)
+                            tma_load_2d(&map_x, full, slot + off_x + off, x_row + i, t.k_base + k0, kEvictNormal);
+                    } else {
+                        tma_load_2d(&map_x, full, slot + off_x, t.k_base + k0, x_row, kEvictNormal);
+                    }
                     if (load_sfw) tma_load_2d(&map_sfw, full, slot + off_sfw, t.sfw_col, t.sfw_row + (kb >> p.sf_shift_w), kEvictNormal);
                     if (load_sfx) tma_load_2d(&map_sfx, full, slot + off_sfx, t.sfx_col, t.sfx_row + (kb >> p.sf_shift_x), kEvictNormal);
                     if (first) DGB_STAMP(2);
@@ -393,10 +465,19 @@ fp8_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
         if (is_leader) {
             Scheduler<kGemmType, kCluster> sched(p, cta_rank);
             Tile t;
-            const uint32_t idesc_base = make_idesc(128 * kCtaGroup, p.block_m, 0, 0);
-            // descriptors of slot 0; a slot offset adds (bytes >> 4) to the 14-bit start-address field
-            const uint64_t w_desc0 = make_smem_desc(smem_base, 0, 1024, kLayoutSwizzle128B);
-            const uint64_t x_desc0 = make_smem_desc(smem_base + off_x, 0, 1024, kLayoutSwizzle128B);
+            const uint32_t idesc_base = make_idesc(128 * kCtaGroup, p.block_m, kWMn ? 1 : 0, kXMn ? 1 : 0);
+            // descriptors of slot 0; a slot offset adds (bytes >> 4) to the 14-bit start-address field.
+            //   K-major : 8-row x 128 B swizzle atoms stacked along MN (SBO 1024); +32 B per UMMA_K step
+            //   MN-major: atoms of S bytes (MN) x 8 K-rows; SBO = 8*S between K groups, LBO = 128*S between MN atoms;
+            //             +32 K-rows = 32*S bytes per UMMA_K step            (cf. reference mma/sm100.cuh:96-132)
+            const uint32_t xs = kXMn ? p.x_swizzle : 128u;
+            const uint32_t x_layout = xs == 128 ? kLayoutSwizzle128B : (xs == 64 ? kLayoutSwizzle64B : kLayoutSwizzle32B);
+            const uint64_t w_desc0 = kWMn ? make_smem_desc(smem_base, kBlockK * 128, 8 * 128, kLayoutSwizzle128B)
+                                          : make_smem_desc(smem_base, 0, 1024, kLayoutSwizzle128B);
+            const uint64_t x_desc0 = kXMn ? make_smem_desc(smem_base + off_x, kBlockK * xs, 8 * xs, x_layout)
+                                          : make_smem_desc(smem_base + off_x, 0, 1024, kLayoutSwizzle128B);
+            const uint32_t w_kstep = kWMn ? (kUmmaK * 128) >> 4 : kUmmaK >> 4;
+            const uint32_t x_kstep = kXMn ? (kUmmaK * xs) >> 4 : kUmmaK >> 4;
             const uint64_t sfw_desc0 = make_smem_desc(smem_base + off_sfw, 0, 128, kLayoutNoSwizzle);
             const uint64_t sfx_desc0 = make_smem_desc(smem_base + off_sfx, 0, 128, kLayoutNoSwizzle);
             const uint32_t tmem_sfw = tmem_base + kTmemColSFW, tmem_sfx = tmem_base + kTmemColSFX;
@@ -426,10 +507,12 @@ fp8_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
                         // one UE8M0 byte per 32 K-elements: byte id inside the packed word
                         const uint32_t idesc = idesc_with_sf_ids(idesc_base, sfw_mask ? sfw_sub : 0u, sfx_mask ? sfx_sub : 0u);
                         const uint32_t id_step = (sfw_mask ? 0u : (1u << 29)) | (sfx_mask ? 0u : (1u << 4));  // gran_k 32
+                        const uint32_t n_umma = kb + 1 == t.kb_end ? t.last_umma : kBlockK / kUmmaK;   // K may end inside the block
 #pragma unroll
                         for (uint32_t j = 0; j < kBlockK / kUmmaK; ++j)
-                            mma_mxf8_block_scale<kCtaGroup>(tmem_d, w_desc + j * (kUmmaK >> 4), x_desc + j * (kUmmaK >> 4),
-                                                           idesc + j * id_step, tmem_sfw, tmem_sfx, (!first || j != 0) ? 1u : 0u);
+                            if (j < n_umma)
+                                mma_mxf8_block_scale<kCtaGroup>(tmem_d, w_desc + j * w_kstep, x_desc + j * x_kstep,
+                                                               idesc + j * id_step, tmem_sfw, tmem_sfx, (!first || j != 0) ? 1u : 0u);
                         // retire -> the smem slot may be overwritten (signals every CTA of the pair)
                         mma_commit<kCtaGroup>(empty_bar + ring.bar, kEmptyMask);
                         if (first) DGB_STAMP(4);

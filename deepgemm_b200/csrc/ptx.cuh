@@ -254,6 +254,8 @@ DGB_DEVICE uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint3
 }
 constexpr uint32_t kLayoutNoSwizzle = 0;
 constexpr uint32_t kLayoutSwizzle128B = 2;
+constexpr uint32_t kLayoutSwizzle64B = 4;
+constexpr uint32_t kLayoutSwizzle32B = 6;
 
 // 32-bit instruction descriptor for kind::mxf8f6f4.block_scale, E4M3 x E4M3, UE8M0 scales, FP32 accumulate:
 //   [4,6) b_sf_id | [7,10) a_fmt | [10,13) b_fmt | 15 a_major | 16 b_major | [17,23) N>>3 | 23 scale=UE8M0

@@ -76,13 +76,20 @@ transpose_sf_fp32_kernel(const float* __restrict__ sf, float* __restrict__ out, 
 //   by a short uniform scan, so nothing but the grid size depends on host-side knowledge of `ks`.
 __global__ void __launch_bounds__(128)
 pack_sf_ue8m0_k_grouped_kernel(const float* __restrict__ sf, uint32_t* __restrict__ out, uint32_t mn,
-                               const int32_t* __restrict__ ks, uint32_t num_groups, uint32_t gran_k) {
+                               const int32_t* __restrict__ ks, uint32_t num_groups, uint32_t gran_k,
+                               uint32_t psum_alignment /* 0: ks[g] = K of group g; else ks[g] = end K, starts aligned */) {
     asm volatile("griddepcontrol.wait;" ::: "memory");
     const uint32_t c = blockIdx.x * 128 + threadIdx.x;
     const uint32_t pr = blockIdx.y;
-    uint32_t in_row = 0, packed_row = 0, first = 0, count = 0;
+    uint32_t in_row = 0, packed_row = 0, first = 0, count = 0, prev_end = 0;
     for (uint32_t g = 0; g < num_groups; ++g) {
-        const uint32_t kg = static_cast<uint32_t>(max(0, __ldg(ks + g)));
+        const uint32_t v = static_cast<uint32_t>(max(0, __ldg(ks + g)));
+        uint32_t kg = v;
+        if (psum_alignment) {
+            const uint32_t start = (prev_end + psum_alignment - 1) / psum_alignment * psum_alignment;
+            kg = v > start ? v - start : 0u;
+            prev_end = max(start, v);
+        }
         const uint32_t n_in = (kg + gran_k - 1) / gran_k, n_packed = (n_in + 3) / 4;
         if (pr < packed_row + n_packed) {
             first = in_row + (pr - packed_row) * 4;
@@ -98,7 +105,7 @@ pack_sf_ue8m0_k_grouped_kernel(const float* __restrict__ sf, uint32_t* __restric
         if (bits & 0x807fffffu) asm volatile("trap;");
         packed |= (bits >> 23) << (8 * j);
     }
-    out[static_cast<size_t>(pr) * mn + c] = packed;
+    out[static_cast<size_t>(pr) * mn + c] = packed;   // rows past the last group (upper-bound allocations) get 0
 }
 
 }  // namespace dgb200

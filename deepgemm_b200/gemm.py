@@ -224,8 +224,39 @@ def k_grouped_fp8_gemm_tn_contiguous(a: TensorPair, b: TensorPair, d: torch.Tens
                                      grouped_layout: torch.Tensor, c: Optional[torch.Tensor] = None,
                                      recipe: Tuple[int, int, int] = (1, 1, 128), compiled_dims: str = 'mn',
                                      use_psum_layout: bool = False) -> None:
-    """Weight gradient D[g] = C[g] + A[k_g,:M].T @ B[k_g,:N] (gemm.hpp:299-346)."""
-    raise RuntimeError('k_grouped_fp8_gemm_tn_contiguous is not built yet (deepgemm_b200)')
+    """Weight gradient D[g] = C[g] + A[k_g,:M].T @ B[k_g,:N]: A [sum_k, M], B [sum_k, N] FP8 (both MN-major), D = C
+    [G, M, N] FP32 accumulated in place, per-(gran_k x 1) scale factors (gemm.hpp:299-346)."""
+    (a_t, sfa), (b_t, sfb) = a, b
+    _check_fp8(a_t), _check_fp8(b_t)
+    _require(recipe[0] == 1 and recipe[1] == 1, 'recipe is (1, 1, gran_k)')
+    gran_k = recipe[2]
+    _require(gran_k in (32, 128), 'gran_k == 32 or gran_k == 128')
+    k_alignment = get_mk_alignment_for_contiguous_layout()
+    _require(k_alignment % 32 == 0, 'k_alignment % 32 == 0')
+    _require(d.dim() == 3 and a_t.dim() == 2 and b_t.dim() == 2, 'd is 3-D, a and b are 2-D')
+    num_groups, m, n = d.shape
+    (sum_k_a, m_), (sum_k_b, n_) = a_t.shape, b_t.shape
+    _require(grouped_layout.is_contiguous() and grouped_layout.dtype == torch.int32 and grouped_layout.numel() == num_groups,
+             'grouped_layout is a contiguous int32 [num_groups] tensor')
+    if ks_cpu is not None and len(ks_cpu) > 0:
+        _require(len(ks_cpu) == num_groups, 'len(ks_cpu) == num_groups')
+        _require(all(k % k_alignment == 0 for k in ks_cpu), 'k % k_alignment == 0')
+        sum_k = sum(ks_cpu)
+    else:
+        _require(use_psum_layout, 'ks_cpu may only be omitted with use_psum_layout')
+        sum_k = sum_k_a
+    _require(m == m_ and n == n_ and sum_k == sum_k_a and sum_k == sum_k_b, 'shapes agree')
+    _require(a_t.is_contiguous() and b_t.is_contiguous() and d.is_contiguous(), 'a, b, d are contiguous')
+    _require(c is not None and c.is_contiguous(), 'c is required and contiguous')
+    _require(d.dtype == torch.float32, 'd.dtype == float')
+    if _early_return(m, n, sum_k, d, c):
+        return
+    sfa_t = _layout.transform_k_grouped_sf_into_required_layout(sfa, ks_cpu, grouped_layout, recipe, k_alignment, use_psum_layout)
+    sfb_t = _layout.transform_k_grouped_sf_into_required_layout(sfb, ks_cpu, grouped_layout, recipe, k_alignment, use_psum_layout)
+    _require(sfa_t.size(0) == sfb_t.size(0), 'sfa and sfb have the same number of packed rows')
+    check(lib().dgb200_k_grouped_fp8_gemm_tn_contiguous(
+        a_t.data_ptr(), sfa_t.data_ptr(), b_t.data_ptr(), sfb_t.data_ptr(), d.data_ptr(), grouped_layout.data_ptr(),
+        num_groups, m, n, sum_k, sfa_t.size(0), gran_k, int(use_psum_layout), _stream()))
 
 
 def k_grouped_fp8_gemm_nt_contiguous(a, b, d, ks_cpu, grouped_layout, c=None, recipe=(1, 1, 128), compiled_dims='mn',

@@ -74,7 +74,54 @@ def get_mn_major_tma_aligned_packed_ue8m0_tensor(sf: torch.Tensor, psum_layout: 
 def get_k_grouped_mn_major_tma_aligned_packed_ue8m0_tensor(sf: torch.Tensor, grouped_layout: torch.Tensor,
                                                            ks_cpu: Optional[Sequence[int]], gran_k: int, k_alignment: int,
                                                            use_psum_layout: bool = False) -> torch.Tensor:
-    raise RuntimeError('k-grouped SF packing is not built yet (deepgemm_b200)')
+    """K-grouped FP32 SFs [sum_g ceil(k_g/gran_k), mn] -> packed int32 [sum_g ceil(k_g/(4 gran_k)), mn]; every group is
+    padded to a multiple of 4 granules on its own (smxx_layout.hpp:255-316). `grouped_layout` (device) holds per-group K,
+    or end offsets with `use_psum_layout`; `ks_cpu` is only used to size the output (None / [] -> upper bound)."""
+    _require(gran_k in (32, 128), 'gran_k == 32 or gran_k == 128')
+    _require(k_alignment % 32 == 0, 'k_alignment % 32 == 0')
+    _require(sf.dim() == 2 and sf.dtype == torch.float32 and sf.is_contiguous(), 'sf is a contiguous 2-D float tensor')
+    sf_k, mn = sf.shape
+    num_groups = grouped_layout.numel()
+    _require(num_groups <= 128 and mn % 4 == 0, 'num_groups <= 128 and mn % 4 == 0')
+    _require(grouped_layout.is_contiguous() and grouped_layout.dtype == torch.int32, 'grouped_layout is contiguous int32')
+    has_ks = ks_cpu is not None and len(ks_cpu) > 0
+    if has_ks:
+        _require(len(ks_cpu) == num_groups, 'len(ks_cpu) == num_groups')
+        packed_rows = sum(_ceil_div(k, gran_k * 4) for k in ks_cpu)
+        _require(use_psum_layout or sum(_ceil_div(k, gran_k) for k in ks_cpu) == sf_k, 'sum(ceil(k/gran_k)) == sf.size(0)')
+    else:
+        _require(use_psum_layout, 'ks_cpu may only be omitted with use_psum_layout')
+        packed_rows = (sf_k + num_groups * 3) // 4
+    out = torch.empty((packed_rows, mn), dtype=torch.int32, device=sf.device)
+    if packed_rows:
+        check(lib().dgb200_pack_sf_ue8m0_k_grouped(sf.data_ptr(), out.data_ptr(), mn, grouped_layout.data_ptr(), num_groups,
+                                                   packed_rows, gran_k, k_alignment if use_psum_layout else 0, _stream()))
+    return out
+
+
+def check_k_grouped_packed_ue8m0_tensor(sf: torch.Tensor, grouped_layout: torch.Tensor, ks_cpu, gran_k: int,
+                                        k_alignment: int, use_psum_layout: bool) -> torch.Tensor:
+    """Validate a caller-packed k-grouped SF tensor (smxx_layout.hpp:319-352)."""
+    _require(sf.dtype == torch.int32 and sf.dim() == 2 and sf.is_contiguous(), 'sf is a contiguous 2-D int tensor')
+    _require(sf.size(1) % 4 == 0 and sf.size(0) > 0, 'mn % 4 == 0 and packed_sf_k > 0')
+    if ks_cpu is not None and len(ks_cpu) > 0:
+        _require(len(ks_cpu) == grouped_layout.numel(), 'len(ks_cpu) == num_groups')
+        if not use_psum_layout:
+            _require(sf.size(0) >= sum(_ceil_div(k, gran_k * 4) for k in ks_cpu), 'enough packed SF rows')
+    else:
+        _require(use_psum_layout, 'ks_cpu may only be omitted with use_psum_layout')
+    return sf
+
+
+def transform_k_grouped_sf_into_required_layout(sf, ks_cpu, grouped_layout, recipe, k_alignment, use_psum_layout):
+    """csrc/apis/layout.hpp:92-122 (arch 10 branch)."""
+    _require(sf.dim() == 2 and recipe[0] == 1 and recipe[1] == 1, 'k-grouped SFs are 2-D with a (1, 1, gran_k) recipe')
+    if sf.dtype == torch.float32:
+        return get_k_grouped_mn_major_tma_aligned_packed_ue8m0_tensor(sf, grouped_layout, ks_cpu, recipe[2], k_alignment,
+                                                                      use_psum_layout)
+    if sf.dtype == torch.int32:
+        return check_k_grouped_packed_ue8m0_tensor(sf, grouped_layout, ks_cpu, recipe[2], k_alignment, use_psum_layout)
+    raise RuntimeError('Unknown cases')
 
 
 def check_sf_layout(sf: torch.Tensor, mn: int, k: int, gran_mn: int, gran_k: int, num_groups: Optional[int],

@@ -73,10 +73,13 @@ int dgb200_transpose_sf_fp32(const float* sf, float* out, int mn, int sf_k, int 
                              int64_t stride_g, int64_t stride_mn, int64_t stride_k, void* stream);
 
 /* K-grouped variant (get_k_grouped_mn_major_tma_aligned_packed_ue8m0_tensor, smxx_layout.hpp:255-316):
- *   sf  : fp32 [sum_g ceil(k_g/gran_k), mn] contiguous;  out: int32 [sum_g ceil(k_g/(4*gran_k)), mn] contiguous.
- *   ks_host: per-group K (host array, as the reference's `ks_cpu`). */
-int dgb200_pack_sf_ue8m0_k_grouped(const float* sf, int32_t* out, int mn, const int32_t* ks_host, int num_groups,
-                                   int gran_k, void* stream);
+ *   sf  : fp32 [sum_g ceil(k_g/gran_k), mn] contiguous;  out: int32 [packed_rows, mn] contiguous, where every group
+ *   is padded to a multiple of 4 granules on its own (packed_rows = sum_g ceil(k_g/(4*gran_k)), computed by the caller
+ *   from its host copy of the per-group K, the reference's `ks_cpu`, or an upper bound: extra rows are zero-filled).
+ *   `ks_device`: int32[num_groups]: K of each group (psum_alignment == 0) or end K of each group, whose start is the
+ *   previous end rounded up to `psum_alignment` (psum layout). */
+int dgb200_pack_sf_ue8m0_k_grouped(const float* sf, int32_t* out, int mn, const int32_t* ks_device, int num_groups,
+                                   int packed_rows, int gran_k, int psum_alignment, void* stream);
 
 /* ---- GEMMs ------------------------------------------------------------------------------------------------ */
 
@@ -116,11 +119,14 @@ int dgb200_m_grouped_fp8_gemm_nt_masked(const void* a, const int32_t* sfa, const
                                         int sfa_stride, int sfb_stride, int gran_k_a, int gran_k_b, void* stream);
 
 /* Weight gradient, K grouped           -- k_grouped_fp8_gemm_tn_contiguous, csrc/apis/gemm.hpp:299-346.
- *   a [sum_k, m], b [sum_k, n] (both MN-major), d [num_groups, m, n] fp32 accumulated in place (D holds C),
- *   ks_host int32[num_groups] per-group K (multiples of the mk alignment), sfa/sfb k-grouped packed layouts. */
+ *   a [sum_k, m], b [sum_k, n] e4m3 (both MN-major: m / n contiguous), d [num_groups, m, n] fp32 accumulated IN PLACE
+ *   (D holds C on entry), grouped_layout int32[num_groups] on the device: K of each group (use_psum_layout == 0) or
+ *   the end K of each group with group starts aligned to the mk alignment (use_psum_layout != 0). Per-group K must be
+ *   a multiple of 32. sfa / sfb: k-grouped packed UE8M0 [sf_rows, m] / [sf_rows, n] (dgb200_pack_sf_ue8m0_k_grouped),
+ *   gran_k 32 or 128 for both. Groups with K == 0 leave D untouched. */
 int dgb200_k_grouped_fp8_gemm_tn_contiguous(const void* a, const int32_t* sfa, const void* b, const int32_t* sfb,
-                                            float* d, const int32_t* ks_host, int num_groups, int m, int n,
-                                            int gran_k, void* stream);
+                                            float* d, const int32_t* grouped_layout, int num_groups, int m, int n,
+                                            int sum_k, int sf_rows, int gran_k, int use_psum_layout, void* stream);
 
 /* ---- introspection (bench / tests) -------------------------------------------------------------------------- */
 typedef struct dgb200_config {

@@ -157,6 +157,47 @@ def m_grouped_fp8_gemm_nt_masked(a, b, masked_m: torch.Tensor, recipe=(1, 128, 1
     return d
 
 
+def k_grouped_fp8_gemm_tn_contiguous(a, b, c: torch.Tensor, ks: Sequence[int], gran_k: int = 128,
+                                     group_ends: Optional[Sequence[int]] = None, high_precision: bool = True) -> torch.Tensor:
+    """Oracle for k_grouped_fp8_gemm_tn_contiguous (gemm.hpp:299-346): a=(A [sum_k, M] e4m3, SFA [sum ceil(k_g/gran_k), M]),
+    b likewise with N; D[g] = C[g] + A_g^T B_g in FP32. `group_ends` (psum layout): group g occupies rows
+    [end_g - k_g, end_g) of A/B; default: groups back to back. SF rows are compact per group (ceil(k_g/gran_k) each)."""
+    (a_t, sfa), (b_t, sfb) = a, b
+    d = c.clone().float()
+    if group_ends is None:
+        group_ends, acc = [], 0
+        for kg in ks:
+            acc += kg
+            group_ends.append(acc)
+    sf_row = 0
+    for gi, (kg, end) in enumerate(zip(ks, group_ends)):
+        if kg == 0:
+            continue
+        start = end - kg
+        n_sf = ceil_div(kg, gran_k)
+        rows = torch.arange(kg) // gran_k
+        ad = a_t[start:end].float() * sfa[sf_row:sf_row + n_sf][rows]
+        bd = b_t[start:end].float() * sfb[sf_row:sf_row + n_sf][rows]
+        prod = (ad.double().t() @ bd.double()).float() if high_precision else ad.t() @ bd
+        d[gi] += prod
+        sf_row += n_sf
+    return d
+
+
+def pack_sf_ue8m0_k_grouped(sf: torch.Tensor, ks: Sequence[int], gran_k: int) -> torch.Tensor:
+    """K-grouped packed SFs: each group's granules padded to a multiple of 4, packed 4 per int32 along K
+    (restates the per-group use of the wire format in tests/test_layout.py:93-98)."""
+    outs, row = [], 0
+    for kg in ks:
+        n_sf = ceil_div(kg, gran_k)
+        if n_sf == 0:
+            continue
+        part = sf[row:row + n_sf].t().contiguous()                       # [mn, n_sf]
+        outs.append(torch.empty((part.shape[0], ceil_div(n_sf, 4)), dtype=torch.int32).copy_(pack_sf_ue8m0_mn_major(part)).t())
+        row += n_sf
+    return torch.cat(outs) if outs else torch.empty((0, sf.shape[1]), dtype=torch.int32)
+
+
 # ------------------------------------------------------------------------------------------------ CPU baseline
 def bf16_emulated_gemm_nt(a, b, recipe=(1, 128, 128)) -> torch.Tensor:
     """The CPU baseline BASELINE.md section 4 names: dequantise FP8 x UE8M0 to BF16 (exact -- 4 significant bits and

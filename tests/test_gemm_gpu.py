@@ -193,6 +193,106 @@ def test_sf_pack_kernel_bit_exact(dg):
     assert t.shape == sf.shape and t.stride() == (7 * 100, 1, 100) and torch.equal(t, sf)
 
 
+@pytest.mark.parametrize('layout', ['nn', 'tn', 'tt'])
+@pytest.mark.parametrize('m,n,k', [(256, 384, 512), (4096, 512, 1024), (192, 2112, 1536), (100, 256, 640)])
+def test_dense_layout_variants_match_nt_bitwise(dg, layout, m, n, k):
+    """fp8_gemm_{nn,tn,tt}: MN-major operands (csrc/apis/gemm.hpp:126-164). Same numbers, same K order as the NT call on
+    the same quantised data, so the outputs must be bit-identical to it (and NT is pinned to the oracle above)."""
+    _, _, qa, qb = _quant_dense(m, n, k, seed=k)
+    d_nt = torch.empty((m, n), device='cuda', dtype=torch.bfloat16)
+    dg.fp8_gemm_nt(qa, qb, d_nt)
+    a_t = (qa[0].t().contiguous(), qa[1].t().contiguous())       # A given as [K, M]
+    b_t = (qb[0].t().contiguous(), qb[1].t().contiguous())       # B given as [K, N]
+    d = torch.full((m, n), float('nan'), device='cuda', dtype=torch.bfloat16)
+    if layout == 'nn':
+        dg.fp8_gemm_nn(qa, b_t, d)
+    elif layout == 'tn':
+        dg.fp8_gemm_tn(a_t, b_t, d)
+    else:
+        dg.fp8_gemm_tt(a_t, qb, d)
+    assert torch.equal(d, d_nt), layout
+
+
+@pytest.mark.parametrize('gran_k', [128, 32])
+@pytest.mark.parametrize('use_psum', [False, True])
+def test_k_grouped_matches_oracle(dg, gran_k, use_psum):
+    """Weight gradient: D[g] = C[g] + A_g^T B_g, FP32 in place (tests/test_fp8_fp4.py:193-242 covers the same cases:
+    empty groups, K tails, gran_k 32/128, psum layout with unaligned group ends)."""
+    from deepgemm_b200.utils import per_channel_cast_to_fp8
+    from oracle import blockwise
+    random.seed(gran_k + use_psum)
+    gen = torch.Generator(device='cuda').manual_seed(9)
+    g, m, n = 5, 512, 384
+    k_alignment = 128 if gran_k == 128 else 32
+    dg.set_mk_alignment_for_contiguous_layout(k_alignment)
+    try:
+        real_ks = [k_alignment * random.randint(1, 6) for _ in range(g)]
+        real_ks[1] = 0                                              # an empty group
+        real_ks[3] = k_alignment                                    # a K tail shorter than one k-block (when 32)
+        if use_psum:
+            real_ks[0] -= 7                                         # psum: group ends need not be aligned
+            ends, prev = [], 0
+            for kk in real_ks:
+                prev = blockwise.align(prev, k_alignment) + kk
+                ends.append(prev)
+            total_k = blockwise.align(ends[-1], k_alignment)
+        else:
+            ends, total_k = None, sum(real_ks)
+        a = torch.zeros((total_k, m), device='cuda', dtype=torch.bfloat16)
+        b = torch.zeros((total_k, n), device='cuda', dtype=torch.bfloat16)
+        a8 = torch.zeros((total_k, m), device='cuda', dtype=torch.float8_e4m3fn)
+        b8 = torch.zeros((total_k, n), device='cuda', dtype=torch.float8_e4m3fn)
+        sfa_l, sfb_l, pos = [], [], 0
+        for i, kk in enumerate(real_ks):
+            end = ends[i] if use_psum else pos + kk
+            start = end - kk
+            pos = end
+            if kk == 0:
+                continue
+            pad = blockwise.align(kk, gran_k)
+            xa = torch.zeros((pad, m), device='cuda', dtype=torch.bfloat16)
+            xb = torch.zeros((pad, n), device='cuda', dtype=torch.bfloat16)
+            xa[:kk] = torch.randn((kk, m), device='cuda', dtype=torch.bfloat16, generator=gen)
+            xb[:kk] = torch.randn((kk, n), device='cuda', dtype=torch.bfloat16, generator=gen)
+            qa, sa = per_channel_cast_to_fp8(xa, True, gran_k)
+            qb, sb = per_channel_cast_to_fp8(xb, True, gran_k)
+            a8[start:end], b8[start:end] = qa[:kk], qb[:kk]
+            sfa_l.append(sa), sfb_l.append(sb)
+        sfa, sfb = torch.cat(sfa_l), torch.cat(sfb_l)
+        c = torch.randn((g, m, n), device='cuda') * 32
+        d = c.clone()
+        layout = torch.tensor(ends if use_psum else real_ks, device='cuda', dtype=torch.int32)
+        ks_arg = [blockwise.align(kk, k_alignment) for kk in real_ks] if use_psum else real_ks
+        dg.k_grouped_fp8_gemm_tn_contiguous((a8, sfa), (b8, sfb), d, ks_arg, layout, c=d, recipe=(1, 1, gran_k),
+                                            use_psum_layout=use_psum)
+        want = blockwise.k_grouped_fp8_gemm_tn_contiguous((a8.cpu(), sfa.cpu()), (b8.cpu(), sfb.cpu()), c.cpu(), real_ks, gran_k,
+                                                          group_ends=ends)
+        _assert_close_to_oracle(d, want, f'k-grouped gran_k={gran_k} psum={use_psum}')
+        assert torch.equal(d[1], c[1])                              # the empty group left its D block untouched
+        if not use_psum:
+            packed = dg.get_k_grouped_mn_major_tma_aligned_packed_ue8m0_tensor(sfa, layout, real_ks, gran_k, k_alignment)
+            assert torch.equal(packed.cpu(), blockwise.pack_sf_ue8m0_k_grouped(sfa.cpu(), real_ks, gran_k))
+    finally:
+        dg.set_mk_alignment_for_contiguous_layout(128)
+
+
+def test_m_grouped_contiguous_nn_layout(dg):
+    """m_grouped_fp8_gemm_nn_contiguous: B given as [G, K, N] (gemm.hpp:234-248) -- bit-identical to the NT call."""
+    from deepgemm_b200.utils import per_token_cast_to_fp8
+    gen = torch.Generator(device='cuda').manual_seed(12)
+    g, n, k, per = 3, 512, 768, 128
+    a = torch.randn((g * per, k), device='cuda', dtype=torch.bfloat16, generator=gen)
+    qa = per_token_cast_to_fp8(a, True)
+    _, qb = _grouped_weights(g, n, k, gen)
+    layout = torch.arange(g, device='cuda', dtype=torch.int32).repeat_interleave(per)
+    d_nt = torch.empty((g * per, n), device='cuda', dtype=torch.bfloat16)
+    dg.m_grouped_fp8_gemm_nt_contiguous(qa, qb, d_nt, layout)
+    b_kn = (qb[0].transpose(1, 2).contiguous(), qb[1].transpose(1, 2).contiguous())   # [G, K, N]
+    d_nn = torch.full_like(d_nt, float('nan'))
+    dg.m_grouped_fp8_gemm_nn_contiguous(qa, b_kn, d_nn, layout)
+    assert torch.equal(d_nn, d_nt)
+
+
 def _grouped_weights(g, n, k, gen):
     from deepgemm_b200.utils import per_block_cast_to_fp8
     b = torch.randn((g, n, k), device='cuda', dtype=torch.bfloat16, generator=gen)
