@@ -216,6 +216,171 @@ def run_dense(args, rank, world, device):
     return out
 
 
+# ------------------------------------------------------------------------------------------------ grouped workloads
+def _grouped_weights(g, n, k, device, seed):
+    """[G,N,K] FP8 weights + 128x128 scales, generated expert by expert to bound memory."""
+    from deepgemm_b200.utils import per_block_cast_to_fp8
+    gen = torch.Generator(device=device).manual_seed(seed)
+    b = torch.empty((g, n, k), device=device, dtype=torch.float8_e4m3fn)
+    sfb = torch.empty((g, (n + 127) // 128, (k + 127) // 128), device=device, dtype=torch.float32)
+    for i in range(g):
+        b[i], sfb[i] = per_block_cast_to_fp8(torch.randn((n, k), device=device, dtype=torch.bfloat16, generator=gen), True)
+    return b, sfb
+
+
+def _time_events(fn, steps, warmup, world):
+    from deepgemm_b200.testing import flush_l2
+    for _ in range(warmup):
+        fn()
+    barrier(world)
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    for s0, s1 in evs:
+        flush_l2()
+        s0.record()
+        fn()
+        s1.record()
+    barrier(world)
+    return sum(a.elapsed_time(b) for a, b in evs) / steps
+
+
+def run_grouped(args, rank, world, device):
+    """BASELINE configs 3 (contiguous prefill, 256 experts, N=4096, K=7168) and 4 (masked decode under a CUDA graph,
+    256 experts, M_max=128, N=7168, K=2048). HBM-bound: roofline = algorithmic bytes / measured HBM copy bandwidth."""
+    import random
+    import deepgemm_b200 as dg
+    from deepgemm_b200 import _lib
+    from deepgemm_b200.utils import per_token_cast_to_fp8
+    peaks, peak_kind = load_peaks()
+    random.seed(0)
+    masked = args.workload == 'masked'
+    g = 256
+    if masked:
+        m_max, n, k, mean_m = 128, 7168, 2048, args.mean_m or 64
+    else:
+        n, k, mean_m = 4096, 7168, args.mean_m or 128
+    b, sfb = _grouped_weights(g, n, k, device, seed=0)
+    sfb_p = dg.transform_sf_into_required_layout(sfb, n, k, (1, 128, 128), g, False)
+    if masked:
+        a = torch.randn((g, m_max, k), device=device, dtype=torch.bfloat16)
+        qs = [per_token_cast_to_fp8(a[i], True) for i in range(g)]
+        qa = (torch.stack([q[0] for q in qs]), torch.stack([q[1] for q in qs]))
+        sfa = dg.transform_sf_into_required_layout(qa[1], m_max, k, (1, 128, 128), g, True)
+        counts = torch.tensor([min(m_max, int(mean_m * random.uniform(0.7, 1.3))) for _ in range(g)], device=device, dtype=torch.int32)
+        d = torch.zeros((g, m_max, n), device=device, dtype=torch.bfloat16)
+        valid = int(counts.sum())
+        call = lambda: dg.m_grouped_fp8_gemm_nt_masked((qa[0], sfa), (b, sfb_p), d, counts, int(1.2 * mean_m))  # noqa: E731
+        call()
+        graph, side = torch.cuda.CUDAGraph(), torch.cuda.Stream()
+        with torch.cuda.stream(side):
+            with torch.cuda.graph(graph, stream=side):
+                call()
+        fn = graph.replay
+        rows_total = valid
+        name = f'masked grouped decode (CUDA graph replay), G=256 M_max=128 N=7168 K=2048 mean_m={mean_m}'
+    else:
+        alignment = dg.get_mk_alignment_for_contiguous_layout()
+        ms = [int(mean_m * random.uniform(0.7, 1.3)) for _ in range(g)]
+        aligned = [(x + alignment - 1) // alignment * alignment for x in ms]
+        m = sum(aligned)
+        a = torch.randn((m, k), device=device, dtype=torch.bfloat16)
+        layout = torch.empty(m, device=device, dtype=torch.int32)
+        s0 = 0
+        for i, (mi, ai) in enumerate(zip(ms, aligned)):
+            layout[s0:s0 + mi] = i
+            layout[s0 + mi:s0 + ai] = -1
+            a[s0 + mi:s0 + ai] = 0
+            s0 += ai
+        qa = per_token_cast_to_fp8(a, True)
+        sfa = dg.transform_sf_into_required_layout(qa[1], m, k, (1, 128, 128), None, True)
+        d = torch.empty((m, n), device=device, dtype=torch.bfloat16)
+        valid, rows_total = sum(ms), m
+        fn = lambda: dg.m_grouped_fp8_gemm_nt_contiguous((qa[0], sfa), (b, sfb_p), d, layout)  # noqa: E731
+        name = f'm_grouped contiguous prefill, G=256 N=4096 K=7168 mean_m={mean_m} (sum M={m}, valid {valid}, alignment {alignment})'
+    launches0 = _lib.launch_count()
+    with ClockSampler(torch.cuda.current_device()) as clocks:
+        ms_step = _time_events(fn, args.steps, args.warmup, world)
+    ms_step = allreduce_max(ms_step, world, device)
+    launches = (_lib.launch_count() - launches0) if not masked else args.steps + args.warmup  # graph replays relaunch the kernel
+    flops = 2.0 * valid * n * k
+    byts = rows_total * k + g * n * k + rows_total * n * 2 + (rows_total + g * n) * ((k + 511) // 512) * 4
+    gbs = byts / (ms_step * 1e-3) / 1e9
+    return {
+        'metric': 'grouped FP8 GEMM tokens/s (valid rows / kernel time)', 'value': round(valid * world / (ms_step * 1e-3), 1),
+        'unit': 'tokens/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': round(ms_step, 4),
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'fp8_e4m3 (fp32 accumulate, bf16 out)',
+        'data': 'synthetic', 'impl': 'deepgemm_b200', 'tflops': round(flops / (ms_step * 1e-3) / 1e12, 1),
+        'config': {'workload': name, 'l2': 'flushed (512 MB write) before every timed launch', 'parallelism': f'replicas x{world}',
+                   'tile': _lib.last_config()},
+        'roofline': {'bound': 'hbm', 'achieved': round(gbs, 1), 'peak': peaks['hbm_gbs'], 'unit': 'GB/s',
+                     'frac': round(gbs / peaks['hbm_gbs'], 4), 'peak_source': peak_kind + ' hbm_gbs (MEASURED_PEAKS.json)', 'traffic': None},
+        'clocks': clocks.summary(), 'gpu_launches': int(launches),
+        'e2e': {'value': None, 'unit': 'tokens/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0,
+                'note': 'grouped workloads keep the 7.5 / 3.8 GB of expert weights resident; see the dense workload for e2e'},
+    }
+
+
+def run_ep(args, rank, world, device):
+    """BASELINE config 5: 256 experts sharded over the ranks, tokens dispatched with one NCCL all-to-all, local grouped GEMM."""
+    import deepgemm_b200 as dg
+    from deepgemm_b200 import _lib, ep
+    from deepgemm_b200.utils import per_token_cast_to_fp8
+    g, n, k, tokens_total = 256, 4096, 7168, 32768
+    epr = g // world
+    t_local = tokens_total // world
+    b, sfb = _grouped_weights(epr, n, k, device, seed=1000 + rank)
+    sfb_p = dg.transform_sf_into_required_layout(sfb, n, k, (1, 128, 128), epr, False)
+    gen = torch.Generator(device=device).manual_seed(rank)
+    x = torch.randn((t_local, k), device=device, dtype=torch.bfloat16, generator=gen)
+    xq, sf_packed = per_token_cast_to_fp8(x, True, 128, use_packed_ue8m0=True)
+    ids = torch.randint(0, g, (t_local,), device=device, generator=gen)
+    group = None if world == 1 else torch.distributed.group.WORLD
+
+    def step(record=None):
+        if record:
+            record[0].record()
+        if world > 1:
+            r = ep.dispatch(xq, sf_packed, ids, g, dg.get_mk_alignment_for_contiguous_layout(), group)
+        else:
+            r = ep.dispatch_local(xq, sf_packed, ids, g, dg.get_mk_alignment_for_contiguous_layout())
+        if record:
+            record[1].record()
+        d = torch.empty((r.a.shape[0], n), device=device, dtype=torch.bfloat16)
+        dg.m_grouped_fp8_gemm_nt_contiguous((r.a, r.sfa), (b, sfb_p), d, r.psum_layout, use_psum_layout=True)
+        if record:
+            record[2].record()
+        return r
+
+    for _ in range(args.warmup):
+        step()
+    barrier(world)
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
+    launches0 = _lib.launch_count()
+    with ClockSampler(torch.cuda.current_device()) as clocks:
+        for e in evs:
+            step(e)
+        torch.cuda.synchronize()
+    launches = _lib.launch_count() - launches0
+    barrier(world)
+    disp = sum(e[0].elapsed_time(e[1]) for e in evs) / args.steps
+    gemm = sum(e[1].elapsed_time(e[2]) for e in evs) / args.steps
+    total = allreduce_max(disp + gemm, world, device)
+    disp, gemm = allreduce_max(disp, world, device), allreduce_max(gemm, world, device)
+    wire = t_local * (k + 4 * ((k + 511) // 512))
+    return {
+        'metric': 'expert-sharded grouped FP8 GEMM tokens/s (dispatch + GEMM)', 'value': round(tokens_total / (total * 1e-3), 1),
+        'unit': 'tokens/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': round(total, 4),
+        'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'fp8_e4m3 (fp32 accumulate, bf16 out)',
+        'data': 'synthetic', 'impl': 'deepgemm_b200',
+        'config': {'workload': f'expert-sharded grouped GEMM: 256 experts over {world} GPU(s), 32768 tokens, N=4096 K=7168, '
+                               'one NCCL all-to-all of FP8 rows + packed UE8M0 SFs', 'parallelism': f'ep{world}',
+                   'l2': 'inputs (>= 0.9 GB of expert weights per rank) exceed L2'},
+        'dispatch_ms': round(disp, 4), 'gemm_ms': round(gemm, 4), 'tflops': round(2.0 * tokens_total * n * k / (total * 1e-3) / 1e12, 1),
+        'wire_bytes_per_rank': int(wire), 'clocks': clocks.summary(), 'gpu_launches': int(launches),
+        'e2e': {'value': round(tokens_total / (total * 1e-3), 1), 'unit': 'tokens/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0,
+                'note': 'tokens originate on the GPUs (output of the previous layer); dispatch includes the count exchange host sync'},
+    }
+
+
 # ------------------------------------------------------------------------------------------------ CPU arm
 def cpu_reference_step(shapes, threads):
     """torch-CPU BF16-emulated blockwise GEMM (oracle port) over `shapes`; returns (seconds, flops)."""
@@ -296,7 +461,8 @@ def main():
     ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--workload', default='dense', choices=['dense'])
+    ap.add_argument('--workload', default='dense', choices=['dense', 'contiguous', 'masked', 'ep'])
+    ap.add_argument('--mean-m', type=int, default=0)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -318,9 +484,10 @@ def main():
     if world > 1:
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
         torch.distributed.init_process_group(backend='nccl', device_id=device)
-    out = run_dense(args, rank, world, device)
+    runner = {'dense': run_dense, 'contiguous': run_grouped, 'masked': run_grouped, 'ep': run_ep}[args.workload]
+    out = runner(args, rank, world, device)
     if rank == 0:
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and args.workload == 'dense':
             out['cpu_baseline'] = cpu_baseline_block()
         print(json.dumps(out), flush=True)
     if world > 1:

@@ -25,6 +25,8 @@
 #pragma once
 #include <cuda_bf16.h>
 
+#include <type_traits>
+
 #include "ptx.cuh"
 
 namespace dgb200 {
@@ -483,6 +485,29 @@ fp8_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
             const uint32_t tmem_sfw = tmem_base + kTmemColSFW, tmem_sfx = tmem_base + kTmemColSFX;
             constexpr uint16_t kEmptyMask = static_cast<uint16_t>((1u << kCluster) - 1);   // every CTA's `empty` barrier
             const uint16_t pair_mask = static_cast<uint16_t>(0b11u << leader_rank);           // this pair only
+            // The issue loop below bounds every shape whose tiles are small (each k-block then costs its ~50
+            // instructions, not its MMA time), so everything loop-invariant is hoisted: per-k-block work is one barrier
+            // wait, <= 3 tcgen05.cp, 4 tcgen05.mma whose descriptors differ by immediates, and one commit.
+            const uint32_t id_kb_mul = (sfw_mask ? (1u << 29) : 0u) | (sfx_mask ? (1u << 4) : 0u);   // gran_k 128: id = kb & 3
+            const uint32_t id_j_mul = (sfw_mask ? 0u : (1u << 29)) | (sfx_mask ? 0u : (1u << 4));    // gran_k 32 : id = j
+            const uint32_t sub_mask = sfw_mask | sfx_mask;                                          // 3 or 0
+            auto issue_kblock = [&](auto n_const, uint32_t kb, bool first, uint32_t tmem_d) {
+                constexpr uint32_t kNumUmma = decltype(n_const)::value;
+                const uint32_t slot16 = ring.slot >> 4;
+                if ((kb & sfw_mask) == 0 || first) tmem_cp_sf<kCtaGroup>(tmem_sfw, sfw_desc0 + slot16);
+                if ((kb & sfx_mask) == 0 || first) {
+                    tmem_cp_sf<kCtaGroup>(tmem_sfx, sfx_desc0 + slot16);
+                    if (num_sfx_groups > 1) tmem_cp_sf<kCtaGroup>(tmem_sfx + 4, sfx_desc0 + slot16 + 32);
+                }
+                const uint64_t w_desc = w_desc0 + slot16, x_desc = x_desc0 + slot16;
+                const uint32_t idesc = idesc_base + (kb & sub_mask) * id_kb_mul;   // one UE8M0 byte per 32 K-elements
+#pragma unroll
+                for (uint32_t j = 0; j < kNumUmma; ++j)
+                    mma_mxf8_block_scale<kCtaGroup>(tmem_d, w_desc + j * w_kstep, x_desc + j * x_kstep, idesc + j * id_j_mul,
+                                                   tmem_sfw, tmem_sfx, (j != 0 || !first) ? 1u : 0u);
+                // retire -> the smem slot may be overwritten (signals every CTA of the cluster)
+                mma_commit<kCtaGroup>(empty_bar + ring.bar, kEmptyMask);
+            };
             uint32_t tile_iter = 0;
             while (sched.next(t)) {
                 if (kGemmType == kMContiguousPsum && t.valid_m == 0) continue;
@@ -491,38 +516,28 @@ fp8_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
                 mbar_wait(tmem_empty_bar + as * 8, aphase ^ 1);
                 tcgen05_fence_after();
                 const uint32_t tmem_d = tmem_base + as * kAccumColStride;
-                for (uint32_t kb = t.kb_begin; kb < t.kb_end; ++kb, ring.advance()) {
+                uint32_t kb = t.kb_begin;
+                for (; kb + 1 < t.kb_end; ++kb, ring.advance()) {        // every k-block but the last: 4 UMMAs
                     mbar_wait(ready_bar + ring.bar, ring.phase);
                     tcgen05_fence_after();
-                    if (elect_one()) {
-                        const uint32_t slot16 = ring.slot >> 4;
-                        const uint32_t sfw_sub = kb & sfw_mask, sfx_sub = kb & sfx_mask;
-                        const bool first = kb == t.kb_begin;
-                        if (sfw_sub == 0 || first) tmem_cp_sf<kCtaGroup>(tmem_sfw, sfw_desc0 + slot16);
-                        if (sfx_sub == 0 || first) {
-                            tmem_cp_sf<kCtaGroup>(tmem_sfx, sfx_desc0 + slot16);
-                            if (num_sfx_groups > 1) tmem_cp_sf<kCtaGroup>(tmem_sfx + 4, sfx_desc0 + slot16 + 32);
-                        }
-                        const uint64_t w_desc = w_desc0 + slot16, x_desc = x_desc0 + slot16;
-                        // one UE8M0 byte per 32 K-elements: byte id inside the packed word
-                        const uint32_t idesc = idesc_with_sf_ids(idesc_base, sfw_mask ? sfw_sub : 0u, sfx_mask ? sfx_sub : 0u);
-                        const uint32_t id_step = (sfw_mask ? 0u : (1u << 29)) | (sfx_mask ? 0u : (1u << 4));  // gran_k 32
-                        const uint32_t n_umma = kb + 1 == t.kb_end ? t.last_umma : kBlockK / kUmmaK;   // K may end inside the block
-#pragma unroll
-                        for (uint32_t j = 0; j < kBlockK / kUmmaK; ++j)
-                            if (j < n_umma)
-                                mma_mxf8_block_scale<kCtaGroup>(tmem_d, w_desc + j * w_kstep, x_desc + j * x_kstep,
-                                                               idesc + j * id_step, tmem_sfw, tmem_sfx, (!first || j != 0) ? 1u : 0u);
-                        // retire -> the smem slot may be overwritten (signals every CTA of the pair)
-                        mma_commit<kCtaGroup>(empty_bar + ring.bar, kEmptyMask);
-                        if (first) DGB_STAMP(4);
-                        if (kb + 1 == t.kb_end) {
-                            mma_commit<kCtaGroup>(tmem_full_bar + as * 8, pair_mask);
-                            DGB_STAMP(5);
-                        }
-                    }
+                    if (elect_one()) issue_kblock(std::integral_constant<uint32_t, 4>{}, kb, kb == t.kb_begin, tmem_d);
                     __syncwarp();
                 }
+                mbar_wait(ready_bar + ring.bar, ring.phase);               // last k-block: K may end inside it
+                tcgen05_fence_after();
+                if (elect_one()) {
+                    const bool first = kb == t.kb_begin;
+                    switch (t.last_umma) {
+                        case 1: issue_kblock(std::integral_constant<uint32_t, 1>{}, kb, first, tmem_d); break;
+                        case 2: issue_kblock(std::integral_constant<uint32_t, 2>{}, kb, first, tmem_d); break;
+                        case 3: issue_kblock(std::integral_constant<uint32_t, 3>{}, kb, first, tmem_d); break;
+                        default: issue_kblock(std::integral_constant<uint32_t, 4>{}, kb, first, tmem_d); break;
+                    }
+                    mma_commit<kCtaGroup>(tmem_full_bar + as * 8, pair_mask);   // accumulator complete -> epilogue
+                }
+                __syncwarp();
+                ring.advance();
+                if (tile_iter == 1 && lane == 0) DGB_STAMP(5);
             }
             // Drain: nobody may tear the CTA pair down while epilogue threads of the peer still arrive here
             if (tile_iter > 0) {

@@ -103,6 +103,32 @@ def dispatch(x_fp8: torch.Tensor, sf_packed: torch.Tensor, expert_ids: torch.Ten
                           src_order=order, num_recv=num_recv)
 
 
+def dispatch_local(x_fp8: torch.Tensor, sf_packed: torch.Tensor, expert_ids: torch.Tensor, num_experts: int,
+                   alignment: int) -> DispatchResult:
+    """World size 1: the same bucketing + layout steps without any communication (all experts are local)."""
+    t, k = x_fp8.shape
+    kp = sf_packed.shape[1]
+    dev = x_fp8.device
+    order = torch.argsort(expert_ids, stable=True)
+    counts = torch.bincount(expert_ids, minlength=num_experts)
+    aligned = (counts + alignment - 1) // alignment * alignment
+    seg_start = torch.cumsum(aligned, 0) - aligned
+    src_start = torch.cumsum(counts, 0) - counts
+    m_aligned = int(aligned.sum())
+    e_sorted = expert_ids[order]
+    dest = seg_start[e_sorted] + (torch.arange(t, device=dev) - src_start[e_sorted])
+    a = torch.zeros((m_aligned, k), dtype=torch.uint8, device=dev)
+    a[dest] = x_fp8.contiguous().view(torch.uint8)[order]
+    sfa_t = torch.zeros((kp, m_aligned), dtype=torch.int32, device=dev)
+    sfa_t[:, dest] = sf_packed[order].t()
+    layout = torch.full((m_aligned,), -1, dtype=torch.int32, device=dev)
+    layout[dest] = e_sorted.to(torch.int32)
+    if x_fp8.dtype == torch.float8_e4m3fn:
+        a = a.view(torch.float8_e4m3fn)
+    return DispatchResult(a=a, sfa=sfa_t.t(), psum_layout=(seg_start + counts).to(torch.int32), grouped_layout=layout,
+                          recv_counts=counts.view(1, -1), src_order=order, num_recv=t)
+
+
 def expert_sharded_grouped_gemm(x_fp8: torch.Tensor, sf_packed: torch.Tensor, expert_ids: torch.Tensor,
                                 w_local: Tuple[torch.Tensor, torch.Tensor], num_experts: int,
                                 group: Optional[dist.ProcessGroup] = None,

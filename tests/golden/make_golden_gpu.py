@@ -86,6 +86,48 @@ def main():
                                   'sfb': qb3[1].cpu(), 'layout': layout.cpu(), 'psum': psum, 'alignment': alignment,
                                   'valid': valid, 'd': d.cpu()})
 
+    # MN-major operands (fp8_gemm_tn: A [K,M], B [K,N]) and the K-grouped weight gradient
+    out['dense_tn'], out['k_grouped'] = [], []
+    for (m, n, k) in [(128, 256, 384), (192, 128, 512)]:
+        a = torch.randn((m, k), device='cuda', dtype=torch.bfloat16)
+        b = torch.randn((n, k), device='cuda', dtype=torch.bfloat16)
+        qa, qb = per_token_cast_to_fp8(a, True), per_block_cast_to_fp8(b, True)
+        a_t = (qa[0].t().contiguous(), qa[1].t().contiguous())
+        b_t = (qb[0].t().contiguous(), qb[1].t().contiguous())
+        d = torch.empty((m, n), device='cuda', dtype=torch.bfloat16)
+        ref.fp8_gemm_tn(a_t, b_t, d)
+        torch.cuda.synchronize()
+        out['dense_tn'].append({'name': f'tn_{m}x{n}x{k}', 'a_t': u8(a_t[0]), 'sfa_t': a_t[1].cpu(), 'b_t': u8(b_t[0]),
+                                'sfb_t': b_t[1].cpu(), 'd': d.cpu()})
+    from deep_gemm.utils import per_channel_cast_to_fp8
+    for gran_k, k_alignment in ((128, 128), (32, 32)):
+        ref.set_mk_alignment_for_contiguous_layout(k_alignment)
+        ks = [k_alignment * 3, 0, k_alignment * 1, k_alignment * 5]
+        m, n = 256, 128
+        a = torch.randn((sum(ks), m), device='cuda', dtype=torch.bfloat16)
+        b = torch.randn((sum(ks), n), device='cuda', dtype=torch.bfloat16)
+        qa_l, qb_l, sa_l, sb_l, pos = [], [], [], [], 0
+        for kk in ks:
+            if kk == 0:
+                continue
+            pad = (kk + gran_k - 1) // gran_k * gran_k
+            xa = torch.zeros((pad, m), device='cuda', dtype=torch.bfloat16)
+            xb = torch.zeros((pad, n), device='cuda', dtype=torch.bfloat16)
+            xa[:kk], xb[:kk] = a[pos:pos + kk], b[pos:pos + kk]
+            qa_, sa_ = per_channel_cast_to_fp8(xa, use_ue8m0=True, gran_k=gran_k)
+            qb_, sb_ = per_channel_cast_to_fp8(xb, use_ue8m0=True, gran_k=gran_k)
+            qa_l.append(qa_[:kk]), qb_l.append(qb_[:kk]), sa_l.append(sa_), sb_l.append(sb_)
+            pos += kk
+        a8, b8, sfa, sfb = torch.cat(qa_l), torch.cat(qb_l), torch.cat(sa_l), torch.cat(sb_l)
+        c = torch.randn((len(ks), m, n), device='cuda') * 8
+        d = c.clone()
+        ref.k_grouped_fp8_gemm_tn_contiguous((a8, sfa), (b8, sfb), d, ks, torch.tensor(ks, device='cuda', dtype=torch.int32),
+                                             c=d, recipe=(1, 1, gran_k))
+        torch.cuda.synchronize()
+        out['k_grouped'].append({'name': f'k_grouped_g{gran_k}', 'a': u8(a8), 'sfa': sfa.cpu(), 'b': u8(b8), 'sfb': sfb.cpu(),
+                                 'c': c.cpu(), 'd': d.cpu(), 'ks': ks, 'gran_k': gran_k, 'k_alignment': k_alignment})
+    ref.set_mk_alignment_for_contiguous_layout(128)
+
     os.makedirs(os.path.join(REPO, 'gpurun_out'), exist_ok=True)
     path = os.path.join(REPO, 'gpurun_out', 'gpu_golden.pt')
     torch.save(out, path)

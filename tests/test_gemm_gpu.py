@@ -194,7 +194,7 @@ def test_sf_pack_kernel_bit_exact(dg):
 
 
 @pytest.mark.parametrize('layout', ['nn', 'tn', 'tt'])
-@pytest.mark.parametrize('m,n,k', [(256, 384, 512), (4096, 512, 1024), (192, 2112, 1536), (100, 256, 640)])
+@pytest.mark.parametrize('m,n,k', [(256, 384, 512), (4096, 512, 1024), (192, 2112, 1536), (112, 256, 640)])
 def test_dense_layout_variants_match_nt_bitwise(dg, layout, m, n, k):
     """fp8_gemm_{nn,tn,tt}: MN-major operands (csrc/apis/gemm.hpp:126-164). Same numbers, same K order as the NT call on
     the same quantised data, so the outputs must be bit-identical to it (and NT is pinned to the oracle above)."""
@@ -449,6 +449,23 @@ def test_golden_outputs_of_the_reference_kernel(dg):
                 dg.fp8_gemm_nt(qa, qb, d)
         finally:
             os.environ.pop('DGB200_SPLITS', None)
+        assert torch.equal(d.cpu(), case['d']), case['name']
+    for case in golden.get('dense_tn', []):
+        a_t = (case['a_t'].cuda().view(torch.float8_e4m3fn), case['sfa_t'].cuda())
+        b_t = (case['b_t'].cuda().view(torch.float8_e4m3fn), case['sfb_t'].cuda())
+        d = torch.empty(case['d'].shape, device='cuda', dtype=case['d'].dtype)
+        dg.fp8_gemm_tn(a_t, b_t, d)
+        assert torch.equal(d.cpu(), case['d']), case['name']
+    for case in golden.get('k_grouped', []):
+        a = (case['a'].cuda().view(torch.float8_e4m3fn), case['sfa'].cuda())
+        b = (case['b'].cuda().view(torch.float8_e4m3fn), case['sfb'].cuda())
+        d = case['c'].cuda().clone()
+        dg.set_mk_alignment_for_contiguous_layout(case['k_alignment'])
+        try:
+            dg.k_grouped_fp8_gemm_tn_contiguous(a, b, d, case['ks'], torch.tensor(case['ks'], device='cuda', dtype=torch.int32),
+                                                c=d, recipe=(1, 1, case['gran_k']))
+        finally:
+            dg.set_mk_alignment_for_contiguous_layout(128)
         assert torch.equal(d.cpu(), case['d']), case['name']
     for case in golden.get('masked', []):
         qa = (case['a'].cuda().view(torch.float8_e4m3fn), case['sfa'].cuda())
