@@ -1,0 +1,54 @@
+"""Summarise .ncu-rep files (key metrics per kernel launch) as markdown. usage: ncu_summary.py out.md rep1 [rep2 ...]"""
+import csv
+import io
+import subprocess
+import sys
+
+WANT = [
+    ('gpu__time_duration.sum', 'duration'),
+    ('sm__cycles_elapsed.avg.per_second', 'SM clock'),
+    ('sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed', 'tensor pipe active'),
+    ('dram__bytes_read.sum', 'DRAM read'),
+    ('dram__bytes_write.sum', 'DRAM write'),
+    ('dram__bytes_read.sum.per_second', 'DRAM read rate'),
+    ('gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed', 'DRAM throughput % of peak'),
+    ('l1tex__m_xbar2l1tex_read_bytes.sum', 'L2->SM bytes'),
+    ('l1tex__m_xbar2l1tex_read_bytes.sum.per_second', 'L2->SM rate'),
+    ('lts__t_sector_hit_rate.pct', 'L2 hit rate'),
+    ('lts__throughput.avg.pct_of_peak_sustained_elapsed', 'L2 throughput % of peak'),
+    ('launch__registers_per_thread', 'registers/thread'),
+    ('launch__grid_size', 'grid'),
+    ('launch__block_size', 'block'),
+    ('launch__shared_mem_per_block_dynamic', 'dynamic smem'),
+    ('launch__cluster_size', 'cluster size'),
+    ('sm__warps_active.avg.pct_of_peak_sustained_active', 'achieved occupancy'),
+]
+
+
+def main():
+    out_path, reps = sys.argv[1], sys.argv[2:]
+    lines = ['# ncu summaries (`ncu --set full --clock-control none --import-source on`, B200)\n']
+    for rep in reps:
+        raw = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
+        rows = list(csv.reader(io.StringIO(raw)))
+        if len(rows) < 3:
+            lines.append(f'## {rep}\n(no data)\n')
+            continue
+        hdr, units = rows[0], rows[1]
+        for vals in rows[2:]:
+            d = {h: (v, u) for h, u, v in zip(hdr, units, vals)}
+            name = d.get('Kernel Name', ('?', ''))[0]
+            lines.append(f'## {rep.split("/")[-1]} — `{name[:110]}`\n')
+            lines.append('| metric | value |\n|---|---|')
+            for key, label in WANT:
+                if key in d:
+                    v, u = d[key]
+                    lines.append(f'| {label} (`{key}`) | {v} {u} |')
+            rd, wr = d.get('dram__bytes_read.sum'), d.get('dram__bytes_write.sum')
+            lines.append('')
+    open(out_path, 'w').write('\n'.join(lines) + '\n')
+    print('wrote', out_path)
+
+
+if __name__ == '__main__':
+    main()
