@@ -69,6 +69,14 @@ SIGNATURES = {
     'dgb200_last_config': (_I, [ctypes.POINTER(_Config)]),
     'dgb200_debug_set_timestamps': (_I, [_P]),
     'dgb200_launch_count': (_L, []),
+    'dgb200_ep_buffer_bytes': (_L, [_I, _I, _I, _I]),
+    'dgb200_ep_buffer_offsets': (_I, [_I, _I, _I, _I, ctypes.POINTER(_L)]),
+    'dgb200_ep_alloc': (_I, [_L, ctypes.POINTER(_P)]),
+    'dgb200_ep_free': (_I, [_P]),
+    'dgb200_ep_export': (_I, [_P, _P]),
+    'dgb200_ep_import': (_I, [_P, ctypes.POINTER(_P)]),
+    'dgb200_ep_unimport': (_I, [_P]),
+    'dgb200_ep_dispatch': (_I, [_P, _L, _P, _L, _L, _P, _I, _I, _I, _I, _I, _I, ctypes.POINTER(_P), _I, _I, _P, _P]),
 }
 
 _lib = None

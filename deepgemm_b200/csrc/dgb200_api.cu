@@ -12,6 +12,7 @@
 #include <algorithm>
 #include <atomic>
 #include <cstdarg>
+#include <cstddef>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -23,6 +24,7 @@
 #include "../../include/dgb200.h"
 #include "fp8_gemm_kernel.cuh"
 #include "sf_layout.cuh"
+#include "ep_dispatch.cuh"
 
 namespace dgb200 {
 namespace {
@@ -749,6 +751,97 @@ int dgb200_debug_set_timestamps(void* device_int64_buffer) {
 int64_t dgb200_workspace_bytes(int m, int n) {
     if (m <= 0 || n <= 0) return 0;
     return static_cast<int64_t>(kSplitKHeaderBytes) + static_cast<int64_t>(kMaxSplits) * m * n * sizeof(float);
+}
+
+// ------------------------------------------------------------------------------------------------ expert-parallel dispatch
+int64_t dgb200_ep_buffer_bytes(int world, int num_experts, int capacity, int k) {
+    if (world <= 0 || num_experts <= 0 || capacity <= 0 || k <= 0) return 0;
+    return static_cast<int64_t>(ep::make_layout(world, num_experts, capacity, k).total);
+}
+
+int dgb200_ep_buffer_offsets(int world, int num_experts, int capacity, int k, int64_t* offsets) {
+    DGB_REQUIRE(world > 0 && num_experts > 0 && capacity > 0 && k > 0 && offsets != nullptr);
+    const ep::Layout l = ep::make_layout(world, num_experts, capacity, k);
+    offsets[DGB200_EP_OFF_A] = l.a_off;
+    offsets[DGB200_EP_OFF_SFA] = l.sfa_off;
+    offsets[DGB200_EP_OFF_PSUM] = l.psum_off;
+    offsets[DGB200_EP_OFF_COUNTS] = l.counts_off;
+    offsets[DGB200_EP_OFF_NUM_ROWS] = offsetof(ep::Control, num_rows);
+    offsets[DGB200_EP_OFF_OVERFLOW] = offsetof(ep::Control, overflow);
+    return DGB200_OK;
+}
+
+int dgb200_ep_alloc(int64_t bytes, void** ptr) {
+    DGB_REQUIRE(bytes > 0 && ptr != nullptr);
+    DGB_CUDA(cudaMalloc(ptr, bytes));
+    DGB_CUDA(cudaMemset(*ptr, 0, bytes));
+    DGB_CUDA(cudaDeviceSynchronize());
+    return DGB200_OK;
+}
+int dgb200_ep_free(void* ptr) {
+    DGB_CUDA(cudaFree(ptr));
+    return DGB200_OK;
+}
+int dgb200_ep_export(void* ptr, void* handle_64_bytes) {
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    DGB_REQUIRE(ptr != nullptr && handle_64_bytes != nullptr);
+    cudaIpcMemHandle_t h;
+    DGB_CUDA(cudaIpcGetMemHandle(&h, ptr));
+    memcpy(handle_64_bytes, &h, 64);
+    return DGB200_OK;
+}
+int dgb200_ep_import(const void* handle_64_bytes, void** ptr) {
+    DGB_REQUIRE(ptr != nullptr && handle_64_bytes != nullptr);
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle_64_bytes, 64);
+    DGB_CUDA(cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return DGB200_OK;
+}
+int dgb200_ep_unimport(void* ptr) {
+    DGB_CUDA(cudaIpcCloseMemHandle(ptr));
+    return DGB200_OK;
+}
+
+int dgb200_ep_dispatch(const void* x, int64_t ldx, const int32_t* sf, int64_t sf_stride_t, int64_t sf_stride_k,
+                       const void* expert_ids, int id_bytes, int num_tokens, int k, int num_experts, int rank, int world,
+                       void* const* buffers, int capacity, int alignment, int32_t* token_row, void* stream) {
+    if (int e = ensure_device()) return e;
+    DGB_REQUIRE(world > 0 && world <= static_cast<int>(ep::kMaxWorld) && rank >= 0 && rank < world);
+    DGB_REQUIRE(num_experts > 0 && num_experts <= static_cast<int>(ep::kMaxExperts) && num_experts % world == 0);
+    DGB_REQUIRE(num_tokens >= 0 && capacity > 0 && alignment > 0);
+    DGB_REQUIRE(k > 0 && k % 16 == 0 && ceil_div(k, 512) <= 32);
+    DGB_REQUIRE(id_bytes == 4 || id_bytes == 8);
+    DGB_REQUIRE(buffers != nullptr && token_row != nullptr);
+    DGB_REQUIRE(num_tokens == 0 || (x != nullptr && sf != nullptr && expert_ids != nullptr));
+    DGB_REQUIRE(ldx % 16 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0);
+    ep::Peers peers;
+    for (int p = 0; p < world; ++p) {
+        DGB_REQUIRE(buffers[p] != nullptr);
+        peers.base[p] = static_cast<uint8_t*>(buffers[p]);
+    }
+    const ep::Layout l = ep::make_layout(world, num_experts, capacity, k);
+    const auto s = static_cast<cudaStream_t>(stream);
+    uint8_t* mine = peers.base[rank];
+    int32_t* counts = reinterpret_cast<int32_t*>(mine + l.counts_off);
+    const uint32_t kp = ceil_div(k, 512);
+    if (id_bytes == 4)
+        ep::bucket_kernel<int32_t><<<num_experts, 1024, 0, s>>>(expert_ids, num_tokens, token_row, counts);
+    else
+        ep::bucket_kernel<int64_t><<<num_experts, 1024, 0, s>>>(expert_ids, num_tokens, token_row, counts);
+    ep::exchange_kernel<<<1, 1024, 0, s>>>(peers, l, rank, world, num_experts, capacity, alignment);
+    const int grid = std::max(1, std::min(ceil_div(num_tokens, 8), rt().sm_count * 8));
+    if (id_bytes == 4)
+        ep::scatter_kernel<int32_t><<<grid, 256, 0, s>>>(peers, l, static_cast<const uint8_t*>(x), ldx, sf, sf_stride_t,
+                                                          sf_stride_k, expert_ids, token_row, num_tokens, k, kp, rank,
+                                                          world, num_experts, capacity);
+    else
+        ep::scatter_kernel<int64_t><<<grid, 256, 0, s>>>(peers, l, static_cast<const uint8_t*>(x), ldx, sf, sf_stride_t,
+                                                          sf_stride_k, expert_ids, token_row, num_tokens, k, kp, rank,
+                                                          world, num_experts, capacity);
+    ep::wait_kernel<<<1, 32, 0, s>>>(mine, world);
+    DGB_CUDA(cudaGetLastError());
+    g_launch_count.fetch_add(4, std::memory_order_relaxed);
+    return DGB200_OK;
 }
 
 int dgb200_last_config(dgb200_config* out) {

@@ -1,0 +1,265 @@
+// Expert-parallel dispatch over NVLink peer memory (plain CUDA, HBM / NVLink bound byte movement).
+//
+// Where the m-grouped contiguous GEMM sits inside expert parallelism (the reference's own baseline pairs it with a
+// DeepEP dispatch, tests/test_mega_moe.py:148-205), the tokens must first travel to the rank that owns their expert and
+// land in the contiguous-grouped layout (expert segments aligned to the M alignment, "psum" end rows per expert,
+// MN-major packed UE8M0 scale factors). Instead of all-to-all + re-layout passes, every rank writes its rows STRAIGHT
+// into the destination rank's GEMM input buffer with peer stores (NVSwitch: every peer at full bandwidth):
+//
+//   bucket   (G CTAs)  : stable rank of every local token inside its expert + per-expert counts       (local)
+//   exchange (1 CTA)   : publish my counts to every peer's table, wait for theirs, derive for every expert the first
+//                        destination row of MY tokens (segment start on the owner + rows of lower source ranks)
+//   scatter  (many CTAs): one warp per token: 16-byte loads from local HBM, 16-byte stores into the owner's A buffer,
+//                        scale-factor words into the owner's MN-major SF buffer; last CTA signals every peer
+//   wait     (1 warp)  : all sources have signalled -> the GEMM that follows in stream order may read the buffer
+//
+// No host synchronisation anywhere (counts never leave the devices), so the whole step is CUDA-graph capturable.
+// Flags are monotonic epochs kept in device memory; buffer reuse across steps is ordered by the exchange of the next
+// step (a rank publishes its counts only after its previous GEMM finished in stream order, and nobody scatters before
+// it has seen every rank's counts).
+#pragma once
+#include <cstdint>
+
+namespace dgb200 {
+namespace ep {
+
+constexpr uint32_t kMaxWorld = 16;
+constexpr uint32_t kMaxExperts = 2048;
+constexpr uint64_t kWaitTimeoutNs = 30ull * 1000 * 1000 * 1000;
+
+// Control block at the start of every rank's buffer (all offsets identical on all ranks).
+struct Control {
+    uint32_t epoch;               // last completed dispatch (local)
+    uint32_t done_ctas;           // scatter CTAs finished (local)
+    uint32_t num_rows;            // rows of the local A buffer in use after the last dispatch (aligned end of the last expert)
+    uint32_t overflow;            // set when a dispatch would not fit `capacity`
+    uint32_t pad[28];
+    uint32_t counts_flag[kMaxWorld * 8];   // [s*8]: epoch of the counts source rank s published here (32 B apart)
+    uint32_t data_flag[kMaxWorld * 8];     // [s*8]: epoch of the rows source rank s finished writing here
+};
+
+struct Peers {
+    uint8_t* base[kMaxWorld];
+};
+
+struct Layout {
+    uint64_t table_off;     // int32 [world][num_experts]  counts published by every source rank
+    uint64_t dst_base_off;  // int32 [num_experts]         first destination row of MY tokens for each expert (local)
+    uint64_t psum_off;      // int32 [experts_per_rank]    end row of each local expert segment (the GEMM's psum layout)
+    uint64_t counts_off;    // int32 [num_experts]         my own per-expert token counts (local)
+    uint64_t sfa_off;       // int32 [kp][capacity]        MN-major packed UE8M0 scale factors
+    uint64_t a_off;         // uint8 [capacity][k]         FP8 rows
+    uint64_t total;
+};
+
+__host__ __device__ inline uint64_t align_up64(uint64_t x, uint64_t a) { return (x + a - 1) / a * a; }
+
+inline Layout make_layout(uint32_t world, uint32_t num_experts, uint32_t capacity, uint32_t k) {
+    Layout l;
+    uint64_t off = align_up64(sizeof(Control), 1024);
+    l.table_off = off, off += align_up64(4ull * world * num_experts, 1024);
+    l.dst_base_off = off, off += align_up64(4ull * num_experts, 1024);
+    l.psum_off = off, off += align_up64(4ull * num_experts, 1024);
+    l.counts_off = off, off += align_up64(4ull * num_experts, 1024);
+    l.sfa_off = off, off += align_up64(4ull * ((k + 511) / 512) * capacity, 1024);
+    l.a_off = off, off += align_up64(1ull * capacity * k, 1024);
+    l.total = off;
+    return l;
+}
+
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint64_t ep_globaltimer() {
+    uint64_t t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+// spin until *flag reaches `epoch` (flags only grow); trap instead of hanging the GPU if a peer never shows up
+__device__ __forceinline__ void wait_flag(const uint32_t* flag, uint32_t epoch) {
+    uint64_t t0 = 0;
+    uint32_t spins = 0;
+    while (static_cast<int32_t>(ld_acquire_sys(flag) - epoch) < 0) {
+        if ((++spins & 0x3FF) == 0) {
+            const uint64_t now = ep_globaltimer();
+            if (t0 == 0) t0 = now;
+            if (now - t0 > kWaitTimeoutNs) {
+                printf("dgb200 ep: timed out waiting for a peer flag (epoch %u)\n", epoch);
+                asm volatile("trap;");
+            }
+        }
+    }
+}
+
+template <typename id_t>
+__device__ __forceinline__ int64_t load_id(const void* ids, uint32_t t) {
+    return static_cast<int64_t>(__ldg(reinterpret_cast<const id_t*>(ids) + t));
+}
+
+// grid = num_experts, block = 1024. slot[t] = number of earlier local tokens with the same expert (stable order).
+template <typename id_t>
+__global__ void __launch_bounds__(1024)
+bucket_kernel(const void* __restrict__ ids, uint32_t num_tokens, int32_t* __restrict__ slot, int32_t* __restrict__ counts) {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    __shared__ uint32_t warp_off[33];
+    const uint32_t e = blockIdx.x, tid = threadIdx.x, warp = tid / 32, lane = tid % 32;
+    uint32_t base = 0;
+    for (uint32_t t0 = 0; t0 < num_tokens; t0 += 1024) {
+        const uint32_t t = t0 + tid;
+        const bool match = t < num_tokens && load_id<id_t>(ids, t) == static_cast<int64_t>(e);
+        const uint32_t ballot = __ballot_sync(0xffffffffu, match);
+        if (lane == 0) warp_off[warp] = __popc(ballot);
+        __syncthreads();
+        if (warp == 0) {
+            const uint32_t c = warp_off[lane];
+            uint32_t incl = c;
+#pragma unroll
+            for (uint32_t d = 1; d < 32; d *= 2) {
+                const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= d) incl += v;
+            }
+            warp_off[lane] = incl - c;
+            if (lane == 31) warp_off[32] = incl;
+        }
+        __syncthreads();
+        if (match) slot[t] = static_cast<int32_t>(base + warp_off[warp] + __popc(ballot & ((1u << lane) - 1)));
+        base += warp_off[32];
+        __syncthreads();
+    }
+    if (tid == 0) counts[e] = static_cast<int32_t>(base);
+}
+
+// grid = 1, block = 1024.
+__global__ void __launch_bounds__(1024)
+exchange_kernel(Peers peers, Layout l, uint32_t rank, uint32_t world, uint32_t num_experts, uint32_t capacity,
+                uint32_t alignment) {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    __shared__ uint32_t s_total[kMaxExperts], s_before[kMaxExperts];
+    const uint32_t tid = threadIdx.x;
+    uint8_t* mine = peers.base[rank];
+    Control* ctrl = reinterpret_cast<Control*>(mine);
+    const uint32_t epoch = ctrl->epoch + 1;
+    const int32_t* counts = reinterpret_cast<const int32_t*>(mine + l.counts_off);
+
+    // publish my counts into row `rank` of every peer's table
+    for (uint32_t i = tid; i < world * num_experts; i += blockDim.x) {
+        const uint32_t p = i / num_experts, e = i - p * num_experts;
+        reinterpret_cast<int32_t*>(peers.base[p] + l.table_off)[rank * num_experts + e] = counts[e];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (tid < world) {
+        st_release_sys(&reinterpret_cast<Control*>(peers.base[tid])->counts_flag[rank * 8], epoch);
+        wait_flag(&ctrl->counts_flag[tid * 8], epoch);
+    }
+    __syncthreads();
+
+    const int32_t* table = reinterpret_cast<const int32_t*>(mine + l.table_off);
+    for (uint32_t e = tid; e < num_experts; e += blockDim.x) {
+        uint32_t total = 0, before = 0;
+        for (uint32_t s = 0; s < world; ++s) {
+            const uint32_t c = static_cast<uint32_t>(__ldcv(table + s * num_experts + e));
+            total += c;
+            if (s < rank) before += c;
+        }
+        s_total[e] = total, s_before[e] = before;
+    }
+    __syncthreads();
+    const uint32_t epr = num_experts / world;
+    int32_t* dst_base = reinterpret_cast<int32_t*>(mine + l.dst_base_off);
+    int32_t* psum = reinterpret_cast<int32_t*>(mine + l.psum_off);
+    for (uint32_t e = tid; e < num_experts; e += blockDim.x) {
+        const uint32_t owner = e / epr;
+        uint32_t seg = 0;
+        for (uint32_t j = owner * epr; j < e; ++j) seg += (s_total[j] + alignment - 1) / alignment * alignment;
+        dst_base[e] = static_cast<int32_t>(seg + s_before[e]);
+        if (owner == rank) {
+            psum[e - rank * epr] = static_cast<int32_t>(min(seg + s_total[e], capacity));   // stays in bounds on overflow
+            if (e == (rank + 1) * epr - 1) {
+                const uint32_t rows = seg + (s_total[e] + alignment - 1) / alignment * alignment;
+                ctrl->num_rows = rows;
+                if (rows > capacity) ctrl->overflow = 1;
+            }
+        }
+    }
+    __syncthreads();
+    if (tid == 0) ctrl->epoch = epoch;
+}
+
+// One warp per token. `x` rows of `k` bytes (pitch ldx), `sf` [T][kp] int32 words with strides (sf_stride_t, sf_stride_k).
+template <typename id_t>
+__global__ void __launch_bounds__(256)
+scatter_kernel(Peers peers, Layout l, const uint8_t* __restrict__ x, int64_t ldx, const int32_t* __restrict__ sf,
+               int64_t sf_stride_t, int64_t sf_stride_k, const void* __restrict__ ids, int32_t* __restrict__ token_row,
+               uint32_t num_tokens, uint32_t k, uint32_t kp, uint32_t rank, uint32_t world, uint32_t num_experts,
+               uint32_t capacity) {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    uint8_t* mine = peers.base[rank];
+    Control* ctrl = reinterpret_cast<Control*>(mine);
+    const uint32_t epoch = ctrl->epoch;                       // the exchange of this dispatch already bumped it
+    const int32_t* dst_base = reinterpret_cast<const int32_t*>(mine + l.dst_base_off);
+    const uint32_t epr = num_experts / world;
+    const uint32_t lane = threadIdx.x % 32;
+    const uint32_t warps_per_cta = blockDim.x / 32;
+    const uint32_t chunks = k / 16;
+
+    for (uint32_t t = blockIdx.x * warps_per_cta + threadIdx.x / 32; t < num_tokens; t += gridDim.x * warps_per_cta) {
+        const int64_t e = load_id<id_t>(ids, t);
+        if (e < 0 || e >= static_cast<int64_t>(num_experts)) {          // token routed nowhere (DeepEP uses -1)
+            if (lane == 0) token_row[t] = -1;
+            continue;
+        }
+        const uint32_t owner = static_cast<uint32_t>(e) / epr;
+        const uint32_t row = static_cast<uint32_t>(__ldg(dst_base + e)) + static_cast<uint32_t>(token_row[t]);
+        if (row >= capacity) {                                            // the exchange flagged `overflow`; drop
+            if (lane == 0) token_row[t] = -1;
+            continue;
+        }
+        const uint4* src = reinterpret_cast<const uint4*>(x + static_cast<int64_t>(t) * ldx);
+        uint4* dst = reinterpret_cast<uint4*>(peers.base[owner] + l.a_off + static_cast<uint64_t>(row) * k);
+        uint32_t c = lane;
+        for (; c + 96 < chunks; c += 128) {                               // 4 x 16 B in flight per lane
+            const uint4 v0 = __ldg(src + c), v1 = __ldg(src + c + 32), v2 = __ldg(src + c + 64), v3 = __ldg(src + c + 96);
+            dst[c] = v0, dst[c + 32] = v1, dst[c + 64] = v2, dst[c + 96] = v3;
+        }
+        for (; c < chunks; c += 32) dst[c] = __ldg(src + c);
+        if (lane < kp) {
+            int32_t* sfa = reinterpret_cast<int32_t*>(peers.base[owner] + l.sfa_off);
+            sfa[static_cast<uint64_t>(lane) * capacity + row] = __ldg(sf + t * sf_stride_t + lane * sf_stride_k);
+        }
+        __syncwarp();
+        if (lane == 0) token_row[t] = static_cast<int32_t>(row);
+    }
+
+    // completion: the last CTA to finish tells every peer that all of this rank's rows have landed
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const uint32_t prev = atomicAdd(&ctrl->done_ctas, 1u);
+        if (prev == gridDim.x - 1) {
+            ctrl->done_ctas = 0;
+            __threadfence_system();
+            for (uint32_t p = 0; p < world; ++p)
+                st_release_sys(&reinterpret_cast<Control*>(peers.base[p])->data_flag[rank * 8], epoch);
+        }
+    }
+}
+
+// grid = 1, block = 32: returns once every source rank's rows of the current epoch are visible here.
+__global__ void __launch_bounds__(32)
+wait_kernel(uint8_t* mine, uint32_t world) {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    Control* ctrl = reinterpret_cast<Control*>(mine);
+    const uint32_t epoch = ctrl->epoch;
+    if (threadIdx.x < world) wait_flag(&ctrl->data_flag[threadIdx.x * 8], epoch);
+    __syncwarp();
+    __threadfence_system();
+}
+
+}  // namespace ep
+}  // namespace dgb200

@@ -1,23 +1,23 @@
 """Expert-sharded M-grouped FP8 GEMM (BASELINE config 5).
 
 The grouped-contiguous path shards naturally by experts: rank r of P owns experts [r*G/P, (r+1)*G/P). Tokens start
-evenly distributed over the ranks, each with one destination expert. One step =
+distributed over the ranks, each with one destination expert, and must land on the owner in the layout the GEMM
+consumes (expert segments aligned to `get_mk_alignment_for_contiguous_layout()`, psum layout = end row per expert,
+MN-major packed UE8M0 scale factors). This mirrors how the reference's grouped GEMM sits inside expert parallelism in
+its own baseline (tests/test_mega_moe.py:148-205: DeepEP dispatch -> m_grouped_fp8_fp4_gemm_nt_contiguous(
+use_psum_layout=True) -> combine). The reverse path ("combine") is the next row.
 
-  1. bucket the local tokens by destination expert (stable sort)                        -- device, no host sync
-  2. exchange per-(rank, expert) counts:   all_to_all_single of a [P, G/P] int32 table  -- 4*G bytes per rank
-  3. ONE payload all-to-all: every token travels as one row of K + 4*ceil(K/512) bytes = FP8 values followed by its
-     packed UE8M0 scale factors (7168 + 56 B for DeepSeek-V3) over NCCL (NVLink 5 / NVSwitch: every peer at full
-     bandwidth, so a flat variable-count all-to-all is the idiomatic dispatch; no topology-aware ring)
-  4. lay the received rows out in the contiguous-grouped format the GEMM consumes (expert segments aligned to
-     `get_mk_alignment_for_contiguous_layout()`, psum layout = end row per expert) and transpose the scale factors to
-     the MN-major wire format
-  5. local `m_grouped_fp8_gemm_nt_contiguous` on this rank's experts.
+Two implementations:
 
-This mirrors how the reference's grouped GEMM sits inside expert parallelism in its own baseline
-(tests/test_mega_moe.py:148-205: DeepEP dispatch -> m_grouped_fp8_fp4_gemm_nt_contiguous(use_psum_layout=True) ->
-combine). The reverse all-to-all + weighted reduce ("combine") is the next row.
+* `EpBuffer.dispatch` -- THE PRODUCT PATH (CUDA only). Hand-written kernels (csrc/ep_dispatch.cuh) write every token
+  row (K FP8 bytes + its 4*ceil(K/512) scale-factor bytes) straight into the owner's GEMM input buffer with NVLink peer
+  stores: bucket -> count exchange through peer memory -> scatter -> wait. No host synchronisation (the counts never
+  leave the devices), no intermediate buffers, no re-layout pass, CUDA-graph capturable. The plumbing (buffer
+  allocation, CUDA IPC handle exchange over `torch.distributed`) happens once, in the constructor.
 
-Steps 1-4 are torch plumbing and run on any backend (the world_size-2 `gloo` CPU test covers them); step 5 needs CUDA.
+* `dispatch_alltoall` -- the library baseline: counts `all_to_all_single` + ONE payload `all_to_all_single` + torch
+  index ops for the re-layout. Runs on any backend (the world_size-2 `gloo` CPU test covers the host logic) and is
+  what `EpBuffer.dispatch` is checked against on GPUs; it is NOT a fallback -- `EpBuffer` fails without CUDA.
 """
 from dataclasses import dataclass
 from typing import Optional, Tuple
@@ -48,7 +48,7 @@ def pack_rows(x_fp8: torch.Tensor, sf_packed: torch.Tensor) -> torch.Tensor:
     return torch.cat([x_fp8.contiguous().view(torch.uint8), sf_packed.contiguous().view(torch.uint8).view(t, -1)], dim=1)
 
 
-def dispatch(x_fp8: torch.Tensor, sf_packed: torch.Tensor, expert_ids: torch.Tensor, num_experts: int, alignment: int,
+def dispatch_alltoall(x_fp8: torch.Tensor, sf_packed: torch.Tensor, expert_ids: torch.Tensor, num_experts: int, alignment: int,
              group: Optional[dist.ProcessGroup] = None) -> DispatchResult:
     """Steps 1-4. `x_fp8` [T,K] e4m3 (or uint8), `sf_packed` [T, ceil(K/512)] int32 (K-major, as
     per_token_cast_to_fp8(..., use_packed_ue8m0=True) returns), `expert_ids` [T] int64 in [0, num_experts)."""
@@ -129,18 +129,129 @@ def dispatch_local(x_fp8: torch.Tensor, sf_packed: torch.Tensor, expert_ids: tor
                           recv_counts=counts.view(1, -1), src_order=order, num_recv=t)
 
 
+class _RawCuda:
+    """Adapter so torch can view library-owned device memory (`torch.as_tensor` reads __cuda_array_interface__)."""
+
+    def __init__(self, ptr: int, nbytes: int):
+        self.__cuda_array_interface__ = {'shape': (nbytes,), 'typestr': '|u1', 'data': (ptr, False), 'version': 2}
+
+
+@dataclass
+class PeerDispatch:
+    a: torch.Tensor             # [capacity, K] e4m3 view of the local dispatch buffer
+    sfa: torch.Tensor           # int32 [capacity, ceil(K/512)], strides (1, capacity)
+    psum_layout: torch.Tensor   # int32 [experts_per_rank] end row of each local expert (device-side; never read here)
+    token_row: torch.Tensor     # int32 [T]: row of each LOCAL token inside its owner's buffer (-1 = not routed)
+    expected_m: int             # host-side estimate of rows per expert, for the GEMM heuristics only
+
+
+class EpBuffer:
+    """One symmetric dispatch buffer per rank, mapped into every peer (CUDA IPC over NVLink).
+
+    capacity = maximum rows this rank can receive in one dispatch INCLUDING the per-expert alignment padding
+    (worst case: all tokens of all ranks + experts_per_rank * alignment)."""
+
+    def __init__(self, num_experts: int, capacity: int, k: int, group: Optional[dist.ProcessGroup] = None,
+                 device: Optional[torch.device] = None):
+        from . import runtime
+        from ._lib import check, lib
+        import ctypes
+        if not torch.cuda.is_available():
+            raise RuntimeError('EpBuffer needs CUDA (there is no CPU fallback; dispatch_alltoall is the library baseline)')
+        self._lib, self._check = lib(), check
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.group = group
+        self.device = torch.device('cuda', torch.cuda.current_device()) if device is None else device
+        self.num_experts, self.capacity, self.k = num_experts, capacity, k
+        self.kp = _ceil_div(k, 512)
+        self.alignment = runtime.get_mk_alignment_for_contiguous_layout()
+        assert num_experts % self.world == 0
+        self.nbytes = int(self._lib.dgb200_ep_buffer_bytes(self.world, num_experts, capacity, k))
+        offs = (ctypes.c_int64 * 6)()
+        check(self._lib.dgb200_ep_buffer_offsets(self.world, num_experts, capacity, k, offs))
+        self.off_a, self.off_sfa, self.off_psum, self.off_counts, self.off_rows, self.off_overflow = list(offs)
+        with torch.cuda.device(self.device):
+            ptr = ctypes.c_void_p()
+            check(self._lib.dgb200_ep_alloc(self.nbytes, ctypes.byref(ptr)))
+            self.ptr = ptr.value
+            self.peer_ptrs = [None] * self.world
+            self.peer_ptrs[self.rank] = self.ptr
+            if self.world > 1:
+                handle = (ctypes.c_ubyte * 64)()
+                check(self._lib.dgb200_ep_export(self.ptr, handle))
+                mine = torch.tensor(list(handle), dtype=torch.uint8, device=self.device)
+                every = torch.empty(self.world * 64, dtype=torch.uint8, device=self.device)
+                dist.all_gather_into_tensor(every, mine, group=group)
+                every = every.cpu().view(self.world, 64)
+                for p in range(self.world):
+                    if p == self.rank:
+                        continue
+                    raw = (ctypes.c_ubyte * 64)(*every[p].tolist())
+                    out = ctypes.c_void_p()
+                    check(self._lib.dgb200_ep_import(raw, ctypes.byref(out)))
+                    self.peer_ptrs[p] = out.value
+                dist.barrier(group=group)          # every peer has mapped every buffer before the first dispatch
+        self._ptr_array = (ctypes.c_void_p * self.world)(*self.peer_ptrs)
+        self._bytes = torch.as_tensor(_RawCuda(self.ptr, self.nbytes), device=self.device)
+        b = self._bytes
+        self.a = b[self.off_a:self.off_a + capacity * k].view(torch.float8_e4m3fn).view(capacity, k)
+        self.sfa = b[self.off_sfa:self.off_sfa + 4 * self.kp * capacity].view(torch.int32).view(self.kp, capacity).t()
+        epr = num_experts // self.world
+        self.psum_layout = b[self.off_psum:self.off_psum + 4 * epr].view(torch.int32)
+        self.counts = b[self.off_counts:self.off_counts + 4 * num_experts].view(torch.int32)
+        self._ctrl = b[:64].view(torch.int32)
+
+    # device-side scalars (reading them synchronises; the data path never does)
+    def num_rows(self) -> int:
+        return int(self._ctrl[self.off_rows // 4].item())
+
+    def overflowed(self) -> bool:
+        return bool(self._ctrl[self.off_overflow // 4].item())
+
+    def dispatch(self, x_fp8: torch.Tensor, sf_packed: torch.Tensor, expert_ids: torch.Tensor,
+                 token_row: Optional[torch.Tensor] = None) -> PeerDispatch:
+        """Enqueue the four dispatch kernels on the current stream. x_fp8 [T,K] e4m3 (row pitch multiple of 16 B),
+        sf_packed [T, ceil(K/512)] int32 (any strides), expert_ids [T] int32/int64 (outside [0,G) = not routed)."""
+        t, k = x_fp8.shape
+        assert k == self.k and x_fp8.stride(1) == 1 and x_fp8.is_cuda
+        assert sf_packed.dtype == torch.int32 and sf_packed.shape == (t, self.kp)
+        assert expert_ids.dtype in (torch.int32, torch.int64) and expert_ids.is_contiguous() and expert_ids.numel() == t
+        if token_row is None:
+            token_row = torch.empty(t, dtype=torch.int32, device=x_fp8.device)
+        self._check(self._lib.dgb200_ep_dispatch(
+            x_fp8.data_ptr(), x_fp8.stride(0), sf_packed.data_ptr(), sf_packed.stride(0), sf_packed.stride(1),
+            expert_ids.data_ptr(), expert_ids.element_size(), t, k, self.num_experts, self.rank, self.world,
+            self._ptr_array, self.capacity, self.alignment, token_row.data_ptr(),
+            torch.cuda.current_stream().cuda_stream))
+        return PeerDispatch(a=self.a, sfa=self.sfa, psum_layout=self.psum_layout, token_row=token_row,
+                            expected_m=max(1, t * self.world // self.num_experts))
+
+    def close(self) -> None:
+        if getattr(self, 'ptr', None) is None:
+            return
+        torch.cuda.synchronize(self.device)
+        if self.world > 1:
+            dist.barrier(group=self.group)       # nobody unmaps while a peer may still be writing
+        for p, ptr in enumerate(self.peer_ptrs):
+            if p != self.rank and ptr is not None:
+                self._lib.dgb200_ep_unimport(ptr)
+        self.a = self.sfa = self.psum_layout = self.counts = self._ctrl = self._bytes = None
+        self._lib.dgb200_ep_free(self.ptr)
+        self.ptr = None
+
+
 def expert_sharded_grouped_gemm(x_fp8: torch.Tensor, sf_packed: torch.Tensor, expert_ids: torch.Tensor,
-                                w_local: Tuple[torch.Tensor, torch.Tensor], num_experts: int,
-                                group: Optional[dist.ProcessGroup] = None,
-                                use_psum_layout: bool = True) -> Tuple[torch.Tensor, DispatchResult]:
-    """Dispatch + local grouped GEMM. `w_local` = (B [G/P, N, K] e4m3, SFB) for THIS rank's experts (SFB FP32
-    [G/P, N/128, K/128] or pre-packed int32). Returns (D [m_aligned, N] bf16 on the expert rank, dispatch record)."""
-    from . import gemm, runtime
-    alignment = runtime.get_mk_alignment_for_contiguous_layout()
-    r = dispatch(x_fp8, sf_packed, expert_ids, num_experts, alignment, group)
+                                w_local: Tuple[torch.Tensor, torch.Tensor], buffer: EpBuffer,
+                                d: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, PeerDispatch]:
+    """Peer-memory dispatch + local grouped GEMM, all enqueued on the current stream without host synchronisation.
+    `w_local` = (B [G/P, N, K] e4m3, SFB) for THIS rank's experts (SFB FP32 [G/P, N/128, K/128] or pre-packed int32).
+    Returns (D [capacity, N] bf16 on the expert rank -- rows as laid out by `psum_layout` --, dispatch record)."""
+    from . import gemm
+    r = buffer.dispatch(x_fp8, sf_packed, expert_ids)
     n = w_local[0].shape[1]
-    d = torch.empty((r.a.shape[0], n), dtype=torch.bfloat16, device=x_fp8.device)
-    if r.a.shape[0] > 0:
-        layout = r.psum_layout if use_psum_layout else r.grouped_layout
-        gemm.m_grouped_fp8_gemm_nt_contiguous((r.a, r.sfa), w_local, d, layout, use_psum_layout=use_psum_layout)
+    if d is None:
+        d = torch.empty((buffer.capacity, n), dtype=torch.bfloat16, device=x_fp8.device)
+    gemm.m_grouped_fp8_gemm_nt_contiguous((r.a, r.sfa), w_local, d, r.psum_layout, use_psum_layout=True,
+                                          expected_m_for_psum_layout=r.expected_m)
     return d, r

@@ -128,6 +128,35 @@ int dgb200_k_grouped_fp8_gemm_tn_contiguous(const void* a, const int32_t* sfa, c
                                             float* d, const int32_t* grouped_layout, int num_groups, int m, int n,
                                             int sum_k, int sf_rows, int gran_k, int use_psum_layout, void* stream);
 
+/* ---- expert-parallel dispatch over NVLink peer memory ----------------------------------------------------------
+ * The m-grouped contiguous GEMM sharded by experts (rank r of `world` owns experts [r*G/world, (r+1)*G/world)); the
+ * reference pairs its grouped GEMM with an external dispatch library for this (tests/test_mega_moe.py:148-205).
+ * Every rank owns one "dispatch buffer" of dgb200_ep_buffer_bytes() bytes, identical layout on all ranks, mapped into
+ * every peer (dgb200_ep_export / _import use CUDA IPC; any other peer-mapping mechanism works as long as `buffers[p]`
+ * is rank p's buffer as addressable from the calling device). dgb200_ep_dispatch() enqueues four kernels that write
+ * the local tokens straight into the owners' buffers in the contiguous-grouped psum layout and return once all rows
+ * destined to THIS rank have landed (in stream order) -- the GEMM then reads, inside the local buffer,
+ *   a   = base + offsets[DGB200_EP_OFF_A]    uint8/e4m3 [capacity, k]
+ *   sfa = base + offsets[DGB200_EP_OFF_SFA]  int32 [ceil(k/512), capacity] (MN-major, sfa_stride = capacity)
+ *   psum layout = base + offsets[DGB200_EP_OFF_PSUM] int32 [G/world], m = capacity.
+ * No host synchronisation, CUDA-graph capturable; all ranks must call it the same number of times. */
+enum { DGB200_EP_OFF_A = 0, DGB200_EP_OFF_SFA = 1, DGB200_EP_OFF_PSUM = 2, DGB200_EP_OFF_COUNTS = 3,
+       DGB200_EP_OFF_NUM_ROWS = 4, DGB200_EP_OFF_OVERFLOW = 5, DGB200_EP_NUM_OFFSETS = 6 };
+int64_t dgb200_ep_buffer_bytes(int world, int num_experts, int capacity, int k);
+int dgb200_ep_buffer_offsets(int world, int num_experts, int capacity, int k, int64_t* offsets /* [DGB200_EP_NUM_OFFSETS] */);
+int dgb200_ep_alloc(int64_t bytes, void** ptr);                 /* cudaMalloc + zero fill: IPC exportable */
+int dgb200_ep_free(void* ptr);
+int dgb200_ep_export(void* ptr, void* handle_64_bytes);         /* cudaIpcGetMemHandle */
+int dgb200_ep_import(const void* handle_64_bytes, void** ptr);  /* cudaIpcOpenMemHandle (enables peer access) */
+int dgb200_ep_unimport(void* ptr);
+/* x [num_tokens, k] e4m3 rows (pitch ldx bytes), sf: packed UE8M0 words of token t at sf[t*sf_stride_t + j*sf_stride_k],
+ * j < ceil(k/512); expert_ids int32 (id_bytes 4) or int64 (id_bytes 8), values outside [0, num_experts) = not routed.
+ * token_row int32[num_tokens] (out): row of each token inside its owner's buffer (-1: not routed / dropped on
+ * overflow, which also sets the word at DGB200_EP_OFF_OVERFLOW). k % 16 == 0, ceil(k/512) <= 32. */
+int dgb200_ep_dispatch(const void* x, int64_t ldx, const int32_t* sf, int64_t sf_stride_t, int64_t sf_stride_k,
+                       const void* expert_ids, int id_bytes, int num_tokens, int k, int num_experts, int rank, int world,
+                       void* const* buffers, int capacity, int alignment, int32_t* token_row, void* stream);
+
 /* ---- introspection (bench / tests) -------------------------------------------------------------------------- */
 typedef struct dgb200_config {
     int block_m;     /* token rows per tile */

@@ -28,7 +28,7 @@ def _worker(rank, world, port, t, k, num_experts, alignment, out):
     try:
         from deepgemm_b200 import ep
         x, sf, ids = _make_rank_inputs(rank, t, k, num_experts)
-        r = ep.dispatch(x, sf, ids, num_experts, alignment)
+        r = ep.dispatch_alltoall(x, sf, ids, num_experts, alignment)
         res = {k_: getattr(r, k_) for k_ in ('a', 'psum_layout', 'grouped_layout', 'recv_counts', 'num_recv')}
         res['sfa'] = torch.empty(r.sfa.shape, dtype=torch.int32).copy_(r.sfa)
         res['sfa_stride'] = tuple(r.sfa.stride())

@@ -1,0 +1,117 @@
+"""GPU tests of the peer-memory expert-parallel dispatch (csrc/ep_dispatch.cuh through the C ABI, deepgemm_b200/ep.py).
+
+Single GPU: world size 1 exercises all four kernels (bucket / exchange / scatter / wait) with the rank being its own
+peer; the result must be bit-identical to the torch re-layout `dispatch_local`. With >= 2 GPUs the torchrun script
+tools/ep_check.py additionally checks the NVLink path against the NCCL all-to-all baseline and under a CUDA graph.
+Reference context: the grouped GEMM inside expert parallelism, tests/test_mega_moe.py:148-205."""
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope='module')
+def dg():
+    if not torch.cuda.is_available():
+        pytest.skip('needs a GPU')
+    import deepgemm_b200
+    return deepgemm_b200
+
+
+@pytest.mark.parametrize('id_dtype', [torch.int64, torch.int32])
+@pytest.mark.parametrize('num_experts,t,k', [(8, 777, 1024), (32, 4096, 7168), (4, 5, 512)])
+def test_peer_dispatch_world1_equals_torch_relayout(dg, num_experts, t, k, id_dtype):
+    from deepgemm_b200 import ep
+    from deepgemm_b200.utils import per_token_cast_to_fp8
+    dev = torch.device('cuda', 0)
+    gen = torch.Generator(device=dev).manual_seed(t)
+    align = dg.get_mk_alignment_for_contiguous_layout()
+    x = torch.randn((t, k), device=dev, dtype=torch.bfloat16, generator=gen)
+    xq, sf = per_token_cast_to_fp8(x, True, 128, use_packed_ue8m0=True)
+    buf = ep.EpBuffer(num_experts, t + num_experts * align, k)
+    try:
+        for it in range(3):                                   # buffer reuse across epochs
+            ids = torch.randint(0, num_experts if it < 2 else 2, (t,), device=dev, generator=gen).to(id_dtype)
+            if it == 1:
+                ids[::7] = -1                                 # unrouted tokens are skipped
+            r = buf.dispatch(xq, sf, ids)
+            torch.cuda.synchronize()
+            keep = ids >= 0
+            ref = ep.dispatch_local(xq[keep], sf[keep], ids[keep].long(), num_experts, align)
+            m_al = ref.a.shape[0]
+            assert buf.num_rows() == m_al and not buf.overflowed()
+            assert torch.equal(r.psum_layout, ref.psum_layout)
+            valid = ref.grouped_layout >= 0
+            assert torch.equal(r.a[:m_al].view(torch.uint8)[valid], ref.a.view(torch.uint8)[valid])
+            assert torch.equal(r.sfa[:m_al][valid], ref.sfa[valid])
+            assert bool((r.token_row[~keep] == -1).all())
+            rows = r.token_row[keep].long()
+            assert torch.equal(r.a.view(torch.uint8)[rows], xq.view(torch.uint8)[keep])
+            assert torch.equal(ref.grouped_layout[rows].long(), ids[keep].long())
+    finally:
+        buf.close()
+
+
+def test_peer_dispatch_overflow_is_flagged_not_written(dg):
+    from deepgemm_b200 import ep
+    from deepgemm_b200.utils import per_token_cast_to_fp8
+    dev = torch.device('cuda', 0)
+    x = torch.randn((512, 512), device=dev, dtype=torch.bfloat16)
+    xq, sf = per_token_cast_to_fp8(x, True, 128, use_packed_ue8m0=True)
+    buf = ep.EpBuffer(4, 256, 512)
+    try:
+        r = buf.dispatch(xq, sf, torch.zeros(512, dtype=torch.int64, device=dev))
+        torch.cuda.synchronize()
+        assert buf.overflowed()
+        assert int((r.token_row >= 0).sum()) == 256 and int(r.token_row.max()) == 255
+    finally:
+        buf.close()
+
+
+def test_expert_sharded_grouped_gemm_world1_matches_oracle(dg):
+    from deepgemm_b200 import ep
+    from deepgemm_b200.utils import per_block_cast_to_fp8, per_token_cast_to_fp8
+    from oracle import blockwise
+    dev = torch.device('cuda', 0)
+    g, n, k, t = 4, 256, 512, 300
+    gen = torch.Generator(device=dev).manual_seed(5)
+    align = dg.get_mk_alignment_for_contiguous_layout()
+    w = torch.randn((g, n, k), device=dev, dtype=torch.bfloat16, generator=gen)
+    qs = [per_block_cast_to_fp8(w[i], True) for i in range(g)]
+    wq = (torch.stack([q[0] for q in qs]), torch.stack([q[1] for q in qs]))
+    x = torch.randn((t, k), device=dev, dtype=torch.bfloat16, generator=gen)
+    xq, sf_packed = per_token_cast_to_fp8(x, True, 128, use_packed_ue8m0=True)
+    _, sf_fp32 = per_token_cast_to_fp8(x, True, 128)
+    ids = torch.randint(0, g, (t,), device=dev, generator=gen)
+    buf = ep.EpBuffer(g, t + g * align, k)
+    try:
+        d, r = ep.expert_sharded_grouped_gemm(xq, sf_packed, ids, wq, buf)
+        torch.cuda.synchronize()
+        rows = r.token_row.long().cpu()
+        got = d.cpu()[rows].float()
+        for e in range(g):
+            sel = (ids == e).cpu()
+            if not bool(sel.any()):
+                continue
+            want = blockwise.fp8_gemm_nt((xq.cpu()[sel], sf_fp32.cpu()[sel]), (wq[0][e].cpu(), wq[1][e].cpu())).float()
+            mag = want.abs()
+            assert bool(((got[sel] - want).abs() <= mag * 2.0 ** -7 + 1e-5 * mag.max()).all())
+    finally:
+        buf.close()
+
+
+def test_multi_gpu_peer_dispatch_under_torchrun(dg):
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip('needs >= 2 GPUs on one node')
+    n = 2 if n < 4 else 4
+    cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', f'--nproc-per-node={n}', '--master-addr', '127.0.0.1',
+           '--master-port', '29541', os.path.join(REPO, 'tools', 'ep_check.py')]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=REPO)
+    assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
+    assert res.stdout.count('ep check ok') == n

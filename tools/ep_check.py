@@ -1,6 +1,10 @@
-"""Multi-GPU check of the expert-sharded grouped GEMM (run under torchrun, one rank per GPU).
-Every rank verifies (a) conservation: the rows it received are exactly the rows the others sent for its experts
-(global byte checksum), (b) its grouped GEMM output against an FP32 matmul of the dequantised received rows."""
+"""Multi-GPU check of the expert-sharded grouped GEMM (run under torchrun, one rank per GPU; also works with 1 GPU).
+Every rank verifies, over several dispatches with different routings (buffer reuse / epochs):
+ (a) the peer-memory dispatch (EpBuffer, csrc/ep_dispatch.cuh) lands bit-identical rows, scale factors and psum layout
+     to the NCCL all-to-all baseline (ep.dispatch_alltoall),
+ (b) token_row maps every locally-owned token to its row,
+ (c) the grouped GEMM output against an FP32 matmul of the dequantised received rows,
+ (d) a CUDA graph of dispatch + GEMM replays to the same result."""
 import os
 import sys
 
@@ -10,47 +14,95 @@ import torch.distributed as dist  # noqa: E402
 
 
 def main():
-    rank, world, local = int(os.environ['RANK']), int(os.environ['WORLD_SIZE']), int(os.environ['LOCAL_RANK'])
+    rank, world, local = int(os.environ.get('RANK', 0)), int(os.environ.get('WORLD_SIZE', 1)), int(os.environ.get('LOCAL_RANK', 0))
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
+    if 'RANK' not in os.environ:
+        os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT='29533', RANK='0', WORLD_SIZE='1')
     dist.init_process_group('nccl', device_id=dev)
-    import deepgemm_b200 as dg  # noqa: F401
+    import deepgemm_b200 as dg
     from deepgemm_b200 import ep
     from deepgemm_b200.testing import calc_diff
     from deepgemm_b200.utils import per_block_cast_to_fp8, per_token_cast_to_fp8
     g, n, k, t_local = 16, 512, 1024, 1000
     epr = g // world
+    align = dg.get_mk_alignment_for_contiguous_layout()
+    capacity = t_local * world + epr * align
     gen = torch.Generator(device=dev).manual_seed(1 + rank)
     w = torch.randn((epr, n, k), device=dev, dtype=torch.bfloat16, generator=gen)
     qs = [per_block_cast_to_fp8(w[i], True) for i in range(epr)]
     wq = (torch.stack([q[0] for q in qs]), torch.stack([q[1] for q in qs]))
-    x = torch.randn((t_local, k), device=dev, dtype=torch.bfloat16, generator=gen)
-    xq, sf = per_token_cast_to_fp8(x, True, 128, use_packed_ue8m0=True)
-    ids = torch.randint(0, g, (t_local,), device=dev, generator=gen)
-    d, r = ep.expert_sharded_grouped_gemm(xq, sf, ids, wq, g)
-    torch.cuda.synchronize()
-    # (a) conservation of tokens and bytes
-    sent = torch.tensor([float(t_local), float(xq.view(torch.uint8).double().sum())], device=dev, dtype=torch.float64)
-    recv = torch.tensor([float(r.num_recv), float(r.a.view(torch.uint8).double().sum())], device=dev, dtype=torch.float64)
-    dist.all_reduce(sent), dist.all_reduce(recv)
-    assert torch.equal(sent, recv), (sent, recv)
-    # (b) GEMM on the received rows
+    buf = ep.EpBuffer(g, capacity, k)
     torch.backends.cuda.matmul.allow_tf32 = False
-    dense_sf = torch.empty(r.sfa.shape, dtype=torch.int32, device=dev).copy_(r.sfa)
-    sfa = (dense_sf.view(torch.uint8).to(torch.int32) << 23).view(torch.float32)      # [m, 4*kp] per-128 scales
-    a_deq = r.a.float() * sfa[:, :k // 128].repeat_interleave(128, 1)
-    ok_rows, start = 0, 0
-    for e in range(epr):
-        end = int(r.psum_layout[e])
-        if end > start:
-            w_deq = wq[0][e].float() * wq[1][e].repeat_interleave(128, 0).repeat_interleave(128, 1)
-            want = a_deq[start:end] @ w_deq.t()
-            diff = calc_diff(d[start:end], want)
-            assert diff < 1e-5, (rank, e, diff)
-            ok_rows += end - start
-        start = (end + 127) // 128 * 128
-    assert ok_rows == r.num_recv
-    print(f'rank {rank}/{world}: ep check ok, received {r.num_recv} rows', flush=True)
+
+    def check(xq, sf, ids, d, r, tag):
+        torch.cuda.synchronize()
+        ref = ep.dispatch_alltoall(xq, sf, ids, g, align)
+        m_al = ref.a.shape[0]
+        assert buf.num_rows() == m_al, (buf.num_rows(), m_al)
+        assert not buf.overflowed()
+        assert torch.equal(r.psum_layout, ref.psum_layout), tag
+        valid = ref.grouped_layout >= 0
+        assert torch.equal(r.a[:m_al].view(torch.uint8)[valid], ref.a.view(torch.uint8)[valid]), tag
+        assert torch.equal(r.sfa[:m_al][valid], ref.sfa[valid]), tag
+        # (b) my tokens that I own myself
+        mine = (ids // epr) == rank
+        rows = r.token_row[mine].long()
+        assert torch.equal(r.a.view(torch.uint8)[rows], xq.view(torch.uint8)[mine]), tag
+        # (c) GEMM on the received rows
+        dense_sf = torch.empty((m_al, r.sfa.shape[1]), dtype=torch.int32, device=dev).copy_(r.sfa[:m_al])
+        sfa = (dense_sf.view(torch.uint8).to(torch.int32) << 23).view(torch.float32)
+        a_deq = r.a[:m_al].float() * sfa[:, :k // 128].repeat_interleave(128, 1)
+        ok_rows, start = 0, 0
+        for e in range(epr):
+            end = int(r.psum_layout[e])
+            if end > start:
+                w_deq = wq[0][e].float() * wq[1][e].repeat_interleave(128, 0).repeat_interleave(128, 1)
+                diff = calc_diff(d[start:end], a_deq[start:end] @ w_deq.t())
+                assert diff < 1e-5, (rank, e, diff, tag)
+                ok_rows += end - start
+            start = (end + align - 1) // align * align
+        assert ok_rows == ref.num_recv
+        return ok_rows
+
+    d = torch.empty((capacity, n), dtype=torch.bfloat16, device=dev)
+    total = 0
+    for it in range(4):
+        x = torch.randn((t_local, k), device=dev, dtype=torch.bfloat16, generator=gen)
+        xq, sf = per_token_cast_to_fp8(x, True, 128, use_packed_ue8m0=True)
+        hi = g if it != 2 else max(1, g // 4)          # iteration 2: skewed routing (few experts, some ranks idle)
+        ids = torch.randint(0, hi, (t_local,), device=dev, generator=gen)
+        if it == 3:
+            ids = ids.to(torch.int32)
+        d.fill_(float('nan'))
+        _, r = ep.expert_sharded_grouped_gemm(xq, sf, ids, wq, buf, d)
+        total += check(xq, sf, ids.long(), d, r, f'iter {it}')
+
+    # (d) CUDA graph: capture dispatch + GEMM once, replay with new inputs
+    sx, ssf, sids = torch.empty_like(xq), torch.empty_like(sf), torch.empty(t_local, dtype=torch.int64, device=dev)
+    row = torch.empty(t_local, dtype=torch.int32, device=dev)
+    side = torch.cuda.Stream()
+    with torch.cuda.stream(side):
+        for _ in range(2):                              # warm-up outside capture (same count on every rank)
+            r = buf.dispatch(sx.copy_(xq), ssf.copy_(sf), sids.copy_(ids), row)
+            dg.m_grouped_fp8_gemm_nt_contiguous((r.a, r.sfa), wq, d, r.psum_layout, use_psum_layout=True)
+    torch.cuda.synchronize()
+    dist.barrier()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph, stream=side):
+        r = buf.dispatch(sx, ssf, sids, row)
+        dg.m_grouped_fp8_gemm_nt_contiguous((r.a, r.sfa), wq, d, r.psum_layout, use_psum_layout=True)
+    for it in range(2):
+        x = torch.randn((t_local, k), device=dev, dtype=torch.bfloat16, generator=gen)
+        xq, sf = per_token_cast_to_fp8(x, True, 128, use_packed_ue8m0=True)
+        ids = torch.randint(0, g, (t_local,), device=dev, generator=gen)
+        sx.copy_(xq), ssf.copy_(sf), sids.copy_(ids)
+        d.fill_(float('nan'))
+        graph.replay()
+        total += check(xq, sf, ids, d, r, f'graph {it}')
+    print(f'rank {rank}/{world}: ep check ok, {total} rows verified over 6 dispatches (2 under CUDA graph)', flush=True)
+    del graph
+    buf.close()
     dist.destroy_process_group()
 
 
