@@ -10,7 +10,7 @@ import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _REPO = os.path.dirname(_HERE)
-LIB_PATH = os.path.join(_HERE, 'lib', 'libdgb200.so')
+LIB_PATH = os.environ.get('DGB200_LIB') or os.path.join(_HERE, 'lib', 'libdgb200.so')   # env: development only
 SOURCES = [os.path.join(_HERE, 'csrc', f) for f in
            ('dgb200_api.cu', 'fp8_gemm_kernel.cuh', 'ptx.cuh', 'sf_layout.cuh')] + [os.path.join(_REPO, 'include', 'dgb200.h')]
 

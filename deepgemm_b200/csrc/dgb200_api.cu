@@ -370,12 +370,23 @@ int launch_kernel(Kernel kernel, const Config& cfg, cudaStream_t stream, const C
 //   masked         : bf16, no C, both K-major, clusters 1,2                             (gemm.hpp:263,275)
 //   k-grouped(+psum): fp32, accumulate into D, both MN-major, clusters 1,2             (gemm.hpp:325-328)
 #define DGB_LAUNCH(TYPE, CL, OUT, ACC, XMN, WMN) \
-    launch_kernel(fp8_gemm_kernel<TYPE, CL, OUT, ACC, XMN, WMN>, cfg, c.stream, mx, mw, msfx, msfw, p)
+    launch_kernel(fp8_gemm_kernel<TYPE, CL, OUT, ACC, XMN, WMN, false>, cfg, c.stream, mx, mw, msfx, msfw, p)
+#define DGB_LAUNCH_SPLITK(CL, OUT, ACC, XMN, WMN) \
+    launch_kernel(fp8_gemm_kernel<kDense, CL, OUT, ACC, XMN, WMN, true>, cfg, c.stream, mx, mw, msfx, msfw, p)
 
 template <int kType, int kCluster, bool kXMn, bool kWMn>
 int dispatch_out(const GemmCall& c, const Config& cfg, const CUtensorMap& mx, const CUtensorMap& mw,
                  const CUtensorMap& msfx, const CUtensorMap& msfw, const GemmParams& p) {
     if constexpr (kType == kDense) {
+        if constexpr (kCluster <= 2) {
+            if (cfg.num_splits > 1) {
+                if (c.d_dtype == DGB200_BF16)
+                    return c.accumulate ? DGB_LAUNCH_SPLITK(kCluster, __nv_bfloat16, true, kXMn, kWMn)
+                                        : DGB_LAUNCH_SPLITK(kCluster, __nv_bfloat16, false, kXMn, kWMn);
+                return c.accumulate ? DGB_LAUNCH_SPLITK(kCluster, float, true, kXMn, kWMn)
+                                    : DGB_LAUNCH_SPLITK(kCluster, float, false, kXMn, kWMn);
+            }
+        }
         if (c.d_dtype == DGB200_BF16)
             return c.accumulate ? DGB_LAUNCH(kType, kCluster, __nv_bfloat16, true, kXMn, kWMn)
                                 : DGB_LAUNCH(kType, kCluster, __nv_bfloat16, false, kXMn, kWMn);

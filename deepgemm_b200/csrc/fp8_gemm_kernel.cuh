@@ -101,7 +101,7 @@ struct Tile {
 
 // kCluster = CTAs per cluster: 1 (single CTA MMA), 2 (one cta_group::2 pair) or 4 / 8 (2 / 4 pairs that work on
 // consecutive m-blocks of the SAME weight panel and share its TMA loads by multicast; dense only).
-template <int kGemmType, int kCluster>
+template <int kGemmType, int kCluster, bool kSplitK = false>
 struct Scheduler {
     static constexpr uint32_t kPairs = kCluster >= 2 ? kCluster / 2 : 1;
     static constexpr uint32_t kCtaGroup = kCluster >= 2 ? 2 : 1;
@@ -189,7 +189,7 @@ struct Scheduler {
         if constexpr (kGemmType == kDense || kGemmType == kMContiguous) {
             const uint32_t num_m = (p.num_m_blocks + kPairs - 1) / kPairs;   // m-blocks are handed out kPairs at a time
             uint32_t local = idx;
-            if (kGemmType == kDense && p.num_splits > 1) {
+            if (kSplitK) {
                 // split-K: slice index varies slowest, so the CTAs of one slice stream disjoint weight panels
                 const uint32_t per_split = num_m * num_n_units;
                 if (idx >= per_split * p.num_splits) return false;
@@ -337,7 +337,10 @@ __device__ __forceinline__ void splitk_finalize(const float* ws, size_t slice_el
 
 // kXMn / kWMn: the token / weight operand is MN-major in global memory (its M / N extent is contiguous, K strided):
 // fp8_gemm_{nn,tn,tt}, m_grouped nn, and both operands of the K-grouped weight-gradient GEMM.
-template <int kGemmType, int kCluster, typename out_t, bool kAccumulate, bool kXMn = false, bool kWMn = false>
+// kSplitK: the dense split-K variant (K slices + finalising pass); kept out of the common instantiations because its
+// epilogue doubles the code size, which a cold instruction cache charges to every short launch.
+template <int kGemmType, int kCluster, typename out_t, bool kAccumulate, bool kXMn = false, bool kWMn = false,
+          bool kSplitK = false>
 __global__ void __launch_bounds__(kNumThreads, 1)
 fp8_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
                 const __grid_constant__ CUtensorMap map_sfx, const __grid_constant__ CUtensorMap map_sfw,
@@ -373,41 +376,57 @@ fp8_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
     const uint32_t tmem_ptr_smem = tmem_empty_bar + 16;
     const uint32_t splitk_flag_smem = tmem_ptr_smem + 4;
 
-    // Setup, arranged so that the independent pieces overlap: the first cluster barrier (both CTAs of a pair must be
-    // resident before a cta_group::2 TMEM allocation) is split-phase around the barrier initialisation, which is
-    // spread over the lanes of warp 1; warp 2 allocates tensor memory as soon as the cluster is known to be up.
-    if constexpr (kCluster > 1) cluster_arrive_relaxed();
-    if (warp_idx == 0 && elect_one()) {
-        prefetch_tensormap(&map_x);
-        prefetch_tensormap(&map_w);
-        prefetch_tensormap(&map_sfx);
-        prefetch_tensormap(&map_sfw);
-    }
-    if (warp_idx == 1) {
+    // Setup, arranged so that nothing waits that does not have to.
+    //  * Warp 0 (TMA producer) initialises the barriers only it and the MMA commits touch (full / empty), warp 1 the
+    //    rest; both publish them with `fence.mbarrier_init.release.cluster` + a relaxed arrive on the ONE cluster barrier
+    //    of the prologue (a release-arrive would cost a MEMBAR.ALL.GPU). Passing that barrier therefore means: every
+    //    CTA of the cluster is resident and all its mbarriers are live.
+    //  * Warp 0 does not wait for it: its loads are local and the first thing a peer can do to it -- an MMA commit on
+    //    `empty` -- happens only after the peer has passed the barrier, i.e. after warp 0's own arrive. So the producer
+    //    starts streaming ~150 cycles into the kernel and collects the barrier phase after its loop. (Multi-pair
+    //    clusters multicast into their peers' shared memory, so there it waits like everyone else.)
+    //  * The others wait, warp 2 allocates tensor memory, and a CTA-local named barrier (warps 1..11) publishes the
+    //    TMEM address. The peer's allocation is ordered before the leader's first MMA by the peer's re-tiler warp,
+    //    which allocates first and arrives on the leader's `ready` barrier afterwards.
+    constexpr bool kEarlyProducer = kPairs == 1;
+    bool producer_lane = false;
+    if (warp_idx == 0) {
         for (uint32_t i = lane; i < num_stages; i += 32) {
             mbar_init(full_bar + i * 8, 1);
             mbar_init(empty_bar + i * 8, kPairs);      // one commit per pair: peers multicast weights into this slot too
-            mbar_init(ready_bar + i * 8, 32 * kCtaGroup);
         }
+        fence_mbar_init();
+        __syncwarp();
+        producer_lane = elect_one();
+        if (producer_lane) {
+            prefetch_tensormap(&map_x);
+            prefetch_tensormap(&map_w);
+            prefetch_tensormap(&map_sfx);
+            prefetch_tensormap(&map_sfw);
+        }
+        __syncwarp();
+    } else if (warp_idx == 1) {
+        for (uint32_t i = lane; i < num_stages; i += 32) mbar_init(ready_bar + i * 8, 32 * kCtaGroup);
         if (lane < 2) {
             mbar_init(tmem_full_bar + lane * 8, 1);
             mbar_init(tmem_empty_bar + lane * 8, kNumEpilogueThreads * kCtaGroup);
         }
         fence_mbar_init();
+        __syncwarp();
     }
-    if constexpr (kCluster > 1) cluster_wait();
-    if (warp_idx == 2) tmem_alloc<kCtaGroup>(tmem_ptr_smem, kTmemCols);
-    tcgen05_fence_before();
-    if constexpr (kCluster > 1) {
-        // relaxed arrive: `fence.mbarrier_init.release.cluster` above already publishes the barrier inits, and a
-        // release-arrive would cost a MEMBAR.ALL.GPU
-        cluster_arrive_relaxed();
-        cluster_wait();
-    } else {
-        __syncthreads();
+    if constexpr (kCluster > 1) cluster_arrive_relaxed();
+    uint32_t tmem_base = 0;
+    if (warp_idx != 0 || !kEarlyProducer) {
+        if constexpr (kCluster > 1) cluster_wait();
+        if (warp_idx == 2) tmem_alloc<kCtaGroup>(tmem_ptr_smem, kTmemCols);
+        tcgen05_fence_before();
+        if constexpr (kEarlyProducer)
+            named_bar_sync(2, kNumThreads - 32);           // warps 1..11; warp 0 needs nothing that is set up here
+        else
+            __syncthreads();
+        tcgen05_fence_after();
+        tmem_base = ld_shared_u32(tmem_ptr_smem);
     }
-    tcgen05_fence_after();
-    const uint32_t tmem_base = ld_shared_u32(tmem_ptr_smem);
 
     // Programmatic dependent launch: everything above overlaps the previous kernel's tail
     asm volatile("griddepcontrol.wait;" ::: "memory");
@@ -418,30 +437,24 @@ fp8_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
 
     if (warp_idx == 0) {
         // =================================================================== TMA producer (one lane, every CTA)
-        if (elect_one()) {
-            Scheduler<kGemmType, kCluster> sched(p, cta_rank);
+        if (producer_lane) {
+            Scheduler<kGemmType, kCluster, kSplitK> sched(p, cta_rank);
             Tile t;
             const uint32_t ab_bytes = kWTileBytes + x_tile_bytes;
             const uint32_t sfw_tx = kBlockN * 4, sfx_tx = p.block_m * 4;
-            // multi-pair clusters: this CTA fetches 1/kPairs of its weight tile and multicasts it to the CTAs of the
-            // same parity in every pair (they need the same 128 weight rows for their own m-blocks)
             constexpr uint32_t kWRows = kBlockN / kPairs;
             uint16_t w_mask = 0;
             for (uint32_t q = 0; q < kPairs; ++q) w_mask |= static_cast<uint16_t>(1u << (2 * q + (cta_rank & 1)));
             while (sched.next(t)) {
-                if (kGemmType == kMContiguousPsum && t.valid_m == 0) continue;   // padding-only tile: nothing to load
+                if (kGemmType == kMContiguousPsum && t.valid_m == 0) continue;
                 const uint32_t x_row = t.x_row + (cta_rank & 1) * load_m;
                 uint32_t k0 = t.kb_begin * kBlockK;
                 for (uint32_t kb = t.kb_begin; kb < t.kb_end; ++kb, k0 += kBlockK, ring.advance()) {
                     const uint32_t full = full_bar + ring.bar, slot = smem_base + ring.slot;
                     mbar_wait(empty_bar + ring.bar, ring.phase ^ 1);
-                    // a packed SF word covers 4 k-blocks (gran_k 128); a split-K slice may start inside one
                     const bool first = kb == t.kb_begin;
                     const bool load_sfw = (kb & sfw_mask) == 0 || first, load_sfx = (kb & sfx_mask) == 0 || first;
                     mbar_arrive_expect_tx(full, ab_bytes + (load_sfw ? sfw_tx : 0u) + (load_sfx ? sfx_tx : 0u));
-                    // K-major operand: box = 128 K-bytes x rows, coordinates (k, row).
-                    // MN-major operand: box = S contiguous MN-bytes x 128 K-rows, coordinates (mn, k row); S = 128 for the
-                    // weights (one swizzle atom), p.x_swizzle for the tokens (load_m / S atoms side by side).
                     if constexpr (kWMn) {
                         tma_load_2d(&map_w, full, slot, t.n0, t.wk_base + t.k_base + k0, kEvictNormal);
                     } else if constexpr (kPairs == 1) {
@@ -462,10 +475,14 @@ fp8_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
                 }
             }
         }
+        if constexpr (kCluster > 1 && kEarlyProducer) {
+            __syncwarp();
+            cluster_wait();        // collect the prologue's cluster barrier phase (long complete)
+        }
     } else if (warp_idx == 1) {
         // =================================================================== MMA issuer (leader CTA only)
         if (is_leader) {
-            Scheduler<kGemmType, kCluster> sched(p, cta_rank);
+            Scheduler<kGemmType, kCluster, kSplitK> sched(p, cta_rank);
             Tile t;
             const uint32_t idesc_base = make_idesc(128 * kCtaGroup, p.block_m, kWMn ? 1 : 0, kXMn ? 1 : 0);
             // descriptors of slot 0; a slot offset adds (bytes >> 4) to the 14-bit start-address field.
@@ -547,7 +564,7 @@ fp8_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
         }
     } else if (warp_idx == 2) {
         // =================================================================== SF re-tiler / slot forwarder
-        Scheduler<kGemmType, kCluster> sched(p, cta_rank);
+        Scheduler<kGemmType, kCluster, kSplitK> sched(p, cta_rank);
         Tile t;
         // tcgen05.cp 32x128b wants word (row r of the 128-group) at [r % 32][r / 32]; TMA delivered it at [r]
         auto retile = [&](uint32_t base) {
@@ -583,7 +600,7 @@ fp8_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
         }
     } else if (warp_idx >= 4) {
         // =================================================================== epilogue: TMEM -> registers -> global
-        Scheduler<kGemmType, kCluster> sched(p, cta_rank);
+        Scheduler<kGemmType, kCluster, kSplitK> sched(p, cta_rank);
         Tile t;
         const uint32_t quad = warp_idx & 3;                 // TMEM lane quadrant this warp may read
         const uint32_t half = (warp_idx - 4) >> 2;          // 0: chunks 0,2,4.. | 1: chunks 1,3,5..
@@ -607,7 +624,7 @@ fp8_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
             if (threadIdx.x == 128) DGB_STAMP(6);
             const uint32_t taddr = tmem_base + ((quad * 32) << 16) + as * kAccumColStride;
             const uint32_t load_cols = (max(t.valid_m, 1u) + 15) / 16 * 16;
-            if (kGemmType == kDense && p.num_splits > 1) {
+            if constexpr (kSplitK) {
                 // ---------------------------------------------------------------- split-K epilogue
                 // (1) park this slice's FP32 partial tile in the workspace, (2) count arrivals per output block,
                 // (3) the last slice to arrive adds the partials in slice order (deterministic) and writes D.
@@ -726,6 +743,7 @@ fp8_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
     // ---- teardown
     if (threadIdx.x == 128) DGB_STAMP(7);
     if (threadIdx.x == 0) DGB_STAMP(8);
+    __syncwarp();
     tcgen05_fence_before();
     if constexpr (kCluster > 1) {
         cluster_arrive_relaxed();   // (a release-arrive here would wait for every output store to become visible)

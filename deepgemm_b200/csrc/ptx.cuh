@@ -58,6 +58,9 @@ DGB_DEVICE bool elect_one() {
 DGB_DEVICE void cluster_arrive_relaxed() { asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory"); }
 DGB_DEVICE void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
 DGB_DEVICE void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+// per-thread forms (no .aligned): for a lane that joins the cluster barrier on its own schedule
+DGB_DEVICE void cluster_arrive_relaxed_thread() { asm volatile("barrier.cluster.arrive.relaxed;" ::: "memory"); }
+DGB_DEVICE void cluster_wait_thread() { asm volatile("barrier.cluster.wait.acquire;" ::: "memory"); }
 
 // ---------------------------------------------------------------- mbarrier (all addresses are 32-bit shared::cta)
 DGB_DEVICE void mbar_init(uint32_t bar, uint32_t count) {

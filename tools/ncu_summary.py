@@ -1,4 +1,4 @@
-"""Summarise .ncu-rep files (key metrics per kernel launch) as markdown. usage: ncu_summary.py out.md rep1 [rep2 ...]"""
+"""Summarise .ncu-rep files (or their `--page raw --csv` dumps) (key metrics per kernel launch) as markdown. usage: ncu_summary.py out.md rep1 [rep2 ...]"""
 import csv
 import io
 import subprocess
@@ -29,7 +29,10 @@ def main():
     out_path, reps = sys.argv[1], sys.argv[2:]
     lines = ['# ncu summaries (`ncu --set full --clock-control none --import-source on`, B200)\n']
     for rep in reps:
-        raw = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
+        if rep.endswith('.csv'):
+            raw = open(rep).read()
+        else:
+            raw = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
         rows = list(csv.reader(io.StringIO(raw)))
         if len(rows) < 3:
             lines.append(f'## {rep}\n(no data)\n')
