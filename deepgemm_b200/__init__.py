@@ -17,10 +17,10 @@ from .layout import (  # noqa: F401
     transform_sf_into_required_layout,
 )
 from .runtime import (  # noqa: F401
-    get_mk_alignment_for_contiguous_layout, get_num_sms, get_pdl, get_tc_util,
+    get_mk_alignment_for_contiguous_layout, get_num_sms, get_pdl, get_split_k, get_tc_util,
     get_theoretical_mk_alignment_for_contiguous_layout, get_tma_aligned_size,
     set_block_size_multiple_of, set_ignore_compile_dims, set_mk_alignment_for_contiguous_layout,
-    set_num_sms, set_pdl, set_tc_util,
+    set_num_sms, set_pdl, set_split_k, set_tc_util,
 )
 
 # canonical names of the reference (csrc/apis/gemm.hpp:649-717): `fp8_fp4_*`, with `fp8_*` as aliases

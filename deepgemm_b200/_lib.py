@@ -37,7 +37,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
 class _Config(ctypes.Structure):
     _fields_ = [(n, ctypes.c_int) for n in ('block_m', 'cluster', 'num_stages', 'num_sms', 'smem_bytes', 'num_tiles',
-                                            'num_splits')]
+                                            'num_splits', 'cluster_split')]
 
 
 _P, _I, _L = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64
@@ -52,6 +52,8 @@ SIGNATURES = {
     'dgb200_get_tc_util': (_I, []),
     'dgb200_set_pdl': (_I, [_I]),
     'dgb200_get_pdl': (_I, []),
+    'dgb200_set_split_k': (_I, [_I]),
+    'dgb200_get_split_k': (_I, []),
     'dgb200_set_mk_alignment_for_contiguous_layout': (_I, [_I]),
     'dgb200_get_mk_alignment_for_contiguous_layout': (_I, []),
     'dgb200_get_theoretical_mk_alignment_for_contiguous_layout': (_I, [_I]),

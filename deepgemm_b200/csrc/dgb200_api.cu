@@ -31,7 +31,7 @@ namespace {
 
 // ------------------------------------------------------------------------------------------------ errors
 thread_local std::string g_last_error;
-thread_local dgb200_config g_last_config = {0, 0, 0, 0, 0, 0, 0};
+thread_local dgb200_config g_last_config = {0, 0, 0, 0, 0, 0, 0, 0};
 std::atomic<int64_t> g_launch_count{0};
 std::atomic<long long*> g_debug_ts{nullptr};
 
@@ -73,6 +73,7 @@ struct Runtime {
     int tc_util = 100;
     int pdl = 0;
     int mk_alignment = 128;  // HeuristicsRuntime::kLegacyMKAlignmentForContiguousLayout
+    int split_k = 1;         // 0: never cut K (bit-identical to the reference's K order); 1: heuristics may
     EncodeTiledFn encode = nullptr;
 };
 Runtime& rt() {
@@ -181,14 +182,18 @@ struct Problem {
 struct Config {
     int block_m, cluster, stages, num_sms, smem_bytes, swizzle_group;
     int num_splits, kb_per_split;   // split-K (dense, small problems): K cut into num_splits ranges
+    int csplit;                     // cluster split-K: `cluster` single-CTA MMAs share one tile (then num_splits == cluster)
+    int grid, grid_y;               // grid == 0: persistent grid over num_sms; else exactly grid x grid_y CTAs
 };
 
 constexpr int kSmemCapacity = 232448;  // 227 KB usable per CTA on sm_100 (heuristics/sm100.hpp:15)
 
 int stage_bytes(int block_m, int cluster) { return static_cast<int>(slot_bytes(block_m, cluster)); }
-int smem_bytes_for(int block_m, int cluster, int stages) {
-    return stages * stage_bytes(block_m, cluster) + (3 * stages + 4) * 8 + 16;
+int smem_bytes_for(int block_m, int cluster, int stages, int staging_bytes = 0) {
+    // stage slots | barriers | tmem pointer + split-K flag | (cluster split-K: reduction barrier, 16-byte aligned staging)
+    return stages * stage_bytes(block_m, cluster) + (3 * stages + 4) * 8 + 16 + (staging_bytes ? 32 + staging_bytes : 0);
 }
+int csplit_staging_bytes(int block_m, int splits) { return (splits - 1) * (block_m / splits) * 128 * 4; }
 
 // Estimated cycles for the whole problem with a given tile height. All busy CTAs advance one k-block per "step";
 // a step is bounded by the slowest of four resources (constants are B200 measurements / fits):
@@ -197,7 +202,8 @@ int smem_bytes_for(int block_m, int cluster, int stages) {
 //   L2          : all busy CTAs together pull at most ~kL2Rate B/cycle
 //   HBM         : bytes that are new to the chip in this step (weight tiles are shared by the m-blocks in flight,
 //                 token tiles by the n-units in flight) at ~kHbmRate B/cycle
-constexpr double kSmIngest = 45.0, kL2Rate = 8000.0, kHbmRate = 3400.0, kTileOverhead = 1500.0, kSplitOverhead = 2500.0;
+constexpr double kSmIngest = 45.0, kL2Rate = 8000.0, kHbmRate = 3400.0, kTileOverhead = 1500.0, kSplitOverhead = 2500.0,
+                 kCSplitOverhead = 1200.0;
 constexpr int kMaxSplits = 8;
 constexpr int kSplitKCounters = 4096;                 // ints at the start of the workspace
 constexpr size_t kSplitKHeaderBytes = kSplitKCounters * sizeof(int);
@@ -248,7 +254,7 @@ Config choose_config(const Problem& pb, int num_sms_override = 0) {
         if (candidates.empty()) candidates.push_back(16);
     }
     const int num_kb = ceil_div(pb.k, (int)kBlockK);
-    const int max_splits = std::min({pb.max_splits, kMaxSplits, std::max(1, num_kb / 4)});
+    const int max_splits = rt().split_k ? std::min({pb.max_splits, kMaxSplits, std::max(1, num_kb / 4)}) : 1;
     double best = 1e300;
     c.block_m = candidates[0];
     c.num_splits = 1;
@@ -273,13 +279,43 @@ Config choose_config(const Problem& pb, int num_sms_override = 0) {
     if (const char* v = getenv("DGB200_SPLITS")) c.num_splits = std::max(1, std::min(atoi(v), max_splits));
     c.kb_per_split = ceil_div(num_kb, c.num_splits);
     c.num_splits = ceil_div(num_kb, c.kb_per_split);
-    const int cta_group = std::min(c.cluster, 2);
-    int stages = (kSmemCapacity - 64) / stage_bytes(c.block_m, cta_group);
-    while (stages > 1 && smem_bytes_for(c.block_m, cta_group, stages) > kSmemCapacity) --stages;
+
+    // Cluster split-K (dense, K-major, small M): S single-CTA MMAs share one output tile, each streams 1/S of K, and
+    // the partial tiles are reduced through distributed shared memory. Every weight byte then crosses L2 -> SM once
+    // (instead of once per m-block) and all SMs stream from HBM even when there are few output tiles.
+    c.csplit = 0, c.grid = 0, c.grid_y = 1;
+    const char* splits_env = getenv("DGB200_SPLITS");
+    const bool pinned = getenv("DGB200_BLOCK_M") || getenv("DGB200_CLUSTER") || (splits_env && atoi(splits_env) <= 1);
+    if (pb.type == kDense && !pb.any_mn && c.cluster == 2 && pb.m > 0 && rt().split_k && !(pinned && !getenv("DGB200_CSPLIT"))) {
+        const int want = env_int("DGB200_CSPLIT", -1);            // -1: heuristic, 0: off, 2/4: forced
+        int pick = 0, pick_bm = 0;
+        double pick_t = best;
+        for (int sp : {4, 2}) {
+            if (want == 0 || (want > 0 && want != sp)) continue;
+            const int bm = std::min(align_up(std::min(pb.m, 128), 16 * sp), align_up(128, 16 * sp));
+            const int tiles = ceil_div(pb.m, bm) * ceil_div(pb.n, (int)kBlockN);
+            if (bm > (int)kMaxBlockM || ceil_div(num_kb, sp) * (sp - 1) >= num_kb || num_kb / sp < 2) continue;
+            if (want < 0 && tiles * sp > c.num_sms) continue;    // one resident cluster per tile
+            // per k-block step of all busy CTAs: SM ingest, L2 and HBM (every byte is new) bounds; then the exchange
+            const double busy = (double)tiles * sp, cta_bytes = (128.0 + bm) * kBlockK;
+            const double step = std::max({(double)bm, cta_bytes / kSmIngest, busy * cta_bytes / kL2Rate, busy * cta_bytes / kHbmRate});
+            const double t = ceil_div(num_kb, sp) * step + kTileOverhead + kCSplitOverhead + 6.0 * bm / sp;
+            if (want > 0 || t < pick_t * 0.95) pick = sp, pick_bm = bm, pick_t = t;
+        }
+        if (pick) {
+            c.csplit = pick, c.cluster = pick, c.block_m = pick_bm;
+            c.kb_per_split = ceil_div(num_kb, pick), c.num_splits = pick;
+            c.grid = ceil_div(pb.n, (int)kBlockN) * pick, c.grid_y = ceil_div(pb.m, pick_bm);   // (n-tile x slice, m-block)
+        }
+    }
+    const int cta_group = c.csplit ? 1 : std::min(c.cluster, 2);
+    const int staging = c.csplit ? csplit_staging_bytes(c.block_m, c.csplit) : 0;
+    int stages = (kSmemCapacity - 64 - (staging ? 32 + staging : 0)) / stage_bytes(c.block_m, cta_group);
+    while (stages > 1 && smem_bytes_for(c.block_m, cta_group, stages, staging) > kSmemCapacity) --stages;
     stages = std::min(stages, 32);
     if (int v = env_int("DGB200_STAGES", 0)) stages = std::min(v, stages);
     c.stages = std::max(stages, 1);
-    c.smem_bytes = smem_bytes_for(c.block_m, cta_group, c.stages);
+    c.smem_bytes = smem_bytes_for(c.block_m, cta_group, c.stages, staging);
     c.swizzle_group = env_int("DGB200_SWIZZLE_GROUP", 8);
     return c;
 }
@@ -323,7 +359,7 @@ int launch_kernel(Kernel kernel, const Config& cfg, cudaStream_t stream, const C
         }
     }
     cudaLaunchConfig_t lc{};
-    lc.gridDim = dim3(cfg.num_sms / cfg.cluster * cfg.cluster, 1, 1);
+    lc.gridDim = cfg.grid > 0 ? dim3(cfg.grid, cfg.grid_y, 1) : dim3(cfg.num_sms / cfg.cluster * cfg.cluster, 1, 1);
     lc.blockDim = dim3(kNumThreads, 1, 1);
     lc.dynamicSmemBytes = cfg.smem_bytes;
     lc.stream = stream;
@@ -336,7 +372,7 @@ int launch_kernel(Kernel kernel, const Config& cfg, cudaStream_t stream, const C
         attrs[na].val.clusterDim.z = 1;
         ++na;
     }
-    if (cfg.cluster > 2) {
+    if (cfg.cluster > 2 && cfg.grid == 0) {
         // 4/8-CTA clusters must sit inside one GPC: ask how many fit at once and size the persistent grid to that
         static std::mutex occ_mu;
         static std::unordered_map<const void*, int> resident;   // kernel (x cluster size, implied) -> clusters
@@ -371,6 +407,8 @@ int launch_kernel(Kernel kernel, const Config& cfg, cudaStream_t stream, const C
 //   k-grouped(+psum): fp32, accumulate into D, both MN-major, clusters 1,2             (gemm.hpp:325-328)
 #define DGB_LAUNCH(TYPE, CL, OUT, ACC, XMN, WMN) \
     launch_kernel(fp8_gemm_kernel<TYPE, CL, OUT, ACC, XMN, WMN, false>, cfg, c.stream, mx, mw, msfx, msfw, p)
+#define DGB_LAUNCH_CSPLIT(CL, OUT, ACC) \
+    launch_kernel(fp8_gemm_kernel<kDense, CL, OUT, ACC, false, false, false, true>, cfg, c.stream, mx, mw, msfx, msfw, p)
 #define DGB_LAUNCH_SPLITK(CL, OUT, ACC, XMN, WMN) \
     launch_kernel(fp8_gemm_kernel<kDense, CL, OUT, ACC, XMN, WMN, true>, cfg, c.stream, mx, mw, msfx, msfw, p)
 
@@ -378,6 +416,13 @@ template <int kType, int kCluster, bool kXMn, bool kWMn>
 int dispatch_out(const GemmCall& c, const Config& cfg, const CUtensorMap& mx, const CUtensorMap& mw,
                  const CUtensorMap& msfx, const CUtensorMap& msfw, const GemmParams& p) {
     if constexpr (kType == kDense) {
+        if constexpr ((kCluster == 2 || kCluster == 4) && !kXMn && !kWMn) {
+            if (cfg.csplit) {
+                if (c.d_dtype == DGB200_BF16)
+                    return c.accumulate ? DGB_LAUNCH_CSPLIT(kCluster, __nv_bfloat16, true) : DGB_LAUNCH_CSPLIT(kCluster, __nv_bfloat16, false);
+                return c.accumulate ? DGB_LAUNCH_CSPLIT(kCluster, float, true) : DGB_LAUNCH_CSPLIT(kCluster, float, false);
+            }
+        }
         if constexpr (kCluster <= 2) {
             if (cfg.num_splits > 1) {
                 if (c.d_dtype == DGB200_BF16)
@@ -451,11 +496,12 @@ int run_gemm(const GemmCall& c) {
     if (cfg.num_splits > 1 && ceil_div(c.m, cfg.block_m) * ceil_div(c.n, (int)kBlockN) > kSplitKCounters)
         cfg.num_splits = 1, cfg.kb_per_split = ceil_div(c.k, (int)kBlockK);
     if (pb.any_mn && cfg.cluster > 2) cfg.cluster = 2;            // weight multicast is built for K-major tiles only
-    const int cta_group = cfg.cluster >= 2 ? 2 : 1, pairs = cfg.cluster >= 2 ? cfg.cluster / 2 : 1;
+    const int cta_group = (cfg.cluster >= 2 && !cfg.csplit) ? 2 : 1, pairs = (cfg.cluster >= 2 && !cfg.csplit) ? cfg.cluster / 2 : 1;
     const int load_m = cfg.block_m / cta_group;
     DGB_REQUIRE(cfg.block_m % 16 == 0 && cfg.block_m >= 16 && cfg.block_m <= (int)kMaxBlockM);
     DGB_REQUIRE(cfg.cluster == 1 || cfg.cluster == 2 || (c.type == kDense && (cfg.cluster == 4 || cfg.cluster == 8)));
-    DGB_REQUIRE(cfg.cluster <= 2 || cfg.num_splits == 1);
+    DGB_REQUIRE(cfg.cluster <= 2 || cfg.num_splits == 1 || cfg.csplit);
+    if (cfg.csplit) DGB_REQUIRE(cfg.block_m % (16 * cfg.csplit) == 0 && cfg.cluster == cfg.csplit);
     if (c.type == kMContiguous || c.type == kMContiguousPsum) DGB_REQUIRE(c.alignment % cfg.block_m == 0);
     if (c.x_mn) DGB_REQUIRE(load_m % 32 == 0);
 
@@ -505,8 +551,9 @@ int run_gemm(const GemmCall& c) {
     p.swizzle_group = std::max(1, cfg.swizzle_group);
     p.num_splits = cfg.num_splits;
     p.kb_per_split = cfg.kb_per_split;
-    p.splitk_counters = cfg.num_splits > 1 ? static_cast<int*>(c.workspace) : nullptr;
-    p.splitk_ws = cfg.num_splits > 1 ? reinterpret_cast<float*>(static_cast<char*>(c.workspace) + kSplitKHeaderBytes) : nullptr;
+    const bool ws_split = cfg.num_splits > 1 && !cfg.csplit;
+    p.splitk_counters = ws_split ? static_cast<int*>(c.workspace) : nullptr;
+    p.splitk_ws = ws_split ? reinterpret_cast<float*>(static_cast<char*>(c.workspace) + kSplitKHeaderBytes) : nullptr;
     p.debug_ts = g_debug_ts.load();
     p.num_n_units = ceil_div(c.n, (int)kBlockN * cta_group);
     p.num_m_blocks = ceil_div(c.m, cfg.block_m);
@@ -515,11 +562,11 @@ int run_gemm(const GemmCall& c) {
     p.x_swizzle = x_swizzle;
     p.sf_k_span = 4 * c.gran_k_a;
 
-    g_last_config = dgb200_config{cfg.block_m, cfg.cluster, cfg.stages, cfg.num_sms, cfg.smem_bytes, 0, cfg.num_splits};
+    g_last_config = dgb200_config{cfg.block_m, cfg.cluster, cfg.stages, cfg.num_sms, cfg.smem_bytes, 0, cfg.num_splits, cfg.csplit};
     if (env_int("DGB200_PRINT_CONFIGS", 0))
         fprintf(stderr, "dgb200 config: type=%d m=%d n=%d k=%d groups=%d majors=%d%d -> block_m=%d cluster=%d stages=%d sms=%d smem=%d splits=%d\n",
                 c.type, c.m, c.n, c.k, c.groups, (int)c.x_mn, (int)c.w_mn, cfg.block_m, cfg.cluster, cfg.stages, cfg.num_sms,
-                cfg.smem_bytes, cfg.num_splits);
+                cfg.smem_bytes, cfg.csplit ? -cfg.num_splits : cfg.num_splits);
 
     switch (c.type) {
         case kDense: return dispatch_majors<kDense>(c, cfg, mx, mw, msfx, msfw, p);
@@ -564,6 +611,12 @@ int dgb200_set_pdl(int enabled) {
     return DGB200_OK;
 }
 int dgb200_get_pdl(void) { return rt().pdl; }
+int dgb200_set_split_k(int allow) {
+    rt().split_k = allow ? 1 : 0;
+    return DGB200_OK;
+}
+int dgb200_get_split_k(void) { return rt().split_k; }
+
 int dgb200_set_mk_alignment_for_contiguous_layout(int alignment) {
     DGB_REQUIRE(alignment > 0 && alignment % 16 == 0);
     rt().mk_alignment = alignment;
@@ -747,10 +800,10 @@ int dgb200_plan(int gemm_type, int m, int n, int k, int num_groups, int expected
     Problem pb{gemm_type, m, expected_m > 0 ? expected_m : m, n, k, num_groups, std::max(alignment, 1)};
     if (gemm_type == kDense && n % 4 == 0) pb.max_splits = kMaxSplits;   // as if a workspace were supplied
     const Config cfg = choose_config(pb, num_sms);
-    const int n_units = ceil_div(n, (int)kBlockN * std::min(cfg.cluster, 2));
+    const int n_units = ceil_div(n, (int)kBlockN * (cfg.csplit ? 1 : std::min(cfg.cluster, 2)));
     const int m_blocks = gemm_type == kMMasked ? num_groups * ceil_div(pb.expected_m, cfg.block_m) : ceil_div(m, cfg.block_m);
     *out = dgb200_config{cfg.block_m, cfg.cluster, cfg.stages, cfg.num_sms, cfg.smem_bytes, m_blocks * n_units * cfg.num_splits,
-                         cfg.num_splits};
+                         cfg.num_splits, cfg.csplit};
     return DGB200_OK;
 }
 

@@ -101,10 +101,12 @@ struct Tile {
 
 // kCluster = CTAs per cluster: 1 (single CTA MMA), 2 (one cta_group::2 pair) or 4 / 8 (2 / 4 pairs that work on
 // consecutive m-blocks of the SAME weight panel and share its TMA loads by multicast; dense only).
-template <int kGemmType, int kCluster, bool kSplitK = false>
+// kCSplit: the cluster is kCluster single-CTA MMAs that cut K of ONE output tile between them (split-K inside the
+// cluster, reduced through distributed shared memory); `rank` is then 0 and `split_rank` the slice.
+template <int kGemmType, int kCluster, bool kSplitK = false, bool kCSplit = false>
 struct Scheduler {
-    static constexpr uint32_t kPairs = kCluster >= 2 ? kCluster / 2 : 1;
-    static constexpr uint32_t kCtaGroup = kCluster >= 2 ? 2 : 1;
+    static constexpr uint32_t kPairs = (kCluster >= 2 && !kCSplit) ? kCluster / 2 : 1;
+    static constexpr uint32_t kCtaGroup = (kCluster >= 2 && !kCSplit) ? 2 : 1;
     const GemmParams& p;
     uint32_t cta_rank, cluster_id, num_clusters;
     uint32_t num_n_units;
@@ -115,7 +117,8 @@ struct Scheduler {
     uint32_t k_start = 0, k_end = 0, sf_rows_before = 0;
     bool kg_loaded = false;
 
-    __device__ Scheduler(const GemmParams& p_, uint32_t rank) : p(p_), cta_rank(rank) {
+    uint32_t split_rank;
+    __device__ Scheduler(const GemmParams& p_, uint32_t rank, uint32_t split_rank_ = 0) : p(p_), cta_rank(rank), split_rank(split_rank_) {
         cluster_id = blockIdx.x / kCluster;
         num_clusters = gridDim.x / kCluster;
         num_n_units = p.num_n_units;
@@ -135,6 +138,22 @@ struct Scheduler {
     }
 
     __device__ bool next(Tile& t) {
+        if constexpr (kCSplit) {
+            // one tile per cluster, addressed by the 2-D grid: (blockIdx.x / kCluster, blockIdx.y) = (n-tile, m-block)
+            if (iter++ != 0) return false;
+            const uint32_t num_kb = (p.k + kBlockK - 1) / kBlockK;
+            t.split = split_rank, t.counter_idx = 0, t.k_base = 0, t.wk_base = 0;
+            t.kb_begin = split_rank * p.kb_per_split;
+            t.kb_end = min(num_kb, t.kb_begin + p.kb_per_split);
+            t.last_umma = t.kb_end != num_kb ? kBlockK / kUmmaK : ((p.k - (num_kb - 1) * kBlockK) + kUmmaK - 1) / kUmmaK;
+            t.x_row = blockIdx.y * p.block_m;
+            t.d_row = t.x_row, t.sfx_col = t.x_row, t.sfx_row = 0;
+            t.valid_m = min(p.block_m, p.m - t.x_row);
+            t.store_m = t.valid_m;
+            t.n0 = cluster_id * kBlockN;
+            t.w_row = t.n0, t.sfw_col = t.n0, t.sfw_row = 0;
+            return true;
+        }
         const uint32_t idx = cluster_id + (iter++) * num_clusters;
         uint32_t m_blk, n_unit, group = 0;
         const uint32_t num_kb_total = (p.k + kBlockK - 1) / kBlockK;
@@ -201,6 +220,7 @@ struct Scheduler {
             } else if (idx >= num_m * num_n_units) {
                 return false;
             }
+
             split(local, num_m, m_blk, n_unit);
             m_blk = m_blk * kPairs + (cta_rank >> 1);                        // this pair's m-block inside the group
             t.x_row = m_blk * p.block_m;
@@ -339,8 +359,12 @@ __device__ __forceinline__ void splitk_finalize(const float* ws, size_t slice_el
 // fp8_gemm_{nn,tn,tt}, m_grouped nn, and both operands of the K-grouped weight-gradient GEMM.
 // kSplitK: the dense split-K variant (K slices + finalising pass); kept out of the common instantiations because its
 // epilogue doubles the code size, which a cold instruction cache charges to every short launch.
+// kCSplit: split-K inside a cluster of kCluster single-CTA MMAs (dense, small M): every CTA accumulates one K slice of
+// the same output tile; the partial tiles are exchanged through distributed shared memory (reduce-scatter over the
+// token columns, `st.async` + transaction barrier) and added in slice order, so each weight byte crosses L2->SM once
+// instead of once per m-block and nothing goes through global memory. One tile per cluster (the host guarantees it).
 template <int kGemmType, int kCluster, typename out_t, bool kAccumulate, bool kXMn = false, bool kWMn = false,
-          bool kSplitK = false>
+          bool kSplitK = false, bool kCSplit = false>
 __global__ void __launch_bounds__(kNumThreads, 1)
 fp8_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
                 const __grid_constant__ CUtensorMap map_sfx, const __grid_constant__ CUtensorMap map_sfw,
@@ -353,9 +377,10 @@ fp8_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
     const uint32_t lane = lane_id();
     if (threadIdx.x == 0) DGB_STAMP(0);
     if (threadIdx.x == 0 && p.debug_ts != nullptr) p.debug_ts[16 + 2 * blockIdx.x] = globaltimer_ns();   // per-CTA entry
-    constexpr int kCtaGroup = kCluster >= 2 ? 2 : 1;          // CTAs per UMMA (cta_group)
-    constexpr uint32_t kPairs = kCluster >= 2 ? kCluster / 2 : 1;   // CTA pairs per cluster (share the weight loads)
-    const uint32_t cta_rank = kCluster == 1 ? 0u : cluster_ctarank();
+    constexpr int kCtaGroup = (kCluster >= 2 && !kCSplit) ? 2 : 1;          // CTAs per UMMA (cta_group)
+    constexpr uint32_t kPairs = (kCluster >= 2 && !kCSplit) ? kCluster / 2 : 1;   // CTA pairs per cluster (share the weight loads)
+    const uint32_t cta_rank = (kCluster == 1 || kCSplit) ? 0u : cluster_ctarank();   // position inside the MMA group(s)
+    const uint32_t split_rank = kCSplit ? cluster_ctarank() : 0u;                     // K slice (cluster split-K)
     const uint32_t pair_idx = cta_rank >> 1, leader_rank = cta_rank & ~1u;
     const bool is_leader = (cta_rank & 1) == 0;
 
@@ -375,6 +400,8 @@ fp8_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
     const uint32_t tmem_empty_bar = tmem_full_bar + 16;        // [2] accumulator drained by all epilogue threads (leader)
     const uint32_t tmem_ptr_smem = tmem_empty_bar + 16;
     const uint32_t splitk_flag_smem = tmem_ptr_smem + 4;
+    const uint32_t red_bar = tmem_ptr_smem + 8;                // cluster split-K: partial tiles of the peers have landed
+    const uint32_t red_stage = (tmem_ptr_smem + 16 + 15) & ~15u;   // cluster split-K: float4 [kCluster-1][chunk/4][128]
 
     // Setup, arranged so that nothing waits that does not have to.
     //  * Warp 0 (TMA producer) initialises the barriers only it and the MMA commits touch (full / empty), warp 1 the
@@ -411,6 +438,7 @@ fp8_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
             mbar_init(tmem_full_bar + lane * 8, 1);
             mbar_init(tmem_empty_bar + lane * 8, kNumEpilogueThreads * kCtaGroup);
         }
+        if (kCSplit && lane == 2) mbar_init(red_bar, 1);
         fence_mbar_init();
         __syncwarp();
     }
@@ -437,21 +465,24 @@ fp8_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
 
     if (warp_idx == 0) {
         // =================================================================== TMA producer (one lane, every CTA)
-        if (producer_lane) {
-            Scheduler<kGemmType, kCluster, kSplitK> sched(p, cta_rank);
+        // (`elect_one()` right at the branch: ptxas then knows the region is single-threaded and keeps every TMA operand in
+        // uniform registers; behind a plain bool it falls back to R2UR.BROADCAST waterfall loops, ~2x slower per k-block)
+        if (elect_one()) {
+            Scheduler<kGemmType, kCluster, kSplitK, kCSplit> sched(p, cta_rank, split_rank);
             Tile t;
             const uint32_t ab_bytes = kWTileBytes + x_tile_bytes;
             const uint32_t sfw_tx = kBlockN * 4, sfx_tx = p.block_m * 4;
             constexpr uint32_t kWRows = kBlockN / kPairs;
             uint16_t w_mask = 0;
             for (uint32_t q = 0; q < kPairs; ++q) w_mask |= static_cast<uint16_t>(1u << (2 * q + (cta_rank & 1)));
+            uint32_t fresh = num_stages;          // slots never used yet: nothing to wait for (a TRYWAIT costs ~90 cycles)
             while (sched.next(t)) {
                 if (kGemmType == kMContiguousPsum && t.valid_m == 0) continue;
                 const uint32_t x_row = t.x_row + (cta_rank & 1) * load_m;
                 uint32_t k0 = t.kb_begin * kBlockK;
                 for (uint32_t kb = t.kb_begin; kb < t.kb_end; ++kb, k0 += kBlockK, ring.advance()) {
                     const uint32_t full = full_bar + ring.bar, slot = smem_base + ring.slot;
-                    mbar_wait(empty_bar + ring.bar, ring.phase ^ 1);
+                    if (fresh) --fresh; else mbar_wait(empty_bar + ring.bar, ring.phase ^ 1);
                     const bool first = kb == t.kb_begin;
                     const bool load_sfw = (kb & sfw_mask) == 0 || first, load_sfx = (kb & sfx_mask) == 0 || first;
                     mbar_arrive_expect_tx(full, ab_bytes + (load_sfw ? sfw_tx : 0u) + (load_sfx ? sfx_tx : 0u));
@@ -482,7 +513,7 @@ fp8_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
     } else if (warp_idx == 1) {
         // =================================================================== MMA issuer (leader CTA only)
         if (is_leader) {
-            Scheduler<kGemmType, kCluster, kSplitK> sched(p, cta_rank);
+            Scheduler<kGemmType, kCluster, kSplitK, kCSplit> sched(p, cta_rank, split_rank);
             Tile t;
             const uint32_t idesc_base = make_idesc(128 * kCtaGroup, p.block_m, kWMn ? 1 : 0, kXMn ? 1 : 0);
             // descriptors of slot 0; a slot offset adds (bytes >> 4) to the 14-bit start-address field.
@@ -500,7 +531,7 @@ fp8_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
             const uint64_t sfw_desc0 = make_smem_desc(smem_base + off_sfw, 0, 128, kLayoutNoSwizzle);
             const uint64_t sfx_desc0 = make_smem_desc(smem_base + off_sfx, 0, 128, kLayoutNoSwizzle);
             const uint32_t tmem_sfw = tmem_base + kTmemColSFW, tmem_sfx = tmem_base + kTmemColSFX;
-            constexpr uint16_t kEmptyMask = static_cast<uint16_t>((1u << kCluster) - 1);   // every CTA's `empty` barrier
+            constexpr uint16_t kEmptyMask = static_cast<uint16_t>((1u << (kCSplit ? 1 : kCluster)) - 1);   // every CTA's `empty` barrier
             const uint16_t pair_mask = static_cast<uint16_t>(0b11u << leader_rank);           // this pair only
             // The issue loop below bounds every shape whose tiles are small (each k-block then costs its ~50
             // instructions, not its MMA time), so everything loop-invariant is hoisted: per-k-block work is one barrier
@@ -564,7 +595,7 @@ fp8_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
         }
     } else if (warp_idx == 2) {
         // =================================================================== SF re-tiler / slot forwarder
-        Scheduler<kGemmType, kCluster, kSplitK> sched(p, cta_rank);
+        Scheduler<kGemmType, kCluster, kSplitK, kCSplit> sched(p, cta_rank, split_rank);
         Tile t;
         // tcgen05.cp 32x128b wants word (row r of the 128-group) at [r % 32][r / 32]; TMA delivered it at [r]
         auto retile = [&](uint32_t base) {
@@ -575,7 +606,7 @@ fp8_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
             st_shared_v4(base + lane * 16, v0, v1, v2, v3);
         };
         // barrier of the pair's leader CTA, as a shared::cluster address
-        const uint32_t ready_dst = kCluster > 1 ? mapa(ready_bar, leader_rank) : ready_bar;
+        const uint32_t ready_dst = kCtaGroup > 1 ? mapa(ready_bar, leader_rank) : ready_bar;
         while (sched.next(t)) {
             if (kGemmType == kMContiguousPsum && t.valid_m == 0) continue;
             for (uint32_t kb = t.kb_begin; kb < t.kb_end; ++kb, ring.advance()) {
@@ -592,7 +623,7 @@ fp8_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
                     }
                     fence_proxy_async_smem();   // generic-proxy writes -> visible to tcgen05.cp
                 }
-                if constexpr (kCluster > 1)
+                if constexpr (kCtaGroup > 1)
                     mbar_arrive_remote(ready_dst + ring.bar);
                 else
                     mbar_arrive(ready_dst + ring.bar);
@@ -600,12 +631,12 @@ fp8_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
         }
     } else if (warp_idx >= 4) {
         // =================================================================== epilogue: TMEM -> registers -> global
-        Scheduler<kGemmType, kCluster, kSplitK> sched(p, cta_rank);
+        Scheduler<kGemmType, kCluster, kSplitK, kCSplit> sched(p, cta_rank, split_rank);
         Tile t;
         const uint32_t quad = warp_idx & 3;                 // TMEM lane quadrant this warp may read
         const uint32_t half = (warp_idx - 4) >> 2;          // 0: chunks 0,2,4.. | 1: chunks 1,3,5..
         out_t* d = reinterpret_cast<out_t*>(p.d);
-        const uint32_t tmem_empty_dst = kCluster > 1 ? mapa(tmem_empty_bar, leader_rank) : tmem_empty_bar;
+        const uint32_t tmem_empty_dst = kCtaGroup > 1 ? mapa(tmem_empty_bar, leader_rank) : tmem_empty_bar;
         const size_t row_bytes = static_cast<size_t>(p.ld_d) * sizeof(out_t);
         uint32_t tile_iter = 0;
         while (sched.next(t)) {
@@ -624,6 +655,103 @@ fp8_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
             if (threadIdx.x == 128) DGB_STAMP(6);
             const uint32_t taddr = tmem_base + ((quad * 32) << 16) + as * kAccumColStride;
             const uint32_t load_cols = (max(t.valid_m, 1u) + 15) / 16 * 16;
+            if constexpr (kCSplit) {
+                // ---------------------------------------------------------------- cluster split-K epilogue
+                // The tile's token columns are cut into kCluster chunks of `c` columns; CTA r owns chunk r. Work unit =
+                // one 16-column piece (one TMEM load); the two warps of a lane quadrant take alternate pieces.
+                //   foreign piece: TMEM -> registers -> local outbox -> bulk copy into the owner's staging buffer
+                //   own piece    : (after the peers' bytes have landed) partials added in slice order -> D
+                // Staging of owner q: float4 [source slot][c/4 column quads][128 weight rows]; a warp writes / reads 512
+                // contiguous bytes per quad.
+                constexpr uint32_t S = kCluster;
+                const uint32_t c = p.block_m / S, pieces_per_chunk = c / 16, quads = c / 4;
+                const uint32_t chunk_bytes = c * 128 * 4;                      // one source's partial of one chunk
+                if (threadIdx.x == 4 * 32) mbar_arrive_expect_tx(red_bar, (S - 1) * chunk_bytes);
+                const uint32_t row_n = quad * 32 + lane;                       // weight row of this thread inside the tile
+                const uint32_t num_pieces = p.block_m / 16;
+                // Foreign pieces go to a local outbox first (the stage ring is idle by now: this CTA's only tile has been
+                // consumed), laid out exactly like the owner's staging slot, and travel as ONE bulk copy per owner:
+                // SM-issued remote stores top out near 20 B/clk, the copy engine does not occupy the epilogue warps.
+                for (uint32_t i = half; i < num_pieces; i += 2) {
+                    const uint32_t q = i / pieces_per_chunk;
+                    if (q == split_rank) continue;
+                    uint32_t v[16];
+                    tmem_ld_32x32b_x16(taddr + i * 16, v);
+                    tmem_ld_wait();
+                    const uint32_t pi = i - q * pieces_per_chunk;
+                    const uint32_t dst = smem_base + q * chunk_bytes + ((pi * 4) * 128 + row_n) * 16;
+#pragma unroll
+                    for (uint32_t g = 0; g < 4; ++g)
+                        st_shared_f4(dst + g * 128 * 16, v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
+                }
+                fence_proxy_async_smem();                                     // generic writes -> visible to the copy engine
+                if (threadIdx.x == 4 * 32) DGB_STAMP(10);
+                named_bar_sync(1, kNumEpilogueThreads);
+                if (threadIdx.x == 4 * 32) DGB_STAMP(11);
+                if (threadIdx.x == 4 * 32) {
+#pragma unroll
+                    for (uint32_t q = 0; q < S; ++q) {
+                        if (q == split_rank) continue;
+                        const uint32_t slot = split_rank < q ? split_rank : split_rank - 1;
+                        bulk_copy_to_peer(mapa(red_stage + slot * chunk_bytes, q), smem_base + q * chunk_bytes, chunk_bytes,
+                                          mapa(red_bar, q));
+                    }
+                }
+                // My own chunk in units of 8 token columns (the two warps of a quadrant alternate): load the own partial
+                // now, add the peers' partials in slice order once they have landed, write D.
+                constexpr uint32_t kMaxUnits = 4;                             // c <= 64 -> <= 8 units, 4 per warp
+                uint32_t own[kMaxUnits][8];
+                const uint32_t units = c / 8;
+#pragma unroll
+                for (uint32_t ui = 0; ui < kMaxUnits; ++ui) {
+                    const uint32_t u = half + 2 * ui;
+                    if (u < units) tmem_ld_32x32b_x8(taddr + split_rank * c + u * 8, own[ui]);
+                }
+                tmem_ld_wait();
+                tcgen05_fence_before();
+                mbar_arrive(tmem_empty_dst + as * 8);                        // last TMEM read of this tile
+                if (threadIdx.x == 4 * 32) DGB_STAMP(12);
+                mbar_wait(red_bar, 0);
+                if (threadIdx.x == 4 * 32) DGB_STAMP(13);
+#pragma unroll
+                for (uint32_t ui = 0; ui < kMaxUnits; ++ui) {
+                    const uint32_t u = half + 2 * ui;
+                    if (u >= units) break;
+                    float acc[8];
+#pragma unroll
+                    for (uint32_t s = 0; s < S; ++s) {                          // slice order: deterministic
+                        if (s == split_rank) {
+#pragma unroll
+                            for (uint32_t j = 0; j < 8; ++j)
+                                acc[j] = s == 0 ? __uint_as_float(own[ui][j]) : acc[j] + __uint_as_float(own[ui][j]);
+                        } else {
+                            const uint32_t slot = s < split_rank ? s : s - 1;
+                            const uint32_t src = red_stage + slot * chunk_bytes + ((u * 2) * 128 + row_n) * 16;
+                            const float4 x0 = ld_shared_f4(src), x1 = ld_shared_f4(src + 128 * 16);
+                            if (s == 0) {
+                                acc[0] = x0.x, acc[1] = x0.y, acc[2] = x0.z, acc[3] = x0.w;
+                                acc[4] = x1.x, acc[5] = x1.y, acc[6] = x1.z, acc[7] = x1.w;
+                            } else {
+                                acc[0] += x0.x, acc[1] += x0.y, acc[2] += x0.z, acc[3] += x0.w;
+                                acc[4] += x1.x, acc[5] += x1.y, acc[6] += x1.z, acc[7] += x1.w;
+                            }
+                        }
+                    }
+                    const uint32_t r0 = split_rank * c + u * 8;               // first token row of this unit in the tile
+                    if (n_ok && r0 < t.valid_m) {
+                        char* row = d_col + static_cast<size_t>(r0) * row_bytes;
+                        if (r0 + 8 <= t.valid_m) {
+#pragma unroll
+                            for (uint32_t j = 0; j < 8; ++j, row += row_bytes) store_out<out_t>(reinterpret_cast<out_t*>(row), acc[j], kAccumulate);
+                        } else {
+#pragma unroll
+                            for (uint32_t j = 0; j < 8; ++j, row += row_bytes)
+                                if (r0 + j < t.valid_m) store_out<out_t>(reinterpret_cast<out_t*>(row), acc[j], kAccumulate);
+                        }
+                    }
+                }
+                continue;
+            }
             if constexpr (kSplitK) {
                 // ---------------------------------------------------------------- split-K epilogue
                 // (1) park this slice's FP32 partial tile in the workspace, (2) count arrivals per output block,
@@ -631,7 +759,7 @@ fp8_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
                 float* ws_col = p.splitk_ws + (static_cast<size_t>(t.split) * p.m + t.d_row) * p.n + n;
                 auto release = [&]() {
                     tcgen05_fence_before();
-                    if constexpr (kCluster > 1)
+                    if constexpr (kCtaGroup > 1)
                         mbar_arrive_remote(tmem_empty_dst + as * 8);
                     else
                         mbar_arrive(tmem_empty_dst + as * 8);
@@ -698,7 +826,7 @@ fp8_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
             auto release_accumulator = [&]() {
                 // last read of this accumulator buffer by this warp: hand it back before the stores drain
                 tcgen05_fence_before();
-                if constexpr (kCluster > 1)
+                if constexpr (kCtaGroup > 1)
                     mbar_arrive_remote(tmem_empty_dst + as * 8);
                 else
                     mbar_arrive(tmem_empty_dst + as * 8);

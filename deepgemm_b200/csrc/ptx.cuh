@@ -241,6 +241,12 @@ DGB_DEVICE void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&v)[16]) {
         : "r"(taddr)
         : "memory");
 }
+DGB_DEVICE void tmem_ld_32x32b_x8(uint32_t taddr, uint32_t (&v)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                 : "r"(taddr)
+                 : "memory");
+}
 DGB_DEVICE void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // ---------------------------------------------------------------- descriptors
@@ -279,6 +285,29 @@ DGB_DEVICE uint32_t ld_shared_u32(uint32_t addr) {
     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
     return v;
 }
+// 16-byte store into a peer CTA's shared memory that completes 16 transaction bytes on the peer's mbarrier
+// (`dst` and `bar` are shared::cluster addresses from mapa)
+DGB_DEVICE void st_async_v4(uint32_t dst, uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint32_t bar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(dst),
+                 "r"(a), "r"(b), "r"(c), "r"(d), "r"(bar)
+                 : "memory");
+}
+// bulk copy of `bytes` (multiple of 16) from this CTA's shared memory into a peer's, completing transaction bytes on
+// the peer's mbarrier (`dst`, `bar`: shared::cluster addresses from mapa; `src`: shared::cta)
+DGB_DEVICE void bulk_copy_to_peer(uint32_t dst, uint32_t src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "r"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+DGB_DEVICE void st_shared_f4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+DGB_DEVICE float4 ld_shared_f4(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+
 DGB_DEVICE void named_bar_sync(uint32_t id, uint32_t nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }

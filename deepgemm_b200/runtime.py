@@ -35,6 +35,16 @@ def get_pdl() -> bool:
     return bool(lib().dgb200_get_pdl())
 
 
+def set_split_k(enabled: bool) -> None:
+    """No reference equivalent: allow (default) or forbid cutting K of small dense problems into slices. Off, every
+    output is bit-identical to the reference's SM100 kernel; on, small-M shapes agree to FP32 rounding and run faster."""
+    check(lib().dgb200_set_split_k(int(bool(enabled))))
+
+
+def get_split_k() -> bool:
+    return bool(lib().dgb200_get_split_k())
+
+
 def set_ignore_compile_dims(value: bool) -> None:
     """JIT hint in the reference (heuristics/runtime.hpp:18-24); shapes are always run-time values here."""
 

@@ -49,6 +49,13 @@ int dgb200_set_tc_util(int percent);      /* accepted for API parity; only the r
 int dgb200_get_tc_util(void);
 int dgb200_set_pdl(int enabled);          /* programmatic dependent launch attribute on every kernel launch */
 int dgb200_get_pdl(void);
+/* Split-K (no reference equivalent). Small dense problems may cut K into slices -- across the CTAs of a cluster
+ * (partials exchanged through distributed shared memory) or, with a workspace, across the grid -- so that all SMs
+ * stream weights. The slices are added in a fixed order (run-to-run deterministic), but not in the reference's one
+ * pass over K: results then agree with the reference to FP32 rounding instead of bit for bit. allow = 0 turns every
+ * form of split-K off (default 1). */
+int dgb200_set_split_k(int allow);
+int dgb200_get_split_k(void);
 int dgb200_set_mk_alignment_for_contiguous_layout(int alignment);
 int dgb200_get_mk_alignment_for_contiguous_layout(void);
 int dgb200_get_theoretical_mk_alignment_for_contiguous_layout(int expected_m /* <=0: none */);
@@ -166,6 +173,7 @@ typedef struct dgb200_config {
     int smem_bytes;  /* dynamic shared memory per CTA */
     int num_tiles;   /* upper bound on (cluster) tiles */
     int num_splits;  /* split-K slices (1 = none) */
+    int cluster_split; /* != 0: the slices are the CTAs of one cluster, reduced through distributed shared memory */
 } dgb200_config;
 /* Pure function (no CUDA): the configuration the heuristics pick for a problem on `num_sms` SMs.
  * gemm_type: 0 dense, 1 m-grouped contiguous, 2 m-grouped masked, 3 m-grouped contiguous psum.

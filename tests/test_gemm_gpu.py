@@ -139,6 +139,49 @@ def test_dense_split_k_matches_oracle_and_is_deterministic(dg, m, n, k, splits, 
     _assert_close_to_oracle(outs[0], d1, 'split vs unsplit')
 
 
+@pytest.mark.parametrize('m,n,k,cs', [(64, 4096, 7168, 4), (128, 4096, 7168, 4), (1, 2112, 7168, 4), (100, 520, 1536, 4),
+                                      (64, 1024, 512, 2), (200, 384, 2048, 2), (33, 136, 1408, 2)])
+@pytest.mark.parametrize('out_dtype', [torch.bfloat16, torch.float32])
+def test_dense_cluster_split_k_matches_oracle_and_is_deterministic(dg, m, n, k, cs, out_dtype, monkeypatch):
+    """Split-K inside a cluster: `cs` single-CTA MMAs each accumulate one K slice of the same output tile and exchange
+    the partial tiles through distributed shared memory (csrc/fp8_gemm_kernel.cuh, kCSplit). Slices are added in a
+    fixed order: deterministic, equal to the oracle to FP32 rounding; set_split_k(False) restores the one-pass bits."""
+    from deepgemm_b200 import _lib
+    from oracle import blockwise
+    _, _, qa, qb = _quant_dense(m, n, k, seed=m + n)
+    monkeypatch.setenv('DGB200_CSPLIT', str(cs))
+    outs = []
+    for _ in range(3):
+        d = torch.full((m, n), float('nan'), device='cuda', dtype=out_dtype)
+        dg.fp8_gemm_nt(qa, qb, d)
+        outs.append(d)
+    cfg = _lib.last_config()
+    assert cfg['cluster_split'] == cs and cfg['cluster'] == cs and cfg['num_splits'] == cs, cfg
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
+    want = blockwise.fp8_gemm_nt(_cpu(qa), _cpu(qb), out_dtype=out_dtype)
+    _assert_close_to_oracle(outs[0], want, f'cluster split-k {m}x{n}x{k}')
+    # accumulate into C
+    c = (torch.randn((m, n), device='cuda', generator=torch.Generator(device='cuda').manual_seed(m + k)) * 8).to(out_dtype)
+    d = c.clone()
+    dg.fp8_gemm_nt(qa, qb, d, c=d)
+    _assert_close_to_oracle(d, blockwise.fp8_gemm_nt(_cpu(qa), _cpu(qb), out_dtype=out_dtype, c=c.cpu()), 'cluster split-k + C',
+                            mag=1.5 * (outs[0].float().abs() + c.float().abs()))
+    # the knob: no split -> same bits as the single-pass kernel
+    monkeypatch.delenv('DGB200_CSPLIT')
+    dg.set_split_k(False)
+    try:
+        d1 = torch.empty((m, n), device='cuda', dtype=out_dtype)
+        dg.fp8_gemm_nt(qa, qb, d1)
+        assert _lib.last_config()['num_splits'] == 1 and _lib.last_config()['cluster_split'] == 0
+    finally:
+        dg.set_split_k(True)
+    monkeypatch.setenv('DGB200_SPLITS', '1')
+    d2 = torch.empty((m, n), device='cuda', dtype=out_dtype)
+    dg.fp8_gemm_nt(qa, qb, d2)
+    assert torch.equal(d1, d2)
+    _assert_close_to_oracle(outs[0], d1, 'split vs unsplit')
+
+
 @pytest.mark.parametrize('out_dtype', [torch.bfloat16, torch.float32])
 def test_dense_accumulate_into_c(dg, out_dtype):
     from oracle import blockwise

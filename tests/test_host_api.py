@@ -70,9 +70,15 @@ def test_heuristics_baseline_shapes(lib):
     for m in (1, 64, 128, 512, 4096):
         cfg = lib.plan(0, m, 4096, 7168)
         assert cfg['block_m'] % 16 == 0 and 16 <= cfg['block_m'] <= 240
-        assert cfg['cluster'] == 2 and cfg['num_sms'] == 148
+        cs = cfg['cluster_split']
+        assert cfg['cluster'] == (cs or 2) and cfg['num_sms'] == 148 and cs in (0, 2, 4)
         assert cfg['smem_bytes'] <= 232448 and cfg['num_stages'] >= 4
-        assert cfg['block_m'] - 16 < max(m, 16)
+        if cs:      # cluster split-K: few output tiles, K cut over the CTAs of a cluster, token chunks of 16 columns per CTA
+            assert m <= 256 and cfg['num_splits'] == cs and cfg['block_m'] % (16 * cs) == 0 and cfg['num_tiles'] <= 148
+        else:
+            assert cfg['block_m'] - 16 < max(m, 16)
+    assert lib.plan(0, 64, 4096, 7168)['cluster_split'] == 4       # the decode-sized headline shapes stream K from all SMs
+    assert lib.plan(0, 512, 4096, 7168)['cluster_split'] == 0 and lib.plan(0, 4096, 4096, 7168)['cluster_split'] == 0
     big = lib.plan(0, 4096, 4096, 7168)
     assert big['block_m'] >= 192                      # compute-bound shape wants tall tiles
     cont = lib.plan(1, 32768, 4096, 7168, 256, 128, 128)
@@ -139,3 +145,21 @@ def test_product_path_never_imports_the_oracle():
             if f.endswith(('.py', '.cu', '.cuh', '.h')):
                 text = open(os.path.join(root, f)).read()
                 assert 'import oracle' not in text and 'from oracle' not in text, f
+
+
+def test_gemm_kernels_keep_tma_operands_in_uniform_registers():
+    """Build sanity (no GPU): the TMA producer / MMA issuer run as one elected thread; if ptxas loses that fact it wraps
+    every UTMALDG in an R2UR.BROADCAST 'waterfall' loop, which measured ~2x slower per k-block on B200. None allowed."""
+    import shutil
+    import subprocess
+    from deepgemm_b200 import _lib
+    cuobjdump = shutil.which('cuobjdump') or '/usr/local/cuda/bin/cuobjdump'
+    if not os.path.exists(cuobjdump):
+        pytest.skip('cuobjdump not available')
+    sass = subprocess.run([cuobjdump, '-sass', _lib.build()], capture_output=True, text=True, check=True).stdout
+    kernels = sass.split('Function : ')[1:]
+    gemm = [k for k in kernels if 'fp8_gemm_kernel' in k.split('\n', 1)[0]]
+    assert len(gemm) >= 40
+    bad = [k.split('\n', 1)[0] for k in gemm if 'R2UR.BROADCAST' in k]
+    assert not bad, bad[:3]
+    assert all('UTMALDG' in k and ('UTCQMMA' in k or 'UTCOMMA' in k or 'UTCHMMA' in k or 'UTCMMA' in k or 'UTC' in k) for k in gemm)

@@ -1,3 +1,1 @@
-python tools/stamps.py 2>&1 | cut -c1-900
-echo COLD
-python tools/stamps.py --cold 2>&1 | cut -c1-900
+for cs in 4; do echo "CSPLIT=$cs"; DGB200_CSPLIT=$cs python tools/stamps.py 2>&1 | cut -c1-1200; done
