@@ -462,6 +462,15 @@ fp8_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
 
     const uint32_t sfw_mask = (1u << p.sf_shift_w) - 1, sfx_mask = (1u << p.sf_shift_x) - 1;
     Ring ring(slot_stride, num_stages);
+    // UMMA N of a tile = its valid token rows rounded up to 16, not the tile height: a ragged last m-block (dense M not
+    // a multiple of block_m, the tail of an expert's segment, a short masked group) costs tensor time in proportion to
+    // its rows. With a CTA pair each CTA supplies N/2 token rows, so CTA 1 loads from row N/2 of the tile (not
+    // block_m/2) and accumulator column j stays token row j. (Shapes are run-time values here; a kernel specialised
+    // at compile time on block_m pays for the padding.) MN-major tokens keep the full height (swizzle-atom alignment).
+    auto tile_n = [&](const Tile& t) -> uint32_t {
+        if (kXMn || kCSplit) return p.block_m;
+        return max(16u, min(p.block_m, (t.valid_m + 15u) & ~15u));
+    };
 
     if (warp_idx == 0) {
         // =================================================================== TMA producer (one lane, every CTA)
@@ -478,7 +487,7 @@ fp8_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
             uint32_t fresh = num_stages;          // slots never used yet: nothing to wait for (a TRYWAIT costs ~90 cycles)
             while (sched.next(t)) {
                 if (kGemmType == kMContiguousPsum && t.valid_m == 0) continue;
-                const uint32_t x_row = t.x_row + (cta_rank & 1) * load_m;
+                const uint32_t x_row = t.x_row + (cta_rank & 1) * (tile_n(t) / kCtaGroup);
                 uint32_t k0 = t.kb_begin * kBlockK;
                 for (uint32_t kb = t.kb_begin; kb < t.kb_end; ++kb, k0 += kBlockK, ring.advance()) {
                     const uint32_t full = full_bar + ring.bar, slot = smem_base + ring.slot;
@@ -515,7 +524,7 @@ fp8_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
         if (is_leader) {
             Scheduler<kGemmType, kCluster, kSplitK, kCSplit> sched(p, cta_rank, split_rank);
             Tile t;
-            const uint32_t idesc_base = make_idesc(128 * kCtaGroup, p.block_m, kWMn ? 1 : 0, kXMn ? 1 : 0);
+            uint32_t idesc_base = 0;     // per tile: UMMA M = 128 x CTAs, N = tile_n(t)
             // descriptors of slot 0; a slot offset adds (bytes >> 4) to the 14-bit start-address field.
             //   K-major : 8-row x 128 B swizzle atoms stacked along MN (SBO 1024); +32 B per UMMA_K step
             //   MN-major: atoms of S bytes (MN) x 8 K-rows; SBO = 8*S between K groups, LBO = 128*S between MN atoms;
@@ -563,6 +572,7 @@ fp8_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
                 ++tile_iter;
                 mbar_wait(tmem_empty_bar + as * 8, aphase ^ 1);
                 tcgen05_fence_after();
+                idesc_base = make_idesc(128 * kCtaGroup, tile_n(t), kWMn ? 1 : 0, kXMn ? 1 : 0);
                 const uint32_t tmem_d = tmem_base + as * kAccumColStride;
                 uint32_t kb = t.kb_begin;
                 for (; kb + 1 < t.kb_end; ++kb, ring.advance()) {        // every k-block but the last: 4 UMMAs

@@ -14,10 +14,11 @@ from deepgemm_b200 import _lib  # noqa: E402
 NAMES = ['entry', 'setup_done', 'first_tma', 'first_data', 'x4', 'last_mma', 'acc_ready', 'stores_issued',
          'teardown_begin', 'exit', 'cs_outbox', 'cs_bar', 'cs_sent', 'cs_recv']
 COLD = '--cold' in sys.argv
+SHAPES = [(4096, 4096, 7168), (4096, 7168, 2048)] if '--big' in sys.argv else [(64, 4096, 7168), (128, 4096, 7168)]
 flush = torch.empty(256 << 20, dtype=torch.int32, device='cuda') if COLD else None
 ts = torch.zeros(16 + 2 * 160, dtype=torch.int64, device='cuda')
 _lib.lib().dgb200_debug_set_timestamps(ts.data_ptr())
-for (m, n, k) in [(64, 4096, 7168), (128, 4096, 7168)]:
+for (m, n, k) in SHAPES:
     for splits in ('1',):
         a, b, qa, qb = make_inputs(m, n, k)
         sfa = dg.transform_sf_into_required_layout(qa[1], m, k, (1, 128, 128), None, True)

@@ -1,0 +1,60 @@
+"""Config sweeps on the big dense shapes (kernel-only, cold L2 via bench_kineto). usage: tune.py [big|small]"""
+import json
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch  # noqa: E402
+
+from tools.bringup import import_reference, make_inputs  # noqa: E402
+import deepgemm_b200 as dg  # noqa: E402
+from deepgemm_b200 import _lib  # noqa: E402
+from deepgemm_b200.testing import bench_kineto  # noqa: E402
+
+KEYS = ('DGB200_BLOCK_M', 'DGB200_CLUSTER', 'DGB200_STAGES', 'DGB200_SWIZZLE_GROUP', 'DGB200_CSPLIT', 'DGB200_SPLITS')
+
+
+def setenv(**kw):
+    for k in KEYS:
+        os.environ.pop(k, None)
+    for k, v in kw.items():
+        if v is not None:
+            os.environ['DGB200_' + k.upper()] = str(v)
+
+
+def run(shapes, configs, with_ref=True):
+    ref = import_reference() if with_ref else None
+    for (m, n, k) in shapes:
+        a, b, qa, qb = make_inputs(m, n, k)
+        sfa = dg.transform_sf_into_required_layout(qa[1], m, k, (1, 128, 128), None, True)
+        sfb = dg.transform_sf_into_required_layout(qb[1], n, k, (1, 128, 128), None, False)
+        d = torch.empty((m, n), device='cuda', dtype=torch.bfloat16)
+        rows = []
+        if ref is not None:
+            t = bench_kineto(lambda: ref.fp8_gemm_nt((qa[0], sfa), (qb[0], sfb), d), 'gemm_', num_tests=10)
+            rows.append(('ref', round(t * 1e6, 2)))
+        for cfg in configs:
+            setenv(**cfg)
+            try:
+                dg.fp8_gemm_nt((qa[0], sfa), (qb[0], sfb), d)
+                used = _lib.last_config()
+                t = bench_kineto(lambda: dg.fp8_gemm_nt((qa[0], sfa), (qb[0], sfb), d), 'fp8_gemm_kernel', num_tests=10)
+                rows.append((json.dumps(cfg), round(t * 1e6, 2), used['block_m'], used['num_stages'], used['cluster'], used['num_splits']))
+            except Exception as e:  # noqa: BLE001
+                rows.append((json.dumps(cfg), 'error ' + str(e)[:80]))
+        setenv()
+        print(f'== {m}x{n}x{k}', flush=True)
+        for r in rows:
+            print('  ', *r, flush=True)
+
+
+if __name__ == '__main__':
+    mode = sys.argv[1] if len(sys.argv) > 1 else 'big'
+    if mode == 'big':
+        cfgs = [{}] + [dict(block_m=bm, swizzle_group=sg) for bm in (128, 160, 192, 208, 224, 240) for sg in (4, 8, 16)]
+        cfgs += [dict(block_m=bm, stages=st) for bm in (224, 240) for st in (4, 5)]
+        run([(4096, 7168, 2048), (4096, 4096, 7168)], cfgs)
+    elif mode == 'small':
+        cfgs = [{}, dict(csplit=0), dict(csplit=4), dict(csplit=2)] + [dict(csplit=0, block_m=bm) for bm in (16, 32, 64)]
+        run([(1, 2112, 7168), (16, 4096, 7168), (32, 4096, 7168), (64, 4096, 7168), (96, 4096, 7168), (128, 4096, 7168), (192, 4096, 7168),
+             (256, 4096, 7168), (64, 7168, 2048), (128, 7168, 2048), (64, 2112, 7168), (128, 24576, 1536), (64, 32768, 512), (128, 7168, 16384)], cfgs)
