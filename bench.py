@@ -41,6 +41,17 @@ def load_peaks():
     return dict(FALLBACK_PEAKS), 'fallback'
 
 
+def committed_traffic(key):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the committed `ncu --set full` capture
+    (profiles/traffic.json, written by tools/ncu_summary.py); None if that kernel has no capture."""
+    path = os.path.join(REPO, 'profiles', 'traffic.json')
+    if not os.path.exists(path):
+        return None
+    with open(path) as f:
+        t = json.load(f).get(key)
+    return None if t is None else int(t['dram_read_bytes'] + t['dram_write_bytes'])
+
+
 # ------------------------------------------------------------------------------------------------ clocks
 class ClockSampler:
     """Samples `nvidia-smi` SM clocks / throttle reasons while the timed region runs."""
@@ -114,6 +125,9 @@ def run_dense(args, rank, world, device):
             dg.fp8_gemm_nt((p['qa'][0], p['sfa']), (p['qb'][0], p['sfb']), p['d'])
             if record is not None:
                 record[i][1].record()
+            elif 'tile' not in p:
+                cfg = _lib.last_config()
+                p['tile'] = {k_: cfg[k_] for k_ in ('block_m', 'cluster', 'num_stages', 'num_splits', 'cluster_split')}
 
     # ---- kernel-only (inputs resident) ------------------------------------------------------------
     # The clock sampler (a thread that forks nvidia-smi) starts before the warm-up so that its start-up noise and the
@@ -151,7 +165,7 @@ def run_dense(args, rank, world, device):
         bound = 'tensor' if fl / byts > fp8_peak * 1e12 / (peaks['hbm_gbs'] * 1e9) else 'hbm'
         frac = tf / fp8_peak if bound == 'tensor' else gbs / peaks['hbm_gbs']
         per_shape.append({'m': m, 'n': n, 'k': k, 'us': round(ms * 1e3, 2), 'tflops': round(tf, 1), 'gbs': round(gbs, 1),
-                          'bound': bound, 'frac_of_' + peak_kind: round(frac, 4)})
+                          'bound': bound, 'frac_of_' + peak_kind: round(frac, 4), 'tile': p['tile']})
 
     # dominant kernel of the step = the M=4096 launch (tensor bound)
     dom = per_shape[-1]
@@ -159,7 +173,8 @@ def run_dense(args, rank, world, device):
                 'achieved': dom['tflops'], 'peak': round(fp8_peak, 1), 'unit': 'TFLOP/s',
                 'frac': round(dom['tflops'] / fp8_peak, 4),
                 'peak_source': f'2 x {peak_kind} bf16_tflops (MEASURED_PEAKS.json); nominal dense FP8 = {NOMINAL_FP8_TFLOPS}',
-                'frac_of_nominal': round(dom['tflops'] / NOMINAL_FP8_TFLOPS, 4), 'traffic': None,
+                'frac_of_nominal': round(dom['tflops'] / NOMINAL_FP8_TFLOPS, 4), 'traffic': committed_traffic('dense_m4096'),
+                'algorithmic_bytes': int(4096 * 7168 + 4096 * 7168 + 4096 * 4096 * 2 + 2 * 4096 * 14 * 4),
                 'share_of_step': round(per_shape_ms[-1] / sum(per_shape_ms), 4)}
 
     # ---- end to end: pinned host buffers -> H2D -> SF pack -> GEMM -> D2H ---------------------------

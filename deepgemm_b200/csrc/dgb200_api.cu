@@ -289,18 +289,20 @@ Config choose_config(const Problem& pb, int num_sms_override = 0) {
     if (pb.type == kDense && !pb.any_mn && c.cluster == 2 && pb.m > 0 && rt().split_k && !(pinned && !getenv("DGB200_CSPLIT"))) {
         const int want = env_int("DGB200_CSPLIT", -1);            // -1: heuristic, 0: off, 2/4: forced
         int pick = 0, pick_bm = 0;
-        double pick_t = best;
         for (int sp : {4, 2}) {
             if (want == 0 || (want > 0 && want != sp)) continue;
             const int bm = std::min(align_up(std::min(pb.m, 128), 16 * sp), align_up(128, 16 * sp));
             const int tiles = ceil_div(pb.m, bm) * ceil_div(pb.n, (int)kBlockN);
             if (bm > (int)kMaxBlockM || ceil_div(num_kb, sp) * (sp - 1) >= num_kb || num_kb / sp < 2) continue;
-            if (want < 0 && tiles * sp > c.num_sms) continue;    // one resident cluster per tile
-            // per k-block step of all busy CTAs: SM ingest, L2 and HBM (every byte is new) bounds; then the exchange
-            const double busy = (double)tiles * sp, cta_bytes = (128.0 + bm) * kBlockK;
-            const double step = std::max({(double)bm, cta_bytes / kSmIngest, busy * cta_bytes / kL2Rate, busy * cta_bytes / kHbmRate});
-            const double t = ceil_div(num_kb, sp) * step + kTileOverhead + kCSplitOverhead + 6.0 * bm / sp;
-            if (want > 0 || t < pick_t * 0.95) pick = sp, pick_bm = bm, pick_t = t;
+            if (want > 0) {
+                pick = sp, pick_bm = bm;
+                break;
+            }
+            // Measured on B200 (tools/tune.py small): four slices win whenever the whole tile set fits the chip once
+            // (tiles x 4 <= SMs) and K is long enough to amortise the exchange (~1.5 us): M <= 128 at N = 4096 / 2112,
+            // K = 7168 runs 8-17% faster than one CTA pair per tile; two slices never paid.
+            if (sp == 4 && pb.m <= 128 && tiles * sp <= c.num_sms && num_kb >= 16) pick = sp, pick_bm = bm;
+            if (pick) break;
         }
         if (pick) {
             c.csplit = pick, c.cluster = pick, c.block_m = pick_bm;

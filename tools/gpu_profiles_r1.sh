@@ -3,7 +3,7 @@
 O=gpurun_out/r1
 mkdir -p $O
 nvidia-smi --query-gpu=name,clocks.max.sm,clocks.sm,power.limit --format=csv > $O/smi.txt
-timeout 1500 python -m pytest tests -x -q -m gpu > $O/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -3 $O/pytest_gpu.log | cut -c1-300
+timeout 1500 python -m pytest tests -q -m gpu > $O/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -3 $O/pytest_gpu.log | cut -c1-300
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $O/smoke.log 2>&1; echo "smoke rc=$?"; tail -2 $O/smoke.log
 timeout 900 python bench.py > $O/bench.log 2>&1; echo "bench rc=$?"; tail -1 $O/bench.log | cut -c1-1500
 timeout 900 python bench.py --impl reference --steps 2 --warmup 1 > $O/bench_ref_arm.log 2>&1; echo "bench ref rc=$?"; tail -1 $O/bench_ref_arm.log | cut -c1-600
@@ -16,6 +16,7 @@ timeout 600 $NCU -k regex:sm100_fp8 -s 1 -c 1 -f -o $O/ref_4096 python tools/pro
 timeout 600 $NCU -k regex:fp8_gemm_kernel -s 1 -c 1 -f -o $O/ours_64 python tools/prof_one.py ours 64 4096 7168 > $O/prof_ours_64.log 2>&1; echo "rc=$?"
 timeout 600 $NCU -k regex:sm100_fp8 -s 1 -c 1 -f -o $O/ref_64 python tools/prof_one.py ref 64 4096 7168 > $O/prof_ref_64.log 2>&1; echo "rc=$?"
 timeout 600 $NCU -k regex:fp8_gemm_kernel -s 1 -c 1 -f -o $O/ours_512 python tools/prof_one.py ours 512 4096 7168 > $O/prof_ours_512.log 2>&1; echo "rc=$?"
+timeout 600 $NCU -k regex:fp8_gemm_kernel -s 1 -c 1 -f -o $O/ours_128 python tools/prof_one.py ours 128 4096 7168 > $O/prof_ours_128.log 2>&1; echo "rc=$?"
 timeout 900 $NCU -k regex:fp8_gemm_kernel -s 1 -c 1 -f -o $O/ours_contig python tools/prof_grouped.py ours 48 256 > $O/prof_ours_contig.log 2>&1; echo "rc=$?"
 timeout 900 $NCU -k regex:"scatter_kernel|bucket_kernel|exchange_kernel|wait_kernel" -s 8 -c 4 -f -o $O/ep_dispatch python bench.py --workload ep --steps 2 --warmup 3 > $O/prof_ep.log 2>&1; echo "rc=$?"
 for f in $O/*.ncu-rep; do ncu -i $f --page raw --csv > ${f%.ncu-rep}.raw.csv 2>/dev/null; done

@@ -25,6 +25,17 @@ WANT = [
 ]
 
 
+KEYS = {'ours_4096': 'dense_m4096', 'ours_512': 'dense_m512', 'ours_64': 'dense_m64', 'ours_128': 'dense_m128',
+        'ours_contig': 'contiguous_g48_m256', 'ours_masked': 'masked', 'ep_dispatch': 'ep_dispatch',
+        'ref_4096': 'reference_dense_m4096', 'ref_64': 'reference_dense_m64'}
+TRAFFIC = {}
+UNIT = {'byte': 1, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9, 'Tbyte': 1e12}
+
+
+def to_bytes(value, unit):
+    return float(value.replace(',', '')) * UNIT.get(unit, 1)
+
+
 def main():
     out_path, reps = sys.argv[1], sys.argv[2:]
     lines = ['# ncu summaries (`ncu --set full --clock-control none --import-source on`, B200)\n']
@@ -48,9 +59,21 @@ def main():
                     v, u = d[key]
                     lines.append(f'| {label} (`{key}`) | {v} {u} |')
             rd, wr = d.get('dram__bytes_read.sum'), d.get('dram__bytes_write.sum')
+            key = KEYS.get(rep.split('/')[-1].split('.')[0])
+            if key == 'ep_dispatch':
+                key = 'ep_' + name.split('(')[0].split('<')[0].split()[-1]
+            if key and rd and wr:
+                TRAFFIC[key] = {'dram_read_bytes': to_bytes(*rd), 'dram_write_bytes': to_bytes(*wr),
+                                'duration_us': float(d['gpu__time_duration.sum'][0]), 'kernel': name[:80]}
             lines.append('')
     open(out_path, 'w').write('\n'.join(lines) + '\n')
     print('wrote', out_path)
+    if TRAFFIC:
+        import json
+        import os
+        path = os.path.join(os.path.dirname(out_path), 'traffic.json')
+        json.dump(TRAFFIC, open(path, 'w'), indent=1, sort_keys=True)
+        print('wrote', path)
 
 
 if __name__ == '__main__':
