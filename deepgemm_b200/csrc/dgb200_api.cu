@@ -184,6 +184,7 @@ struct Config {
     int num_splits, kb_per_split;   // split-K (dense, small problems): K cut into num_splits ranges
     int csplit;                     // cluster split-K: `cluster` single-CTA MMAs share one tile (then num_splits == cluster)
     int grid, grid_y;               // grid == 0: persistent grid over num_sms; else exactly grid x grid_y CTAs
+    bool overlap_producer = false;  // launch as a programmatic dependent that does not wait for the preceding kernel
 };
 
 constexpr int kSmemCapacity = 232448;  // 227 KB usable per CTA on sm_100 (heuristics/sm100.hpp:15)
@@ -335,6 +336,8 @@ struct GemmCall {
     int a_rows;  // total rows of the flattened A
     int64_t lda, ldb, ldd;
     bool x_mn = false, w_mn = false;  // operand is MN-major (M / N contiguous, K strided by lda / ldb)
+    const uint32_t* arrival = nullptr;           // EP dispatch in flight: per-group arrival counters / their targets;
+    const uint32_t* arrival_expected = nullptr;  // the launch overlaps the producer kernel (no griddepcontrol.wait)
     int sfa_krows = 0, sfb_krows = 0; // k-grouped: total packed SF rows (0: derive from k)
     int sfa_stride, sfb_stride, sfa_cols, sfb_cols;
     int gran_k_a, gran_k_b;
@@ -365,7 +368,7 @@ int launch_kernel(Kernel kernel, const Config& cfg, cudaStream_t stream, const C
     lc.blockDim = dim3(kNumThreads, 1, 1);
     lc.dynamicSmemBytes = cfg.smem_bytes;
     lc.stream = stream;
-    cudaLaunchAttribute attrs[2];
+    cudaLaunchAttribute attrs[3];
     int na = 0;
     if (cfg.cluster > 1) {
         attrs[na].id = cudaLaunchAttributeClusterDimension;
@@ -390,7 +393,7 @@ int launch_kernel(Kernel kernel, const Config& cfg, cudaStream_t stream, const C
         const int clusters = std::min(it->second, cfg.num_sms / cfg.cluster);
         lc.gridDim = dim3(clusters * cfg.cluster, 1, 1);
     }
-    if (rt().pdl) {
+    if (rt().pdl || cfg.overlap_producer) {
         attrs[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         attrs[na].val.programmaticStreamSerializationAllowed = 1;
         ++na;
@@ -505,6 +508,7 @@ int run_gemm(const GemmCall& c) {
     DGB_REQUIRE(cfg.cluster <= 2 || cfg.num_splits == 1 || cfg.csplit);
     if (cfg.csplit) DGB_REQUIRE(cfg.block_m % (16 * cfg.csplit) == 0 && cfg.cluster == cfg.csplit);
     if (c.type == kMContiguous || c.type == kMContiguousPsum) DGB_REQUIRE(c.alignment % cfg.block_m == 0);
+    cfg.overlap_producer = c.arrival != nullptr;
     if (c.x_mn) DGB_REQUIRE(load_m % 32 == 0);
 
     const int num_kp_a = ceil_div(c.k, c.gran_k_a * 4), num_kp_b = ceil_div(c.k, c.gran_k_b * 4);
@@ -556,6 +560,7 @@ int run_gemm(const GemmCall& c) {
     const bool ws_split = cfg.num_splits > 1 && !cfg.csplit;
     p.splitk_counters = ws_split ? static_cast<int*>(c.workspace) : nullptr;
     p.splitk_ws = ws_split ? reinterpret_cast<float*>(static_cast<char*>(c.workspace) + kSplitKHeaderBytes) : nullptr;
+    p.arrival = c.arrival, p.arrival_expected = c.arrival_expected;
     p.debug_ts = g_debug_ts.load();
     p.num_n_units = ceil_div(c.n, (int)kBlockN * cta_group);
     p.num_m_blocks = ceil_div(c.m, cfg.block_m);
@@ -747,6 +752,37 @@ int dgb200_m_grouped_fp8_gemm_nt_contiguous(const void* a, const int32_t* sfa, c
     return run_gemm(c);
 }
 
+int dgb200_ep_grouped_gemm(void* local_buffer, int world, int num_experts, int capacity, int k, const void* b,
+                           const int32_t* sfb, void* d, int n, int64_t ldb, int64_t ldd, int major_b, int sfb_stride,
+                           int gran_k_b, int expected_m, int overlap_dispatch, void* stream) {
+    DGB_REQUIRE(local_buffer != nullptr && world > 0 && num_experts > 0 && num_experts % world == 0 && capacity > 0);
+    DGB_REQUIRE(n > 0 && k > 0 && b != nullptr && sfb != nullptr && d != nullptr);
+    DGB_REQUIRE(major_b == DGB200_K_MAJOR || major_b == DGB200_MN_MAJOR);
+    DGB_REQUIRE(ldb >= (major_b == DGB200_K_MAJOR ? k : n) && ldd >= n && sfb_stride >= align_up(n, 4));
+    const ep::Layout l = ep::make_layout(world, num_experts, capacity, k);
+    uint8_t* base = static_cast<uint8_t*>(local_buffer);
+    GemmCall c{};
+    c.type = kMContiguousPsum;
+    c.w_mn = major_b == DGB200_MN_MAJOR;
+    c.a = base + l.a_off, c.sfa = reinterpret_cast<const int32_t*>(base + l.sfa_off), c.b = b, c.sfb = sfb, c.d = d;
+    c.grouped_layout = reinterpret_cast<const int32_t*>(base + l.psum_off);
+    c.m = capacity, c.n = n, c.k = k, c.groups = num_experts / world, c.a_rows = capacity;
+    c.lda = k, c.ldb = ldb, c.ldd = ldd;
+    c.sfa_stride = capacity, c.sfb_stride = sfb_stride;
+    c.sfa_cols = align_up(capacity, 4), c.sfb_cols = align_up(n, 4);
+    c.gran_k_a = 128, c.gran_k_b = gran_k_b;
+    c.d_dtype = DGB200_BF16, c.accumulate = 0;
+    c.expected_m = expected_m > 0 ? expected_m : ceil_div(capacity, c.groups);
+    c.alignment = rt().mk_alignment;
+    c.zero_padding = 1;
+    if (overlap_dispatch) {
+        c.arrival = reinterpret_cast<const uint32_t*>(base + l.arrived_off);
+        c.arrival_expected = reinterpret_cast<const uint32_t*>(base + l.expected_off);
+    }
+    c.stream = static_cast<cudaStream_t>(stream);
+    return run_gemm(c);
+}
+
 int dgb200_m_grouped_fp8_gemm_nt_masked(const void* a, const int32_t* sfa, const void* b, const int32_t* sfb, void* d,
                                         const int32_t* masked_m, int num_groups, int m_max, int n, int k,
                                         int expected_m, int sfa_stride, int sfb_stride, int gran_k_a, int gran_k_b,
@@ -870,14 +906,15 @@ int dgb200_ep_unimport(void* ptr) {
 
 int dgb200_ep_dispatch(const void* x, int64_t ldx, const int32_t* sf, int64_t sf_stride_t, int64_t sf_stride_k,
                        const void* expert_ids, int id_bytes, int num_tokens, int k, int num_experts, int rank, int world,
-                       void* const* buffers, int capacity, int alignment, int32_t* token_row, void* stream) {
+                       void* const* buffers, int capacity, int alignment, int32_t* token_row, int32_t* order_scratch,
+                       int wait_for_all, void* stream) {
     if (int e = ensure_device()) return e;
     DGB_REQUIRE(world > 0 && world <= static_cast<int>(ep::kMaxWorld) && rank >= 0 && rank < world);
     DGB_REQUIRE(num_experts > 0 && num_experts <= static_cast<int>(ep::kMaxExperts) && num_experts % world == 0);
     DGB_REQUIRE(num_tokens >= 0 && capacity > 0 && alignment > 0);
     DGB_REQUIRE(k > 0 && k % 16 == 0 && ceil_div(k, 512) <= 32);
     DGB_REQUIRE(id_bytes == 4 || id_bytes == 8);
-    DGB_REQUIRE(buffers != nullptr && token_row != nullptr);
+    DGB_REQUIRE(buffers != nullptr && token_row != nullptr && (wait_for_all || num_tokens == 0 || order_scratch != nullptr));
     DGB_REQUIRE(num_tokens == 0 || (x != nullptr && sf != nullptr && expert_ids != nullptr));
     DGB_REQUIRE(ldx % 16 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0);
     ep::Peers peers;
@@ -894,19 +931,31 @@ int dgb200_ep_dispatch(const void* x, int64_t ldx, const int32_t* sf, int64_t sf
         ep::bucket_kernel<int32_t><<<num_experts, 1024, 0, s>>>(expert_ids, num_tokens, token_row, counts);
     else
         ep::bucket_kernel<int64_t><<<num_experts, 1024, 0, s>>>(expert_ids, num_tokens, token_row, counts);
-    ep::exchange_kernel<<<1, 1024, 0, s>>>(peers, l, rank, world, num_experts, capacity, alignment);
-    const int grid = std::max(1, std::min(ceil_div(num_tokens, 8), rt().sm_count * 8));
-    if (id_bytes == 4)
-        ep::scatter_kernel<int32_t><<<grid, 256, 0, s>>>(peers, l, static_cast<const uint8_t*>(x), ldx, sf, sf_stride_t,
-                                                          sf_stride_k, expert_ids, token_row, num_tokens, k, kp, rank,
-                                                          world, num_experts, capacity);
-    else
-        ep::scatter_kernel<int64_t><<<grid, 256, 0, s>>>(peers, l, static_cast<const uint8_t*>(x), ldx, sf, sf_stride_t,
-                                                          sf_stride_k, expert_ids, token_row, num_tokens, k, kp, rank,
-                                                          world, num_experts, capacity);
-    ep::wait_kernel<<<1, 32, 0, s>>>(mine, world);
+    // wait_for_all: plain token order, 8 CTAs per SM, nothing but the final flags. Otherwise (a consumer watches the
+    // per-expert arrival counters): expert-sorted order, and a persistent single wave of 4 CTAs per SM with <= 32
+    // registers, so that every CTA is resident from the start and the consumer's CTAs (384 threads, 1 per SM) fit beside.
+    const bool signal = !wait_for_all;
+    const int grid = std::max(1, std::min(ceil_div(num_tokens, 8), rt().sm_count * (signal ? 4 : 8)));
+    ep::exchange_kernel<<<1, 1024, 0, s>>>(peers, l, rank, world, num_experts, capacity, alignment, signal);
+    const auto* xb = static_cast<const uint8_t*>(x);
+    if (signal && num_tokens > 0) {
+        if (id_bytes == 4)
+            ep::order_kernel<int32_t><<<ceil_div(num_tokens, 256), 256, 0, s>>>(mine, l, expert_ids, num_tokens, num_experts, token_row, order_scratch);
+        else
+            ep::order_kernel<int64_t><<<ceil_div(num_tokens, 256), 256, 0, s>>>(mine, l, expert_ids, num_tokens, num_experts, token_row, order_scratch);
+    }
+#define DGB_SCATTER(ID, SIG)                                                                                          \
+    ep::scatter_kernel<ID, SIG><<<grid, 256, 0, s>>>(peers, l, xb, ldx, sf, sf_stride_t, sf_stride_k, expert_ids, token_row, \
+                                                     order_scratch, num_tokens, k, kp, rank, world, num_experts, capacity)
+    if (id_bytes == 4) {
+        if (signal) DGB_SCATTER(int32_t, true); else DGB_SCATTER(int32_t, false);
+    } else {
+        if (signal) DGB_SCATTER(int64_t, true); else DGB_SCATTER(int64_t, false);
+    }
+#undef DGB_SCATTER
+    if (wait_for_all) ep::wait_kernel<<<1, 32, 0, s>>>(mine, world);
     DGB_CUDA(cudaGetLastError());
-    g_launch_count.fetch_add(4, std::memory_order_relaxed);
+    g_launch_count.fetch_add(wait_for_all ? 4 : (num_tokens > 0 ? 4 : 3), std::memory_order_relaxed);
     return DGB200_OK;
 }
 

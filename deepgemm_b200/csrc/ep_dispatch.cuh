@@ -33,7 +33,8 @@ struct Control {
     uint32_t done_ctas;           // scatter CTAs finished (local)
     uint32_t num_rows;            // rows of the local A buffer in use after the last dispatch (aligned end of the last expert)
     uint32_t overflow;            // set when a dispatch would not fit `capacity`
-    uint32_t pad[28];
+    uint32_t num_routed;          // local tokens with a valid expert in the last dispatch
+    uint32_t pad[27];
     uint32_t counts_flag[kMaxWorld * 8];   // [s*8]: epoch of the counts source rank s published here (32 B apart)
     uint32_t data_flag[kMaxWorld * 8];     // [s*8]: epoch of the rows source rank s finished writing here
 };
@@ -47,6 +48,10 @@ struct Layout {
     uint64_t dst_base_off;  // int32 [num_experts]         first destination row of MY tokens for each expert (local)
     uint64_t psum_off;      // int32 [experts_per_rank]    end row of each local expert segment (the GEMM's psum layout)
     uint64_t counts_off;    // int32 [num_experts]         my own per-expert token counts (local)
+    uint64_t sorted_off;    // int32 [num_experts]         position of my first token of each expert in expert-sorted order (local)
+    uint64_t arrived_off;   // uint32 [experts_per_rank]   rows landed for each local expert, cumulative over all dispatches
+                            //                             (incremented by the sources with remote atomics)
+    uint64_t expected_off;  // uint32 [experts_per_rank]   value `arrived` reaches when the current dispatch is complete (local)
     uint64_t sfa_off;       // int32 [kp][capacity]        MN-major packed UE8M0 scale factors
     uint64_t a_off;         // uint8 [capacity][k]         FP8 rows
     uint64_t total;
@@ -61,6 +66,9 @@ inline Layout make_layout(uint32_t world, uint32_t num_experts, uint32_t capacit
     l.dst_base_off = off, off += align_up64(4ull * num_experts, 1024);
     l.psum_off = off, off += align_up64(4ull * num_experts, 1024);
     l.counts_off = off, off += align_up64(4ull * num_experts, 1024);
+    l.sorted_off = off, off += align_up64(4ull * num_experts, 1024);
+    l.arrived_off = off, off += align_up64(4ull * num_experts, 1024);
+    l.expected_off = off, off += align_up64(4ull * num_experts, 1024);
     l.sfa_off = off, off += align_up64(4ull * ((k + 511) / 512) * capacity, 1024);
     l.a_off = off, off += align_up64(1ull * capacity * k, 1024);
     l.total = off;
@@ -102,32 +110,58 @@ __device__ __forceinline__ int64_t load_id(const void* ids, uint32_t t) {
 }
 
 // grid = num_experts, block = 1024. slot[t] = number of earlier local tokens with the same expert (stable order).
+// Every thread looks at 4 consecutive tokens per pass (one 16 / 32-byte load), so a pass covers 4096 tokens with one
+// warp scan + one 32-entry block scan.
 template <typename id_t>
 __global__ void __launch_bounds__(1024)
 bucket_kernel(const void* __restrict__ ids, uint32_t num_tokens, int32_t* __restrict__ slot, int32_t* __restrict__ counts) {
     asm volatile("griddepcontrol.wait;" ::: "memory");
     __shared__ uint32_t warp_off[33];
     const uint32_t e = blockIdx.x, tid = threadIdx.x, warp = tid / 32, lane = tid % 32;
+    const id_t* p = reinterpret_cast<const id_t*>(ids);
+    const bool vec_ok = (reinterpret_cast<uintptr_t>(ids) & 31) == 0;
     uint32_t base = 0;
-    for (uint32_t t0 = 0; t0 < num_tokens; t0 += 1024) {
-        const uint32_t t = t0 + tid;
-        const bool match = t < num_tokens && load_id<id_t>(ids, t) == static_cast<int64_t>(e);
-        const uint32_t ballot = __ballot_sync(0xffffffffu, match);
-        if (lane == 0) warp_off[warp] = __popc(ballot);
+    for (uint32_t t0 = 0; t0 < num_tokens; t0 += 4096) {
+        const uint32_t t = t0 + tid * 4;
+        bool m[4];
+        if (vec_ok && t + 4 <= num_tokens) {
+            if constexpr (sizeof(id_t) == 4) {
+                const int4 v = __ldg(reinterpret_cast<const int4*>(p + t));
+                m[0] = v.x == static_cast<int>(e), m[1] = v.y == static_cast<int>(e), m[2] = v.z == static_cast<int>(e), m[3] = v.w == static_cast<int>(e);
+            } else {
+                const longlong2 v0 = __ldg(reinterpret_cast<const longlong2*>(p + t)), v1 = __ldg(reinterpret_cast<const longlong2*>(p + t + 2));
+                m[0] = v0.x == static_cast<long long>(e), m[1] = v0.y == static_cast<long long>(e);
+                m[2] = v1.x == static_cast<long long>(e), m[3] = v1.y == static_cast<long long>(e);
+            }
+        } else {
+#pragma unroll
+            for (uint32_t j = 0; j < 4; ++j) m[j] = t + j < num_tokens && load_id<id_t>(ids, t + j) == static_cast<int64_t>(e);
+        }
+        const uint32_t mine = m[0] + m[1] + m[2] + m[3];
+        uint32_t incl = mine;                                   // inclusive scan over the warp
+#pragma unroll
+        for (uint32_t d = 1; d < 32; d *= 2) {
+            const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += v;
+        }
+        if (lane == 31) warp_off[warp] = incl;
         __syncthreads();
         if (warp == 0) {
             const uint32_t c = warp_off[lane];
-            uint32_t incl = c;
+            uint32_t w = c;
 #pragma unroll
             for (uint32_t d = 1; d < 32; d *= 2) {
-                const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
-                if (lane >= d) incl += v;
+                const uint32_t v = __shfl_up_sync(0xffffffffu, w, d);
+                if (lane >= d) w += v;
             }
-            warp_off[lane] = incl - c;
-            if (lane == 31) warp_off[32] = incl;
+            warp_off[lane] = w - c;
+            if (lane == 31) warp_off[32] = w;
         }
         __syncthreads();
-        if (match) slot[t] = static_cast<int32_t>(base + warp_off[warp] + __popc(ballot & ((1u << lane) - 1)));
+        uint32_t pos = base + warp_off[warp] + incl - mine;
+#pragma unroll
+        for (uint32_t j = 0; j < 4; ++j)
+            if (m[j]) slot[t + j] = static_cast<int32_t>(pos++);
         base += warp_off[32];
         __syncthreads();
     }
@@ -137,9 +171,9 @@ bucket_kernel(const void* __restrict__ ids, uint32_t num_tokens, int32_t* __rest
 // grid = 1, block = 1024.
 __global__ void __launch_bounds__(1024)
 exchange_kernel(Peers peers, Layout l, uint32_t rank, uint32_t world, uint32_t num_experts, uint32_t capacity,
-                uint32_t alignment) {
+                uint32_t alignment, bool want_order) {
     asm volatile("griddepcontrol.wait;" ::: "memory");
-    __shared__ uint32_t s_total[kMaxExperts], s_before[kMaxExperts];
+    __shared__ uint32_t s_total[kMaxExperts], s_before[kMaxExperts], s_aligned[kMaxExperts], s_sorted[kMaxExperts];
     const uint32_t tid = threadIdx.x;
     uint8_t* mine = peers.base[rank];
     Control* ctrl = reinterpret_cast<Control*>(mine);
@@ -153,10 +187,25 @@ exchange_kernel(Peers peers, Layout l, uint32_t rank, uint32_t world, uint32_t n
     }
     __threadfence_system();
     __syncthreads();
-    if (tid < world) {
-        st_release_sys(&reinterpret_cast<Control*>(peers.base[tid])->counts_flag[rank * 8], epoch);
-        wait_flag(&ctrl->counts_flag[tid * 8], epoch);
+    if (tid < world) st_release_sys(&reinterpret_cast<Control*>(peers.base[tid])->counts_flag[rank * 8], epoch);
+
+    // while the counts travel: expert-sorted order of my own tokens (needs only my counts)
+    // send order: local expert index first, owner rank second -- every owner receives its expert 0, then its expert 1,
+    // ... at the same pace (plain expert order would serve the owners one after the other)
+    if (want_order) {
+        const uint32_t epr_ = num_experts / world;
+        // s_sorted[key] = count of the expert with that send key; then an exclusive prefix over keys
+        for (uint32_t e = tid; e < num_experts; e += blockDim.x) s_sorted[(e % epr_) * world + e / epr_] = static_cast<uint32_t>(counts[e]);
+        __syncthreads();
+        for (uint32_t e = tid; e < num_experts; e += blockDim.x) {
+            const uint32_t key = (e % epr_) * world + e / epr_;
+            uint32_t before = 0;
+            for (uint32_t j = 0; j < key; ++j) before += s_sorted[j];
+            reinterpret_cast<int32_t*>(mine + l.sorted_off)[e] = static_cast<int32_t>(before);
+            if (key == num_experts - 1) ctrl->num_routed = before + s_sorted[key];
+        }
     }
+    if (tid < world) wait_flag(&ctrl->counts_flag[tid * 8], epoch);
     __syncthreads();
 
     const int32_t* table = reinterpret_cast<const int32_t*>(mine + l.table_off);
@@ -168,6 +217,7 @@ exchange_kernel(Peers peers, Layout l, uint32_t rank, uint32_t world, uint32_t n
             if (s < rank) before += c;
         }
         s_total[e] = total, s_before[e] = before;
+        s_aligned[e] = (total + alignment - 1) / alignment * alignment;
     }
     __syncthreads();
     const uint32_t epr = num_experts / world;
@@ -176,12 +226,14 @@ exchange_kernel(Peers peers, Layout l, uint32_t rank, uint32_t world, uint32_t n
     for (uint32_t e = tid; e < num_experts; e += blockDim.x) {
         const uint32_t owner = e / epr;
         uint32_t seg = 0;
-        for (uint32_t j = owner * epr; j < e; ++j) seg += (s_total[j] + alignment - 1) / alignment * alignment;
+        for (uint32_t j = owner * epr; j < e; ++j) seg += s_aligned[j];
         dst_base[e] = static_cast<int32_t>(seg + s_before[e]);
         if (owner == rank) {
+            // cumulative, like `arrived`; only dispatches that signal arrivals count (the two kinds may alternate)
+            if (want_order) reinterpret_cast<uint32_t*>(mine + l.expected_off)[e - rank * epr] += s_total[e];
             psum[e - rank * epr] = static_cast<int32_t>(min(seg + s_total[e], capacity));   // stays in bounds on overflow
             if (e == (rank + 1) * epr - 1) {
-                const uint32_t rows = seg + (s_total[e] + alignment - 1) / alignment * alignment;
+                const uint32_t rows = seg + s_aligned[e];
                 ctrl->num_rows = rows;
                 if (rows > capacity) ctrl->overflow = 1;
             }
@@ -191,38 +243,77 @@ exchange_kernel(Peers peers, Layout l, uint32_t rank, uint32_t world, uint32_t n
     if (tid == 0) ctrl->epoch = epoch;
 }
 
-// One warp per token. `x` rows of `k` bytes (pitch ldx), `sf` [T][kp] int32 words with strides (sf_stride_t, sf_stride_k).
+// order[p] = the p-th of my routed tokens in expert-sorted (stable) order: the order the scatter walks them in, so that
+// experts complete one after the other on their owners. grid = ceil(T / 256).
 template <typename id_t>
 __global__ void __launch_bounds__(256)
+order_kernel(const uint8_t* __restrict__ mine, Layout l, const void* __restrict__ ids, uint32_t num_tokens,
+             uint32_t num_experts, int32_t* __restrict__ token_row, int32_t* __restrict__ order) {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    const uint32_t t = blockIdx.x * 256 + threadIdx.x;
+    if (t >= num_tokens) return;
+    const int32_t* sorted = reinterpret_cast<const int32_t*>(mine + l.sorted_off);
+    const int64_t e = load_id<id_t>(ids, t);
+    if (e < 0 || e >= static_cast<int64_t>(num_experts))
+        token_row[t] = -1;                                                   // routed nowhere (DeepEP uses -1)
+    else
+        order[static_cast<uint32_t>(__ldg(sorted + e)) + static_cast<uint32_t>(token_row[t])] = static_cast<int32_t>(t);
+}
+
+// One warp per token, tokens walked in expert-sorted order. `x` rows of `k` bytes (pitch ldx), `sf` [T][kp] int32 words
+// with strides (sf_stride_t, sf_stride_k). After a row has been written its owner's per-expert arrival counter is
+// incremented (remote atomic): a consumer may start on an expert as soon as all of its rows are in
+// (dgb200_ep_grouped_gemm), without waiting for the whole dispatch.
+// kSignal = false: plain token order, no counters (the consumer waits for the whole dispatch: wait_kernel).
+template <typename id_t, bool kSignal>
+__global__ void __launch_bounds__(256, kSignal ? 8 : 4)   // kSignal: <= 32 registers, so that 4 CTAs per SM leave room for a co-resident GEMM CTA
 scatter_kernel(Peers peers, Layout l, const uint8_t* __restrict__ x, int64_t ldx, const int32_t* __restrict__ sf,
                int64_t sf_stride_t, int64_t sf_stride_k, const void* __restrict__ ids, int32_t* __restrict__ token_row,
-               uint32_t num_tokens, uint32_t k, uint32_t kp, uint32_t rank, uint32_t world, uint32_t num_experts,
-               uint32_t capacity) {
+               const int32_t* __restrict__ order, uint32_t num_tokens_plain, uint32_t k, uint32_t kp, uint32_t rank,
+               uint32_t world, uint32_t num_experts, uint32_t capacity) {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");     // a flag-synchronised consumer may start now
     asm volatile("griddepcontrol.wait;" ::: "memory");
     uint8_t* mine = peers.base[rank];
     Control* ctrl = reinterpret_cast<Control*>(mine);
     const uint32_t epoch = ctrl->epoch;                       // the exchange of this dispatch already bumped it
+    const uint32_t num_routed = kSignal ? ctrl->num_routed : num_tokens_plain;
     const int32_t* dst_base = reinterpret_cast<const int32_t*>(mine + l.dst_base_off);
     const uint32_t epr = num_experts / world;
     const uint32_t lane = threadIdx.x % 32;
     const uint32_t warps_per_cta = blockDim.x / 32;
     const uint32_t chunks = k / 16;
 
-    for (uint32_t t = blockIdx.x * warps_per_cta + threadIdx.x / 32; t < num_tokens; t += gridDim.x * warps_per_cta) {
-        const int64_t e = load_id<id_t>(ids, t);
-        if (e < 0 || e >= static_cast<int64_t>(num_experts)) {          // token routed nowhere (DeepEP uses -1)
+    for (uint32_t pos = blockIdx.x * warps_per_cta + threadIdx.x / 32; pos < num_routed; pos += gridDim.x * warps_per_cta) {
+        const uint32_t t = kSignal ? static_cast<uint32_t>(__ldg(order + pos)) : pos;
+        const int64_t e64 = load_id<id_t>(ids, t);
+        if (!kSignal && (e64 < 0 || e64 >= static_cast<int64_t>(num_experts))) {     // routed nowhere (DeepEP uses -1)
             if (lane == 0) token_row[t] = -1;
             continue;
         }
-        const uint32_t owner = static_cast<uint32_t>(e) / epr;
+        const uint32_t e = static_cast<uint32_t>(e64);
+        const uint32_t owner = e / epr;
         const uint32_t row = static_cast<uint32_t>(__ldg(dst_base + e)) + static_cast<uint32_t>(token_row[t]);
-        if (row >= capacity) {                                            // the exchange flagged `overflow`; drop
-            if (lane == 0) token_row[t] = -1;
+        uint32_t* arrived = reinterpret_cast<uint32_t*>(peers.base[owner] + l.arrived_off) + (e - owner * epr);
+        if (row >= capacity) {                                            // the exchange flagged `overflow`; drop, but count
+            __syncwarp();
+            if (lane == 0) {
+                token_row[t] = -1;
+                if (kSignal) asm volatile("red.relaxed.sys.global.add.u32 [%0], 1;" ::"l"(arrived) : "memory");
+            }
             continue;
         }
         const uint4* src = reinterpret_cast<const uint4*>(x + static_cast<int64_t>(t) * ldx);
         uint4* dst = reinterpret_cast<uint4*>(peers.base[owner] + l.a_off + static_cast<uint64_t>(row) * k);
         uint32_t c = lane;
+        if constexpr (!kSignal) {
+            for (; c + 192 < chunks; c += 224) {                          // 7 x 16 B in flight per lane (K = 7168: 2 rounds)
+                uint4 v[7];
+#pragma unroll
+                for (uint32_t j = 0; j < 7; ++j) v[j] = __ldg(src + c + 32 * j);
+#pragma unroll
+                for (uint32_t j = 0; j < 7; ++j) dst[c + 32 * j] = v[j];
+            }
+        }
         for (; c + 96 < chunks; c += 128) {                               // 4 x 16 B in flight per lane
             const uint4 v0 = __ldg(src + c), v1 = __ldg(src + c + 32), v2 = __ldg(src + c + 64), v3 = __ldg(src + c + 96);
             dst[c] = v0, dst[c + 32] = v1, dst[c + 64] = v2, dst[c + 96] = v3;
@@ -232,8 +323,14 @@ scatter_kernel(Peers peers, Layout l, const uint8_t* __restrict__ x, int64_t ldx
             int32_t* sfa = reinterpret_cast<int32_t*>(peers.base[owner] + l.sfa_off);
             sfa[static_cast<uint64_t>(lane) * capacity + row] = __ldg(sf + t * sf_stride_t + lane * sf_stride_k);
         }
-        __syncwarp();
-        if (lane == 0) token_row[t] = static_cast<int32_t>(row);
+        __syncwarp();                                                     // every lane's stores precede lane 0's release
+        if (lane == 0) {
+            token_row[t] = static_cast<int32_t>(row);
+            if (kSignal) {
+                asm volatile("fence.acq_rel.sys;" ::: "memory");
+                asm volatile("red.relaxed.sys.global.add.u32 [%0], 1;" ::"l"(arrived) : "memory");
+            }
+        }
     }
 
     // completion: the last CTA to finish tells every peer that all of this rank's rows have landed

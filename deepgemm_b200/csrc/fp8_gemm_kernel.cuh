@@ -70,6 +70,8 @@ struct GemmParams {
     int* splitk_counters;       // split-K: one arrival counter per (m-block, 128-column block), zero between launches
     uint32_t num_splits;        // K is cut into this many ranges of `kb_per_split` k-blocks (1 = no split)
     uint32_t kb_per_split;
+    const uint32_t* arrival;    // psum layout fed by the EP dispatch: rows landed per group (cumulative), or nullptr
+    const uint32_t* arrival_expected;   // ... and the value each counter reaches when the group is complete
     long long* debug_ts;        // optional (development): CTA 0 stamps clock64() at 10 points of its life
     uint32_t num_n_units;       // ceil(n / (128 * cluster))
     uint32_t num_m_blocks;      // dense / contiguous: ceil(m / block_m)
@@ -456,8 +458,9 @@ fp8_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
         tmem_base = ld_shared_u32(tmem_ptr_smem);
     }
 
-    // Programmatic dependent launch: everything above overlaps the previous kernel's tail
-    asm volatile("griddepcontrol.wait;" ::: "memory");
+    // Programmatic dependent launch: everything above overlaps the previous kernel's tail. A launch that synchronises
+    // with its producer through the per-group arrival counters (EP dispatch still in flight) must not wait for it.
+    if (p.arrival == nullptr) asm volatile("griddepcontrol.wait;" ::: "memory");
     if (threadIdx.x == 0) DGB_STAMP(1);
 
     const uint32_t sfw_mask = (1u << p.sf_shift_w) - 1, sfx_mask = (1u << p.sf_shift_x) - 1;
@@ -485,8 +488,30 @@ fp8_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
             uint16_t w_mask = 0;
             for (uint32_t q = 0; q < kPairs; ++q) w_mask |= static_cast<uint16_t>(1u << (2 * q + (cta_rank & 1)));
             uint32_t fresh = num_stages;          // slots never used yet: nothing to wait for (a TRYWAIT costs ~90 cycles)
+            uint32_t landed_group = 0xffffffffu;
             while (sched.next(t)) {
                 if (kGemmType == kMContiguousPsum && t.valid_m == 0) continue;
+                if constexpr (kGemmType == kMContiguousPsum) {
+                    // rows of this expert still travelling (dispatch kernels of the peers run concurrently)? wait for
+                    // its arrival counter; groups are walked in order, the sources send them in order
+                    if (p.arrival != nullptr && sched.g != landed_group) {
+                        const uint32_t want = __ldg(p.arrival_expected + sched.g);
+                        uint64_t t0 = 0;
+                        uint32_t spins = 0, got;
+                        while (true) {
+                            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(got) : "l"(p.arrival + sched.g) : "memory");
+                            if (static_cast<int32_t>(got - want) >= 0) break;
+                            __nanosleep(64);
+                            if ((++spins & 0x3FF) == 0) {
+                                const uint64_t now = globaltimer_ns();
+                                if (t0 == 0) t0 = now;
+                                if (now - t0 > kSpinTimeoutNs) asm volatile("trap;");
+                            }
+                        }
+                        asm volatile("fence.proxy.async;" ::: "memory");   // rows were written by generic stores, TMA reads them
+                        landed_group = sched.g;
+                    }
+                }
                 const uint32_t x_row = t.x_row + (cta_rank & 1) * (tile_n(t) / kCtaGroup);
                 uint32_t k0 = t.kb_begin * kBlockK;
                 for (uint32_t kb = t.kb_begin; kb < t.kb_end; ++kb, k0 += kBlockK, ring.advance()) {

@@ -201,6 +201,7 @@ class EpBuffer:
         self.psum_layout = b[self.off_psum:self.off_psum + 4 * epr].view(torch.int32)
         self.counts = b[self.off_counts:self.off_counts + 4 * num_experts].view(torch.int32)
         self._ctrl = b[:64].view(torch.int32)
+        self._order = None
 
     # device-side scalars (reading them synchronises; the data path never does)
     def num_rows(self) -> int:
@@ -210,22 +211,46 @@ class EpBuffer:
         return bool(self._ctrl[self.off_overflow // 4].item())
 
     def dispatch(self, x_fp8: torch.Tensor, sf_packed: torch.Tensor, expert_ids: torch.Tensor,
-                 token_row: Optional[torch.Tensor] = None) -> PeerDispatch:
-        """Enqueue the four dispatch kernels on the current stream. x_fp8 [T,K] e4m3 (row pitch multiple of 16 B),
-        sf_packed [T, ceil(K/512)] int32 (any strides), expert_ids [T] int32/int64 (outside [0,G) = not routed)."""
+                 token_row: Optional[torch.Tensor] = None, wait: bool = True) -> PeerDispatch:
+        """Enqueue the dispatch kernels on the current stream. x_fp8 [T,K] e4m3 (row pitch multiple of 16 B),
+        sf_packed [T, ceil(K/512)] int32 (any strides), expert_ids [T] int32/int64 (outside [0,G) = not routed).
+        wait=False leaves out the final "everything has landed" kernel: only `grouped_gemm(..., overlap=True)` may
+        follow, which watches the per-expert arrival counters itself and runs beside the scatter."""
         t, k = x_fp8.shape
         assert k == self.k and x_fp8.stride(1) == 1 and x_fp8.is_cuda
         assert sf_packed.dtype == torch.int32 and sf_packed.shape == (t, self.kp)
         assert expert_ids.dtype in (torch.int32, torch.int64) and expert_ids.is_contiguous() and expert_ids.numel() == t
         if token_row is None:
             token_row = torch.empty(t, dtype=torch.int32, device=x_fp8.device)
+        if self._order is None or self._order.numel() < t:
+            self._order = torch.empty(max(t, 1), dtype=torch.int32, device=x_fp8.device)   # scratch: expert-sorted token order
         self._check(self._lib.dgb200_ep_dispatch(
             x_fp8.data_ptr(), x_fp8.stride(0), sf_packed.data_ptr(), sf_packed.stride(0), sf_packed.stride(1),
             expert_ids.data_ptr(), expert_ids.element_size(), t, k, self.num_experts, self.rank, self.world,
-            self._ptr_array, self.capacity, self.alignment, token_row.data_ptr(),
+            self._ptr_array, self.capacity, self.alignment, token_row.data_ptr(), self._order.data_ptr(), int(wait),
             torch.cuda.current_stream().cuda_stream))
         return PeerDispatch(a=self.a, sfa=self.sfa, psum_layout=self.psum_layout, token_row=token_row,
                             expected_m=max(1, t * self.world // self.num_experts))
+
+    def grouped_gemm(self, w_local: Tuple[torch.Tensor, torch.Tensor], d: torch.Tensor, expected_m: int,
+                     overlap: bool = True) -> None:
+        """D[capacity, N] = grouped GEMM of this rank's experts over the dispatch buffer (psum layout, zero padding).
+        `w_local` = (B [G/P, N, K] e4m3, SFB FP32 [G/P, N/128, K/128] or packed int32). overlap=True must directly
+        follow `dispatch(..., wait=False)` on the same stream (see include/dgb200.h, dgb200_ep_grouped_gemm)."""
+        from . import layout as _layout
+        b, sfb = w_local
+        epr = self.num_experts // self.world
+        assert b.dim() == 3 and b.shape[0] == epr and b.shape[2] == self.k and b.dtype == torch.float8_e4m3fn
+        n = b.shape[1]
+        assert d.shape == (self.capacity, n) and d.dtype == torch.bfloat16 and d.stride(1) == 1
+        if sfb.dtype != torch.int32:
+            sfb = _layout.transform_sf_into_required_layout(sfb, n, self.k, (1, 128, 128), epr, False)
+        k_major = b.stride(2) == 1
+        ldb = b.stride(1) if k_major else b.stride(2)
+        self._check(self._lib.dgb200_ep_grouped_gemm(
+            self.ptr, self.world, self.num_experts, self.capacity, self.k, b.data_ptr(), sfb.data_ptr(), d.data_ptr(), n,
+            ldb, d.stride(0), 0 if k_major else 1, sfb.stride(-1), 128, int(expected_m), int(overlap),
+            torch.cuda.current_stream().cuda_stream))
 
     def close(self) -> None:
         if getattr(self, 'ptr', None) is None:
@@ -243,15 +268,17 @@ class EpBuffer:
 
 def expert_sharded_grouped_gemm(x_fp8: torch.Tensor, sf_packed: torch.Tensor, expert_ids: torch.Tensor,
                                 w_local: Tuple[torch.Tensor, torch.Tensor], buffer: EpBuffer,
-                                d: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, PeerDispatch]:
+                                d: Optional[torch.Tensor] = None, overlap: bool = False) -> Tuple[torch.Tensor, PeerDispatch]:
     """Peer-memory dispatch + local grouped GEMM, all enqueued on the current stream without host synchronisation.
     `w_local` = (B [G/P, N, K] e4m3, SFB) for THIS rank's experts (SFB FP32 [G/P, N/128, K/128] or pre-packed int32).
+    overlap=False (default): dispatch, wait for everything, then the contiguous-psum GEMM. overlap=True: the GEMM kernel
+    starts beside the scatter kernel and begins with the experts whose rows have already landed (tokens are then sent in
+    expert order and every row bumps its expert's arrival counter); measured +3.5 % at 2 GPUs, nothing at 1 and 4 at the
+    BASELINE size -- the per-row system-scope release costs about what the overlap hides.
     Returns (D [capacity, N] bf16 on the expert rank -- rows as laid out by `psum_layout` --, dispatch record)."""
-    from . import gemm
-    r = buffer.dispatch(x_fp8, sf_packed, expert_ids)
+    r = buffer.dispatch(x_fp8, sf_packed, expert_ids, wait=not overlap)
     n = w_local[0].shape[1]
     if d is None:
         d = torch.empty((buffer.capacity, n), dtype=torch.bfloat16, device=x_fp8.device)
-    gemm.m_grouped_fp8_gemm_nt_contiguous((r.a, r.sfa), w_local, d, r.psum_layout, use_psum_layout=True,
-                                          expected_m_for_psum_layout=r.expected_m)
+    buffer.grouped_gemm(w_local, d, r.expected_m, overlap=overlap)
     return d, r

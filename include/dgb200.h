@@ -159,10 +159,23 @@ int dgb200_ep_unimport(void* ptr);
 /* x [num_tokens, k] e4m3 rows (pitch ldx bytes), sf: packed UE8M0 words of token t at sf[t*sf_stride_t + j*sf_stride_k],
  * j < ceil(k/512); expert_ids int32 (id_bytes 4) or int64 (id_bytes 8), values outside [0, num_experts) = not routed.
  * token_row int32[num_tokens] (out): row of each token inside its owner's buffer (-1: not routed / dropped on
- * overflow, which also sets the word at DGB200_EP_OFF_OVERFLOW). k % 16 == 0, ceil(k/512) <= 32. */
+ * overflow, which also sets the word at DGB200_EP_OFF_OVERFLOW). k % 16 == 0, ceil(k/512) <= 32.
+ * wait_for_all != 0 appends the kernel that returns once every source's rows have landed (then any consumer may
+ * follow in stream order); 0 leaves that to a consumer that watches the per-expert arrival counters itself
+ * (dgb200_ep_grouped_gemm with overlap_dispatch). Tokens are sent in expert order, so experts complete one by one. */
 int dgb200_ep_dispatch(const void* x, int64_t ldx, const int32_t* sf, int64_t sf_stride_t, int64_t sf_stride_k,
                        const void* expert_ids, int id_bytes, int num_tokens, int k, int num_experts, int rank, int world,
-                       void* const* buffers, int capacity, int alignment, int32_t* token_row, void* stream);
+                       void* const* buffers, int capacity, int alignment, int32_t* token_row,
+                       int32_t* order_scratch /* int32[num_tokens], device */, int wait_for_all, void* stream);
+/* The grouped GEMM of this rank's experts over its dispatch buffer (psum layout, zero padding, BF16 D [capacity, n];
+ * b [G/world, n, k] e4m3, sfb packed UE8M0). With overlap_dispatch != 0 it must directly follow a dgb200_ep_dispatch(...,
+ * wait_for_all = 0, ...) on the same stream: the kernel is then launched as a programmatic dependent of the scatter
+ * kernel, runs beside it, and its TMA producer waits expert by expert on the arrival counters the sources increment
+ * (remote atomics) -- the transfer of expert g+1.. overlaps the math of expert g. With overlap_dispatch == 0 it is
+ * dgb200_m_grouped_fp8_gemm_nt_contiguous on the buffer (use after wait_for_all = 1). */
+int dgb200_ep_grouped_gemm(void* local_buffer, int world, int num_experts, int capacity, int k, const void* b,
+                           const int32_t* sfb, void* d, int n, int64_t ldb, int64_t ldd, int major_b, int sfb_stride,
+                           int gran_k_b, int expected_m, int overlap_dispatch, void* stream);
 
 /* ---- introspection (bench / tests) -------------------------------------------------------------------------- */
 typedef struct dgb200_config {

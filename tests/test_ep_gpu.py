@@ -73,7 +73,8 @@ def test_peer_dispatch_overflow_is_flagged_not_written(dg):
         buf.close()
 
 
-def test_expert_sharded_grouped_gemm_world1_matches_oracle(dg):
+@pytest.mark.parametrize('overlap', [False, True])
+def test_expert_sharded_grouped_gemm_world1_matches_oracle(dg, overlap):
     from deepgemm_b200 import ep
     from deepgemm_b200.utils import per_block_cast_to_fp8, per_token_cast_to_fp8
     from oracle import blockwise
@@ -90,7 +91,7 @@ def test_expert_sharded_grouped_gemm_world1_matches_oracle(dg):
     ids = torch.randint(0, g, (t,), device=dev, generator=gen)
     buf = ep.EpBuffer(g, t + g * align, k)
     try:
-        d, r = ep.expert_sharded_grouped_gemm(xq, sf_packed, ids, wq, buf)
+        d, r = ep.expert_sharded_grouped_gemm(xq, sf_packed, ids, wq, buf, overlap=overlap)
         torch.cuda.synchronize()
         rows = r.token_row.long().cpu()
         got = d.cpu()[rows].float()

@@ -75,7 +75,7 @@ def main():
         if it == 3:
             ids = ids.to(torch.int32)
         d.fill_(float('nan'))
-        _, r = ep.expert_sharded_grouped_gemm(xq, sf, ids, wq, buf, d)
+        _, r = ep.expert_sharded_grouped_gemm(xq, sf, ids, wq, buf, d, overlap=(it % 2 == 0))
         total += check(xq, sf, ids.long(), d, r, f'iter {it}')
 
     # (d) CUDA graph: capture dispatch + GEMM once, replay with new inputs
@@ -84,14 +84,14 @@ def main():
     side = torch.cuda.Stream()
     with torch.cuda.stream(side):
         for _ in range(2):                              # warm-up outside capture (same count on every rank)
-            r = buf.dispatch(sx.copy_(xq), ssf.copy_(sf), sids.copy_(ids), row)
-            dg.m_grouped_fp8_gemm_nt_contiguous((r.a, r.sfa), wq, d, r.psum_layout, use_psum_layout=True)
+            r = buf.dispatch(sx.copy_(xq), ssf.copy_(sf), sids.copy_(ids), row, wait=False)
+            buf.grouped_gemm(wq, d, r.expected_m, overlap=True)
     torch.cuda.synchronize()
     dist.barrier()
     graph = torch.cuda.CUDAGraph()
     with torch.cuda.graph(graph, stream=side):
-        r = buf.dispatch(sx, ssf, sids, row)
-        dg.m_grouped_fp8_gemm_nt_contiguous((r.a, r.sfa), wq, d, r.psum_layout, use_psum_layout=True)
+        r = buf.dispatch(sx, ssf, sids, row, wait=False)
+        buf.grouped_gemm(wq, d, r.expected_m, overlap=True)
     for it in range(2):
         x = torch.randn((t_local, k), device=dev, dtype=torch.bfloat16, generator=gen)
         xq, sf = per_token_cast_to_fp8(x, True, 128, use_packed_ue8m0=True)
