@@ -197,7 +197,8 @@ int dgb200_plan(int gemm_type, int m, int n, int k, int num_groups, int expected
 int dgb200_last_config(dgb200_config* out);
 /* Development aid: when set to a device buffer of (16 + 2 * grid) int64, CTA 0 of every GEMM launch stamps clock64()
  * at ten points of its life (entry, setup done, first TMA, first data, first MMA, last MMA, accumulator ready, stores
- * issued, teardown begin/end) into [0,10), and every CTA b stamps %globaltimer (ns) at entry / exit into
+ * issued, teardown begin/end) into [0,10) (cluster split-K: outbox written / barrier / copies issued / partials landed
+ * into [10,14)), and every CTA b stamps %globaltimer (ns) at entry / exit into
  * [16 + 2b], [17 + 2b]. NULL (default) disables it. */
 int dgb200_debug_set_timestamps(void* device_int64_buffer);
 /* Number of kernels launched by this library since process start (all threads). */
