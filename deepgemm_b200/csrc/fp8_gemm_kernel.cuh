@@ -72,6 +72,7 @@ struct GemmParams {
     uint32_t kb_per_split;
     const uint32_t* arrival;    // psum layout fed by the EP dispatch: rows landed per group (cumulative), or nullptr
     const uint32_t* arrival_expected;   // ... and the value each counter reaches when the group is complete
+    uint64_t w_hint, x_hint;    // L2 cache policies of the weight / token TMA loads (ptx.cuh kEvict*)
     long long* debug_ts;        // optional (development): CTA 0 stamps clock64() at 10 points of its life
     uint32_t num_n_units;       // ceil(n / (128 * cluster))
     uint32_t num_m_blocks;      // dense / contiguous: ceil(m / block_m)
@@ -521,18 +522,18 @@ fp8_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
                     const bool load_sfw = (kb & sfw_mask) == 0 || first, load_sfx = (kb & sfx_mask) == 0 || first;
                     mbar_arrive_expect_tx(full, ab_bytes + (load_sfw ? sfw_tx : 0u) + (load_sfx ? sfx_tx : 0u));
                     if constexpr (kWMn) {
-                        tma_load_2d(&map_w, full, slot, t.n0, t.wk_base + t.k_base + k0, kEvictNormal);
+                        tma_load_2d(&map_w, full, slot, t.n0, t.wk_base + t.k_base + k0, p.w_hint);
                     } else if constexpr (kPairs == 1) {
-                        tma_load_2d(&map_w, full, slot, t.k_base + k0, t.w_row, kEvictNormal);
+                        tma_load_2d(&map_w, full, slot, t.k_base + k0, t.w_row, p.w_hint);
                     } else {
                         tma_load_2d_multicast(&map_w, full, slot + pair_idx * (kWRows * kBlockK), k0, t.w_row + pair_idx * kWRows,
-                                              w_mask, kEvictNormal);
+                                              w_mask, p.w_hint);
                     }
                     if constexpr (kXMn) {
                         for (uint32_t i = 0, off = 0; i < load_m; i += p.x_swizzle, off += p.x_swizzle * kBlockK)
-                            tma_load_2d(&map_x, full, slot + off_x + off, x_row + i, t.k_base + k0, kEvictNormal);
+                            tma_load_2d(&map_x, full, slot + off_x + off, x_row + i, t.k_base + k0, p.x_hint);
                     } else {
-                        tma_load_2d(&map_x, full, slot + off_x, t.k_base + k0, x_row, kEvictNormal);
+                        tma_load_2d(&map_x, full, slot + off_x, t.k_base + k0, x_row, p.x_hint);
                     }
                     if (load_sfw) tma_load_2d(&map_sfw, full, slot + off_sfw, t.sfw_col, t.sfw_row + (kb >> p.sf_shift_w), kEvictNormal);
                     if (load_sfx) tma_load_2d(&map_sfx, full, slot + off_sfx, t.sfx_col, t.sfx_row + (kb >> p.sf_shift_x), kEvictNormal);
