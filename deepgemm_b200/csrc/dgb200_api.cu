@@ -184,6 +184,7 @@ struct Config {
     int num_splits, kb_per_split;   // split-K (dense, small problems): K cut into num_splits ranges
     int csplit;                     // cluster split-K: `cluster` single-CTA MMAs share one tile (then num_splits == cluster)
     int grid, grid_y;               // grid == 0: persistent grid over num_sms; else exactly grid x grid_y CTAs
+    int num_tall = 0, block_m_low = 0;   // dense wave balancing: first num_tall m-blocks block_m high, the rest block_m_low
     bool overlap_producer = false;  // launch as a programmatic dependent that does not wait for the preceding kernel
 };
 
@@ -280,6 +281,40 @@ Config choose_config(const Problem& pb, int num_sms_override = 0) {
     if (const char* v = getenv("DGB200_SPLITS")) c.num_splits = std::max(1, std::min(atoi(v), max_splits));
     c.kb_per_split = ceil_div(num_kb, c.num_splits);
     c.num_splits = ceil_div(num_kb, c.kb_per_split);
+
+    // Wave balancing (dense, tensor-bound sizes). A persistent grid of P CTA pairs runs ceil(tiles / P) rounds, so e.g.
+    // M = N = 4096 with 240-row tiles is 288 tiles = 3.89 -> 4 rounds on 74 pairs although the work is worth 3.69. Tile
+    // height barely matters above ~160 rows (measured), the tile COUNT does: pick the number of m-blocks that minimises
+    // the simulated makespan of the round-robin schedule, and make the blocks as even as multiples of 16 allow (two
+    // heights, the taller ones first).
+    c.num_tall = 0, c.block_m_low = 0;
+    if (pb.type == kDense && !pb.x_mn && c.num_splits == 1 && c.cluster == 2 && pb.m >= 1024 && c.block_m >= 160 &&
+        !getenv("DGB200_BLOCK_M") && env_int("DGB200_BALANCE", 1)) {
+        const int units = c.num_sms / 2, n_units = ceil_div(pb.n, (int)kBlockN * 2);
+        const double overhead_rows = kTileOverhead / (2.0 * num_kb);      // per-tile fixed cost in units of token rows
+        double best_ms = 1e300;
+        int best_nb = 0;
+        for (int nb = ceil_div(pb.m, (int)kMaxBlockM); nb <= ceil_div(pb.m, 160) && nb * n_units <= 64 * units; ++nb) {
+            const int hi = align_up(ceil_div(pb.m, nb), 16), lo = hi - 16;
+            if (hi > (int)kMaxBlockM || lo < 16) continue;
+            // tall blocks: smallest count with tall * hi + (nb - tall) * lo >= m
+            const int tall = std::max(0, std::min(nb, ceil_div(pb.m - nb * lo, 16)));
+            std::vector<double> load(units, 0.0);
+            const int gw = std::max(1, env_int("DGB200_SWIZZLE_GROUP", 8));
+            int idx = 0;
+            for (int g0 = 0; g0 < n_units; g0 += gw) {
+                const int width = std::min(gw, n_units - g0);
+                for (int mb = 0; mb < nb; ++mb) {
+                    const int row0 = mb < tall ? mb * hi : tall * hi + (mb - tall) * lo;
+                    const int h = std::max(0, std::min(mb < tall ? hi : lo, pb.m - row0));
+                    for (int j = 0; j < width; ++j, ++idx) load[idx % units] += align_up(std::max(h, 1), 16) + overhead_rows;
+                }
+            }
+            const double ms = *std::max_element(load.begin(), load.end());
+            if (ms < best_ms * 0.995) best_ms = ms, best_nb = nb, c.block_m = hi, c.block_m_low = lo, c.num_tall = tall;
+        }
+        (void)best_nb;
+    }
 
     // Cluster split-K (dense, K-major, small M): S single-CTA MMAs share one output tile, each streams 1/S of K, and
     // the partial tiles are reduced through distributed shared memory. Every weight byte then crosses L2 -> SM once
@@ -573,6 +608,12 @@ int run_gemm(const GemmCall& c) {
     p.debug_ts = g_debug_ts.load();
     p.num_n_units = ceil_div(c.n, (int)kBlockN * cta_group);
     p.num_m_blocks = ceil_div(c.m, cfg.block_m);
+    p.num_tall = 0xffffffffu, p.block_m_low = cfg.block_m;
+    if (c.type == kDense && cfg.block_m_low > 0) {
+        p.num_tall = cfg.num_tall, p.block_m_low = cfg.block_m_low;
+        const int rest = std::max(0, c.m - cfg.num_tall * cfg.block_m);
+        p.num_m_blocks = cfg.num_tall + ceil_div(rest, cfg.block_m_low);
+    }
     p.m_alignment = std::max(1, c.alignment);
     p.zero_padding = c.zero_padding;
     p.x_swizzle = x_swizzle;

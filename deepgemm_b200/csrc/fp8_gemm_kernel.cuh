@@ -75,7 +75,10 @@ struct GemmParams {
     uint64_t w_hint, x_hint;    // L2 cache policies of the weight / token TMA loads (ptx.cuh kEvict*)
     long long* debug_ts;        // optional (development): CTA 0 stamps clock64() at 10 points of its life
     uint32_t num_n_units;       // ceil(n / (128 * cluster))
-    uint32_t num_m_blocks;      // dense / contiguous: ceil(m / block_m)
+    uint32_t num_m_blocks;      // dense / contiguous: number of m-blocks
+    uint32_t num_tall, block_m_low;   // dense: the first `num_tall` m-blocks are block_m rows high, the others
+                                      // block_m_low (= block_m or block_m - 16): lets the host pick the m-block COUNT
+                                      // that fills whole waves of CTA pairs instead of the height (0: all block_m)
     uint32_t m_alignment;       // contiguous layouts: group start alignment (K alignment for k-grouped psum)
     uint32_t zero_padding;      // psum: write zeros to [end, aligned end)
     uint32_t x_swizzle;         // MN-major tokens: swizzle width in bytes (128 / 64 / 32) = rows of one TMA box
@@ -226,11 +229,16 @@ struct Scheduler {
 
             split(local, num_m, m_blk, n_unit);
             m_blk = m_blk * kPairs + (cta_rank >> 1);                        // this pair's m-block inside the group
+            uint32_t height = p.block_m;
             t.x_row = m_blk * p.block_m;
+            if (kGemmType == kDense && m_blk >= p.num_tall) {                // two tile heights (dense only)
+                height = p.block_m_low;
+                t.x_row = p.num_tall * p.block_m + (m_blk - p.num_tall) * p.block_m_low;
+            }
             t.d_row = t.x_row;
             t.sfx_col = t.x_row;
             t.sfx_row = 0;
-            t.valid_m = t.x_row < p.m ? min(p.block_m, p.m - t.x_row) : 0u;  // 0: a pair past the last m-block idles along
+            t.valid_m = t.x_row < p.m ? min(height, p.m - t.x_row) : 0u;     // 0: a pair past the last m-block idles along
             t.store_m = t.valid_m;
             t.counter_idx = m_blk * (num_n_units * kCtaGroup) + n_unit * kCtaGroup + (cta_rank & 1);
             if constexpr (kGemmType == kMContiguous) group = static_cast<uint32_t>(max(0, __ldg(p.grouped_layout + t.x_row)));

@@ -182,6 +182,28 @@ def test_dense_cluster_split_k_matches_oracle_and_is_deterministic(dg, m, n, k, 
     _assert_close_to_oracle(outs[0], d1, 'split vs unsplit')
 
 
+@pytest.mark.parametrize('m,n,k', [(4096, 4096, 512), (2000, 2112, 640), (1024, 7168, 256), (3333, 512, 384)])
+def test_dense_wave_balanced_tile_heights_give_identical_bits(dg, m, n, k, monkeypatch):
+    """Large dense problems pick the NUMBER of m-blocks that fills whole rounds of CTA pairs and use two tile heights
+    (block_m and block_m - 16). Heights are a scheduling matter only: same bits as uniform tiles."""
+    from deepgemm_b200 import _lib
+    _, _, qa, qb = _quant_dense(m, n, k, seed=k)
+    monkeypatch.setenv('DGB200_BALANCE', '0')
+    base = torch.empty((m, n), device='cuda', dtype=torch.bfloat16)
+    dg.fp8_gemm_nt(qa, qb, base)
+    uniform = _lib.last_config()
+    monkeypatch.setenv('DGB200_BALANCE', '1')
+    d = torch.full((m, n), float('nan'), device='cuda', dtype=torch.bfloat16)
+    dg.fp8_gemm_nt(qa, qb, d)
+    assert torch.equal(d, base), (uniform, _lib.last_config())
+    c = torch.randn((m, n), device='cuda', generator=torch.Generator(device='cuda').manual_seed(1)).to(torch.bfloat16)
+    d1, d2 = c.clone(), c.clone()
+    dg.fp8_gemm_nt(qa, qb, d1, c=d1)
+    monkeypatch.setenv('DGB200_BALANCE', '0')
+    dg.fp8_gemm_nt(qa, qb, d2, c=d2)
+    assert torch.equal(d1, d2)
+
+
 @pytest.mark.parametrize('out_dtype', [torch.bfloat16, torch.float32])
 def test_dense_accumulate_into_c(dg, out_dtype):
     from oracle import blockwise
