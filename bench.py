@@ -353,7 +353,7 @@ def run_ep(args, rank, world, device):
     # capacity: balanced routing + 25% head room + alignment padding (a production caller sizes for its worst case)
     capacity = (int(t_local * 1.25) + epr * align + 127) // 128 * 128
     buf = ep.EpBuffer(g, capacity, k)
-    d = torch.empty((capacity, n), device=device, dtype=torch.bfloat16)
+    d = buf.output(n)                      # symmetric (peer-mapped) output, so that the combine can be timed too
     token_row = torch.empty(t_local, dtype=torch.int32, device=device)
     overlap = os.environ.get('DGB200_EP_OVERLAP', '0') != '0'   # GEMM beside the scatter (per-expert arrival counters)
 
@@ -388,6 +388,23 @@ def run_ep(args, rank, world, device):
     total = allreduce_max(disp + gemm, world, device)
     disp, gemm = allreduce_max(disp, world, device), allreduce_max(gemm, world, device)
 
+    # the way back (top-1 combine: every source pulls its tokens' output rows over NVLink), timed on its own
+    out_tokens = torch.empty((t_local, n), device=device, dtype=torch.bfloat16)
+    step()
+    buf.combine(token_row, ids, out_tokens)
+    torch.cuda.synchronize()
+    barrier(world)
+    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    comb = 0.0
+    for _ in range(3):
+        step()
+        c0.record()
+        buf.combine(token_row, ids, out_tokens)
+        c1.record()
+        torch.cuda.synchronize()
+        comb += c0.elapsed_time(c1) / 3
+    combine_ms = allreduce_max(comb, world, device)
+
     # library baseline for the same dispatch: NCCL all-to-all + torch re-layout (outside the timed region)
     group = torch.distributed.group.WORLD if world > 1 else None
     def baseline():
@@ -420,7 +437,7 @@ def run_ep(args, rank, world, device):
                                'peer-memory dispatch (NVLink stores of FP8 rows + packed UE8M0 SFs into the owner\'s GEMM buffer)',
                    'parallelism': f'ep{world}', 'l2': 'inputs (>= 0.9 GB of expert weights per rank) exceed L2'},
         'dispatch_ms': round(disp, 4), 'gemm_ms': round(gemm, 4), 'dispatch_alltoall_baseline_ms': round(base_ms, 4),
-        'overlap': bool(overlap), 'overlap_note': 'with overlap the two phases share the GPU: dispatch_ms/gemm_ms are stream-event splits, only ms_per_step is meaningful',
+        'combine_ms': round(combine_ms, 4), 'overlap': bool(overlap), 'overlap_note': 'with overlap the two phases share the GPU: dispatch_ms/gemm_ms are stream-event splits, only ms_per_step is meaningful',
         'tflops': round(2.0 * tokens_total * n * k / (total * 1e-3) / 1e12, 1),
         'wire_bytes_per_rank': int(wire), 'remote_bytes_per_rank': int(remote), 'rows_received_rank0': buf_rows,
         'roofline': {'kernel': 'ep::scatter_kernel (+bucket/exchange/wait)', 'bound': 'hbm', 'achieved': round(gbs, 1),

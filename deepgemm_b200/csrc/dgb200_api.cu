@@ -802,6 +802,40 @@ int dgb200_m_grouped_fp8_gemm_nt_contiguous(const void* a, const int32_t* sfa, c
     return run_gemm(c);
 }
 
+int dgb200_ep_combine(void* out, int64_t ldo, const int32_t* token_row, const void* expert_ids, int id_bytes, int num_tokens,
+                      int n, int elt_bytes, int num_experts, int rank, int world, void* const* buffers,
+                      void* const* d_buffers, int64_t ldd, void* stream) {
+    if (int e = ensure_device()) return e;
+    DGB_REQUIRE(world > 0 && world <= static_cast<int>(ep::kMaxWorld) && rank >= 0 && rank < world);
+    DGB_REQUIRE(num_experts > 0 && num_experts % world == 0 && num_tokens >= 0 && n > 0);
+    DGB_REQUIRE(id_bytes == 4 || id_bytes == 8);
+    DGB_REQUIRE(elt_bytes == 2 || elt_bytes == 4);
+    DGB_REQUIRE(buffers != nullptr && d_buffers != nullptr);
+    DGB_REQUIRE(num_tokens == 0 || (out != nullptr && token_row != nullptr && expert_ids != nullptr));
+    DGB_REQUIRE((static_cast<int64_t>(n) * elt_bytes) % 16 == 0 && (ldo * elt_bytes) % 16 == 0 && (ldd * elt_bytes) % 16 == 0);
+    DGB_REQUIRE(ldo >= n && ldd >= n && (reinterpret_cast<uintptr_t>(out) & 15) == 0);
+    ep::Peers ctrl, dbufs;
+    for (int p = 0; p < world; ++p) {
+        DGB_REQUIRE(buffers[p] != nullptr && d_buffers[p] != nullptr && (reinterpret_cast<uintptr_t>(d_buffers[p]) & 15) == 0);
+        ctrl.base[p] = static_cast<uint8_t*>(buffers[p]);
+        dbufs.base[p] = static_cast<uint8_t*>(d_buffers[p]);
+    }
+    const auto s = static_cast<cudaStream_t>(stream);
+    ep::combine_publish_kernel<<<1, 32, 0, s>>>(ctrl, rank, world);
+    const int grid = std::max(1, std::min(ceil_div(std::max(num_tokens, 1), 8), rt().sm_count * 8));
+    if (id_bytes == 4)
+        ep::combine_gather_kernel<int32_t><<<grid, 256, 0, s>>>(ctrl, dbufs, expert_ids, token_row, static_cast<uint8_t*>(out),
+                                                                ldo * elt_bytes, ldd * elt_bytes, n * elt_bytes, num_tokens,
+                                                                num_experts, rank, world);
+    else
+        ep::combine_gather_kernel<int64_t><<<grid, 256, 0, s>>>(ctrl, dbufs, expert_ids, token_row, static_cast<uint8_t*>(out),
+                                                                ldo * elt_bytes, ldd * elt_bytes, n * elt_bytes, num_tokens,
+                                                                num_experts, rank, world);
+    DGB_CUDA(cudaGetLastError());
+    g_launch_count.fetch_add(2, std::memory_order_relaxed);
+    return DGB200_OK;
+}
+
 int dgb200_ep_grouped_gemm(void* local_buffer, int world, int num_experts, int capacity, int k, const void* b,
                            const int32_t* sfb, void* d, int n, int64_t ldb, int64_t ldd, int major_b, int sfb_stride,
                            int gran_k_b, int expected_m, int overlap_dispatch, void* stream) {

@@ -37,6 +37,7 @@ struct Control {
     uint32_t pad[27];
     uint32_t counts_flag[kMaxWorld * 8];   // [s*8]: epoch of the counts source rank s published here (32 B apart)
     uint32_t data_flag[kMaxWorld * 8];     // [s*8]: epoch of the rows source rank s finished writing here
+    uint32_t gemm_flag[kMaxWorld * 8];     // [o*8]: epoch of the grouped GEMM owner rank o has finished (combine)
 };
 
 struct Peers {
@@ -356,6 +357,51 @@ wait_kernel(uint8_t* mine, uint32_t world) {
     if (threadIdx.x < world) wait_flag(&ctrl->data_flag[threadIdx.x * 8], epoch);
     __syncwarp();
     __threadfence_system();
+}
+
+// ---------------------------------------------------------------------------------------------- combine (top-1 routing)
+// The way back: every token's output row sits in its expert owner's D buffer [capacity, n] (peer mapped); the source
+// rank pulls it over NVLink into token order. `publish` runs after the owner's grouped GEMM in stream order.
+__global__ void __launch_bounds__(32)
+combine_publish_kernel(Peers ctrl_bufs, uint32_t rank, uint32_t world) {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    const uint32_t epoch = reinterpret_cast<const Control*>(ctrl_bufs.base[rank])->epoch;
+    __threadfence_system();                      // (kernel boundary already ordered the GEMM's stores; belt and braces)
+    if (threadIdx.x < world)
+        st_release_sys(&reinterpret_cast<Control*>(ctrl_bufs.base[threadIdx.x])->gemm_flag[rank * 8], epoch);
+}
+
+// One warp per local token: out[t, :] = D_owner[token_row[t], :] (16-byte loads from the owner's memory), zeros for
+// tokens that were not routed / dropped. grid: persistent, any size.
+template <typename id_t>
+__global__ void __launch_bounds__(256)
+combine_gather_kernel(Peers ctrl_bufs, Peers d_bufs, const void* __restrict__ ids, const int32_t* __restrict__ token_row,
+                      uint8_t* __restrict__ out, int64_t ldo_bytes, int64_t ldd_bytes, uint32_t row_bytes,
+                      uint32_t num_tokens, uint32_t num_experts, uint32_t rank, uint32_t world) {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    const Control* ctrl = reinterpret_cast<const Control*>(ctrl_bufs.base[rank]);
+    const uint32_t epoch = ctrl->epoch;
+    if (threadIdx.x < world) wait_flag(&ctrl->gemm_flag[threadIdx.x * 8], epoch);   // every owner's GEMM of this step is done
+    __syncthreads();
+    const uint32_t epr = num_experts / world;
+    const uint32_t lane = threadIdx.x % 32, warps_per_cta = blockDim.x / 32;
+    const uint32_t chunks = row_bytes / 16;
+    for (uint32_t t = blockIdx.x * warps_per_cta + threadIdx.x / 32; t < num_tokens; t += gridDim.x * warps_per_cta) {
+        const int32_t row = __ldg(token_row + t);
+        uint4* dst = reinterpret_cast<uint4*>(out + static_cast<int64_t>(t) * ldo_bytes);
+        if (row < 0) {
+            for (uint32_t c = lane; c < chunks; c += 32) dst[c] = make_uint4(0u, 0u, 0u, 0u);
+            continue;
+        }
+        const uint32_t owner = static_cast<uint32_t>(load_id<id_t>(ids, t)) / epr;
+        const uint4* src = reinterpret_cast<const uint4*>(d_bufs.base[owner] + static_cast<int64_t>(row) * ldd_bytes);
+        uint32_t c = lane;
+        for (; c + 96 < chunks; c += 128) {
+            const uint4 v0 = __ldcv(src + c), v1 = __ldcv(src + c + 32), v2 = __ldcv(src + c + 64), v3 = __ldcv(src + c + 96);
+            dst[c] = v0, dst[c + 32] = v1, dst[c + 64] = v2, dst[c + 96] = v3;
+        }
+        for (; c < chunks; c += 32) dst[c] = __ldcv(src + c);
+    }
 }
 
 }  // namespace ep

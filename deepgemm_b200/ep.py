@@ -202,6 +202,7 @@ class EpBuffer:
         self.counts = b[self.off_counts:self.off_counts + 4 * num_experts].view(torch.int32)
         self._ctrl = b[:64].view(torch.int32)
         self._order = None
+        self._out = None            # (n, local ptr, peer ptr array, tensor view): symmetric grouped-GEMM output for combine()
 
     # device-side scalars (reading them synchronises; the data path never does)
     def num_rows(self) -> int:
@@ -252,6 +253,61 @@ class EpBuffer:
             ldb, d.stride(0), 0 if k_major else 1, sfb.stride(-1), 128, int(expected_m), int(overlap),
             torch.cuda.current_stream().cuda_stream))
 
+    def _share(self, ptr: int):
+        """Exchange the CUDA IPC handle of a library allocation and map every peer's copy; returns the pointer list."""
+        import ctypes
+        ptrs = [None] * self.world
+        ptrs[self.rank] = ptr
+        if self.world > 1:
+            handle = (ctypes.c_ubyte * 64)()
+            self._check(self._lib.dgb200_ep_export(ptr, handle))
+            mine = torch.tensor(list(handle), dtype=torch.uint8, device=self.device)
+            every = torch.empty(self.world * 64, dtype=torch.uint8, device=self.device)
+            dist.all_gather_into_tensor(every, mine, group=self.group)
+            every = every.cpu().view(self.world, 64)
+            for p in range(self.world):
+                if p == self.rank:
+                    continue
+                raw = (ctypes.c_ubyte * 64)(*every[p].tolist())
+                out = ctypes.c_void_p()
+                self._check(self._lib.dgb200_ep_import(raw, ctypes.byref(out)))
+                ptrs[p] = out.value
+            dist.barrier(group=self.group)
+        return ptrs
+
+    def output(self, n: int) -> torch.Tensor:
+        """The symmetric (peer-mapped) grouped-GEMM output D [capacity, n] bf16 that `combine` gathers from. Collective
+        on first use (allocation + handle exchange); pass it as `d` to grouped_gemm / expert_sharded_grouped_gemm."""
+        import ctypes
+        if self._out is not None:
+            assert self._out[0] == n, 'one output width per EpBuffer'
+            return self._out[3]
+        nbytes = self.capacity * n * 2
+        with torch.cuda.device(self.device):
+            ptr = ctypes.c_void_p()
+            self._check(self._lib.dgb200_ep_alloc(nbytes, ctypes.byref(ptr)))
+            ptrs = self._share(ptr.value)
+        view = torch.as_tensor(_RawCuda(ptr.value, nbytes), device=self.device).view(torch.bfloat16).view(self.capacity, n)
+        self._out = (n, ptr.value, (ctypes.c_void_p * self.world)(*ptrs), view, ptrs)
+        return view
+
+    def combine(self, token_row: torch.Tensor, expert_ids: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """The way back (top-1 routing): out[t] = D_owner(t)[token_row[t]], zeros for unrouted tokens. Enqueue on the
+        stream that ran this rank's grouped GEMM into `self.output(n)`; every rank calls it once per dispatch."""
+        assert self._out is not None, 'run the grouped GEMM into EpBuffer.output(n) first'
+        n = self._out[0]
+        t = token_row.numel()
+        assert token_row.dtype == torch.int32 and token_row.is_contiguous()
+        assert expert_ids.dtype in (torch.int32, torch.int64) and expert_ids.is_contiguous() and expert_ids.numel() == t
+        if out is None:
+            out = torch.empty((t, n), dtype=torch.bfloat16, device=token_row.device)
+        assert out.shape == (t, n) and out.dtype == torch.bfloat16 and out.stride(1) == 1
+        self._check(self._lib.dgb200_ep_combine(
+            out.data_ptr(), out.stride(0) if t > 1 else n, token_row.data_ptr(), expert_ids.data_ptr(), expert_ids.element_size(), t, n, 2,
+            self.num_experts, self.rank, self.world, self._ptr_array, self._out[2], n,
+            torch.cuda.current_stream().cuda_stream))
+        return out
+
     def close(self) -> None:
         if getattr(self, 'ptr', None) is None:
             return
@@ -261,6 +317,13 @@ class EpBuffer:
         for p, ptr in enumerate(self.peer_ptrs):
             if p != self.rank and ptr is not None:
                 self._lib.dgb200_ep_unimport(ptr)
+        if self._out is not None:
+            for p, ptr in enumerate(self._out[4]):
+                if p != self.rank and ptr is not None:
+                    self._lib.dgb200_ep_unimport(ptr)
+            view_ptr = self._out[1]
+            self._out = None
+            self._lib.dgb200_ep_free(view_ptr)
         self.a = self.sfa = self.psum_layout = self.counts = self._ctrl = self._bytes = None
         self._lib.dgb200_ep_free(self.ptr)
         self.ptr = None

@@ -177,6 +177,17 @@ int dgb200_ep_grouped_gemm(void* local_buffer, int world, int num_experts, int c
                            const int32_t* sfb, void* d, int n, int64_t ldb, int64_t ldd, int major_b, int sfb_stride,
                            int gran_k_b, int expected_m, int overlap_dispatch, void* stream);
 
+/* The way back (top-1 routing): out[t, 0:n] = D_owner(t)[token_row[t], 0:n] for every local token, zeros where
+ * token_row[t] < 0. `d_buffers[p]` = rank p's grouped-GEMM output [capacity, n] (pitch ldd elements, elt_bytes 2 or 4)
+ * as addressable from this device (peer mapped, e.g. dgb200_ep_alloc + _export/_import); `buffers` = the dispatch
+ * buffers (their control blocks carry the handshake). Enqueue on the stream that ran this rank's grouped GEMM: a first
+ * kernel tells every peer that this rank's D is complete, the gather waits for every owner's message, then pulls the
+ * rows over NVLink. All ranks must call it once per dispatch. D may be overwritten again after the next
+ * dgb200_ep_dispatch has returned control to the stream (its count exchange orders the two). */
+int dgb200_ep_combine(void* out, int64_t ldo, const int32_t* token_row, const void* expert_ids, int id_bytes, int num_tokens,
+                      int n, int elt_bytes, int num_experts, int rank, int world, void* const* buffers,
+                      void* const* d_buffers, int64_t ldd, void* stream);
+
 /* ---- introspection (bench / tests) -------------------------------------------------------------------------- */
 typedef struct dgb200_config {
     int block_m;     /* token rows per tile */

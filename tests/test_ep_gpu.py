@@ -106,6 +106,47 @@ def test_expert_sharded_grouped_gemm_world1_matches_oracle(dg, overlap):
         buf.close()
 
 
+def test_combine_world1_returns_every_token_its_row(dg):
+    from deepgemm_b200 import ep
+    from deepgemm_b200.utils import per_block_cast_to_fp8, per_token_cast_to_fp8
+    dev = torch.device('cuda', 0)
+    g, n, k, t = 8, 384, 512, 1000
+    gen = torch.Generator(device=dev).manual_seed(9)
+    align = dg.get_mk_alignment_for_contiguous_layout()
+    w = torch.randn((g, n, k), device=dev, dtype=torch.bfloat16, generator=gen)
+    qs = [per_block_cast_to_fp8(w[i], True) for i in range(g)]
+    wq = (torch.stack([q[0] for q in qs]), torch.stack([q[1] for q in qs]))
+    x = torch.randn((t, k), device=dev, dtype=torch.bfloat16, generator=gen)
+    xq, sf_packed = per_token_cast_to_fp8(x, True, 128, use_packed_ue8m0=True)
+    ids = torch.randint(0, g, (t,), device=dev, generator=gen)
+    ids[::11] = -1
+    buf = ep.EpBuffer(g, t + g * align, k)
+    try:
+        d = buf.output(n)
+        for _ in range(2):                                     # twice: epochs, buffer reuse
+            d.fill_(float('nan'))
+            _, r = ep.expert_sharded_grouped_gemm(xq, sf_packed, ids, wq, buf, d)
+            out = buf.combine(r.token_row, ids)
+            torch.cuda.synchronize()
+            routed = ids >= 0
+            assert torch.equal(out[routed], d[r.token_row[routed].long()])
+            assert bool((out[~routed] == 0).all()) and not bool(torch.isnan(out.float()).any())
+            # and the rows are the right answers: same as running every token through its expert densely
+            for e in range(g):
+                sel = ids == e
+                if bool(sel.any()):
+                    ref = torch.empty((int(sel.sum()), n), device=dev, dtype=torch.bfloat16)
+                    _, sf_fp32 = per_token_cast_to_fp8(x[sel], True, 128)
+                    dg.set_split_k(False)
+                    try:
+                        dg.fp8_gemm_nt((xq[sel].contiguous(), sf_fp32), (wq[0][e], wq[1][e]), ref)
+                    finally:
+                        dg.set_split_k(True)
+                    assert torch.equal(out[sel], ref)
+    finally:
+        buf.close()
+
+
 def test_multi_gpu_peer_dispatch_under_torchrun(dg):
     n = torch.cuda.device_count()
     if n < 2:

@@ -65,7 +65,25 @@ def main():
         assert ok_rows == ref.num_recv
         return ok_rows
 
-    d = torch.empty((capacity, n), dtype=torch.bfloat16, device=dev)
+    d = buf.output(n)                       # symmetric: combine() gathers from it
+    # every rank can rebuild every expert's weights (seeded by the owner's rank) to check what combine brings back
+    w_all = []
+    for o in range(world):
+        go = torch.Generator(device=dev).manual_seed(1 + o)
+        wo = torch.randn((epr, n, k), device=dev, dtype=torch.bfloat16, generator=go)
+        w_all.append([per_block_cast_to_fp8(wo[i], True) for i in range(epr)])
+
+    def check_combine(xq, sf, ids, r, tag):
+        out = buf.combine(r.token_row, ids)
+        torch.cuda.synchronize()
+        sfx = (sf.contiguous().view(torch.uint8).to(torch.int32) << 23).view(torch.float32)
+        x_deq = xq.float() * sfx[:, :k // 128].repeat_interleave(128, 1)
+        for e in ids.unique().tolist():
+            sel = ids == e
+            wq_e, sw_e = w_all[e // epr][e % epr]
+            w_deq = wq_e.float() * sw_e.repeat_interleave(128, 0).repeat_interleave(128, 1)
+            diff = calc_diff(out[sel], x_deq[sel] @ w_deq.t())
+            assert diff < 1e-5, (rank, e, diff, tag)
     total = 0
     for it in range(4):
         x = torch.randn((t_local, k), device=dev, dtype=torch.bfloat16, generator=gen)
@@ -77,6 +95,7 @@ def main():
         d.fill_(float('nan'))
         _, r = ep.expert_sharded_grouped_gemm(xq, sf, ids, wq, buf, d, overlap=(it % 2 == 0))
         total += check(xq, sf, ids.long(), d, r, f'iter {it}')
+        check_combine(xq, sf, ids.long() if ids.dtype != torch.int64 else ids, r, f'combine {it}')
 
     # (d) CUDA graph: capture dispatch + GEMM once, replay with new inputs
     sx, ssf, sids = torch.empty_like(xq), torch.empty_like(sf), torch.empty(t_local, dtype=torch.int64, device=dev)
