@@ -992,7 +992,6 @@ int dgb200_ep_dispatch(const void* x, int64_t ldx, const int32_t* sf, int64_t sf
                        const void* expert_ids, int id_bytes, int num_tokens, int k, int num_experts, int rank, int world,
                        void* const* buffers, int capacity, int alignment, int32_t* token_row, int32_t* order_scratch,
                        int wait_for_all, void* stream) {
-    if (int e = ensure_device()) return e;
     DGB_REQUIRE(world > 0 && world <= static_cast<int>(ep::kMaxWorld) && rank >= 0 && rank < world);
     DGB_REQUIRE(num_experts > 0 && num_experts <= static_cast<int>(ep::kMaxExperts) && num_experts % world == 0);
     DGB_REQUIRE(num_tokens >= 0 && capacity > 0 && alignment > 0);
@@ -1001,6 +1000,7 @@ int dgb200_ep_dispatch(const void* x, int64_t ldx, const int32_t* sf, int64_t sf
     DGB_REQUIRE(buffers != nullptr && token_row != nullptr && (wait_for_all || num_tokens == 0 || order_scratch != nullptr));
     DGB_REQUIRE(num_tokens == 0 || (x != nullptr && sf != nullptr && expert_ids != nullptr));
     DGB_REQUIRE(ldx % 16 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0);
+    if (int e = ensure_device()) return e;
     ep::Peers peers;
     for (int p = 0; p < world; ++p) {
         DGB_REQUIRE(buffers[p] != nullptr);

@@ -18,6 +18,10 @@
 //  * Scale factors arrive in the reference's documented wire format (packed UE8M0 int32, MN-major,
 //    csrc/utils/layout.hpp:100-107) so user-packed tensors keep working; a helper warp re-tiles each 128-word
 //    group into the `tcgen05.cp` 32x128b layout before the MMA warp copies it into TMEM.
+//  * Things only run-time shapes allow: the UMMA N of every tile follows its valid rows (`tile_n`), dense problems
+//    use two tile heights so that the m-block COUNT fills whole rounds of CTA pairs, and small-M problems cut K
+//    across a cluster of single-CTA MMAs that reduce through distributed shared memory (`kCSplit`).
+//  * The TMA producer free-runs ahead of the setup barriers (its first loads need nothing the other warps set up).
 //
 // Warp roles (384 threads): w0 TMA producer | w1 MMA issuer (leader CTA) | w2 TMEM alloc + SF re-tiler |
 //                           w3 idle | w4-11 epilogue (TMEM -> registers -> global; two warps per lane quadrant,

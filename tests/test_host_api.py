@@ -163,3 +163,34 @@ def test_gemm_kernels_keep_tma_operands_in_uniform_registers():
     bad = [k.split('\n', 1)[0] for k in gemm if 'R2UR.BROADCAST' in k]
     assert not bad, bad[:3]
     assert all('UTMALDG' in k and ('UTCQMMA' in k or 'UTCOMMA' in k or 'UTCHMMA' in k or 'UTCMMA' in k or 'UTC' in k) for k in gemm)
+
+
+def test_ep_buffer_layout_and_argument_checks(lib):
+    """Host side of the expert-parallel entry points (no GPU): the layout is a pure function, regions are ordered,
+    aligned and large enough; bad arguments are rejected with the library's error text."""
+    import ctypes
+    L = lib.lib()
+    world, g, cap, k = 4, 256, 10240, 7168
+    total = L.dgb200_ep_buffer_bytes(world, g, cap, k)
+    offs = (ctypes.c_int64 * 6)()
+    assert L.dgb200_ep_buffer_offsets(world, g, cap, k, offs) == 0
+    a, sfa, psum, counts, rows, overflow = list(offs)
+    assert 0 < rows < overflow < 256 < psum and psum % 1024 == 0 and counts % 1024 == 0
+    assert sfa % 1024 == 0 and a % 1024 == 0 and sfa + 4 * ((k + 511) // 512) * cap <= a and a + cap * k <= total
+    assert total < a + cap * k + 4096
+    assert L.dgb200_ep_buffer_bytes(0, g, cap, k) == 0
+    bufs = (ctypes.c_void_p * world)(*([4096] * world))
+    # experts must divide over the ranks; K must be a multiple of 16; ids are int32 or int64
+    for bad in (dict(g=255), dict(k=7170), dict(idb=2)):
+        rc = L.dgb200_ep_dispatch(4096, k, 4096, 14, 1, 4096, bad.get('idb', 8), 16, bad.get('k', k), bad.get('g', g), 0, world,
+                                  bufs, cap, 128, 4096, 4096, 1, None)
+        assert rc != 0 and b'Assertion error' in L.dgb200_last_error()
+
+
+def test_dense_plan_balances_rounds_of_cta_pairs(lib):
+    """M = N = 4096 on 74 CTA pairs: 240-row tiles are 288 tiles = 3.89 rounds; the planner picks 23 m-blocks (368 tiles,
+    4.97 rounds) of 192 / 176 rows instead."""
+    cfg = lib.plan(0, 4096, 4096, 7168)
+    assert cfg['block_m'] == 192 and cfg['cluster'] == 2 and cfg['num_splits'] == 1
+    small = lib.plan(0, 512, 4096, 7168)
+    assert small['block_m'] == 128                       # below 1024 rows the tile height is chosen by the cost model alone
