@@ -994,7 +994,7 @@ int dgb200_ep_dispatch(const void* x, int64_t ldx, const int32_t* sf, int64_t sf
                        int wait_for_all, void* stream) {
     DGB_REQUIRE(world > 0 && world <= static_cast<int>(ep::kMaxWorld) && rank >= 0 && rank < world);
     DGB_REQUIRE(num_experts > 0 && num_experts <= static_cast<int>(ep::kMaxExperts) && num_experts % world == 0);
-    DGB_REQUIRE(num_tokens >= 0 && capacity > 0 && alignment > 0);
+    DGB_REQUIRE(num_tokens >= 0 && capacity > 0 && capacity % 4 == 0 && alignment > 0);   // SF pitch = capacity words (TMA: 16 B)
     DGB_REQUIRE(k > 0 && k % 16 == 0 && ceil_div(k, 512) <= 32);
     DGB_REQUIRE(id_bytes == 4 || id_bytes == 8);
     DGB_REQUIRE(buffers != nullptr && token_row != nullptr && (wait_for_all || num_tokens == 0 || order_scratch != nullptr));

@@ -163,6 +163,7 @@ class EpBuffer:
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.group = group
         self.device = torch.device('cuda', torch.cuda.current_device()) if device is None else device
+        capacity = (capacity + 15) // 16 * 16        # the scale-factor rows have a pitch of `capacity` words: TMA wants 16 B
         self.num_experts, self.capacity, self.k = num_experts, capacity, k
         self.kp = _ceil_div(k, 512)
         self.alignment = runtime.get_mk_alignment_for_contiguous_layout()

@@ -159,7 +159,7 @@ int dgb200_ep_unimport(void* ptr);
 /* x [num_tokens, k] e4m3 rows (pitch ldx bytes), sf: packed UE8M0 words of token t at sf[t*sf_stride_t + j*sf_stride_k],
  * j < ceil(k/512); expert_ids int32 (id_bytes 4) or int64 (id_bytes 8), values outside [0, num_experts) = not routed.
  * token_row int32[num_tokens] (out): row of each token inside its owner's buffer (-1: not routed / dropped on
- * overflow, which also sets the word at DGB200_EP_OFF_OVERFLOW). k % 16 == 0, ceil(k/512) <= 32.
+ * overflow, which also sets the word at DGB200_EP_OFF_OVERFLOW). k % 16 == 0, ceil(k/512) <= 32, capacity % 4 == 0.
  * wait_for_all != 0 appends the kernel that returns once every source's rows have landed (then any consumer may
  * follow in stream order); 0 leaves that to a consumer that watches the per-expert arrival counters itself
  * (dgb200_ep_grouped_gemm with overlap_dispatch). Tokens are sent in expert order, so experts complete one by one. */
