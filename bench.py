@@ -54,24 +54,53 @@ def committed_traffic(key):
 
 # ------------------------------------------------------------------------------------------------ clocks
 class ClockSampler:
-    """Samples `nvidia-smi` SM clocks / throttle reasons while the timed region runs."""
+    """Samples SM clocks / throttle reasons while the timed region runs: NVML in-process every ~2 ms (the timed region of
+    the default run lasts ~10 ms, one `nvidia-smi` fork takes longer than that); falls back to forking nvidia-smi."""
     QUERY = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
              'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
              'clocks_event_reasons.sw_power_cap')
 
     def __init__(self, index=0):
         self.index, self.rows, self._stop, self._t = index, [], threading.Event(), None
+        self._nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            visible = os.environ.get('CUDA_VISIBLE_DEVICES')
+            phys = int(visible.split(',')[index]) if visible and visible.split(',')[index].isdigit() else index
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self._max = float(pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM))
+            self._nvml = pynvml
+        except Exception:  # noqa: BLE001
+            self._nvml = None
+
+    def _sample_nvml(self):
+        n = self._nvml
+        sm = float(n.nvmlDeviceGetClockInfo(self._h, n.NVML_CLOCK_SM))
+        try:
+            mask = n.nvmlDeviceGetCurrentClocksEventReasons(self._h)
+        except Exception:  # noqa: BLE001
+            mask = n.nvmlDeviceGetCurrentClocksThrottleReasons(self._h)
+        flag = lambda bit: 'Active' if mask & bit else 'Not Active'   # noqa: E731
+        try:
+            watts = n.nvmlDeviceGetPowerUsage(self._h) / 1000.0
+        except Exception:  # noqa: BLE001
+            watts = 0.0
+        return [str(sm), str(self._max), f'{watts:.0f}', flag(0x8), flag(0x40), flag(0x20), flag(0x4)]
 
     def _run(self):
         while not self._stop.is_set():
             try:
-                out = subprocess.run(['nvidia-smi', f'--query-gpu={self.QUERY}', '--format=csv,noheader,nounits',
-                                      '-i', str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([c.strip() for c in out.split(',')])
+                if self._nvml is not None:
+                    self.rows.append(self._sample_nvml())
+                else:
+                    out = subprocess.run(['nvidia-smi', f'--query-gpu={self.QUERY}', '--format=csv,noheader,nounits',
+                                          '-i', str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
+                    if out:
+                        self.rows.append([c.strip() for c in out.split(',')])
             except Exception:  # noqa: BLE001
                 pass
-            self._stop.wait(0.1)
+            self._stop.wait(0.002 if self._nvml is not None else 0.1)
 
     def __enter__(self):
         self._t = threading.Thread(target=self._run, daemon=True)
@@ -90,8 +119,10 @@ class ClockSampler:
                 if v.lower().startswith('active'):
                     reasons.add(name)
         mx = max((float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace('.', '').isdigit()), default=None)
-        return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': mx, 'reasons': sorted(reasons),
-                'samples': len(self.rows)}
+        watts = sorted(float(r[2]) for r in self.rows if len(r) > 2 and r[2].replace('.', '').isdigit())
+        return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_min_mhz': sm[0] if sm else None, 'sm_max_mhz': mx,
+                'reasons': sorted(reasons), 'samples': len(self.rows), 'power_w_median': watts[len(watts) // 2] if watts else None,
+                'source': 'nvml' if self._nvml is not None else 'nvidia-smi'}
 
 
 # ------------------------------------------------------------------------------------------------ workloads
