@@ -923,7 +923,9 @@ int dgb200_plan(int gemm_type, int m, int n, int k, int num_groups, int expected
     if (gemm_type == kDense && n % 4 == 0) pb.max_splits = kMaxSplits;   // as if a workspace were supplied
     const Config cfg = choose_config(pb, num_sms);
     const int n_units = ceil_div(n, (int)kBlockN * (cfg.csplit ? 1 : std::min(cfg.cluster, 2)));
-    const int m_blocks = gemm_type == kMMasked ? num_groups * ceil_div(pb.expected_m, cfg.block_m) : ceil_div(m, cfg.block_m);
+    int m_blocks = gemm_type == kMMasked ? num_groups * ceil_div(pb.expected_m, cfg.block_m) : ceil_div(m, cfg.block_m);
+    if (gemm_type == kDense && cfg.block_m_low > 0)   // two tile heights (wave balancing)
+        m_blocks = cfg.num_tall + ceil_div(std::max(0, m - cfg.num_tall * cfg.block_m), cfg.block_m_low);
     *out = dgb200_config{cfg.block_m, cfg.cluster, cfg.stages, cfg.num_sms, cfg.smem_bytes, m_blocks * n_units * cfg.num_splits,
                          cfg.num_splits, cfg.csplit};
     return DGB200_OK;

@@ -192,5 +192,6 @@ def test_dense_plan_balances_rounds_of_cta_pairs(lib):
     4.97 rounds) of 192 / 176 rows instead."""
     cfg = lib.plan(0, 4096, 4096, 7168)
     assert cfg['block_m'] == 192 and cfg['cluster'] == 2 and cfg['num_splits'] == 1
+    assert cfg['num_tiles'] == 23 * 16                  # 3 x 192 + 20 x 176 rows = 4096, times 16 column pairs
     small = lib.plan(0, 512, 4096, 7168)
     assert small['block_m'] == 128                       # below 1024 rows the tile height is chosen by the cost model alone
