@@ -54,6 +54,10 @@ if __name__ == '__main__':
         cfgs = [{}] + [dict(block_m=bm, swizzle_group=sg) for bm in (128, 160, 192, 208, 224, 240) for sg in (4, 8, 16)]
         cfgs += [dict(block_m=bm, stages=st) for bm in (224, 240) for st in (4, 5)]
         run([(4096, 7168, 2048), (4096, 4096, 7168)], cfgs)
+    elif mode == 'mid':
+        cfgs = [{}] + [dict(block_m=bm, csplit=0) for bm in (48, 64, 96, 128, 160, 192, 240)]
+        run([(192, 4096, 7168), (256, 4096, 7168), (384, 4096, 7168), (768, 4096, 7168), (1024, 4096, 7168), (256, 7168, 2048),
+             (512, 7168, 2048), (1024, 7168, 2048)], cfgs)
     elif mode == 'small':
         cfgs = [{}, dict(csplit=0), dict(csplit=4), dict(csplit=2)] + [dict(csplit=0, block_m=bm) for bm in (16, 32, 64)]
         run([(1, 2112, 7168), (16, 4096, 7168), (32, 4096, 7168), (64, 4096, 7168), (96, 4096, 7168), (128, 4096, 7168), (192, 4096, 7168),
