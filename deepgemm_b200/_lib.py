@@ -11,33 +11,58 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _REPO = os.path.dirname(_HERE)
 LIB_PATH = os.environ.get('DGB200_LIB') or os.path.join(_HERE, 'lib', 'libdgb200.so')   # env: development only
-SOURCES = [os.path.join(_HERE, 'csrc', f) for f in
-           ('dgb200_api.cu', 'fp8_gemm_kernel.cuh', 'ptx.cuh', 'sf_layout.cuh')] + [os.path.join(_REPO, 'include', 'dgb200.h')]
+_CSRC = os.path.join(_HERE, 'csrc')
+# translation units (host API first, then the kernel-instance units) and every header they include: a change to any
+# header rebuilds everything, a change to one unit rebuilds that unit
+UNITS = [os.path.join(_CSRC, 'dgb200_api.cu')] + sorted(
+    os.path.join(_CSRC, f) for f in os.listdir(_CSRC) if f.startswith('gemm_') and f.endswith('.cu'))
+SOURCES = UNITS + sorted(os.path.join(_CSRC, f) for f in os.listdir(_CSRC) if f.endswith(('.cuh', '.h'))) + \
+    [os.path.join(_REPO, 'include', 'dgb200.h')]
 
-NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
-              '--expt-relaxed-constexpr', '-shared', '-Xcompiler', '-fPIC']
+COMPILE_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
+                 '--expt-relaxed-constexpr', '-Xcompiler', '-fPIC']
+NVCC_FLAGS = COMPILE_FLAGS + ['-shared']   # (kept for tools that compile a single file)
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
-    """Compile the AOT library for sm_100a with nvcc (cross-compiles without a GPU)."""
+    """Compile the AOT library for sm_100a with nvcc (cross-compiles without a GPU). The kernel instances live in
+    several translation units (csrc/gemm_*.cu) that are compiled in parallel, then linked into one shared object."""
+    from concurrent.futures import ThreadPoolExecutor
     if not force and os.path.exists(LIB_PATH):
         newest = max(os.path.getmtime(s) for s in SOURCES if os.path.exists(s))
         if os.path.getmtime(LIB_PATH) >= newest:
             return LIB_PATH
     os.makedirs(os.path.dirname(LIB_PATH), exist_ok=True)
     nvcc = os.path.join(os.environ.get('CUDA_HOME', '/usr/local/cuda'), 'bin', 'nvcc')
-    cmd = [nvcc] + NVCC_FLAGS + (['-Xptxas', '-v'] if verbose else []) + ['-o', LIB_PATH, SOURCES[0], '-lcudart']
+    obj_dir = os.path.join(os.path.dirname(LIB_PATH), 'obj')
+    os.makedirs(obj_dir, exist_ok=True)
+    headers = [s for s in SOURCES if not s.endswith('.cu')]
+    newest_header = max(os.path.getmtime(h) for h in headers)
+
+    def compile_one(src: str) -> str:
+        obj = os.path.join(obj_dir, os.path.basename(src)[:-3] + '.o')
+        if not force and os.path.exists(obj) and os.path.getmtime(obj) >= max(os.path.getmtime(src), newest_header):
+            return obj
+        cmd = [nvcc] + COMPILE_FLAGS + (['-Xptxas', '-v'] if verbose else []) + ['-c', src, '-o', obj]
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        if res.returncode != 0:
+            raise RuntimeError(f'nvcc failed:\n{" ".join(cmd)}\n{res.stdout}\n{res.stderr}')
+        if verbose:
+            print(res.stderr)
+        return obj
+
+    with ThreadPoolExecutor(max_workers=min(len(UNITS), os.cpu_count() or 1)) as pool:
+        objs = list(pool.map(compile_one, UNITS))
+    cmd = [nvcc, '-shared', '-o', LIB_PATH] + objs + ['-lcudart']
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
-        raise RuntimeError(f'nvcc failed:\n{" ".join(cmd)}\n{res.stdout}\n{res.stderr}')
-    if verbose:
-        print(res.stderr)
+        raise RuntimeError(f'link failed:\n{" ".join(cmd)}\n{res.stdout}\n{res.stderr}')
     return LIB_PATH
 
 
 class _Config(ctypes.Structure):
     _fields_ = [(n, ctypes.c_int) for n in ('block_m', 'cluster', 'num_stages', 'num_sms', 'smem_bytes', 'num_tiles',
-                                            'num_splits', 'cluster_split')]
+                                            'num_splits', 'cluster_split', 'tma_store')]
 
 
 _P, _I, _L = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64
@@ -63,6 +88,10 @@ SIGNATURES = {
     'dgb200_pack_sf_ue8m0_k_grouped': (_I, [_P, _P, _I, _P, _I, _I, _I, _I, _P]),
     'dgb200_fp8_gemm_nt': (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _L, _L, _L, _I, _I, _I, _I, _I, _I, _I, _I, _P, _L, _P]),
     'dgb200_workspace_bytes': (_L, [_I, _I]),
+    'dgb200_fp8_gemm_nt_skip_head_mid': (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _L, _L, _L, _I, _I, _I, _I, _I, _I, _P]),
+    'dgb200_fp8_bmm': (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _L, _L, _L, _L, _L, _L, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
+    'dgb200_per_token_cast_to_fp8': (_I, [_P, _L, _P, _L, _P, _I, _I, _I, _I, _P]),
+    'dgb200_debug_fp8_peak': (_I, [_I, _I, _I, _P]),
     'dgb200_m_grouped_fp8_gemm_nt_contiguous': (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _L, _L, _L, _I, _I, _I,
                                                      _I, _I, _I, _I, _I, _P]),
     'dgb200_m_grouped_fp8_gemm_nt_masked': (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P]),

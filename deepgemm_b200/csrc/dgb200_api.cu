@@ -21,42 +21,22 @@
 #include <unordered_map>
 #include <vector>
 
-#include "../../include/dgb200.h"
-#include "fp8_gemm_kernel.cuh"
+#include "launch.cuh"
 #include "sf_layout.cuh"
 #include "ep_dispatch.cuh"
+#include "quant.cuh"
+#include "peak_probe.cuh"
 
 namespace dgb200 {
 namespace {
 
 // ------------------------------------------------------------------------------------------------ errors
 thread_local std::string g_last_error;
-thread_local dgb200_config g_last_config = {0, 0, 0, 0, 0, 0, 0, 0};
+thread_local dgb200_config g_last_config = {0, 0, 0, 0, 0, 0, 0, 0, 0};
 std::atomic<int64_t> g_launch_count{0};
 std::atomic<long long*> g_debug_ts{nullptr};
 
-int fail(int code, const char* fmt, ...) {
-    char buf[1024];
-    va_list ap;
-    va_start(ap, fmt);
-    vsnprintf(buf, sizeof(buf), fmt, ap);
-    va_end(ap);
-    g_last_error = buf;
-    return code;
-}
-
-#define DGB_REQUIRE(cond)                                                                                     \
-    do {                                                                                                      \
-        if (!(cond))                                                                                          \
-            return fail(DGB200_ERR_INVALID_ARGUMENT, "Assertion error (%s:%d): %s", __FILE__, __LINE__, #cond); \
-    } while (0)
-
-#define DGB_CUDA(call)                                                                                          \
-    do {                                                                                                        \
-        cudaError_t e_ = (call);                                                                                \
-        if (e_ != cudaSuccess)                                                                                  \
-            return fail(DGB200_ERR_CUDA, "CUDA runtime error (%s:%d): %s", __FILE__, __LINE__, cudaGetErrorString(e_)); \
-    } while (0)
+#define fail host_fail
 
 // ------------------------------------------------------------------------------------------------ runtime state
 using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -110,7 +90,7 @@ int ensure_device() {
 int effective_num_sms() {
     Runtime& r = rt();
     int n = r.num_sms > 0 ? std::min(r.num_sms, r.sm_count) : r.sm_count;
-    return n & ~1;  // CTA pairs need an even grid
+    return n >= 2 ? (n & ~1) : n;  // CTA pairs need an even grid (a budget of 1 SM runs single-CTA MMAs)
 }
 
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
@@ -123,49 +103,53 @@ inline int env_int(const char* name, int dflt) {
 // ------------------------------------------------------------------------------------------------ tensor maps
 struct MapKey {
     const void* ptr;
-    uint64_t d0, d1, stride;
+    uint64_t d0, d1, d2, stride, stride2;
     uint32_t b0, b1, dtype, swizzle;
     bool operator==(const MapKey& o) const {
-        return ptr == o.ptr && d0 == o.d0 && d1 == o.d1 && stride == o.stride && b0 == o.b0 && b1 == o.b1 &&
-               dtype == o.dtype && swizzle == o.swizzle;
+        return ptr == o.ptr && d0 == o.d0 && d1 == o.d1 && d2 == o.d2 && stride == o.stride && stride2 == o.stride2 &&
+               b0 == o.b0 && b1 == o.b1 && dtype == o.dtype && swizzle == o.swizzle;
     }
 };
 struct MapKeyHash {
     size_t operator()(const MapKey& k) const {
         uint64_t h = reinterpret_cast<uint64_t>(k.ptr);
         auto mix = [&](uint64_t v) { h ^= v + 0x9e3779b97f4a7c15ull + (h << 6) + (h >> 2); };
-        mix(k.d0), mix(k.d1), mix(k.stride), mix(k.b0), mix(k.b1), mix(k.dtype), mix(k.swizzle);
+        mix(k.d0), mix(k.d1), mix(k.d2), mix(k.stride), mix(k.stride2), mix(k.b0), mix(k.b1), mix(k.dtype), mix(k.swizzle);
         return static_cast<size_t>(h);
     }
 };
 
-// 2-D tiled map: inner dim d0 contiguous, outer dim d1 with `stride_bytes` pitch; box b0 x b1.
-// Encoding is a pure function of its arguments, so maps are memoised per thread (the reference re-encodes five
-// maps on every call, impls/sm100_fp8_fp4_gemm_1d1d.hpp:117-135).
-int make_map_2d(CUtensorMap* out, const void* ptr, CUtensorMapDataType dtype, uint64_t d0, uint64_t d1,
-                uint64_t stride_bytes, uint32_t b0, uint32_t b1, CUtensorMapSwizzle swizzle) {
+// Tiled map: inner dim d0 contiguous, outer dim d1 with `stride_bytes` pitch, optional batch dim d2 (0 = rank 2) with
+// `stride2_bytes` pitch; box b0 x b1 (x 1). Encoding is a pure function of its arguments, so maps are memoised per thread
+// (the reference re-encodes five maps on every call, impls/sm100_fp8_fp4_gemm_1d1d.hpp:117-135).
+int make_map(CUtensorMap* out, const void* ptr, CUtensorMapDataType dtype, uint64_t d0, uint64_t d1, uint64_t stride_bytes,
+             uint32_t b0, uint32_t b1, CUtensorMapSwizzle swizzle, uint64_t d2 = 0, uint64_t stride2_bytes = 0) {
     thread_local std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
-    const MapKey key{ptr, d0, d1, stride_bytes, b0, b1, static_cast<uint32_t>(dtype), static_cast<uint32_t>(swizzle)};
+    const MapKey key{ptr, d0, d1, d2, stride_bytes, stride2_bytes, b0, b1, static_cast<uint32_t>(dtype), static_cast<uint32_t>(swizzle)};
     auto it = cache.find(key);
     if (it != cache.end()) {
         *out = it->second;
         return DGB200_OK;
     }
-    const cuuint64_t dims[2] = {d0, d1};
-    const cuuint64_t strides[1] = {stride_bytes};
-    const cuuint32_t box[2] = {b0, b1};
-    const cuuint32_t elem_strides[2] = {1, 1};
-    CUresult res = rt().encode(out, dtype, 2, const_cast<void*>(ptr), dims, strides, box, elem_strides,
+    const cuuint64_t dims[3] = {d0, d1, d2};
+    const cuuint64_t strides[2] = {stride_bytes, stride2_bytes};
+    const cuuint32_t box[3] = {b0, b1, 1};
+    const cuuint32_t elem_strides[3] = {1, 1, 1};
+    CUresult res = rt().encode(out, dtype, d2 > 0 ? 3 : 2, const_cast<void*>(ptr), dims, strides, box, elem_strides,
                                CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (res != CUDA_SUCCESS)
         return fail(DGB200_ERR_CUDA,
-                    "cuTensorMapEncodeTiled failed (%d): ptr=%p dims={%llu,%llu} stride=%llu box={%u,%u} swizzle=%d",
-                    static_cast<int>(res), ptr, (unsigned long long)d0, (unsigned long long)d1,
-                    (unsigned long long)stride_bytes, b0, b1, static_cast<int>(swizzle));
+                    "cuTensorMapEncodeTiled failed (%d): ptr=%p dims={%llu,%llu,%llu} strides={%llu,%llu} box={%u,%u} swizzle=%d",
+                    static_cast<int>(res), ptr, (unsigned long long)d0, (unsigned long long)d1, (unsigned long long)d2,
+                    (unsigned long long)stride_bytes, (unsigned long long)stride2_bytes, b0, b1, static_cast<int>(swizzle));
     if (cache.size() > 4096) cache.clear();
     cache.emplace(key, *out);
     return DGB200_OK;
+}
+int make_map_2d(CUtensorMap* out, const void* ptr, CUtensorMapDataType dtype, uint64_t d0, uint64_t d1,
+                uint64_t stride_bytes, uint32_t b0, uint32_t b1, CUtensorMapSwizzle swizzle) {
+    return make_map(out, ptr, dtype, d0, d1, stride_bytes, b0, b1, swizzle);
 }
 
 // ------------------------------------------------------------------------------------------------ heuristics
@@ -178,18 +162,8 @@ struct Problem {
     int max_splits = 1;  // > 1 only for dense problems whose caller supplied a split-K workspace
     bool x_mn = false;   // MN-major tokens: the token tile is loaded in 32/64/128-row swizzle atoms
     bool any_mn = false; // any MN-major operand: no weight multicast
+    bool tma_store_ok = false;   // the output may leave through the staged TMA-store epilogue (plain BF16 tiles)
 };
-struct Config {
-    int block_m, cluster, stages, num_sms, smem_bytes, swizzle_group;
-    int num_splits, kb_per_split;   // split-K (dense, small problems): K cut into num_splits ranges
-    int csplit;                     // cluster split-K: `cluster` single-CTA MMAs share one tile (then num_splits == cluster)
-    int grid, grid_y;               // grid == 0: persistent grid over num_sms; else exactly grid x grid_y CTAs
-    int num_tall = 0, block_m_low = 0;   // dense wave balancing: first num_tall m-blocks block_m high, the rest block_m_low
-    bool overlap_producer = false;  // launch as a programmatic dependent that does not wait for the preceding kernel
-};
-
-constexpr int kSmemCapacity = 232448;  // 227 KB usable per CTA on sm_100 (heuristics/sm100.hpp:15)
-
 int stage_bytes(int block_m, int cluster) { return static_cast<int>(slot_bytes(block_m, cluster)); }
 int smem_bytes_for(int block_m, int cluster, int stages, int staging_bytes = 0) {
     // stage slots | barriers | tmem pointer + split-K flag | (cluster split-K: reduction barrier, 16-byte aligned staging)
@@ -204,9 +178,9 @@ int csplit_staging_bytes(int block_m, int splits) { return (splits - 1) * (block
 //   L2          : all busy CTAs together pull at most ~kL2Rate B/cycle
 //   HBM         : bytes that are new to the chip in this step (weight tiles are shared by the m-blocks in flight,
 //                 token tiles by the n-units in flight) at ~kHbmRate B/cycle
-constexpr double kSmIngest = 45.0, kL2Rate = 8000.0, kHbmRate = 3400.0, kTileOverhead = 1500.0, kSplitOverhead = 2500.0,
-                 kCSplitOverhead = 1200.0;
+constexpr double kSmIngest = 45.0, kL2Rate = 8000.0, kHbmRate = 3400.0, kTileOverhead = 1500.0, kSplitOverhead = 2500.0;
 constexpr int kMaxSplits = 8;
+constexpr int kTmaStoreMinBlockM = 64;                // shorter tiles keep the direct-store epilogue
 constexpr int kSplitKCounters = 4096;                 // ints at the start of the workspace
 constexpr size_t kSplitKHeaderBytes = kSplitKCounters * sizeof(int);
 
@@ -217,7 +191,7 @@ double estimate_cycles(const Problem& pb, int block_m, int cluster_total, int nu
     const int num_kb = ceil_div(ceil_div(pb.k, (int)kBlockK), splits);
     int m_blocks;  // m-blocks that share one weight panel
     double tiles;
-    if (pb.type == kMMasked) {
+    if (pb.type == kMMasked || pb.type == kBatched) {
         m_blocks = ceil_div(std::max(pb.expected_m, 1), block_m);
         tiles = (double)pb.groups * m_blocks * n_units;
     } else if (pb.type == kDense) {
@@ -246,7 +220,7 @@ Config choose_config(const Problem& pb, int num_sms_override = 0) {
     c.cluster = c.num_sms >= 2 ? 2 : 1;
     if (int v = env_int("DGB200_CLUSTER", 0)) c.cluster = v;
     std::vector<int> candidates;
-    if (pb.type == kDense || pb.type == kMMasked || pb.type == kKGrouped || pb.type == kKGroupedPsum) {
+    if (pb.type == kDense || pb.type == kMMasked || pb.type == kKGrouped || pb.type == kKGroupedPsum || pb.type == kBatched) {
         const int step = pb.x_mn ? 32 * std::min(c.cluster, 2) : 16;   // MN-major tokens: load_m is a multiple of 32
         for (int bm = step; bm <= (int)kMaxBlockM; bm += step) candidates.push_back(bm);
     } else {
@@ -293,7 +267,6 @@ Config choose_config(const Problem& pb, int num_sms_override = 0) {
         const int units = c.num_sms / 2, n_units = ceil_div(pb.n, (int)kBlockN * 2);
         const double overhead_rows = kTileOverhead / (2.0 * num_kb);      // per-tile fixed cost in units of token rows
         double best_ms = 1e300;
-        int best_nb = 0;
         for (int nb = ceil_div(pb.m, (int)kMaxBlockM); nb <= ceil_div(pb.m, 160) && nb * n_units <= 64 * units; ++nb) {
             const int hi = align_up(ceil_div(pb.m, nb), 16), lo = hi - 16;
             if (hi > (int)kMaxBlockM || lo < 16) continue;
@@ -311,9 +284,8 @@ Config choose_config(const Problem& pb, int num_sms_override = 0) {
                 }
             }
             const double ms = *std::max_element(load.begin(), load.end());
-            if (ms < best_ms * 0.995) best_ms = ms, best_nb = nb, c.block_m = hi, c.block_m_low = lo, c.num_tall = tall;
+            if (ms < best_ms * 0.995) best_ms = ms, c.block_m = hi, c.block_m_low = lo, c.num_tall = tall;
         }
-        (void)best_nb;
     }
 
     // Cluster split-K (dense, K-major, small M): S single-CTA MMAs share one output tile, each streams 1/S of K, and
@@ -348,172 +320,26 @@ Config choose_config(const Problem& pb, int num_sms_override = 0) {
     }
     const int cta_group = c.csplit ? 1 : std::min(c.cluster, 2);
     const int staging = c.csplit ? csplit_staging_bytes(c.block_m, c.csplit) : 0;
-    int stages = (kSmemCapacity - 64 - (staging ? 32 + staging : 0)) / stage_bytes(c.block_m, cta_group);
-    while (stages > 1 && smem_bytes_for(c.block_m, cta_group, stages, staging) > kSmemCapacity) --stages;
+    // Staged TMA-store epilogue: pays when tiles are tall (the direct epilogue stores 64 B per instruction and keeps the
+    // epilogue warps busy until the last row has left); small tiles keep all of shared memory for the TMA -> MMA ring.
+    // DGB200_TMA_STORE = 0 / 1 pins the choice (development).
+    c.tma_store = 0;
+    if (pb.tma_store_ok && c.cluster == 2 && !c.csplit && c.num_splits == 1) {
+        const int want = env_int("DGB200_TMA_STORE", -1);
+        c.tma_store = want >= 0 ? (want != 0) : (c.block_m >= kTmaStoreMinBlockM);
+    }
+    const int store_bytes = c.tma_store ? (int)kStoreStagingBytes : 0;
+    int stages = (kSmemCapacity - 64 - store_bytes - (staging ? 32 + staging : 0)) / stage_bytes(c.block_m, cta_group);
+    while (stages > 1 && smem_bytes_for(c.block_m, cta_group, stages, staging) + store_bytes > kSmemCapacity) --stages;
     stages = std::min(stages, 32);
     if (int v = env_int("DGB200_STAGES", 0)) stages = std::min(v, stages);
     c.stages = std::max(stages, 1);
-    c.smem_bytes = smem_bytes_for(c.block_m, cta_group, c.stages, staging);
+    c.smem_bytes = smem_bytes_for(c.block_m, cta_group, c.stages, staging) + store_bytes;
     c.swizzle_group = env_int("DGB200_SWIZZLE_GROUP", 8);
     return c;
 }
 
 // ------------------------------------------------------------------------------------------------ launch
-struct GemmCall {
-    int type;
-    const void* a;
-    const void* b;
-    const int32_t* sfa;
-    const int32_t* sfb;
-    void* d;
-    const int32_t* grouped_layout;
-    int m, n, k, groups;
-    int a_rows;  // total rows of the flattened A
-    int64_t lda, ldb, ldd;
-    bool x_mn = false, w_mn = false;  // operand is MN-major (M / N contiguous, K strided by lda / ldb)
-    const uint32_t* arrival = nullptr;           // EP dispatch in flight: per-group arrival counters / their targets;
-    const uint32_t* arrival_expected = nullptr;  // the launch overlaps the producer kernel (no griddepcontrol.wait)
-    int sfa_krows = 0, sfb_krows = 0; // k-grouped: total packed SF rows (0: derive from k)
-    int sfa_stride, sfb_stride, sfa_cols, sfb_cols;
-    int gran_k_a, gran_k_b;
-    int d_dtype, accumulate;
-    int expected_m, alignment, zero_padding;
-    void* workspace;
-    size_t workspace_bytes;
-    cudaStream_t stream;
-};
-
-template <typename Kernel>
-int launch_kernel(Kernel kernel, const Config& cfg, cudaStream_t stream, const CUtensorMap& mx, const CUtensorMap& mw,
-                  const CUtensorMap& msfx, const CUtensorMap& msfw, const GemmParams& p) {
-    // Opt in to > 48 KB dynamic smem once per instantiation and device
-    // (all instantiations share one function-pointer type, so the memo is keyed by the kernel address)
-    static std::mutex mu;
-    static std::unordered_map<const void*, int> configured;  // kernel -> device it was configured on
-    {
-        std::lock_guard<std::mutex> lock(mu);
-        auto it = configured.find(reinterpret_cast<const void*>(kernel));
-        if (it == configured.end() || it->second != rt().device) {
-            DGB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemCapacity));
-            configured[reinterpret_cast<const void*>(kernel)] = rt().device;
-        }
-    }
-    cudaLaunchConfig_t lc{};
-    lc.gridDim = cfg.grid > 0 ? dim3(cfg.grid, cfg.grid_y, 1) : dim3(cfg.num_sms / cfg.cluster * cfg.cluster, 1, 1);
-    lc.blockDim = dim3(kNumThreads, 1, 1);
-    lc.dynamicSmemBytes = cfg.smem_bytes;
-    lc.stream = stream;
-    cudaLaunchAttribute attrs[3];
-    int na = 0;
-    if (cfg.cluster > 1) {
-        attrs[na].id = cudaLaunchAttributeClusterDimension;
-        attrs[na].val.clusterDim.x = cfg.cluster;
-        attrs[na].val.clusterDim.y = 1;
-        attrs[na].val.clusterDim.z = 1;
-        ++na;
-    }
-    if (cfg.cluster > 2 && cfg.grid == 0) {
-        // 4/8-CTA clusters must sit inside one GPC: ask how many fit at once and size the persistent grid to that
-        static std::mutex occ_mu;
-        static std::unordered_map<const void*, int> resident;   // kernel (x cluster size, implied) -> clusters
-        std::lock_guard<std::mutex> lock(occ_mu);
-        auto it = resident.find(reinterpret_cast<const void*>(kernel));
-        if (it == resident.end()) {
-            lc.attrs = attrs, lc.numAttrs = na;
-            int n = 0;
-            cudaError_t e = cudaOccupancyMaxActiveClusters(&n, kernel, &lc);
-            if (e != cudaSuccess || n <= 0) n = cfg.num_sms / cfg.cluster;
-            it = resident.emplace(reinterpret_cast<const void*>(kernel), n).first;
-        }
-        const int clusters = std::min(it->second, cfg.num_sms / cfg.cluster);
-        lc.gridDim = dim3(clusters * cfg.cluster, 1, 1);
-    }
-    if (rt().pdl || cfg.overlap_producer) {
-        attrs[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-        attrs[na].val.programmaticStreamSerializationAllowed = 1;
-        ++na;
-    }
-    lc.attrs = attrs;
-    lc.numAttrs = na;
-    DGB_CUDA(cudaLaunchKernelEx(&lc, kernel, mx, mw, msfx, msfw, p));
-    g_launch_count.fetch_add(1, std::memory_order_relaxed);
-    return DGB200_OK;
-}
-
-// Instantiation menu (everything is compiled ahead of time; keep it to what the API can reach):
-//   dense          : out {bf16, fp32} x accumulate {0,1} x majors {KK: clusters 1,2,4,8 | KM, MK, MM: clusters 1,2}
-//   contiguous/psum: bf16, no C, tokens K-major, weights {K, MN}, clusters 1,2        (gemm.hpp:181,193)
-//   masked         : bf16, no C, both K-major, clusters 1,2                             (gemm.hpp:263,275)
-//   k-grouped(+psum): fp32, accumulate into D, both MN-major, clusters 1,2             (gemm.hpp:325-328)
-#define DGB_LAUNCH(TYPE, CL, OUT, ACC, XMN, WMN) \
-    launch_kernel(fp8_gemm_kernel<TYPE, CL, OUT, ACC, XMN, WMN, false>, cfg, c.stream, mx, mw, msfx, msfw, p)
-#define DGB_LAUNCH_CSPLIT(CL, OUT, ACC) \
-    launch_kernel(fp8_gemm_kernel<kDense, CL, OUT, ACC, false, false, false, true>, cfg, c.stream, mx, mw, msfx, msfw, p)
-#define DGB_LAUNCH_SPLITK(CL, OUT, ACC, XMN, WMN) \
-    launch_kernel(fp8_gemm_kernel<kDense, CL, OUT, ACC, XMN, WMN, true>, cfg, c.stream, mx, mw, msfx, msfw, p)
-
-template <int kType, int kCluster, bool kXMn, bool kWMn>
-int dispatch_out(const GemmCall& c, const Config& cfg, const CUtensorMap& mx, const CUtensorMap& mw,
-                 const CUtensorMap& msfx, const CUtensorMap& msfw, const GemmParams& p) {
-    if constexpr (kType == kDense) {
-        if constexpr ((kCluster == 2 || kCluster == 4) && !kXMn && !kWMn) {
-            if (cfg.csplit) {
-                if (c.d_dtype == DGB200_BF16)
-                    return c.accumulate ? DGB_LAUNCH_CSPLIT(kCluster, __nv_bfloat16, true) : DGB_LAUNCH_CSPLIT(kCluster, __nv_bfloat16, false);
-                return c.accumulate ? DGB_LAUNCH_CSPLIT(kCluster, float, true) : DGB_LAUNCH_CSPLIT(kCluster, float, false);
-            }
-        }
-        if constexpr (kCluster <= 2) {
-            if (cfg.num_splits > 1) {
-                if (c.d_dtype == DGB200_BF16)
-                    return c.accumulate ? DGB_LAUNCH_SPLITK(kCluster, __nv_bfloat16, true, kXMn, kWMn)
-                                        : DGB_LAUNCH_SPLITK(kCluster, __nv_bfloat16, false, kXMn, kWMn);
-                return c.accumulate ? DGB_LAUNCH_SPLITK(kCluster, float, true, kXMn, kWMn)
-                                    : DGB_LAUNCH_SPLITK(kCluster, float, false, kXMn, kWMn);
-            }
-        }
-        if (c.d_dtype == DGB200_BF16)
-            return c.accumulate ? DGB_LAUNCH(kType, kCluster, __nv_bfloat16, true, kXMn, kWMn)
-                                : DGB_LAUNCH(kType, kCluster, __nv_bfloat16, false, kXMn, kWMn);
-        return c.accumulate ? DGB_LAUNCH(kType, kCluster, float, true, kXMn, kWMn)
-                            : DGB_LAUNCH(kType, kCluster, float, false, kXMn, kWMn);
-    } else if constexpr (kType == kKGrouped || kType == kKGroupedPsum) {
-        return DGB_LAUNCH(kType, kCluster, float, true, true, true);
-    } else {
-        return DGB_LAUNCH(kType, kCluster, __nv_bfloat16, false, false, kWMn);
-    }
-}
-
-template <int kType, bool kXMn, bool kWMn>
-int dispatch_cluster(const GemmCall& c, const Config& cfg, const CUtensorMap& mx, const CUtensorMap& mw,
-                     const CUtensorMap& msfx, const CUtensorMap& msfw, const GemmParams& p) {
-    if constexpr (kType == kDense && !kXMn && !kWMn) {
-        if (cfg.cluster == 8) return dispatch_out<kType, 8, kXMn, kWMn>(c, cfg, mx, mw, msfx, msfw, p);
-        if (cfg.cluster == 4) return dispatch_out<kType, 4, kXMn, kWMn>(c, cfg, mx, mw, msfx, msfw, p);
-    }
-    if (cfg.cluster == 2) return dispatch_out<kType, 2, kXMn, kWMn>(c, cfg, mx, mw, msfx, msfw, p);
-    if (cfg.cluster == 1) return dispatch_out<kType, 1, kXMn, kWMn>(c, cfg, mx, mw, msfx, msfw, p);
-    return fail(DGB200_ERR_INVALID_ARGUMENT, "unsupported cluster size %d for gemm type %d", cfg.cluster, (int)kType);
-}
-
-template <int kType>
-int dispatch_majors(const GemmCall& c, const Config& cfg, const CUtensorMap& mx, const CUtensorMap& mw,
-                    const CUtensorMap& msfx, const CUtensorMap& msfw, const GemmParams& p) {
-    if constexpr (kType == kDense) {
-        if (c.x_mn && c.w_mn) return dispatch_cluster<kType, true, true>(c, cfg, mx, mw, msfx, msfw, p);
-        if (c.x_mn) return dispatch_cluster<kType, true, false>(c, cfg, mx, mw, msfx, msfw, p);
-        if (c.w_mn) return dispatch_cluster<kType, false, true>(c, cfg, mx, mw, msfx, msfw, p);
-        return dispatch_cluster<kType, false, false>(c, cfg, mx, mw, msfx, msfw, p);
-    } else if constexpr (kType == kKGrouped || kType == kKGroupedPsum) {
-        return dispatch_cluster<kType, true, true>(c, cfg, mx, mw, msfx, msfw, p);
-    } else if constexpr (kType == kMMasked) {
-        return dispatch_cluster<kType, false, false>(c, cfg, mx, mw, msfx, msfw, p);
-    } else {
-        if (c.w_mn) return dispatch_cluster<kType, false, true>(c, cfg, mx, mw, msfx, msfw, p);
-        return dispatch_cluster<kType, false, false>(c, cfg, mx, mw, msfx, msfw, p);
-    }
-}
-
 int run_gemm(const GemmCall& c) {
     if (int e = ensure_device()) return e;
     DGB_REQUIRE(c.gran_k_a == 32 || c.gran_k_a == 128);
@@ -524,10 +350,16 @@ int run_gemm(const GemmCall& c) {
     DGB_REQUIRE(c.sfa_stride % 4 == 0 && c.sfb_stride % 4 == 0);
     const bool k_grouped = c.type == kKGrouped || c.type == kKGroupedPsum;
 
+    const bool batched = c.type == kBatched;
+    const bool head_split = c.head_mid > 0;
     Problem pb{c.type, c.m, c.expected_m, c.n, c.k, c.groups, c.alignment};
     pb.x_mn = c.x_mn, pb.any_mn = c.x_mn || c.w_mn;
+    // TMA stores need a 16-byte aligned base and row pitch; tiles that must not touch rows past `valid_m` (masked, psum),
+    // accumulate into C or remap columns keep the predicated direct stores
+    pb.tma_store_ok = (c.type == kDense || c.type == kMContiguous) && c.d_dtype == DGB200_BF16 && !c.accumulate && !head_split &&
+                      (reinterpret_cast<uintptr_t>(c.d) & 15) == 0 && (c.ldd * 2) % 16 == 0 && c.arrival == nullptr;
     // split-K needs scratch: [4096 arrival counters][num_splits x m x n fp32 partial tiles]
-    if (c.type == kDense && c.workspace != nullptr && c.n % 4 == 0 && c.workspace_bytes > kSplitKHeaderBytes &&
+    if (c.type == kDense && !head_split && c.workspace != nullptr && c.n % 4 == 0 && c.workspace_bytes > kSplitKHeaderBytes &&
         (reinterpret_cast<uintptr_t>(c.workspace) & 15) == 0) {
         const size_t per_split = static_cast<size_t>(c.m) * c.n * sizeof(float);
         pb.max_splits = static_cast<int>(std::min<size_t>(kMaxSplits, (c.workspace_bytes - kSplitKHeaderBytes) / per_split));
@@ -540,6 +372,7 @@ int run_gemm(const GemmCall& c) {
     const int load_m = cfg.block_m / cta_group;
     DGB_REQUIRE(cfg.block_m % 16 == 0 && cfg.block_m >= 16 && cfg.block_m <= (int)kMaxBlockM);
     DGB_REQUIRE(cfg.cluster == 1 || cfg.cluster == 2 || (c.type == kDense && (cfg.cluster == 4 || cfg.cluster == 8)));
+    if (cfg.cluster > 2 && !cfg.csplit) cfg.tma_store = 0;
     DGB_REQUIRE(cfg.cluster <= 2 || cfg.num_splits == 1 || cfg.csplit);
     if (cfg.csplit) DGB_REQUIRE(cfg.block_m % (16 * cfg.csplit) == 0 && cfg.cluster == cfg.csplit);
     if (c.type == kMContiguous || c.type == kMContiguousPsum) DGB_REQUIRE(c.alignment % cfg.block_m == 0);
@@ -547,36 +380,47 @@ int run_gemm(const GemmCall& c) {
     if (c.x_mn) DGB_REQUIRE(load_m % 32 == 0);
 
     const int num_kp_a = ceil_div(c.k, c.gran_k_a * 4), num_kp_b = ceil_div(c.k, c.gran_k_b * 4);
-    const int b_groups = (c.type == kDense || k_grouped) ? 1 : c.groups;
-    const int sfa_groups = c.type == kMMasked ? c.groups : 1;
+    const int b_groups = (c.type == kDense || k_grouped || batched) ? 1 : c.groups;      // groups folded into the weight map's rows
+    const int sfa_groups = (c.type == kMMasked || batched) ? c.groups : 1;
+    const int sfb_groups = batched ? c.groups : b_groups;
     const uint64_t sfa_krows = c.sfa_krows > 0 ? (uint64_t)c.sfa_krows : (uint64_t)num_kp_a * sfa_groups;
-    const uint64_t sfb_krows = c.sfb_krows > 0 ? (uint64_t)c.sfb_krows : (uint64_t)num_kp_b * b_groups;
+    const uint64_t sfb_krows = c.sfb_krows > 0 ? (uint64_t)c.sfb_krows : (uint64_t)num_kp_b * sfb_groups;
 
     // Tensor maps. K-major operand [rows, K]: box 128 K-bytes x rows. MN-major operand [K rows, MN]: box S MN-bytes x
     // 128 K-rows, S = one swizzle atom (128 for the weights; the widest of 128/64/32 that divides load_m for tokens).
-    CUtensorMap mx, mw, msfx, msfw;
+    // Batched problems add the batch as a third dimension with its own pitch (box depth 1), so permuted views
+    // (fp8_einsum) need no copy.
+    Maps maps;
+    memset(&maps, 0, sizeof(maps));
     int x_swizzle = 128;
+    const uint64_t nb = batched ? (uint64_t)c.groups : 0;     // rank-3 maps only for the batched type
     if (c.x_mn) {
         x_swizzle = load_m % 128 == 0 ? 128 : (load_m % 64 == 0 ? 64 : 32);
         const CUtensorMapSwizzle sw = x_swizzle == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
                                       : (x_swizzle == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
-        if (int e = make_map_2d(&mx, c.a, CU_TENSOR_MAP_DATA_TYPE_UINT8, c.m, c.a_rows, c.lda, x_swizzle, kBlockK, sw)) return e;
+        if (int e = make_map(&maps.x, c.a, CU_TENSOR_MAP_DATA_TYPE_UINT8, c.m, c.a_rows, c.lda, x_swizzle, kBlockK, sw, nb,
+                             c.batch_stride_a)) return e;
     } else {
-        if (int e = make_map_2d(&mx, c.a, CU_TENSOR_MAP_DATA_TYPE_UINT8, c.k, c.a_rows, c.lda, kBlockK, load_m,
-                                CU_TENSOR_MAP_SWIZZLE_128B)) return e;
+        if (int e = make_map(&maps.x, c.a, CU_TENSOR_MAP_DATA_TYPE_UINT8, c.k, c.a_rows, c.lda, kBlockK, load_m,
+                             CU_TENSOR_MAP_SWIZZLE_128B, nb, c.batch_stride_a)) return e;
     }
     if (c.w_mn) {
         const uint64_t k_rows = k_grouped ? (uint64_t)c.a_rows : (uint64_t)c.k * b_groups;
-        if (int e = make_map_2d(&mw, c.b, CU_TENSOR_MAP_DATA_TYPE_UINT8, c.n, k_rows, c.ldb, kBlockN, kBlockK,
-                                CU_TENSOR_MAP_SWIZZLE_128B)) return e;
+        if (int e = make_map(&maps.w, c.b, CU_TENSOR_MAP_DATA_TYPE_UINT8, c.n, k_rows, c.ldb, kBlockN, kBlockK,
+                             CU_TENSOR_MAP_SWIZZLE_128B, nb, c.batch_stride_b)) return e;
     } else {
-        if (int e = make_map_2d(&mw, c.b, CU_TENSOR_MAP_DATA_TYPE_UINT8, c.k, (uint64_t)c.n * b_groups, c.ldb, kBlockK,
-                                kBlockN / pairs, CU_TENSOR_MAP_SWIZZLE_128B)) return e;
+        if (int e = make_map(&maps.w, c.b, CU_TENSOR_MAP_DATA_TYPE_UINT8, c.k, (uint64_t)c.n * b_groups, c.ldb, kBlockK,
+                             kBlockN / pairs, CU_TENSOR_MAP_SWIZZLE_128B, nb, c.batch_stride_b)) return e;
     }
-    if (int e = make_map_2d(&msfx, c.sfa, CU_TENSOR_MAP_DATA_TYPE_INT32, c.sfa_cols, sfa_krows, (uint64_t)c.sfa_stride * 4,
+    if (int e = make_map_2d(&maps.sfx, c.sfa, CU_TENSOR_MAP_DATA_TYPE_INT32, c.sfa_cols, sfa_krows, (uint64_t)c.sfa_stride * 4,
                             cfg.block_m, 1, CU_TENSOR_MAP_SWIZZLE_NONE)) return e;
-    if (int e = make_map_2d(&msfw, c.sfb, CU_TENSOR_MAP_DATA_TYPE_INT32, c.sfb_cols, sfb_krows, (uint64_t)c.sfb_stride * 4,
+    if (int e = make_map_2d(&maps.sfw, c.sfb, CU_TENSOR_MAP_DATA_TYPE_INT32, c.sfb_cols, sfb_krows, (uint64_t)c.sfb_stride * 4,
                             kBlockN, 1, CU_TENSOR_MAP_SWIZZLE_NONE)) return e;
+    if (cfg.tma_store) {
+        // D [rows, N] BF16: box 64 columns (one 128 B swizzle atom) x 16 rows; rows / columns past the end are clipped
+        if (int e = make_map_2d(&maps.d, c.d, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, c.n, c.m, (uint64_t)c.ldd * 2, 64, kStoreRows,
+                                CU_TENSOR_MAP_SWIZZLE_128B)) return e;
+    }
 
     GemmParams p{};
     p.d = c.d;
@@ -618,25 +462,43 @@ int run_gemm(const GemmCall& c) {
     p.zero_padding = c.zero_padding;
     p.x_swizzle = x_swizzle;
     p.sf_k_span = 4 * c.gran_k_a;
+    p.d_batch_stride = batched ? static_cast<uint64_t>(c.batch_stride_d) : 0;
+    p.head_lr = head_split ? c.head_left + c.head_right : 1, p.head_mid = head_split ? c.head_mid : 0, p.head_right = c.head_right;
 
-    g_last_config = dgb200_config{cfg.block_m, cfg.cluster, cfg.stages, cfg.num_sms, cfg.smem_bytes, 0, cfg.num_splits, cfg.csplit};
+    g_last_config = dgb200_config{cfg.block_m, cfg.cluster, cfg.stages, cfg.num_sms, cfg.smem_bytes, 0, cfg.num_splits, cfg.csplit,
+                                  cfg.tma_store};
     if (env_int("DGB200_PRINT_CONFIGS", 0))
-        fprintf(stderr, "dgb200 config: type=%d m=%d n=%d k=%d groups=%d majors=%d%d -> block_m=%d cluster=%d stages=%d sms=%d smem=%d splits=%d\n",
+        fprintf(stderr, "dgb200 config: type=%d m=%d n=%d k=%d groups=%d majors=%d%d -> block_m=%d cluster=%d stages=%d sms=%d smem=%d splits=%d tma_store=%d\n",
                 c.type, c.m, c.n, c.k, c.groups, (int)c.x_mn, (int)c.w_mn, cfg.block_m, cfg.cluster, cfg.stages, cfg.num_sms,
-                cfg.smem_bytes, cfg.csplit ? -cfg.num_splits : cfg.num_splits);
+                cfg.smem_bytes, cfg.csplit ? -cfg.num_splits : cfg.num_splits, cfg.tma_store);
 
     switch (c.type) {
-        case kDense: return dispatch_majors<kDense>(c, cfg, mx, mw, msfx, msfw, p);
-        case kMContiguous: return dispatch_majors<kMContiguous>(c, cfg, mx, mw, msfx, msfw, p);
-        case kMMasked: return dispatch_majors<kMMasked>(c, cfg, mx, mw, msfx, msfw, p);
-        case kMContiguousPsum: return dispatch_majors<kMContiguousPsum>(c, cfg, mx, mw, msfx, msfw, p);
-        case kKGrouped: return dispatch_majors<kKGrouped>(c, cfg, mx, mw, msfx, msfw, p);
-        case kKGroupedPsum: return dispatch_majors<kKGroupedPsum>(c, cfg, mx, mw, msfx, msfw, p);
+        case kDense:
+            if (cfg.num_splits > 1 && !cfg.csplit) return dispatch_dense_splitk(c, cfg, maps, p);
+            return (c.x_mn || c.w_mn) ? dispatch_dense_mn(c, cfg, maps, p) : dispatch_dense_kk(c, cfg, maps, p);
+        case kMContiguous: case kMMasked: case kMContiguousPsum: case kKGrouped: case kKGroupedPsum:
+            return dispatch_grouped(c, cfg, maps, p);
+        case kBatched: return dispatch_batched(c, cfg, maps, p);
         default: return fail(DGB200_ERR_INVALID_ARGUMENT, "unknown gemm type %d", c.type);
     }
 }
 
 }  // namespace
+
+// ---- services for the kernel-instance translation units (launch.cuh)
+int host_fail(int code, const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+    return code;
+}
+int rt_device() { return rt().device; }
+int rt_pdl() { return rt().pdl; }
+void count_launches(int n) { g_launch_count.fetch_add(n, std::memory_order_relaxed); }
+
 }  // namespace dgb200
 
 // ================================================================================================ C ABI
@@ -648,14 +510,16 @@ const char* dgb200_last_error(void) { return g_last_error.c_str(); }
 int dgb200_version(void) { return DGB200_VERSION; }
 
 int dgb200_set_num_sms(int num_sms) {
-    DGB_REQUIRE(num_sms > 0 && num_sms % 2 == 0);
+    // Like the reference (csrc/jit/device_runtime.hpp:103-105): any 0 <= n <= SM count, 0 = all SMs. An odd budget
+    // (e.g. total - communication SMs) is accepted; the launch rounds it down to whole CTA pairs.
+    DGB_REQUIRE(num_sms >= 0);
     if (rt().device_ready) DGB_REQUIRE(num_sms <= rt().sm_count);
     rt().num_sms = num_sms;
     return DGB200_OK;
 }
 int dgb200_get_num_sms(void) {
-    if (!rt().device_ready) return rt().num_sms;
-    return effective_num_sms();
+    if (rt().num_sms > 0 || !rt().device_ready) return rt().num_sms;   // what the caller set (reference semantics)
+    return rt().sm_count;
 }
 int dgb200_set_tc_util(int percent) {
     DGB_REQUIRE(percent > 0 && percent <= 100);
@@ -802,6 +666,102 @@ int dgb200_m_grouped_fp8_gemm_nt_contiguous(const void* a, const int32_t* sfa, c
     return run_gemm(c);
 }
 
+int dgb200_fp8_gemm_nt_skip_head_mid(const void* a, const int32_t* sfa, const void* b, const int32_t* sfb, void* d, int m,
+                                     int n, int k, int64_t lda, int64_t ldb, int64_t ldd, int head_left, int head_mid,
+                                     int head_right, int sfa_stride, int sfb_stride, int d_dtype, void* stream) {
+    DGB_REQUIRE(m >= 0 && n > 0 && k > 0);                                  // attention.hpp:42
+    DGB_REQUIRE(head_left >= 0 && head_mid >= 0 && head_right >= 0 && head_left + head_right > 0);
+    DGB_REQUIRE(n % (head_left + head_right) == 0);                         // attention.hpp:49
+    const int n_out = n + n / (head_left + head_right) * head_mid;
+    DGB_REQUIRE(d_dtype == DGB200_BF16 || d_dtype == DGB200_FP32);
+    DGB_REQUIRE(lda >= k && ldb >= k && ldd >= n_out);
+    if (m == 0) return DGB200_OK;                                           // attention.hpp:52-53
+    DGB_REQUIRE(sfa_stride >= align_up(m, 4) && sfb_stride >= align_up(n, 4));
+    GemmCall c{};
+    c.type = kDense;
+    c.a = a, c.b = b, c.sfa = sfa, c.sfb = sfb, c.d = d, c.grouped_layout = nullptr;
+    c.m = m, c.n = n, c.k = k, c.groups = 1, c.a_rows = m;
+    c.lda = lda, c.ldb = ldb, c.ldd = ldd;
+    c.sfa_stride = sfa_stride, c.sfb_stride = sfb_stride;
+    c.sfa_cols = align_up(m, 4), c.sfb_cols = align_up(n, 4);
+    c.gran_k_a = 128, c.gran_k_b = 128;                                     // attention.hpp:59
+    c.d_dtype = d_dtype, c.accumulate = 0;
+    c.expected_m = m, c.alignment = 1, c.zero_padding = 0;
+    c.workspace = nullptr, c.workspace_bytes = 0;
+    c.head_left = head_left, c.head_mid = head_mid, c.head_right = head_right;
+    c.stream = static_cast<cudaStream_t>(stream);
+    return run_gemm(c);
+}
+
+int dgb200_fp8_bmm(const void* a, const int32_t* sfa, const void* b, const int32_t* sfb, void* d, int batch, int m, int n,
+                   int k, int64_t lda, int64_t ldb, int64_t ldd, int64_t batch_stride_a, int64_t batch_stride_b,
+                   int64_t batch_stride_d, int major_a, int major_b, int sfa_stride, int sfb_stride, int gran_k_a,
+                   int gran_k_b, int d_dtype, int accumulate, void* stream) {
+    DGB_REQUIRE(batch >= 0 && m >= 0 && n >= 0 && k >= 0);
+    if (batch == 0 || m == 0 || n == 0) return DGB200_OK;                    // einsum.hpp:160-161
+    DGB_REQUIRE(k > 0);                                                     // k == 0 is the host wrapper's job (gemm.hpp:36-40)
+    DGB_REQUIRE(d_dtype == DGB200_BF16 || d_dtype == DGB200_FP32);
+    DGB_REQUIRE(major_a == DGB200_K_MAJOR || major_a == DGB200_MN_MAJOR);
+    DGB_REQUIRE(major_b == DGB200_K_MAJOR || major_b == DGB200_MN_MAJOR);
+    DGB_REQUIRE(lda >= (major_a == DGB200_K_MAJOR ? k : m) && ldb >= (major_b == DGB200_K_MAJOR ? k : n) && ldd >= n);
+    DGB_REQUIRE(batch_stride_a % 16 == 0 && batch_stride_b % 16 == 0 && batch_stride_a > 0 && batch_stride_b > 0 && batch_stride_d > 0);
+    DGB_REQUIRE(sfa_stride >= align_up(m, 4) && sfb_stride >= align_up(n, 4));
+    GemmCall c{};
+    c.type = kBatched;
+    c.a = a, c.b = b, c.sfa = sfa, c.sfb = sfb, c.d = d, c.grouped_layout = nullptr;
+    c.x_mn = major_a == DGB200_MN_MAJOR, c.w_mn = major_b == DGB200_MN_MAJOR;
+    c.m = m, c.n = n, c.k = k, c.groups = batch, c.a_rows = c.x_mn ? k : m;
+    c.lda = lda, c.ldb = ldb, c.ldd = ldd;
+    c.batch_stride_a = batch_stride_a, c.batch_stride_b = batch_stride_b, c.batch_stride_d = batch_stride_d;
+    c.sfa_stride = sfa_stride, c.sfb_stride = sfb_stride;
+    c.sfa_cols = align_up(m, 4), c.sfb_cols = align_up(n, 4);
+    c.gran_k_a = gran_k_a, c.gran_k_b = gran_k_b;
+    c.d_dtype = d_dtype, c.accumulate = accumulate != 0;
+    c.expected_m = m, c.alignment = 1, c.zero_padding = 0;
+    c.workspace = nullptr, c.workspace_bytes = 0;
+    c.stream = static_cast<cudaStream_t>(stream);
+    return run_gemm(c);
+}
+
+int dgb200_per_token_cast_to_fp8(const void* x, int64_t ldx, void* q, int64_t ldq, int32_t* sf, int sf_stride, int m, int k,
+                                 int gran_k, void* stream) {
+    if (int e = ensure_device()) return e;
+    DGB_REQUIRE(m >= 0 && k >= 0 && (gran_k == 32 || gran_k == 128));
+    if (m == 0 || k == 0) return DGB200_OK;
+    DGB_REQUIRE(x != nullptr && q != nullptr && sf != nullptr && ldx >= k && ldq >= k && sf_stride >= align_up(m, 4));
+    DGB_REQUIRE(ceil_div(m, 8) <= 65535);
+    const dim3 grid(ceil_div(k, 512), ceil_div(m, 8));
+    const auto s = static_cast<cudaStream_t>(stream);
+    if (gran_k == 128)
+        per_token_cast_to_fp8_kernel<128><<<grid, 256, 0, s>>>(static_cast<const __nv_bfloat16*>(x), ldx, static_cast<uint8_t*>(q), ldq,
+                                                               reinterpret_cast<uint32_t*>(sf), sf_stride, m, k);
+    else
+        per_token_cast_to_fp8_kernel<32><<<grid, 256, 0, s>>>(static_cast<const __nv_bfloat16*>(x), ldx, static_cast<uint8_t*>(q), ldq,
+                                                              reinterpret_cast<uint32_t*>(sf), sf_stride, m, k);
+    DGB_CUDA(cudaGetLastError());
+    g_launch_count.fetch_add(1, std::memory_order_relaxed);
+    return DGB200_OK;
+}
+
+int dgb200_debug_fp8_peak(int umma_n, int iters, int num_sms, void* stream) {
+    if (int e = ensure_device()) return e;
+    DGB_REQUIRE(umma_n >= 16 && umma_n <= 256 && umma_n % 16 == 0 && iters > 0);
+    const int sms = (num_sms > 0 ? std::min(num_sms, rt().sm_count) : rt().sm_count) & ~1;
+    DGB_REQUIRE(sms >= 2);
+    cudaLaunchConfig_t lc{};
+    lc.gridDim = dim3(sms, 1, 1), lc.blockDim = dim3(128, 1, 1);
+    lc.dynamicSmemBytes = 36 * 1024;
+    lc.stream = static_cast<cudaStream_t>(stream);
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeClusterDimension;
+    attr.val.clusterDim.x = 2, attr.val.clusterDim.y = 1, attr.val.clusterDim.z = 1;
+    lc.attrs = &attr, lc.numAttrs = 1;
+    DGB_CUDA(cudaLaunchKernelEx(&lc, fp8_mma_peak_kernel, static_cast<uint32_t>(umma_n), static_cast<uint32_t>(iters),
+                                static_cast<uint32_t*>(nullptr)));
+    g_launch_count.fetch_add(1, std::memory_order_relaxed);
+    return DGB200_OK;
+}
+
 int dgb200_ep_combine(void* out, int64_t ldo, const int32_t* token_row, const void* expert_ids, int id_bytes, int num_tokens,
                       int n, int elt_bytes, int num_experts, int rank, int world, void* const* buffers,
                       void* const* d_buffers, int64_t ldd, void* stream) {
@@ -921,13 +881,14 @@ int dgb200_plan(int gemm_type, int m, int n, int k, int num_groups, int expected
     DGB_REQUIRE(m > 0 && n > 0 && k > 0 && num_groups > 0);
     Problem pb{gemm_type, m, expected_m > 0 ? expected_m : m, n, k, num_groups, std::max(alignment, 1)};
     if (gemm_type == kDense && n % 4 == 0) pb.max_splits = kMaxSplits;   // as if a workspace were supplied
+    pb.tma_store_ok = gemm_type == kDense || gemm_type == kMContiguous;   // as if D were an aligned BF16 tensor
     const Config cfg = choose_config(pb, num_sms);
     const int n_units = ceil_div(n, (int)kBlockN * (cfg.csplit ? 1 : std::min(cfg.cluster, 2)));
     int m_blocks = gemm_type == kMMasked ? num_groups * ceil_div(pb.expected_m, cfg.block_m) : ceil_div(m, cfg.block_m);
     if (gemm_type == kDense && cfg.block_m_low > 0)   // two tile heights (wave balancing)
         m_blocks = cfg.num_tall + ceil_div(std::max(0, m - cfg.num_tall * cfg.block_m), cfg.block_m_low);
     *out = dgb200_config{cfg.block_m, cfg.cluster, cfg.stages, cfg.num_sms, cfg.smem_bytes, m_blocks * n_units * cfg.num_splits,
-                         cfg.num_splits, cfg.csplit};
+                         cfg.num_splits, cfg.csplit, cfg.tma_store};
     return DGB200_OK;
 }
 

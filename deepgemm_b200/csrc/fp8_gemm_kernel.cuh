@@ -42,6 +42,7 @@ enum GemmType : int {
     kMContiguousPsum = 3,  // grouped_layout[g] = end row of group g, starts aligned              (scheduler/gemm.cuh:217-237)
     kKGrouped = 4,      // D[g] += A[k_g, :M]^T B[k_g, :N], grouped_layout[g] = K of group g        (gemm.hpp:299, sched :259-283)
     kKGroupedPsum = 5,  // same, grouped_layout[g] = end K of group g, starts aligned to m_alignment
+    kBatched = 6,       // D[b] = A[b] B[b]^T with arbitrary batch strides (3-D tensor maps)      (einsum.hpp:137-175, fp8_bmm)
 };
 
 constexpr uint32_t kBlockN = 128;        // weight rows per CTA == TMEM lanes
@@ -55,6 +56,9 @@ constexpr uint32_t kTmemCols = 512;
 constexpr uint32_t kNumThreads = 384;
 constexpr uint32_t kNumEpilogueThreads = 256;   // two warps per TMEM lane quadrant
 constexpr uint32_t kWTileBytes = kBlockN * kBlockK;  // 16 KB
+constexpr uint32_t kStoreRows = 16;                  // output rows per TMA store (one staging buffer = 16 rows x 128 columns bf16)
+constexpr uint32_t kStoreBufBytes = kStoreRows * kBlockN * 2;       // 4 KB: two 128B-swizzled boxes of 16 rows x 64 columns
+constexpr uint32_t kStoreStagingBytes = 4 * kStoreBufBytes;         // two 4-warp groups x two buffers
 
 struct GemmParams {
     void* d;                    // output (bf16 or fp32), row stride ld_d elements
@@ -87,6 +91,11 @@ struct GemmParams {
     uint32_t zero_padding;      // psum: write zeros to [end, aligned end)
     uint32_t x_swizzle;         // MN-major tokens: swizzle width in bytes (128 / 64 / 32) = rows of one TMA box
     uint32_t sf_k_span;         // k-grouped: K elements covered by one packed SF word (4 * gran_k)
+    uint64_t d_batch_stride;    // batched: elements between consecutive batches of D (0 otherwise)
+    // Head-split output remap (fp8_gemm_nt_skip_head_mid, attention.hpp:19-74 / epilogue/transform.cuh:15-22): output
+    // column n is stored at n + (n + head_right) / head_lr * head_mid, i.e. every (left | right) head of the GEMM's N
+    // leaves a gap of `mid` untouched columns between its halves. head_mid == 0: identity.
+    uint32_t head_lr, head_mid, head_right;
 };
 
 // ------------------------------------------------------------------------------------------------ scheduler
@@ -107,6 +116,7 @@ struct Tile {
     uint32_t k_base;            // K offset of the tile's group in A / B (k-grouped), else 0
     uint32_t wk_base;           // K-row offset of the tile's group in an MN-major grouped B ([G,K,N] flattened), else 0
     uint32_t last_umma;         // UMMAs (32 K-elements each) to issue in the last k-block (4 unless K ends inside it)
+    uint32_t batch;             // batched: third tensor-map coordinate / D batch index (0 otherwise)
 };
 
 // kCluster = CTAs per cluster: 1 (single CTA MMA), 2 (one cta_group::2 pair) or 4 / 8 (2 / 4 pairs that work on
@@ -132,7 +142,7 @@ struct Scheduler {
         cluster_id = blockIdx.x / kCluster;
         num_clusters = gridDim.x / kCluster;
         num_n_units = p.num_n_units;
-        if constexpr (kGemmType == kMContiguousPsum) row_end = static_cast<uint32_t>(__ldg(p.grouped_layout));
+        if constexpr (kGemmType == kMContiguousPsum) row_end = static_cast<uint32_t>(max(0, __ldg(p.grouped_layout)));
     }
 
     // L2-friendly order inside one problem of `num_m` m-blocks: walk `swizzle_group` n-units at a time.
@@ -152,7 +162,7 @@ struct Scheduler {
             // one tile per cluster, addressed by the 2-D grid: (blockIdx.x / kCluster, blockIdx.y) = (n-tile, m-block)
             if (iter++ != 0) return false;
             const uint32_t num_kb = (p.k + kBlockK - 1) / kBlockK;
-            t.split = split_rank, t.counter_idx = 0, t.k_base = 0, t.wk_base = 0;
+            t.split = split_rank, t.counter_idx = 0, t.k_base = 0, t.wk_base = 0, t.batch = 0;
             t.kb_begin = split_rank * p.kb_per_split;
             t.kb_end = min(num_kb, t.kb_begin + p.kb_per_split);
             t.last_umma = t.kb_end != num_kb ? kBlockK / kUmmaK : ((p.k - (num_kb - 1) * kBlockK) + kUmmaK - 1) / kUmmaK;
@@ -168,7 +178,7 @@ struct Scheduler {
         uint32_t m_blk, n_unit, group = 0;
         const uint32_t num_kb_total = (p.k + kBlockK - 1) / kBlockK;
         t.kb_begin = 0, t.kb_end = num_kb_total, t.split = 0, t.counter_idx = 0;
-        t.k_base = 0, t.wk_base = 0;
+        t.k_base = 0, t.wk_base = 0, t.batch = 0;
         t.last_umma = ((p.k - (num_kb_total - 1) * kBlockK) + kUmmaK - 1) / kUmmaK;
         if constexpr (kGemmType == kKGrouped || kGemmType == kKGroupedPsum) {
             // groups are walked in order; every non-empty group contributes num_m_blocks * num_n_units tiles
@@ -246,6 +256,24 @@ struct Scheduler {
             t.store_m = t.valid_m;
             t.counter_idx = m_blk * (num_n_units * kCtaGroup) + n_unit * kCtaGroup + (cta_rank & 1);
             if constexpr (kGemmType == kMContiguous) group = static_cast<uint32_t>(max(0, __ldg(p.grouped_layout + t.x_row)));
+        } else if constexpr (kGemmType == kBatched) {
+            // every batch is a full [m, n] problem; batches are walked in order (tensor-map coordinate 2 = batch)
+            const uint32_t per_batch = p.num_m_blocks * num_n_units;
+            if (idx >= per_batch * p.num_groups) return false;
+            g = idx < per_batch ? 0u : idx / per_batch;
+            split(idx - g * per_batch, p.num_m_blocks, m_blk, n_unit);
+            t.batch = g;
+            t.x_row = m_blk * p.block_m;
+            t.d_row = t.x_row;
+            t.sfx_col = t.x_row;
+            t.sfx_row = g * p.num_kp_x;
+            t.valid_m = min(p.block_m, p.m - t.x_row);
+            t.store_m = t.valid_m;
+            t.n0 = (n_unit * kCtaGroup + (cta_rank & 1)) * kBlockN;
+            t.w_row = t.n0;
+            t.sfw_col = t.n0;
+            t.sfw_row = g * p.num_kp_w;
+            return true;
         } else if constexpr (kGemmType == kMMasked) {
             uint32_t num_m;
             while (true) {
@@ -270,14 +298,18 @@ struct Scheduler {
         } else {  // kMContiguousPsum
             uint32_t num_m, cover_end;
             while (true) {
-                // rows [row_start, row_end) are real; with zero padding the gap up to the aligned end is written too
+                // rows [row_start, row_end) are real; with zero padding the gap up to the aligned end is written too.
+                // Everything is clamped to the buffer: a caller whose `m` is not a multiple of the alignment (or whose
+                // prefix sums run past it -- an overflowing EP dispatch) gets short segments, never rows >= m.
+                row_start = min(row_start, p.m), row_end = min(max(row_end, row_start), p.m);
                 cover_end = p.zero_padding ? min(p.m, (row_end + p.m_alignment - 1) / p.m_alignment * p.m_alignment) : row_end;
+                cover_end = max(cover_end, row_start);
                 num_m = (cover_end - row_start + p.block_m - 1) / p.block_m;
                 if (idx < (unit_cum + num_m) * num_n_units) break;
                 unit_cum += num_m;
                 if (++g >= p.num_groups) return false;
                 row_start = (row_end + p.m_alignment - 1) / p.m_alignment * p.m_alignment;
-                row_end = max(row_start, static_cast<uint32_t>(__ldg(p.grouped_layout + g)));
+                row_end = max(row_start, static_cast<uint32_t>(max(0, __ldg(p.grouped_layout + g))));
             }
             split(idx - unit_cum * num_n_units, num_m, m_blk, n_unit);
             group = g;
@@ -378,12 +410,18 @@ __device__ __forceinline__ void splitk_finalize(const float* ws, size_t slice_el
 // the same output tile; the partial tiles are exchanged through distributed shared memory (reduce-scatter over the
 // token columns, `st.async` + transaction barrier) and added in slice order, so each weight byte crosses L2->SM once
 // instead of once per m-block and nothing goes through global memory. One tile per cluster (the host guarantees it).
+// kTmaStore: BF16 output tiles leave through shared memory: TMEM -> registers (16x256b fragments) -> BF16 pairs ->
+// `stmatrix.trans` into a 128B-swizzled staging box -> `cp.async.bulk.tensor` store, 16 output rows at a time, two
+// staging buffers per 4-warp group (replaces the reference's epilogue/sm100_store_cd_swap_ab.cuh:22-128). The stores
+// are asynchronous, so the epilogue warps are done with a tile once its accumulator has been read; rows / columns past
+// the end of D are clipped by the tensor map. Used for tall tiles (dense, contiguous); the direct-store epilogue stays
+// for small tiles (all shared memory feeds the ring) and for layouts that need exact row predication (masked, psum).
 template <int kGemmType, int kCluster, typename out_t, bool kAccumulate, bool kXMn = false, bool kWMn = false,
-          bool kSplitK = false, bool kCSplit = false>
+          bool kSplitK = false, bool kCSplit = false, bool kTmaStore = false>
 __global__ void __launch_bounds__(kNumThreads, 1)
 fp8_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
                 const __grid_constant__ CUtensorMap map_sfx, const __grid_constant__ CUtensorMap map_sfw,
-                const __grid_constant__ GemmParams p) {
+                const __grid_constant__ CUtensorMap map_d, const __grid_constant__ GemmParams p) {
 #if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ >= 1000)
     using namespace ptx;
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -405,7 +443,10 @@ fp8_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
     const uint32_t x_tile_bytes = load_m * kBlockK;                         // multiple of 1024 (load_m % 8 == 0)
     const uint32_t num_sfx_groups = (p.block_m + 127) / 128;                // 128-row UTCCP groups of token SFs
     const uint32_t slot_stride = slot_bytes(p.block_m, kCtaGroup);
-    const uint32_t smem_base = smem_u32(smem);
+    static_assert(!kTmaStore || (std::is_same_v<out_t, __nv_bfloat16> && !kAccumulate && !kSplitK && !kCSplit && kCluster == 2),
+                  "the TMA-store epilogue is built for plain BF16 output tiles of a CTA pair");
+    const uint32_t staging = smem_u32(smem);                               // kTmaStore: 2 groups x 2 buffers x 4 KB
+    const uint32_t smem_base = staging + (kTmaStore ? kStoreStagingBytes : 0u);   // the TMA -> MMA ring starts here
     const uint32_t off_x = kWTileBytes, off_sfw = off_x + x_tile_bytes, off_sfx = off_sfw + 512;
     const uint32_t bars = smem_base + num_stages * slot_stride;
     const uint32_t full_bar = bars;                            // TMA bytes landed (per CTA)
@@ -430,7 +471,9 @@ fp8_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
     //  * The others wait, warp 2 allocates tensor memory, and a CTA-local named barrier (warps 1..11) publishes the
     //    TMEM address. The peer's allocation is ordered before the leader's first MMA by the peer's re-tiler warp,
     //    which allocates first and arrives on the leader's `ready` barrier afterwards.
-    constexpr bool kEarlyProducer = kPairs == 1;
+    // (Without a cluster there is no cluster barrier to carry warp 0's mbarrier initialisation to the other warps, so a
+    // single-CTA launch takes the plain __syncthreads() prologue.)
+    constexpr bool kEarlyProducer = kPairs == 1 && kCluster > 1;
     bool producer_lane = false;
     if (warp_idx == 0) {
         for (uint32_t i = lane; i < num_stages; i += 32) {
@@ -445,6 +488,7 @@ fp8_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
             prefetch_tensormap(&map_w);
             prefetch_tensormap(&map_sfx);
             prefetch_tensormap(&map_sfw);
+            if constexpr (kTmaStore) prefetch_tensormap(&map_d);
         }
         __syncwarp();
     } else if (warp_idx == 1) {
@@ -533,6 +577,19 @@ fp8_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
                     const bool first = kb == t.kb_begin;
                     const bool load_sfw = (kb & sfw_mask) == 0 || first, load_sfx = (kb & sfx_mask) == 0 || first;
                     mbar_arrive_expect_tx(full, ab_bytes + (load_sfw ? sfw_tx : 0u) + (load_sfx ? sfx_tx : 0u));
+                    if constexpr (kGemmType == kBatched) {
+                        // 3-D maps {inner, outer, batch}: boxes are one batch deep, so the tiles land exactly like 2-D ones
+                        if constexpr (kWMn)
+                            tma_load_3d(&map_w, full, slot, t.n0, k0, t.batch, p.w_hint);
+                        else
+                            tma_load_3d(&map_w, full, slot, k0, t.w_row, t.batch, p.w_hint);
+                        if constexpr (kXMn) {
+                            for (uint32_t i = 0, off = 0; i < load_m; i += p.x_swizzle, off += p.x_swizzle * kBlockK)
+                                tma_load_3d(&map_x, full, slot + off_x + off, x_row + i, k0, t.batch, p.x_hint);
+                        } else {
+                            tma_load_3d(&map_x, full, slot + off_x, k0, x_row, t.batch, p.x_hint);
+                        }
+                    } else {
                     if constexpr (kWMn) {
                         tma_load_2d(&map_w, full, slot, t.n0, t.wk_base + t.k_base + k0, p.w_hint);
                     } else if constexpr (kPairs == 1) {
@@ -546,6 +603,7 @@ fp8_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
                             tma_load_2d(&map_x, full, slot + off_x + off, x_row + i, t.k_base + k0, p.x_hint);
                     } else {
                         tma_load_2d(&map_x, full, slot + off_x, t.k_base + k0, x_row, p.x_hint);
+                    }
                     }
                     if (load_sfw) tma_load_2d(&map_sfw, full, slot + off_sfw, t.sfw_col, t.sfw_row + (kb >> p.sf_shift_w), kEvictNormal);
                     if (load_sfx) tma_load_2d(&map_sfx, full, slot + off_sfx, t.sfx_col, t.sfx_row + (kb >> p.sf_shift_x), kEvictNormal);
@@ -687,10 +745,14 @@ fp8_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
         const uint32_t tmem_empty_dst = kCtaGroup > 1 ? mapa(tmem_empty_bar, leader_rank) : tmem_empty_bar;
         const size_t row_bytes = static_cast<size_t>(p.ld_d) * sizeof(out_t);
         uint32_t tile_iter = 0;
+        [[maybe_unused]] uint32_t store_iter = 0;              // kTmaStore: units this group has staged so far
+
         while (sched.next(t)) {
             const uint32_t n = t.n0 + quad * 32 + lane;
             const bool n_ok = n < p.n;
-            char* d_col = reinterpret_cast<char*>(d + static_cast<size_t>(t.d_row) * p.ld_d + n);
+            const uint32_t n_store = p.head_mid ? n + (n + p.head_right) / p.head_lr * p.head_mid : n;   // head-split remap
+            char* d_col = reinterpret_cast<char*>(d + static_cast<size_t>(t.batch) * p.d_batch_stride +
+                                                  static_cast<size_t>(t.d_row) * p.ld_d + n_store);
             if (kGemmType == kMContiguousPsum && t.valid_m == 0) {
                 if (n_ok && half == 0)
                     for (uint32_t r = 0; r < t.store_m; ++r) store_out<out_t>(reinterpret_cast<out_t*>(d_col + r * row_bytes), 0.0f, false);
@@ -712,7 +774,7 @@ fp8_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
                 // Staging of owner q: float4 [source slot][c/4 column quads][128 weight rows]; a warp writes / reads 512
                 // contiguous bytes per quad.
                 constexpr uint32_t S = kCluster;
-                const uint32_t c = p.block_m / S, pieces_per_chunk = c / 16, quads = c / 4;
+                const uint32_t c = p.block_m / S, pieces_per_chunk = c / 16;
                 const uint32_t chunk_bytes = c * 128 * 4;                      // one source's partial of one chunk
                 if (threadIdx.x == 4 * 32) mbar_arrive_expect_tx(red_bar, (S - 1) * chunk_bytes);
                 const uint32_t row_n = quad * 32 + lane;                       // weight row of this thread inside the tile
@@ -879,6 +941,45 @@ fp8_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
                 else
                     mbar_arrive(tmem_empty_dst + as * 8);
             };
+            if constexpr (kTmaStore) {
+                // ---------------------------------------------------------------- staged TMA-store epilogue
+                // Work unit = 16 token rows x this CTA's 128 weight rows. The two warps of a lane quadrant belong to two
+                // independent 4-warp groups that take alternate units; each group owns two 4 KB staging buffers.
+                //   tcgen05.ld 16x256b: thread t gets (TMEM lane t/4 (+8), columns 2(t%4), +1) = the stmatrix fragment, so
+                //   one stmatrix.x4.trans writes 8 token rows x 32 weight columns as 16-byte pieces into the swizzled box.
+                const uint32_t num_units = load_cols / kStoreRows;
+                const uint32_t group_bar = 3 + half;
+                const uint32_t bufs = staging + half * (2 * kStoreBufBytes);
+                const uint32_t frag_row = lane & 7, frag_piece = (quad & 1) * 4 + (lane >> 3);
+                const uint32_t frag_off = (quad >> 1) * (kStoreBufBytes / 2) + frag_row * 128 + ((frag_piece ^ frag_row) << 4);
+                if (half >= num_units) release_accumulator();     // nothing to read for this warp
+                for (uint32_t u = half; u < num_units; u += 2, ++store_iter) {
+                    const uint32_t buf = bufs + (store_iter & 1) * kStoreBufBytes;
+                    if (quad == 0) tma_store_wait_read<1>();       // the store that last used this buffer has read it out
+                    named_bar_sync(group_bar, 128);
+                    uint32_t v[16];
+                    const uint32_t ta = taddr + u * kStoreRows;
+                    tmem_ld_16x256b(ta, &v[0]);
+                    tmem_ld_16x256b(ta + (16u << 16), &v[4]);
+                    tmem_ld_16x256b(ta + 8, &v[8]);
+                    tmem_ld_16x256b(ta + 8 + (16u << 16), &v[12]);
+                    tmem_ld_wait();
+                    if (u + 2 >= num_units) release_accumulator();
+                    stmatrix_x4_trans(buf + frag_off, pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]),
+                                      pack_bf16x2(v[6], v[7]));
+                    stmatrix_x4_trans(buf + frag_off + 8 * 128, pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]),
+                                      pack_bf16x2(v[12], v[13]), pack_bf16x2(v[14], v[15]));
+                    fence_proxy_async_smem();                      // generic writes -> visible to the TMA engine
+                    named_bar_sync(group_bar, 128);
+                    if (quad == 0 && lane == 0) {
+                        const uint32_t row = t.d_row + u * kStoreRows;
+                        if (t.n0 < p.n) tma_store_2d(&map_d, buf, t.n0, row);
+                        if (t.n0 + 64 < p.n) tma_store_2d(&map_d, buf + kStoreBufBytes / 2, t.n0 + 64, row);
+                        tma_store_commit();
+                    }
+                }
+                continue;
+            }
             if (half * 32 >= load_cols) release_accumulator();   // nothing to read for this warp
             // 32 token rows per iteration: two TMEM loads in flight, then 32 row stores (one instruction each,
             // 32 consecutive columns per warp). Full chunks take the branch-free path.
@@ -913,6 +1014,9 @@ fp8_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
             if (n_ok && half == 0)
                 for (uint32_t r = t.valid_m; r < t.store_m; ++r)
                     store_out<out_t>(reinterpret_cast<out_t*>(d_col + r * row_bytes), 0.0f, false);
+        }
+        if constexpr (kTmaStore) {
+            if (quad == 0) tma_store_wait_all();               // the staging buffers must outlive every store that reads them
         }
     }
 

@@ -145,6 +145,16 @@ DGB_DEVICE void tma_load_2d(const CUtensorMap* map, uint32_t bar, uint32_t smem_
         : "memory");
 }
 
+// 3-D tiled load (batched GEMM: coordinate 2 = batch, box depth 1)
+DGB_DEVICE void tma_load_3d(const CUtensorMap* map, uint32_t bar, uint32_t smem_dst, uint32_t c0, uint32_t c1, uint32_t c2,
+                            uint64_t hint) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+        " [%0], [%1, {%3, %4, %5}], [%2], %6;" ::"r"(smem_dst),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "l"(hint)
+        : "memory");
+}
+
 // Same, delivered to the same shared-memory offset of every CTA in `cta_mask` (and counted on each one's barrier).
 DGB_DEVICE void tma_load_2d_multicast(const CUtensorMap* map, uint32_t bar, uint32_t smem_dst, uint32_t c0, uint32_t c1,
                                       uint16_t cta_mask, uint64_t hint) {
@@ -153,6 +163,35 @@ DGB_DEVICE void tma_load_2d_multicast(const CUtensorMap* map, uint32_t bar, uint
         " [%0], [%1, {%3, %4}], [%2], %5, %6;" ::"r"(smem_dst),
         "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "h"(cta_mask), "l"(hint)
         : "memory");
+}
+
+// 2-D tiled store: this CTA's shared memory -> global (via tensor map), tracked by the thread's bulk async-group.
+DGB_DEVICE void tma_store_2d(const CUtensorMap* map, uint32_t smem_src, uint32_t c0, uint32_t c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                     reinterpret_cast<uint64_t>(map)),
+                 "r"(smem_src), "r"(c0), "r"(c1)
+                 : "memory");
+}
+DGB_DEVICE void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// at most kPending of this thread's bulk groups may still be READING their shared-memory source
+template <int kPending>
+DGB_DEVICE void tma_store_wait_read() {
+    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(kPending) : "memory");
+}
+DGB_DEVICE void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+// four 8x8 b16 matrices, transposed on the way: matrix i's stored row r (16 bytes at the address given by thread 8i + r)
+// receives element r of every fragment row, i.e. the fragment's column r
+DGB_DEVICE void stmatrix_x4_trans(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("stmatrix.sync.aligned.x4.m8n8.shared.b16.trans [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c),
+                 "r"(d)
+                 : "memory");
+}
+// {lo, hi} FP32 -> packed BF16 pair (round to nearest even), lo in bits [0, 16)
+DGB_DEVICE uint32_t pack_bf16x2(uint32_t lo, uint32_t hi) {
+    uint32_t r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(__uint_as_float(hi)), "f"(__uint_as_float(lo)));
+    return r;
 }
 
 // ---------------------------------------------------------------- tensor memory
@@ -244,6 +283,14 @@ DGB_DEVICE void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&v)[16]) {
 DGB_DEVICE void tmem_ld_32x32b_x8(uint32_t taddr, uint32_t (&v)[8]) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
                  : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                 : "r"(taddr)
+                 : "memory");
+}
+// TMEM -> registers, 16 lanes x 8 columns: thread t gets lane t/4 (regs 0,1) and t/4 + 8 (regs 2,3), columns 2(t%4), +1
+// -- the accumulator-fragment layout stmatrix consumes. Lanes 16..31 of the warp's quadrant: add 16 << 16 to `taddr`.
+DGB_DEVICE void tmem_ld_16x256b(uint32_t taddr, uint32_t* v) {
+    asm volatile("tcgen05.ld.sync.aligned.16x256b.x1.b32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3])
                  : "r"(taddr)
                  : "memory");
 }

@@ -163,10 +163,13 @@ class EpBuffer:
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.group = group
         self.device = torch.device('cuda', torch.cuda.current_device()) if device is None else device
-        capacity = (capacity + 15) // 16 * 16        # the scale-factor rows have a pitch of `capacity` words: TMA wants 16 B
+        self.alignment = runtime.get_mk_alignment_for_contiguous_layout()
+        # whole alignment units (an expert segment may start at any multiple of the alignment below `capacity`, and the
+        # grouped GEMM zero-fills up to the aligned end); also makes the scale-factor pitch a multiple of 16 B for TMA
+        unit = self.alignment * 16 // __import__('math').gcd(self.alignment, 16)
+        capacity = (capacity + unit - 1) // unit * unit
         self.num_experts, self.capacity, self.k = num_experts, capacity, k
         self.kp = _ceil_div(k, 512)
-        self.alignment = runtime.get_mk_alignment_for_contiguous_layout()
         assert num_experts % self.world == 0
         self.nbytes = int(self._lib.dgb200_ep_buffer_bytes(self.world, num_experts, capacity, k))
         offs = (ctypes.c_int64 * 6)()

@@ -15,7 +15,7 @@ def get_num_sms() -> int:
     n = lib().dgb200_get_num_sms()
     if n == 0:
         import torch
-        n = torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count & ~1
+        n = torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count
     return n
 
 

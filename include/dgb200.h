@@ -43,8 +43,9 @@ const char* dgb200_last_error(void);
 int dgb200_version(void);
 
 /* ---- runtime knobs: csrc/apis/runtime.hpp:11-49, csrc/apis/layout.hpp:142-150 --------------------------- */
-int dgb200_set_num_sms(int num_sms);      /* must be even and <= device SM count (heuristics/config.hpp:47) */
-int dgb200_get_num_sms(void);             /* 0 until a device is first used, then the value in effect */
+int dgb200_set_num_sms(int num_sms);      /* 0 <= n <= device SM count, 0 = all (jit/device_runtime.hpp:103-105); odd
+                                             budgets are accepted and rounded down to whole CTA pairs at launch */
+int dgb200_get_num_sms(void);             /* the value set; 0 -> all SMs of the device once one has been used */
 int dgb200_set_tc_util(int percent);      /* accepted for API parity; only the reference's BF16 kernel consumes it */
 int dgb200_get_tc_util(void);
 int dgb200_set_pdl(int enabled);          /* programmatic dependent launch attribute on every kernel launch */
@@ -104,6 +105,37 @@ int dgb200_fp8_gemm_nt(const void* a, const int32_t* sfa, const void* b, const i
  * in slice order. dgb200_workspace_bytes() gives a size that is always sufficient for an (m, n) problem. */
 #define DGB200_WORKSPACE_HEADER_BYTES 16384
 int64_t dgb200_workspace_bytes(int m, int n);
+
+/* Dense GEMM whose output skips a gap in every head  -- fp8_gemm_nt_skip_head_mid, csrc/apis/attention.hpp:19-74
+ * (epilogue remap: deep_gemm/include/deep_gemm/epilogue/transform.cuh:15-22).
+ *   a [m, k], b [n, k] both K-major, gran_k 128; n is a multiple of (head_left + head_right)
+ *   d [m, n + n / (head_left + head_right) * head_mid]: GEMM column j lands at  j + (j + head_right) / (head_left +
+ *   head_right) * head_mid, i.e. each head is written as [left | (mid columns left untouched) | right]. */
+int dgb200_fp8_gemm_nt_skip_head_mid(const void* a, const int32_t* sfa, const void* b, const int32_t* sfb, void* d,
+                                     int m, int n, int k, int64_t lda, int64_t ldb, int64_t ldd,
+                                     int head_left, int head_mid, int head_right,
+                                     int sfa_stride, int sfb_stride, int d_dtype, void* stream);
+
+/* Batched GEMM D[i] (= C[i] +) A[i] B[i]^T     -- fp8_bmm / fp8_einsum, csrc/apis/einsum.hpp:137-214 (launcher
+ * csrc/jit_kernels/impls/sm100_fp8_fp4_gemm_1d1d.hpp:393-467).
+ *   a: batch i at a + i * batch_stride_a; K_MAJOR: rows of k contiguous bytes, pitch lda; MN_MAJOR: m contiguous, k pitch lda
+ *   b: likewise with n;  d: batch i at d + i * batch_stride_d (elements), row pitch ldd, columns contiguous
+ *   Arbitrary (16-byte multiple) pitches, so permuted views such as the "bhr,hdr->bhd" operands need no copy.
+ *   sfa / sfb: packed UE8M0 [batch, mn, ceil(k / (4 gran_k))], MN-major, batch i at i * num_kp * sf_stride words.
+ *   accumulate != 0: D holds C on entry. */
+int dgb200_fp8_bmm(const void* a, const int32_t* sfa, const void* b, const int32_t* sfb, void* d,
+                   int batch, int m, int n, int k, int64_t lda, int64_t ldb, int64_t ldd,
+                   int64_t batch_stride_a, int64_t batch_stride_b, int64_t batch_stride_d,
+                   int major_a, int major_b, int sfa_stride, int sfb_stride, int gran_k_a, int gran_k_b,
+                   int d_dtype, int accumulate, void* stream);
+
+/* Activation quantiser (the step in front of the GEMM in inference)  -- per_token_cast_to_fp8(x, use_ue8m0=True,
+ * gran_k, use_packed_ue8m0=True), deep_gemm/utils/math.py:26-38, fused with the MN-major packing of
+ * csrc/apis/layout.hpp:48-58: x [m, k] BF16 (row pitch ldx elements) -> q [m, k] E4M3 (row pitch ldq bytes) and
+ * sf int32 [m, ceil(k / (4 gran_k))] MN-major (word (r, w) at sf[w * sf_stride + r], sf_stride >= align(m, 4)),
+ * ready to be passed to the GEMMs above. Bit-identical to the reference's Python. gran_k: 32 or 128. */
+int dgb200_per_token_cast_to_fp8(const void* x, int64_t ldx, void* q, int64_t ldq, int32_t* sf, int sf_stride,
+                                 int m, int k, int gran_k, void* stream);
 
 /* Rows of A grouped by expert          -- m_grouped_fp8_fp4_gemm_nt_contiguous, csrc/apis/gemm.hpp:166-232.
  *   a [m, k], b [num_groups, n, k], d [m, n] bf16
@@ -198,6 +230,7 @@ typedef struct dgb200_config {
     int num_tiles;   /* upper bound on (cluster) tiles */
     int num_splits;  /* split-K slices (1 = none) */
     int cluster_split; /* != 0: the slices are the CTAs of one cluster, reduced through distributed shared memory */
+    int tma_store;   /* != 0: output tiles are staged in shared memory and written with TMA stores */
 } dgb200_config;
 /* Pure function (no CUDA): the configuration the heuristics pick for a problem on `num_sms` SMs.
  * gemm_type: 0 dense, 1 m-grouped contiguous, 2 m-grouped masked, 3 m-grouped contiguous psum.
@@ -206,6 +239,10 @@ int dgb200_plan(int gemm_type, int m, int n, int k, int num_groups, int expected
                 dgb200_config* out);
 /* Configuration the last GEMM call on this thread used (DG_PRINT_CONFIGS analogue, heuristics/common.hpp:39-50). */
 int dgb200_last_config(dgb200_config* out);
+/* Measurement aid: issue-only `tcgen05.mma.cta_group::2.kind::mxf8f6f4.block_scale` loop,
+ * UMMA 256 x umma_n x 32, operands resident in shared memory (no TMA, no epilogue), `iters` 128-deep k-blocks per CTA
+ * pair on num_sms SMs (<= 0: all). FLOPs = (num_sms / 2) * iters * 4 * 2 * 256 * umma_n * 32; the caller times it. */
+int dgb200_debug_fp8_peak(int umma_n, int iters, int num_sms, void* stream);
 /* Development aid: when set to a device buffer of (16 + 2 * grid) int64, CTA 0 of every GEMM launch stamps clock64()
  * at ten points of its life (entry, setup done, first TMA, first data, first MMA, last MMA, accumulator ready, stores
  * issued, teardown begin/end) into [0,10) (cluster split-K: outbox written / barrier / copies issued / partials landed

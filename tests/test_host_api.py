@@ -47,8 +47,14 @@ def test_version_and_knobs_roundtrip(lib):
     dg.set_mk_alignment_for_contiguous_layout(224)
     assert dg.get_mk_alignment_for_contiguous_layout() == 224
     dg.set_mk_alignment_for_contiguous_layout(128)
+    # any 0 <= n <= SM count like the reference (jit/device_runtime.hpp:103-105); 0 = all SMs; an odd budget is
+    # accepted (the reference only trips over it later, heuristics/config.hpp:47) and rounded down to whole CTA pairs
+    dg.set_num_sms(147)
+    assert lib.lib().dgb200_get_num_sms() == 147
+    dg.set_num_sms(0)
+    assert lib.lib().dgb200_get_num_sms() == 0
     with pytest.raises(RuntimeError):
-        dg.set_num_sms(147)  # must be even (heuristics/config.hpp:47)
+        dg.set_num_sms(-2)
     with pytest.raises(RuntimeError):
         dg.set_mk_alignment_for_contiguous_layout(100)
 
