@@ -6,14 +6,25 @@ DeepSeek-V3 dense shapes M in {64,128,512,4096}, N=4096, K=7168 (synthetic BF16 
 reference's tests: 1x128 UE8M0 token scales, 128x128 UE8M0 weight scales). `value` = sum(2MNK) / sum(device time) in
 TFLOPS with operands resident in HBM and packed scale factors prepared (kernel-only, cold L2: a 512 MB flush
 precedes every timed launch, timed with CUDA events on the launching stream). `e2e` = the same step through the
-public API from PINNED HOST buffers: H2D of A/B/scale factors, FP32->UE8M0 scale packing, the GEMMs, D2H of D.
+public API from PINNED HOST buffers: H2D of BF16 activations and FP8 weights + scales, the CUDA activation quantiser,
+scale packing, the GEMMs, D2H of D.
 
-Other workloads (not the driver's default): `--workload contiguous` (config 3), `--workload masked` (config 4,
-CUDA-graph replay). With --gpus N > 1 every rank runs an independent replica (the dense GEMM does not shard:
-"replicas only"); `value` is the sum over ranks / max-over-ranks time.
+Outside the timed regions the same line also carries (every block degrades to {"unavailable": reason}):
+  * `vs_reference_kernel` -- the UNMODIFIED reference SM100 kernel (oracle/_ref, JIT-compiled on the box) timed beside
+    ours on the same tensors with the same flush + CUDA-event method, interleaved launch by launch, per dense shape;
+    `bitwise_equal` compares the two outputs with split-K off (north_star: ">= the reference on every listed shape").
+  * `grouped` -- BASELINE configs 3 (contiguous, 256 experts, mean M 128) and 4 (masked decode under a CUDA graph, mean M 64)
+    with their HBM roofline and the same A/B.
+  * `ep` -- BASELINE config 5 at THIS run's --gpus N: the expert-sharded step (peer-memory dispatch + grouped GEMM +
+    weighted top-k combine) with dispatch / GEMM / combine split and, for N > 1, the 1-GPU step run on rank 0 so that
+    `efficiency_vs_n1` is in the line. `value` stays the dense metric (replicas), so the driver's scaling table keeps one
+    metric across N.
+  * `fp8_peak` -- the issue-only tcgen05.mma block-scaled FP8 probe (burst and 2 s sustained); `roofline.peak` uses it.
 
-`--impl reference` times the CPU arm: the torch-CPU BF16-emulated blockwise GEMM (oracle port; the reference has no
-CPU implementation of this path) on a bounded sample of the same step with all host threads.
+`--impl reference` runs the UNMODIFIED reference through its own public API (`deep_gemm.fp8_gemm_nt` from oracle/_ref) on
+the same four shapes with the same method (value kernel-only, e2e from pinned host buffers), as replicas on every rank;
+when the reference cannot be imported it falls back to the torch-CPU BF16-emulated GEMM (oracle port) on a bounded sample.
+Its `cpu_baseline` block is that CPU port in both cases (the reference has no CPU implementation of this path).
 """
 import argparse
 import json
@@ -125,6 +136,97 @@ class ClockSampler:
                 'source': 'nvml' if self._nvml is not None else 'nvidia-smi'}
 
 
+# ------------------------------------------------------------------------------------------------ the reference install
+_REF = None
+
+
+def import_reference():
+    """The UNMODIFIED reference (oracle/_ref, built by oracle/build_ref.sh). `deep_gemm` inside this repository is our alias
+    package, so the reference is imported from its install directory first and stays registered under its own name (bench.py
+    itself only uses `deepgemm_b200`). Raises if it is not there (the caller reports `unavailable`)."""
+    global _REF
+    if _REF is not None:
+        return _REF
+    ref_root = os.path.join(REPO, 'oracle', '_ref')
+    if not os.path.isdir(os.path.join(ref_root, 'deep_gemm')):
+        raise RuntimeError('oracle/_ref is not built (oracle/build_ref.sh needs /root/reference)')
+    os.environ.setdefault('DG_JIT_CACHE_DIR', f'/tmp/dg_ref_cache_{os.environ.get("LOCAL_RANK", "0")}')
+    os.environ.setdefault('CUDA_HOME', '/usr/local/cuda')
+    for k in [k for k in sys.modules if k == 'deep_gemm' or k.startswith('deep_gemm.')]:
+        del sys.modules[k]
+    sys.path.insert(0, ref_root)
+    import deep_gemm as ref
+    assert ref_root in ref.__file__, ref.__file__
+    _REF = ref
+    return _REF
+
+
+def time_ab(fn_a, fn_b, iters, warmup=3):
+    """Device time of two callables on the same stream, interleaved launch by launch, each preceded by an L2 flush and
+    bracketed by CUDA events. Returns (median_a_ms, median_b_ms, min_a_ms, min_b_ms); fn_b may be None."""
+    from deepgemm_b200.testing import flush_l2
+    fns = [f for f in (fn_a, fn_b) if f is not None]
+    for _ in range(warmup):
+        for f in fns:
+            f()
+    torch.cuda.synchronize()
+    evs = [[(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in fns] for _ in range(iters)]
+    for it in range(iters):
+        for j, f in enumerate(fns):
+            flush_l2()
+            evs[it][j][0].record()
+            f()
+            evs[it][j][1].record()
+    torch.cuda.synchronize()
+    out = []
+    for j in range(len(fns)):
+        ts = sorted(e[j][0].elapsed_time(e[j][1]) for e in evs)
+        out.append((ts[len(ts) // 2], ts[0]))
+    if fn_b is None:
+        return out[0][0], None, out[0][1], None
+    return out[0][0], out[1][0], out[0][1], out[1][1]
+
+
+# ------------------------------------------------------------------------------------------------ FP8 tensor peak
+def fp8_peak_block(device):
+    """Issue-only tcgen05.mma block-scaled FP8 probe (csrc/peak_probe.cuh): burst = best of 10 launches of ~1 ms,
+    sustained = back-to-back launches for ~2 s with the SM clock sampled meanwhile."""
+    from deepgemm_b200 import _lib
+    lib = _lib.lib()
+    sms = torch.cuda.get_device_properties(device).multi_processor_count & ~1
+    stream = torch.cuda.current_stream().cuda_stream
+    out = {}
+    for n_, iters in ((256, 4096), (240, 4096)):
+        flops = (sms // 2) * iters * 4 * 2.0 * 256 * n_ * 32
+        for _ in range(3):
+            _lib.check(lib.dgb200_debug_fp8_peak(n_, iters, sms, stream))
+        torch.cuda.synchronize()
+        best = float('inf')
+        for _ in range(10):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            _lib.check(lib.dgb200_debug_fp8_peak(n_, iters, sms, stream))
+            e1.record()
+            torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        out[f'burst_tflops_n{n_}'] = round(flops / (best * 1e-3) / 1e12, 1)
+        if n_ == 256:
+            reps = max(1, int(2000.0 / best))
+            with ClockSampler(torch.cuda.current_device()) as clocks:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(reps):
+                    _lib.check(lib.dgb200_debug_fp8_peak(n_, iters, sms, stream))
+                e1.record()
+                torch.cuda.synchronize()
+            out['sustained_tflops_n256'] = round(flops * reps / (e0.elapsed_time(e1) * 1e-3) / 1e12, 1)
+            out['sustained_seconds'] = round(e0.elapsed_time(e1) * 1e-3, 2)
+            out['sustained_clocks'] = clocks.summary()
+    out['method'] = ('tcgen05.mma.cta_group::2.kind::mxf8f6f4.block_scale, UMMA 256xNx32, operands resident in shared memory '
+                     '(random finite E4M3), one CTA pair per 2 SMs, no TMA / epilogue; FLOPs = pairs*iters*4*2*256*N*32')
+    return out
+
+
 # ------------------------------------------------------------------------------------------------ workloads
 def make_dense_problem(m, n, k, device, seed):
     from deepgemm_b200.utils import per_block_cast_to_fp8, per_token_cast_to_fp8
@@ -132,61 +234,130 @@ def make_dense_problem(m, n, k, device, seed):
     a = torch.randn((m, k), device=device, dtype=torch.bfloat16, generator=g)
     b = torch.randn((n, k), device=device, dtype=torch.bfloat16, generator=g)
     qa, qb = per_token_cast_to_fp8(a, True), per_block_cast_to_fp8(b, True)
-    return qa, qb
+    return a, qa, qb
+
+
+def dense_step_setup(device, gemm, transform):
+    """The four DeepSeek-V3 dense problems with packed scale factors for the implementation behind `gemm` / `transform`."""
+    probs = []
+    for i, (m, n, k) in enumerate(DENSE_SHAPES):
+        a, qa, qb = make_dense_problem(m, n, k, device, seed=i)
+        sfa = transform(qa[1], m, k, (1, 128, 128), None, True)
+        sfb = transform(qb[1], n, k, (1, 128, 128), None, False)
+        d = torch.empty((m, n), device=device, dtype=torch.bfloat16)
+        probs.append(dict(m=m, n=n, k=k, a=a, qa=qa, qb=qb, sfa=sfa, sfb=sfb, d=d))
+    return probs
+
+
+def time_dense_step(args, world, device, probs, gemm, on_first_call=None):
+    """W warm-up steps, then exactly K timed steps; every launch preceded by an L2 flush and bracketed by CUDA events.
+    Returns (per-shape mean ms, per-step ms lists, clock summary, wall seconds)."""
+    from deepgemm_b200.testing import flush_l2
+
+    def step(record=None):
+        for i, p in enumerate(probs):
+            flush_l2()
+            if record is not None:
+                record[i][0].record()
+            gemm((p['qa'][0], p['sfa']), (p['qb'][0], p['sfb']), p['d'])
+            if record is not None:
+                record[i][1].record()
+            elif on_first_call is not None:
+                on_first_call(p)
+
+    # the clock sampler starts before the warm-up: its start-up noise and the idle->busy clock ramp fall outside the timed region
+    with ClockSampler(torch.cuda.current_device()) as clocks:
+        for _ in range(args.warmup):
+            step()
+        torch.cuda.synchronize()
+        barrier(world)
+        events = [[(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in probs]
+                  for _ in range(args.steps)]
+        clocks.rows.clear()
+        t0 = time.perf_counter()
+        for s in range(args.steps):
+            step(events[s])
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - t0
+    barrier(world)
+    per_step_ms = [[e[i][0].elapsed_time(e[i][1]) for i in range(len(probs))] for e in events]
+    per_shape_ms = [sum(st[i] for st in per_step_ms) / args.steps for i in range(len(probs))]
+    return per_shape_ms, per_step_ms, clocks.summary(), wall
+
+
+def dense_ab_block(probs, dg, iters=20):
+    """Per dense shape: ours vs the unmodified reference kernel, same tensors, same flush + CUDA-event method, interleaved."""
+    try:
+        ref = import_reference()
+    except Exception as e:  # noqa: BLE001
+        return {'unavailable': f'{type(e).__name__}: {e}'[:300]}
+    rows = []
+    for p in probs:
+        m, n, k = p['m'], p['n'], p['k']
+        try:
+            sfa_r = ref.transform_sf_into_required_layout(p['qa'][1], m, k, (1, 128, 128), None, True)
+            sfb_r = ref.transform_sf_into_required_layout(p['qb'][1], n, k, (1, 128, 128), None, False)
+            d_ref, d_our = torch.empty_like(p['d']), torch.empty_like(p['d'])
+            f_ref = lambda: ref.fp8_gemm_nt((p['qa'][0], sfa_r), (p['qb'][0], sfb_r), d_ref)   # noqa: E731
+            f_our = lambda: dg.fp8_gemm_nt((p['qa'][0], p['sfa']), (p['qb'][0], p['sfb']), d_our)   # noqa: E731
+            f_ref()                                                       # JIT compile (seconds, once per shape)
+            torch.cuda.synchronize()
+            dg.set_split_k(False)
+            try:
+                f_our()
+                torch.cuda.synchronize()
+                bitwise = bool(torch.equal(d_ref, d_our))
+            finally:
+                dg.set_split_k(True)
+            f_our()
+            torch.cuda.synchronize()
+            default_mismatch = int((d_ref != d_our).sum())
+            ours, refk, ours_min, ref_min = time_ab(f_our, f_ref, iters)
+            rows.append({'m': m, 'n': n, 'k': k, 'ours_us': round(ours * 1e3, 2), 'ref_kernel_us': round(refk * 1e3, 2),
+                         'speedup': round(refk / ours, 4), 'ours_min_us': round(ours_min * 1e3, 2), 'ref_min_us': round(ref_min * 1e3, 2),
+                         'ours_tflops': round(2.0 * m * n * k / (ours * 1e-3) / 1e12, 1),
+                         'ref_tflops': round(2.0 * m * n * k / (refk * 1e-3) / 1e12, 1),
+                         'bitwise_equal': bitwise, 'default_config_mismatching_elements': default_mismatch})
+        except Exception as e:  # noqa: BLE001
+            rows.append({'m': m, 'n': n, 'k': k, 'unavailable': f'{type(e).__name__}: {e}'[:300]})
+    ok = [r for r in rows if 'speedup' in r]
+    return {'method': 'median of %d interleaved launches each, L2 flushed (512 MB write) before every launch, CUDA events; '
+                      'bitwise_equal with set_split_k(False), default_config_mismatching_elements with the default (cluster split-K for M <= 128)' % iters,
+            'reference': 'deepseek-ai/DeepGEMM sm100_fp8_fp4_gemm_1d1d (oracle/_ref, unmodified, NVCC JIT on this box)',
+            'per_shape': rows, 'ours_ge_reference_on_every_shape': bool(ok) and all(r['speedup'] >= 1.0 for r in ok) and len(ok) == len(rows)}
 
 
 def run_dense(args, rank, world, device):
     import deepgemm_b200 as dg
     from deepgemm_b200 import _lib
-    from deepgemm_b200.testing import flush_l2
     peaks, peak_kind = load_peaks()
-    probs = []
-    for i, (m, n, k) in enumerate(DENSE_SHAPES):
-        qa, qb = make_dense_problem(m, n, k, device, seed=i)
-        sfa = dg.transform_sf_into_required_layout(qa[1], m, k, (1, 128, 128), None, True)
-        sfb = dg.transform_sf_into_required_layout(qb[1], n, k, (1, 128, 128), None, False)
-        d = torch.empty((m, n), device=device, dtype=torch.bfloat16)
-        probs.append(dict(m=m, n=n, k=k, qa=qa, qb=qb, sfa=sfa, sfb=sfb, d=d))
+    probs = dense_step_setup(device, dg.fp8_gemm_nt, dg.transform_sf_into_required_layout)
 
-    def step_kernel_only(record=None):
-        for i, p in enumerate(probs):
-            flush_l2()
-            if record is not None:
-                record[i][0].record()
-            dg.fp8_gemm_nt((p['qa'][0], p['sfa']), (p['qb'][0], p['sfb']), p['d'])
-            if record is not None:
-                record[i][1].record()
-            elif 'tile' not in p:
-                cfg = _lib.last_config()
-                p['tile'] = {k_: cfg[k_] for k_ in ('block_m', 'cluster', 'num_stages', 'num_splits', 'cluster_split')}
+    def note_tile(p):
+        if 'tile' not in p:
+            cfg = _lib.last_config()
+            p['tile'] = {k_: cfg[k_] for k_ in ('block_m', 'cluster', 'num_stages', 'num_splits', 'cluster_split', 'tma_store')}
 
-    # ---- kernel-only (inputs resident) ------------------------------------------------------------
-    # The clock sampler (a thread that forks nvidia-smi) starts before the warm-up so that its start-up noise and the
-    # GPU's idle->busy clock ramp fall outside the timed region.
-    with ClockSampler(torch.cuda.current_device()) as clocks:
-        for _ in range(args.warmup):
-            step_kernel_only()
-        torch.cuda.synchronize()
-        barrier(world)
-        events = [[(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in probs]
-                  for _ in range(args.steps)]
-        launches0 = _lib.launch_count()
-        clocks.rows.clear()
-        t_wall0 = time.perf_counter()
-        for s in range(args.steps):
-            step_kernel_only(events[s])
-        torch.cuda.synchronize()
-        t_wall = time.perf_counter() - t_wall0
-    launches = _lib.launch_count() - launches0
-    barrier(world)
-    per_step_ms = [[e[i][0].elapsed_time(e[i][1]) for i in range(len(probs))] for e in events]
-    per_shape_ms = [sum(st[i] for st in per_step_ms) / args.steps for i in range(len(probs))]
-    step_ms = sum(per_shape_ms)
-    step_ms = allreduce_max(step_ms, world, device)
+    launches0 = _lib.launch_count()
+    per_shape_ms, per_step_ms, clock_summary, t_wall = time_dense_step(args, world, device, probs, dg.fp8_gemm_nt, note_tile)
+    launches = (_lib.launch_count() - launches0) * args.steps // (args.steps + args.warmup)
+    step_ms = allreduce_max(sum(per_shape_ms), world, device)
     flops = sum(2.0 * p['m'] * p['n'] * p['k'] for p in probs)
     value = flops * world / (step_ms * 1e-3) / 1e12
 
-    fp8_peak = 2.0 * peaks['bf16_tflops']  # measured proxy: FP8 tensor rate = 2x the measured cuBLAS BF16 burst
+    # ---- FP8 tensor peak: the measured issue-only probe; the 2 x BF16 cuBLAS proxy stays beside it
+    proxy_peak = 2.0 * peaks['bf16_tflops']
+    try:
+        peak_probe = fp8_peak_block(device) if rank == 0 or world == 1 else None
+    except Exception as e:  # noqa: BLE001
+        peak_probe = {'unavailable': f'{type(e).__name__}: {e}'[:300]}
+    fp8_peak, peak_source = proxy_peak, f'2 x {peak_kind} bf16_tflops (MEASURED_PEAKS.json): FP8 probe unavailable'
+    if peak_probe and 'burst_tflops_n256' in peak_probe:
+        fp8_peak = peak_probe['burst_tflops_n256']
+        peak_source = ('measured issue-only tcgen05.mma FP8 block-scaled burst on this GPU (fp8_peak.burst_tflops_n256); '
+                       f'proxy 2 x {peak_kind} bf16_tflops = {proxy_peak:.1f}; nominal dense FP8 = {NOMINAL_FP8_TFLOPS}')
+    if world > 1:
+        fp8_peak = allreduce_max(fp8_peak if rank == 0 else 0.0, world, device)
     per_shape = []
     for p, ms in zip(probs, per_shape_ms):
         m, n, k = p['m'], p['n'], p['k']
@@ -202,48 +373,17 @@ def run_dense(args, rank, world, device):
     dom = per_shape[-1]
     roofline = {'bound': 'tensor', 'kernel': 'fp8_gemm_kernel<dense> M=4096 N=4096 K=7168',
                 'achieved': dom['tflops'], 'peak': round(fp8_peak, 1), 'unit': 'TFLOP/s',
-                'frac': round(dom['tflops'] / fp8_peak, 4),
-                'peak_source': f'2 x {peak_kind} bf16_tflops (MEASURED_PEAKS.json); nominal dense FP8 = {NOMINAL_FP8_TFLOPS}',
+                'frac': round(dom['tflops'] / fp8_peak, 4), 'peak_source': peak_source,
+                'frac_of_2x_bf16_proxy': round(dom['tflops'] / proxy_peak, 4),
                 'frac_of_nominal': round(dom['tflops'] / NOMINAL_FP8_TFLOPS, 4), 'traffic': committed_traffic('dense_m4096'),
                 'algorithmic_bytes': int(4096 * 7168 + 4096 * 7168 + 4096 * 4096 * 2 + 2 * 4096 * 14 * 4),
                 'share_of_step': round(per_shape_ms[-1] / sum(per_shape_ms), 4)}
 
-    # ---- end to end: pinned host buffers -> H2D -> SF pack -> GEMM -> D2H ---------------------------
-    host = []
-    for p in probs:
-        h = {k_: v.cpu().pin_memory() for k_, v in (('a', p['qa'][0].view(torch.uint8)), ('sfa', p['qa'][1]))}
-        h['d'] = torch.empty((p['m'], p['n']), dtype=torch.bfloat16).pin_memory()
-        host.append(h)
-    hb = probs[0]['qb'][0].view(torch.uint8).cpu().pin_memory()
-    hsfb = probs[0]['qb'][1].cpu().pin_memory()
-    # NOTE: all four shapes share N, K: the weight matrix travels once per step
-    dev_a = [torch.empty_like(p['qa'][0].view(torch.uint8)) for p in probs]
-    dev_sfa = [torch.empty_like(p['qa'][1]) for p in probs]
-    dev_b, dev_sfb = torch.empty_like(probs[0]['qb'][0].view(torch.uint8)), torch.empty_like(probs[0]['qb'][1])
-    h2d = hb.numel() + hsfb.numel() * 4 + sum(h['a'].numel() + h['sfa'].numel() * 4 for h in host)
-    d2h = sum(h['d'].numel() * 2 for h in host)
-
-    def step_e2e():
-        dev_b.copy_(hb, non_blocking=True)
-        dev_sfb.copy_(hsfb, non_blocking=True)
-        for i, p in enumerate(probs):
-            dev_a[i].copy_(host[i]['a'], non_blocking=True)
-            dev_sfa[i].copy_(host[i]['sfa'], non_blocking=True)
-            dg.fp8_gemm_nt((dev_a[i].view(torch.float8_e4m3fn), dev_sfa[i]), (dev_b.view(torch.float8_e4m3fn), dev_sfb), p['d'])
-            host[i]['d'].copy_(p['d'], non_blocking=True)
-
-    for _ in range(max(args.warmup, 3)):
-        step_e2e()
-    torch.cuda.synchronize()
-    barrier(world)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        step_e2e()
-    e1.record()
-    torch.cuda.synchronize()
-    barrier(world)
-    e2e_ms = allreduce_max(e0.elapsed_time(e1) / args.steps, world, device)
+    # ---- end to end: pinned host buffers -> H2D -> quantise / pack -> GEMM -> D2H ---------------------------------
+    e2e_ms, h2d, d2h = time_dense_e2e(args, world, device, probs,
+                                      quantise=dg.per_token_cast_to_fp8_packed,
+                                      pack_b=lambda sf, n, k: dg.transform_sf_into_required_layout(sf, n, k, (1, 128, 128), None, False),
+                                      gemm=dg.fp8_gemm_nt)
     e2e_value = flops * world / (e2e_ms * 1e-3) / 1e12
 
     out = {
@@ -253,13 +393,80 @@ def run_dense(args, rank, world, device):
         'data': 'synthetic', 'impl': 'deepgemm_b200',
         'config': {'workload': 'dense fp8_gemm_nt M in {64,128,512,4096} N=4096 K=7168, 1x128/128x128 UE8M0 SF',
                    'l2': 'flushed (512 MB write) before every timed launch', 'parallelism': f'replicas x{world}'},
-        'per_shape': per_shape, 'roofline': roofline, 'clocks': clocks.summary(),
+        'per_shape': per_shape, 'roofline': roofline, 'clocks': clock_summary,
         'e2e': {'value': round(e2e_value, 3), 'unit': 'TFLOPS', 'ms_per_step': round(e2e_ms, 4),
-                'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h)},
+                'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h),
+                'path': 'pinned host BF16 activations + FP8 weights/FP32 scales -> H2D -> CUDA quantiser (packed UE8M0) + weight-scale pack -> fp8_gemm_nt -> D2H'},
         'gpu_launches': int(launches), 'wall_ms_per_step_incl_flush': round(t_wall * 1e3 / args.steps, 3),
         'per_step_us': [[round(x * 1e3, 1) for x in st] for st in per_step_ms[:8]],
     }
-    return out
+    if peak_probe is not None:
+        out['fp8_peak'] = peak_probe
+    return out, probs
+
+
+def add_dense_extras(out, probs, args, rank, world, device):
+    """Outside the timed regions: the comparisons the north star is about (reference-kernel A/B, configs 3 / 4, config 5)."""
+    import deepgemm_b200 as dg
+    if rank == 0:
+        out['vs_reference_kernel'] = guarded(lambda: dense_ab_block(probs, dg))
+    probs.clear()
+    torch.cuda.empty_cache()
+    barrier(world)
+    weights = None
+    if rank == 0:
+        out['grouped'], weights = grouped_blocks(device, dg)
+    barrier(world)
+    out_ep = guarded(lambda: ep_block(args, rank, world, device, dg, weights))
+    if rank == 0:
+        out['ep'] = out_ep
+
+
+def time_dense_e2e(args, world, device, probs, quantise, pack_b, gemm):
+    """The dense step through the public API from pinned HOST buffers: BF16 activations, FP8 weights + FP32 block scales.
+    Every step copies them to the device, quantises the activations (packed UE8M0 out), packs the weight scales, runs the
+    four GEMMs and reads every D back."""
+    host = []
+    for p in probs:
+        host.append({'a': p['a'].cpu().pin_memory(), 'd': torch.empty((p['m'], p['n']), dtype=torch.bfloat16).pin_memory()})
+    hb = probs[0]['qb'][0].view(torch.uint8).cpu().pin_memory()        # all four shapes share N, K: the weight matrix travels once per step
+    hsfb = probs[0]['qb'][1].cpu().pin_memory()
+    dev_a = [torch.empty_like(p['a']) for p in probs]
+    dev_b, dev_sfb = torch.empty_like(probs[0]['qb'][0].view(torch.uint8)), torch.empty_like(probs[0]['qb'][1])
+    h2d = hb.numel() + hsfb.numel() * 4 + sum(h['a'].numel() * 2 for h in host)
+    d2h = sum(h['d'].numel() * 2 for h in host)
+    n, k = probs[0]['n'], probs[0]['k']
+
+    def step():
+        dev_b.copy_(hb, non_blocking=True)
+        dev_sfb.copy_(hsfb, non_blocking=True)
+        sfb = pack_b(dev_sfb, n, k)
+        for i, p in enumerate(probs):
+            dev_a[i].copy_(host[i]['a'], non_blocking=True)
+            qa = quantise(dev_a[i])
+            gemm(qa, (dev_b.view(torch.float8_e4m3fn), sfb), p['d'])
+            host[i]['d'].copy_(p['d'], non_blocking=True)
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    torch.cuda.synchronize()
+    barrier(world)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    barrier(world)
+    return allreduce_max(e0.elapsed_time(e1) / args.steps, world, device), h2d, d2h
+
+
+def guarded(fn):
+    try:
+        return fn()
+    except Exception as e:  # noqa: BLE001
+        import traceback
+        return {'unavailable': f'{type(e).__name__}: {e}'[:300], 'where': traceback.format_exc().strip().splitlines()[-3:]}
 
 
 # ------------------------------------------------------------------------------------------------ grouped workloads
@@ -289,199 +496,302 @@ def _time_events(fn, steps, warmup, world):
     return sum(a.elapsed_time(b) for a, b in evs) / steps
 
 
-def run_grouped(args, rank, world, device):
-    """BASELINE configs 3 (contiguous prefill, 256 experts, N=4096, K=7168) and 4 (masked decode under a CUDA graph,
-    256 experts, M_max=128, N=7168, K=2048). HBM-bound: roofline = algorithmic bytes / measured HBM copy bandwidth."""
+def build_grouped_problem(kind, device, dg, mean_m, weights=None, seed=0):
+    """BASELINE config 3 (`contiguous`) / 4 (`masked`). Returns a dict with `ours` (callable), the tensors the reference
+    needs, and the algorithmic work."""
     import random
-    import deepgemm_b200 as dg
-    from deepgemm_b200 import _lib
     from deepgemm_b200.utils import per_token_cast_to_fp8
-    peaks, peak_kind = load_peaks()
-    random.seed(0)
-    masked = args.workload == 'masked'
+    rnd = random.Random(seed)
     g = 256
-    if masked:
-        m_max, n, k, mean_m = 128, 7168, 2048, args.mean_m or 64
+    if kind == 'masked':
+        m_max, n, k = 128, 7168, 2048
     else:
-        n, k, mean_m = 4096, 7168, args.mean_m or 128
-    b, sfb = _grouped_weights(g, n, k, device, seed=0)
+        n, k = 4096, 7168
+    b, sfb = weights if weights is not None else _grouped_weights(g, n, k, device, seed=0)
     sfb_p = dg.transform_sf_into_required_layout(sfb, n, k, (1, 128, 128), g, False)
-    if masked:
-        a = torch.randn((g, m_max, k), device=device, dtype=torch.bfloat16)
-        qs = [per_token_cast_to_fp8(a[i], True) for i in range(g)]
-        qa = (torch.stack([q[0] for q in qs]), torch.stack([q[1] for q in qs]))
+    if kind == 'masked':
+        a = torch.randn((g * m_max, k), device=device, dtype=torch.bfloat16)
+        q = per_token_cast_to_fp8(a, True)
+        del a
+        qa = (q[0].view(g, m_max, k), q[1].view(g, m_max, -1))
         sfa = dg.transform_sf_into_required_layout(qa[1], m_max, k, (1, 128, 128), g, True)
-        counts = torch.tensor([min(m_max, int(mean_m * random.uniform(0.7, 1.3))) for _ in range(g)], device=device, dtype=torch.int32)
+        counts = torch.tensor([min(m_max, int(mean_m * rnd.uniform(0.7, 1.3))) for _ in range(g)], device=device, dtype=torch.int32)
         d = torch.zeros((g, m_max, n), device=device, dtype=torch.bfloat16)
         valid = int(counts.sum())
-        call = lambda: dg.m_grouped_fp8_gemm_nt_masked((qa[0], sfa), (b, sfb_p), d, counts, int(1.2 * mean_m))  # noqa: E731
+        expected_m = int(1.2 * mean_m)
+        call = lambda: dg.m_grouped_fp8_gemm_nt_masked((qa[0], sfa), (b, sfb_p), d, counts, expected_m)  # noqa: E731
         call()
         graph, side = torch.cuda.CUDAGraph(), torch.cuda.Stream()
         with torch.cuda.stream(side):
             with torch.cuda.graph(graph, stream=side):
                 call()
-        fn = graph.replay
-        rows_total = valid
-        name = f'masked grouped decode (CUDA graph replay), G=256 M_max=128 N=7168 K=2048 mean_m={mean_m}'
-    else:
-        alignment = dg.get_mk_alignment_for_contiguous_layout()
-        ms = [int(mean_m * random.uniform(0.7, 1.3)) for _ in range(g)]
-        aligned = [(x + alignment - 1) // alignment * alignment for x in ms]
-        m = sum(aligned)
-        a = torch.randn((m, k), device=device, dtype=torch.bfloat16)
-        layout = torch.empty(m, device=device, dtype=torch.int32)
-        s0 = 0
-        for i, (mi, ai) in enumerate(zip(ms, aligned)):
-            layout[s0:s0 + mi] = i
-            layout[s0 + mi:s0 + ai] = -1
-            a[s0 + mi:s0 + ai] = 0
-            s0 += ai
-        qa = per_token_cast_to_fp8(a, True)
-        sfa = dg.transform_sf_into_required_layout(qa[1], m, k, (1, 128, 128), None, True)
-        d = torch.empty((m, n), device=device, dtype=torch.bfloat16)
-        valid, rows_total = sum(ms), m
-        fn = lambda: dg.m_grouped_fp8_gemm_nt_contiguous((qa[0], sfa), (b, sfb_p), d, layout)  # noqa: E731
-        name = f'm_grouped contiguous prefill, G=256 N=4096 K=7168 mean_m={mean_m} (sum M={m}, valid {valid}, alignment {alignment})'
+        return dict(kind=kind, ours=graph.replay, ours_eager=call, qa=qa, b=b, sfb=sfb, d=d, counts=counts, expected_m=expected_m,
+                    valid=valid, rows_total=valid, g=g, n=n, k=k, m_max=m_max, _graph=graph,
+                    name=f'masked grouped decode (CUDA graph replay), G=256 M_max=128 N=7168 K=2048 mean_m={mean_m}')
+    alignment = dg.get_mk_alignment_for_contiguous_layout()
+    ms = [int(mean_m * rnd.uniform(0.7, 1.3)) for _ in range(g)]
+    aligned = [(x + alignment - 1) // alignment * alignment for x in ms]
+    m = sum(aligned)
+    a = torch.randn((m, k), device=device, dtype=torch.bfloat16)
+    layout = torch.empty(m, dtype=torch.int32)
+    s0 = 0
+    for i, (mi, ai) in enumerate(zip(ms, aligned)):
+        layout[s0:s0 + mi] = i
+        layout[s0 + mi:s0 + ai] = -1
+        s0 += ai
+    layout = layout.to(device)
+    a[layout < 0] = 0
+    qa = per_token_cast_to_fp8(a, True)
+    del a
+    sfa = dg.transform_sf_into_required_layout(qa[1], m, k, (1, 128, 128), None, True)
+    d = torch.empty((m, n), device=device, dtype=torch.bfloat16)
+    fn = lambda: dg.m_grouped_fp8_gemm_nt_contiguous((qa[0], sfa), (b, sfb_p), d, layout)  # noqa: E731
+    return dict(kind=kind, ours=fn, qa=qa, b=b, sfb=sfb, d=d, layout=layout, valid=sum(ms), rows_total=m, g=g, n=n, k=k,
+                name=f'm_grouped contiguous prefill, G=256 N=4096 K=7168 mean_m={mean_m} (sum M={m}, valid {sum(ms)}, alignment {alignment})')
+
+
+def grouped_reference_fn(p):
+    """The unmodified reference on the same tensors (its own SF transform; masked: under its own CUDA graph)."""
+    ref = import_reference()
+    g, n, k = p['g'], p['n'], p['k']
+    sfb_r = ref.transform_sf_into_required_layout(p['sfb'], n, k, (1, 128, 128), g, False)
+    d_ref = torch.zeros_like(p['d'])
+    if p['kind'] == 'masked':
+        sfa_r = ref.transform_sf_into_required_layout(p['qa'][1], p['m_max'], k, (1, 128, 128), g, True)
+        call = lambda: ref.m_grouped_fp8_gemm_nt_masked((p['qa'][0], sfa_r), (p['b'], sfb_r), d_ref, p['counts'], p['expected_m'])  # noqa: E731
+        call()
+        torch.cuda.synchronize()
+        graph, side = torch.cuda.CUDAGraph(), torch.cuda.Stream()
+        with torch.cuda.stream(side):
+            with torch.cuda.graph(graph, stream=side):
+                call()
+        p['_ref_graph'] = graph
+        return graph.replay, d_ref
+    sfa_r = ref.transform_sf_into_required_layout(p['qa'][1], p['rows_total'], k, (1, 128, 128), None, True)
+    ref.set_mk_alignment_for_contiguous_layout(128)
+    call = lambda: ref.m_grouped_fp8_gemm_nt_contiguous((p['qa'][0], sfa_r), (p['b'], sfb_r), d_ref, p['layout'])  # noqa: E731
+    call()
+    torch.cuda.synchronize()
+    return call, d_ref
+
+
+def grouped_line(p, ms_step, peaks, peak_kind):
+    g, n, k = p['g'], p['n'], p['k']
+    rows = p['rows_total']
+    flops = 2.0 * p['valid'] * n * k
+    byts = rows * k + g * n * k + rows * n * 2 + (rows + g * n) * ((k + 511) // 512) * 4
+    gbs = byts / (ms_step * 1e-3) / 1e9
+    return {'workload': p['name'], 'us': round(ms_step * 1e3, 1), 'tokens_per_s': round(p['valid'] / (ms_step * 1e-3), 1),
+            'tflops': round(flops / (ms_step * 1e-3) / 1e12, 1),
+            'roofline': {'bound': 'hbm', 'achieved': round(gbs, 1), 'peak': peaks['hbm_gbs'], 'unit': 'GB/s',
+                         'frac': round(gbs / peaks['hbm_gbs'], 4), 'peak_source': peak_kind + ' hbm_gbs (MEASURED_PEAKS.json)',
+                         'algorithmic_bytes': int(byts), 'traffic': committed_traffic('contiguous_g256_m128' if p['kind'] != 'masked' else 'masked_g256_m64')}}
+
+
+def grouped_blocks(device, dg, iters=10):
+    """Configs 3 and 4 beside the reference kernel (rank 0, outside the dense timed region). Returns (block, weights of the
+    contiguous problem for reuse by the 1-GPU EP step)."""
+    from deepgemm_b200 import _lib
+    peaks, peak_kind = load_peaks()
+    out, keep = {}, None
+    for kind, mean_m in (('contiguous', 128), ('masked', 64)):
+        try:
+            p = build_grouped_problem(kind, device, dg, mean_m)
+            p['ours']()
+            torch.cuda.synchronize()
+            tile = _lib.last_config()
+            try:
+                f_ref, d_ref = grouped_reference_fn(p)
+                ref_err = None
+            except Exception as e:  # noqa: BLE001
+                f_ref, d_ref, ref_err = None, None, f'{type(e).__name__}: {e}'[:300]
+            ours, refk, ours_min, ref_min = time_ab(p['ours'], f_ref, iters)
+            line = grouped_line(p, ours, peaks, peak_kind)
+            line['tile'] = tile
+            if f_ref is not None:
+                p['ours']()
+                f_ref()
+                torch.cuda.synchronize()
+                if kind == 'masked':
+                    rows = torch.arange(p['m_max'], device=device).unsqueeze(0) < p['counts'].unsqueeze(1)
+                    same = bool(torch.equal(p['d'][rows], d_ref[rows]))
+                else:
+                    same = bool(torch.equal(p['d'][p['layout'] >= 0], d_ref[p['layout'] >= 0]))
+                line.update({'ref_kernel_us': round(refk * 1e3, 1), 'speedup': round(refk / ours, 4), 'ours_min_us': round(ours_min * 1e3, 1),
+                             'ref_min_us': round(ref_min * 1e3, 1), 'bitwise_equal_valid_rows': same})
+            else:
+                line['reference'] = {'unavailable': ref_err}
+            out[kind] = line
+            if kind == 'contiguous':
+                keep = (p['b'], p['sfb'])
+            p.pop('_graph', None), p.pop('_ref_graph', None)
+            del p, d_ref, f_ref
+        except Exception as e:  # noqa: BLE001
+            out[kind] = {'unavailable': f'{type(e).__name__}: {e}'[:300]}
+        torch.cuda.empty_cache()
+    out['method'] = f'median of {iters} interleaved launches each (ours, reference), L2 flushed before every launch, CUDA events'
+    return out, keep
+
+
+def run_grouped(args, rank, world, device):
+    """`--workload contiguous|masked`: BASELINE configs 3 / 4 as the headline line (HBM-bound: roofline = algorithmic bytes /
+    measured HBM copy bandwidth)."""
+    import deepgemm_b200 as dg
+    from deepgemm_b200 import _lib
+    peaks, peak_kind = load_peaks()
+    masked = args.workload == 'masked'
+    p = build_grouped_problem(args.workload, device, dg, args.mean_m or (64 if masked else 128))
     launches0 = _lib.launch_count()
     with ClockSampler(torch.cuda.current_device()) as clocks:
-        ms_step = _time_events(fn, args.steps, args.warmup, world)
+        ms_step = _time_events(p['ours'], args.steps, args.warmup, world)
     ms_step = allreduce_max(ms_step, world, device)
     launches = (_lib.launch_count() - launches0) if not masked else args.steps + args.warmup  # graph replays relaunch the kernel
-    flops = 2.0 * valid * n * k
-    byts = rows_total * k + g * n * k + rows_total * n * 2 + (rows_total + g * n) * ((k + 511) // 512) * 4
-    gbs = byts / (ms_step * 1e-3) / 1e9
+    line = grouped_line(p, ms_step, peaks, peak_kind)
     return {
-        'metric': 'grouped FP8 GEMM tokens/s (valid rows / kernel time)', 'value': round(valid * world / (ms_step * 1e-3), 1),
+        'metric': 'grouped FP8 GEMM tokens/s (valid rows / kernel time)', 'value': round(p['valid'] * world / (ms_step * 1e-3), 1),
         'unit': 'tokens/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': round(ms_step, 4),
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'fp8_e4m3 (fp32 accumulate, bf16 out)',
-        'data': 'synthetic', 'impl': 'deepgemm_b200', 'tflops': round(flops / (ms_step * 1e-3) / 1e12, 1),
-        'config': {'workload': name, 'l2': 'flushed (512 MB write) before every timed launch', 'parallelism': f'replicas x{world}',
+        'data': 'synthetic', 'impl': 'deepgemm_b200', 'tflops': line['tflops'],
+        'config': {'workload': p['name'], 'l2': 'flushed (512 MB write) before every timed launch', 'parallelism': f'replicas x{world}',
                    'tile': _lib.last_config()},
-        'roofline': {'bound': 'hbm', 'achieved': round(gbs, 1), 'peak': peaks['hbm_gbs'], 'unit': 'GB/s',
-                     'frac': round(gbs / peaks['hbm_gbs'], 4), 'peak_source': peak_kind + ' hbm_gbs (MEASURED_PEAKS.json)', 'traffic': None},
-        'clocks': clocks.summary(), 'gpu_launches': int(launches),
+        'roofline': line['roofline'], 'clocks': clocks.summary(), 'gpu_launches': int(launches),
         'e2e': {'value': None, 'unit': 'tokens/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0,
                 'note': 'grouped workloads keep the 7.5 / 3.8 GB of expert weights resident; see the dense workload for e2e'},
     }
 
 
-def run_ep(args, rank, world, device):
-    """BASELINE config 5: 256 experts sharded over the ranks; tokens written straight into the owners' GEMM input
-    buffers by the peer-memory dispatch kernels (NVLink stores), then the local grouped GEMM. No host sync per step."""
-    import deepgemm_b200 as dg
-    from deepgemm_b200 import _lib, ep
+# ------------------------------------------------------------------------------------------------ expert-sharded step
+def ep_step_timing(steps, warmup, world, device, dg, buf, xq, sf_packed, ids, wq, sfb_p, n, group_world):
+    """dispatch -> grouped GEMM -> weighted combine on `buf`; per-phase CUDA-event times, max over the ranks of
+    `group_world` (1 = this rank alone)."""
+    t_local = xq.shape[0]
+    d = buf.output(n)
+    token_row = torch.empty(t_local, dtype=torch.int32, device=device)
+    out_tokens = torch.empty((t_local, n), device=device, dtype=torch.bfloat16)
+
+    def step(ev=None):
+        if ev:
+            ev[0].record()
+        r = buf.dispatch(xq, sf_packed, ids, token_row)
+        if ev:
+            ev[1].record()
+        buf.grouped_gemm((wq, sfb_p), d, r.expected_m, overlap=False)
+        if ev:
+            ev[2].record()
+        buf.combine(token_row, ids, out_tokens)
+        if ev:
+            ev[3].record()
+
+    for _ in range(warmup):
+        step()
+    torch.cuda.synchronize()
+    assert not buf.overflowed(), 'dispatch buffer capacity exceeded'
+    barrier(group_world)
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(steps)]
+    for e in evs:
+        step(e)
+    torch.cuda.synchronize()
+    barrier(group_world)
+    mean = lambda i, j: sum(e[i].elapsed_time(e[j]) for e in evs) / steps  # noqa: E731
+    res = {'dispatch_ms': mean(0, 1), 'gemm_ms': mean(1, 2), 'combine_ms': mean(2, 3), 'step_ms': mean(0, 3)}
+    if group_world > 1:
+        res = {k_: allreduce_max(v, group_world, device) for k_, v in res.items()}
+    return res
+
+
+def ep_problem(rank, world, device, dg, g, n, k, tokens_total, weights=None):
     from deepgemm_b200.utils import per_token_cast_to_fp8
-    g, n, k, tokens_total = 256, 4096, 7168, 32768
-    epr = g // world
-    t_local = tokens_total // world
-    align = dg.get_mk_alignment_for_contiguous_layout()
-    b, sfb = _grouped_weights(epr, n, k, device, seed=1000 + rank)
+    epr, t_local = g // world, tokens_total // world
+    if weights is not None and weights[0].shape[0] == epr:
+        b, sfb = weights
+    else:
+        b, sfb = _grouped_weights(epr, n, k, device, seed=1000 + rank)
     sfb_p = dg.transform_sf_into_required_layout(sfb, n, k, (1, 128, 128), epr, False)
     gen = torch.Generator(device=device).manual_seed(rank)
     x = torch.randn((t_local, k), device=device, dtype=torch.bfloat16, generator=gen)
     xq, sf_packed = per_token_cast_to_fp8(x, True, 128, use_packed_ue8m0=True)
     ids = torch.randint(0, g, (t_local,), device=device, generator=gen)
+    align = dg.get_mk_alignment_for_contiguous_layout()
     # capacity: balanced routing + 25% head room + alignment padding (a production caller sizes for its worst case)
     capacity = (int(t_local * 1.25) + epr * align + 127) // 128 * 128
+    return b, sfb_p, xq, sf_packed, ids, capacity
+
+
+def ep_block(args, rank, world, device, dg, weights_1gpu=None, steps=10, warmup=3):
+    """BASELINE config 5 at this run's world size: 256 experts sharded over the ranks, 32768 tokens (top-1), N=4096, K=7168.
+    One step = peer-memory dispatch (one persistent kernel) + local grouped GEMM + combine over NVLink. For world > 1 rank 0
+    also runs the same 32768 tokens on one GPU so that the strong-scaling efficiency is in the line."""
+    from deepgemm_b200 import ep
+    g, n, k, tokens_total = 256, 4096, 7168, 32768
+    res = {'workload': f'expert-sharded grouped GEMM: 256 experts over {world} GPU(s), 32768 tokens top-1, N=4096 K=7168; '
+                       'step = dispatch (NVLink peer stores into the owner\'s GEMM buffer) + grouped GEMM + combine',
+           'steps': steps, 'warmup': warmup, 'parallelism': f'ep{world}', 'scaling': 'strong'}
+    b, sfb_p, xq, sf_packed, ids, capacity = ep_problem(rank, world, device, dg, g, n, k, tokens_total, weights_1gpu if world == 1 else None)
     buf = ep.EpBuffer(g, capacity, k)
-    d = buf.output(n)                      # symmetric (peer-mapped) output, so that the combine can be timed too
-    token_row = torch.empty(t_local, dtype=torch.int32, device=device)
-    overlap = os.environ.get('DGB200_EP_OVERLAP', '0') != '0'   # GEMM beside the scatter (per-expert arrival counters)
+    try:
+        t = ep_step_timing(steps, warmup, world, device, dg, buf, xq, sf_packed, ids, b, sfb_p, n, world)
+    finally:
+        buf.close()
+    del b, sfb_p, xq, sf_packed, ids
+    torch.cuda.empty_cache()
+    res.update({k_: round(v, 4) for k_, v in t.items()})
+    res['tokens_per_s'] = round(tokens_total / (t['step_ms'] * 1e-3), 1)
+    res['tflops'] = round(2.0 * tokens_total * n * k / (t['step_ms'] * 1e-3) / 1e12, 1)
+    row_bytes = k + 4 * ((k + 511) // 512)
+    res['dispatch_wire_bytes_per_rank'] = int(tokens_total // world * row_bytes)
+    res['dispatch_remote_bytes_per_rank'] = int(tokens_total // world * row_bytes * (world - 1) / world)
+    if world > 1:
+        # the 1-GPU step of the same problem, on rank 0 alone (the others wait at the barrier below)
+        one = None
+        if rank == 0:
+            b1, sfb1, xq1, sf1, ids1, cap1 = ep_problem(0, 1, device, dg, g, n, k, tokens_total)
+            buf1 = ep.EpBuffer(g, cap1, k, local_only=True)
+            try:
+                one = ep_step_timing(steps, warmup, 1, device, dg, buf1, xq1, sf1, ids1, b1, sfb1, n, 1)
+            finally:
+                buf1.close()
+            del b1, sfb1, xq1, sf1, ids1
+            torch.cuda.empty_cache()
+        barrier(world)
+        if rank == 0:
+            res['n1'] = {k_: round(v, 4) for k_, v in one.items()}
+            res['speedup_vs_n1'] = round(one['step_ms'] / t['step_ms'], 3)
+            res['efficiency_vs_n1'] = round(one['step_ms'] / t['step_ms'] / world, 4)
+            res['gemm_efficiency_vs_n1'] = round(one['gemm_ms'] / t['gemm_ms'] / world, 4)
+    else:
+        res['speedup_vs_n1'], res['efficiency_vs_n1'] = 1.0, 1.0
+    return res
 
-    def step(record=None):
-        if record:
-            record[0].record()
-        r = buf.dispatch(xq, sf_packed, ids, token_row, wait=not overlap)
-        if record:
-            if overlap:
-                record[1] = record[0]      # nothing may sit between the scatter and its dependent GEMM launch
-            else:
-                record[1].record()
-        buf.grouped_gemm((b, sfb_p), d, r.expected_m, overlap=overlap)
-        if record:
-            record[2].record()
 
-    for _ in range(args.warmup):
-        step()
-    torch.cuda.synchronize()
-    assert not buf.overflowed(), 'dispatch buffer capacity exceeded'
-    barrier(world)
-    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
+def run_ep(args, rank, world, device):
+    """`--workload ep`: BASELINE config 5 as the headline line."""
+    import deepgemm_b200 as dg
+    from deepgemm_b200 import _lib
     launches0 = _lib.launch_count()
     with ClockSampler(torch.cuda.current_device()) as clocks:
-        for e in evs:
-            step(e)
-        torch.cuda.synchronize()
+        blk = ep_block(args, rank, world, device, dg, None, steps=args.steps, warmup=args.warmup)
     launches = _lib.launch_count() - launches0
-    barrier(world)
-    disp = sum(e[0].elapsed_time(e[1]) for e in evs) / args.steps
-    gemm = sum(e[1].elapsed_time(e[2]) for e in evs) / args.steps
-    total = allreduce_max(disp + gemm, world, device)
-    disp, gemm = allreduce_max(disp, world, device), allreduce_max(gemm, world, device)
-
-    # the way back (top-1 combine: every source pulls its tokens' output rows over NVLink), timed on its own
-    out_tokens = torch.empty((t_local, n), device=device, dtype=torch.bfloat16)
-    step()
-    buf.combine(token_row, ids, out_tokens)
-    torch.cuda.synchronize()
-    barrier(world)
-    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    comb = 0.0
-    for _ in range(3):
-        step()
-        c0.record()
-        buf.combine(token_row, ids, out_tokens)
-        c1.record()
-        torch.cuda.synchronize()
-        comb += c0.elapsed_time(c1) / 3
-    combine_ms = allreduce_max(comb, world, device)
-
-    # library baseline for the same dispatch: NCCL all-to-all + torch re-layout (outside the timed region)
-    group = torch.distributed.group.WORLD if world > 1 else None
-    def baseline():
-        return ep.dispatch_alltoall(xq, sf_packed, ids, g, align, group) if world > 1 else \
-            ep.dispatch_local(xq, sf_packed, ids, g, align)
-    baseline()
-    torch.cuda.synchronize()
-    barrier(world)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(3):
-        baseline()
-    e1.record()
-    torch.cuda.synchronize()
-    base_ms = allreduce_max(e0.elapsed_time(e1) / 3, world, device)
-
-    row_bytes = k + 4 * ((k + 511) // 512)
-    wire = t_local * row_bytes                                    # bytes this rank's scatter kernel moves (read + write each)
-    remote = wire * (world - 1) / world
     peaks, peak_kind = load_peaks()
-    gbs = 2.0 * wire / (disp * 1e-3) / 1e9 if disp > 0 else 0.0
-    buf_rows = buf.num_rows()
-    buf.close()
+    total = blk['step_ms']
+    gbs = 2.0 * blk['dispatch_wire_bytes_per_rank'] / (blk['dispatch_ms'] * 1e-3) / 1e9 if blk['dispatch_ms'] > 0 else 0.0
     return {
-        'metric': 'expert-sharded grouped FP8 GEMM tokens/s (dispatch + GEMM)', 'value': round(tokens_total / (total * 1e-3), 1),
+        'metric': 'expert-sharded grouped FP8 GEMM tokens/s (dispatch + GEMM + combine)', 'value': blk['tokens_per_s'],
         'unit': 'tokens/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': round(total, 4),
         'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'fp8_e4m3 (fp32 accumulate, bf16 out)',
         'data': 'synthetic', 'impl': 'deepgemm_b200',
-        'config': {'workload': f'expert-sharded grouped GEMM: 256 experts over {world} GPU(s), 32768 tokens, N=4096 K=7168, '
-                               'peer-memory dispatch (NVLink stores of FP8 rows + packed UE8M0 SFs into the owner\'s GEMM buffer)',
-                   'parallelism': f'ep{world}', 'l2': 'inputs (>= 0.9 GB of expert weights per rank) exceed L2'},
-        'dispatch_ms': round(disp, 4), 'gemm_ms': round(gemm, 4), 'dispatch_alltoall_baseline_ms': round(base_ms, 4),
-        'combine_ms': round(combine_ms, 4), 'overlap': bool(overlap), 'overlap_note': 'with overlap the two phases share the GPU: dispatch_ms/gemm_ms are stream-event splits, only ms_per_step is meaningful',
-        'tflops': round(2.0 * tokens_total * n * k / (total * 1e-3) / 1e12, 1),
-        'wire_bytes_per_rank': int(wire), 'remote_bytes_per_rank': int(remote), 'rows_received_rank0': buf_rows,
-        'roofline': {'kernel': 'ep::scatter_kernel (+bucket/exchange/wait)', 'bound': 'hbm', 'achieved': round(gbs, 1),
+        'config': {'workload': blk['workload'], 'parallelism': f'ep{world}', 'l2': 'inputs (>= 0.9 GB of expert weights per rank) exceed L2'},
+        'ep': blk,
+        'roofline': {'kernel': 'ep::dispatch_fused_kernel', 'bound': 'hbm', 'achieved': round(gbs, 1),
                      'peak': peaks['hbm_gbs'], 'unit': 'GB/s', 'frac': round(gbs / peaks['hbm_gbs'], 4),
                      'peak_source': peak_kind + ' hbm_gbs (MEASURED_PEAKS.json)', 'traffic': None,
-                     'note': 'algorithmic bytes = read + write of every local token row once; the remote share crosses NVLink'},
+                     'note': 'algorithmic bytes = read + write of every local token row once; the remote share crosses NVLink (770 GB/s per direction measured)'},
         'clocks': clocks.summary(), 'gpu_launches': int(launches),
-        'e2e': {'value': round(tokens_total / (total * 1e-3), 1), 'unit': 'tokens/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0,
+        'e2e': {'value': blk['tokens_per_s'], 'unit': 'tokens/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0,
                 'note': 'tokens originate on the GPUs (output of the previous layer); nothing crosses PCIe in this path'},
     }
 
 
-# ------------------------------------------------------------------------------------------------ CPU arm
+# ------------------------------------------------------------------------------------------------ reference arm
 def cpu_reference_step(shapes, threads):
     """torch-CPU BF16-emulated blockwise GEMM (oracle port) over `shapes`; returns (seconds, flops)."""
     from deepgemm_b200.utils import per_block_cast_to_fp8, per_token_cast_to_fp8
@@ -512,9 +822,40 @@ def cpu_baseline_block():
             'seconds': round(sec, 3)}
 
 
-def run_reference_arm(args, rank, world):
-    if rank != 0:
-        return None
+def run_reference_arm_gpu(args, rank, world, device):
+    """The UNMODIFIED reference (oracle/_ref) through its own public API on the same step, same method: kernel-only `value`
+    (its SM100 kernel with its own packed scale factors) and `e2e` from pinned host buffers (its Python quantiser path:
+    FP8 + FP32 scales on the host -> H2D -> its own SF transform + GEMM -> D2H)."""
+    ref = import_reference()
+    probs = dense_step_setup(device, ref.fp8_gemm_nt, ref.transform_sf_into_required_layout)
+    per_shape_ms, per_step_ms, clock_summary, _ = time_dense_step(args, world, device, probs, ref.fp8_gemm_nt)
+    step_ms = allreduce_max(sum(per_shape_ms), world, device)
+    flops = sum(2.0 * p['m'] * p['n'] * p['k'] for p in probs)
+    value = flops * world / (step_ms * 1e-3) / 1e12
+    # e2e: the reference has no CUDA activation quantiser; its callers quantise with the torch helpers of deep_gemm.utils.
+    from deepgemm_b200.utils import per_token_cast_to_fp8 as torch_quantiser   # bit-identical restatement of the reference's helper
+    e2e_ms, h2d, d2h = time_dense_e2e(args, world, device, probs,
+                                      quantise=lambda a: torch_quantiser(a, True),
+                                      pack_b=lambda sf, n, k: sf, gemm=ref.fp8_gemm_nt)
+    return {
+        'impl': 'reference', 'metric': 'FP8 TFLOPS over the DeepSeek-V3 dense shapes (sum 2MNK / sum kernel time)',
+        'value': round(value, 2), 'unit': 'TFLOPS', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+        'ms_per_step': round(step_ms, 4), 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'dtype': 'fp8_e4m3 (fp32 accumulate, bf16 out)', 'data': 'synthetic',
+        'reference': 'deepseek-ai/DeepGEMM, unmodified, oracle/_ref: deep_gemm.fp8_gemm_nt -> sm100_fp8_fp4_gemm_1d1d (NVCC JIT on this box)',
+        'config': {'workload': 'dense fp8_gemm_nt M in {64,128,512,4096} N=4096 K=7168, 1x128/128x128 UE8M0 SF',
+                   'l2': 'flushed (512 MB write) before every timed launch', 'parallelism': f'replicas x{world}'},
+        'per_shape': [{'m': p['m'], 'n': p['n'], 'k': p['k'], 'us': round(ms * 1e3, 2),
+                       'tflops': round(2.0 * p['m'] * p['n'] * p['k'] / (ms * 1e-3) / 1e12, 1)} for p, ms in zip(probs, per_shape_ms)],
+        'clocks': clock_summary,
+        'e2e': {'value': round(flops * world / (e2e_ms * 1e-3) / 1e12, 3), 'unit': 'TFLOPS', 'ms_per_step': round(e2e_ms, 4),
+                'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h),
+                'path': 'pinned host BF16 activations + FP8 weights/FP32 scales -> H2D -> torch quantiser (deep_gemm.utils.per_token_cast_to_fp8) -> deep_gemm.fp8_gemm_nt (its own SF transform) -> D2H'},
+        'gpu_launches': 0,
+    }
+
+
+def run_reference_arm_cpu(args, why):
     threads = os.cpu_count() or 1
     sample = DENSE_SHAPES[:3]
     for _ in range(min(args.warmup, 1)):
@@ -528,11 +869,12 @@ def run_reference_arm(args, rank, world):
     v = round(fl / sec / 1e12, 4)
     return {
         'impl': 'reference', 'metric': 'FP8 TFLOPS over the DeepSeek-V3 dense shapes (sum 2MNK / sum kernel time)',
-        'value': v, 'unit': 'TFLOPS', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+        'value': v, 'unit': 'TFLOPS', 'n_gpus': 1, 'steps': args.steps, 'warmup': args.warmup,
         'ms_per_step': round(sec * 1e3, 3), 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
         'dtype': 'bf16 emulation of fp8_e4m3 x ue8m0 (fp32 accumulate)', 'data': 'synthetic',
         'config': {'workload': 'dense fp8_gemm_nt M in {64,128,512,4096} N=4096 K=7168, 1x128/128x128 UE8M0 SF',
                    'sample': 'bounded: M in {64,128,512} per step'},
+        'reference_kernel_unavailable': why,
         'cpu_baseline': {'value': v, 'unit': 'TFLOPS', 'cores': threads, 'kind': 'port',
                          'sample': 'M in {64,128,512} of the dense step, torch CPU BF16 matmul of the dequantised operands'},
         'e2e': {'value': v, 'unit': 'TFLOPS', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
@@ -564,6 +906,8 @@ def main():
     ap.add_argument('--workload', default='dense', choices=['dense', 'contiguous', 'masked', 'ep'])
     ap.add_argument('--mean-m', type=int, default=0)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-extras', action='store_true', help='dense workload: skip the reference A/B, grouped and EP blocks')
+    ap.add_argument('--extras-timeout', type=float, default=420.0)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -571,12 +915,10 @@ def main():
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
 
-    if args.impl == 'reference':
-        out = run_reference_arm(args, rank, world)
-        if out is not None:
-            print(json.dumps(out), flush=True)
+    if args.impl == 'reference' and not torch.cuda.is_available():
+        if rank == 0:
+            print(json.dumps(run_reference_arm_cpu(args, 'no CUDA device')), flush=True)
         return
-
     if not torch.cuda.is_available():
         raise SystemExit('bench.py needs a CUDA device (the FP8 GEMM path has no CPU fallback)')
     torch.cuda.set_device(local_rank)
@@ -584,13 +926,43 @@ def main():
     if world > 1:
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
         torch.distributed.init_process_group(backend='nccl', device_id=device)
-    runner = {'dense': run_dense, 'contiguous': run_grouped, 'masked': run_grouped, 'ep': run_ep}[args.workload]
-    out = runner(args, rank, world, device)
-    if rank == 0:
-        if not args.no_cpu_baseline and args.workload == 'dense':
-            out['cpu_baseline'] = cpu_baseline_block()
+
+    if args.impl == 'reference':
+        try:
+            import_reference()
+            why = None
+        except Exception as e:  # noqa: BLE001
+            why = f'{type(e).__name__}: {e}'[:300]
+        if why is None:
+            out = run_reference_arm_gpu(args, rank, world, device)
+            if rank == 0 and not args.no_cpu_baseline:
+                out['cpu_baseline'] = cpu_baseline_block()
+        else:
+            out = run_reference_arm_cpu(args, why) if rank == 0 else None
+    else:
+        if args.workload == 'dense':
+            out, probs = run_dense(args, rank, world, device)
+            if rank == 0 and not args.no_cpu_baseline:
+                out['cpu_baseline'] = cpu_baseline_block()
+            if not args.no_extras:
+                # The extra blocks JIT-compile the reference and run multi-rank handshakes: if any of it wedges, the line
+                # measured above must still come out. A watchdog prints it and leaves.
+                def bail():
+                    if rank == 0:
+                        out.setdefault('extras', {'unavailable': f'watchdog: extra blocks exceeded {args.extras_timeout} s'})
+                        print(json.dumps(out), flush=True)
+                    os._exit(0)
+                dog = threading.Timer(args.extras_timeout, bail)
+                dog.daemon = True
+                dog.start()
+                add_dense_extras(out, probs, args, rank, world, device)
+                dog.cancel()
+        else:
+            out = {'contiguous': run_grouped, 'masked': run_grouped, 'ep': run_ep}[args.workload](args, rank, world, device)
+    if rank == 0 and out is not None:
         print(json.dumps(out), flush=True)
     if world > 1:
+        torch.distributed.barrier()
         torch.distributed.destroy_process_group()
 
 

@@ -1,12 +1,13 @@
 """deepgemm_b200 -- B200-native FP8 blockwise-scaled GEMM behind the ``deep_gemm`` API.
 
 Drop-in scope: fp8_gemm_{nt,nn,tn,tt}, m_grouped_fp8_gemm_{nt,nn}_contiguous,
-m_grouped_fp8_gemm_nt_masked, k_grouped_fp8_gemm_tn_contiguous, the SF layout transforms and the runtime knobs.
+m_grouped_fp8_gemm_nt_masked, k_grouped_fp8_gemm_tn_contiguous, fp8_gemm_nt_skip_head_mid, fp8_einsum, the SF layout
+transforms and the runtime knobs; plus the CUDA activation quantiser `per_token_cast_to_fp8_packed`.
 Importing this package does not touch CUDA (the reference guarantees the same, tests/test_lazy_init.py).
 """
 from . import testing, utils  # noqa: F401
 from .gemm import (  # noqa: F401
-    fp8_gemm_nn, fp8_gemm_nt, fp8_gemm_tn, fp8_gemm_tt,
+    fp8_bmm, fp8_einsum, fp8_gemm_nn, fp8_gemm_nt, fp8_gemm_nt_skip_head_mid, fp8_gemm_tn, fp8_gemm_tt,
     k_grouped_fp8_gemm_nt_contiguous, k_grouped_fp8_gemm_tn_contiguous,
     m_grouped_fp8_gemm_nn_contiguous, m_grouped_fp8_gemm_nt_contiguous, m_grouped_fp8_gemm_nt_masked,
 )
@@ -16,6 +17,7 @@ from .layout import (  # noqa: F401
     get_mn_major_tma_aligned_tensor,
     transform_sf_into_required_layout,
 )
+from .quant import per_token_cast_to_fp8_packed  # noqa: F401
 from .runtime import (  # noqa: F401
     get_mk_alignment_for_contiguous_layout, get_num_sms, get_pdl, get_split_k, get_tc_util,
     get_theoretical_mk_alignment_for_contiguous_layout, get_tma_aligned_size,

@@ -107,8 +107,8 @@ SIGNATURES = {
     'dgb200_ep_export': (_I, [_P, _P]),
     'dgb200_ep_import': (_I, [_P, ctypes.POINTER(_P)]),
     'dgb200_ep_unimport': (_I, [_P]),
-    'dgb200_ep_dispatch': (_I, [_P, _L, _P, _L, _L, _P, _I, _I, _I, _I, _I, _I, ctypes.POINTER(_P), _I, _I, _P, _P, _I, _P]),
-    'dgb200_ep_combine': (_I, [_P, _L, _P, _P, _I, _I, _I, _I, _I, _I, _I, ctypes.POINTER(_P), ctypes.POINTER(_P), _L, _P]),
+    'dgb200_ep_dispatch': (_I, [_P, _L, _P, _L, _L, _P, _I, _I, _I, _I, _I, _I, _I, ctypes.POINTER(_P), _I, _I, _P, _P, _I, _P]),
+    'dgb200_ep_combine': (_I, [_P, _L, _P, _P, _I, _I, _I, _P, _I, _I, _I, _I, _I, ctypes.POINTER(_P), ctypes.POINTER(_P), _L, _P]),
     'dgb200_ep_grouped_gemm': (_I, [_P, _I, _I, _I, _I, _P, _P, _P, _I, _L, _L, _I, _I, _I, _I, _I, _P]),
 }
 

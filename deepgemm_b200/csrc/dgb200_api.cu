@@ -763,13 +763,13 @@ int dgb200_debug_fp8_peak(int umma_n, int iters, int num_sms, void* stream) {
 }
 
 int dgb200_ep_combine(void* out, int64_t ldo, const int32_t* token_row, const void* expert_ids, int id_bytes, int num_tokens,
-                      int n, int elt_bytes, int num_experts, int rank, int world, void* const* buffers,
-                      void* const* d_buffers, int64_t ldd, void* stream) {
+                      int topk, const float* weights, int n, int elt_bytes, int num_experts, int rank, int world,
+                      void* const* buffers, void* const* d_buffers, int64_t ldd, void* stream) {
     if (int e = ensure_device()) return e;
     DGB_REQUIRE(world > 0 && world <= static_cast<int>(ep::kMaxWorld) && rank >= 0 && rank < world);
-    DGB_REQUIRE(num_experts > 0 && num_experts % world == 0 && num_tokens >= 0 && n > 0);
+    DGB_REQUIRE(num_experts > 0 && num_experts % world == 0 && num_tokens >= 0 && n > 0 && topk >= 1);
     DGB_REQUIRE(id_bytes == 4 || id_bytes == 8);
-    DGB_REQUIRE(elt_bytes == 2 || elt_bytes == 4);
+    DGB_REQUIRE(elt_bytes == 2 || (elt_bytes == 4 && topk == 1 && weights == nullptr));   // the weighted reduce is BF16 -> FP32 -> BF16
     DGB_REQUIRE(buffers != nullptr && d_buffers != nullptr);
     DGB_REQUIRE(num_tokens == 0 || (out != nullptr && token_row != nullptr && expert_ids != nullptr));
     DGB_REQUIRE((static_cast<int64_t>(n) * elt_bytes) % 16 == 0 && (ldo * elt_bytes) % 16 == 0 && (ldd * elt_bytes) % 16 == 0);
@@ -784,13 +784,13 @@ int dgb200_ep_combine(void* out, int64_t ldo, const int32_t* token_row, const vo
     ep::combine_publish_kernel<<<1, 32, 0, s>>>(ctrl, rank, world);
     const int grid = std::max(1, std::min(ceil_div(std::max(num_tokens, 1), 8), rt().sm_count * 8));
     if (id_bytes == 4)
-        ep::combine_gather_kernel<int32_t><<<grid, 256, 0, s>>>(ctrl, dbufs, expert_ids, token_row, static_cast<uint8_t*>(out),
-                                                                ldo * elt_bytes, ldd * elt_bytes, n * elt_bytes, num_tokens,
-                                                                num_experts, rank, world);
+        ep::combine_gather_kernel<int32_t><<<grid, 256, 0, s>>>(ctrl, dbufs, expert_ids, token_row, weights, topk,
+                                                                static_cast<uint8_t*>(out), ldo * elt_bytes, ldd * elt_bytes,
+                                                                n * elt_bytes, num_tokens, num_experts, rank, world);
     else
-        ep::combine_gather_kernel<int64_t><<<grid, 256, 0, s>>>(ctrl, dbufs, expert_ids, token_row, static_cast<uint8_t*>(out),
-                                                                ldo * elt_bytes, ldd * elt_bytes, n * elt_bytes, num_tokens,
-                                                                num_experts, rank, world);
+        ep::combine_gather_kernel<int64_t><<<grid, 256, 0, s>>>(ctrl, dbufs, expert_ids, token_row, weights, topk,
+                                                                static_cast<uint8_t*>(out), ldo * elt_bytes, ldd * elt_bytes,
+                                                                n * elt_bytes, num_tokens, num_experts, rank, world);
     DGB_CUDA(cudaGetLastError());
     g_launch_count.fetch_add(2, std::memory_order_relaxed);
     return DGB200_OK;
@@ -952,17 +952,20 @@ int dgb200_ep_unimport(void* ptr) {
 }
 
 int dgb200_ep_dispatch(const void* x, int64_t ldx, const int32_t* sf, int64_t sf_stride_t, int64_t sf_stride_k,
-                       const void* expert_ids, int id_bytes, int num_tokens, int k, int num_experts, int rank, int world,
-                       void* const* buffers, int capacity, int alignment, int32_t* token_row, int32_t* order_scratch,
-                       int wait_for_all, void* stream) {
+                       const void* expert_ids, int id_bytes, int num_tokens, int topk, int k, int num_experts, int rank,
+                       int world, void* const* buffers, int capacity, int alignment, int32_t* token_row,
+                       int32_t* order_scratch, int wait_for_all, void* stream) {
     DGB_REQUIRE(world > 0 && world <= static_cast<int>(ep::kMaxWorld) && rank >= 0 && rank < world);
     DGB_REQUIRE(num_experts > 0 && num_experts <= static_cast<int>(ep::kMaxExperts) && num_experts % world == 0);
-    DGB_REQUIRE(num_tokens >= 0 && capacity > 0 && capacity % 4 == 0 && alignment > 0);   // SF pitch = capacity words (TMA: 16 B)
+    DGB_REQUIRE(num_tokens >= 0 && topk >= 1 && capacity > 0 && capacity % 4 == 0 && alignment > 0);   // SF pitch = capacity words (TMA: 16 B)
+    DGB_REQUIRE(static_cast<int64_t>(num_tokens) * topk < (1ll << 31));
     DGB_REQUIRE(k > 0 && k % 16 == 0 && ceil_div(k, 512) <= 32);
     DGB_REQUIRE(id_bytes == 4 || id_bytes == 8);
+    const int num_entries = num_tokens * topk;
     DGB_REQUIRE(buffers != nullptr && token_row != nullptr && (wait_for_all || num_tokens == 0 || order_scratch != nullptr));
     DGB_REQUIRE(num_tokens == 0 || (x != nullptr && sf != nullptr && expert_ids != nullptr));
     DGB_REQUIRE(ldx % 16 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0);
+    DGB_REQUIRE(wait_for_all || topk == 1);            // the dispatch || GEMM mode is built for top-1 routing
     if (int e = ensure_device()) return e;
     ep::Peers peers;
     for (int p = 0; p < world; ++p) {
@@ -972,37 +975,65 @@ int dgb200_ep_dispatch(const void* x, int64_t ldx, const int32_t* sf, int64_t sf
     const ep::Layout l = ep::make_layout(world, num_experts, capacity, k);
     const auto s = static_cast<cudaStream_t>(stream);
     uint8_t* mine = peers.base[rank];
-    int32_t* counts = reinterpret_cast<int32_t*>(mine + l.counts_off);
     const uint32_t kp = ceil_div(k, 512);
+    const auto* xb = static_cast<const uint8_t*>(x);
+    if (wait_for_all) {
+        // One persistent kernel; every CTA must be resident (it synchronises through grid barriers), so the grid is cut to
+        // what the occupancy API says fits, and to the work there is.
+        static std::mutex mu;
+        static int resident[2] = {0, 0};
+        int fit;
+        {
+            std::lock_guard<std::mutex> lock(mu);
+            int& r = resident[id_bytes == 8];
+            if (r == 0) {
+                int per_sm = 0;
+                if (id_bytes == 4)
+                    DGB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ep::dispatch_fused_kernel<int32_t>, ep::kFusedThreads, 0));
+                else
+                    DGB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ep::dispatch_fused_kernel<int64_t>, ep::kFusedThreads, 0));
+                r = std::max(1, per_sm) * rt().sm_count;
+            }
+            fit = r;
+        }
+        const int warps = ep::kFusedThreads / 32;
+        const int grid = std::max(1, std::min({fit, (int)ep::kMaxRankCtas, ceil_div(std::max(num_entries, 1), warps)}));
+        const int slice = std::max((int)ep::kFusedThreads, align_up(ceil_div(std::max(num_entries, 1), grid), (int)ep::kFusedThreads));
+        if (id_bytes == 4)
+            ep::dispatch_fused_kernel<int32_t><<<grid, ep::kFusedThreads, 0, s>>>(peers, l, xb, ldx, sf, sf_stride_t, sf_stride_k, expert_ids,
+                                                                                  token_row, num_entries, topk, slice, k, kp, rank, world,
+                                                                                  num_experts, capacity, alignment);
+        else
+            ep::dispatch_fused_kernel<int64_t><<<grid, ep::kFusedThreads, 0, s>>>(peers, l, xb, ldx, sf, sf_stride_t, sf_stride_k, expert_ids,
+                                                                                  token_row, num_entries, topk, slice, k, kp, rank, world,
+                                                                                  num_experts, capacity, alignment);
+        DGB_CUDA(cudaGetLastError());
+        g_launch_count.fetch_add(1, std::memory_order_relaxed);
+        return DGB200_OK;
+    }
+    // dispatch || GEMM: the round-1 chain. Expert-sorted send order, and a persistent single wave of 4 scatter CTAs per SM
+    // with <= 32 registers, so that every CTA is resident from the start and the consumer's CTAs (384 threads, 1 per SM) fit beside.
+    int32_t* counts = reinterpret_cast<int32_t*>(mine + l.counts_off);
     if (id_bytes == 4)
         ep::bucket_kernel<int32_t><<<num_experts, 1024, 0, s>>>(expert_ids, num_tokens, token_row, counts);
     else
         ep::bucket_kernel<int64_t><<<num_experts, 1024, 0, s>>>(expert_ids, num_tokens, token_row, counts);
-    // wait_for_all: plain token order, 8 CTAs per SM, nothing but the final flags. Otherwise (a consumer watches the
-    // per-expert arrival counters): expert-sorted order, and a persistent single wave of 4 CTAs per SM with <= 32
-    // registers, so that every CTA is resident from the start and the consumer's CTAs (384 threads, 1 per SM) fit beside.
-    const bool signal = !wait_for_all;
-    const int grid = std::max(1, std::min(ceil_div(num_tokens, 8), rt().sm_count * (signal ? 4 : 8)));
-    ep::exchange_kernel<<<1, 1024, 0, s>>>(peers, l, rank, world, num_experts, capacity, alignment, signal);
-    const auto* xb = static_cast<const uint8_t*>(x);
-    if (signal && num_tokens > 0) {
+    const int grid = std::max(1, std::min(ceil_div(num_tokens, 8), rt().sm_count * 4));
+    ep::exchange_kernel<<<1, 1024, 0, s>>>(peers, l, rank, world, num_experts, capacity, alignment, true);
+    if (num_tokens > 0) {
         if (id_bytes == 4)
             ep::order_kernel<int32_t><<<ceil_div(num_tokens, 256), 256, 0, s>>>(mine, l, expert_ids, num_tokens, num_experts, token_row, order_scratch);
         else
             ep::order_kernel<int64_t><<<ceil_div(num_tokens, 256), 256, 0, s>>>(mine, l, expert_ids, num_tokens, num_experts, token_row, order_scratch);
     }
-#define DGB_SCATTER(ID, SIG)                                                                                          \
-    ep::scatter_kernel<ID, SIG><<<grid, 256, 0, s>>>(peers, l, xb, ldx, sf, sf_stride_t, sf_stride_k, expert_ids, token_row, \
-                                                     order_scratch, num_tokens, k, kp, rank, world, num_experts, capacity)
-    if (id_bytes == 4) {
-        if (signal) DGB_SCATTER(int32_t, true); else DGB_SCATTER(int32_t, false);
-    } else {
-        if (signal) DGB_SCATTER(int64_t, true); else DGB_SCATTER(int64_t, false);
-    }
-#undef DGB_SCATTER
-    if (wait_for_all) ep::wait_kernel<<<1, 32, 0, s>>>(mine, world);
+    if (id_bytes == 4)
+        ep::scatter_kernel<int32_t, true><<<grid, 256, 0, s>>>(peers, l, xb, ldx, sf, sf_stride_t, sf_stride_k, expert_ids, token_row,
+                                                               order_scratch, num_tokens, k, kp, rank, world, num_experts, capacity);
+    else
+        ep::scatter_kernel<int64_t, true><<<grid, 256, 0, s>>>(peers, l, xb, ldx, sf, sf_stride_t, sf_stride_k, expert_ids, token_row,
+                                                               order_scratch, num_tokens, k, kp, rank, world, num_experts, capacity);
     DGB_CUDA(cudaGetLastError());
-    g_launch_count.fetch_add(wait_for_all ? 4 : (num_tokens > 0 ? 4 : 3), std::memory_order_relaxed);
+    g_launch_count.fetch_add(num_tokens > 0 ? 4 : 3, std::memory_order_relaxed);
     return DGB200_OK;
 }
 

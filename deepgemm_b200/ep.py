@@ -5,14 +5,15 @@ distributed over the ranks, each with one destination expert, and must land on t
 consumes (expert segments aligned to `get_mk_alignment_for_contiguous_layout()`, psum layout = end row per expert,
 MN-major packed UE8M0 scale factors). This mirrors how the reference's grouped GEMM sits inside expert parallelism in
 its own baseline (tests/test_mega_moe.py:148-205: DeepEP dispatch -> m_grouped_fp8_fp4_gemm_nt_contiguous(
-use_psum_layout=True) -> combine). The reverse path ("combine") is the next row.
+use_psum_layout=True) -> combine). `EpBuffer.combine` is the reverse path: weighted top-k reduce over NVLink.
 
 Two implementations:
 
-* `EpBuffer.dispatch` -- THE PRODUCT PATH (CUDA only). Hand-written kernels (csrc/ep_dispatch.cuh) write every token
-  row (K FP8 bytes + its 4*ceil(K/512) scale-factor bytes) straight into the owner's GEMM input buffer with NVLink peer
-  stores: bucket -> count exchange through peer memory -> scatter -> wait. No host synchronisation (the counts never
-  leave the devices), no intermediate buffers, no re-layout pass, CUDA-graph capturable. The plumbing (buffer
+* `EpBuffer.dispatch` -- THE PRODUCT PATH (CUDA only). One hand-written persistent kernel (csrc/ep_dispatch.cuh) writes
+  every token row (K FP8 bytes + its 4*ceil(K/512) scale-factor bytes) straight into the owner's GEMM input buffer with
+  NVLink peer stores: rank the (token, slot) entries (O(T)) -> count exchange through peer memory -> scatter -> signal
+  and wait, separated by grid barriers. Top-k routing: a token is copied once per routed slot. No host synchronisation (the
+  counts never leave the devices), no intermediate buffers, no re-layout pass, CUDA-graph capturable. The plumbing (buffer
   allocation, CUDA IPC handle exchange over `torch.distributed`) happens once, in the constructor.
 
 * `dispatch_alltoall` -- the library baseline: counts `all_to_all_single` + ONE payload `all_to_all_single` + torch
@@ -141,7 +142,7 @@ class PeerDispatch:
     a: torch.Tensor             # [capacity, K] e4m3 view of the local dispatch buffer
     sfa: torch.Tensor           # int32 [capacity, ceil(K/512)], strides (1, capacity)
     psum_layout: torch.Tensor   # int32 [experts_per_rank] end row of each local expert (device-side; never read here)
-    token_row: torch.Tensor     # int32 [T]: row of each LOCAL token inside its owner's buffer (-1 = not routed)
+    token_row: torch.Tensor     # int32 [T * topk]: row of each LOCAL (token, slot) entry inside its owner's buffer (-1 = not routed)
     expected_m: int             # host-side estimate of rows per expert, for the GEMM heuristics only
 
 
@@ -152,15 +153,16 @@ class EpBuffer:
     (worst case: all tokens of all ranks + experts_per_rank * alignment)."""
 
     def __init__(self, num_experts: int, capacity: int, k: int, group: Optional[dist.ProcessGroup] = None,
-                 device: Optional[torch.device] = None):
+                 device: Optional[torch.device] = None, local_only: bool = False):
         from . import runtime
         from ._lib import check, lib
         import ctypes
         if not torch.cuda.is_available():
             raise RuntimeError('EpBuffer needs CUDA (there is no CPU fallback; dispatch_alltoall is the library baseline)')
         self._lib, self._check = lib(), check
-        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
-        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        # local_only: a world-size-1 buffer (all experts here) even inside an initialised process group
+        self.world = dist.get_world_size(group) if dist.is_initialized() and not local_only else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() and not local_only else 0
         self.group = group
         self.device = torch.device('cuda', torch.cuda.current_device()) if device is None else device
         self.alignment = runtime.get_mk_alignment_for_contiguous_layout()
@@ -217,25 +219,33 @@ class EpBuffer:
 
     def dispatch(self, x_fp8: torch.Tensor, sf_packed: torch.Tensor, expert_ids: torch.Tensor,
                  token_row: Optional[torch.Tensor] = None, wait: bool = True) -> PeerDispatch:
-        """Enqueue the dispatch kernels on the current stream. x_fp8 [T,K] e4m3 (row pitch multiple of 16 B),
-        sf_packed [T, ceil(K/512)] int32 (any strides), expert_ids [T] int32/int64 (outside [0,G) = not routed).
-        wait=False leaves out the final "everything has landed" kernel: only `grouped_gemm(..., overlap=True)` may
-        follow, which watches the per-expert arrival counters itself and runs beside the scatter."""
+        """Enqueue the dispatch on the current stream. x_fp8 [T,K] e4m3 (row pitch multiple of 16 B), sf_packed
+        [T, ceil(K/512)] int32 (any strides), expert_ids [T] (top-1) or [T, topk] int32/int64 (outside [0,G) = slot not
+        routed; a token is copied once per routed slot). wait=True (default): one persistent kernel that returns when every
+        row destined to this rank has landed. wait=False (top-1 only) leaves the final wait out: only
+        `grouped_gemm(..., overlap=True)` may follow, which watches the per-expert arrival counters itself."""
         t, k = x_fp8.shape
         assert k == self.k and x_fp8.stride(1) == 1 and x_fp8.is_cuda
         assert sf_packed.dtype == torch.int32 and sf_packed.shape == (t, self.kp)
-        assert expert_ids.dtype in (torch.int32, torch.int64) and expert_ids.is_contiguous() and expert_ids.numel() == t
+        assert expert_ids.dtype in (torch.int32, torch.int64) and expert_ids.is_contiguous()
+        assert expert_ids.dim() in (1, 2) and expert_ids.shape[0] == t
+        topk = 1 if expert_ids.dim() == 1 else expert_ids.shape[1]
+        assert wait or topk == 1, 'dispatch || GEMM is built for top-1 routing'
         if token_row is None:
-            token_row = torch.empty(t, dtype=torch.int32, device=x_fp8.device)
-        if self._order is None or self._order.numel() < t:
-            self._order = torch.empty(max(t, 1), dtype=torch.int32, device=x_fp8.device)   # scratch: expert-sorted token order
+            token_row = torch.empty(t * topk, dtype=torch.int32, device=x_fp8.device)
+        assert token_row.dtype == torch.int32 and token_row.numel() == t * topk and token_row.is_contiguous()
+        order_ptr = None
+        if not wait:
+            if self._order is None or self._order.numel() < t:
+                self._order = torch.empty(max(t, 1), dtype=torch.int32, device=x_fp8.device)   # scratch: expert-sorted token order
+            order_ptr = self._order.data_ptr()
         self._check(self._lib.dgb200_ep_dispatch(
             x_fp8.data_ptr(), x_fp8.stride(0), sf_packed.data_ptr(), sf_packed.stride(0), sf_packed.stride(1),
-            expert_ids.data_ptr(), expert_ids.element_size(), t, k, self.num_experts, self.rank, self.world,
-            self._ptr_array, self.capacity, self.alignment, token_row.data_ptr(), self._order.data_ptr(), int(wait),
+            expert_ids.data_ptr(), expert_ids.element_size(), t, topk, k, self.num_experts, self.rank, self.world,
+            self._ptr_array, self.capacity, self.alignment, token_row.data_ptr(), order_ptr, int(wait),
             torch.cuda.current_stream().cuda_stream))
         return PeerDispatch(a=self.a, sfa=self.sfa, psum_layout=self.psum_layout, token_row=token_row,
-                            expected_m=max(1, t * self.world // self.num_experts))
+                            expected_m=max(1, t * topk * self.world // self.num_experts))
 
     def grouped_gemm(self, w_local: Tuple[torch.Tensor, torch.Tensor], d: torch.Tensor, expected_m: int,
                      overlap: bool = True) -> None:
@@ -295,19 +305,26 @@ class EpBuffer:
         self._out = (n, ptr.value, (ctypes.c_void_p * self.world)(*ptrs), view, ptrs)
         return view
 
-    def combine(self, token_row: torch.Tensor, expert_ids: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-        """The way back (top-1 routing): out[t] = D_owner(t)[token_row[t]], zeros for unrouted tokens. Enqueue on the
-        stream that ran this rank's grouped GEMM into `self.output(n)`; every rank calls it once per dispatch."""
+    def combine(self, token_row: torch.Tensor, expert_ids: torch.Tensor, out: Optional[torch.Tensor] = None,
+                weights: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """The way back: out[t] = sum_j weights[t, j] * D_owner(t, j)[token_row[t, j]] (FP32 products and sum in slot
+        order, one BF16 rounding; unrouted slots skipped, tokens without a routed slot get zeros). `expert_ids` [T] or
+        [T, topk] as given to dispatch, `weights` FP32 [T, topk] or None (= 1; top-1 without weights is a pure gather).
+        Enqueue on the stream that ran this rank's grouped GEMM into `self.output(n)`; every rank calls it once per dispatch."""
         assert self._out is not None, 'run the grouped GEMM into EpBuffer.output(n) first'
         n = self._out[0]
-        t = token_row.numel()
-        assert token_row.dtype == torch.int32 and token_row.is_contiguous()
-        assert expert_ids.dtype in (torch.int32, torch.int64) and expert_ids.is_contiguous() and expert_ids.numel() == t
+        t = expert_ids.shape[0]
+        topk = 1 if expert_ids.dim() == 1 else expert_ids.shape[1]
+        assert token_row.dtype == torch.int32 and token_row.is_contiguous() and token_row.numel() == t * topk
+        assert expert_ids.dtype in (torch.int32, torch.int64) and expert_ids.is_contiguous()
+        if weights is not None:
+            assert weights.dtype == torch.float32 and weights.is_contiguous() and weights.numel() == t * topk
         if out is None:
             out = torch.empty((t, n), dtype=torch.bfloat16, device=token_row.device)
         assert out.shape == (t, n) and out.dtype == torch.bfloat16 and out.stride(1) == 1
         self._check(self._lib.dgb200_ep_combine(
-            out.data_ptr(), out.stride(0) if t > 1 else n, token_row.data_ptr(), expert_ids.data_ptr(), expert_ids.element_size(), t, n, 2,
+            out.data_ptr(), out.stride(0) if t > 1 else n, token_row.data_ptr(), expert_ids.data_ptr(), expert_ids.element_size(), t,
+            topk, None if weights is None else weights.data_ptr(), n, 2,
             self.num_experts, self.rank, self.world, self._ptr_array, self._out[2], n,
             torch.cuda.current_stream().cuda_stream))
         return out

@@ -128,6 +128,83 @@ def fp8_gemm_nt(a: TensorPair, b: TensorPair, d: torch.Tensor, c: Optional[torch
                                    int(c is not None), ws_ptr, ws_bytes, stream))
 
 
+def fp8_gemm_nt_skip_head_mid(a: TensorPair, b: TensorPair, d: torch.Tensor, head_splits: Tuple[int, int, int],
+                              recipe: Optional[Tuple[int, int, int]] = None, compiled_dims: str = 'nk',
+                              disable_ue8m0_cast: bool = False) -> None:
+    """D[:, head h] = [ left | (mid columns left untouched) | right ] of A @ B.T's head h: the GEMM's N is a multiple of
+    left + right, D is n + n / (left + right) * mid wide and GEMM column j lands at j + (j + right) // (left + right) * mid.
+    Used by DeepSeek-V3 MLA to write the no-PE / PE halves of every head around a gap filled elsewhere.
+    Reference: csrc/apis/attention.hpp:19-74 (epilogue remap deep_gemm/include/deep_gemm/epilogue/transform.cuh:15-22)."""
+    (a_t, sfa), (b_t, sfb) = a, b
+    _check_fp8(a_t), _check_fp8(b_t)
+    _require(_major_ab(a_t) == _K_MAJOR and _major_ab(b_t) == _K_MAJOR, 'major_a == K and major_b == K')
+    _check_cd(d)
+    _require(a_t.dim() == 2 and b_t.dim() == 2 and d.dim() == 2, 'a, b, d are 2-D')
+    (m, k), (n, k_), (m_, n_) = a_t.shape, b_t.shape, d.shape
+    _require(m == m_ and k == k_, 'm == m_ and k == k_')
+    _require(n > 0 and k > 0, 'n > 0 and k > 0')
+    _d_dtype(d)
+    left, mid, right = (int(x) for x in head_splits)
+    _require(left >= 0 and mid >= 0 and right >= 0 and left + right > 0, 'head splits are non-negative')
+    _require(n % (left + right) == 0 and n_ == n + n // (left + right) * mid, 'n % (left + right) == 0 and n_ == n + n / (left + right) * mid')
+    if m == 0:
+        return
+    sfa_t, sfb_t, gran_k_a, gran_k_b = _layout.transform_sf_pair_into_required_layout(
+        sfa, sfb, m, n, k, recipe, None, None, None, None, disable_ue8m0_cast)
+    _require(gran_k_a == 128 and gran_k_b == 128, 'gran_k_a == 128 and gran_k_b == 128')
+    _require(sfa_t.dtype == torch.int32 and sfb_t.dtype == torch.int32, 'Unsupported architecture or scaling factor types')
+    check(lib().dgb200_fp8_gemm_nt_skip_head_mid(
+        a_t.data_ptr(), sfa_t.data_ptr(), b_t.data_ptr(), sfb_t.data_ptr(), d.data_ptr(), m, n, k, a_t.stride(0), b_t.stride(0),
+        d.stride(0), left, mid, right, sfa_t.stride(-1), sfb_t.stride(-1), _d_dtype(d), _stream()))
+
+
+def fp8_bmm(a: torch.Tensor, sfa: torch.Tensor, b: torch.Tensor, sfb: torch.Tensor, d: torch.Tensor,
+            c: Optional[torch.Tensor] = None, recipe: Optional[Tuple[int, int, int]] = None,
+            compiled_dims: str = 'nk') -> None:
+    """D[i] = (C[i] +) A[i] @ B[i].T over a batch, A [B, M, K], B [B, N, K], D [B, M, N]; every tensor may be a permuted
+    view (only the innermost-stride rules of a GEMM operand apply), which is what `fp8_einsum` feeds it.
+    Reference: csrc/apis/einsum.hpp:137-175 (sm100_fp8_bmm, csrc/jit_kernels/impls/sm100_fp8_fp4_gemm_1d1d.hpp:393-467)."""
+    _check_fp8(a), _check_fp8(b)
+    _require(a.dim() == 3 and b.dim() == 3 and d.dim() == 3, 'a, b, d are 3-D')
+    _require(a.stride(-1) == 1 or a.stride(-2) == 1, 'a.stride(-1) == 1 or a.stride(-2) == 1')
+    _require(b.stride(-1) == 1 or b.stride(-2) == 1, 'b.stride(-1) == 1 or b.stride(-2) == 1')
+    _require(d.stride(-1) == 1, 'd.stride(-1) == 1')
+    major_a = _K_MAJOR if a.stride(-1) == 1 else _MN_MAJOR
+    major_b = _K_MAJOR if b.stride(-1) == 1 else _MN_MAJOR
+    (bs, m, k), (bs_, n, k_), (bs__, m_, n_) = a.shape, b.shape, d.shape
+    _require(bs == bs_ == bs__, 'batch sizes agree')
+    _require(m == m_ and n == n_ and k == k_, 'm == m_ and n == n_ and k == k_')
+    _d_dtype(d)
+    if bs == 0 or _early_return(m, n, k, d, c):
+        return
+    sfa_t, sfb_t, gran_k_a, gran_k_b = _layout.transform_sf_pair_into_required_layout(
+        sfa, sfb, m, n, k, recipe, None, None, bs, bs, False)
+    _require(sfa_t.dtype == torch.int32 and sfb_t.dtype == torch.int32, 'Unsupported architecture or scaling factor types')
+    lda = a.stride(1) if major_a == _K_MAJOR else a.stride(2)
+    ldb = b.stride(1) if major_b == _K_MAJOR else b.stride(2)
+    check(lib().dgb200_fp8_bmm(a.data_ptr(), sfa_t.data_ptr(), b.data_ptr(), sfb_t.data_ptr(), d.data_ptr(), bs, m, n, k,
+                               lda, ldb, d.stride(1), a.stride(0), b.stride(0), d.stride(0), major_a, major_b,
+                               sfa_t.stride(-1), sfb_t.stride(-1), gran_k_a, gran_k_b, _d_dtype(d), int(c is not None),
+                               _stream()))
+
+
+def fp8_einsum(expr: str, a: TensorPair, b: TensorPair, d: torch.Tensor, c: Optional[torch.Tensor] = None,
+               recipe: Tuple[int, int, int] = (1, 128, 128)) -> None:
+    """The three hard-wired FP8 contractions of the reference (csrc/apis/einsum.hpp:177-214), each a batched GEMM over
+    permuted views -- (batch, m, n, k) = (h, b, d, r), (h, b, r, d) and (h, d, r, b) -- with no copies."""
+    (a_t, sfa), (b_t, sfb) = a, b
+    if expr == 'bhr,hdr->bhd':
+        fp8_bmm(a_t.permute(1, 0, 2), sfa.permute(1, 0, 2), b_t, sfb, d.permute(1, 0, 2),
+                None if c is None else c.permute(1, 0, 2), recipe, 'nk')
+    elif expr == 'bhd,hdr->bhr':
+        fp8_bmm(a_t.permute(1, 0, 2), sfa.permute(1, 0, 2), b_t.permute(0, 2, 1), sfb.permute(0, 2, 1), d.permute(1, 0, 2),
+                None if c is None else c.permute(1, 0, 2), recipe, 'nk')
+    elif expr == 'bhd,bhr->hdr':
+        fp8_bmm(a_t.permute(1, 2, 0), sfa.permute(1, 2, 0), b_t.permute(1, 2, 0), sfb.permute(1, 2, 0), d, c, recipe, 'mn')
+    else:
+        raise RuntimeError(f'Unsupported einsum expression: {expr}')
+
+
 def _t(pair: TensorPair, d0: int = 0, d1: int = 1) -> TensorPair:
     return pair[0].transpose(d0, d1), pair[1].transpose(d0, d1)
 

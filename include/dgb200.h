@@ -172,7 +172,7 @@ int dgb200_k_grouped_fp8_gemm_tn_contiguous(const void* a, const int32_t* sfa, c
  * reference pairs its grouped GEMM with an external dispatch library for this (tests/test_mega_moe.py:148-205).
  * Every rank owns one "dispatch buffer" of dgb200_ep_buffer_bytes() bytes, identical layout on all ranks, mapped into
  * every peer (dgb200_ep_export / _import use CUDA IPC; any other peer-mapping mechanism works as long as `buffers[p]`
- * is rank p's buffer as addressable from the calling device). dgb200_ep_dispatch() enqueues four kernels that write
+ * is rank p's buffer as addressable from the calling device). dgb200_ep_dispatch() enqueues one persistent kernel that writes
  * the local tokens straight into the owners' buffers in the contiguous-grouped psum layout and return once all rows
  * destined to THIS rank have landed (in stream order) -- the GEMM then reads, inside the local buffer,
  *   a   = base + offsets[DGB200_EP_OFF_A]    uint8/e4m3 [capacity, k]
@@ -189,16 +189,20 @@ int dgb200_ep_export(void* ptr, void* handle_64_bytes);         /* cudaIpcGetMem
 int dgb200_ep_import(const void* handle_64_bytes, void** ptr);  /* cudaIpcOpenMemHandle (enables peer access) */
 int dgb200_ep_unimport(void* ptr);
 /* x [num_tokens, k] e4m3 rows (pitch ldx bytes), sf: packed UE8M0 words of token t at sf[t*sf_stride_t + j*sf_stride_k],
- * j < ceil(k/512); expert_ids int32 (id_bytes 4) or int64 (id_bytes 8), values outside [0, num_experts) = not routed.
- * token_row int32[num_tokens] (out): row of each token inside its owner's buffer (-1: not routed / dropped on
+ * j < ceil(k/512). Routing: expert_ids [num_tokens, topk] (row-major; int32 = id_bytes 4, int64 = id_bytes 8), values
+ * outside [0, num_experts) = slot not routed; token t is copied once per routed slot ("entry" t * topk + j).
+ * token_row int32[num_tokens * topk] (out): row of each entry inside its owner's buffer (-1: not routed / dropped on
  * overflow, which also sets the word at DGB200_EP_OFF_OVERFLOW). k % 16 == 0, ceil(k/512) <= 32, capacity % 4 == 0.
- * wait_for_all != 0 appends the kernel that returns once every source's rows have landed (then any consumer may
- * follow in stream order); 0 leaves that to a consumer that watches the per-expert arrival counters itself
- * (dgb200_ep_grouped_gemm with overlap_dispatch). Tokens are sent in expert order, so experts complete one by one. */
+ * wait_for_all != 0 (the default path): ONE persistent kernel -- rank entries (O(T)), exchange counts with the peers,
+ * scatter rows over NVLink, signal and wait for every source -- after which any consumer may follow in stream order.
+ * wait_for_all == 0 (top-1 only): the count / exchange / order / scatter kernel chain without the final wait, for a
+ * consumer that watches the per-expert arrival counters itself (dgb200_ep_grouped_gemm with overlap_dispatch); tokens
+ * are then sent in expert order, so experts complete one by one. `order_scratch` is only used by that mode. */
 int dgb200_ep_dispatch(const void* x, int64_t ldx, const int32_t* sf, int64_t sf_stride_t, int64_t sf_stride_k,
-                       const void* expert_ids, int id_bytes, int num_tokens, int k, int num_experts, int rank, int world,
-                       void* const* buffers, int capacity, int alignment, int32_t* token_row,
-                       int32_t* order_scratch /* int32[num_tokens], device */, int wait_for_all, void* stream);
+                       const void* expert_ids, int id_bytes, int num_tokens, int topk, int k, int num_experts, int rank,
+                       int world, void* const* buffers, int capacity, int alignment, int32_t* token_row,
+                       int32_t* order_scratch /* int32[num_tokens], device; may be NULL with wait_for_all */,
+                       int wait_for_all, void* stream);
 /* The grouped GEMM of this rank's experts over its dispatch buffer (psum layout, zero padding, BF16 D [capacity, n];
  * b [G/world, n, k] e4m3, sfb packed UE8M0). With overlap_dispatch != 0 it must directly follow a dgb200_ep_dispatch(...,
  * wait_for_all = 0, ...) on the same stream: the kernel is then launched as a programmatic dependent of the scatter
@@ -209,16 +213,18 @@ int dgb200_ep_grouped_gemm(void* local_buffer, int world, int num_experts, int c
                            const int32_t* sfb, void* d, int n, int64_t ldb, int64_t ldd, int major_b, int sfb_stride,
                            int gran_k_b, int expected_m, int overlap_dispatch, void* stream);
 
-/* The way back (top-1 routing): out[t, 0:n] = D_owner(t)[token_row[t], 0:n] for every local token, zeros where
- * token_row[t] < 0. `d_buffers[p]` = rank p's grouped-GEMM output [capacity, n] (pitch ldd elements, elt_bytes 2 or 4)
- * as addressable from this device (peer mapped, e.g. dgb200_ep_alloc + _export/_import); `buffers` = the dispatch
- * buffers (their control blocks carry the handshake). Enqueue on the stream that ran this rank's grouped GEMM: a first
- * kernel tells every peer that this rank's D is complete, the gather waits for every owner's message, then pulls the
- * rows over NVLink. All ranks must call it once per dispatch. D may be overwritten again after the next
- * dgb200_ep_dispatch has returned control to the stream (its count exchange orders the two). */
+/* The way back (weighted top-k combine, the last step of the reference's baseline MoE layer, tests/test_mega_moe.py:196-202):
+ *   out[t, 0:n] = sum_j weights[t, j] * D_owner(t, j)[token_row[t * topk + j], 0:n]      (slots with token_row < 0 skipped)
+ * products and running sum in FP32 in slot order (separate multiply and add), rounded once to BF16; a token without any
+ * routed slot gets zeros. weights == NULL means 1.0; with topk == 1 that is a pure gather (bit-exact copy, elt_bytes 2 or 4).
+ * `d_buffers[p]` = rank p's grouped-GEMM output [capacity, n] (pitch ldd elements) as addressable from this device (peer
+ * mapped, e.g. dgb200_ep_alloc + _export/_import); `buffers` = the dispatch buffers (their control blocks carry the
+ * handshake). Enqueue on the stream that ran this rank's grouped GEMM: a first kernel tells every peer that this rank's D
+ * is complete, the gather waits for every owner's message, then pulls the rows over NVLink. All ranks must call it once
+ * per dispatch. D may be overwritten again after the next dgb200_ep_dispatch has returned control to the stream. */
 int dgb200_ep_combine(void* out, int64_t ldo, const int32_t* token_row, const void* expert_ids, int id_bytes, int num_tokens,
-                      int n, int elt_bytes, int num_experts, int rank, int world, void* const* buffers,
-                      void* const* d_buffers, int64_t ldd, void* stream);
+                      int topk, const float* weights, int n, int elt_bytes, int num_experts, int rank, int world,
+                      void* const* buffers, void* const* d_buffers, int64_t ldd, void* stream);
 
 /* ---- introspection (bench / tests) -------------------------------------------------------------------------- */
 typedef struct dgb200_config {

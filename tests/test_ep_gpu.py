@@ -1,7 +1,7 @@
 """GPU tests of the peer-memory expert-parallel dispatch (csrc/ep_dispatch.cuh through the C ABI, deepgemm_b200/ep.py).
 
-Single GPU: world size 1 exercises all four kernels (bucket / exchange / scatter / wait) with the rank being its own
-peer; the result must be bit-identical to the torch re-layout `dispatch_local`. With >= 2 GPUs the torchrun script
+Single GPU: world size 1 exercises every phase of the fused dispatch kernel (rank / exchange / scatter / complete) and the
+round-1 kernel chain of the dispatch || GEMM mode with the rank being its own peer; the result must be bit-identical to the torch re-layout `dispatch_local`. With >= 2 GPUs the torchrun script
 tools/ep_check.py additionally checks the NVLink path against the NCCL all-to-all baseline and under a CUDA graph.
 Reference context: the grouped GEMM inside expert parallelism, tests/test_mega_moe.py:148-205."""
 import os
@@ -79,7 +79,7 @@ def test_expert_sharded_grouped_gemm_world1_matches_oracle(dg, overlap):
     from deepgemm_b200.utils import per_block_cast_to_fp8, per_token_cast_to_fp8
     from oracle import blockwise
     dev = torch.device('cuda', 0)
-    g, n, k, t = 4, 256, 512, 333        # capacity 333 + 4 * 128 = 845 is rounded up to a multiple of 16 by EpBuffer
+    g, n, k, t = 4, 256, 512, 333        # capacity 333 + 4 * 128 = 845 is rounded up to whole alignment units by EpBuffer
     gen = torch.Generator(device=dev).manual_seed(5)
     align = dg.get_mk_alignment_for_contiguous_layout()
     w = torch.randn((g, n, k), device=dev, dtype=torch.bfloat16, generator=gen)
@@ -143,6 +143,108 @@ def test_combine_world1_returns_every_token_its_row(dg):
                     finally:
                         dg.set_split_k(True)
                     assert torch.equal(out[sel], ref)
+    finally:
+        buf.close()
+
+
+def _weighted_combine_reference(d_rows, weights, routed):
+    """The kernel's arithmetic, spelled out: FP32 product, FP32 running sum in slot order, one BF16 rounding."""
+    t, topk, n = d_rows.shape
+    acc = torch.zeros((t, n), dtype=torch.float32, device=d_rows.device)
+    for j in range(topk):
+        term = weights[:, j:j + 1] * d_rows[:, j].float()
+        acc = torch.where(routed[:, j:j + 1], acc + term, acc)
+    return acc.to(torch.bfloat16)
+
+
+@pytest.mark.parametrize('topk', [2, 8])
+def test_topk_dispatch_and_weighted_combine_world1(dg, topk):
+    """Top-k routing: every (token, slot) entry lands in its expert's segment; combine = FP32 weighted sum of the k expert
+    outputs, bit-checked against a torch loop with the same operation order (tests/test_mega_moe.py:196-202 is the
+    reference's baseline for this step)."""
+    from deepgemm_b200 import ep
+    from deepgemm_b200.utils import per_block_cast_to_fp8, per_token_cast_to_fp8
+    dev = torch.device('cuda', 0)
+    g, n, k, t = 16, 256, 512, 700
+    gen = torch.Generator(device=dev).manual_seed(40 + topk)
+    align = dg.get_mk_alignment_for_contiguous_layout()
+    w = torch.randn((g, n, k), device=dev, dtype=torch.bfloat16, generator=gen)
+    qs = [per_block_cast_to_fp8(w[i], True) for i in range(g)]
+    wq = (torch.stack([q[0] for q in qs]), torch.stack([q[1] for q in qs]))
+    x = torch.randn((t, k), device=dev, dtype=torch.bfloat16, generator=gen)
+    xq, sf_packed = per_token_cast_to_fp8(x, True, 128, use_packed_ue8m0=True)
+    _, sf_fp32 = per_token_cast_to_fp8(x, True, 128)
+    ids = torch.stack([torch.randperm(g, device=dev, generator=gen)[:topk] for _ in range(t)])      # distinct experts per token
+    ids[::13, 1] = -1                                                                               # some slots not routed
+    weights = torch.rand((t, topk), device=dev, generator=gen)
+    buf = ep.EpBuffer(g, t * topk + g * align, k)
+    try:
+        d = buf.output(n)
+        for _ in range(2):
+            d.fill_(float('nan'))
+            r = buf.dispatch(xq, sf_packed, ids)
+            buf.grouped_gemm(wq, d, r.expected_m, overlap=False)
+            out = buf.combine(r.token_row, ids, weights=weights)
+            torch.cuda.synchronize()
+            assert not buf.overflowed()
+            rows = r.token_row.view(t, topk)
+            routed = ids >= 0
+            assert bool((rows[~routed] == -1).all()) and bool((rows[routed] >= 0).all())
+            # the dispatch put token t's bytes in every one of its rows
+            flat = rows[routed].long()
+            src = torch.arange(t, device=dev).unsqueeze(1).expand(t, topk)[routed]
+            assert torch.equal(buf.a.view(torch.uint8)[flat], xq.view(torch.uint8)[src])
+            assert flat.unique().numel() == flat.numel(), 'two entries share a row'
+            # segment membership: row of an entry lies inside its expert's segment of the psum layout
+            psum = r.psum_layout.long()
+            starts = torch.cat([torch.zeros(1, dtype=torch.long, device=dev), (psum[:-1] + align - 1) // align * align])
+            e = ids[routed].long()
+            assert bool(((flat >= starts[e]) & (flat < psum[e])).all())
+            # every row holds its expert's answer (dense kernel, split-K off: same bits)
+            dg.set_split_k(False)
+            try:
+                for ex in (0, 7, 15):
+                    sel = (ids == ex).any(dim=1)
+                    if bool(sel.any()):
+                        ref = torch.empty((int(sel.sum()), n), device=dev, dtype=torch.bfloat16)
+                        dg.fp8_gemm_nt((xq[sel].contiguous(), sf_fp32[sel].contiguous()), (wq[0][ex], wq[1][ex]), ref)
+                        slot = (ids[sel] == ex).float().argmax(dim=1)
+                        assert torch.equal(d[rows[sel].gather(1, slot.unsqueeze(1)).squeeze(1).long()], ref)
+            finally:
+                dg.set_split_k(True)
+            # the weighted reduce, bit for bit
+            d_rows = d[rows.clamp(min=0).long()]
+            want = _weighted_combine_reference(d_rows, weights, routed)
+            assert torch.equal(out, want)
+    finally:
+        buf.close()
+
+
+def test_overflowing_dispatch_followed_by_the_grouped_gemm_stays_in_bounds(dg):
+    """with the psum ends clamped to `capacity` by an overflowing dispatch, the grouped GEMM must neither walk
+    phantom tiles nor write past D: dropped tokens, no crash."""
+    from deepgemm_b200 import ep
+    from deepgemm_b200.utils import per_block_cast_to_fp8, per_token_cast_to_fp8
+    dev = torch.device('cuda', 0)
+    g, n, k, t = 4, 256, 512, 1200
+    gen = torch.Generator(device=dev).manual_seed(11)
+    w = torch.randn((g, n, k), device=dev, dtype=torch.bfloat16, generator=gen)
+    qs = [per_block_cast_to_fp8(w[i], True) for i in range(g)]
+    wq = (torch.stack([q[0] for q in qs]), torch.stack([q[1] for q in qs]))
+    x = torch.randn((t, k), device=dev, dtype=torch.bfloat16, generator=gen)
+    xq, sf_packed = per_token_cast_to_fp8(x, True, 128, use_packed_ue8m0=True)
+    ids = torch.randint(0, g, (t,), device=dev, generator=gen)
+    buf = ep.EpBuffer(g, 1000, k)                          # rounded up to 1024 rows: too small for 1200 tokens + padding
+    try:
+        guard = torch.full((buf.capacity + 256, n), 99.0, device=dev, dtype=torch.bfloat16)
+        d = guard[:buf.capacity]
+        r = buf.dispatch(xq, sf_packed, ids)
+        buf.grouped_gemm(wq, d, r.expected_m, overlap=False)
+        torch.cuda.synchronize()
+        assert buf.overflowed()
+        assert bool((guard[buf.capacity:] == 99.0).all())
+        kept = r.token_row >= 0
+        assert 0 < int(kept.sum()) < t and int(r.token_row.max()) < buf.capacity
     finally:
         buf.close()
 

@@ -188,7 +188,7 @@ def test_ep_buffer_layout_and_argument_checks(lib):
     bufs = (ctypes.c_void_p * world)(*([4096] * world))
     # experts must divide over the ranks; K must be a multiple of 16; ids are int32 or int64
     for bad in (dict(g=255), dict(k=7170), dict(idb=2)):
-        rc = L.dgb200_ep_dispatch(4096, k, 4096, 14, 1, 4096, bad.get('idb', 8), 16, bad.get('k', k), bad.get('g', g), 0, world,
+        rc = L.dgb200_ep_dispatch(4096, k, 4096, 14, 1, 4096, bad.get('idb', 8), 16, 1, bad.get('k', k), bad.get('g', g), 0, world,
                                   bufs, cap, 128, 4096, 4096, 1, None)
         assert rc != 0 and b'Assertion error' in L.dgb200_last_error()
 

@@ -27,7 +27,7 @@ def main():
     g, n, k, t_local = 16, 512, 1024, 1000
     epr = g // world
     align = dg.get_mk_alignment_for_contiguous_layout()
-    capacity = t_local * world + epr * align
+    capacity = 2 * t_local * world + epr * align
     gen = torch.Generator(device=dev).manual_seed(1 + rank)
     w = torch.randn((epr, n, k), device=dev, dtype=torch.bfloat16, generator=gen)
     qs = [per_block_cast_to_fp8(w[i], True) for i in range(epr)]
@@ -66,6 +66,7 @@ def main():
         return ok_rows
 
     d = buf.output(n)                       # symmetric: combine() gathers from it
+    # (capacity must also hold the top-8 round below: t_local / 4 tokens x 8 slots per rank)
     # every rank can rebuild every expert's weights (seeded by the owner's rank) to check what combine brings back
     w_all = []
     for o in range(world):
@@ -97,6 +98,48 @@ def main():
         total += check(xq, sf, ids.long(), d, r, f'iter {it}')
         check_combine(xq, sf, ids.long() if ids.dtype != torch.int64 else ids, r, f'combine {it}')
 
+    # (c') top-8 routing + weighted combine, bit-checked: out[t] = sum_j w[t,j] * D_owner[row(t,j)] with FP32 products and an
+    #      FP32 running sum in slot order (the owners' D rows are fetched here through torch from an all-gather of D)
+    topk = 8
+    for it in range(2):
+        x = torch.randn((t_local // 4, k), device=dev, dtype=torch.bfloat16, generator=gen)
+        xq, sf = per_token_cast_to_fp8(x, True, 128, use_packed_ue8m0=True)
+        tl = x.shape[0]
+        ids8 = torch.stack([torch.randperm(g, device=dev, generator=gen)[:topk] for _ in range(tl)])
+        if it == 1:
+            ids8[::5, 3] = -1
+        wts = torch.rand((tl, topk), device=dev, generator=gen)
+        d.fill_(float('nan'))
+        r = buf.dispatch(xq, sf, ids8)
+        buf.grouped_gemm(wq, d, r.expected_m, overlap=False)
+        out = buf.combine(r.token_row, ids8, weights=wts)
+        torch.cuda.synchronize()
+        assert not buf.overflowed()
+        d_all = [torch.empty_like(d) for _ in range(world)]
+        dist.all_gather(d_all, d.contiguous())
+        d_all = torch.stack(d_all)                                       # [world, capacity, n]
+        rows = r.token_row.view(tl, topk).long()
+        routed = ids8 >= 0
+        owner = (ids8.clamp(min=0) // epr).long()
+        acc = torch.zeros((tl, n), dtype=torch.float32, device=dev)
+        for j in range(topk):
+            term = wts[:, j:j + 1] * d_all[owner[:, j], rows[:, j].clamp(min=0)].float()
+            acc = torch.where(routed[:, j:j + 1], acc + term, acc)
+        assert torch.equal(out, acc.to(torch.bfloat16)), f'weighted top-{topk} combine {it}'
+        # and the rows are right: FP32 matmul of the dequantised token with the owner's expert weights
+        sfx = (sf.contiguous().view(torch.uint8).to(torch.int32) << 23).view(torch.float32)
+        x_deq = xq.float() * sfx[:, :k // 128].repeat_interleave(128, 1)
+        for e in (0, g // 2, g - 1):
+            sel = (ids8 == e).any(dim=1)
+            if bool(sel.any()):
+                wq_e, sw_e = w_all[e // epr][e % epr]
+                w_deq = wq_e.float() * sw_e.repeat_interleave(128, 0).repeat_interleave(128, 1)
+                slot = (ids8[sel] == e).float().argmax(dim=1)
+                got = d_all[e // epr][rows[sel].gather(1, slot.unsqueeze(1)).squeeze(1)]
+                assert calc_diff(got, x_deq[sel] @ w_deq.t()) < 1e-5, (rank, e)
+        dist.barrier()                                                   # nobody re-dispatches while a peer still reads D
+    total += 0
+
     # (d) CUDA graph: capture dispatch + GEMM once, replay with new inputs
     sx, ssf, sids = torch.empty_like(xq), torch.empty_like(sf), torch.empty(t_local, dtype=torch.int64, device=dev)
     row = torch.empty(t_local, dtype=torch.int32, device=dev)
@@ -119,7 +162,7 @@ def main():
         d.fill_(float('nan'))
         graph.replay()
         total += check(xq, sf, ids, d, r, f'graph {it}')
-    print(f'rank {rank}/{world}: ep check ok, {total} rows verified over 6 dispatches (2 under CUDA graph)', flush=True)
+    print(f'rank {rank}/{world}: ep check ok, {total} rows verified over 6 dispatches (2 under CUDA graph), top-8 weighted combine bit-exact', flush=True)
     del graph
     buf.close()
     dist.destroy_process_group()
