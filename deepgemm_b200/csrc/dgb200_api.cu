@@ -181,6 +181,7 @@ int csplit_staging_bytes(int block_m, int splits) { return (splits - 1) * (block
 constexpr double kSmIngest = 45.0, kL2Rate = 8000.0, kHbmRate = 3400.0, kTileOverhead = 1500.0, kSplitOverhead = 2500.0;
 constexpr int kMaxSplits = 8;
 constexpr int kTmaStoreMinBlockM = 64;                // shorter tiles keep the direct-store epilogue
+constexpr int kPairSplitMinM = 0, kPairSplitMaxM = 0;  // pair split-K by default for M in this range (0: only when forced)
 constexpr int kSplitKCounters = 4096;                 // ints at the start of the workspace
 constexpr size_t kSplitKHeaderBytes = kSplitKCounters * sizeof(int);
 
@@ -318,7 +319,37 @@ Config choose_config(const Problem& pb, int num_sms_override = 0) {
             c.grid = ceil_div(pb.n, (int)kBlockN) * pick, c.grid_y = ceil_div(pb.m, pick_bm);   // (n-tile x slice, m-block)
         }
     }
-    const int cta_group = c.csplit ? 1 : std::min(c.cluster, 2);
+    // Pair split-K (dense, K-major, medium M): the same exchange between S CTA PAIRS (cluster of 2 S). A pair owns 256 weight
+    // rows x block_m tokens of HALF (a quarter) of K, so a 192..480-row problem runs as few tall tiles on all SMs instead of
+    // many short ones: the bytes every SM pulls through L2 per output drop by ~40 % (the mid-M shapes are bound by L2 -> SM
+    // traffic, not by HBM or the tensor pipe). DGB200_PSPLIT = 0 / 2 / 4 pins it, DGB200_PSPLIT_BM the tile height.
+    if (!c.csplit && pb.type == kDense && !pb.any_mn && c.cluster == 2 && pb.m > 0 && rt().split_k && c.num_splits == 1) {
+        const int want = env_int("DGB200_PSPLIT", -1);
+        int pick = 0, pick_bm = 0;
+        for (int sp : {2, 4}) {
+            if (want == 0 || (want > 0 && want != sp) || (want < 0 && pinned)) continue;
+            const int unit = 16 * sp, max_bm = (int)kMaxBlockM / unit * unit;
+            int bm = align_up(ceil_div(pb.m, ceil_div(pb.m, max_bm)), unit);
+            if (int v = env_int("DGB200_PSPLIT_BM", 0)) bm = v;
+            if (bm % unit != 0 || bm > max_bm || num_kb / sp < 2 || ceil_div(num_kb, sp) * (sp - 1) >= num_kb) continue;
+            const int tiles = ceil_div(pb.m, bm) * ceil_div(pb.n, 2 * (int)kBlockN);
+            if (want > 0) {
+                pick = sp, pick_bm = bm;
+                break;
+            }
+            // heuristic (tools/tune.py mid, B200): one wave of pair-slices, more than one m-block's worth of rows per tile
+            if (kPairSplitMinM > 0 && pb.m >= kPairSplitMinM && pb.m <= kPairSplitMaxM && sp == 2 && tiles * sp * 2 <= c.num_sms && num_kb >= 16)
+                pick = sp, pick_bm = bm;
+            if (pick) break;
+        }
+        if (pick) {
+            c.csplit = pick, c.cluster = 2 * pick, c.block_m = pick_bm;
+            c.kb_per_split = ceil_div(num_kb, pick), c.num_splits = pick;
+            c.grid = ceil_div(pb.n, 2 * (int)kBlockN) * 2 * pick, c.grid_y = ceil_div(pb.m, pick_bm);   // (n-unit x slice x 2, m-block)
+            c.num_tall = 0, c.block_m_low = 0;
+        }
+    }
+    const int cta_group = c.csplit ? c.cluster / c.csplit : std::min(c.cluster, 2);
     const int staging = c.csplit ? csplit_staging_bytes(c.block_m, c.csplit) : 0;
     // Staged TMA-store epilogue: pays when tiles are tall (the direct epilogue stores 64 B per instruction and keeps the
     // epilogue warps busy until the last row has left); small tiles keep all of shared memory for the TMA -> MMA ring.
@@ -368,13 +399,15 @@ int run_gemm(const GemmCall& c) {
     if (cfg.num_splits > 1 && ceil_div(c.m, cfg.block_m) * ceil_div(c.n, (int)kBlockN) > kSplitKCounters)
         cfg.num_splits = 1, cfg.kb_per_split = ceil_div(c.k, (int)kBlockK);
     if (pb.any_mn && cfg.cluster > 2) cfg.cluster = 2;            // weight multicast is built for K-major tiles only
-    const int cta_group = (cfg.cluster >= 2 && !cfg.csplit) ? 2 : 1, pairs = (cfg.cluster >= 2 && !cfg.csplit) ? cfg.cluster / 2 : 1;
+    const int cta_group = cfg.csplit ? cfg.cluster / cfg.csplit : (cfg.cluster >= 2 ? 2 : 1);
+    const int pairs = (cfg.cluster >= 2 && !cfg.csplit) ? cfg.cluster / 2 : 1;
     const int load_m = cfg.block_m / cta_group;
     DGB_REQUIRE(cfg.block_m % 16 == 0 && cfg.block_m >= 16 && cfg.block_m <= (int)kMaxBlockM);
     DGB_REQUIRE(cfg.cluster == 1 || cfg.cluster == 2 || (c.type == kDense && (cfg.cluster == 4 || cfg.cluster == 8)));
+    DGB_REQUIRE(cta_group == 1 || cta_group == 2);
     if (cfg.cluster > 2 && !cfg.csplit) cfg.tma_store = 0;
     DGB_REQUIRE(cfg.cluster <= 2 || cfg.num_splits == 1 || cfg.csplit);
-    if (cfg.csplit) DGB_REQUIRE(cfg.block_m % (16 * cfg.csplit) == 0 && cfg.cluster == cfg.csplit);
+    if (cfg.csplit) DGB_REQUIRE(cfg.block_m % (16 * cfg.csplit) == 0 && (cfg.cluster == cfg.csplit || cfg.cluster == 2 * cfg.csplit));
     if (c.type == kMContiguous || c.type == kMContiguousPsum) DGB_REQUIRE(c.alignment % cfg.block_m == 0);
     cfg.overlap_producer = c.arrival != nullptr;
     if (c.x_mn) DGB_REQUIRE(load_m % 32 == 0);
@@ -883,7 +916,7 @@ int dgb200_plan(int gemm_type, int m, int n, int k, int num_groups, int expected
     if (gemm_type == kDense && n % 4 == 0) pb.max_splits = kMaxSplits;   // as if a workspace were supplied
     pb.tma_store_ok = gemm_type == kDense || gemm_type == kMContiguous;   // as if D were an aligned BF16 tensor
     const Config cfg = choose_config(pb, num_sms);
-    const int n_units = ceil_div(n, (int)kBlockN * (cfg.csplit ? 1 : std::min(cfg.cluster, 2)));
+    const int n_units = ceil_div(n, (int)kBlockN * (cfg.csplit ? cfg.cluster / cfg.csplit : std::min(cfg.cluster, 2)));
     int m_blocks = gemm_type == kMMasked ? num_groups * ceil_div(pb.expected_m, cfg.block_m) : ceil_div(m, cfg.block_m);
     if (gemm_type == kDense && cfg.block_m_low > 0)   // two tile heights (wave balancing)
         m_blocks = cfg.num_tall + ceil_div(std::max(0, m - cfg.num_tall * cfg.block_m), cfg.block_m_low);

@@ -121,12 +121,13 @@ struct Tile {
 
 // kCluster = CTAs per cluster: 1 (single CTA MMA), 2 (one cta_group::2 pair) or 4 / 8 (2 / 4 pairs that work on
 // consecutive m-blocks of the SAME weight panel and share its TMA loads by multicast; dense only).
-// kCSplit: the cluster is kCluster single-CTA MMAs that cut K of ONE output tile between them (split-K inside the
-// cluster, reduced through distributed shared memory); `rank` is then 0 and `split_rank` the slice.
-template <int kGemmType, int kCluster, bool kSplitK = false, bool kCSplit = false>
+// kCSplit (0 = off, else the number of K slices): the cluster is kCSplit MMA groups -- single CTAs (kCluster == kCSplit) or
+// CTA pairs (kCluster == 2 kCSplit) -- that cut K of ONE output tile between them (split-K inside the cluster, reduced
+// through distributed shared memory); `rank` is then the position inside the MMA group and `split_rank` the slice.
+template <int kGemmType, int kCluster, bool kSplitK = false, int kCSplit = 0>
 struct Scheduler {
     static constexpr uint32_t kPairs = (kCluster >= 2 && !kCSplit) ? kCluster / 2 : 1;
-    static constexpr uint32_t kCtaGroup = (kCluster >= 2 && !kCSplit) ? 2 : 1;
+    static constexpr uint32_t kCtaGroup = kCSplit ? kCluster / kCSplit : (kCluster >= 2 ? 2 : 1);
     const GemmParams& p;
     uint32_t cta_rank, cluster_id, num_clusters;
     uint32_t num_n_units;
@@ -170,7 +171,7 @@ struct Scheduler {
             t.d_row = t.x_row, t.sfx_col = t.x_row, t.sfx_row = 0;
             t.valid_m = min(p.block_m, p.m - t.x_row);
             t.store_m = t.valid_m;
-            t.n0 = cluster_id * kBlockN;
+            t.n0 = (cluster_id * kCtaGroup + (cta_rank & 1)) * kBlockN;
             t.w_row = t.n0, t.sfw_col = t.n0, t.sfw_row = 0;
             return true;
         }
@@ -406,8 +407,8 @@ __device__ __forceinline__ void splitk_finalize(const float* ws, size_t slice_el
 // fp8_gemm_{nn,tn,tt}, m_grouped nn, and both operands of the K-grouped weight-gradient GEMM.
 // kSplitK: the dense split-K variant (K slices + finalising pass); kept out of the common instantiations because its
 // epilogue doubles the code size, which a cold instruction cache charges to every short launch.
-// kCSplit: split-K inside a cluster of kCluster single-CTA MMAs (dense, small M): every CTA accumulates one K slice of
-// the same output tile; the partial tiles are exchanged through distributed shared memory (reduce-scatter over the
+// kCSplit (number of slices): split-K inside a cluster of kCSplit MMA groups (single CTAs, or CTA pairs for taller tiles;
+// dense, small / medium M): every group accumulates one K slice of the same output tile; the partial tiles are exchanged through distributed shared memory (reduce-scatter over the
 // token columns, `st.async` + transaction barrier) and added in slice order, so each weight byte crosses L2->SM once
 // instead of once per m-block and nothing goes through global memory. One tile per cluster (the host guarantees it).
 // kTmaStore: BF16 output tiles leave through shared memory: TMEM -> registers (16x256b fragments) -> BF16 pairs ->
@@ -417,7 +418,7 @@ __device__ __forceinline__ void splitk_finalize(const float* ws, size_t slice_el
 // the end of D are clipped by the tensor map. Used for tall tiles (dense, contiguous); the direct-store epilogue stays
 // for small tiles (all shared memory feeds the ring) and for layouts that need exact row predication (masked, psum).
 template <int kGemmType, int kCluster, typename out_t, bool kAccumulate, bool kXMn = false, bool kWMn = false,
-          bool kSplitK = false, bool kCSplit = false, bool kTmaStore = false>
+          bool kSplitK = false, int kCSplit = 0, bool kTmaStore = false>
 __global__ void __launch_bounds__(kNumThreads, 1)
 fp8_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
                 const __grid_constant__ CUtensorMap map_sfx, const __grid_constant__ CUtensorMap map_sfw,
@@ -430,11 +431,15 @@ fp8_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
     const uint32_t lane = lane_id();
     if (threadIdx.x == 0) DGB_STAMP(0);
     if (threadIdx.x == 0 && p.debug_ts != nullptr) p.debug_ts[16 + 2 * blockIdx.x] = globaltimer_ns();   // per-CTA entry
-    constexpr int kCtaGroup = (kCluster >= 2 && !kCSplit) ? 2 : 1;          // CTAs per UMMA (cta_group)
+    constexpr int kCtaGroup = kCSplit ? kCluster / kCSplit : (kCluster >= 2 ? 2 : 1);   // CTAs per UMMA (cta_group)
+    static_assert(kCtaGroup == 1 || kCtaGroup == 2, "an MMA group is one CTA or a CTA pair");
     constexpr uint32_t kPairs = (kCluster >= 2 && !kCSplit) ? kCluster / 2 : 1;   // CTA pairs per cluster (share the weight loads)
-    const uint32_t cta_rank = (kCluster == 1 || kCSplit) ? 0u : cluster_ctarank();   // position inside the MMA group(s)
-    const uint32_t split_rank = kCSplit ? cluster_ctarank() : 0u;                     // K slice (cluster split-K)
-    const uint32_t pair_idx = cta_rank >> 1, leader_rank = cta_rank & ~1u;
+    const uint32_t cluster_rank = kCluster == 1 ? 0u : cluster_ctarank();
+    // position inside the MMA group(s): cluster split-K counts inside its own group, the others across the cluster
+    const uint32_t cta_rank = kCSplit ? cluster_rank % kCtaGroup : cluster_rank;
+    const uint32_t split_rank = kCSplit ? cluster_rank / kCtaGroup : 0u;              // K slice (cluster split-K)
+    const uint32_t pair_idx = cta_rank >> 1;
+    const uint32_t leader_rank = kCSplit ? cluster_rank - cta_rank : (cta_rank & ~1u);   // CLUSTER rank of this group's leader CTA
     const bool is_leader = (cta_rank & 1) == 0;
 
     // ---- shared memory carve-up (all sizes are runtime values), as 32-bit shared::cta addresses
@@ -636,8 +641,10 @@ fp8_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
             const uint64_t sfw_desc0 = make_smem_desc(smem_base + off_sfw, 0, 128, kLayoutNoSwizzle);
             const uint64_t sfx_desc0 = make_smem_desc(smem_base + off_sfx, 0, 128, kLayoutNoSwizzle);
             const uint32_t tmem_sfw = tmem_base + kTmemColSFW, tmem_sfx = tmem_base + kTmemColSFX;
-            constexpr uint16_t kEmptyMask = static_cast<uint16_t>((1u << (kCSplit ? 1 : kCluster)) - 1);   // every CTA's `empty` barrier
             const uint16_t pair_mask = static_cast<uint16_t>(0b11u << leader_rank);           // this pair only
+            // `empty` barriers the retiring MMAs release: every CTA that holds operands of them (the whole cluster when pairs
+            // share multicast weight tiles, else this MMA group)
+            const uint16_t kEmptyMask = kCSplit ? pair_mask : static_cast<uint16_t>((1u << kCluster) - 1);
             // The issue loop below bounds every shape whose tiles are small (each k-block then costs its ~50
             // instructions, not its MMA time), so everything loop-invariant is hoisted: per-k-block work is one barrier
             // wait, <= 3 tcgen05.cp, 4 tcgen05.mma whose descriptors differ by immediates, and one commit.
@@ -773,9 +780,10 @@ fp8_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
                 //   own piece    : (after the peers' bytes have landed) partials added in slice order -> D
                 // Staging of owner q: float4 [source slot][c/4 column quads][128 weight rows]; a warp writes / reads 512
                 // contiguous bytes per quad.
-                constexpr uint32_t S = kCluster;
+                constexpr uint32_t S = kCSplit;
                 const uint32_t c = p.block_m / S, pieces_per_chunk = c / 16;
                 const uint32_t chunk_bytes = c * 128 * 4;                      // one source's partial of one chunk
+                auto peer_of = [&](uint32_t q) { return q * kCtaGroup + cta_rank; };   // cluster rank of slice q's CTA that holds my weight rows
                 if (threadIdx.x == 4 * 32) mbar_arrive_expect_tx(red_bar, (S - 1) * chunk_bytes);
                 const uint32_t row_n = quad * 32 + lane;                       // weight row of this thread inside the tile
                 const uint32_t num_pieces = p.block_m / 16;
@@ -803,37 +811,28 @@ fp8_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
                     for (uint32_t q = 0; q < S; ++q) {
                         if (q == split_rank) continue;
                         const uint32_t slot = split_rank < q ? split_rank : split_rank - 1;
-                        bulk_copy_to_peer(mapa(red_stage + slot * chunk_bytes, q), smem_base + q * chunk_bytes, chunk_bytes,
-                                          mapa(red_bar, q));
+                        bulk_copy_to_peer(mapa(red_stage + slot * chunk_bytes, peer_of(q)), smem_base + q * chunk_bytes, chunk_bytes,
+                                          mapa(red_bar, peer_of(q)));
                     }
                 }
-                // My own chunk in units of 8 token columns (the two warps of a quadrant alternate): load the own partial
-                // now, add the peers' partials in slice order once they have landed, write D.
-                constexpr uint32_t kMaxUnits = 4;                             // c <= 64 -> <= 8 units, 4 per warp
-                uint32_t own[kMaxUnits][8];
+                // My own chunk in units of 8 token columns (the two warps of a quadrant alternate): own partial from TMEM,
+                // the peers' partials from the staging buffer once they have landed, added in slice order, written to D.
+                // (One tile per cluster: nothing waits for this accumulator, so it is read where it is needed.)
                 const uint32_t units = c / 8;
-#pragma unroll
-                for (uint32_t ui = 0; ui < kMaxUnits; ++ui) {
-                    const uint32_t u = half + 2 * ui;
-                    if (u < units) tmem_ld_32x32b_x8(taddr + split_rank * c + u * 8, own[ui]);
-                }
-                tmem_ld_wait();
-                tcgen05_fence_before();
-                mbar_arrive(tmem_empty_dst + as * 8);                        // last TMEM read of this tile
                 if (threadIdx.x == 4 * 32) DGB_STAMP(12);
                 mbar_wait(red_bar, 0);
                 if (threadIdx.x == 4 * 32) DGB_STAMP(13);
-#pragma unroll
-                for (uint32_t ui = 0; ui < kMaxUnits; ++ui) {
-                    const uint32_t u = half + 2 * ui;
-                    if (u >= units) break;
+                for (uint32_t u = half; u < units; u += 2) {
+                    uint32_t own[8];
+                    tmem_ld_32x32b_x8(taddr + split_rank * c + u * 8, own);
+                    tmem_ld_wait();
                     float acc[8];
 #pragma unroll
                     for (uint32_t s = 0; s < S; ++s) {                          // slice order: deterministic
                         if (s == split_rank) {
 #pragma unroll
                             for (uint32_t j = 0; j < 8; ++j)
-                                acc[j] = s == 0 ? __uint_as_float(own[ui][j]) : acc[j] + __uint_as_float(own[ui][j]);
+                                acc[j] = s == 0 ? __uint_as_float(own[j]) : acc[j] + __uint_as_float(own[j]);
                         } else {
                             const uint32_t slot = s < split_rank ? s : s - 1;
                             const uint32_t src = red_stage + slot * chunk_bytes + ((u * 2) * 128 + row_n) * 16;
@@ -860,6 +859,11 @@ fp8_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
                         }
                     }
                 }
+                tcgen05_fence_before();
+                if constexpr (kCtaGroup > 1)
+                    mbar_arrive_remote(tmem_empty_dst + as * 8);             // last TMEM read of this tile
+                else
+                    mbar_arrive(tmem_empty_dst + as * 8);
                 continue;
             }
             if constexpr (kSplitK) {

@@ -8,7 +8,7 @@ template <int kCluster, bool kXMn, bool kWMn>
 static int by_output(const GemmCall& c, const Config& cfg, const Maps& maps, const GemmParams& p) {
     if constexpr (kCluster == 2) {
         if (cfg.tma_store)
-            return launch_kernel(fp8_gemm_kernel<kDense, 2, __nv_bfloat16, false, kXMn, kWMn, false, false, true>, cfg, c.stream,
+            return launch_kernel(fp8_gemm_kernel<kDense, 2, __nv_bfloat16, false, kXMn, kWMn, false, 0, true>, cfg, c.stream,
                                  maps, p);
     }
     if (c.d_dtype == DGB200_BF16)

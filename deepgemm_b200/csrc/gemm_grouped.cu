@@ -10,7 +10,7 @@ template <int kType, bool kWMn>
 static int m_grouped(const GemmCall& c, const Config& cfg, const Maps& maps, const GemmParams& p) {
     if constexpr (kType == kMContiguous) {
         if (cfg.cluster == 2 && cfg.tma_store)
-            return launch_kernel(fp8_gemm_kernel<kType, 2, __nv_bfloat16, false, false, kWMn, false, false, true>, cfg, c.stream,
+            return launch_kernel(fp8_gemm_kernel<kType, 2, __nv_bfloat16, false, false, kWMn, false, 0, true>, cfg, c.stream,
                                  maps, p);
     }
     if (cfg.cluster == 2) return launch_kernel(fp8_gemm_kernel<kType, 2, __nv_bfloat16, false, false, kWMn>, cfg, c.stream, maps, p);

@@ -11,7 +11,8 @@ import deepgemm_b200 as dg  # noqa: E402
 from deepgemm_b200 import _lib  # noqa: E402
 from deepgemm_b200.testing import bench_kineto  # noqa: E402
 
-KEYS = ('DGB200_BLOCK_M', 'DGB200_CLUSTER', 'DGB200_STAGES', 'DGB200_SWIZZLE_GROUP', 'DGB200_CSPLIT', 'DGB200_SPLITS')
+KEYS = ('DGB200_BLOCK_M', 'DGB200_CLUSTER', 'DGB200_STAGES', 'DGB200_SWIZZLE_GROUP', 'DGB200_CSPLIT', 'DGB200_SPLITS', 'DGB200_PSPLIT',
+        'DGB200_PSPLIT_BM', 'DGB200_TMA_STORE')
 
 
 def setenv(**kw):
@@ -39,7 +40,8 @@ def run(shapes, configs, with_ref=True):
                 dg.fp8_gemm_nt((qa[0], sfa), (qb[0], sfb), d)
                 used = _lib.last_config()
                 t = bench_kineto(lambda: dg.fp8_gemm_nt((qa[0], sfa), (qb[0], sfb), d), 'fp8_gemm_kernel', num_tests=10)
-                rows.append((json.dumps(cfg), round(t * 1e6, 2), used['block_m'], used['num_stages'], used['cluster'], used['num_splits']))
+                rows.append((json.dumps(cfg), round(t * 1e6, 2), used['block_m'], used['num_stages'], used['cluster'], used['num_splits'],
+                             'tma' if used['tma_store'] else 'direct'))
             except Exception as e:  # noqa: BLE001
                 rows.append((json.dumps(cfg), 'error ' + str(e)[:80]))
         setenv()
@@ -54,10 +56,16 @@ if __name__ == '__main__':
         cfgs = [{}] + [dict(block_m=bm, swizzle_group=sg) for bm in (128, 160, 192, 208, 224, 240) for sg in (4, 8, 16)]
         cfgs += [dict(block_m=bm, stages=st) for bm in (224, 240) for st in (4, 5)]
         run([(4096, 7168, 2048), (4096, 4096, 7168)], cfgs)
+    elif mode == 'store':
+        # staged TMA-store epilogue on / off at the heuristics' own tile choice and at pinned heights
+        cfgs = [dict(tma_store=0), dict(tma_store=1)] + [dict(tma_store=ts, block_m=bm) for bm in (128, 192, 224, 240) for ts in (0, 1)]
+        run([(4096, 4096, 7168), (4096, 7168, 2048), (512, 4096, 7168), (512, 7168, 2048), (1024, 4096, 7168), (4096, 2112, 7168),
+             (4096, 24576, 1536), (4096, 32768, 512)], cfgs)
     elif mode == 'mid':
-        cfgs = [{}] + [dict(block_m=bm, csplit=0) for bm in (48, 64, 96, 128, 160, 192, 240)]
-        run([(192, 4096, 7168), (256, 4096, 7168), (384, 4096, 7168), (768, 4096, 7168), (1024, 4096, 7168), (256, 7168, 2048),
-             (512, 7168, 2048), (1024, 7168, 2048)], cfgs)
+        cfgs = [{}] + [dict(block_m=bm, csplit=0) for bm in (64, 96, 128, 192)]
+        cfgs += [dict(psplit=2, psplit_bm=bm, csplit=0) for bm in (96, 128, 160, 192, 224)] + [dict(psplit=4, psplit_bm=bm, csplit=0) for bm in (128, 192)]
+        run([(192, 4096, 7168), (256, 4096, 7168), (320, 4096, 7168), (384, 4096, 7168), (448, 4096, 7168), (512, 4096, 7168),
+             (256, 7168, 2048), (512, 7168, 2048), (256, 2112, 7168), (384, 7168, 16384)], cfgs)
     elif mode == 'small':
         cfgs = [{}, dict(csplit=0), dict(csplit=4), dict(csplit=2)] + [dict(csplit=0, block_m=bm) for bm in (16, 32, 64)]
         run([(1, 2112, 7168), (16, 4096, 7168), (32, 4096, 7168), (64, 4096, 7168), (96, 4096, 7168), (128, 4096, 7168), (192, 4096, 7168),
