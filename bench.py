@@ -19,6 +19,7 @@ Outside the timed regions the same line also carries (every block degrades to {"
     weighted top-k combine) with dispatch / GEMM / combine split and, for N > 1, the 1-GPU step run on rank 0 so that
     `efficiency_vs_n1` is in the line. `value` stays the dense metric (replicas), so the driver's scaling table keeps one
     metric across N.
+  * `decode_chain` -- the M = 64 GEMM inside a chain of 12 layers (stream order / PDL / CUDA graph), ours and the reference's.
   * `fp8_peak` -- the issue-only tcgen05.mma block-scaled FP8 probe (burst and 2 s sustained); `roofline.peak` uses it.
 
 `--impl reference` runs the UNMODIFIED reference through its own public API (`deep_gemm.fp8_gemm_nt` from oracle/_ref) on
@@ -162,8 +163,9 @@ def import_reference():
 
 
 def time_ab(fn_a, fn_b, iters, warmup=3):
-    """Device time of two callables on the same stream, interleaved launch by launch, each preceded by an L2 flush and
-    bracketed by CUDA events. Returns (median_a_ms, median_b_ms, min_a_ms, min_b_ms); fn_b may be None."""
+    """Device time of two callables on the same stream, interleaved launch by launch (the order alternates every
+    iteration), each preceded by an L2 flush and bracketed by CUDA events.
+    Returns (median_a_ms, median_b_ms, min_a_ms, min_b_ms); fn_b may be None."""
     from deepgemm_b200.testing import flush_l2
     fns = [f for f in (fn_a, fn_b) if f is not None]
     for _ in range(warmup):
@@ -172,10 +174,11 @@ def time_ab(fn_a, fn_b, iters, warmup=3):
     torch.cuda.synchronize()
     evs = [[(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in fns] for _ in range(iters)]
     for it in range(iters):
-        for j, f in enumerate(fns):
+        order = range(len(fns)) if it % 2 == 0 else reversed(range(len(fns)))
+        for j in order:
             flush_l2()
             evs[it][j][0].record()
-            f()
+            fns[j]()
             evs[it][j][1].record()
     torch.cuda.synchronize()
     out = []
@@ -185,6 +188,12 @@ def time_ab(fn_a, fn_b, iters, warmup=3):
     if fn_b is None:
         return out[0][0], None, out[0][1], None
     return out[0][0], out[1][0], out[0][1], out[1][1]
+
+
+def kineto_us(fn, name, num_tests=10):
+    """Mean kernel time by the profiler, the reference's own method (deep_gemm/testing/bench.py:79-146), in us."""
+    from deepgemm_b200.testing import bench_kineto
+    return round(bench_kineto(fn, name, num_tests=num_tests) * 1e6, 2)
 
 
 # ------------------------------------------------------------------------------------------------ FP8 tensor peak
@@ -313,18 +322,23 @@ def dense_ab_block(probs, dg, iters=20):
             torch.cuda.synchronize()
             default_mismatch = int((d_ref != d_our).sum())
             ours, refk, ours_min, ref_min = time_ab(f_our, f_ref, iters)
+            k_our, k_ref = kineto_us(f_our, 'fp8_gemm_kernel'), kineto_us(f_ref, 'gemm_')
             rows.append({'m': m, 'n': n, 'k': k, 'ours_us': round(ours * 1e3, 2), 'ref_kernel_us': round(refk * 1e3, 2),
                          'speedup': round(refk / ours, 4), 'ours_min_us': round(ours_min * 1e3, 2), 'ref_min_us': round(ref_min * 1e3, 2),
+                         'ours_kineto_us': k_our, 'ref_kineto_us': k_ref, 'speedup_kineto': round(k_ref / k_our, 4) if k_our else None,
                          'ours_tflops': round(2.0 * m * n * k / (ours * 1e-3) / 1e12, 1),
                          'ref_tflops': round(2.0 * m * n * k / (refk * 1e-3) / 1e12, 1),
                          'bitwise_equal': bitwise, 'default_config_mismatching_elements': default_mismatch})
         except Exception as e:  # noqa: BLE001
             rows.append({'m': m, 'n': n, 'k': k, 'unavailable': f'{type(e).__name__}: {e}'[:300]})
     ok = [r for r in rows if 'speedup' in r]
-    return {'method': 'median of %d interleaved launches each, L2 flushed (512 MB write) before every launch, CUDA events; '
-                      'bitwise_equal with set_split_k(False), default_config_mismatching_elements with the default (cluster split-K for M <= 128)' % iters,
+    return {'method': 'median of %d interleaved launches each (order alternating), L2 flushed (512 MB write) before every launch, CUDA events '
+                      '(*_us: includes the launch gaps around one kernel); *_kineto_us: mean kernel time by torch.profiler, the reference\'s own '
+                      'bench_kineto method; bitwise_equal with set_split_k(False), default_config_mismatching_elements with the default '
+                      '(cluster split-K for M <= 256)' % iters,
             'reference': 'deepseek-ai/DeepGEMM sm100_fp8_fp4_gemm_1d1d (oracle/_ref, unmodified, NVCC JIT on this box)',
-            'per_shape': rows, 'ours_ge_reference_on_every_shape': bool(ok) and all(r['speedup'] >= 1.0 for r in ok) and len(ok) == len(rows)}
+            'per_shape': rows, 'ours_ge_reference_on_every_shape': bool(ok) and all(r['speedup'] >= 1.0 for r in ok) and len(ok) == len(rows),
+            'ours_ge_reference_on_every_shape_kineto': bool(ok) and all((r.get('speedup_kineto') or 0) >= 1.0 for r in ok) and len(ok) == len(rows)}
 
 
 def run_dense(args, rank, world, device):
@@ -412,6 +426,9 @@ def add_dense_extras(out, probs, args, rank, world, device):
         out['vs_reference_kernel'] = guarded(lambda: dense_ab_block(probs, dg))
     probs.clear()
     torch.cuda.empty_cache()
+    if rank == 0:
+        out['decode_chain'] = guarded(lambda: decode_chain_block(device, dg))
+    torch.cuda.empty_cache()
     barrier(world)
     weights = None
     if rank == 0:
@@ -459,6 +476,75 @@ def time_dense_e2e(args, world, device, probs, quantise, pack_b, gemm):
     torch.cuda.synchronize()
     barrier(world)
     return allreduce_max(e0.elapsed_time(e1) / args.steps, world, device), h2d, d2h
+
+
+def decode_chain_block(device, dg, layers=12, m=64, n=4096, k=7168, reps=8):
+    """A decode micro-step: `layers` different weight matrices (12 x 29 MB > L2, so every GEMM streams its weights from HBM)
+    applied back to back with M = 64 tokens, no flush and no event between the launches -- what the small-M kernel looks like
+    inside a real step, where the ~4-5 us of launch gap around an isolated, event-timed launch disappear: plain stream order,
+    programmatic dependent launch (set_pdl: the next GEMM's prologue and weight prefetch overlap this one's tail), and one CUDA
+    graph of the chain. Per-GEMM time = total / launches; the reference's kernel runs the same chain."""
+    from deepgemm_b200.utils import per_block_cast_to_fp8, per_token_cast_to_fp8
+    peaks, peak_kind = load_peaks()
+    gen = torch.Generator(device=device).manual_seed(5)
+    a = torch.randn((m, k), device=device, dtype=torch.bfloat16, generator=gen)
+    qa = per_token_cast_to_fp8(a, True)
+    ws = [per_block_cast_to_fp8(torch.randn((n, k), device=device, dtype=torch.bfloat16, generator=gen), True) for _ in range(layers)]
+    byts = m * k + n * k + m * n * 2 + (m + n) * ((k + 511) // 512) * 4
+    out = {'workload': f'{layers} layers of fp8_gemm_nt {m}x{n}x{k} back to back ({layers * n * k / 1e6:.0f} MB of weights cycling through a 126 MB L2)',
+           'hbm_roofline_us': round(byts / peaks['hbm_gbs'] / 1e3, 2)}
+
+    def run(lib_mod, tag):
+        sfa = lib_mod.transform_sf_into_required_layout(qa[1], m, k, (1, 128, 128), None, True)
+        sfbs = [lib_mod.transform_sf_into_required_layout(w[1], n, k, (1, 128, 128), None, False) for w in ws]
+        ds = [torch.empty((m, n), device=device, dtype=torch.bfloat16) for _ in range(layers)]
+
+        def chain():
+            for i in range(layers):
+                lib_mod.fp8_gemm_nt((qa[0], sfa), (ws[i][0], sfbs[i]), ds[i])
+
+        def timed(fn):
+            for _ in range(3):
+                fn()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(reps):
+                fn()
+            e1.record()
+            torch.cuda.synchronize()
+            return round(e0.elapsed_time(e1) * 1e3 / (reps * layers), 2)
+
+        res = {}
+        for pdl in (False, True):
+            lib_mod.set_pdl(pdl)
+            try:
+                res['pdl_us' if pdl else 'stream_us'] = timed(chain)
+                chain()
+                torch.cuda.synchronize()
+                graph, side = torch.cuda.CUDAGraph(), torch.cuda.Stream()
+                with torch.cuda.stream(side):
+                    with torch.cuda.graph(graph, stream=side):
+                        chain()
+                res['graph_pdl_us' if pdl else 'graph_us'] = timed(graph.replay)
+                del graph
+            except Exception as e:  # noqa: BLE001
+                res['pdl_error' if pdl else 'error'] = f'{type(e).__name__}: {e}'[:200]
+            finally:
+                lib_mod.set_pdl(False)
+        best = min(v for v in res.values() if isinstance(v, float))
+        res['best_us'] = best
+        res['best_frac_of_hbm_roofline'] = round(out['hbm_roofline_us'] / best, 4)
+        out[tag] = res
+
+    run(dg, 'ours')
+    try:
+        run(import_reference(), 'reference')
+        out['speedup_best'] = round(out['reference']['best_us'] / out['ours']['best_us'], 4)
+    except Exception as e:  # noqa: BLE001
+        out['reference'] = {'unavailable': f'{type(e).__name__}: {e}'[:300]}
+    out['method'] = f'CUDA events around {reps} x {layers} launches, per-GEMM time = total / launches; no L2 flush needed: the weights exceed L2'
+    return out
 
 
 def guarded(fn):
@@ -617,8 +703,10 @@ def grouped_blocks(device, dg, iters=10):
                     same = bool(torch.equal(p['d'][rows], d_ref[rows]))
                 else:
                     same = bool(torch.equal(p['d'][p['layout'] >= 0], d_ref[p['layout'] >= 0]))
+                k_our, k_ref = kineto_us(p['ours'], 'fp8_gemm_kernel', 5), kineto_us(f_ref, 'gemm_', 5)
                 line.update({'ref_kernel_us': round(refk * 1e3, 1), 'speedup': round(refk / ours, 4), 'ours_min_us': round(ours_min * 1e3, 1),
-                             'ref_min_us': round(ref_min * 1e3, 1), 'bitwise_equal_valid_rows': same})
+                             'ref_min_us': round(ref_min * 1e3, 1), 'ours_kineto_us': k_our, 'ref_kineto_us': k_ref,
+                             'speedup_kineto': round(k_ref / k_our, 4) if k_our else None, 'bitwise_equal_valid_rows': same})
             else:
                 line['reference'] = {'unavailable': ref_err}
             out[kind] = line

@@ -180,8 +180,8 @@ int csplit_staging_bytes(int block_m, int splits) { return (splits - 1) * (block
 //                 token tiles by the n-units in flight) at ~kHbmRate B/cycle
 constexpr double kSmIngest = 45.0, kL2Rate = 8000.0, kHbmRate = 3400.0, kTileOverhead = 1500.0, kSplitOverhead = 2500.0;
 constexpr int kMaxSplits = 8;
-constexpr int kTmaStoreMinBlockM = 64;                // shorter tiles keep the direct-store epilogue
-constexpr int kPairSplitMinM = 0, kPairSplitMaxM = 0;  // pair split-K by default for M in this range (0: only when forced)
+constexpr int kTmaStoreMinBlockM = 176;               // shorter tiles keep the direct-store epilogue
+constexpr int kPairSplitMaxBlockM = 128;              // pair split-K by default: one m-block of at most this many rows
 constexpr int kSplitKCounters = 4096;                 // ints at the start of the workspace
 constexpr size_t kSplitKHeaderBytes = kSplitKCounters * sizeof(int);
 
@@ -323,13 +323,15 @@ Config choose_config(const Problem& pb, int num_sms_override = 0) {
     // rows x block_m tokens of HALF (a quarter) of K, so a 192..480-row problem runs as few tall tiles on all SMs instead of
     // many short ones: the bytes every SM pulls through L2 per output drop by ~40 % (the mid-M shapes are bound by L2 -> SM
     // traffic, not by HBM or the tensor pipe). DGB200_PSPLIT = 0 / 2 / 4 pins it, DGB200_PSPLIT_BM the tile height.
-    if (!c.csplit && pb.type == kDense && !pb.any_mn && c.cluster == 2 && pb.m > 0 && rt().split_k && c.num_splits == 1) {
+    if (!c.csplit && pb.type == kDense && !pb.any_mn && c.cluster == 2 && pb.m > 0 && rt().split_k) {
         const int want = env_int("DGB200_PSPLIT", -1);
         int pick = 0, pick_bm = 0;
         for (int sp : {2, 4}) {
             if (want == 0 || (want > 0 && want != sp) || (want < 0 && pinned)) continue;
             const int unit = 16 * sp, max_bm = (int)kMaxBlockM / unit * unit;
-            int bm = align_up(ceil_div(pb.m, ceil_div(pb.m, max_bm)), unit);
+            // forced: tallest tiles that cover M evenly; heuristic: m-blocks of at most kPairSplitMaxBlockM rows
+            const int cap = want > 0 ? max_bm : std::min(max_bm, kPairSplitMaxBlockM / unit * unit);
+            int bm = align_up(ceil_div(pb.m, ceil_div(pb.m, cap)), unit);
             if (int v = env_int("DGB200_PSPLIT_BM", 0)) bm = v;
             if (bm % unit != 0 || bm > max_bm || num_kb / sp < 2 || ceil_div(num_kb, sp) * (sp - 1) >= num_kb) continue;
             const int tiles = ceil_div(pb.m, bm) * ceil_div(pb.n, 2 * (int)kBlockN);
@@ -337,9 +339,10 @@ Config choose_config(const Problem& pb, int num_sms_override = 0) {
                 pick = sp, pick_bm = bm;
                 break;
             }
-            // heuristic (tools/tune.py mid, B200): one wave of pair-slices, more than one m-block's worth of rows per tile
-            if (kPairSplitMinM > 0 && pb.m >= kPairSplitMinM && pb.m <= kPairSplitMaxM && sp == 2 && tiles * sp * 2 <= c.num_sms && num_kb >= 16)
-                pick = sp, pick_bm = bm;
+            // Measured (tools/tune.py mid, kineto us, ours plain / pair split / reference): 192 x 4096 x 7168 15.2 / 14.0 / 14.6,
+            // 256 x 4096 x 7168 15.9 / 15.0 / 14.3, 256 x 2112 x 7168 14.2 / 12.1 / 11.8 -- it pays while all pair-slices run
+            // as ONE wave and K is long; with more tiles than that (320+ rows at N = 4096, or N = 7168) the plain kernel wins.
+            if (sp == 2 && pb.m > 128 && tiles * sp * 2 <= c.num_sms && num_kb >= 32 && c.num_splits == 1) pick = sp, pick_bm = bm;
             if (pick) break;
         }
         if (pick) {
@@ -354,14 +357,23 @@ Config choose_config(const Problem& pb, int num_sms_override = 0) {
     // Staged TMA-store epilogue: pays when tiles are tall (the direct epilogue stores 64 B per instruction and keeps the
     // epilogue warps busy until the last row has left); small tiles keep all of shared memory for the TMA -> MMA ring.
     // DGB200_TMA_STORE = 0 / 1 pins the choice (development).
+    auto max_stages = [&](int store_bytes) {
+        int st = (kSmemCapacity - 64 - store_bytes - (staging ? 32 + staging : 0)) / stage_bytes(c.block_m, cta_group);
+        while (st > 1 && smem_bytes_for(c.block_m, cta_group, st, staging) + store_bytes > kSmemCapacity) --st;
+        return st;
+    };
     c.tma_store = 0;
     if (pb.tma_store_ok && c.cluster == 2 && !c.csplit && c.num_splits == 1) {
+        // Measured (tools/tune.py store): the staged epilogue wins 1-4 % on tall tiles with a long enough K loop to hide it
+        // behind (4096 x 4096 x 7168, 4096 x 7168 x 2048, 4096 x 24576 x 1536 at 240 rows); it loses when it costs a pipeline
+        // stage, on short tiles, and when the kernel is epilogue-bound (K = 512: 8 warps of direct stores move more bytes per
+        // cycle than one TMA issuer).
         const int want = env_int("DGB200_TMA_STORE", -1);
-        c.tma_store = want >= 0 ? (want != 0) : (c.block_m >= kTmaStoreMinBlockM);
+        c.tma_store = want >= 0 ? (want != 0)
+                                : (c.block_m >= kTmaStoreMinBlockM && num_kb >= 12 && max_stages((int)kStoreStagingBytes) == max_stages(0));
     }
     const int store_bytes = c.tma_store ? (int)kStoreStagingBytes : 0;
-    int stages = (kSmemCapacity - 64 - store_bytes - (staging ? 32 + staging : 0)) / stage_bytes(c.block_m, cta_group);
-    while (stages > 1 && smem_bytes_for(c.block_m, cta_group, stages, staging) + store_bytes > kSmemCapacity) --stages;
+    int stages = max_stages(store_bytes);
     stages = std::min(stages, 32);
     if (int v = env_int("DGB200_STAGES", 0)) stages = std::min(v, stages);
     c.stages = std::max(stages, 1);

@@ -58,7 +58,7 @@ constexpr uint32_t kNumEpilogueThreads = 256;   // two warps per TMEM lane quadr
 constexpr uint32_t kWTileBytes = kBlockN * kBlockK;  // 16 KB
 constexpr uint32_t kStoreRows = 16;                  // output rows per TMA store (one staging buffer = 16 rows x 128 columns bf16)
 constexpr uint32_t kStoreBufBytes = kStoreRows * kBlockN * 2;       // 4 KB: two 128B-swizzled boxes of 16 rows x 64 columns
-constexpr uint32_t kStoreStagingBytes = 4 * kStoreBufBytes;         // two 4-warp groups x two buffers
+constexpr uint32_t kStoreStagingBytes = 2 * kStoreBufBytes;         // two buffers, shared by the eight epilogue warps
 
 struct GemmParams {
     void* d;                    // output (bf16 or fp32), row stride ld_d elements
@@ -413,7 +413,7 @@ __device__ __forceinline__ void splitk_finalize(const float* ws, size_t slice_el
 // instead of once per m-block and nothing goes through global memory. One tile per cluster (the host guarantees it).
 // kTmaStore: BF16 output tiles leave through shared memory: TMEM -> registers (16x256b fragments) -> BF16 pairs ->
 // `stmatrix.trans` into a 128B-swizzled staging box -> `cp.async.bulk.tensor` store, 16 output rows at a time, two
-// staging buffers per 4-warp group (replaces the reference's epilogue/sm100_store_cd_swap_ab.cuh:22-128). The stores
+// 4 KB staging buffers (replaces the reference's epilogue/sm100_store_cd_swap_ab.cuh:22-128). The stores
 // are asynchronous, so the epilogue warps are done with a tile once its accumulator has been read; rows / columns past
 // the end of D are clipped by the tensor map. Used for tall tiles (dense, contiguous); the direct-store epilogue stays
 // for small tiles (all shared memory feeds the ring) and for layouts that need exact row predication (masked, psum).
@@ -450,7 +450,7 @@ fp8_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
     const uint32_t slot_stride = slot_bytes(p.block_m, kCtaGroup);
     static_assert(!kTmaStore || (std::is_same_v<out_t, __nv_bfloat16> && !kAccumulate && !kSplitK && !kCSplit && kCluster == 2),
                   "the TMA-store epilogue is built for plain BF16 output tiles of a CTA pair");
-    const uint32_t staging = smem_u32(smem);                               // kTmaStore: 2 groups x 2 buffers x 4 KB
+    const uint32_t staging = smem_u32(smem);                               // kTmaStore: 2 buffers x 4 KB
     const uint32_t smem_base = staging + (kTmaStore ? kStoreStagingBytes : 0u);   // the TMA -> MMA ring starts here
     const uint32_t off_x = kWTileBytes, off_sfw = off_x + x_tile_bytes, off_sfx = off_sfw + 512;
     const uint32_t bars = smem_base + num_stages * slot_stride;
@@ -479,6 +479,26 @@ fp8_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
     // (Without a cluster there is no cluster barrier to carry warp 0's mbarrier initialisation to the other warps, so a
     // single-CTA launch takes the plain __syncthreads() prologue.)
     constexpr bool kEarlyProducer = kPairs == 1 && kCluster > 1;
+    if constexpr (kCSplit != 0) {
+        // One tile per cluster, known from the block index alone: the otherwise idle warp 3 asks L2 for this CTA's first
+        // weight / token / scale tiles as its very first instructions. A cold launch (page walks, DRAM row opens) then has
+        // ~1000 cycles of head start on the producer's first TMA load, which has to wait for the barrier setup.
+        if (warp_idx == 3 && elect_one()) {
+            const uint32_t n0 = ((blockIdx.x / kCluster) * kCtaGroup + (cta_rank & 1)) * kBlockN;
+            const uint32_t kb0 = split_rank * p.kb_per_split;
+            const uint32_t x_row0 = blockIdx.y * p.block_m + (cta_rank & 1) * (p.block_m / kCtaGroup);
+            prefetch_tensormap(&map_w);
+            prefetch_tensormap(&map_x);
+            tma_prefetch_2d(&map_w, kb0 * kBlockK, n0);
+            tma_prefetch_2d(&map_x, kb0 * kBlockK, x_row0);
+            tma_prefetch_2d(&map_sfw, n0, kb0 >> p.sf_shift_w);
+            tma_prefetch_2d(&map_sfx, blockIdx.y * p.block_m, kb0 >> p.sf_shift_x);
+            const uint32_t kb_last = (p.k + kBlockK - 1) / kBlockK - 1;
+#pragma unroll
+            for (uint32_t j = 1; j < 4; ++j)
+                if (kb0 + j <= kb_last) tma_prefetch_2d(&map_w, (kb0 + j) * kBlockK, n0);
+        }
+    }
     bool producer_lane = false;
     if (warp_idx == 0) {
         for (uint32_t i = lane; i < num_stages; i += 32) {
@@ -522,6 +542,9 @@ fp8_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
 
     // Programmatic dependent launch: everything above overlaps the previous kernel's tail. A launch that synchronises
     // with its producer through the per-group arrival counters (EP dispatch still in flight) must not wait for it.
+    // (The next kernel of a programmatically chained stream may start ITS prologue -- barrier setup, TMEM allocation, the
+    // L2 prefetch of its weights -- as soon as every CTA of this grid has got here; it still waits for our results.)
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (p.arrival == nullptr) asm volatile("griddepcontrol.wait;" ::: "memory");
     if (threadIdx.x == 0) DGB_STAMP(1);
 
@@ -947,41 +970,37 @@ fp8_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
             };
             if constexpr (kTmaStore) {
                 // ---------------------------------------------------------------- staged TMA-store epilogue
-                // Work unit = 16 token rows x this CTA's 128 weight rows. The two warps of a lane quadrant belong to two
-                // independent 4-warp groups that take alternate units; each group owns two 4 KB staging buffers.
+                // Work unit = 16 token rows x this CTA's 128 weight rows = one 4 KB staging buffer (two 128B-swizzled boxes of
+                // 16 rows x 64 columns). All eight warps work on a unit: the two warps of a lane quadrant take its upper /
+                // lower 8 token rows.
                 //   tcgen05.ld 16x256b: thread t gets (TMEM lane t/4 (+8), columns 2(t%4), +1) = the stmatrix fragment, so
                 //   one stmatrix.x4.trans writes 8 token rows x 32 weight columns as 16-byte pieces into the swizzled box.
                 const uint32_t num_units = load_cols / kStoreRows;
-                const uint32_t group_bar = 3 + half;
-                const uint32_t bufs = staging + half * (2 * kStoreBufBytes);
                 const uint32_t frag_row = lane & 7, frag_piece = (quad & 1) * 4 + (lane >> 3);
-                const uint32_t frag_off = (quad >> 1) * (kStoreBufBytes / 2) + frag_row * 128 + ((frag_piece ^ frag_row) << 4);
-                if (half >= num_units) release_accumulator();     // nothing to read for this warp
-                for (uint32_t u = half; u < num_units; u += 2, ++store_iter) {
-                    const uint32_t buf = bufs + (store_iter & 1) * kStoreBufBytes;
-                    if (quad == 0) tma_store_wait_read<1>();       // the store that last used this buffer has read it out
-                    named_bar_sync(group_bar, 128);
-                    uint32_t v[16];
-                    const uint32_t ta = taddr + u * kStoreRows;
+                const uint32_t frag_off = (quad >> 1) * (kStoreBufBytes / 2) + (half * 8 + frag_row) * 128 + ((frag_piece ^ frag_row) << 4);
+                const bool issuer_warp = warp_idx == 4;
+                for (uint32_t u = 0; u < num_units; ++u, ++store_iter) {
+                    const uint32_t buf = staging + (store_iter & 1) * kStoreBufBytes;
+                    if (issuer_warp) tma_store_wait_read<1>();     // the store that last used this buffer has read it out
+                    named_bar_sync(3, kNumEpilogueThreads);
+                    uint32_t v[8];
+                    const uint32_t ta = taddr + u * kStoreRows + half * 8;
                     tmem_ld_16x256b(ta, &v[0]);
                     tmem_ld_16x256b(ta + (16u << 16), &v[4]);
-                    tmem_ld_16x256b(ta + 8, &v[8]);
-                    tmem_ld_16x256b(ta + 8 + (16u << 16), &v[12]);
                     tmem_ld_wait();
-                    if (u + 2 >= num_units) release_accumulator();
+                    if (u + 1 == num_units) release_accumulator();
                     stmatrix_x4_trans(buf + frag_off, pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]),
                                       pack_bf16x2(v[6], v[7]));
-                    stmatrix_x4_trans(buf + frag_off + 8 * 128, pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]),
-                                      pack_bf16x2(v[12], v[13]), pack_bf16x2(v[14], v[15]));
                     fence_proxy_async_smem();                      // generic writes -> visible to the TMA engine
-                    named_bar_sync(group_bar, 128);
-                    if (quad == 0 && lane == 0) {
+                    named_bar_sync(3, kNumEpilogueThreads);
+                    if (issuer_warp && lane == 0) {
                         const uint32_t row = t.d_row + u * kStoreRows;
                         if (t.n0 < p.n) tma_store_2d(&map_d, buf, t.n0, row);
                         if (t.n0 + 64 < p.n) tma_store_2d(&map_d, buf + kStoreBufBytes / 2, t.n0 + 64, row);
                         tma_store_commit();
                     }
                 }
+                if (num_units == 0) release_accumulator();
                 continue;
             }
             if (half * 32 >= load_cols) release_accumulator();   // nothing to read for this warp
@@ -1020,7 +1039,7 @@ fp8_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
                     store_out<out_t>(reinterpret_cast<out_t*>(d_col + r * row_bytes), 0.0f, false);
         }
         if constexpr (kTmaStore) {
-            if (quad == 0) tma_store_wait_all();               // the staging buffers must outlive every store that reads them
+            if (warp_idx == 4) tma_store_wait_all();           // the staging buffers must outlive every store that reads them
         }
     }
 

@@ -145,6 +145,13 @@ DGB_DEVICE void tma_load_2d(const CUtensorMap* map, uint32_t bar, uint32_t smem_
         : "memory");
 }
 
+// Ask L2 for one box of a tiled tensor (no shared-memory destination, no completion: a hint)
+DGB_DEVICE void tma_prefetch_2d(const CUtensorMap* map, uint32_t c0, uint32_t c1) {
+    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(reinterpret_cast<uint64_t>(map)), "r"(c0),
+                 "r"(c1)
+                 : "memory");
+}
+
 // 3-D tiled load (batched GEMM: coordinate 2 = batch, box depth 1)
 DGB_DEVICE void tma_load_3d(const CUtensorMap* map, uint32_t bar, uint32_t smem_dst, uint32_t c0, uint32_t c1, uint32_t c2,
                             uint64_t hint) {

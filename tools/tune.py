@@ -58,14 +58,18 @@ if __name__ == '__main__':
         run([(4096, 7168, 2048), (4096, 4096, 7168)], cfgs)
     elif mode == 'store':
         # staged TMA-store epilogue on / off at the heuristics' own tile choice and at pinned heights
-        cfgs = [dict(tma_store=0), dict(tma_store=1)] + [dict(tma_store=ts, block_m=bm) for bm in (128, 192, 224, 240) for ts in (0, 1)]
+        cfgs = [{}, dict(tma_store=0), dict(tma_store=1)] + [dict(tma_store=ts, block_m=bm) for bm in (192, 208, 240) for ts in (0, 1)]
         run([(4096, 4096, 7168), (4096, 7168, 2048), (512, 4096, 7168), (512, 7168, 2048), (1024, 4096, 7168), (4096, 2112, 7168),
-             (4096, 24576, 1536), (4096, 32768, 512)], cfgs)
+             (4096, 24576, 1536), (4096, 32768, 512), (4096, 7168, 16384)], cfgs)
     elif mode == 'mid':
         cfgs = [{}] + [dict(block_m=bm, csplit=0) for bm in (64, 96, 128, 192)]
         cfgs += [dict(psplit=2, psplit_bm=bm, csplit=0) for bm in (96, 128, 160, 192, 224)] + [dict(psplit=4, psplit_bm=bm, csplit=0) for bm in (128, 192)]
         run([(192, 4096, 7168), (256, 4096, 7168), (320, 4096, 7168), (384, 4096, 7168), (448, 4096, 7168), (512, 4096, 7168),
              (256, 7168, 2048), (512, 7168, 2048), (256, 2112, 7168), (384, 7168, 16384)], cfgs)
+    elif mode == 'mid2':
+        cfgs = [{}, dict(psplit=0)] + [dict(psplit=2, psplit_bm=bm, csplit=0) for bm in (64, 96, 128)]
+        run([(160, 4096, 7168), (192, 4096, 7168), (224, 4096, 7168), (256, 4096, 7168), (320, 4096, 7168), (256, 2112, 7168), (384, 2112, 7168),
+             (192, 7168, 16384), (256, 576, 7168), (256, 7168, 2048)], cfgs)
     elif mode == 'small':
         cfgs = [{}, dict(csplit=0), dict(csplit=4), dict(csplit=2)] + [dict(csplit=0, block_m=bm) for bm in (16, 32, 64)]
         run([(1, 2112, 7168), (16, 4096, 7168), (32, 4096, 7168), (64, 4096, 7168), (96, 4096, 7168), (128, 4096, 7168), (192, 4096, 7168),
