@@ -329,9 +329,18 @@ Config choose_config(const Problem& pb, int num_sms_override = 0) {
         for (int sp : {2, 4}) {
             if (want == 0 || (want > 0 && want != sp) || (want < 0 && pinned)) continue;
             const int unit = 16 * sp, max_bm = (int)kMaxBlockM / unit * unit;
-            // forced: tallest tiles that cover M evenly; heuristic: m-blocks of at most kPairSplitMaxBlockM rows
+            // forced: tallest tiles that cover M evenly. Heuristic: the SHORTEST tiles (>= 64 rows, <= kPairSplitMaxBlockM) whose
+            // clusters of 4 all run at once -- 8 GPCs x 4 clusters on a 148-SM part -- since more CTAs stream more bytes at a
+            // time (256 x 2112 x 7168: 96-row tiles 11.9 us, 128-row 12.8; 64-row tiles = 36 clusters, a second wave: 18.8).
+            const int max_clusters = c.num_sms * 7 / 32;
             const int cap = want > 0 ? max_bm : std::min(max_bm, kPairSplitMaxBlockM / unit * unit);
             int bm = align_up(ceil_div(pb.m, ceil_div(pb.m, cap)), unit);
+            if (want <= 0)
+                for (int cand = 64; cand <= cap; cand += unit)
+                    if (ceil_div(pb.m, cand) * ceil_div(pb.n, 2 * (int)kBlockN) <= max_clusters) {
+                        bm = cand;
+                        break;
+                    }
             if (int v = env_int("DGB200_PSPLIT_BM", 0)) bm = v;
             if (bm % unit != 0 || bm > max_bm || num_kb / sp < 2 || ceil_div(num_kb, sp) * (sp - 1) >= num_kb) continue;
             const int tiles = ceil_div(pb.m, bm) * ceil_div(pb.n, 2 * (int)kBlockN);
@@ -342,7 +351,7 @@ Config choose_config(const Problem& pb, int num_sms_override = 0) {
             // Measured (tools/tune.py mid, kineto us, ours plain / pair split / reference): 192 x 4096 x 7168 15.2 / 14.0 / 14.6,
             // 256 x 4096 x 7168 15.9 / 15.0 / 14.3, 256 x 2112 x 7168 14.2 / 12.1 / 11.8 -- it pays while all pair-slices run
             // as ONE wave and K is long; with more tiles than that (320+ rows at N = 4096, or N = 7168) the plain kernel wins.
-            if (sp == 2 && pb.m > 128 && tiles * sp * 2 <= c.num_sms && num_kb >= 32 && c.num_splits == 1) pick = sp, pick_bm = bm;
+            if (sp == 2 && pb.m > 128 && bm >= 64 && tiles <= max_clusters && num_kb >= 32 && c.num_splits == 1) pick = sp, pick_bm = bm;
             if (pick) break;
         }
         if (pick) {

@@ -25,7 +25,7 @@ def _require(cond: bool, what: str) -> None:
 
 
 def _stream() -> int:
-    return torch.cuda.current_stream().cuda_stream
+    return torch._C._cuda_getCurrentRawStream(torch.cuda.current_device())
 
 
 # Split-K scratch (include/dgb200.h, `workspace`): one zero-initialised buffer per (device, stream), so GEMMs that may
@@ -48,22 +48,22 @@ def _workspace(m: int, n: int, device: torch.device, stream: int):
     return ws.data_ptr(), ws.numel()
 
 
-def _major_check(t: torch.Tensor) -> None:
-    """csrc/utils/layout.hpp:13-19."""
-    _require(t.dim() in (2, 3), 'dim == 2 or dim == 3')
-    if t.dim() == 3:
-        _require(t.stride(0) == t.size(-2) * t.size(-1), 't.stride(0) == t.size(-2) * t.size(-1)')
-    _require(t.stride(-2) == 1 or t.stride(-1) == 1, 't.stride(-2) == 1 or t.stride(-1) == 1')
+def _major_check(t: torch.Tensor) -> int:
+    """csrc/utils/layout.hpp:13-19; returns the major of the checked tensor."""
+    shape, stride = t.shape, t.stride()
+    _require(len(shape) in (2, 3), 'dim == 2 or dim == 3')
+    if len(shape) == 3:
+        _require(stride[0] == shape[-2] * shape[-1], 't.stride(0) == t.size(-2) * t.size(-1)')
+    _require(stride[-2] == 1 or stride[-1] == 1, 't.stride(-2) == 1 or t.stride(-1) == 1')
+    return _K_MAJOR if stride[-1] == 1 else _MN_MAJOR
 
 
 def _major_ab(t: torch.Tensor) -> int:
-    _major_check(t)
-    return _K_MAJOR if t.stride(-1) == 1 else _MN_MAJOR
+    return _major_check(t)
 
 
 def _check_cd(t: torch.Tensor) -> None:
-    _major_check(t)
-    _require(t.stride(-1) == 1, 'C/D must be row-major (stride(-1) == 1)')
+    _require(_major_check(t) == _K_MAJOR, 'C/D must be row-major (stride(-1) == 1)')
 
 
 def _check_fp8(t: torch.Tensor) -> None:
@@ -107,24 +107,29 @@ def fp8_gemm_nt(a: TensorPair, b: TensorPair, d: torch.Tensor, c: Optional[torch
     Reference: fp8_fp4_gemm_nt, csrc/apis/gemm.hpp:73-124. `compiled_dims` is a JIT hint there; ignored here."""
     (a_t, sfa), (b_t, sfb) = a, b
     _check_fp8(a_t), _check_fp8(b_t)
-    major_a, major_b = _major_ab(a_t), _major_ab(b_t)
-    _check_cd(d)
-    _require(a_t.dim() == 2 and b_t.dim() == 2 and d.dim() == 2, 'a, b, d are 2-D')
-    (m, k), (n, k_), (m_, n_) = a_t.shape, b_t.shape, d.shape
+    sha, shb, shd = a_t.shape, b_t.shape, d.shape
+    _require(len(sha) == 2 and len(shb) == 2 and len(shd) == 2, 'a, b, d are 2-D')
+    sta, stb, std = a_t.stride(), b_t.stride(), d.stride()
+    _require(sta[0] == 1 or sta[1] == 1, 't.stride(-2) == 1 or t.stride(-1) == 1')
+    _require(stb[0] == 1 or stb[1] == 1, 't.stride(-2) == 1 or t.stride(-1) == 1')
+    _require(std[1] == 1, 'C/D must be row-major (stride(-1) == 1)')
+    major_a = _K_MAJOR if sta[1] == 1 else _MN_MAJOR
+    major_b = _K_MAJOR if stb[1] == 1 else _MN_MAJOR
+    (m, k), (n, k_), (m_, n_) = sha, shb, shd
     _require(m == m_ and n == n_ and k == k_, 'm == m_ and n == n_ and k == k_')
-    _d_dtype(d)
+    d_dtype = _d_dtype(d)
     if _early_return(m, n, k, d, c):
         return
     sfa_t, sfb_t, gran_k_a, gran_k_b = _layout.transform_sf_pair_into_required_layout(
         sfa, sfb, m, n, k, recipe, recipe_a, recipe_b, None, None, disable_ue8m0_cast)
     _require(sfa_t.dtype == torch.int32 and sfb_t.dtype == torch.int32, 'Unsupported architecture or scaling factor types')
-    lda = a_t.stride(0) if major_a == _K_MAJOR else a_t.stride(1)
-    ldb = b_t.stride(0) if major_b == _K_MAJOR else b_t.stride(1)
+    lda = sta[0] if major_a == _K_MAJOR else sta[1]
+    ldb = stb[0] if major_b == _K_MAJOR else stb[1]
     stream = _stream()
     ws_ptr, ws_bytes = _workspace(m, n, d.device, stream)
     check(lib().dgb200_fp8_gemm_nt(a_t.data_ptr(), sfa_t.data_ptr(), b_t.data_ptr(), sfb_t.data_ptr(), d.data_ptr(),
-                                   m, n, k, lda, ldb, d.stride(0), major_a, major_b,
-                                   sfa_t.stride(-1), sfb_t.stride(-1), gran_k_a, gran_k_b, _d_dtype(d),
+                                   m, n, k, lda, ldb, std[0], major_a, major_b,
+                                   sfa_t.stride(-1), sfb_t.stride(-1), gran_k_a, gran_k_b, d_dtype,
                                    int(c is not None), ws_ptr, ws_bytes, stream))
 
 

@@ -126,21 +126,23 @@ def transform_k_grouped_sf_into_required_layout(sf, ks_cpu, grouped_layout, reci
 
 def check_sf_layout(sf: torch.Tensor, mn: int, k: int, gran_mn: int, gran_k: int, num_groups: Optional[int],
                     tma_stride_check: bool = False, type_check: Optional[torch.dtype] = None) -> torch.Tensor:
-    """csrc/utils/layout.hpp:80-117."""
+    """csrc/utils/layout.hpp:80-117. (Shape and strides are read once: this sits on the per-call path of every GEMM.)"""
+    dtype = sf.dtype
     if type_check is not None:
-        _require(sf.dtype == type_check, f'sf.dtype == {type_check}')
-    _require(sf.dtype in (torch.float32, torch.int32), 'sf must be float or int')
-    _require(sf.dim() == (3 if num_groups is not None else 2), 'sf.dim() == num_groups.has_value() + 2')
+        _require(dtype == type_check, f'sf.dtype == {type_check}')
+    is_float = dtype == torch.float32
+    _require(is_float or dtype == torch.int32, 'sf must be float or int')
+    shape, stride = sf.shape, sf.stride()
+    _require(len(shape) == (3 if num_groups is not None else 2), 'sf.dim() == num_groups.has_value() + 2')
     if num_groups is not None:
-        _require(sf.size(-3) == num_groups, 'sf.size(-3) == num_groups')
-    _require(sf.size(-2) == _ceil_div(mn, gran_mn), 'sf.size(-2) == ceil_div(mn, gran_mn)')
-    _require(sf.size(-1) == _ceil_div(k, gran_k * (1 if sf.dtype == torch.float32 else 4)),
-             'sf.size(-1) == ceil_div(k, gran_k * (1 or 4))')
+        _require(shape[-3] == num_groups, 'sf.size(-3) == num_groups')
+    _require(shape[-2] == -(-mn // gran_mn), 'sf.size(-2) == ceil_div(mn, gran_mn)')
+    _require(shape[-1] == -(-k // (gran_k * (1 if is_float else 4))), 'sf.size(-1) == ceil_div(k, gran_k * (1 or 4))')
     if tma_stride_check:
         if num_groups is not None:
-            _require(sf.stride(-3) == sf.stride(-1) * sf.size(-1), 'sf.stride(-3) == sf.stride(-1) * sf.size(-1)')
-        _require(sf.stride(-2) == 1 or mn == 1, 'sf must be MN-major')
-        _require(sf.stride(-1) == get_tma_aligned_size(mn, sf.element_size()), 'sf.stride(-1) == tma_aligned(mn)')
+            _require(stride[-3] == stride[-1] * shape[-1], 'sf.stride(-3) == sf.stride(-1) * sf.size(-1)')
+        _require(stride[-2] == 1 or mn == 1, 'sf must be MN-major')
+        _require(stride[-1] == -(-mn // 4) * 4, 'sf.stride(-1) == tma_aligned(mn)')       # 4-byte elements: align(mn, 16 / 4)
     return sf
 
 
@@ -159,15 +161,15 @@ def transform_sf_into_required_layout(sf: torch.Tensor, mn: int, k: int, recipe:
     else:
         _require(len(recipe) == 2 and is_sfa is None, 'invalid recipe')
         gran_mn, gran_k = recipe
+    if sf.dtype == torch.int32 and gran_mn == 1 and gran_k in (32, 128):
+        # pre-packed scale factors (the per-call path of an inference loop): one pass of checks, no kernel
+        return check_sf_layout(sf, mn, k, gran_mn, gran_k, num_groups, tma_stride_check=True, type_check=torch.int32)
     check_sf_layout(sf, mn, k, gran_mn, gran_k, num_groups)
-
     if sf.dtype == torch.float32 and gran_k in (32, 128):
         # The SM100 kernel needs power-of-two scales (hardware block scaling); the reference asserts the same
         # (layout.hpp:49-50) and leaves `disable_ue8m0_cast=True` without an SM100 kernel (gemm.hpp:118-122).
         _require(not disable_ue8m0_cast, 'not disable_ue8m0_cast (FP32 scale factors are cast to UE8M0 on SM100)')
         return _pack(sf, mn, gran_mn, psum_layout)
-    if sf.dtype == torch.int32 and gran_mn == 1 and gran_k in (32, 128):
-        return check_sf_layout(sf, mn, k, gran_mn, gran_k, num_groups, tma_stride_check=True, type_check=torch.int32)
     raise RuntimeError('Unknown SF transformation')
 
 

@@ -45,6 +45,9 @@ dense(600, 768, 1024, {'DGB200_CLUSTER': '4', 'DGB200_SPLITS': '1'})   # weight-
 dense(256, 384, 512, majors='mm', fp32=True, c=True)                    # MN-major operands (wgrad form)
 dense(200, 256, 512, {'DGB200_CLUSTER': '1', 'DGB200_SPLITS': '1'})    # single-CTA MMA, plain prologue
 
+for kk in KNOBS:
+    os.environ.pop(kk, None)
+
 # skip_head_mid, bmm / einsum, quantiser
 a = torch.randn((77, 384), device='cuda', dtype=torch.bfloat16)
 b = torch.randn((768, 384), device='cuda', dtype=torch.bfloat16)
