@@ -62,7 +62,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
 class _Config(ctypes.Structure):
     _fields_ = [(n, ctypes.c_int) for n in ('block_m', 'cluster', 'num_stages', 'num_sms', 'smem_bytes', 'num_tiles',
-                                            'num_splits', 'cluster_split', 'tma_store')]
+                                            'num_splits', 'cluster_split', 'tma_store', 'swap_ab')]
 
 
 _P, _I, _L = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64

@@ -32,7 +32,7 @@ namespace {
 
 // ------------------------------------------------------------------------------------------------ errors
 thread_local std::string g_last_error;
-thread_local dgb200_config g_last_config = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+thread_local dgb200_config g_last_config = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
 std::atomic<int64_t> g_launch_count{0};
 std::atomic<long long*> g_debug_ts{nullptr};
 
@@ -163,6 +163,7 @@ struct Problem {
     bool x_mn = false;   // MN-major tokens: the token tile is loaded in 32/64/128-row swizzle atoms
     bool any_mn = false; // any MN-major operand: no weight multicast
     bool tma_store_ok = false;   // the output may leave through the staged TMA-store epilogue (plain BF16 tiles)
+    bool swapped = false;        // transposed-output orientation: `m` is the weight count (tiled freely), `n` the token count (lanes)
 };
 int stage_bytes(int block_m, int cluster) { return static_cast<int>(slot_bytes(block_m, cluster)); }
 int smem_bytes_for(int block_m, int cluster, int stages, int staging_bytes = 0) {
@@ -219,7 +220,9 @@ Config choose_config(const Problem& pb, int num_sms_override = 0) {
     Config c{};
     c.num_sms = num_sms_override > 0 ? (num_sms_override & ~1) : effective_num_sms();
     c.cluster = c.num_sms >= 2 ? 2 : 1;
+    if (pb.swapped && pb.n <= (int)kBlockN) c.cluster = 1;    // up to 128 token rows fit the lanes of one CTA: no pair needed
     if (int v = env_int("DGB200_CLUSTER", 0)) c.cluster = v;
+    c.swap_d = pb.swapped;
     std::vector<int> candidates;
     if (pb.type == kDense || pb.type == kMMasked || pb.type == kKGrouped || pb.type == kKGroupedPsum || pb.type == kBatched) {
         const int step = pb.x_mn ? 32 * std::min(c.cluster, 2) : 16;   // MN-major tokens: load_m is a multiple of 32
@@ -263,7 +266,7 @@ Config choose_config(const Problem& pb, int num_sms_override = 0) {
     // the simulated makespan of the round-robin schedule, and make the blocks as even as multiples of 16 allow (two
     // heights, the taller ones first).
     c.num_tall = 0, c.block_m_low = 0;
-    if (pb.type == kDense && !pb.x_mn && c.num_splits == 1 && c.cluster == 2 && pb.m >= 1024 && c.block_m >= 160 &&
+    if (pb.type == kDense && !pb.swapped && !pb.x_mn && c.num_splits == 1 && c.cluster == 2 && pb.m >= 1024 && c.block_m >= 160 &&
         !getenv("DGB200_BLOCK_M") && env_int("DGB200_BALANCE", 1)) {
         const int units = c.num_sms / 2, n_units = ceil_div(pb.n, (int)kBlockN * 2);
         const double overhead_rows = kTileOverhead / (2.0 * num_kb);      // per-tile fixed cost in units of token rows
@@ -295,7 +298,7 @@ Config choose_config(const Problem& pb, int num_sms_override = 0) {
     c.csplit = 0, c.grid = 0, c.grid_y = 1;
     const char* splits_env = getenv("DGB200_SPLITS");
     const bool pinned = getenv("DGB200_BLOCK_M") || getenv("DGB200_CLUSTER") || (splits_env && atoi(splits_env) <= 1);
-    if (pb.type == kDense && !pb.any_mn && c.cluster == 2 && pb.m > 0 && rt().split_k && !(pinned && !getenv("DGB200_CSPLIT"))) {
+    if (pb.type == kDense && !pb.swapped && !pb.any_mn && c.cluster == 2 && pb.m > 0 && rt().split_k && !(pinned && !getenv("DGB200_CSPLIT"))) {
         const int want = env_int("DGB200_CSPLIT", -1);            // -1: heuristic, 0: off, 2/4: forced
         int pick = 0, pick_bm = 0;
         for (int sp : {4, 2}) {
@@ -323,7 +326,7 @@ Config choose_config(const Problem& pb, int num_sms_override = 0) {
     // rows x block_m tokens of HALF (a quarter) of K, so a 192..480-row problem runs as few tall tiles on all SMs instead of
     // many short ones: the bytes every SM pulls through L2 per output drop by ~40 % (the mid-M shapes are bound by L2 -> SM
     // traffic, not by HBM or the tensor pipe). DGB200_PSPLIT = 0 / 2 / 4 pins it, DGB200_PSPLIT_BM the tile height.
-    if (!c.csplit && pb.type == kDense && !pb.any_mn && c.cluster == 2 && pb.m > 0 && rt().split_k) {
+    if (!c.csplit && pb.type == kDense && !pb.swapped && !pb.any_mn && c.cluster == 2 && pb.m > 0 && rt().split_k) {
         const int want = env_int("DGB200_PSPLIT", -1);
         int pick = 0, pick_bm = 0;
         for (int sp : {2, 4}) {
@@ -391,6 +394,14 @@ Config choose_config(const Problem& pb, int num_sms_override = 0) {
     return c;
 }
 
+// Which orientation for a dense K-major problem? DGB200_SWAP = 0 / 1 pins it (development).
+bool want_swapped_orientation(int m, int n, int k) {
+    const int want = env_int("DGB200_SWAP", -1);
+    if (want >= 0) return want != 0;
+    (void)m, (void)n, (void)k;
+    return false;
+}
+
 // ------------------------------------------------------------------------------------------------ launch
 int run_gemm(const GemmCall& c) {
     if (int e = ensure_device()) return e;
@@ -406,12 +417,13 @@ int run_gemm(const GemmCall& c) {
     const bool head_split = c.head_mid > 0;
     Problem pb{c.type, c.m, c.expected_m, c.n, c.k, c.groups, c.alignment};
     pb.x_mn = c.x_mn, pb.any_mn = c.x_mn || c.w_mn;
+    pb.swapped = c.swap_d;
     // TMA stores need a 16-byte aligned base and row pitch; tiles that must not touch rows past `valid_m` (masked, psum),
     // accumulate into C or remap columns keep the predicated direct stores
-    pb.tma_store_ok = (c.type == kDense || c.type == kMContiguous) && c.d_dtype == DGB200_BF16 && !c.accumulate && !head_split &&
+    pb.tma_store_ok = (c.type == kDense || c.type == kMContiguous) && !c.swap_d && c.d_dtype == DGB200_BF16 && !c.accumulate && !head_split &&
                       (reinterpret_cast<uintptr_t>(c.d) & 15) == 0 && (c.ldd * 2) % 16 == 0 && c.arrival == nullptr;
     // split-K needs scratch: [4096 arrival counters][num_splits x m x n fp32 partial tiles]
-    if (c.type == kDense && !head_split && c.workspace != nullptr && c.n % 4 == 0 && c.workspace_bytes > kSplitKHeaderBytes &&
+    if (c.type == kDense && !head_split && !c.swap_d && c.workspace != nullptr && c.n % 4 == 0 && c.workspace_bytes > kSplitKHeaderBytes &&
         (reinterpret_cast<uintptr_t>(c.workspace) & 15) == 0) {
         const size_t per_split = static_cast<size_t>(c.m) * c.n * sizeof(float);
         pb.max_splits = static_cast<int>(std::min<size_t>(kMaxSplits, (c.workspace_bytes - kSplitKHeaderBytes) / per_split));
@@ -520,7 +532,7 @@ int run_gemm(const GemmCall& c) {
     p.head_lr = head_split ? c.head_left + c.head_right : 1, p.head_mid = head_split ? c.head_mid : 0, p.head_right = c.head_right;
 
     g_last_config = dgb200_config{cfg.block_m, cfg.cluster, cfg.stages, cfg.num_sms, cfg.smem_bytes, 0, cfg.num_splits, cfg.csplit,
-                                  cfg.tma_store};
+                                  cfg.tma_store, cfg.swap_d};
     if (env_int("DGB200_PRINT_CONFIGS", 0))
         fprintf(stderr, "dgb200 config: type=%d m=%d n=%d k=%d groups=%d majors=%d%d -> block_m=%d cluster=%d stages=%d sms=%d smem=%d splits=%d tma_store=%d\n",
                 c.type, c.m, c.n, c.k, c.groups, (int)c.x_mn, (int)c.w_mn, cfg.block_m, cfg.cluster, cfg.stages, cfg.num_sms,
@@ -528,6 +540,7 @@ int run_gemm(const GemmCall& c) {
 
     switch (c.type) {
         case kDense:
+            if (c.swap_d) return dispatch_dense_swap(c, cfg, maps, p);
             if (cfg.num_splits > 1 && !cfg.csplit) return dispatch_dense_splitk(c, cfg, maps, p);
             return (c.x_mn || c.w_mn) ? dispatch_dense_mn(c, cfg, maps, p) : dispatch_dense_kk(c, cfg, maps, p);
         case kMContiguous: case kMMasked: case kMContiguousPsum: case kKGrouped: case kKGroupedPsum:
@@ -688,6 +701,12 @@ int dgb200_fp8_gemm_nt(const void* a, const int32_t* sfa, const void* b, const i
     c.expected_m = m, c.alignment = 1, c.zero_padding = 0;
     c.workspace = workspace, c.workspace_bytes = workspace_bytes > 0 ? static_cast<size_t>(workspace_bytes) : 0;
     c.stream = static_cast<cudaStream_t>(stream);
+    if (!c.x_mn && !c.w_mn && want_swapped_orientation(m, n, k)) {
+        // second orientation: tokens on the TMEM lanes, weights tiled freely along N (the kernel writes D[lane][column])
+        std::swap(c.a, c.b), std::swap(c.sfa, c.sfb), std::swap(c.m, c.n), std::swap(c.lda, c.ldb);
+        std::swap(c.sfa_stride, c.sfb_stride), std::swap(c.sfa_cols, c.sfb_cols), std::swap(c.gran_k_a, c.gran_k_b);
+        c.a_rows = c.m, c.expected_m = c.m, c.swap_d = true;
+    }
     return run_gemm(c);
 }
 
@@ -942,7 +961,7 @@ int dgb200_plan(int gemm_type, int m, int n, int k, int num_groups, int expected
     if (gemm_type == kDense && cfg.block_m_low > 0)   // two tile heights (wave balancing)
         m_blocks = cfg.num_tall + ceil_div(std::max(0, m - cfg.num_tall * cfg.block_m), cfg.block_m_low);
     *out = dgb200_config{cfg.block_m, cfg.cluster, cfg.stages, cfg.num_sms, cfg.smem_bytes, m_blocks * n_units * cfg.num_splits,
-                         cfg.num_splits, cfg.csplit, cfg.tma_store};
+                         cfg.num_splits, cfg.csplit, cfg.tma_store, cfg.swap_d};
     return DGB200_OK;
 }
 

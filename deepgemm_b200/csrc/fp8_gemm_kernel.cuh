@@ -417,8 +417,14 @@ __device__ __forceinline__ void splitk_finalize(const float* ws, size_t slice_el
 // are asynchronous, so the epilogue warps are done with a tile once its accumulator has been read; rows / columns past
 // the end of D are clipped by the tensor map. Used for tall tiles (dense, contiguous); the direct-store epilogue stays
 // for small tiles (all shared memory feeds the ring) and for layouts that need exact row predication (masked, psum).
+// kSwapD: the second orientation. The host hands the TOKENS to the lane side ("w": 128 rows per CTA) and the WEIGHTS to the
+// column side ("x": block_m rows per tile, any multiple of 16), so TMEM lane = output row, TMEM column = output column, and
+// the epilogue writes D[lane][column]: every thread owns one output row and stores 16 consecutive columns per TMEM load.
+// What it buys is tile-count freedom along N: with few token rows the number of tiles is N / block_m for ANY block_m, so the
+// tiles can be cut to fill exactly one wave of SMs (the reference reaches the same through its non-swap-AB templates,
+// csrc/jit_kernels/heuristics/sm100.hpp:27-92). Dense, K-major operands.
 template <int kGemmType, int kCluster, typename out_t, bool kAccumulate, bool kXMn = false, bool kWMn = false,
-          bool kSplitK = false, int kCSplit = 0, bool kTmaStore = false>
+          bool kSplitK = false, int kCSplit = 0, bool kTmaStore = false, bool kSwapD = false>
 __global__ void __launch_bounds__(kNumThreads, 1)
 fp8_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
                 const __grid_constant__ CUtensorMap map_sfx, const __grid_constant__ CUtensorMap map_sfw,
@@ -450,6 +456,8 @@ fp8_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
     const uint32_t slot_stride = slot_bytes(p.block_m, kCtaGroup);
     static_assert(!kTmaStore || (std::is_same_v<out_t, __nv_bfloat16> && !kAccumulate && !kSplitK && !kCSplit && kCluster == 2),
                   "the TMA-store epilogue is built for plain BF16 output tiles of a CTA pair");
+    static_assert(!kSwapD || (kGemmType == kDense && !kXMn && !kWMn && !kSplitK && !kCSplit && !kTmaStore && kCluster <= 2),
+                  "the transposed-output orientation is built for plain dense K-major problems");
     const uint32_t staging = smem_u32(smem);                               // kTmaStore: 2 buffers x 4 KB
     const uint32_t smem_base = staging + (kTmaStore ? kStoreStagingBytes : 0u);   // the TMA -> MMA ring starts here
     const uint32_t off_x = kWTileBytes, off_sfw = off_x + x_tile_bytes, off_sfx = off_sfw + 512;
@@ -968,6 +976,51 @@ fp8_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
                 else
                     mbar_arrive(tmem_empty_dst + as * 8);
             };
+            if constexpr (kSwapD) {
+                // ---------------------------------------------------------------- transposed-output epilogue
+                // lane = output row (token), TMEM column = output column (weight): 16 consecutive columns per load, written
+                // as 16-byte pieces when D allows it (base and row pitch multiples of 16 bytes; tile origins are multiples of
+                // 16 columns), element by element on ragged edges and when accumulating into C.
+                out_t* d_row = d + static_cast<size_t>(n) * p.ld_d + t.d_row;
+                const bool vec_ok = !kAccumulate && ((reinterpret_cast<uintptr_t>(d) | (static_cast<uintptr_t>(p.ld_d) * sizeof(out_t))) & 15) == 0;
+                if (half * 32 >= load_cols) release_accumulator();
+                for (uint32_t c0 = half * 32; c0 < load_cols; c0 += 64) {
+                    uint32_t v[32];
+                    const bool second = c0 + 16 < load_cols;
+                    tmem_ld_32x32b_x16(taddr + c0, *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
+                    if (second) tmem_ld_32x32b_x16(taddr + c0 + 16, *reinterpret_cast<uint32_t(*)[16]>(&v[16]));
+                    tmem_ld_wait();
+                    if (c0 + 64 >= load_cols) release_accumulator();
+                    if (n_ok) {
+#pragma unroll
+                        for (uint32_t h = 0; h < 2; ++h) {
+                            const uint32_t r0 = c0 + h * 16;
+                            out_t* dst = d_row + r0;
+                            if (r0 + 16 <= t.valid_m && vec_ok) {
+                                if constexpr (std::is_same_v<out_t, __nv_bfloat16>) {
+                                    uint4 lo, hi;
+                                    lo.x = pack_bf16x2(v[h * 16 + 0], v[h * 16 + 1]), lo.y = pack_bf16x2(v[h * 16 + 2], v[h * 16 + 3]);
+                                    lo.z = pack_bf16x2(v[h * 16 + 4], v[h * 16 + 5]), lo.w = pack_bf16x2(v[h * 16 + 6], v[h * 16 + 7]);
+                                    hi.x = pack_bf16x2(v[h * 16 + 8], v[h * 16 + 9]), hi.y = pack_bf16x2(v[h * 16 + 10], v[h * 16 + 11]);
+                                    hi.z = pack_bf16x2(v[h * 16 + 12], v[h * 16 + 13]), hi.w = pack_bf16x2(v[h * 16 + 14], v[h * 16 + 15]);
+                                    reinterpret_cast<uint4*>(dst)[0] = lo;
+                                    reinterpret_cast<uint4*>(dst)[1] = hi;
+                                } else {
+#pragma unroll
+                                    for (uint32_t q4 = 0; q4 < 4; ++q4)
+                                        reinterpret_cast<uint4*>(dst)[q4] = make_uint4(v[h * 16 + 4 * q4], v[h * 16 + 4 * q4 + 1],
+                                                                                       v[h * 16 + 4 * q4 + 2], v[h * 16 + 4 * q4 + 3]);
+                                }
+                            } else if (r0 < t.valid_m) {
+#pragma unroll
+                                for (uint32_t j = 0; j < 16; ++j)
+                                    if (r0 + j < t.valid_m) store_out<out_t>(dst + j, __uint_as_float(v[h * 16 + j]), kAccumulate);
+                            }
+                        }
+                    }
+                }
+                continue;
+            }
             if constexpr (kTmaStore) {
                 // ---------------------------------------------------------------- staged TMA-store epilogue
                 // Work unit = 16 token rows x this CTA's 128 weight rows = one 4 KB staging buffer (two 128B-swizzled boxes of

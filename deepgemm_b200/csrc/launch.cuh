@@ -46,6 +46,7 @@ struct Config {
     int num_tall = 0, block_m_low = 0;   // dense wave balancing: first num_tall m-blocks block_m high, the rest block_m_low
     bool overlap_producer = false;  // launch as a programmatic dependent that does not wait for the preceding kernel
     int tma_store = 0;              // BF16 output staged through shared memory and written with TMA stores
+    int swap_d = 0;                 // transposed-output orientation (tokens on the TMEM lanes)
 };
 
 struct GemmCall {
@@ -72,6 +73,7 @@ struct GemmCall {
     cudaStream_t stream;
     int64_t batch_stride_a = 0, batch_stride_b = 0, batch_stride_d = 0;   // batched (elements)
     int head_left = 0, head_mid = 0, head_right = 0;                     // fp8_gemm_nt_skip_head_mid
+    bool swap_d = false;   // operands already exchanged by the caller (a = weights, b = tokens): the kernel writes D[lane][column]
 };
 
 struct Maps {
@@ -140,5 +142,6 @@ int dispatch_dense_mn(const GemmCall& c, const Config& cfg, const Maps& maps, co
 int dispatch_dense_splitk(const GemmCall& c, const Config& cfg, const Maps& maps, const GemmParams& p);  // gemm_dense_splitk.cu
 int dispatch_grouped(const GemmCall& c, const Config& cfg, const Maps& maps, const GemmParams& p);       // gemm_grouped.cu
 int dispatch_batched(const GemmCall& c, const Config& cfg, const Maps& maps, const GemmParams& p);       // gemm_batched.cu
+int dispatch_dense_swap(const GemmCall& c, const Config& cfg, const Maps& maps, const GemmParams& p);    // gemm_dense_swap.cu
 
 }  // namespace dgb200

@@ -140,6 +140,55 @@ def test_pair_split_k_matches_oracle_and_is_deterministic(dg, m, n, k, slices, b
     assert_close_to_oracle(d, want, 'psplit accumulate', mag=prod.abs() + c.cpu().float().abs())
 
 
+# ------------------------------------------------------------------------------------------------ second orientation
+@pytest.mark.parametrize('m,n,k', [(64, 7168, 2048), (128, 24576, 1536), (100, 520, 768), (300, 1000, 512), (1, 2112, 7168),
+                                   (256, 1001, 384), (64, 32768, 512)])
+@pytest.mark.parametrize('out_dtype', [torch.bfloat16, torch.float32])
+def test_transposed_output_orientation_gives_identical_bits(dg, m, n, k, out_dtype, monkeypatch):
+    """Tokens on the TMEM lanes, weights tiled freely along N (fp8_gemm_kernel<..., kSwapD>): the same products summed over K
+    in the same order, so the bits equal the weights-on-lanes kernel's; ragged N, unaligned row pitches (N = 1001) and C
+    accumulation take the element-wise store path."""
+    from deepgemm_b200 import _lib
+    _, _, qa, qb = _quant_dense(m, n, k, seed=m * 7 + n)
+    monkeypatch.setenv('DGB200_SPLITS', '1')
+    outs = []
+    for swap in ('0', '1'):
+        monkeypatch.setenv('DGB200_SWAP', swap)
+        buf = torch.full((m + 8, n + 24), 333.0, device='cuda', dtype=out_dtype)
+        d = buf[:m, :n]
+        dg.fp8_gemm_nt(qa, qb, d)
+        cfg = _lib.last_config()
+        assert cfg['swap_ab'] == int(swap)
+        if swap == '1':
+            assert cfg['cluster'] == (1 if m <= 128 else 2)
+        assert bool((buf[m:] == 333.0).all()) and bool((buf[:, n:] == 333.0).all()), 'wrote outside D'
+        outs.append(d.clone())
+    assert torch.equal(outs[0], outs[1])
+    c = (torch.randn((m, n), device='cuda') * 16).to(out_dtype)
+    accs = []
+    for swap in ('0', '1'):
+        monkeypatch.setenv('DGB200_SWAP', swap)
+        d = c.clone()
+        dg.fp8_gemm_nt(qa, qb, d, c=d)
+        accs.append(d)
+    assert torch.equal(accs[0], accs[1])
+
+
+@pytest.mark.parametrize('bn', [16, 48, 112, 176, 240])
+def test_transposed_output_every_tile_width(dg, bn, monkeypatch):
+    m, n, k = 120, 2000, 640
+    _, _, qa, qb = _quant_dense(m, n, k, seed=bn)
+    monkeypatch.setenv('DGB200_SPLITS', '1')
+    monkeypatch.setenv('DGB200_SWAP', '0')
+    base = torch.empty((m, n), device='cuda', dtype=torch.bfloat16)
+    dg.fp8_gemm_nt(qa, qb, base)
+    monkeypatch.setenv('DGB200_SWAP', '1')
+    monkeypatch.setenv('DGB200_BLOCK_M', str(bn))
+    d = torch.full_like(base, float('nan'))
+    dg.fp8_gemm_nt(qa, qb, d)
+    assert torch.equal(d, base)
+
+
 # ------------------------------------------------------------------------------------------------ skip_head_mid
 @pytest.mark.parametrize('m,n,k,splits', [(128, 8192, 512, (128, 64, 128)), (4096, 2048, 512, (128, 64, 128)), (77, 768, 384, (64, 32, 128)),
                                           (33, 512, 256, (128, 0, 128))])

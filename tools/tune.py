@@ -12,7 +12,7 @@ from deepgemm_b200 import _lib  # noqa: E402
 from deepgemm_b200.testing import bench_kineto  # noqa: E402
 
 KEYS = ('DGB200_BLOCK_M', 'DGB200_CLUSTER', 'DGB200_STAGES', 'DGB200_SWIZZLE_GROUP', 'DGB200_CSPLIT', 'DGB200_SPLITS', 'DGB200_PSPLIT',
-        'DGB200_PSPLIT_BM', 'DGB200_TMA_STORE')
+        'DGB200_PSPLIT_BM', 'DGB200_TMA_STORE', 'DGB200_SWAP')
 
 
 def setenv(**kw):
@@ -41,7 +41,7 @@ def run(shapes, configs, with_ref=True):
                 used = _lib.last_config()
                 t = bench_kineto(lambda: dg.fp8_gemm_nt((qa[0], sfa), (qb[0], sfb), d), 'fp8_gemm_kernel', num_tests=10)
                 rows.append((json.dumps(cfg), round(t * 1e6, 2), used['block_m'], used['num_stages'], used['cluster'], used['num_splits'],
-                             'tma' if used['tma_store'] else 'direct'))
+                             'tma' if used['tma_store'] else 'direct', 'swap' if used['swap_ab'] else ''))
             except Exception as e:  # noqa: BLE001
                 rows.append((json.dumps(cfg), 'error ' + str(e)[:80]))
         setenv()
@@ -70,6 +70,17 @@ if __name__ == '__main__':
         cfgs = [{}, dict(psplit=0)] + [dict(psplit=2, psplit_bm=bm, csplit=0) for bm in (64, 96, 128)]
         run([(160, 4096, 7168), (192, 4096, 7168), (224, 4096, 7168), (256, 4096, 7168), (320, 4096, 7168), (256, 2112, 7168), (384, 2112, 7168),
              (192, 7168, 16384), (256, 576, 7168), (256, 7168, 2048)], cfgs)
+    elif mode == 'swap':
+        # second orientation: tokens on the lanes, weight tiles of any multiple of 16 rows
+        def auto_bn(n_, sms=148):
+            return [bn for bn in sorted({-(-(-(-n_ // w)) // 16) * 16 for w in (sms, sms - 20, 2 * sms, 74, 3 * sms)}) if 16 <= bn <= 240]
+        for shape in [(64, 7168, 2048), (128, 7168, 2048), (128, 24576, 1536), (64, 32768, 512), (128, 7168, 16384), (128, 2112, 7168),
+                      (128, 576, 7168), (64, 4096, 7168), (128, 4096, 7168), (1, 7168, 2048), (1, 24576, 1536), (256, 4096, 7168),
+                      (256, 7168, 2048), (512, 7168, 2048)]:
+            cfgs = [dict(swap=0)] + [dict(swap=1, block_m=bn) for bn in auto_bn(shape[1])]
+            if shape[0] > 128:
+                cfgs += [dict(swap=1, block_m=bn) for bn in auto_bn(shape[1], 74)]
+            run([shape], cfgs)
     elif mode == 'small':
         cfgs = [{}, dict(csplit=0), dict(csplit=4), dict(csplit=2)] + [dict(csplit=0, block_m=bm) for bm in (16, 32, 64)]
         run([(1, 2112, 7168), (16, 4096, 7168), (32, 4096, 7168), (64, 4096, 7168), (96, 4096, 7168), (128, 4096, 7168), (192, 4096, 7168),
