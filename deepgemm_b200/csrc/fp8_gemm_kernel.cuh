@@ -507,6 +507,26 @@ fp8_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
                 if (kb0 + j <= kb_last) tma_prefetch_2d(&map_w, (kb0 + j) * kBlockK, n0);
         }
     }
+    if constexpr (kCSplit == 0 && kGemmType == kDense && !kXMn && !kWMn && kPairs == 1) {
+        // Same head start for the first tile of a persistent dense launch (its coordinates cost one scheduler step).
+        if (warp_idx == 3 && elect_one()) {
+            Scheduler<kGemmType, kCluster, kSplitK, kCSplit> sched(p, cta_rank, split_rank);
+            Tile t;
+            if (sched.next(t) && t.valid_m > 0) {
+                const uint32_t rows = max(16u, min(p.block_m, (t.valid_m + 15u) & ~15u));
+                const uint32_t x_row0 = t.x_row + (cta_rank & 1) * (rows / kCtaGroup);
+                prefetch_tensormap(&map_w);
+                prefetch_tensormap(&map_x);
+                tma_prefetch_2d(&map_w, t.kb_begin * kBlockK, t.w_row);
+                tma_prefetch_2d(&map_x, t.kb_begin * kBlockK, x_row0);
+                tma_prefetch_2d(&map_sfw, t.sfw_col, t.sfw_row + (t.kb_begin >> p.sf_shift_w));
+                tma_prefetch_2d(&map_sfx, t.sfx_col, t.sfx_row + (t.kb_begin >> p.sf_shift_x));
+#pragma unroll
+                for (uint32_t j = 1; j < 4; ++j)
+                    if (t.kb_begin + j < t.kb_end) tma_prefetch_2d(&map_w, (t.kb_begin + j) * kBlockK, t.w_row);
+            }
+        }
+    }
     bool producer_lane = false;
     if (warp_idx == 0) {
         for (uint32_t i = lane; i < num_stages; i += 32) {

@@ -101,8 +101,8 @@ DGB_DEVICE bool mbar_try_wait(uint32_t bar, uint32_t parity) {
     return done != 0;
 }
 // A protocol bug must not hang the GPU: a wait that lasts longer than kSpinTimeoutNs traps (sticky CUDA error),
-// the same policy as the reference's in-kernel barriers (comm/barrier.cuh:11-12, 60 s there).
-constexpr uint64_t kSpinTimeoutNs = 10ull * 1000 * 1000 * 1000;
+// the same policy and limit (60 s) as the reference's in-kernel barriers (comm/barrier.cuh:11-12).
+constexpr uint64_t kSpinTimeoutNs = 60ull * 1000 * 1000 * 1000;
 DGB_DEVICE uint64_t globaltimer_ns() {
     uint64_t t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));

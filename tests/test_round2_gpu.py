@@ -137,7 +137,9 @@ def test_pair_split_k_matches_oracle_and_is_deterministic(dg, m, n, k, slices, b
     dg.fp8_gemm_nt(qa, qb, d, c=d)
     want = blockwise.fp8_gemm_nt(_cpu(qa), _cpu(qb), out_dtype=out_dtype, c=c.cpu())
     prod = blockwise.fp8_gemm_nt(_cpu(qa), _cpu(qb), out_dtype=torch.float32)
-    assert_close_to_oracle(d, want, 'psplit accumulate', mag=prod.abs() + c.cpu().float().abs())
+    # BF16 accumulate = round(product) then one BF16 add: a sliced FP32 sum may round the product the other way AND move the
+    # final rounding, i.e. up to two BF16 steps of (|product| + |C|) instead of one
+    assert_close_to_oracle(d, want, 'psplit accumulate', mag=2 * (prod.abs() + c.cpu().float().abs()))
 
 
 # ------------------------------------------------------------------------------------------------ second orientation
