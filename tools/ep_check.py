@@ -141,6 +141,9 @@ def main():
     total += 0
 
     # (d) CUDA graph: capture dispatch + GEMM once, replay with new inputs
+    x = torch.randn((t_local, k), device=dev, dtype=torch.bfloat16, generator=gen)
+    xq, sf = per_token_cast_to_fp8(x, True, 128, use_packed_ue8m0=True)
+    ids = torch.randint(0, g, (t_local,), device=dev, generator=gen)
     sx, ssf, sids = torch.empty_like(xq), torch.empty_like(sf), torch.empty(t_local, dtype=torch.int64, device=dev)
     row = torch.empty(t_local, dtype=torch.int32, device=dev)
     side = torch.cuda.Stream()

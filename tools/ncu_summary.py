@@ -25,8 +25,10 @@ WANT = [
 ]
 
 
-KEYS = {'ours_4096': 'dense_m4096', 'ours_512': 'dense_m512', 'ours_64': 'dense_m64', 'ours_128': 'dense_m128',
-        'ours_contig': 'contiguous_g48_m256', 'ours_masked': 'masked', 'ep_dispatch': 'ep_dispatch',
+KEYS = {'ours_4096': 'dense_m4096', 'ours_512': 'dense_m512', 'ours_64': 'dense_m64', 'ours_128': 'dense_m128', 'ours_192': 'dense_m192',
+        'ours_k2048': 'dense_4096x7168x2048', 'ref_k2048': 'reference_dense_4096x7168x2048',
+        'ours_contig': 'contiguous_g256_m128', 'ref_contig': 'reference_contiguous_g256_m128', 'ours_masked': 'masked_g256_m64',
+        'ours_quant': 'per_token_cast_to_fp8_4096x7168', 'ep_dispatch': 'ep_dispatch', 'ep_combine': 'ep_dispatch',
         'ref_4096': 'reference_dense_m4096', 'ref_64': 'reference_dense_m64'}
 TRAFFIC = {}
 UNIT = {'byte': 1, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9, 'Tbyte': 1e12}
