@@ -201,3 +201,26 @@ def test_dense_plan_balances_rounds_of_cta_pairs(lib):
     assert cfg['num_tiles'] == 23 * 16                  # 3 x 192 + 20 x 176 rows = 4096, times 16 column pairs
     small = lib.plan(0, 512, 4096, 7168)
     assert small['block_m'] == 128                       # below 1024 rows the tile height is chosen by the cost model alone
+
+
+def test_plan_picks_pair_split_k_and_the_staged_epilogue_where_measured(lib):
+    """Round-2 heuristics: medium M runs as two CTA-pair K slices while all clusters of 4 fit one
+    wave; tall tiles with a long K loop take the TMA-store epilogue unless it would cost a pipeline stage."""
+    c = lib.plan(0, 192, 4096, 7168)
+    assert (c['cluster'], c['cluster_split'], c['block_m']) == (4, 2, 96)
+    c = lib.plan(0, 256, 4096, 7168)
+    assert (c['cluster'], c['cluster_split'], c['block_m']) == (4, 2, 128)
+    c = lib.plan(0, 256, 2112, 7168)
+    assert (c['cluster'], c['cluster_split'], c['block_m']) == (4, 2, 96)      # 27 clusters; 64-row tiles would need 36 > 32
+    c = lib.plan(0, 320, 4096, 7168)
+    assert c['cluster_split'] == 0 and c['cluster'] == 2                         # 48 clusters: no longer one wave
+    c = lib.plan(0, 256, 7168, 2048)
+    assert c['cluster_split'] == 0                                               # short K: the exchange does not pay
+    c = lib.plan(0, 64, 4096, 7168)
+    assert (c['cluster'], c['cluster_split']) == (4, 4)                          # small M: four single-CTA slices
+    big = lib.plan(0, 4096, 7168, 2048)
+    assert big['tma_store'] == 1 and big['block_m'] >= 176 and big['num_stages'] == 7
+    assert lib.plan(0, 4096, 32768, 512)['tma_store'] == 0                       # epilogue-bound: direct stores
+    assert lib.plan(0, 512, 4096, 7168)['tma_store'] == 0                        # 128-row tiles: the staging would cost a stage
+    assert lib.plan(1, 32768, 4096, 7168, 256, 128, 128)['tma_store'] == 0       # contiguous, 128-row tiles
+    assert all(lib.plan(0, m, 4096, 7168)['swap_ab'] == 0 for m in (1, 64, 512, 4096))   # second orientation: never by default

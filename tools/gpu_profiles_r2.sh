@@ -4,6 +4,7 @@ cd "${GRAFT_REPO_ROOT:-/root/repo}"
 O=gpurun_out/r2p
 mkdir -p $O
 nvidia-smi --query-gpu=name,clocks.max.sm,clocks.sm,power.limit --format=csv > $O/smi.txt
+timeout 600 python tools/tune.py swap2 > $O/tune_swap2.log 2>&1
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $O/smoke.log 2>&1; echo "smoke rc=$?"; tail -2 $O/smoke.log
 timeout 900 python bench.py > $O/bench.log 2> $O/bench.err; echo "bench rc=$?"
 timeout 900 python bench.py --impl reference > $O/bench_ref_arm.log 2> $O/bench_ref_arm.err; echo "bench ref rc=$?"; tail -c 600 $O/bench_ref_arm.log
