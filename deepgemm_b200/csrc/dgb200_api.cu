@@ -375,7 +375,11 @@ Config choose_config(const Problem& pb, int num_sms_override = 0) {
         return st;
     };
     c.tma_store = 0;
-    if (pb.tma_store_ok && c.cluster == 2 && !c.csplit && c.num_splits == 1) {
+    if (pb.swapped) {
+        // transposed output: per-warp 32 x 32 staging (16 KB), tile width a multiple of 32 columns. DGB200_TMA_STORE pins it.
+        const int want = env_int("DGB200_TMA_STORE", -1);
+        c.tma_store = pb.tma_store_ok && c.block_m % (int)kSwapStoreCols == 0 && c.cluster <= 2 && (want >= 0 ? want != 0 : c.block_m >= kTmaStoreMinBlockM);
+    } else if (pb.tma_store_ok && c.cluster == 2 && !c.csplit && c.num_splits == 1) {
         // Measured (tools/tune.py store): the staged epilogue wins 1-4 % on tall tiles with a long enough K loop to hide it
         // behind (4096 x 4096 x 7168, 4096 x 7168 x 2048, 4096 x 24576 x 1536 at 240 rows); it loses when it costs a pipeline
         // stage, on short tiles, and when the kernel is epilogue-bound (K = 512: 8 warps of direct stores move more bytes per
@@ -384,7 +388,7 @@ Config choose_config(const Problem& pb, int num_sms_override = 0) {
         c.tma_store = want >= 0 ? (want != 0)
                                 : (c.block_m >= kTmaStoreMinBlockM && num_kb >= 12 && max_stages((int)kStoreStagingBytes) == max_stages(0));
     }
-    const int store_bytes = c.tma_store ? (int)kStoreStagingBytes : 0;
+    const int store_bytes = c.tma_store ? (pb.swapped ? (int)kSwapStagingBytes : (int)kStoreStagingBytes) : 0;
     int stages = max_stages(store_bytes);
     stages = std::min(stages, 32);
     if (int v = env_int("DGB200_STAGES", 0)) stages = std::min(v, stages);
@@ -420,7 +424,7 @@ int run_gemm(const GemmCall& c) {
     pb.swapped = c.swap_d;
     // TMA stores need a 16-byte aligned base and row pitch; tiles that must not touch rows past `valid_m` (masked, psum),
     // accumulate into C or remap columns keep the predicated direct stores
-    pb.tma_store_ok = (c.type == kDense || c.type == kMContiguous) && !c.swap_d && c.d_dtype == DGB200_BF16 && !c.accumulate && !head_split &&
+    pb.tma_store_ok = (c.type == kDense || c.type == kMContiguous) && c.d_dtype == DGB200_BF16 && !c.accumulate && !head_split &&
                       (reinterpret_cast<uintptr_t>(c.d) & 15) == 0 && (c.ldd * 2) % 16 == 0 && c.arrival == nullptr;
     // split-K needs scratch: [4096 arrival counters][num_splits x m x n fp32 partial tiles]
     if (c.type == kDense && !head_split && !c.swap_d && c.workspace != nullptr && c.n % 4 == 0 && c.workspace_bytes > kSplitKHeaderBytes &&
@@ -482,7 +486,11 @@ int run_gemm(const GemmCall& c) {
                             cfg.block_m, 1, CU_TENSOR_MAP_SWIZZLE_NONE)) return e;
     if (int e = make_map_2d(&maps.sfw, c.sfb, CU_TENSOR_MAP_DATA_TYPE_INT32, c.sfb_cols, sfb_krows, (uint64_t)c.sfb_stride * 4,
                             kBlockN, 1, CU_TENSOR_MAP_SWIZZLE_NONE)) return e;
-    if (cfg.tma_store) {
+    if (cfg.tma_store && c.swap_d) {
+        // transposed output: D [tokens = c.n rows, weights = c.m columns]; box 32 columns (64 B swizzle atom) x 32 rows (one warp)
+        if (int e = make_map_2d(&maps.d, c.d, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, c.m, c.n, (uint64_t)c.ldd * 2, kSwapStoreCols, 32,
+                                CU_TENSOR_MAP_SWIZZLE_64B)) return e;
+    } else if (cfg.tma_store) {
         // D [rows, N] BF16: box 64 columns (one 128 B swizzle atom) x 16 rows; rows / columns past the end are clipped
         if (int e = make_map_2d(&maps.d, c.d, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, c.n, c.m, (uint64_t)c.ldd * 2, 64, kStoreRows,
                                 CU_TENSOR_MAP_SWIZZLE_128B)) return e;

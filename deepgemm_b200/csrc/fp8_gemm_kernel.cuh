@@ -59,6 +59,9 @@ constexpr uint32_t kWTileBytes = kBlockN * kBlockK;  // 16 KB
 constexpr uint32_t kStoreRows = 16;                  // output rows per TMA store (one staging buffer = 16 rows x 128 columns bf16)
 constexpr uint32_t kStoreBufBytes = kStoreRows * kBlockN * 2;       // 4 KB: two 128B-swizzled boxes of 16 rows x 64 columns
 constexpr uint32_t kStoreStagingBytes = 2 * kStoreBufBytes;         // two buffers, shared by the eight epilogue warps
+constexpr uint32_t kSwapStoreCols = 32;              // transposed-output staged epilogue: columns per TMA store (64 B swizzle atom)
+constexpr uint32_t kSwapStoreBufBytes = 32 * kSwapStoreCols * 2;    // 2 KB: 32 output rows (one warp's lanes) x 32 columns bf16
+constexpr uint32_t kSwapStagingBytes = 8 * kSwapStoreBufBytes;      // one buffer per epilogue warp
 
 struct GemmParams {
     void* d;                    // output (bf16 or fp32), row stride ld_d elements
@@ -256,7 +259,20 @@ struct Scheduler {
             t.valid_m = t.x_row < p.m ? min(height, p.m - t.x_row) : 0u;     // 0: a pair past the last m-block idles along
             t.store_m = t.valid_m;
             t.counter_idx = m_blk * (num_n_units * kCtaGroup) + n_unit * kCtaGroup + (cta_rank & 1);
-            if constexpr (kGemmType == kMContiguous) group = static_cast<uint32_t>(max(0, __ldg(p.grouped_layout + t.x_row)));
+            if constexpr (kGemmType == kMContiguous) {
+                group = static_cast<uint32_t>(max(0, __ldg(p.grouped_layout + t.x_row)));
+                // An expert's rows are a prefix of its aligned segment, the rest is padding (-1): count the 16-row groups that
+                // start with a real row (independent loads, one L2 round trip) and leave the padding groups alone -- neither
+                // multiplied (the UMMA N of the tile follows valid_m) nor written. With mean M = 128 and 128-row alignment a
+                // third of the rows the reference multiplies are padding (its BLOCK_M is a compile-time constant).
+                uint32_t groups = 0;
+                const uint32_t max_groups = (t.valid_m + 15) / 16;
+#pragma unroll
+                for (uint32_t j = 1; j < kMaxBlockM / 16; ++j)
+                    if (j < max_groups) groups += __ldg(p.grouped_layout + t.x_row + 16 * j) >= 0 ? 1u : 0u;
+                t.valid_m = min(t.valid_m, 16 * (groups + 1));
+                t.store_m = t.valid_m;
+            }
         } else if constexpr (kGemmType == kBatched) {
             // every batch is a full [m, n] problem; batches are walked in order (tensor-map coordinate 2 = batch)
             const uint32_t per_batch = p.num_m_blocks * num_n_units;
@@ -454,12 +470,12 @@ fp8_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
     const uint32_t x_tile_bytes = load_m * kBlockK;                         // multiple of 1024 (load_m % 8 == 0)
     const uint32_t num_sfx_groups = (p.block_m + 127) / 128;                // 128-row UTCCP groups of token SFs
     const uint32_t slot_stride = slot_bytes(p.block_m, kCtaGroup);
-    static_assert(!kTmaStore || (std::is_same_v<out_t, __nv_bfloat16> && !kAccumulate && !kSplitK && !kCSplit && kCluster == 2),
-                  "the TMA-store epilogue is built for plain BF16 output tiles of a CTA pair");
-    static_assert(!kSwapD || (kGemmType == kDense && !kXMn && !kWMn && !kSplitK && !kCSplit && !kTmaStore && kCluster <= 2),
+    static_assert(!kTmaStore || (std::is_same_v<out_t, __nv_bfloat16> && !kAccumulate && !kSplitK && !kCSplit && (kCluster == 2 || kSwapD)),
+                  "the TMA-store epilogue is built for plain BF16 output tiles");
+    static_assert(!kSwapD || (kGemmType == kDense && !kXMn && !kWMn && !kSplitK && !kCSplit && kCluster <= 2),
                   "the transposed-output orientation is built for plain dense K-major problems");
-    const uint32_t staging = smem_u32(smem);                               // kTmaStore: 2 buffers x 4 KB
-    const uint32_t smem_base = staging + (kTmaStore ? kStoreStagingBytes : 0u);   // the TMA -> MMA ring starts here
+    const uint32_t staging = smem_u32(smem);                               // kTmaStore: 2 buffers x 4 KB (transposed output: 8 x 2 KB)
+    const uint32_t smem_base = staging + (kTmaStore ? (kSwapD ? kSwapStagingBytes : kStoreStagingBytes) : 0u);   // the TMA -> MMA ring starts here
     const uint32_t off_x = kWTileBytes, off_sfw = off_x + x_tile_bytes, off_sfx = off_sfw + 512;
     const uint32_t bars = smem_base + num_stages * slot_stride;
     const uint32_t full_bar = bars;                            // TMA bytes landed (per CTA)
@@ -996,6 +1012,38 @@ fp8_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
                 else
                     mbar_arrive(tmem_empty_dst + as * 8);
             };
+            if constexpr (kSwapD && kTmaStore) {
+                // ---------------------------------------------------------------- transposed output, staged TMA stores
+                // lane = output row, TMEM column = output column: no transpose needed. Every warp stages its own 32 rows x
+                // 32 columns (64 B per row, 64B-swizzled, one 2 KB buffer per warp) and stores them with one
+                // cp.async.bulk.tensor -- no cross-warp synchronisation at all. The two warps of a lane quadrant take alternate
+                // 32-column units; the tile width is a multiple of 32 (host), rows / columns past the end of D are clipped.
+                const uint32_t num_units = (load_cols + kSwapStoreCols - 1) / kSwapStoreCols;   // (a ragged last tile: the map clips)
+                const uint32_t buf = staging + (warp_idx - 4) * kSwapStoreBufBytes;
+                const uint32_t row_off = buf + lane * 64, sw = (lane >> 1) & 3;
+                if (half >= num_units) release_accumulator();
+                for (uint32_t u = half; u < num_units; u += 2) {
+                    tma_store_wait_read<0>();                       // (only lane 0 owns bulk groups) the buffer has been read out
+                    __syncwarp();
+                    uint32_t v[32];
+                    tmem_ld_32x32b_x16(taddr + u * kSwapStoreCols, *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
+                    tmem_ld_32x32b_x16(taddr + u * kSwapStoreCols + 16, *reinterpret_cast<uint32_t(*)[16]>(&v[16]));
+                    tmem_ld_wait();
+                    if (u + 2 >= num_units) release_accumulator();
+#pragma unroll
+                    for (uint32_t piece = 0; piece < 4; ++piece)
+                        st_shared_v4(row_off + ((piece ^ sw) << 4), pack_bf16x2(v[8 * piece + 0], v[8 * piece + 1]),
+                                     pack_bf16x2(v[8 * piece + 2], v[8 * piece + 3]), pack_bf16x2(v[8 * piece + 4], v[8 * piece + 5]),
+                                     pack_bf16x2(v[8 * piece + 6], v[8 * piece + 7]));
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0 && t.n0 + quad * 32 < p.n) {
+                        tma_store_2d(&map_d, buf, t.d_row + u * kSwapStoreCols, t.n0 + quad * 32);
+                        tma_store_commit();
+                    }
+                }
+                continue;
+            }
             if constexpr (kSwapD) {
                 // ---------------------------------------------------------------- transposed-output epilogue
                 // lane = output row (token), TMEM column = output column (weight): 16 consecutive columns per load, written
@@ -1112,7 +1160,7 @@ fp8_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
                     store_out<out_t>(reinterpret_cast<out_t*>(d_col + r * row_bytes), 0.0f, false);
         }
         if constexpr (kTmaStore) {
-            if (warp_idx == 4) tma_store_wait_all();           // the staging buffers must outlive every store that reads them
+            if (warp_idx == 4 || kSwapD) tma_store_wait_all();   // the staging buffers must outlive every store that reads them
         }
     }
 

@@ -6,6 +6,8 @@ namespace dgb200 {
 
 template <int kCluster>
 static int by_output(const GemmCall& c, const Config& cfg, const Maps& maps, const GemmParams& p) {
+    if (cfg.tma_store)
+        return launch_kernel(fp8_gemm_kernel<kDense, kCluster, __nv_bfloat16, false, false, false, false, 0, true, true>, cfg, c.stream, maps, p);
     if (c.d_dtype == DGB200_BF16)
         return c.accumulate
                    ? launch_kernel(fp8_gemm_kernel<kDense, kCluster, __nv_bfloat16, true, false, false, false, 0, false, true>, cfg, c.stream, maps, p)

@@ -176,6 +176,28 @@ def test_transposed_output_orientation_gives_identical_bits(dg, m, n, k, out_dty
     assert torch.equal(accs[0], accs[1])
 
 
+@pytest.mark.parametrize('m,n,k,bn', [(512, 7168, 2048, 224), (300, 1000, 512, 96), (100, 520, 768, 32), (4096, 2048, 512, 224),
+                                      (257, 4104, 384, 160)])
+def test_transposed_output_with_staged_tma_stores(dg, m, n, k, bn, monkeypatch):
+    """Second orientation + per-warp staged TMA stores (32 rows x 32 columns per store): same bits, nothing outside D."""
+    from deepgemm_b200 import _lib
+    _, _, qa, qb = _quant_dense(m, n, k, seed=m + bn)
+    monkeypatch.setenv('DGB200_SPLITS', '1')
+    monkeypatch.setenv('DGB200_SWAP', '0')
+    base = torch.empty((m, n), device='cuda', dtype=torch.bfloat16)
+    dg.fp8_gemm_nt(qa, qb, base)
+    monkeypatch.setenv('DGB200_SWAP', '1')
+    monkeypatch.setenv('DGB200_TMA_STORE', '1')
+    monkeypatch.setenv('DGB200_BLOCK_M', str(bn))
+    buf = torch.full((m + 40, n + 72), 444.0, device='cuda', dtype=torch.bfloat16)
+    d = buf[:m, :n]
+    dg.fp8_gemm_nt(qa, qb, d)
+    cfg = _lib.last_config()
+    assert cfg['swap_ab'] == 1 and cfg['tma_store'] == 1 and cfg['block_m'] == bn
+    assert bool((buf[m:] == 444.0).all()) and bool((buf[:, n:] == 444.0).all()), 'wrote outside D'
+    assert torch.equal(d, base)
+
+
 @pytest.mark.parametrize('bn', [16, 48, 112, 176, 240])
 def test_transposed_output_every_tile_width(dg, bn, monkeypatch):
     m, n, k = 120, 2000, 640
@@ -185,6 +207,7 @@ def test_transposed_output_every_tile_width(dg, bn, monkeypatch):
     base = torch.empty((m, n), device='cuda', dtype=torch.bfloat16)
     dg.fp8_gemm_nt(qa, qb, base)
     monkeypatch.setenv('DGB200_SWAP', '1')
+    monkeypatch.setenv('DGB200_TMA_STORE', '0')
     monkeypatch.setenv('DGB200_BLOCK_M', str(bn))
     d = torch.full_like(base, float('nan'))
     dg.fp8_gemm_nt(qa, qb, d)

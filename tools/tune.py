@@ -86,7 +86,7 @@ if __name__ == '__main__':
         for shape, bns in [((512, 7168, 2048), (192, 208, 224, 240)), ((512, 4096, 7168), (112, 128)), ((4096, 7168, 2048), (208, 224, 240)),
                            ((4096, 7168, 16384), (224,)), ((1024, 7168, 2048), (208, 224)), ((384, 4096, 7168), (112, 128)),
                            ((448, 4096, 7168), (112, 128)), ((4096, 4096, 7168), (224, 240))]:
-            run([shape], [dict(swap=0)] + [dict(swap=1, block_m=bn) for bn in bns])
+            run([shape], [dict(swap=0)] + [dict(swap=1, block_m=bn, tma_store=ts) for bn in bns for ts in (0, 1)])
     elif mode == 'small':
         cfgs = [{}, dict(csplit=0), dict(csplit=4), dict(csplit=2)] + [dict(csplit=0, block_m=bm) for bm in (16, 32, 64)]
         run([(1, 2112, 7168), (16, 4096, 7168), (32, 4096, 7168), (64, 4096, 7168), (96, 4096, 7168), (128, 4096, 7168), (192, 4096, 7168),
