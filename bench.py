@@ -424,6 +424,13 @@ def add_dense_extras(out, probs, args, rank, world, device):
     import deepgemm_b200 as dg
     if rank == 0:
         out['vs_reference_kernel'] = guarded(lambda: dense_ab_block(probs, dg))
+        try:    # the dominant kernel's share of the step by KERNEL time (what an ncu launch list shows: no event gaps)
+            ks = [r['ours_kineto_us'] for r in out['vs_reference_kernel']['per_shape']]
+            out['roofline']['share_of_step_by_kernel_time'] = round(ks[-1] / sum(ks), 4)
+            out['roofline']['achieved_by_kernel_time'] = round(2.0 * 4096 * 4096 * 7168 / (ks[-1] * 1e-6) / 1e12, 1)
+            out['roofline']['frac_by_kernel_time'] = round(out['roofline']['achieved_by_kernel_time'] / out['roofline']['peak'], 4)
+        except Exception:  # noqa: BLE001
+            pass
     probs.clear()
     torch.cuda.empty_cache()
     if rank == 0:
