@@ -672,7 +672,9 @@ def grouped_line(p, ms_step, peaks, peak_kind):
     g, n, k = p['g'], p['n'], p['k']
     rows = p['rows_total']
     flops = 2.0 * p['valid'] * n * k
-    byts = rows * k + g * n * k + rows * n * 2 + (rows + g * n) * ((k + 511) // 512) * 4
+    # A (as laid out, padding included: it is loaded with its tile) + weights + D rows actually written (valid rows: the
+    # contiguous kernel leaves padding groups alone, the masked one never touches rows >= masked_m) + packed scale factors
+    byts = rows * k + g * n * k + p['valid'] * n * 2 + (rows + g * n) * ((k + 511) // 512) * 4
     gbs = byts / (ms_step * 1e-3) / 1e9
     return {'workload': p['name'], 'us': round(ms_step * 1e3, 1), 'tokens_per_s': round(p['valid'] / (ms_step * 1e-3), 1),
             'tflops': round(flops / (ms_step * 1e-3) / 1e12, 1),

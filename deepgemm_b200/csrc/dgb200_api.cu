@@ -164,6 +164,7 @@ struct Problem {
     bool any_mn = false; // any MN-major operand: no weight multicast
     bool tma_store_ok = false;   // the output may leave through the staged TMA-store epilogue (plain BF16 tiles)
     bool swapped = false;        // transposed-output orientation: `m` is the weight count (tiled freely), `n` the token count (lanes)
+    int forced_block_m = 0;      // tile height fixed by the caller (the orientation rule): skips the cost model
 };
 int stage_bytes(int block_m, int cluster) { return static_cast<int>(slot_bytes(block_m, cluster)); }
 int smem_bytes_for(int block_m, int cluster, int stages, int staging_bytes = 0) {
@@ -255,6 +256,7 @@ Config choose_config(const Problem& pb, int num_sms_override = 0) {
             if (t < best * 0.999) best = t, c.block_m = bm, c.num_splits = sp;  // ties -> smaller tile, fewer slices
         }
     }
+    if (pb.forced_block_m > 0) c.block_m = pb.forced_block_m, c.num_splits = 1;
     if (int v = env_int("DGB200_BLOCK_M", 0)) c.block_m = v;
     if (const char* v = getenv("DGB200_SPLITS")) c.num_splits = std::max(1, std::min(atoi(v), max_splits));
     c.kb_per_split = ceil_div(num_kb, c.num_splits);
@@ -398,12 +400,28 @@ Config choose_config(const Problem& pb, int num_sms_override = 0) {
     return c;
 }
 
-// Which orientation for a dense K-major problem? DGB200_SWAP = 0 / 1 pins it (development).
-bool want_swapped_orientation(int m, int n, int k) {
+// Which orientation for a dense K-major problem? DGB200_SWAP = 0 / 1 pins it (development). Returns the weight-tile width
+// to use in the transposed-output orientation (0: stay with the default one; -1: transposed, width chosen by the cost model).
+// Rule (tools/tune.py swap / swap2): the default orientation tiles N in fixed units of 256 weight rows per CTA pair, so a
+// medium-M problem with a wide N needs two rounds of pairs where 224-row weight tiles under 256 tokens make ONE
+// (512 x 7168 x 2048: 12.2 us default, 11.3 transposed with staged stores, 11.2 reference); everywhere else the default
+// orientation was level or ahead, so nothing else selects it.
+int want_swapped_orientation(const GemmCall& c, int num_sms_override = 0) {
     const int want = env_int("DGB200_SWAP", -1);
-    if (want >= 0) return want != 0;
-    (void)m, (void)n, (void)k;
-    return false;
+    if (want >= 0) return want != 0 ? -1 : 0;
+    if (getenv("DGB200_BLOCK_M") || getenv("DGB200_CLUSTER") || getenv("DGB200_SPLITS")) return 0;   // pinned configurations
+    if (c.d_dtype != DGB200_BF16 || c.accumulate || c.m <= (int)kBlockN || (reinterpret_cast<uintptr_t>(c.d) & 15) != 0 || (c.ldd * 2) % 16 != 0)
+        return 0;
+    Problem pb{kDense, c.m, c.m, c.n, c.k, 1, 1};
+    const Config dflt = choose_config(pb, num_sms_override);
+    if (dflt.csplit || dflt.num_splits > 1 || dflt.cluster != 2) return 0;
+    const int pairs = dflt.num_sms / 2, num_kb = ceil_div(c.k, (int)kBlockK);
+    const int default_tiles = ceil_div(c.m, dflt.block_m) * ceil_div(c.n, 2 * (int)kBlockN);
+    if (default_tiles <= pairs || num_kb < 8) return 0;                       // already one round of pairs
+    const int token_units = ceil_div(c.m, 2 * (int)kBlockN);
+    for (int bn = 128; bn <= 224; bn += (int)kSwapStoreCols)                   // the narrowest tiles that still make one round
+        if (token_units * ceil_div(c.n, bn) <= pairs) return bn;
+    return 0;
 }
 
 // ------------------------------------------------------------------------------------------------ launch
@@ -421,7 +439,7 @@ int run_gemm(const GemmCall& c) {
     const bool head_split = c.head_mid > 0;
     Problem pb{c.type, c.m, c.expected_m, c.n, c.k, c.groups, c.alignment};
     pb.x_mn = c.x_mn, pb.any_mn = c.x_mn || c.w_mn;
-    pb.swapped = c.swap_d;
+    pb.swapped = c.swap_d, pb.forced_block_m = c.forced_block_m;
     // TMA stores need a 16-byte aligned base and row pitch; tiles that must not touch rows past `valid_m` (masked, psum),
     // accumulate into C or remap columns keep the predicated direct stores
     pb.tma_store_ok = (c.type == kDense || c.type == kMContiguous) && c.d_dtype == DGB200_BF16 && !c.accumulate && !head_split &&
@@ -709,11 +727,14 @@ int dgb200_fp8_gemm_nt(const void* a, const int32_t* sfa, const void* b, const i
     c.expected_m = m, c.alignment = 1, c.zero_padding = 0;
     c.workspace = workspace, c.workspace_bytes = workspace_bytes > 0 ? static_cast<size_t>(workspace_bytes) : 0;
     c.stream = static_cast<cudaStream_t>(stream);
-    if (!c.x_mn && !c.w_mn && want_swapped_orientation(m, n, k)) {
+    if (int e = ensure_device()) return e;
+    const int swap_bn = (!c.x_mn && !c.w_mn) ? want_swapped_orientation(c) : 0;
+    if (swap_bn != 0) {
         // second orientation: tokens on the TMEM lanes, weights tiled freely along N (the kernel writes D[lane][column])
         std::swap(c.a, c.b), std::swap(c.sfa, c.sfb), std::swap(c.m, c.n), std::swap(c.lda, c.ldb);
         std::swap(c.sfa_stride, c.sfb_stride), std::swap(c.sfa_cols, c.sfb_cols), std::swap(c.gran_k_a, c.gran_k_b);
         c.a_rows = c.m, c.expected_m = c.m, c.swap_d = true;
+        c.forced_block_m = swap_bn > 0 ? swap_bn : 0;
     }
     return run_gemm(c);
 }
@@ -963,7 +984,21 @@ int dgb200_plan(int gemm_type, int m, int n, int k, int num_groups, int expected
     Problem pb{gemm_type, m, expected_m > 0 ? expected_m : m, n, k, num_groups, std::max(alignment, 1)};
     if (gemm_type == kDense && n % 4 == 0) pb.max_splits = kMaxSplits;   // as if a workspace were supplied
     pb.tma_store_ok = gemm_type == kDense || gemm_type == kMContiguous;   // as if D were an aligned BF16 tensor
-    const Config cfg = choose_config(pb, num_sms);
+    Config cfg = choose_config(pb, num_sms);
+    if (gemm_type == kDense && n % 8 == 0) {
+        // the orientation rule of dgb200_fp8_gemm_nt, for a BF16 output with an aligned row pitch
+        GemmCall probe{};
+        probe.m = m, probe.n = n, probe.k = k, probe.d_dtype = DGB200_BF16, probe.accumulate = 0, probe.d = nullptr, probe.ldd = n;
+        const int bn = want_swapped_orientation(probe, num_sms);
+        if (bn != 0) {
+            Problem sw{kDense, n, n, m, k, 1, 1};
+            sw.swapped = true, sw.tma_store_ok = true, sw.forced_block_m = bn > 0 ? bn : 0;
+            cfg = choose_config(sw, num_sms);
+            *out = dgb200_config{cfg.block_m, cfg.cluster, cfg.stages, cfg.num_sms, cfg.smem_bytes,
+                                 ceil_div(n, cfg.block_m) * ceil_div(m, (int)kBlockN * std::min(cfg.cluster, 2)), 1, 0, cfg.tma_store, 1};
+            return DGB200_OK;
+        }
+    }
     const int n_units = ceil_div(n, (int)kBlockN * (cfg.csplit ? cfg.cluster / cfg.csplit : std::min(cfg.cluster, 2)));
     int m_blocks = gemm_type == kMMasked ? num_groups * ceil_div(pb.expected_m, cfg.block_m) : ceil_div(m, cfg.block_m);
     if (gemm_type == kDense && cfg.block_m_low > 0)   // two tile heights (wave balancing)

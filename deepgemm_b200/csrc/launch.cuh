@@ -74,6 +74,7 @@ struct GemmCall {
     int64_t batch_stride_a = 0, batch_stride_b = 0, batch_stride_d = 0;   // batched (elements)
     int head_left = 0, head_mid = 0, head_right = 0;                     // fp8_gemm_nt_skip_head_mid
     bool swap_d = false;   // operands already exchanged by the caller (a = weights, b = tokens): the kernel writes D[lane][column]
+    int forced_block_m = 0;
 };
 
 struct Maps {

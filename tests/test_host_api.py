@@ -223,4 +223,7 @@ def test_plan_picks_pair_split_k_and_the_staged_epilogue_where_measured(lib):
     assert lib.plan(0, 4096, 32768, 512)['tma_store'] == 0                       # epilogue-bound: direct stores
     assert lib.plan(0, 512, 4096, 7168)['tma_store'] == 0                        # 128-row tiles: the staging would cost a stage
     assert lib.plan(1, 32768, 4096, 7168, 256, 128, 128)['tma_store'] == 0       # contiguous, 128-row tiles
-    assert all(lib.plan(0, m, 4096, 7168)['swap_ab'] == 0 for m in (1, 64, 512, 4096))   # second orientation: never by default
+    assert all(lib.plan(0, m, 4096, 7168)['swap_ab'] == 0 for m in (1, 64, 512, 4096))   # second orientation: not for these
+    sw = lib.plan(0, 512, 7168, 2048)      # 28 x 5 tiles = two rounds of pairs; 2 x 32 tiles of 256 tokens x 224 weights = one
+    assert (sw['swap_ab'], sw['block_m'], sw['cluster'], sw['tma_store'], sw['num_tiles']) == (1, 224, 2, 1, 64)
+    assert lib.plan(0, 256, 7168, 2048)['swap_ab'] == 0 and lib.plan(0, 1024, 7168, 2048)['swap_ab'] == 0
