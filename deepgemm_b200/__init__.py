@@ -7,6 +7,8 @@ Importing this package does not touch CUDA (the reference guarantees the same, t
 """
 from . import testing, utils  # noqa: F401
 from .gemm import (  # noqa: F401
+    bf16_gemm_nn, bf16_gemm_nt, bf16_gemm_tn, bf16_gemm_tt, k_grouped_bf16_gemm_tn_contiguous,
+    m_grouped_bf16_gemm_nn_contiguous, m_grouped_bf16_gemm_nt_contiguous, m_grouped_bf16_gemm_nt_masked,
     fp8_bmm, fp8_einsum, fp8_gemm_nn, fp8_gemm_nt, fp8_gemm_nt_skip_head_mid, fp8_gemm_tn, fp8_gemm_tt,
     k_grouped_fp8_gemm_nt_contiguous, k_grouped_fp8_gemm_tn_contiguous,
     m_grouped_fp8_gemm_nn_contiguous, m_grouped_fp8_gemm_nt_contiguous, m_grouped_fp8_gemm_nt_masked,
@@ -31,5 +33,6 @@ m_grouped_fp8_fp4_gemm_nt_contiguous = m_grouped_fp8_gemm_nt_contiguous
 m_grouped_fp8_fp4_gemm_nn_contiguous = m_grouped_fp8_gemm_nn_contiguous
 m_grouped_fp8_fp4_gemm_nt_masked = m_grouped_fp8_gemm_nt_masked
 fp8_m_grouped_gemm_nt_masked = m_grouped_fp8_gemm_nt_masked
+bf16_m_grouped_gemm_nt_masked = m_grouped_bf16_gemm_nt_masked
 
 __version__ = '0.1.0'

@@ -165,6 +165,7 @@ struct Problem {
     bool tma_store_ok = false;   // the output may leave through the staged TMA-store epilogue (plain BF16 tiles)
     bool swapped = false;        // transposed-output orientation: `m` is the weight count (tiled freely), `n` the token count (lanes)
     int forced_block_m = 0;      // tile height fixed by the caller (the orientation rule): skips the cost model
+    bool plain_only = false;     // no split-K of any kind, no multicast clusters (the BF16-operand instances)
 };
 int stage_bytes(int block_m, int cluster) { return static_cast<int>(slot_bytes(block_m, cluster)); }
 int smem_bytes_for(int block_m, int cluster, int stages, int staging_bytes = 0) {
@@ -223,6 +224,7 @@ Config choose_config(const Problem& pb, int num_sms_override = 0) {
     c.cluster = c.num_sms >= 2 ? 2 : 1;
     if (pb.swapped && pb.n <= (int)kBlockN) c.cluster = 1;    // up to 128 token rows fit the lanes of one CTA: no pair needed
     if (int v = env_int("DGB200_CLUSTER", 0)) c.cluster = v;
+    if (pb.plain_only && c.num_sms >= 2) c.cluster = 2;
     c.swap_d = pb.swapped;
     std::vector<int> candidates;
     if (pb.type == kDense || pb.type == kMMasked || pb.type == kKGrouped || pb.type == kKGroupedPsum || pb.type == kBatched) {
@@ -235,7 +237,7 @@ Config choose_config(const Problem& pb, int num_sms_override = 0) {
         if (candidates.empty()) candidates.push_back(16);
     }
     const int num_kb = ceil_div(pb.k, (int)kBlockK);
-    const int max_splits = rt().split_k ? std::min({pb.max_splits, kMaxSplits, std::max(1, num_kb / 4)}) : 1;
+    const int max_splits = (rt().split_k && !pb.plain_only) ? std::min({pb.max_splits, kMaxSplits, std::max(1, num_kb / 4)}) : 1;
     double best = 1e300;
     c.block_m = candidates[0];
     c.num_splits = 1;
@@ -300,7 +302,7 @@ Config choose_config(const Problem& pb, int num_sms_override = 0) {
     c.csplit = 0, c.grid = 0, c.grid_y = 1;
     const char* splits_env = getenv("DGB200_SPLITS");
     const bool pinned = getenv("DGB200_BLOCK_M") || getenv("DGB200_CLUSTER") || (splits_env && atoi(splits_env) <= 1);
-    if (pb.type == kDense && !pb.swapped && !pb.any_mn && c.cluster == 2 && pb.m > 0 && rt().split_k && !(pinned && !getenv("DGB200_CSPLIT"))) {
+    if (pb.type == kDense && !pb.swapped && !pb.plain_only && !pb.any_mn && c.cluster == 2 && pb.m > 0 && rt().split_k && !(pinned && !getenv("DGB200_CSPLIT"))) {
         const int want = env_int("DGB200_CSPLIT", -1);            // -1: heuristic, 0: off, 2/4: forced
         int pick = 0, pick_bm = 0;
         for (int sp : {4, 2}) {
@@ -328,7 +330,7 @@ Config choose_config(const Problem& pb, int num_sms_override = 0) {
     // rows x block_m tokens of HALF (a quarter) of K, so a 192..480-row problem runs as few tall tiles on all SMs instead of
     // many short ones: the bytes every SM pulls through L2 per output drop by ~40 % (the mid-M shapes are bound by L2 -> SM
     // traffic, not by HBM or the tensor pipe). DGB200_PSPLIT = 0 / 2 / 4 pins it, DGB200_PSPLIT_BM the tile height.
-    if (!c.csplit && pb.type == kDense && !pb.swapped && !pb.any_mn && c.cluster == 2 && pb.m > 0 && rt().split_k) {
+    if (!c.csplit && pb.type == kDense && !pb.swapped && !pb.plain_only && !pb.any_mn && c.cluster == 2 && pb.m > 0 && rt().split_k) {
         const int want = env_int("DGB200_PSPLIT", -1);
         int pick = 0, pick_bm = 0;
         for (int sp : {2, 4}) {
@@ -431,18 +433,20 @@ int run_gemm(const GemmCall& c) {
     DGB_REQUIRE(c.gran_k_b == 32 || c.gran_k_b == 128);
     DGB_REQUIRE(c.lda % 16 == 0 && c.ldb % 16 == 0);  // TMA: 16-byte pitch
     DGB_REQUIRE((reinterpret_cast<uintptr_t>(c.a) & 15) == 0 && (reinterpret_cast<uintptr_t>(c.b) & 15) == 0);
-    DGB_REQUIRE((reinterpret_cast<uintptr_t>(c.sfa) & 15) == 0 && (reinterpret_cast<uintptr_t>(c.sfb) & 15) == 0);
-    DGB_REQUIRE(c.sfa_stride % 4 == 0 && c.sfb_stride % 4 == 0);
+    if (!c.bf16_ab) {
+        DGB_REQUIRE((reinterpret_cast<uintptr_t>(c.sfa) & 15) == 0 && (reinterpret_cast<uintptr_t>(c.sfb) & 15) == 0);
+        DGB_REQUIRE(c.sfa_stride % 4 == 0 && c.sfb_stride % 4 == 0);
+    }
     const bool k_grouped = c.type == kKGrouped || c.type == kKGroupedPsum;
 
     const bool batched = c.type == kBatched;
     const bool head_split = c.head_mid > 0;
     Problem pb{c.type, c.m, c.expected_m, c.n, c.k, c.groups, c.alignment};
     pb.x_mn = c.x_mn, pb.any_mn = c.x_mn || c.w_mn;
-    pb.swapped = c.swap_d, pb.forced_block_m = c.forced_block_m;
+    pb.swapped = c.swap_d, pb.forced_block_m = c.forced_block_m, pb.plain_only = c.bf16_ab;
     // TMA stores need a 16-byte aligned base and row pitch; tiles that must not touch rows past `valid_m` (masked, psum),
     // accumulate into C or remap columns keep the predicated direct stores
-    pb.tma_store_ok = (c.type == kDense || c.type == kMContiguous) && c.d_dtype == DGB200_BF16 && !c.accumulate && !head_split &&
+    pb.tma_store_ok = (c.type == kDense || c.type == kMContiguous) && !c.bf16_ab && c.d_dtype == DGB200_BF16 && !c.accumulate && !head_split &&
                       (reinterpret_cast<uintptr_t>(c.d) & 15) == 0 && (c.ldd * 2) % 16 == 0 && c.arrival == nullptr;
     // split-K needs scratch: [4096 arrival counters][num_splits x m x n fp32 partial tiles]
     if (c.type == kDense && !head_split && !c.swap_d && c.workspace != nullptr && c.n % 4 == 0 && c.workspace_bytes > kSplitKHeaderBytes &&
@@ -500,10 +504,12 @@ int run_gemm(const GemmCall& c) {
         if (int e = make_map(&maps.w, c.b, CU_TENSOR_MAP_DATA_TYPE_UINT8, c.k, (uint64_t)c.n * b_groups, c.ldb, kBlockK,
                              kBlockN / pairs, CU_TENSOR_MAP_SWIZZLE_128B, nb, c.batch_stride_b)) return e;
     }
-    if (int e = make_map_2d(&maps.sfx, c.sfa, CU_TENSOR_MAP_DATA_TYPE_INT32, c.sfa_cols, sfa_krows, (uint64_t)c.sfa_stride * 4,
-                            cfg.block_m, 1, CU_TENSOR_MAP_SWIZZLE_NONE)) return e;
-    if (int e = make_map_2d(&maps.sfw, c.sfb, CU_TENSOR_MAP_DATA_TYPE_INT32, c.sfb_cols, sfb_krows, (uint64_t)c.sfb_stride * 4,
-                            kBlockN, 1, CU_TENSOR_MAP_SWIZZLE_NONE)) return e;
+    if (!c.bf16_ab) {
+        if (int e = make_map_2d(&maps.sfx, c.sfa, CU_TENSOR_MAP_DATA_TYPE_INT32, c.sfa_cols, sfa_krows, (uint64_t)c.sfa_stride * 4,
+                                cfg.block_m, 1, CU_TENSOR_MAP_SWIZZLE_NONE)) return e;
+        if (int e = make_map_2d(&maps.sfw, c.sfb, CU_TENSOR_MAP_DATA_TYPE_INT32, c.sfb_cols, sfb_krows, (uint64_t)c.sfb_stride * 4,
+                                kBlockN, 1, CU_TENSOR_MAP_SWIZZLE_NONE)) return e;
+    }
     if (cfg.tma_store && c.swap_d) {
         // transposed output: D [tokens = c.n rows, weights = c.m columns]; box 32 columns (64 B swizzle atom) x 32 rows (one warp)
         if (int e = make_map_2d(&maps.d, c.d, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, c.m, c.n, (uint64_t)c.ldd * 2, kSwapStoreCols, 32,
@@ -564,6 +570,7 @@ int run_gemm(const GemmCall& c) {
                 c.type, c.m, c.n, c.k, c.groups, (int)c.x_mn, (int)c.w_mn, cfg.block_m, cfg.cluster, cfg.stages, cfg.num_sms,
                 cfg.smem_bytes, cfg.csplit ? -cfg.num_splits : cfg.num_splits, cfg.tma_store);
 
+    if (c.bf16_ab) return dispatch_bf16(c, cfg, maps, p);
     switch (c.type) {
         case kDense:
             if (c.swap_d) return dispatch_dense_swap(c, cfg, maps, p);
@@ -765,6 +772,68 @@ int dgb200_m_grouped_fp8_gemm_nt_contiguous(const void* a, const int32_t* sfa, c
     c.alignment = rt().mk_alignment;
     c.zero_padding = use_psum_layout && ensure_zero_padding;
     c.stream = static_cast<cudaStream_t>(stream);
+    return run_gemm(c);
+}
+
+// ---- BF16 operands (no scale factors): K-major, byte-addressed K (see fp8_gemm_kernel.cuh, kBf16AB)
+static void bf16_common(GemmCall& c, int k, int64_t lda, int64_t ldb) {
+    c.bf16_ab = true;
+    c.sfa = c.sfb = nullptr, c.sfa_stride = c.sfb_stride = c.sfa_cols = c.sfb_cols = 4;
+    c.gran_k_a = c.gran_k_b = 128;
+    c.k = 2 * k, c.lda = 2 * lda, c.ldb = 2 * ldb;        // bytes
+    c.workspace = nullptr, c.workspace_bytes = 0;
+}
+
+int dgb200_bf16_gemm_nt(const void* a, const void* b, void* d, int m, int n, int k, int64_t lda, int64_t ldb, int64_t ldd,
+                        int d_dtype, int accumulate, void* stream) {
+    DGB_REQUIRE(m >= 0 && n >= 0 && k >= 0);
+    if (m == 0 || n == 0) return DGB200_OK;
+    DGB_REQUIRE(k > 0 && k % 8 == 0);                    // 16-byte rows for TMA
+    DGB_REQUIRE(d_dtype == DGB200_BF16 || d_dtype == DGB200_FP32);
+    DGB_REQUIRE(lda >= k && ldb >= k && ldd >= n);
+    GemmCall c{};
+    c.type = kDense;
+    c.a = a, c.b = b, c.d = d, c.grouped_layout = nullptr;
+    c.m = m, c.n = n, c.groups = 1, c.a_rows = m, c.ldd = ldd;
+    c.d_dtype = d_dtype, c.accumulate = accumulate != 0;
+    c.expected_m = m, c.alignment = 1, c.zero_padding = 0;
+    c.stream = static_cast<cudaStream_t>(stream);
+    bf16_common(c, k, lda, ldb);
+    return run_gemm(c);
+}
+
+int dgb200_m_grouped_bf16_gemm_nt_contiguous(const void* a, const void* b, void* d, const int32_t* grouped_layout, int num_groups,
+                                             int m, int n, int k, int64_t lda, int64_t ldb, int64_t ldd, int use_psum_layout,
+                                             int ensure_zero_padding, int expected_m_for_psum_layout, void* stream) {
+    DGB_REQUIRE(m >= 0);
+    DGB_REQUIRE(n > 0 && k > 0 && k % 8 == 0 && num_groups > 0);
+    if (m == 0) return DGB200_OK;
+    DGB_REQUIRE(grouped_layout != nullptr && lda >= k && ldb >= k && ldd >= n);
+    GemmCall c{};
+    c.type = use_psum_layout ? kMContiguousPsum : kMContiguous;
+    c.a = a, c.b = b, c.d = d, c.grouped_layout = grouped_layout;
+    c.m = m, c.n = n, c.groups = num_groups, c.a_rows = m, c.ldd = ldd;
+    c.d_dtype = DGB200_BF16, c.accumulate = 0;
+    c.expected_m = expected_m_for_psum_layout > 0 ? expected_m_for_psum_layout : ceil_div(m, num_groups);
+    c.alignment = rt().mk_alignment;
+    c.zero_padding = use_psum_layout && ensure_zero_padding;
+    c.stream = static_cast<cudaStream_t>(stream);
+    bf16_common(c, k, lda, ldb);
+    return run_gemm(c);
+}
+
+int dgb200_m_grouped_bf16_gemm_nt_masked(const void* a, const void* b, void* d, const int32_t* masked_m, int num_groups, int m_max,
+                                         int n, int k, int expected_m, void* stream) {
+    DGB_REQUIRE(expected_m > 0 && m_max > 0 && n > 0 && k > 0 && k % 8 == 0 && num_groups > 0);
+    DGB_REQUIRE(masked_m != nullptr);
+    GemmCall c{};
+    c.type = kMMasked;
+    c.a = a, c.b = b, c.d = d, c.grouped_layout = masked_m;
+    c.m = m_max, c.n = n, c.groups = num_groups, c.a_rows = num_groups * m_max, c.ldd = n;
+    c.d_dtype = DGB200_BF16, c.accumulate = 0;
+    c.expected_m = std::min(expected_m, m_max), c.alignment = 1, c.zero_padding = 0;
+    c.stream = static_cast<cudaStream_t>(stream);
+    bf16_common(c, k, k, k);
     return run_gemm(c);
 }
 

@@ -436,11 +436,15 @@ __device__ __forceinline__ void splitk_finalize(const float* ws, size_t slice_el
 // kSwapD: the second orientation. The host hands the TOKENS to the lane side ("w": 128 rows per CTA) and the WEIGHTS to the
 // column side ("x": block_m rows per tile, any multiple of 16), so TMEM lane = output row, TMEM column = output column, and
 // the epilogue writes D[lane][column]: every thread owns one output row and stores 16 consecutive columns per TMEM load.
+// kBf16AB: BF16 operands without scale factors (the reference's bf16_gemm family, impls/sm100_bf16_gemm.cuh:34-420) on the
+// same skeleton: `tcgen05.mma.kind::f16`, 16 K-elements per instruction. K-major operands are addressed in BYTES (the host
+// passes k = 2 K and UINT8 tensor maps), so a pipeline stage is again one 128-byte swizzle atom per row (64 BF16 of K) and
+// nothing else in the kernel changes; the scale-factor loads, the re-tiling and the tcgen05.cp are compiled out.
 // What it buys is tile-count freedom along N: with few token rows the number of tiles is N / block_m for ANY block_m, so the
 // tiles can be cut to fill exactly one wave of SMs (the reference reaches the same through its non-swap-AB templates,
 // csrc/jit_kernels/heuristics/sm100.hpp:27-92). Dense, K-major operands.
 template <int kGemmType, int kCluster, typename out_t, bool kAccumulate, bool kXMn = false, bool kWMn = false,
-          bool kSplitK = false, int kCSplit = 0, bool kTmaStore = false, bool kSwapD = false>
+          bool kSplitK = false, int kCSplit = 0, bool kTmaStore = false, bool kSwapD = false, bool kBf16AB = false>
 __global__ void __launch_bounds__(kNumThreads, 1)
 fp8_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
                 const __grid_constant__ CUtensorMap map_sfx, const __grid_constant__ CUtensorMap map_sfw,
@@ -474,6 +478,7 @@ fp8_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
                   "the TMA-store epilogue is built for plain BF16 output tiles");
     static_assert(!kSwapD || (kGemmType == kDense && !kXMn && !kWMn && !kSplitK && !kCSplit && kCluster <= 2),
                   "the transposed-output orientation is built for plain dense K-major problems");
+    static_assert(!kBf16AB || (!kXMn && !kWMn && !kSplitK && !kCSplit && !kSwapD && kCluster <= 2), "BF16 operands: K-major, plain kernels");
     const uint32_t staging = smem_u32(smem);                               // kTmaStore: 2 buffers x 4 KB (transposed output: 8 x 2 KB)
     const uint32_t smem_base = staging + (kTmaStore ? (kSwapD ? kSwapStagingBytes : kStoreStagingBytes) : 0u);   // the TMA -> MMA ring starts here
     const uint32_t off_x = kWTileBytes, off_sfw = off_x + x_tile_bytes, off_sfx = off_sfw + 512;
@@ -515,8 +520,10 @@ fp8_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
             prefetch_tensormap(&map_x);
             tma_prefetch_2d(&map_w, kb0 * kBlockK, n0);
             tma_prefetch_2d(&map_x, kb0 * kBlockK, x_row0);
-            tma_prefetch_2d(&map_sfw, n0, kb0 >> p.sf_shift_w);
-            tma_prefetch_2d(&map_sfx, blockIdx.y * p.block_m, kb0 >> p.sf_shift_x);
+            if constexpr (!kBf16AB) {
+                tma_prefetch_2d(&map_sfw, n0, kb0 >> p.sf_shift_w);
+                tma_prefetch_2d(&map_sfx, blockIdx.y * p.block_m, kb0 >> p.sf_shift_x);
+            }
             const uint32_t kb_last = (p.k + kBlockK - 1) / kBlockK - 1;
 #pragma unroll
             for (uint32_t j = 1; j < 4; ++j)
@@ -535,8 +542,10 @@ fp8_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
                 prefetch_tensormap(&map_x);
                 tma_prefetch_2d(&map_w, t.kb_begin * kBlockK, t.w_row);
                 tma_prefetch_2d(&map_x, t.kb_begin * kBlockK, x_row0);
-                tma_prefetch_2d(&map_sfw, t.sfw_col, t.sfw_row + (t.kb_begin >> p.sf_shift_w));
-                tma_prefetch_2d(&map_sfx, t.sfx_col, t.sfx_row + (t.kb_begin >> p.sf_shift_x));
+                if constexpr (!kBf16AB) {
+                    tma_prefetch_2d(&map_sfw, t.sfw_col, t.sfw_row + (t.kb_begin >> p.sf_shift_w));
+                    tma_prefetch_2d(&map_sfx, t.sfx_col, t.sfx_row + (t.kb_begin >> p.sf_shift_x));
+                }
 #pragma unroll
                 for (uint32_t j = 1; j < 4; ++j)
                     if (t.kb_begin + j < t.kb_end) tma_prefetch_2d(&map_w, (t.kb_begin + j) * kBlockK, t.w_row);
@@ -555,8 +564,10 @@ fp8_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
         if (producer_lane) {
             prefetch_tensormap(&map_x);
             prefetch_tensormap(&map_w);
-            prefetch_tensormap(&map_sfx);
-            prefetch_tensormap(&map_sfw);
+            if constexpr (!kBf16AB) {
+                prefetch_tensormap(&map_sfx);
+                prefetch_tensormap(&map_sfw);
+            }
             if constexpr (kTmaStore) prefetch_tensormap(&map_d);
         }
         __syncwarp();
@@ -647,7 +658,7 @@ fp8_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
                     const uint32_t full = full_bar + ring.bar, slot = smem_base + ring.slot;
                     if (fresh) --fresh; else mbar_wait(empty_bar + ring.bar, ring.phase ^ 1);
                     const bool first = kb == t.kb_begin;
-                    const bool load_sfw = (kb & sfw_mask) == 0 || first, load_sfx = (kb & sfx_mask) == 0 || first;
+                    const bool load_sfw = !kBf16AB && ((kb & sfw_mask) == 0 || first), load_sfx = !kBf16AB && ((kb & sfx_mask) == 0 || first);
                     mbar_arrive_expect_tx(full, ab_bytes + (load_sfw ? sfw_tx : 0u) + (load_sfx ? sfx_tx : 0u));
                     if constexpr (kGemmType == kBatched) {
                         // 3-D maps {inner, outer, batch}: boxes are one batch deep, so the tiles land exactly like 2-D ones
@@ -721,17 +732,23 @@ fp8_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
             auto issue_kblock = [&](auto n_const, uint32_t kb, bool first, uint32_t tmem_d) {
                 constexpr uint32_t kNumUmma = decltype(n_const)::value;
                 const uint32_t slot16 = ring.slot >> 4;
-                if ((kb & sfw_mask) == 0 || first) tmem_cp_sf<kCtaGroup>(tmem_sfw, sfw_desc0 + slot16);
-                if ((kb & sfx_mask) == 0 || first) {
-                    tmem_cp_sf<kCtaGroup>(tmem_sfx, sfx_desc0 + slot16);
-                    if (num_sfx_groups > 1) tmem_cp_sf<kCtaGroup>(tmem_sfx + 4, sfx_desc0 + slot16 + 32);
+                if constexpr (!kBf16AB) {
+                    if ((kb & sfw_mask) == 0 || first) tmem_cp_sf<kCtaGroup>(tmem_sfw, sfw_desc0 + slot16);
+                    if ((kb & sfx_mask) == 0 || first) {
+                        tmem_cp_sf<kCtaGroup>(tmem_sfx, sfx_desc0 + slot16);
+                        if (num_sfx_groups > 1) tmem_cp_sf<kCtaGroup>(tmem_sfx + 4, sfx_desc0 + slot16 + 32);
+                    }
                 }
                 const uint64_t w_desc = w_desc0 + slot16, x_desc = x_desc0 + slot16;
                 const uint32_t idesc = idesc_base + (kb & sub_mask) * id_kb_mul;   // one UE8M0 byte per 32 K-elements
 #pragma unroll
-                for (uint32_t j = 0; j < kNumUmma; ++j)
-                    mma_mxf8_block_scale<kCtaGroup>(tmem_d, w_desc + j * w_kstep, x_desc + j * x_kstep, idesc + j * id_j_mul,
-                                                   tmem_sfw, tmem_sfx, (j != 0 || !first) ? 1u : 0u);
+                for (uint32_t j = 0; j < kNumUmma; ++j) {
+                    if constexpr (kBf16AB)
+                        mma_f16<kCtaGroup>(tmem_d, w_desc + j * w_kstep, x_desc + j * x_kstep, idesc_base, (j != 0 || !first) ? 1u : 0u);
+                    else
+                        mma_mxf8_block_scale<kCtaGroup>(tmem_d, w_desc + j * w_kstep, x_desc + j * x_kstep, idesc + j * id_j_mul,
+                                                       tmem_sfw, tmem_sfx, (j != 0 || !first) ? 1u : 0u);
+                }
                 // retire -> the smem slot may be overwritten (signals every CTA of the cluster)
                 mma_commit<kCtaGroup>(empty_bar + ring.bar, kEmptyMask);
             };
@@ -742,7 +759,7 @@ fp8_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
                 ++tile_iter;
                 mbar_wait(tmem_empty_bar + as * 8, aphase ^ 1);
                 tcgen05_fence_after();
-                idesc_base = make_idesc(128 * kCtaGroup, tile_n(t), kWMn ? 1 : 0, kXMn ? 1 : 0);
+                idesc_base = kBf16AB ? make_idesc_bf16(128 * kCtaGroup, tile_n(t)) : make_idesc(128 * kCtaGroup, tile_n(t), kWMn ? 1 : 0, kXMn ? 1 : 0);
                 const uint32_t tmem_d = tmem_base + as * kAccumColStride;
                 uint32_t kb = t.kb_begin;
                 for (; kb + 1 < t.kb_end; ++kb, ring.advance()) {        // every k-block but the last: 4 UMMAs
@@ -793,7 +810,7 @@ fp8_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
                 mbar_wait(full_bar + ring.bar, ring.phase);
                 const bool first = kb == t.kb_begin;
                 if (first && lane == 0) DGB_STAMP(3);
-                const bool do_w = (kb & sfw_mask) == 0 || first, do_x = (kb & sfx_mask) == 0 || first;
+                const bool do_w = !kBf16AB && ((kb & sfw_mask) == 0 || first), do_x = !kBf16AB && ((kb & sfx_mask) == 0 || first);
                 if (do_w | do_x) {
                     const uint32_t slot = smem_base + ring.slot;
                     if (do_w) retile(slot + off_sfw);

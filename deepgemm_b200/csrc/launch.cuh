@@ -75,6 +75,7 @@ struct GemmCall {
     int head_left = 0, head_mid = 0, head_right = 0;                     // fp8_gemm_nt_skip_head_mid
     bool swap_d = false;   // operands already exchanged by the caller (a = weights, b = tokens): the kernel writes D[lane][column]
     int forced_block_m = 0;
+    bool bf16_ab = false;   // BF16 operands without scale factors: k, lda, ldb are in BYTES (2 x elements), sfa / sfb unused
 };
 
 struct Maps {
@@ -144,5 +145,6 @@ int dispatch_dense_splitk(const GemmCall& c, const Config& cfg, const Maps& maps
 int dispatch_grouped(const GemmCall& c, const Config& cfg, const Maps& maps, const GemmParams& p);       // gemm_grouped.cu
 int dispatch_batched(const GemmCall& c, const Config& cfg, const Maps& maps, const GemmParams& p);       // gemm_batched.cu
 int dispatch_dense_swap(const GemmCall& c, const Config& cfg, const Maps& maps, const GemmParams& p);    // gemm_dense_swap.cu
+int dispatch_bf16(const GemmCall& c, const Config& cfg, const Maps& maps, const GemmParams& p);          // gemm_bf16.cu
 
 }  // namespace dgb200

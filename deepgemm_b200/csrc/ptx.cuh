@@ -261,6 +261,29 @@ DGB_DEVICE void mma_mxf8_block_scale(uint32_t tmem_d, uint64_t adesc, uint64_t b
             : "memory");
 }
 
+// D[tmem] (+)= A[smem] * B[smem]^T for 16-bit operands (kind::f16; BF16 here), 16 K-elements per instruction, FP32 accumulate
+template <int kCtaGroup>
+DGB_DEVICE void mma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    if constexpr (kCtaGroup == 1)
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "setp.ne.b32 p, %4, 0;\n"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+            "}\n" ::"r"(tmem_d),
+            "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+            : "memory");
+    else
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "setp.ne.b32 p, %4, 0;\n"
+            "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+            "}\n" ::"r"(tmem_d),
+            "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+            : "memory");
+}
+
 // Make all previously issued tcgen05 ops of this thread arrive on an mbarrier when they retire.
 // cta_group::2 form multicasts the arrival to the barrier at the same offset in both CTAs of the pair.
 template <int kCtaGroup>
@@ -325,6 +348,11 @@ constexpr uint32_t kLayoutSwizzle32B = 6;
 //   [24,29) M>>4 | [29,31) a_sf_id
 DGB_DEVICE constexpr uint32_t make_idesc(uint32_t umma_m, uint32_t umma_n, uint32_t a_mn_major, uint32_t b_mn_major) {
     return (a_mn_major << 15) | (b_mn_major << 16) | ((umma_n >> 3) << 17) | (1u << 23) | ((umma_m >> 4) << 24);
+}
+// 32-bit instruction descriptor for kind::f16 with BF16 x BF16 -> FP32, both operands K-major
+// (cute/arch/mma_sm100_desc.hpp:411-432: [4,6) c_format 1 = F32 | [7,10) a_format 1 = BF16 | [10,13) b_format | [17,23) N>>3 | [24,29) M>>4)
+DGB_DEVICE constexpr uint32_t make_idesc_bf16(uint32_t umma_m, uint32_t umma_n) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((umma_n >> 3) << 17) | ((umma_m >> 4) << 24);
 }
 DGB_DEVICE uint32_t idesc_with_sf_ids(uint32_t idesc, uint32_t a_sf_id, uint32_t b_sf_id) {
     return idesc | (b_sf_id << 4) | (a_sf_id << 29);

@@ -210,6 +210,95 @@ def fp8_einsum(expr: str, a: TensorPair, b: TensorPair, d: torch.Tensor, c: Opti
         raise RuntimeError(f'Unsupported einsum expression: {expr}')
 
 
+# ------------------------------------------------------------------------------------------------ BF16 operands
+def _check_bf16_k_major(t: torch.Tensor, what: str) -> None:
+    _require(t.dtype == torch.bfloat16, f'{what}.dtype == bfloat16')
+    if t.stride(-1) != 1:
+        raise RuntimeError(f'MN-major BF16 operands are not built in this library ({what} must have stride(-1) == 1); '
+                           'the reference supports them (csrc/apis/gemm.hpp:404-462)')
+    _require(t.size(-1) % 8 == 0 and t.stride(-2) % 8 == 0 and t.data_ptr() % 16 == 0, f'{what}: 16-byte aligned rows')
+
+
+def bf16_gemm_nt(a: torch.Tensor, b: torch.Tensor, d: torch.Tensor, c: Optional[torch.Tensor] = None,
+                 compiled_dims: str = 'nk') -> None:
+    """D = (C +) A @ B.T with BF16 A [M,K], B [N,K] (no scale factors), D BF16 or FP32. Reference: bf16_gemm_nt,
+    csrc/apis/gemm.hpp:404-438 (kernel deep_gemm/include/deep_gemm/impls/sm100_bf16_gemm.cuh). K-major operands only."""
+    _require(a.dim() == 2 and b.dim() == 2 and d.dim() == 2, 'a, b, d are 2-D')
+    _check_bf16_k_major(a, 'a'), _check_bf16_k_major(b, 'b')
+    _check_cd(d)
+    (m, k), (n, k_), (m_, n_) = a.shape, b.shape, d.shape
+    _require(m == m_ and n == n_ and k == k_, 'm == m_ and n == n_ and k == k_')
+    d_dtype = _d_dtype(d)
+    if _early_return(m, n, k, d, c):
+        return
+    check(lib().dgb200_bf16_gemm_nt(a.data_ptr(), b.data_ptr(), d.data_ptr(), m, n, k, a.stride(0), b.stride(0), d.stride(0),
+                                    d_dtype, int(c is not None), _stream()))
+
+
+def bf16_gemm_nn(a, b, d, c=None, compiled_dims='nk'):
+    bf16_gemm_nt(a, b.transpose(0, 1), d, c, compiled_dims)
+
+
+def bf16_gemm_tn(a, b, d, c=None, compiled_dims='mn'):
+    bf16_gemm_nt(a.transpose(0, 1), b.transpose(0, 1), d, c, compiled_dims)
+
+
+def bf16_gemm_tt(a, b, d, c=None, compiled_dims='mn'):
+    bf16_gemm_nt(a.transpose(0, 1), b, d, c, compiled_dims)
+
+
+def m_grouped_bf16_gemm_nt_contiguous(a: torch.Tensor, b: torch.Tensor, d: torch.Tensor, grouped_layout: torch.Tensor,
+                                      compiled_dims: str = 'nk', use_psum_layout: bool = False,
+                                      ensure_zero_padding: bool = True,
+                                      expected_m_for_psum_layout: Optional[int] = None) -> None:
+    """A [M_sum,K] BF16 rows grouped by expert, B [G,N,K] BF16, D [M_sum,N] BF16 (gemm.hpp:464-517)."""
+    _require(a.dim() == 2 and b.dim() == 3 and d.dim() == 2, 'a 2-D, b 3-D, d 2-D')
+    _check_bf16_k_major(a, 'a'), _check_bf16_k_major(b, 'b')
+    _require(b.stride(0) == b.size(1) * b.size(2) and b.stride(1) == b.size(2), 'b is densely batched')
+    _require(grouped_layout.is_contiguous() and grouped_layout.dtype == torch.int32, 'grouped_layout is contiguous int32')
+    (m, k), (num_groups, n, k_), (m_, n_) = a.shape, b.shape, d.shape
+    _require(m == m_ and n == n_ and k == k_, 'm == m_ and n == n_ and k == k_')
+    _require(n > 0 and k > 0 and num_groups > 0, 'n > 0 and k > 0 and num_groups > 0')
+    _require(d.dtype == torch.bfloat16, 'd.dtype == bfloat16')
+    if use_psum_layout:
+        _require(grouped_layout.dim() == 1 and grouped_layout.numel() == num_groups, 'grouped_layout is [num_groups]')
+    else:
+        _require(grouped_layout.dim() == 1 and grouped_layout.numel() == m, 'grouped_layout is [m]')
+        _require(expected_m_for_psum_layout is None, 'expected_m_for_psum_layout needs use_psum_layout')
+    _check_cd(d)
+    if m == 0:
+        return
+    check(lib().dgb200_m_grouped_bf16_gemm_nt_contiguous(
+        a.data_ptr(), b.data_ptr(), d.data_ptr(), grouped_layout.data_ptr(), num_groups, m, n, k, a.stride(0), b.stride(1), d.stride(0),
+        int(use_psum_layout), int(ensure_zero_padding), -1 if expected_m_for_psum_layout is None else int(expected_m_for_psum_layout),
+        _stream()))
+
+
+def m_grouped_bf16_gemm_nn_contiguous(a, b, d, grouped_layout, compiled_dims='nk', use_psum_layout=False, ensure_zero_padding=True):
+    m_grouped_bf16_gemm_nt_contiguous(a, b.transpose(1, 2), d, grouped_layout, compiled_dims, use_psum_layout, ensure_zero_padding, None)
+
+
+def m_grouped_bf16_gemm_nt_masked(a: torch.Tensor, b: torch.Tensor, d: torch.Tensor, masked_m: torch.Tensor, expected_m: int,
+                                  compiled_dims: str = 'nk') -> None:
+    """A [G,M_max,K], B [G,N,K] BF16, D [G,M_max,N] BF16; rows >= masked_m[g] are not written (gemm.hpp:528-564)."""
+    _require(a.dim() == 3 and b.dim() == 3 and d.dim() == 3, 'a, b, d are 3-D')
+    _check_bf16_k_major(a, 'a'), _check_bf16_k_major(b, 'b')
+    _require(a.is_contiguous() and b.is_contiguous() and d.is_contiguous(), 'a, b, d are contiguous')
+    _require(masked_m.is_contiguous() and masked_m.dtype == torch.int32, 'masked_m is contiguous int32')
+    (g, m, k), (g_, n, k_), (g__, m_, n_) = a.shape, b.shape, d.shape
+    _require(g == g_ == g__ == masked_m.numel(), 'group counts agree')
+    _require(m == m_ and n == n_ and k == k_, 'm == m_ and n == n_ and k == k_')
+    _require(expected_m > 0 and m > 0 and n > 0 and k > 0 and g > 0, 'positive sizes')
+    _require(d.dtype == torch.bfloat16, 'd.dtype == bfloat16')
+    check(lib().dgb200_m_grouped_bf16_gemm_nt_masked(a.data_ptr(), b.data_ptr(), d.data_ptr(), masked_m.data_ptr(), g, m, n, k,
+                                                     int(expected_m), _stream()))
+
+
+def k_grouped_bf16_gemm_tn_contiguous(*args, **kwargs) -> None:
+    """Weight-gradient form with both operands MN-major (gemm.hpp:566-609): not built for BF16 operands here."""
+    raise RuntimeError('k_grouped_bf16_gemm_tn_contiguous is not built in this library (MN-major BF16 operands)')
+
+
 def _t(pair: TensorPair, d0: int = 0, d1: int = 1) -> TensorPair:
     return pair[0].transpose(d0, d1), pair[1].transpose(d0, d1)
 

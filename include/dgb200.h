@@ -137,6 +137,21 @@ int dgb200_fp8_bmm(const void* a, const int32_t* sfa, const void* b, const int32
 int dgb200_per_token_cast_to_fp8(const void* x, int64_t ldx, void* q, int64_t ldq, int32_t* sf, int sf_stride,
                                  int m, int k, int gran_k, void* stream);
 
+/* BF16 x BF16 GEMMs without scale factors on the same kernel skeleton (tcgen05.mma kind::f16), K-major operands only:
+ *   dgb200_bf16_gemm_nt                       -- bf16_gemm_nt, csrc/apis/gemm.hpp:404-438 (+ nn/tn/tt when the views are K-major)
+ *   dgb200_m_grouped_bf16_gemm_nt_contiguous  -- m_grouped_bf16_gemm_nt_contiguous, gemm.hpp:464-517 (layouts as the FP8 form)
+ *   dgb200_m_grouped_bf16_gemm_nt_masked      -- m_grouped_bf16_gemm_nt_masked, gemm.hpp:528-564
+ * a [m, k], b [n, k] (grouped: [G, n, k]) BF16 with row pitches lda / ldb in ELEMENTS (multiples of 8), k % 8 == 0.
+ * MN-major BF16 operands and k_grouped_bf16_gemm_tn_contiguous are not built (DGB200_ERR_UNSUPPORTED in the Python layer). */
+int dgb200_bf16_gemm_nt(const void* a, const void* b, void* d, int m, int n, int k, int64_t lda, int64_t ldb, int64_t ldd,
+                        int d_dtype, int accumulate, void* stream);
+int dgb200_m_grouped_bf16_gemm_nt_contiguous(const void* a, const void* b, void* d, const int32_t* grouped_layout,
+                                             int num_groups, int m, int n, int k, int64_t lda, int64_t ldb, int64_t ldd,
+                                             int use_psum_layout, int ensure_zero_padding, int expected_m_for_psum_layout,
+                                             void* stream);
+int dgb200_m_grouped_bf16_gemm_nt_masked(const void* a, const void* b, void* d, const int32_t* masked_m, int num_groups,
+                                         int m_max, int n, int k, int expected_m, void* stream);
+
 /* Rows of A grouped by expert          -- m_grouped_fp8_fp4_gemm_nt_contiguous, csrc/apis/gemm.hpp:166-232.
  *   a [m, k], b [num_groups, n, k], d [m, n] bf16
  *   use_psum_layout == 0: grouped_layout int32[m], expert id per row, -1 for padding rows

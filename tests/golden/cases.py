@@ -98,6 +98,16 @@ def make_masked(mean_m, utils, g=256, m_max=128, n=7168, k=2048, weights=None):
     return dict(a=qa, b=weights, masked_m=masked, expected_m=int(1.2 * mean_m))
 
 
+BF16_CASES = [(128, 2112, 7168), (4096, 7168, 2048), (64, 576, 7168)]
+
+
+def make_bf16(m, n, k):
+    gen = torch.Generator(device='cuda').manual_seed(_seed_of(f'bf16_{m}x{n}x{k}'))
+    a = torch.randn((m, k), device='cuda', dtype=torch.bfloat16, generator=gen)
+    b = torch.randn((n, k), device='cuda', dtype=torch.bfloat16, generator=gen)
+    return a, b
+
+
 def digest(t: torch.Tensor) -> str:
     """SHA-256 of the tensor's bytes in row-major order."""
     return hashlib.sha256(t.contiguous().cpu().view(torch.uint8).numpy().tobytes()).hexdigest()

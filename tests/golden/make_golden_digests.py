@@ -20,7 +20,7 @@ sys.path.insert(0, REPO)
 sys.path.insert(0, HERE)
 
 
-def run_part(part, parts):
+def run_part(part, parts, only=None):
     import torch
     os.environ.setdefault('DG_JIT_CACHE_DIR', '/tmp/dg_ref_cache')
     os.environ.setdefault('CUDA_HOME', '/usr/local/cuda')
@@ -33,9 +33,11 @@ def run_part(part, parts):
     assert 'oracle/_ref' in ref.__file__
     out = {}
     work = [('normal', c) for c in cases.normal_cases()] + [('contiguous', mm) for mm in (64, 128)] + \
-           [('masked', mm) for mm in (16, 64, 96)]
+           [('masked', mm) for mm in (16, 64, 96)] + [('bf16', shp) for shp in cases.BF16_CASES]
     for i, (kind, spec) in enumerate(work):
         if i % parts != part:
+            continue
+        if only and kind not in only:
             continue
         if kind == 'normal':
             qa, qb, c, d = cases.make_normal(spec, utils)
@@ -44,6 +46,12 @@ def run_part(part, parts):
             ref.fp8_gemm_nt(qa, qb, d, c=d if c is not None else None)
             torch.cuda.synchronize()
             out[spec['name']] = cases.digest(d)
+        elif kind == 'bf16':
+            a, b = cases.make_bf16(*spec)
+            d = torch.empty((spec[0], spec[1]), device='cuda', dtype=torch.bfloat16)
+            ref.bf16_gemm_nt(a, b, d)
+            torch.cuda.synchronize()
+            out['bf16_%dx%dx%d' % spec] = cases.digest(d)
         elif kind == 'contiguous':
             p = cases.make_contiguous(spec, utils)
             d = torch.zeros((p['m'], p['b'][0].shape[1]), device='cuda', dtype=torch.bfloat16)
@@ -68,17 +76,23 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--part', default='')
     ap.add_argument('--parts', type=int, default=6)
+    ap.add_argument('--only', default='', help='comma list of kinds (normal, contiguous, masked, bf16); merges into the committed file')
     args = ap.parse_args()
     os.makedirs(os.path.join(REPO, 'gpurun_out'), exist_ok=True)
     if args.part:
         part, parts = (int(x) for x in args.part.split('/'))
-        res = run_part(part, parts)
+        res = run_part(part, parts, args.only.split(',') if args.only else None)
         with open(os.path.join(REPO, 'gpurun_out', f'gpu_digests.part{part}.json'), 'w') as f:
             json.dump(res, f)
         return
-    procs = [subprocess.Popen([sys.executable, os.path.abspath(__file__), '--part', f'{i}/{args.parts}']) for i in range(args.parts)]
+    extra = ['--only', args.only] if args.only else []
+    procs = [subprocess.Popen([sys.executable, os.path.abspath(__file__), '--part', f'{i}/{args.parts}'] + extra) for i in range(args.parts)]
     rc = [p.wait() for p in procs]
     merged = {}
+    committed = os.path.join(HERE, 'gpu_digests.json')
+    if args.only and os.path.exists(committed):
+        with open(committed) as f:
+            merged.update({k: v for k, v in json.load(f).items() if k != '_meta'})
     for i in range(args.parts):
         path = os.path.join(REPO, 'gpurun_out', f'gpu_digests.part{i}.json')
         if os.path.exists(path):

@@ -1,0 +1,155 @@
+"""GPU parity tests of the BF16-operand GEMMs (fp8_gemm_kernel<..., kBf16AB>; reference bf16_gemm_nt,
+m_grouped_bf16_gemm_nt_contiguous, m_grouped_bf16_gemm_nt_masked, csrc/apis/gemm.hpp:404-564).
+
+Plain PyTorch FP32 reference for a floating-point kernel: BF16 inputs are exact in FP32, so `a.float() @ b.float().T` (TF32
+off) differs from the kernel only by the FP32 accumulation order inside the tensor core; the reference's own bound for its
+BF16 kernels is calc_diff < 1e-5 (tests/test_bf16.py). Against the reference's kernel on the same inputs the output is
+bit-identical (digests in tests/golden/gpu_digests.json, keys `bf16_*`, when generated)."""
+import json
+import os
+import random
+import sys
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, 'golden'))
+
+
+@pytest.fixture(scope='module')
+def dg():
+    if not torch.cuda.is_available():
+        pytest.skip('needs a GPU')
+    import deepgemm_b200
+    from deepgemm_b200 import _lib
+    _lib.lib()
+    torch.backends.cuda.matmul.allow_tf32 = False
+    return deepgemm_b200
+
+
+def _close(d, ref, what=''):
+    from deepgemm_b200.testing import calc_diff
+    assert not torch.isnan(d.float()).any(), what
+    assert calc_diff(d, ref) < 1e-5, what
+    if d.dtype == torch.float32:
+        assert ((d - ref).abs().max() / ref.abs().max().clamp(min=1.0)) < 1e-5, what
+    else:
+        err = (d.float() - ref).abs()
+        assert bool((err <= ref.abs() * 2.0 ** -7 + 1e-5 * ref.abs().max()).all()), what
+
+
+@pytest.mark.parametrize('m,n,k', [(128, 128, 128), (1, 576, 512), (64, 4096, 7168), (300, 2112, 1536), (4096, 4096, 2048), (97, 136, 200)])
+@pytest.mark.parametrize('out_dtype', [torch.bfloat16, torch.float32])
+def test_bf16_gemm_nt_matches_fp32_matmul(dg, m, n, k, out_dtype):
+    gen = torch.Generator(device='cuda').manual_seed(m + n + k)
+    a = torch.randn((m, k), device='cuda', dtype=torch.bfloat16, generator=gen)
+    b = torch.randn((n, k), device='cuda', dtype=torch.bfloat16, generator=gen)
+    buf = torch.full((m + 8, n + 16), 222.0, device='cuda', dtype=out_dtype)
+    d = buf[:m, :n]
+    dg.bf16_gemm_nt(a, b, d)
+    ref = a.float() @ b.float().t()
+    _close(d, ref, f'{m}x{n}x{k}')
+    assert bool((buf[m:] == 222.0).all()) and bool((buf[:, n:] == 222.0).all())
+    # accumulate into C
+    c = (torch.randn((m, n), device='cuda') * 4).to(out_dtype)
+    d2 = c.clone()
+    dg.bf16_gemm_nt(a, b, d2, c=d2)
+    want = (ref.to(torch.bfloat16).float() + c.float()) if out_dtype == torch.bfloat16 else ref + c
+    err = (d2.float() - want).abs()
+    mag = ref.abs() + c.float().abs()
+    assert bool((err <= mag * 2.0 ** -6 + 1e-5 * mag.max()).all())
+
+
+def test_bf16_gemm_every_tile_config_gives_identical_bits(dg, monkeypatch):
+    m, n, k = 500, 1024, 1024
+    a = torch.randn((m, k), device='cuda', dtype=torch.bfloat16)
+    b = torch.randn((n, k), device='cuda', dtype=torch.bfloat16)
+    base = torch.empty((m, n), device='cuda', dtype=torch.bfloat16)
+    dg.bf16_gemm_nt(a, b, base)
+    for bm, st in ((16, 3), (64, 0), (128, 0), (240, 0), (208, 2)):
+        monkeypatch.setenv('DGB200_BLOCK_M', str(bm))
+        if st:
+            monkeypatch.setenv('DGB200_STAGES', str(st))
+        d = torch.empty_like(base)
+        dg.bf16_gemm_nt(a, b, d)
+        assert torch.equal(d, base), (bm, st)
+        monkeypatch.delenv('DGB200_STAGES', raising=False)
+
+
+def test_bf16_transposed_wrappers_and_mn_major_rejection(dg):
+    a = torch.randn((256, 512), device='cuda', dtype=torch.bfloat16)
+    b = torch.randn((384, 512), device='cuda', dtype=torch.bfloat16)
+    d0 = torch.empty((256, 384), device='cuda', dtype=torch.bfloat16)
+    dg.bf16_gemm_nt(a, b, d0)
+    d1 = torch.empty_like(d0)
+    dg.bf16_gemm_nn(a, b.t(), d1)                               # B given as the [K, N] view of a K-major tensor
+    assert torch.equal(d0, d1)
+    d2 = torch.empty_like(d0)
+    dg.bf16_gemm_tt(a.t(), b, d2)
+    assert torch.equal(d0, d2)
+    with pytest.raises(RuntimeError):
+        dg.bf16_gemm_nt(a, b.t().contiguous().t(), d1)        # genuinely MN-major B: not built
+    with pytest.raises(RuntimeError):
+        dg.k_grouped_bf16_gemm_tn_contiguous(a, b, d0, [512], None)
+
+
+@pytest.mark.parametrize('use_psum', [False, True])
+def test_m_grouped_bf16_contiguous(dg, use_psum):
+    random.seed(3 + use_psum)
+    g, n, k, alignment = 6, 768, 1024, 128
+    ms = [int(150 * random.uniform(0.3, 1.7)) for _ in range(g)]
+    ms[2] = 0
+    aligned = [(x + alignment - 1) // alignment * alignment for x in ms]
+    m = sum(aligned)
+    a = torch.randn((m, k), device='cuda', dtype=torch.bfloat16)
+    b = torch.randn((g, n, k), device='cuda', dtype=torch.bfloat16)
+    layout = torch.empty(g if use_psum else m, device='cuda', dtype=torch.int32)
+    valid = torch.zeros(m, dtype=torch.bool, device='cuda')
+    expert = torch.zeros(m, dtype=torch.long, device='cuda')
+    s = 0
+    for i, (mi, ai) in enumerate(zip(ms, aligned)):
+        if use_psum:
+            layout[i] = s + mi
+        else:
+            layout[s:s + mi] = i
+            layout[s + mi:s + ai] = -1
+        valid[s:s + mi] = True
+        expert[s:s + ai] = i
+        s += ai
+    d = torch.full((m, n), float('nan'), device='cuda', dtype=torch.bfloat16)
+    dg.m_grouped_bf16_gemm_nt_contiguous(a, b, d, layout, use_psum_layout=use_psum)
+    ref = torch.einsum('mk,mnk->mn', a.float(), b.float()[expert])
+    _close(d[valid], ref[valid], f'contiguous psum={use_psum}')
+    if use_psum:
+        assert bool((d[~valid] == 0).all())
+
+
+def test_m_grouped_bf16_masked(dg):
+    g, m_max, n, k = 8, 192, 512, 1024
+    a = torch.randn((g, m_max, k), device='cuda', dtype=torch.bfloat16)
+    b = torch.randn((g, n, k), device='cuda', dtype=torch.bfloat16)
+    masked_m = torch.tensor([5, 192, 0, 64, 100, 17, 128, 33], device='cuda', dtype=torch.int32)
+    d = torch.full((g, m_max, n), 1234.0, device='cuda', dtype=torch.bfloat16)
+    dg.m_grouped_bf16_gemm_nt_masked(a, b, d, masked_m, 64)
+    ref = torch.einsum('gmk,gnk->gmn', a.float(), b.float())
+    for gi, mg in enumerate(masked_m.tolist()):
+        if mg:
+            _close(d[gi, :mg], ref[gi, :mg], f'masked {gi}')
+        assert bool((d[gi, mg:] == 1234.0).all())
+
+
+@pytest.mark.parametrize('m,n,k', [(128, 2112, 7168), (4096, 7168, 2048), (64, 576, 7168)])
+def test_bf16_matches_the_reference_kernel_bit_for_bit(dg, m, n, k):
+    path = os.path.join(HERE, 'golden', 'gpu_digests.json')
+    key = f'bf16_{m}x{n}x{k}'
+    digests = json.load(open(path)) if os.path.exists(path) else {}
+    if key not in digests:
+        pytest.skip(f'no digest for {key}')
+    import cases
+    a, b = cases.make_bf16(m, n, k)
+    d = torch.empty((m, n), device='cuda', dtype=torch.bfloat16)
+    dg.bf16_gemm_nt(a, b, d)
+    torch.cuda.synchronize()
+    assert cases.digest(d) == digests[key]

@@ -1,0 +1,24 @@
+"""BF16-operand GEMMs beside the reference's BF16 kernel (kernel time by the profiler, cold L2). Development tool."""
+import json
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch  # noqa: E402
+
+from tools.bringup import import_reference  # noqa: E402
+import deepgemm_b200 as dg  # noqa: E402
+from deepgemm_b200.testing import bench_kineto  # noqa: E402
+
+ref = import_reference()
+for (m, n, k) in [(64, 4096, 7168), (128, 2112, 7168), (512, 4096, 7168), (4096, 4096, 7168), (4096, 7168, 2048), (4096, 24576, 1536)]:
+    a = torch.randn((m, k), device='cuda', dtype=torch.bfloat16)
+    b = torch.randn((n, k), device='cuda', dtype=torch.bfloat16)
+    d0, d1 = torch.empty((m, n), device='cuda', dtype=torch.bfloat16), torch.empty((m, n), device='cuda', dtype=torch.bfloat16)
+    ref.bf16_gemm_nt(a, b, d0)
+    dg.bf16_gemm_nt(a, b, d1)
+    torch.cuda.synchronize()
+    t_ref = bench_kineto(lambda: ref.bf16_gemm_nt(a, b, d0), 'gemm', num_tests=10)
+    t_our = bench_kineto(lambda: dg.bf16_gemm_nt(a, b, d1), 'fp8_gemm_kernel', num_tests=10)
+    print(json.dumps({'m': m, 'n': n, 'k': k, 'bitwise_equal': bool(torch.equal(d0, d1)), 'ours_us': round(t_our * 1e6, 2), 'ref_us': round(t_ref * 1e6, 2),
+                      'ours_tflops': round(2.0 * m * n * k / t_our / 1e12, 1), 'ref_tflops': round(2.0 * m * n * k / t_ref / 1e12, 1)}), flush=True)
