@@ -7,7 +7,7 @@ Importing this package does not touch CUDA (the reference guarantees the same, t
 """
 from . import testing, utils  # noqa: F401
 from .gemm import (  # noqa: F401
-    bf16_gemm_nn, bf16_gemm_nt, bf16_gemm_tn, bf16_gemm_tt, k_grouped_bf16_gemm_tn_contiguous,
+    bf16_gemm_nn, bf16_gemm_nt, bf16_gemm_tn, bf16_gemm_tt, einsum, k_grouped_bf16_gemm_tn_contiguous,
     m_grouped_bf16_gemm_nn_contiguous, m_grouped_bf16_gemm_nt_contiguous, m_grouped_bf16_gemm_nt_masked,
     fp8_bmm, fp8_einsum, fp8_gemm_nn, fp8_gemm_nt, fp8_gemm_nt_skip_head_mid, fp8_gemm_tn, fp8_gemm_tt,
     k_grouped_fp8_gemm_nt_contiguous, k_grouped_fp8_gemm_tn_contiguous,

@@ -91,8 +91,10 @@ SIGNATURES = {
     'dgb200_fp8_gemm_nt_skip_head_mid': (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _L, _L, _L, _I, _I, _I, _I, _I, _I, _P]),
     'dgb200_fp8_bmm': (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _L, _L, _L, _L, _L, _L, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
     'dgb200_per_token_cast_to_fp8': (_I, [_P, _L, _P, _L, _P, _I, _I, _I, _I, _P]),
-    'dgb200_bf16_gemm_nt': (_I, [_P, _P, _P, _I, _I, _I, _L, _L, _L, _I, _I, _P]),
-    'dgb200_m_grouped_bf16_gemm_nt_contiguous': (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _L, _L, _L, _I, _I, _I, _P]),
+    'dgb200_bf16_gemm_nt': (_I, [_P, _P, _P, _I, _I, _I, _L, _L, _L, _I, _I, _I, _I, _P]),
+    'dgb200_m_grouped_bf16_gemm_nt_contiguous': (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _L, _L, _L, _I, _I, _I, _I, _P]),
+    'dgb200_bf16_bmm': (_I, [_P, _P, _P, _I, _I, _I, _I, _L, _L, _L, _L, _L, _L, _I, _P]),
+    'dgb200_k_grouped_bf16_gemm_tn_contiguous': (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
     'dgb200_m_grouped_bf16_gemm_nt_masked': (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
     'dgb200_debug_fp8_peak': (_I, [_I, _I, _I, _P]),
     'dgb200_m_grouped_fp8_gemm_nt_contiguous': (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _L, _L, _L, _I, _I, _I,

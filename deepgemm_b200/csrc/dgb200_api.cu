@@ -469,7 +469,8 @@ int run_gemm(const GemmCall& c) {
     if (cfg.csplit) DGB_REQUIRE(cfg.block_m % (16 * cfg.csplit) == 0 && (cfg.cluster == cfg.csplit || cfg.cluster == 2 * cfg.csplit));
     if (c.type == kMContiguous || c.type == kMContiguousPsum) DGB_REQUIRE(c.alignment % cfg.block_m == 0);
     cfg.overlap_producer = c.arrival != nullptr;
-    if (c.x_mn) DGB_REQUIRE(load_m % 32 == 0);
+    const int el = c.bf16_ab ? 2 : 1;             // operand bytes per element (K-major operands are addressed in bytes anyway)
+    if (c.x_mn) DGB_REQUIRE((load_m * el) % 32 == 0);
 
     const int num_kp_a = ceil_div(c.k, c.gran_k_a * 4), num_kp_b = ceil_div(c.k, c.gran_k_b * 4);
     const int b_groups = (c.type == kDense || k_grouped || batched) ? 1 : c.groups;      // groups folded into the weight map's rows
@@ -479,7 +480,8 @@ int run_gemm(const GemmCall& c) {
     const uint64_t sfb_krows = c.sfb_krows > 0 ? (uint64_t)c.sfb_krows : (uint64_t)num_kp_b * sfb_groups;
 
     // Tensor maps. K-major operand [rows, K]: box 128 K-bytes x rows. MN-major operand [K rows, MN]: box S MN-bytes x
-    // 128 K-rows, S = one swizzle atom (128 for the weights; the widest of 128/64/32 that divides load_m for tokens).
+    // 128 / el K-rows, S = one swizzle atom (128 for the weights; the widest of 128/64/32 that divides load_m for tokens).
+    // BF16 operands keep the UINT8 maps: whichever extent is contiguous is addressed in bytes.
     // Batched problems add the batch as a third dimension with its own pitch (box depth 1), so permuted views
     // (fp8_einsum) need no copy.
     Maps maps;
@@ -487,18 +489,18 @@ int run_gemm(const GemmCall& c) {
     int x_swizzle = 128;
     const uint64_t nb = batched ? (uint64_t)c.groups : 0;     // rank-3 maps only for the batched type
     if (c.x_mn) {
-        x_swizzle = load_m % 128 == 0 ? 128 : (load_m % 64 == 0 ? 64 : 32);
+        x_swizzle = (load_m * el) % 128 == 0 ? 128 : ((load_m * el) % 64 == 0 ? 64 : 32);
         const CUtensorMapSwizzle sw = x_swizzle == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
                                       : (x_swizzle == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
-        if (int e = make_map(&maps.x, c.a, CU_TENSOR_MAP_DATA_TYPE_UINT8, c.m, c.a_rows, c.lda, x_swizzle, kBlockK, sw, nb,
+        if (int e = make_map(&maps.x, c.a, CU_TENSOR_MAP_DATA_TYPE_UINT8, (uint64_t)c.m * el, c.a_rows, c.lda, x_swizzle, kBlockK / el, sw, nb,
                              c.batch_stride_a)) return e;
     } else {
         if (int e = make_map(&maps.x, c.a, CU_TENSOR_MAP_DATA_TYPE_UINT8, c.k, c.a_rows, c.lda, kBlockK, load_m,
                              CU_TENSOR_MAP_SWIZZLE_128B, nb, c.batch_stride_a)) return e;
     }
     if (c.w_mn) {
-        const uint64_t k_rows = k_grouped ? (uint64_t)c.a_rows : (uint64_t)c.k * b_groups;
-        if (int e = make_map(&maps.w, c.b, CU_TENSOR_MAP_DATA_TYPE_UINT8, c.n, k_rows, c.ldb, kBlockN, kBlockK,
+        const uint64_t k_rows = k_grouped ? (uint64_t)c.a_rows : (uint64_t)(c.k / el) * b_groups;
+        if (int e = make_map(&maps.w, c.b, CU_TENSOR_MAP_DATA_TYPE_UINT8, (uint64_t)c.n * el, k_rows, c.ldb, kBlockN, kBlockK / el,
                              CU_TENSOR_MAP_SWIZZLE_128B, nb, c.batch_stride_b)) return e;
     } else {
         if (int e = make_map(&maps.w, c.b, CU_TENSOR_MAP_DATA_TYPE_UINT8, c.k, (uint64_t)c.n * b_groups, c.ldb, kBlockK,
@@ -556,7 +558,8 @@ int run_gemm(const GemmCall& c) {
         const int rest = std::max(0, c.m - cfg.num_tall * cfg.block_m);
         p.num_m_blocks = cfg.num_tall + ceil_div(rest, cfg.block_m_low);
     }
-    p.m_alignment = std::max(1, c.alignment);
+    p.k_shift = c.bf16_ab ? 1 : 0;
+    p.m_alignment = std::max(1, c.alignment) << (k_grouped ? p.k_shift : 0);
     p.zero_padding = c.zero_padding;
     p.x_swizzle = x_swizzle;
     p.sf_k_span = 4 * c.gran_k_a;
@@ -570,7 +573,7 @@ int run_gemm(const GemmCall& c) {
                 c.type, c.m, c.n, c.k, c.groups, (int)c.x_mn, (int)c.w_mn, cfg.block_m, cfg.cluster, cfg.stages, cfg.num_sms,
                 cfg.smem_bytes, cfg.csplit ? -cfg.num_splits : cfg.num_splits, cfg.tma_store);
 
-    if (c.bf16_ab) return dispatch_bf16(c, cfg, maps, p);
+    if (c.bf16_ab) return (c.x_mn || c.w_mn || batched) ? dispatch_bf16_mn(c, cfg, maps, p) : dispatch_bf16(c, cfg, maps, p);
     switch (c.type) {
         case kDense:
             if (c.swap_d) return dispatch_dense_swap(c, cfg, maps, p);
@@ -775,26 +778,31 @@ int dgb200_m_grouped_fp8_gemm_nt_contiguous(const void* a, const int32_t* sfa, c
     return run_gemm(c);
 }
 
-// ---- BF16 operands (no scale factors): K-major, byte-addressed K (see fp8_gemm_kernel.cuh, kBf16AB)
+// ---- BF16 operands (no scale factors): the contiguous extent of each operand is byte-addressed (see fp8_gemm_kernel.cuh, kBf16AB)
 static void bf16_common(GemmCall& c, int k, int64_t lda, int64_t ldb) {
     c.bf16_ab = true;
     c.sfa = c.sfb = nullptr, c.sfa_stride = c.sfb_stride = c.sfa_cols = c.sfb_cols = 4;
     c.gran_k_a = c.gran_k_b = 128;
     c.k = 2 * k, c.lda = 2 * lda, c.ldb = 2 * ldb;        // bytes
+    c.batch_stride_a *= 2, c.batch_stride_b *= 2;
     c.workspace = nullptr, c.workspace_bytes = 0;
 }
 
 int dgb200_bf16_gemm_nt(const void* a, const void* b, void* d, int m, int n, int k, int64_t lda, int64_t ldb, int64_t ldd,
-                        int d_dtype, int accumulate, void* stream) {
+                        int major_a, int major_b, int d_dtype, int accumulate, void* stream) {
     DGB_REQUIRE(m >= 0 && n >= 0 && k >= 0);
     if (m == 0 || n == 0) return DGB200_OK;
-    DGB_REQUIRE(k > 0 && k % 8 == 0);                    // 16-byte rows for TMA
+    DGB_REQUIRE(k > 0);
     DGB_REQUIRE(d_dtype == DGB200_BF16 || d_dtype == DGB200_FP32);
-    DGB_REQUIRE(lda >= k && ldb >= k && ldd >= n);
+    DGB_REQUIRE(major_a == DGB200_K_MAJOR || major_a == DGB200_MN_MAJOR);
+    DGB_REQUIRE(major_b == DGB200_K_MAJOR || major_b == DGB200_MN_MAJOR);
     GemmCall c{};
     c.type = kDense;
+    c.x_mn = major_a == DGB200_MN_MAJOR, c.w_mn = major_b == DGB200_MN_MAJOR;
+    DGB_REQUIRE(lda >= (c.x_mn ? m : k) && ldb >= (c.w_mn ? n : k) && ldd >= n);
+    DGB_REQUIRE((c.x_mn ? m : k) % 8 == 0 && (c.w_mn ? n : k) % 8 == 0);     // 16-byte rows for TMA
     c.a = a, c.b = b, c.d = d, c.grouped_layout = nullptr;
-    c.m = m, c.n = n, c.groups = 1, c.a_rows = m, c.ldd = ldd;
+    c.m = m, c.n = n, c.groups = 1, c.a_rows = c.x_mn ? k : m, c.ldd = ldd;
     c.d_dtype = d_dtype, c.accumulate = accumulate != 0;
     c.expected_m = m, c.alignment = 1, c.zero_padding = 0;
     c.stream = static_cast<cudaStream_t>(stream);
@@ -803,13 +811,17 @@ int dgb200_bf16_gemm_nt(const void* a, const void* b, void* d, int m, int n, int
 }
 
 int dgb200_m_grouped_bf16_gemm_nt_contiguous(const void* a, const void* b, void* d, const int32_t* grouped_layout, int num_groups,
-                                             int m, int n, int k, int64_t lda, int64_t ldb, int64_t ldd, int use_psum_layout,
-                                             int ensure_zero_padding, int expected_m_for_psum_layout, void* stream) {
+                                             int m, int n, int k, int64_t lda, int64_t ldb, int64_t ldd, int major_b,
+                                             int use_psum_layout, int ensure_zero_padding, int expected_m_for_psum_layout,
+                                             void* stream) {
     DGB_REQUIRE(m >= 0);
     DGB_REQUIRE(n > 0 && k > 0 && k % 8 == 0 && num_groups > 0);
     if (m == 0) return DGB200_OK;
-    DGB_REQUIRE(grouped_layout != nullptr && lda >= k && ldb >= k && ldd >= n);
+    DGB_REQUIRE(major_b == DGB200_K_MAJOR || major_b == DGB200_MN_MAJOR);
     GemmCall c{};
+    c.w_mn = major_b == DGB200_MN_MAJOR;     // B [G, K, N]: N contiguous, ldb = pitch of a K row
+    DGB_REQUIRE(grouped_layout != nullptr && lda >= k && ldb >= (c.w_mn ? n : k) && ldd >= n);
+    DGB_REQUIRE(!c.w_mn || n % 8 == 0);
     c.type = use_psum_layout ? kMContiguousPsum : kMContiguous;
     c.a = a, c.b = b, c.d = d, c.grouped_layout = grouped_layout;
     c.m = m, c.n = n, c.groups = num_groups, c.a_rows = m, c.ldd = ldd;
@@ -834,6 +846,47 @@ int dgb200_m_grouped_bf16_gemm_nt_masked(const void* a, const void* b, void* d, 
     c.expected_m = std::min(expected_m, m_max), c.alignment = 1, c.zero_padding = 0;
     c.stream = static_cast<cudaStream_t>(stream);
     bf16_common(c, k, k, k);
+    return run_gemm(c);
+}
+
+int dgb200_bf16_bmm(const void* a, const void* b, void* d, int batch, int m, int n, int k, int64_t lda, int64_t ldb, int64_t ldd,
+                    int64_t batch_stride_a, int64_t batch_stride_b, int64_t batch_stride_d, int major_b, void* stream) {
+    DGB_REQUIRE(batch >= 0 && m >= 0 && n >= 0 && k > 0);
+    if (batch == 0 || m == 0 || n == 0) return DGB200_OK;
+    DGB_REQUIRE(major_b == DGB200_K_MAJOR || major_b == DGB200_MN_MAJOR);
+    GemmCall c{};
+    c.type = kBatched;
+    c.w_mn = major_b == DGB200_MN_MAJOR;
+    DGB_REQUIRE(lda >= k && ldb >= (c.w_mn ? n : k) && ldd >= n);
+    DGB_REQUIRE(k % 8 == 0 && (!c.w_mn || n % 8 == 0));
+    DGB_REQUIRE(batch_stride_a % 8 == 0 && batch_stride_b % 8 == 0 && batch_stride_a > 0 && batch_stride_b > 0 && batch_stride_d > 0);
+    c.a = a, c.b = b, c.d = d, c.grouped_layout = nullptr;
+    c.m = m, c.n = n, c.groups = batch, c.a_rows = m, c.ldd = ldd;
+    c.batch_stride_a = batch_stride_a, c.batch_stride_b = batch_stride_b, c.batch_stride_d = batch_stride_d;
+    c.d_dtype = DGB200_BF16, c.accumulate = 0;
+    c.expected_m = m, c.alignment = 1, c.zero_padding = 0;
+    c.stream = static_cast<cudaStream_t>(stream);
+    bf16_common(c, k, lda, ldb);
+    return run_gemm(c);
+}
+
+int dgb200_k_grouped_bf16_gemm_tn_contiguous(const void* a, const void* b, float* d, const int32_t* grouped_layout, int num_groups,
+                                             int m, int n, int sum_k, int use_psum_layout, void* stream) {
+    DGB_REQUIRE(num_groups > 0 && m >= 0 && n >= 0 && sum_k >= 0);
+    if (m == 0 || n == 0 || sum_k == 0) return DGB200_OK;            // D already holds C (gemm.hpp:592-593)
+    DGB_REQUIRE(grouped_layout != nullptr);
+    DGB_REQUIRE(m % 8 == 0 && n % 8 == 0);                           // 16-byte rows of the [sum_k, m] / [sum_k, n] operands
+    const int k_alignment = rt().mk_alignment;
+    DGB_REQUIRE(k_alignment % 32 == 0);                              // gemm.hpp:580
+    GemmCall c{};
+    c.type = use_psum_layout ? kKGroupedPsum : kKGrouped;
+    c.x_mn = c.w_mn = true;
+    c.a = a, c.b = b, c.d = d, c.grouped_layout = grouped_layout;
+    c.m = m, c.n = n, c.groups = num_groups, c.a_rows = sum_k, c.ldd = n;
+    c.d_dtype = DGB200_FP32, c.accumulate = 1;
+    c.expected_m = m, c.alignment = k_alignment, c.zero_padding = 0;
+    c.stream = static_cast<cudaStream_t>(stream);
+    bf16_common(c, sum_k, m, n);
     return run_gemm(c);
 }
 

@@ -94,6 +94,7 @@ struct GemmParams {
     uint32_t zero_padding;      // psum: write zeros to [end, aligned end)
     uint32_t x_swizzle;         // MN-major tokens: swizzle width in bytes (128 / 64 / 32) = rows of one TMA box
     uint32_t sf_k_span;         // k-grouped: K elements covered by one packed SF word (4 * gran_k)
+    uint32_t k_shift;           // k-grouped: log2(bytes per operand element); the group sizes arrive in elements, K is walked in bytes
     uint64_t d_batch_stride;    // batched: elements between consecutive batches of D (0 otherwise)
     // Head-split output remap (fp8_gemm_nt_skip_head_mid, attention.hpp:19-74 / epilogue/transform.cuh:15-22): output
     // column n is stored at n + (n + head_right) / head_lr * head_mid, i.e. every (left | right) head of the GEMM's N
@@ -188,7 +189,7 @@ struct Scheduler {
             // groups are walked in order; every non-empty group contributes num_m_blocks * num_n_units tiles
             const uint32_t per_group = p.num_m_blocks * num_n_units;
             auto load_group = [&]() {
-                const uint32_t v = static_cast<uint32_t>(max(0, __ldg(p.grouped_layout + g)));
+                const uint32_t v = static_cast<uint32_t>(max(0, __ldg(p.grouped_layout + g))) << p.k_shift;
                 if constexpr (kGemmType == kKGroupedPsum) {
                     k_start = (k_end + p.m_alignment - 1) / p.m_alignment * p.m_alignment;
                     k_end = max(k_start, v);
@@ -478,7 +479,11 @@ fp8_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
                   "the TMA-store epilogue is built for plain BF16 output tiles");
     static_assert(!kSwapD || (kGemmType == kDense && !kXMn && !kWMn && !kSplitK && !kCSplit && kCluster <= 2),
                   "the transposed-output orientation is built for plain dense K-major problems");
-    static_assert(!kBf16AB || (!kXMn && !kWMn && !kSplitK && !kCSplit && !kSwapD && kCluster <= 2), "BF16 operands: K-major, plain kernels");
+    static_assert(!kBf16AB || (!kSplitK && !kCSplit && !kSwapD && kCluster <= 2), "BF16 operands: plain kernels");
+    // Operand bytes per element, and what one pipeline stage / one UMMA covers along K in ELEMENTS (= rows of an MN-major
+    // operand): FP8 128 / 32, BF16 64 / 16. Everything K-major is addressed in bytes and does not care.
+    constexpr uint32_t kEl = kBf16AB ? 2 : 1;
+    constexpr uint32_t kKRows = kBlockK / kEl, kUmmaKRows = kUmmaK / kEl;
     const uint32_t staging = smem_u32(smem);                               // kTmaStore: 2 buffers x 4 KB (transposed output: 8 x 2 KB)
     const uint32_t smem_base = staging + (kTmaStore ? (kSwapD ? kSwapStagingBytes : kStoreStagingBytes) : 0u);   // the TMA -> MMA ring starts here
     const uint32_t off_x = kWTileBytes, off_sfw = off_x + x_tile_bytes, off_sfx = off_sfw + 512;
@@ -662,19 +667,22 @@ fp8_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
                     mbar_arrive_expect_tx(full, ab_bytes + (load_sfw ? sfw_tx : 0u) + (load_sfx ? sfx_tx : 0u));
                     if constexpr (kGemmType == kBatched) {
                         // 3-D maps {inner, outer, batch}: boxes are one batch deep, so the tiles land exactly like 2-D ones
-                        if constexpr (kWMn)
-                            tma_load_3d(&map_w, full, slot, t.n0, k0, t.batch, p.w_hint);
-                        else
+                        if constexpr (kWMn) {
+                            for (uint32_t j = 0; j < kEl; ++j)
+                                tma_load_3d(&map_w, full, slot + j * (kKRows * 128), t.n0 * kEl + j * 128, k0 / kEl, t.batch, p.w_hint);
+                        } else
                             tma_load_3d(&map_w, full, slot, k0, t.w_row, t.batch, p.w_hint);
                         if constexpr (kXMn) {
-                            for (uint32_t i = 0, off = 0; i < load_m; i += p.x_swizzle, off += p.x_swizzle * kBlockK)
-                                tma_load_3d(&map_x, full, slot + off_x + off, x_row + i, k0, t.batch, p.x_hint);
+                            for (uint32_t i = 0, off = 0; i < load_m * kEl; i += p.x_swizzle, off += p.x_swizzle * kKRows)
+                                tma_load_3d(&map_x, full, slot + off_x + off, x_row * kEl + i, k0 / kEl, t.batch, p.x_hint);
                         } else {
                             tma_load_3d(&map_x, full, slot + off_x, k0, x_row, t.batch, p.x_hint);
                         }
                     } else {
                     if constexpr (kWMn) {
-                        tma_load_2d(&map_w, full, slot, t.n0, t.wk_base + t.k_base + k0, p.w_hint);
+                        // MN-major: the contiguous (byte-addressed) coordinate is N, the K rows are counted in elements
+                        for (uint32_t j = 0; j < kEl; ++j)
+                            tma_load_2d(&map_w, full, slot + j * (kKRows * 128), t.n0 * kEl + j * 128, (t.wk_base + t.k_base + k0) / kEl, p.w_hint);
                     } else if constexpr (kPairs == 1) {
                         tma_load_2d(&map_w, full, slot, t.k_base + k0, t.w_row, p.w_hint);
                     } else {
@@ -682,8 +690,8 @@ fp8_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
                                               w_mask, p.w_hint);
                     }
                     if constexpr (kXMn) {
-                        for (uint32_t i = 0, off = 0; i < load_m; i += p.x_swizzle, off += p.x_swizzle * kBlockK)
-                            tma_load_2d(&map_x, full, slot + off_x + off, x_row + i, t.k_base + k0, p.x_hint);
+                        for (uint32_t i = 0, off = 0; i < load_m * kEl; i += p.x_swizzle, off += p.x_swizzle * kKRows)
+                            tma_load_2d(&map_x, full, slot + off_x + off, x_row * kEl + i, (t.k_base + k0) / kEl, p.x_hint);
                     } else {
                         tma_load_2d(&map_x, full, slot + off_x, t.k_base + k0, x_row, p.x_hint);
                     }
@@ -706,16 +714,16 @@ fp8_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
             uint32_t idesc_base = 0;     // per tile: UMMA M = 128 x CTAs, N = tile_n(t)
             // descriptors of slot 0; a slot offset adds (bytes >> 4) to the 14-bit start-address field.
             //   K-major : 8-row x 128 B swizzle atoms stacked along MN (SBO 1024); +32 B per UMMA_K step
-            //   MN-major: atoms of S bytes (MN) x 8 K-rows; SBO = 8*S between K groups, LBO = 128*S between MN atoms;
-            //             +32 K-rows = 32*S bytes per UMMA_K step            (cf. reference mma/sm100.cuh:96-132)
+            //   MN-major: atoms of S bytes (MN) x 8 K-rows; SBO = 8*S between K groups, LBO = kKRows*S between MN atoms;
+            //             + kUmmaKRows K-rows = kUmmaKRows*S bytes per UMMA_K step   (cf. reference mma/sm100.cuh:96-132)
             const uint32_t xs = kXMn ? p.x_swizzle : 128u;
             const uint32_t x_layout = xs == 128 ? kLayoutSwizzle128B : (xs == 64 ? kLayoutSwizzle64B : kLayoutSwizzle32B);
-            const uint64_t w_desc0 = kWMn ? make_smem_desc(smem_base, kBlockK * 128, 8 * 128, kLayoutSwizzle128B)
+            const uint64_t w_desc0 = kWMn ? make_smem_desc(smem_base, kKRows * 128, 8 * 128, kLayoutSwizzle128B)
                                           : make_smem_desc(smem_base, 0, 1024, kLayoutSwizzle128B);
-            const uint64_t x_desc0 = kXMn ? make_smem_desc(smem_base + off_x, kBlockK * xs, 8 * xs, x_layout)
+            const uint64_t x_desc0 = kXMn ? make_smem_desc(smem_base + off_x, kKRows * xs, 8 * xs, x_layout)
                                           : make_smem_desc(smem_base + off_x, 0, 1024, kLayoutSwizzle128B);
-            const uint32_t w_kstep = kWMn ? (kUmmaK * 128) >> 4 : kUmmaK >> 4;
-            const uint32_t x_kstep = kXMn ? (kUmmaK * xs) >> 4 : kUmmaK >> 4;
+            const uint32_t w_kstep = kWMn ? (kUmmaKRows * 128) >> 4 : kUmmaK >> 4;
+            const uint32_t x_kstep = kXMn ? (kUmmaKRows * xs) >> 4 : kUmmaK >> 4;
             const uint64_t sfw_desc0 = make_smem_desc(smem_base + off_sfw, 0, 128, kLayoutNoSwizzle);
             const uint64_t sfx_desc0 = make_smem_desc(smem_base + off_sfx, 0, 128, kLayoutNoSwizzle);
             const uint32_t tmem_sfw = tmem_base + kTmemColSFW, tmem_sfx = tmem_base + kTmemColSFX;
@@ -759,7 +767,7 @@ fp8_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
                 ++tile_iter;
                 mbar_wait(tmem_empty_bar + as * 8, aphase ^ 1);
                 tcgen05_fence_after();
-                idesc_base = kBf16AB ? make_idesc_bf16(128 * kCtaGroup, tile_n(t)) : make_idesc(128 * kCtaGroup, tile_n(t), kWMn ? 1 : 0, kXMn ? 1 : 0);
+                idesc_base = kBf16AB ? make_idesc_bf16(128 * kCtaGroup, tile_n(t), kWMn ? 1 : 0, kXMn ? 1 : 0) : make_idesc(128 * kCtaGroup, tile_n(t), kWMn ? 1 : 0, kXMn ? 1 : 0);
                 const uint32_t tmem_d = tmem_base + as * kAccumColStride;
                 uint32_t kb = t.kb_begin;
                 for (; kb + 1 < t.kb_end; ++kb, ring.advance()) {        // every k-block but the last: 4 UMMAs

@@ -146,5 +146,6 @@ int dispatch_grouped(const GemmCall& c, const Config& cfg, const Maps& maps, con
 int dispatch_batched(const GemmCall& c, const Config& cfg, const Maps& maps, const GemmParams& p);       // gemm_batched.cu
 int dispatch_dense_swap(const GemmCall& c, const Config& cfg, const Maps& maps, const GemmParams& p);    // gemm_dense_swap.cu
 int dispatch_bf16(const GemmCall& c, const Config& cfg, const Maps& maps, const GemmParams& p);          // gemm_bf16.cu
+int dispatch_bf16_mn(const GemmCall& c, const Config& cfg, const Maps& maps, const GemmParams& p);       // gemm_bf16_mn.cu
 
 }  // namespace dgb200

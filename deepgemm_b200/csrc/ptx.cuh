@@ -349,10 +349,10 @@ constexpr uint32_t kLayoutSwizzle32B = 6;
 DGB_DEVICE constexpr uint32_t make_idesc(uint32_t umma_m, uint32_t umma_n, uint32_t a_mn_major, uint32_t b_mn_major) {
     return (a_mn_major << 15) | (b_mn_major << 16) | ((umma_n >> 3) << 17) | (1u << 23) | ((umma_m >> 4) << 24);
 }
-// 32-bit instruction descriptor for kind::f16 with BF16 x BF16 -> FP32, both operands K-major
+// 32-bit instruction descriptor for kind::f16 with BF16 x BF16 -> FP32 (bits 15 / 16: operand is MN-major)
 // (cute/arch/mma_sm100_desc.hpp:411-432: [4,6) c_format 1 = F32 | [7,10) a_format 1 = BF16 | [10,13) b_format | [17,23) N>>3 | [24,29) M>>4)
-DGB_DEVICE constexpr uint32_t make_idesc_bf16(uint32_t umma_m, uint32_t umma_n) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((umma_n >> 3) << 17) | ((umma_m >> 4) << 24);
+DGB_DEVICE constexpr uint32_t make_idesc_bf16(uint32_t umma_m, uint32_t umma_n, uint32_t a_mn_major = 0, uint32_t b_mn_major = 0) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | (a_mn_major << 15) | (b_mn_major << 16) | ((umma_n >> 3) << 17) | ((umma_m >> 4) << 24);
 }
 DGB_DEVICE uint32_t idesc_with_sf_ids(uint32_t idesc, uint32_t a_sf_id, uint32_t b_sf_id) {
     return idesc | (b_sf_id << 4) | (a_sf_id << 29);

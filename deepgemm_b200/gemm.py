@@ -211,39 +211,46 @@ def fp8_einsum(expr: str, a: TensorPair, b: TensorPair, d: torch.Tensor, c: Opti
 
 
 # ------------------------------------------------------------------------------------------------ BF16 operands
-def _check_bf16_k_major(t: torch.Tensor, what: str) -> None:
+def _bf16_major(t: torch.Tensor, what: str):
+    """(major, pitch of the strided extent in elements) of a BF16 operand's last two dims (get_major_type_ab, csrc/utils/layout.hpp)."""
     _require(t.dtype == torch.bfloat16, f'{what}.dtype == bfloat16')
-    if t.stride(-1) != 1:
-        raise RuntimeError(f'MN-major BF16 operands are not built in this library ({what} must have stride(-1) == 1); '
-                           'the reference supports them (csrc/apis/gemm.hpp:404-462)')
-    _require(t.size(-1) % 8 == 0 and t.stride(-2) % 8 == 0 and t.data_ptr() % 16 == 0, f'{what}: 16-byte aligned rows')
+    if t.stride(-1) == 1:
+        major, contiguous, pitch = _K_MAJOR, t.size(-1), t.stride(-2)
+    else:
+        _require(t.stride(-2) == 1, f'{what} must be K-major or MN-major')
+        major, contiguous, pitch = _MN_MAJOR, t.size(-2), t.stride(-1)
+    _require(contiguous % 8 == 0 and pitch % 8 == 0 and t.data_ptr() % 16 == 0, f'{what}: 16-byte aligned rows')
+    return major, pitch
 
 
 def bf16_gemm_nt(a: torch.Tensor, b: torch.Tensor, d: torch.Tensor, c: Optional[torch.Tensor] = None,
                  compiled_dims: str = 'nk') -> None:
-    """D = (C +) A @ B.T with BF16 A [M,K], B [N,K] (no scale factors), D BF16 or FP32. Reference: bf16_gemm_nt,
-    csrc/apis/gemm.hpp:404-438 (kernel deep_gemm/include/deep_gemm/impls/sm100_bf16_gemm.cuh). K-major operands only."""
+    """D = (C +) A @ B.T with BF16 A [M,K], B [N,K] (no scale factors; either may be a transposed view, i.e. MN-major),
+    D BF16 or FP32. Reference: bf16_gemm_nt, csrc/apis/gemm.hpp:404-438 (kernel impls/sm100_bf16_gemm.cuh)."""
     _require(a.dim() == 2 and b.dim() == 2 and d.dim() == 2, 'a, b, d are 2-D')
-    _check_bf16_k_major(a, 'a'), _check_bf16_k_major(b, 'b')
+    (major_a, lda), (major_b, ldb) = _bf16_major(a, 'a'), _bf16_major(b, 'b')
     _check_cd(d)
     (m, k), (n, k_), (m_, n_) = a.shape, b.shape, d.shape
     _require(m == m_ and n == n_ and k == k_, 'm == m_ and n == n_ and k == k_')
     d_dtype = _d_dtype(d)
     if _early_return(m, n, k, d, c):
         return
-    check(lib().dgb200_bf16_gemm_nt(a.data_ptr(), b.data_ptr(), d.data_ptr(), m, n, k, a.stride(0), b.stride(0), d.stride(0),
-                                    d_dtype, int(c is not None), _stream()))
+    check(lib().dgb200_bf16_gemm_nt(a.data_ptr(), b.data_ptr(), d.data_ptr(), m, n, k, lda, ldb, d.stride(0),
+                                    major_a, major_b, d_dtype, int(c is not None), _stream()))
 
 
 def bf16_gemm_nn(a, b, d, c=None, compiled_dims='nk'):
+    """B given as [K,N] (gemm.hpp:440-446)."""
     bf16_gemm_nt(a, b.transpose(0, 1), d, c, compiled_dims)
 
 
 def bf16_gemm_tn(a, b, d, c=None, compiled_dims='mn'):
+    """A given as [K,M], B as [K,N] (gemm.hpp:448-454)."""
     bf16_gemm_nt(a.transpose(0, 1), b.transpose(0, 1), d, c, compiled_dims)
 
 
 def bf16_gemm_tt(a, b, d, c=None, compiled_dims='mn'):
+    """A given as [K,M] (gemm.hpp:456-462)."""
     bf16_gemm_nt(a.transpose(0, 1), b, d, c, compiled_dims)
 
 
@@ -251,10 +258,12 @@ def m_grouped_bf16_gemm_nt_contiguous(a: torch.Tensor, b: torch.Tensor, d: torch
                                       compiled_dims: str = 'nk', use_psum_layout: bool = False,
                                       ensure_zero_padding: bool = True,
                                       expected_m_for_psum_layout: Optional[int] = None) -> None:
-    """A [M_sum,K] BF16 rows grouped by expert, B [G,N,K] BF16, D [M_sum,N] BF16 (gemm.hpp:464-517)."""
+    """A [M_sum,K] BF16 rows grouped by expert, B [G,N,K] BF16 (or a transposed view of [G,K,N]), D [M_sum,N] BF16
+    (gemm.hpp:464-517)."""
     _require(a.dim() == 2 and b.dim() == 3 and d.dim() == 2, 'a 2-D, b 3-D, d 2-D')
-    _check_bf16_k_major(a, 'a'), _check_bf16_k_major(b, 'b')
-    _require(b.stride(0) == b.size(1) * b.size(2) and b.stride(1) == b.size(2), 'b is densely batched')
+    (major_a, lda), (major_b, ldb) = _bf16_major(a, 'a'), _bf16_major(b, 'b')
+    _require(major_a == _K_MAJOR, 'a is K-major')                                  # gemm.hpp:478
+    _require(b.stride(0) == b.size(1) * b.size(2) and ldb == (b.size(2) if major_b == _K_MAJOR else b.size(1)), 'b is densely batched')
     _require(grouped_layout.is_contiguous() and grouped_layout.dtype == torch.int32, 'grouped_layout is contiguous int32')
     (m, k), (num_groups, n, k_), (m_, n_) = a.shape, b.shape, d.shape
     _require(m == m_ and n == n_ and k == k_, 'm == m_ and n == n_ and k == k_')
@@ -269,12 +278,13 @@ def m_grouped_bf16_gemm_nt_contiguous(a: torch.Tensor, b: torch.Tensor, d: torch
     if m == 0:
         return
     check(lib().dgb200_m_grouped_bf16_gemm_nt_contiguous(
-        a.data_ptr(), b.data_ptr(), d.data_ptr(), grouped_layout.data_ptr(), num_groups, m, n, k, a.stride(0), b.stride(1), d.stride(0),
+        a.data_ptr(), b.data_ptr(), d.data_ptr(), grouped_layout.data_ptr(), num_groups, m, n, k, lda, ldb, d.stride(0), major_b,
         int(use_psum_layout), int(ensure_zero_padding), -1 if expected_m_for_psum_layout is None else int(expected_m_for_psum_layout),
         _stream()))
 
 
 def m_grouped_bf16_gemm_nn_contiguous(a, b, d, grouped_layout, compiled_dims='nk', use_psum_layout=False, ensure_zero_padding=True):
+    """B given as [G,K,N] (gemm.hpp:519-526)."""
     m_grouped_bf16_gemm_nt_contiguous(a, b.transpose(1, 2), d, grouped_layout, compiled_dims, use_psum_layout, ensure_zero_padding, None)
 
 
@@ -282,21 +292,77 @@ def m_grouped_bf16_gemm_nt_masked(a: torch.Tensor, b: torch.Tensor, d: torch.Ten
                                   compiled_dims: str = 'nk') -> None:
     """A [G,M_max,K], B [G,N,K] BF16, D [G,M_max,N] BF16; rows >= masked_m[g] are not written (gemm.hpp:528-564)."""
     _require(a.dim() == 3 and b.dim() == 3 and d.dim() == 3, 'a, b, d are 3-D')
-    _check_bf16_k_major(a, 'a'), _check_bf16_k_major(b, 'b')
-    _require(a.is_contiguous() and b.is_contiguous() and d.is_contiguous(), 'a, b, d are contiguous')
+    _require(a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16, 'a, b are bfloat16')
+    _require(a.is_contiguous() and b.is_contiguous() and d.is_contiguous(), 'a, b, d are contiguous')   # both K-major (gemm.hpp:541)
     _require(masked_m.is_contiguous() and masked_m.dtype == torch.int32, 'masked_m is contiguous int32')
     (g, m, k), (g_, n, k_), (g__, m_, n_) = a.shape, b.shape, d.shape
     _require(g == g_ == g__ == masked_m.numel(), 'group counts agree')
     _require(m == m_ and n == n_ and k == k_, 'm == m_ and n == n_ and k == k_')
     _require(expected_m > 0 and m > 0 and n > 0 and k > 0 and g > 0, 'positive sizes')
+    _require(k % 8 == 0, 'k % 8 == 0')
     _require(d.dtype == torch.bfloat16, 'd.dtype == bfloat16')
     check(lib().dgb200_m_grouped_bf16_gemm_nt_masked(a.data_ptr(), b.data_ptr(), d.data_ptr(), masked_m.data_ptr(), g, m, n, k,
                                                      int(expected_m), _stream()))
 
 
-def k_grouped_bf16_gemm_tn_contiguous(*args, **kwargs) -> None:
-    """Weight-gradient form with both operands MN-major (gemm.hpp:566-609): not built for BF16 operands here."""
-    raise RuntimeError('k_grouped_bf16_gemm_tn_contiguous is not built in this library (MN-major BF16 operands)')
+def k_grouped_bf16_gemm_tn_contiguous(a: torch.Tensor, b: torch.Tensor, d: torch.Tensor, ks_cpu: Optional[List[int]],
+                                      grouped_layout: torch.Tensor, c: Optional[torch.Tensor] = None, compiled_dims: str = 'mn',
+                                      use_psum_layout: bool = False) -> None:
+    """Weight gradient D[g] = C[g] + A[k_g,:M].T @ B[k_g,:N]: A [sum_k, M], B [sum_k, N] BF16 (both MN-major), D = C [G, M, N]
+    FP32 accumulated in place (gemm.hpp:566-608)."""
+    _require(a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16, 'a, b are bfloat16')
+    k_alignment = get_mk_alignment_for_contiguous_layout()
+    _require(k_alignment % 32 == 0, 'k_alignment % 32 == 0')
+    _require(d.dim() == 3 and a.dim() == 2 and b.dim() == 2, 'd is 3-D, a and b are 2-D')
+    num_groups, m, n = d.shape
+    (sum_k_a, m_), (sum_k_b, n_) = a.shape, b.shape
+    _require(grouped_layout.is_contiguous() and grouped_layout.dtype == torch.int32 and grouped_layout.numel() == num_groups,
+             'grouped_layout is a contiguous int32 [num_groups] tensor')
+    if ks_cpu is not None and len(ks_cpu) > 0:
+        _require(len(ks_cpu) == num_groups, 'len(ks_cpu) == num_groups')
+        _require(all(k % k_alignment == 0 for k in ks_cpu), 'k % k_alignment == 0')
+        sum_k = sum(ks_cpu)
+    else:
+        _require(use_psum_layout, 'ks_cpu may only be omitted with use_psum_layout')
+        sum_k = sum_k_a
+    _require(m == m_ and n == n_ and sum_k == sum_k_a and sum_k == sum_k_b, 'shapes agree')
+    _require(a.is_contiguous() and b.is_contiguous() and d.is_contiguous(), 'a, b, d are contiguous')
+    _require(c is not None and c.is_contiguous(), 'c is required and contiguous')
+    _require(d.dtype == torch.float32, 'd.dtype == float')
+    _require(m % 8 == 0 and n % 8 == 0, '16-byte aligned rows')
+    if _early_return(m, n, sum_k, d, c):
+        return
+    check(lib().dgb200_k_grouped_bf16_gemm_tn_contiguous(a.data_ptr(), b.data_ptr(), d.data_ptr(), grouped_layout.data_ptr(),
+                                                         num_groups, m, n, sum_k, int(use_psum_layout), _stream()))
+
+
+def einsum(expr: str, a: torch.Tensor, b: torch.Tensor, d: torch.Tensor, c: Optional[torch.Tensor] = None,
+           use_cublaslt: bool = False) -> None:
+    """The BF16 contractions of the reference that run on its BF16 GEMM kernel (csrc/apis/einsum.hpp:62-136): 'bhr,hdr->bhd'
+    and 'bhd,hdr->bhr', each one batched GEMM over permuted views (batch = h, m = b), no copies. 'bmk,bnk->mn' (a separate
+    batch-reduction kernel in the reference, impls/sm100_bmk_bnk_mn.cuh) is not built."""
+    _require(a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16, 'a, b are bfloat16')
+    _require(not use_cublaslt, 'use_cublaslt is not available in this library')
+    if expr not in ('bhr,hdr->bhd', 'bhd,hdr->bhr'):
+        raise RuntimeError(f'Unsupported einsum expression: {expr}')
+    _require(c is None, 'c is not supported for this expression')                     # einsum.hpp:127,130
+    _require(a.dim() == 3 and b.dim() == 3 and d.dim() == 3, 'a, b, d are 3-D')
+    _require(d.dtype == torch.bfloat16 and a.stride(2) == 1 and b.stride(2) == 1 and d.stride(2) == 1, 'BF16, innermost contiguous')
+    bsz, h, k = a.shape
+    if expr == 'bhr,hdr->bhd':
+        h_, n, k_ = b.shape
+        major_b = _K_MAJOR
+    else:
+        h_, k_, n = b.shape
+        major_b = _MN_MAJOR
+    _require(d.shape == (bsz, h, n) and h == h_ and k == k_, 'shapes agree')
+    if bsz == 0 or h == 0 or n == 0:
+        return
+    for t, what in ((a, 'a'), (b, 'b')):
+        _require(t.data_ptr() % 16 == 0 and all(st % 8 == 0 for st in t.stride()[:2]), f'{what}: 16-byte aligned rows')
+    _require(k % 8 == 0 and n % 8 == 0 if major_b == _MN_MAJOR else k % 8 == 0, '16-byte aligned rows')
+    check(lib().dgb200_bf16_bmm(a.data_ptr(), b.data_ptr(), d.data_ptr(), h, bsz, n, k, a.stride(0), b.stride(1), d.stride(0),
+                                a.stride(1), b.stride(0), d.stride(1), major_b, _stream()))
 
 
 def _t(pair: TensorPair, d0: int = 0, d1: int = 1) -> TensorPair:

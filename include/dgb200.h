@@ -137,20 +137,30 @@ int dgb200_fp8_bmm(const void* a, const int32_t* sfa, const void* b, const int32
 int dgb200_per_token_cast_to_fp8(const void* x, int64_t ldx, void* q, int64_t ldq, int32_t* sf, int sf_stride,
                                  int m, int k, int gran_k, void* stream);
 
-/* BF16 x BF16 GEMMs without scale factors on the same kernel skeleton (tcgen05.mma kind::f16), K-major operands only:
- *   dgb200_bf16_gemm_nt                       -- bf16_gemm_nt, csrc/apis/gemm.hpp:404-438 (+ nn/tn/tt when the views are K-major)
- *   dgb200_m_grouped_bf16_gemm_nt_contiguous  -- m_grouped_bf16_gemm_nt_contiguous, gemm.hpp:464-517 (layouts as the FP8 form)
+/* BF16 x BF16 GEMMs without scale factors on the same kernel skeleton (tcgen05.mma kind::f16):
+ *   dgb200_bf16_gemm_nt                       -- bf16_gemm_{nt,nn,tn,tt}, csrc/apis/gemm.hpp:404-462 (majors as in dgb200_fp8_gemm_nt)
+ *   dgb200_m_grouped_bf16_gemm_nt_contiguous  -- m_grouped_bf16_gemm_{nt,nn}_contiguous, gemm.hpp:464-526 (layouts as the FP8 form)
  *   dgb200_m_grouped_bf16_gemm_nt_masked      -- m_grouped_bf16_gemm_nt_masked, gemm.hpp:528-564
- * a [m, k], b [n, k] (grouped: [G, n, k]) BF16 with row pitches lda / ldb in ELEMENTS (multiples of 8), k % 8 == 0.
- * MN-major BF16 operands and k_grouped_bf16_gemm_tn_contiguous are not built (DGB200_ERR_UNSUPPORTED in the Python layer). */
+ *   dgb200_k_grouped_bf16_gemm_tn_contiguous  -- k_grouped_bf16_gemm_tn_contiguous, gemm.hpp:566-608
+ * K-major: a [m, k], b [n, k] (grouped: [G, n, k]); MN-major: a [k, m], b [k, n] (grouped: [G, k, n]); lda / ldb = pitch of
+ * the strided extent in ELEMENTS, contiguous extents and pitches multiples of 8 elements (16-byte rows for TMA).
+ * k-grouped: a [sum_k, m], b [sum_k, n] BF16 contiguous, d [num_groups, m, n] FP32 holding C on entry (accumulated into),
+ * grouped_layout int32[num_groups] = K of each group (psum: unaligned end K, group starts aligned to mk_alignment). */
 int dgb200_bf16_gemm_nt(const void* a, const void* b, void* d, int m, int n, int k, int64_t lda, int64_t ldb, int64_t ldd,
-                        int d_dtype, int accumulate, void* stream);
+                        int major_a, int major_b, int d_dtype, int accumulate, void* stream);
 int dgb200_m_grouped_bf16_gemm_nt_contiguous(const void* a, const void* b, void* d, const int32_t* grouped_layout,
                                              int num_groups, int m, int n, int k, int64_t lda, int64_t ldb, int64_t ldd,
-                                             int use_psum_layout, int ensure_zero_padding, int expected_m_for_psum_layout,
-                                             void* stream);
+                                             int major_b, int use_psum_layout, int ensure_zero_padding,
+                                             int expected_m_for_psum_layout, void* stream);
 int dgb200_m_grouped_bf16_gemm_nt_masked(const void* a, const void* b, void* d, const int32_t* masked_m, int num_groups,
                                          int m_max, int n, int k, int expected_m, void* stream);
+int dgb200_k_grouped_bf16_gemm_tn_contiguous(const void* a, const void* b, float* d, const int32_t* grouped_layout,
+                                             int num_groups, int m, int n, int sum_k, int use_psum_layout, void* stream);
+/* Batched BF16 GEMM D[i] = A[i] B[i]^T behind einsum('bhr,hdr->bhd' / 'bhd,hdr->bhr'), csrc/apis/einsum.hpp:62-108: a K-major,
+ * b K-major [batch, n, k] or MN-major [batch, k, n], d BF16; pitches and batch strides in elements (as dgb200_fp8_bmm). */
+int dgb200_bf16_bmm(const void* a, const void* b, void* d, int batch, int m, int n, int k, int64_t lda, int64_t ldb,
+                    int64_t ldd, int64_t batch_stride_a, int64_t batch_stride_b, int64_t batch_stride_d, int major_b,
+                    void* stream);
 
 /* Rows of A grouped by expert          -- m_grouped_fp8_fp4_gemm_nt_contiguous, csrc/apis/gemm.hpp:166-232.
  *   a [m, k], b [num_groups, n, k], d [m, n] bf16

@@ -78,7 +78,7 @@ def test_bf16_gemm_every_tile_config_gives_identical_bits(dg, monkeypatch):
         monkeypatch.delenv('DGB200_STAGES', raising=False)
 
 
-def test_bf16_transposed_wrappers_and_mn_major_rejection(dg):
+def test_bf16_transposed_wrappers_on_k_major_views(dg):
     a = torch.randn((256, 512), device='cuda', dtype=torch.bfloat16)
     b = torch.randn((384, 512), device='cuda', dtype=torch.bfloat16)
     d0 = torch.empty((256, 384), device='cuda', dtype=torch.bfloat16)
@@ -89,10 +89,129 @@ def test_bf16_transposed_wrappers_and_mn_major_rejection(dg):
     d2 = torch.empty_like(d0)
     dg.bf16_gemm_tt(a.t(), b, d2)
     assert torch.equal(d0, d2)
+
+
+@pytest.mark.parametrize('m,n,k', [(128, 128, 128), (64, 4096, 7168), (304, 2112, 1536), (4096, 4096, 2048), (96, 136, 200), (8, 576, 512)])
+@pytest.mark.parametrize('majors', ['nn', 'tn', 'tt'])
+def test_bf16_gemm_mn_major_operands_give_the_k_major_bits(dg, m, n, k, majors):
+    """Genuinely MN-major operands (bf16_gemm_{nn,tn,tt}, gemm.hpp:440-462): the same products summed in the same order, so the
+    output must equal the K-major launch bit for bit."""
+    gen = torch.Generator(device='cuda').manual_seed(m * 3 + n + k)
+    a = torch.randn((m, k), device='cuda', dtype=torch.bfloat16, generator=gen)
+    b = torch.randn((n, k), device='cuda', dtype=torch.bfloat16, generator=gen)
+    a_km = a.t().contiguous()      # [K, M]
+    b_kn = b.t().contiguous()      # [K, N]
+    for out_dtype in (torch.bfloat16, torch.float32):
+        base = torch.empty((m, n), device='cuda', dtype=out_dtype)
+        dg.bf16_gemm_nt(a, b, base)
+        _close(base, a.float() @ b.float().t())
+        buf = torch.full((m + 8, n + 16), 222.0, device='cuda', dtype=out_dtype)
+        d = buf[:m, :n]
+        if majors == 'nn':
+            dg.bf16_gemm_nn(a, b_kn, d)
+        elif majors == 'tn':
+            dg.bf16_gemm_tn(a_km, b_kn, d)
+        else:
+            dg.bf16_gemm_tt(a_km, b, d)
+        assert torch.equal(d, base), (majors, out_dtype)
+        assert bool((buf[m:] == 222.0).all()) and bool((buf[:, n:] == 222.0).all())
+    c = torch.randn((m, n), device='cuda')
+    want = c.clone()
+    dg.bf16_gemm_nt(a, b, want, c=want)
+    got = c.clone()
+    dg.bf16_gemm_tn(a_km, b_kn, got, c=got)
+    assert torch.equal(got, want)
+
+
+def test_bf16_mn_major_every_tile_height_gives_identical_bits(dg, monkeypatch):
+    m, n, k = 512, 640, 1088
+    a = torch.randn((m, k), device='cuda', dtype=torch.bfloat16)
+    b = torch.randn((n, k), device='cuda', dtype=torch.bfloat16)
+    a_km, b_kn = a.t().contiguous(), b.t().contiguous()
+    base = torch.empty((m, n), device='cuda', dtype=torch.bfloat16)
+    dg.bf16_gemm_nt(a, b, base)
+    for bm in (32, 64, 96, 128, 160, 192, 224):            # token swizzle atoms of 32 / 64 / 128 bytes
+        monkeypatch.setenv('DGB200_BLOCK_M', str(bm))
+        d = torch.empty_like(base)
+        dg.bf16_gemm_tn(a_km, b_kn, d)
+        assert torch.equal(d, base), bm
+
+
+@pytest.mark.parametrize('use_psum', [False, True])
+def test_m_grouped_bf16_nn_contiguous_gives_the_nt_bits(dg, use_psum):
+    g, n, k, alignment = 4, 512, 768, 128
+    ms = [100, 0, 256, 77]
+    aligned = [(x + alignment - 1) // alignment * alignment for x in ms]
+    m = sum(aligned)
+    a = torch.randn((m, k), device='cuda', dtype=torch.bfloat16)
+    b = torch.randn((g, n, k), device='cuda', dtype=torch.bfloat16)
+    layout = torch.empty(g if use_psum else m, device='cuda', dtype=torch.int32)
+    s = 0
+    for i, (mi, ai) in enumerate(zip(ms, aligned)):
+        if use_psum:
+            layout[i] = s + mi
+        else:
+            layout[s:s + mi] = i
+            layout[s + mi:s + ai] = -1
+        s += ai
+    d0 = torch.zeros((m, n), device='cuda', dtype=torch.bfloat16)
+    d1 = torch.zeros_like(d0)
+    dg.m_grouped_bf16_gemm_nt_contiguous(a, b, d0, layout, use_psum_layout=use_psum)
+    dg.m_grouped_bf16_gemm_nn_contiguous(a, b.transpose(1, 2).contiguous(), d1, layout, use_psum_layout=use_psum)
+    assert torch.equal(d0, d1)
+
+
+@pytest.mark.parametrize('use_psum', [False, True])
+def test_k_grouped_bf16_gemm_tn_contiguous(dg, use_psum):
+    """Weight gradient D[g] = C[g] + A_g^T B_g over K segments (gemm.hpp:566-608; tests/test_bf16.py k-grouped case)."""
+    random.seed(11 + use_psum)
+    g, m, n, k_alignment = 5, 384, 264, 128
+    ks = [k_alignment * random.randint(1, 6) for _ in range(g)]
+    ks[1] = 0
+    if use_psum:
+        ks_real = [max(0, kk - random.randint(0, 60)) if kk else 0 for kk in ks]      # unaligned ends, aligned starts
+    else:
+        ks_real = ks
+    sum_k = sum(ks)
+    a = torch.randn((sum_k, m), device='cuda', dtype=torch.bfloat16)
+    b = torch.randn((sum_k, n), device='cuda', dtype=torch.bfloat16)
+    c = torch.randn((g, m, n), device='cuda', dtype=torch.float32)
+    ref = c.clone()
+    s = 0
+    ends = []
+    for i, (kk, kr) in enumerate(zip(ks, ks_real)):
+        a[s + kr:s + kk] = 0                     # rows between a group's end and the next aligned start are zero padding
+        b[s + kr:s + kk] = 0
+        ref[i] += a[s:s + kr].float().t() @ b[s:s + kr].float()
+        ends.append(s + kr)
+        s += kk
+    if use_psum:
+        layout = torch.tensor(ends, device='cuda', dtype=torch.int32)
+        d = c.clone()
+        dg.k_grouped_bf16_gemm_tn_contiguous(a, b, d, None, layout, c=d, use_psum_layout=True)
+    else:
+        layout = torch.tensor(ks, device='cuda', dtype=torch.int32)
+        d = c.clone()
+        dg.k_grouped_bf16_gemm_tn_contiguous(a, b, d, ks, layout, c=d)
+    _close(d, ref, f'k-grouped psum={use_psum}')
+
+
+@pytest.mark.parametrize('h,r,dd', [(16, 512, 128), (8, 1024, 256)])
+@pytest.mark.parametrize('bsz', [4, 100, 1024])
+def test_bf16_einsum(dg, h, r, dd, bsz):
+    """einsum('bhr,hdr->bhd') and ('bhd,hdr->bhr') on sliced weights, as tests/test_einsum.py:40-80 builds them."""
+    fy = torch.randn((h, dd, r + 128), device='cuda', dtype=torch.bfloat16)
+    y = fy[:, :, :r]
+    x = torch.randn((bsz, h, r), device='cuda', dtype=torch.bfloat16)
+    z = torch.empty((bsz, h, dd), device='cuda', dtype=torch.bfloat16)
+    dg.einsum('bhr,hdr->bhd', x, y, z)
+    _close(z, torch.einsum('bhr,hdr->bhd', x.float(), y.float()), 'bhr,hdr->bhd')
+    x2 = torch.randn((bsz, h, dd), device='cuda', dtype=torch.bfloat16)
+    z2 = torch.empty((bsz, h, r), device='cuda', dtype=torch.bfloat16)
+    dg.einsum('bhd,hdr->bhr', x2, y, z2)
+    _close(z2, torch.einsum('bhd,hdr->bhr', x2.float(), y.float()), 'bhd,hdr->bhr')
     with pytest.raises(RuntimeError):
-        dg.bf16_gemm_nt(a, b.t().contiguous().t(), d1)        # genuinely MN-major B: not built
-    with pytest.raises(RuntimeError):
-        dg.k_grouped_bf16_gemm_tn_contiguous(a, b, d0, [512], None)
+        dg.einsum('bmk,bnk->mn', x, x, z)
 
 
 @pytest.mark.parametrize('use_psum', [False, True])

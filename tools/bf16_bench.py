@@ -22,3 +22,35 @@ for (m, n, k) in [(64, 4096, 7168), (128, 2112, 7168), (512, 4096, 7168), (4096,
     t_our = bench_kineto(lambda: dg.bf16_gemm_nt(a, b, d1), 'fp8_gemm_kernel', num_tests=10)
     print(json.dumps({'m': m, 'n': n, 'k': k, 'bitwise_equal': bool(torch.equal(d0, d1)), 'ours_us': round(t_our * 1e6, 2), 'ref_us': round(t_ref * 1e6, 2),
                       'ours_tflops': round(2.0 * m * n * k / t_our / 1e12, 1), 'ref_tflops': round(2.0 * m * n * k / t_ref / 1e12, 1)}), flush=True)
+
+# MN-major operands and the k-grouped weight-gradient form against the reference's kernels (same inputs)
+for (m, n, k) in [(4096, 4096, 2048), (256, 7168, 4096)]:
+    a = torch.randn((k, m), device='cuda', dtype=torch.bfloat16)
+    b = torch.randn((k, n), device='cuda', dtype=torch.bfloat16)
+    d0, d1 = torch.empty((m, n), device='cuda', dtype=torch.bfloat16), torch.empty((m, n), device='cuda', dtype=torch.bfloat16)
+    ref.bf16_gemm_tn(a, b, d0)
+    dg.bf16_gemm_tn(a, b, d1)
+    torch.cuda.synchronize()
+    t_ref = bench_kineto(lambda: ref.bf16_gemm_tn(a, b, d0), 'gemm', num_tests=10)
+    t_our = bench_kineto(lambda: dg.bf16_gemm_tn(a, b, d1), 'fp8_gemm_kernel', num_tests=10)
+    print(json.dumps({'form': 'tn', 'm': m, 'n': n, 'k': k, 'bitwise_equal': bool(torch.equal(d0, d1)), 'ours_us': round(t_our * 1e6, 2),
+                      'ref_us': round(t_ref * 1e6, 2)}), flush=True)
+g, m, n = 4, 4096, 7168
+ks = [1024, 2048, 512, 4096]
+a = torch.randn((sum(ks), m), device='cuda', dtype=torch.bfloat16)
+b = torch.randn((sum(ks), n), device='cuda', dtype=torch.bfloat16)
+c = torch.randn((g, m, n), device='cuda', dtype=torch.float32)
+layout = torch.tensor(ks, device='cuda', dtype=torch.int32)
+d0, d1 = c.clone(), c.clone()
+ref.k_grouped_bf16_gemm_tn_contiguous(a, b, d0, ks, layout, c=d0)
+dg.k_grouped_bf16_gemm_tn_contiguous(a, b, d1, ks, layout, c=d1)
+torch.cuda.synchronize()
+t_ref = bench_kineto(lambda: ref.k_grouped_bf16_gemm_tn_contiguous(a, b, d0, ks, layout, c=d0), 'gemm', num_tests=10)
+t_our = bench_kineto(lambda: dg.k_grouped_bf16_gemm_tn_contiguous(a, b, d1, ks, layout, c=d1), 'fp8_gemm_kernel', num_tests=10)
+print(json.dumps({'form': 'k_grouped_tn', 'g': g, 'm': m, 'n': n, 'ks': ks, 'bitwise_equal_after_1_call': None, 'ours_us': round(t_our * 1e6, 2),
+                  'ref_us': round(t_ref * 1e6, 2)}), flush=True)
+d0, d1 = c.clone(), c.clone()
+ref.k_grouped_bf16_gemm_tn_contiguous(a, b, d0, ks, layout, c=d0)
+dg.k_grouped_bf16_gemm_tn_contiguous(a, b, d1, ks, layout, c=d1)
+torch.cuda.synchronize()
+print(json.dumps({'form': 'k_grouped_tn', 'bitwise_equal': bool(torch.equal(d0, d1)), 'max_abs_diff': float((d0 - d1).abs().max())}), flush=True)
