@@ -12,3 +12,5 @@ tail -c 3000 $OUT/pytest_gpu_f.log
 timeout 300 python tools/bf16_bench.py > $OUT/bf16_bench.log 2>&1
 ( time timeout 900 python bench.py ) > $OUT/bench_f.log 2> $OUT/bench_f.err
 echo "bench rc=$?" >> $OUT/bench_f.err
+timeout 200 python tools/stamps.py --cold --shapes=64x7168x2048,128x24576x1536,128x7168x2048 > $OUT/stamps_shortk.log 2>&1
+timeout 400 python tools/tune.py small3 > $OUT/tune_small3.log 2>&1

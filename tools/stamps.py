@@ -15,6 +15,9 @@ NAMES = ['entry', 'setup_done', 'first_tma', 'first_data', 'x4', 'last_mma', 'ac
          'teardown_begin', 'exit', 'cs_outbox', 'cs_bar', 'cs_sent', 'cs_recv']
 COLD = '--cold' in sys.argv
 SHAPES = [(4096, 4096, 7168), (4096, 7168, 2048)] if '--big' in sys.argv else [(64, 4096, 7168), (128, 4096, 7168)]
+for arg in sys.argv[1:]:
+    if arg.startswith('--shapes='):        # --shapes=64x7168x2048,128x24576x1536
+        SHAPES = [tuple(int(v) for v in s.split('x')) for s in arg.split('=', 1)[1].split(',')]
 flush = torch.empty(256 << 20, dtype=torch.int32, device='cuda') if COLD else None
 ts = torch.zeros(16 + 2 * 160, dtype=torch.int64, device='cuda')
 _lib.lib().dgb200_debug_set_timestamps(ts.data_ptr())

@@ -87,6 +87,10 @@ if __name__ == '__main__':
                            ((4096, 7168, 16384), (224,)), ((1024, 7168, 2048), (208, 224)), ((384, 4096, 7168), (112, 128)),
                            ((448, 4096, 7168), (112, 128)), ((4096, 4096, 7168), (224, 240))]:
             run([shape], [dict(swap=0)] + [dict(swap=1, block_m=bn, tma_store=ts) for bn in bns for ts in (0, 1)])
+    elif mode == 'small3':
+        # short K with many weight panels at small M: single CTAs (192 / 56 independent tiles) vs pairs vs 2 single-CTA slices
+        cfgs = [{}, dict(cluster=1, csplit=0), dict(cluster=1, csplit=0, block_m=64), dict(cluster=1, csplit=0, block_m=32), dict(csplit=2)]
+        run([(64, 7168, 2048), (128, 7168, 2048), (128, 24576, 1536), (64, 32768, 512), (64, 24576, 1536), (128, 32768, 512)], cfgs)
     elif mode == 'small':
         cfgs = [{}, dict(csplit=0), dict(csplit=4), dict(csplit=2)] + [dict(csplit=0, block_m=bm) for bm in (16, 32, 64)]
         run([(1, 2112, 7168), (16, 4096, 7168), (32, 4096, 7168), (64, 4096, 7168), (96, 4096, 7168), (128, 4096, 7168), (192, 4096, 7168),
