@@ -443,7 +443,7 @@ int run_gemm(const GemmCall& c) {
     const bool head_split = c.head_mid > 0;
     Problem pb{c.type, c.m, c.expected_m, c.n, c.k, c.groups, c.alignment};
     pb.x_mn = c.x_mn, pb.any_mn = c.x_mn || c.w_mn;
-    pb.swapped = c.swap_d, pb.forced_block_m = c.forced_block_m, pb.plain_only = c.bf16_ab;
+    pb.swapped = c.swap_d, pb.forced_block_m = c.forced_block_m, pb.plain_only = c.bf16_ab && !(c.type == kDense && !c.x_mn && !c.w_mn);   // BF16: cluster split-K is built for dense K-major only
     // TMA stores need a 16-byte aligned base and row pitch; tiles that must not touch rows past `valid_m` (masked, psum),
     // accumulate into C or remap columns keep the predicated direct stores
     pb.tma_store_ok = (c.type == kDense || c.type == kMContiguous) && !c.bf16_ab && c.d_dtype == DGB200_BF16 && !c.accumulate && !head_split &&

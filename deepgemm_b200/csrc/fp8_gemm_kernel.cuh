@@ -365,6 +365,54 @@ __device__ __forceinline__ void store_out<__nv_bfloat16>(__nv_bfloat16* ptr, flo
     *ptr = r;
 }
 
+__device__ __forceinline__ float as_f32(float v) { return v; }
+__device__ __forceinline__ float as_f32(uint32_t v) { return __uint_as_float(v); }
+
+// kRows consecutive output rows of one warp-wide column group (row r at `row + r * row_bytes`), the first `valid` of them
+// written. Accumulating into C reads ALL the rows first and only then adds and stores: written as one read-modify-write
+// per row the loads serialise behind the (possibly aliasing) stores, one DRAM round trip per row -- the k-grouped
+// weight-gradient GEMM ran 4.5x slower than the reference that way.
+template <typename out_t, uint32_t kRows, bool kAccumulate, typename value_t>
+__device__ __forceinline__ void store_rows(char* row, size_t row_bytes, const value_t* v, uint32_t valid) {
+    if constexpr (kAccumulate) {
+        out_t prev[kRows];
+        if (valid >= kRows) {
+#pragma unroll
+            for (uint32_t j = 0; j < kRows; ++j) prev[j] = *reinterpret_cast<const out_t*>(row + j * row_bytes);
+#pragma unroll
+            for (uint32_t j = 0; j < kRows; ++j) {
+                const float x = as_f32(v[j]);
+                if constexpr (std::is_same_v<out_t, float>)
+                    *reinterpret_cast<float*>(row + j * row_bytes) = x + prev[j];
+                else   // the reference's memory-side reduce on a BF16 tile (epilogue/sm100_store_cd.cuh:126-128): round, then one BF16 add
+                    *reinterpret_cast<__nv_bfloat16*>(row + j * row_bytes) = __hadd(__float2bfloat16_rn(x), prev[j]);
+            }
+        } else {
+#pragma unroll
+            for (uint32_t j = 0; j < kRows; ++j)
+                if (j < valid) prev[j] = *reinterpret_cast<const out_t*>(row + j * row_bytes);
+#pragma unroll
+            for (uint32_t j = 0; j < kRows; ++j)
+                if (j < valid) {
+                    const float x = as_f32(v[j]);
+                    if constexpr (std::is_same_v<out_t, float>)
+                        *reinterpret_cast<float*>(row + j * row_bytes) = x + prev[j];
+                    else
+                        *reinterpret_cast<__nv_bfloat16*>(row + j * row_bytes) = __hadd(__float2bfloat16_rn(x), prev[j]);
+                }
+        }
+    } else {
+        if (valid >= kRows) {
+#pragma unroll
+            for (uint32_t j = 0; j < kRows; ++j) store_out<out_t>(reinterpret_cast<out_t*>(row + j * row_bytes), as_f32(v[j]), false);
+        } else {
+#pragma unroll
+            for (uint32_t j = 0; j < kRows; ++j)
+                if (j < valid) store_out<out_t>(reinterpret_cast<out_t*>(row + j * row_bytes), as_f32(v[j]), false);
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ the kernel
 // Shared memory: `num_stages` contiguous stage slots, then the barriers.
 //   slot  = [ W 128x128 B | X load_m x 128 B | SFW 512 B | SFX groups x 512 B | pad to 1 KB ]
@@ -456,6 +504,17 @@ fp8_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
 
     const uint32_t warp_idx = __shfl_sync(0xffffffffu, threadIdx.x / 32, 0);
     const uint32_t lane = lane_id();
+#ifdef DGB_WARM_PARAMS
+    // Experiment: the kernel parameter block (5 tensor maps + GemmParams, ~14 lines of 64 B) is freshly written by every
+    // launch, so the first instruction that needs a line waits for it from memory, one line after the other along the
+    // producer's dependent path. Here every warp touches one line at entry so that the misses overlap.
+    if (lane == 0) {
+        constexpr uint32_t kParamLines = (sizeof(GemmParams) + 63) / 64;
+        const char* line = warp_idx < kParamLines ? reinterpret_cast<const char*>(&p) + 64 * warp_idx
+                                                  : reinterpret_cast<const char*>(&map_x) + 64 * (warp_idx - kParamLines);
+        if (warp_idx < kParamLines + 8) (void)*reinterpret_cast<const volatile uint32_t*>(line);
+    }
+#endif
     if (threadIdx.x == 0) DGB_STAMP(0);
     if (threadIdx.x == 0 && p.debug_ts != nullptr) p.debug_ts[16 + 2 * blockIdx.x] = globaltimer_ns();   // per-CTA entry
     constexpr int kCtaGroup = kCSplit ? kCluster / kCSplit : (kCluster >= 2 ? 2 : 1);   // CTAs per UMMA (cta_group)
@@ -479,7 +538,7 @@ fp8_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
                   "the TMA-store epilogue is built for plain BF16 output tiles");
     static_assert(!kSwapD || (kGemmType == kDense && !kXMn && !kWMn && !kSplitK && !kCSplit && kCluster <= 2),
                   "the transposed-output orientation is built for plain dense K-major problems");
-    static_assert(!kBf16AB || (!kSplitK && !kCSplit && !kSwapD && kCluster <= 2), "BF16 operands: plain kernels");
+    static_assert(!kBf16AB || (!kSplitK && !kSwapD && (kCluster <= 2 || kCSplit)), "BF16 operands: plain and cluster split-K kernels");
     // Operand bytes per element, and what one pipeline stage / one UMMA covers along K in ELEMENTS (= rows of an MN-major
     // operand): FP8 128 / 32, BF16 64 / 16. Everything K-major is addressed in bytes and does not care.
     constexpr uint32_t kEl = kBf16AB ? 2 : 1;
@@ -625,6 +684,7 @@ fp8_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
         // (`elect_one()` right at the branch: ptxas then knows the region is single-threaded and keeps every TMA operand in
         // uniform registers; behind a plain bool it falls back to R2UR.BROADCAST waterfall loops, ~2x slower per k-block)
         if (elect_one()) {
+            DGB_STAMP(4);
             Scheduler<kGemmType, kCluster, kSplitK, kCSplit> sched(p, cta_rank, split_rank);
             Tile t;
             const uint32_t ab_bytes = kWTileBytes + x_tile_bytes;
@@ -663,6 +723,7 @@ fp8_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
                     const uint32_t full = full_bar + ring.bar, slot = smem_base + ring.slot;
                     if (fresh) --fresh; else mbar_wait(empty_bar + ring.bar, ring.phase ^ 1);
                     const bool first = kb == t.kb_begin;
+                    if (first) DGB_STAMP(14);
                     const bool load_sfw = !kBf16AB && ((kb & sfw_mask) == 0 || first), load_sfx = !kBf16AB && ((kb & sfx_mask) == 0 || first);
                     mbar_arrive_expect_tx(full, ab_bytes + (load_sfw ? sfw_tx : 0u) + (load_sfx ? sfx_tx : 0u));
                     if constexpr (kGemmType == kBatched) {
@@ -941,14 +1002,7 @@ fp8_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
                     const uint32_t r0 = split_rank * c + u * 8;               // first token row of this unit in the tile
                     if (n_ok && r0 < t.valid_m) {
                         char* row = d_col + static_cast<size_t>(r0) * row_bytes;
-                        if (r0 + 8 <= t.valid_m) {
-#pragma unroll
-                            for (uint32_t j = 0; j < 8; ++j, row += row_bytes) store_out<out_t>(reinterpret_cast<out_t*>(row), acc[j], kAccumulate);
-                        } else {
-#pragma unroll
-                            for (uint32_t j = 0; j < 8; ++j, row += row_bytes)
-                                if (r0 + j < t.valid_m) store_out<out_t>(reinterpret_cast<out_t*>(row), acc[j], kAccumulate);
-                        }
+                        store_rows<out_t, 8, kAccumulate>(row, row_bytes, acc, t.valid_m - r0);
                     }
                 }
                 tcgen05_fence_before();
@@ -1162,20 +1216,9 @@ fp8_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
                 char* row = d_col + static_cast<size_t>(c0) * row_bytes;
                 if (n_ok) {
 #pragma unroll
-                    for (uint32_t h = 0; h < 2; ++h) {
+                    for (uint32_t h = 0; h < 2; ++h) {       // full 16-row halves take the path without per-row predicates
                         const uint32_t r0 = c0 + h * 16;
-                        if (r0 + 16 <= t.valid_m) {          // full 16-row half: no per-row predicates
-#pragma unroll
-                            for (uint32_t j = 0; j < 16; ++j)
-                                store_out<out_t>(reinterpret_cast<out_t*>(row + (h * 16 + j) * row_bytes),
-                                                 __uint_as_float(v[h * 16 + j]), kAccumulate);
-                        } else if (r0 < t.valid_m) {
-#pragma unroll
-                            for (uint32_t j = 0; j < 16; ++j)
-                                if (r0 + j < t.valid_m)
-                                    store_out<out_t>(reinterpret_cast<out_t*>(row + (h * 16 + j) * row_bytes),
-                                                     __uint_as_float(v[h * 16 + j]), kAccumulate);
-                        }
+                        if (r0 < t.valid_m) store_rows<out_t, 16, kAccumulate>(row + h * 16 * row_bytes, row_bytes, &v[h * 16], t.valid_m - r0);
                     }
                 }
             }

@@ -1,10 +1,11 @@
 """GPU parity tests of the BF16-operand GEMMs (fp8_gemm_kernel<..., kBf16AB>; reference bf16_gemm_nt,
 m_grouped_bf16_gemm_nt_contiguous, m_grouped_bf16_gemm_nt_masked, csrc/apis/gemm.hpp:404-564).
 
-Plain PyTorch FP32 reference for a floating-point kernel: BF16 inputs are exact in FP32, so `a.float() @ b.float().T` (TF32
-off) differs from the kernel only by the FP32 accumulation order inside the tensor core; the reference's own bound for its
-BF16 kernels is calc_diff < 1e-5 (tests/test_bf16.py). Against the reference's kernel on the same inputs the output is
-bit-identical (digests in tests/golden/gpu_digests.json, keys `bf16_*`, when generated)."""
+Floating-point kernel, so the checker is a plain PyTorch matmul of the same op: BF16 inputs are exact in FP64, and
+`a.double() @ b.double().T` differs from the kernel only by the FP32 accumulation order inside the tensor core (tolerance in
+`_close`; the reference's own bound for its BF16 kernels is calc_diff < 1e-5, tests/test_bf16.py). Against the reference's
+kernel on the same inputs the output is bit-identical (digests in tests/golden/gpu_digests.json, keys `bf16_*`;
+tools/bf16_bench.py re-checks it live, MN-major and k-grouped forms included)."""
 import json
 import os
 import random
@@ -30,14 +31,18 @@ def dg():
 
 
 def _close(d, ref, what=''):
+    """`ref` is the FP64 product of the (exact) BF16 inputs. Stated tolerance: FP32 outputs within 3e-5 x max|D| (FP32
+    accumulation of up to 7168 terms in the tensor core's own order), BF16 outputs within one BF16 rounding step of it."""
     from deepgemm_b200.testing import calc_diff
+    ref = ref.double()
     assert not torch.isnan(d.float()).any(), what
     assert calc_diff(d, ref) < 1e-5, what
+    scale = float(ref.abs().max().clamp(min=1.0))
     if d.dtype == torch.float32:
-        assert ((d - ref).abs().max() / ref.abs().max().clamp(min=1.0)) < 1e-5, what
+        assert float((d.double() - ref).abs().max()) < 3e-5 * scale, what
     else:
-        err = (d.float() - ref).abs()
-        assert bool((err <= ref.abs() * 2.0 ** -7 + 1e-5 * ref.abs().max()).all()), what
+        err = (d.double() - ref).abs()
+        assert bool((err <= ref.abs() * 2.0 ** -7 + 3e-5 * scale).all()), what
 
 
 @pytest.mark.parametrize('m,n,k', [(128, 128, 128), (1, 576, 512), (64, 4096, 7168), (300, 2112, 1536), (4096, 4096, 2048), (97, 136, 200)])
@@ -49,16 +54,16 @@ def test_bf16_gemm_nt_matches_fp32_matmul(dg, m, n, k, out_dtype):
     buf = torch.full((m + 8, n + 16), 222.0, device='cuda', dtype=out_dtype)
     d = buf[:m, :n]
     dg.bf16_gemm_nt(a, b, d)
-    ref = a.float() @ b.float().t()
+    ref = a.double() @ b.double().t()
     _close(d, ref, f'{m}x{n}x{k}')
     assert bool((buf[m:] == 222.0).all()) and bool((buf[:, n:] == 222.0).all())
     # accumulate into C
     c = (torch.randn((m, n), device='cuda') * 4).to(out_dtype)
     d2 = c.clone()
     dg.bf16_gemm_nt(a, b, d2, c=d2)
-    want = (ref.to(torch.bfloat16).float() + c.float()) if out_dtype == torch.bfloat16 else ref + c
+    want = (ref.to(torch.bfloat16).float() + c.float()) if out_dtype == torch.bfloat16 else ref.float() + c
     err = (d2.float() - want).abs()
-    mag = ref.abs() + c.float().abs()
+    mag = ref.float().abs() + c.float().abs()
     assert bool((err <= mag * 2.0 ** -6 + 1e-5 * mag.max()).all())
 
 
@@ -104,7 +109,7 @@ def test_bf16_gemm_mn_major_operands_give_the_k_major_bits(dg, m, n, k, majors):
     for out_dtype in (torch.bfloat16, torch.float32):
         base = torch.empty((m, n), device='cuda', dtype=out_dtype)
         dg.bf16_gemm_nt(a, b, base)
-        _close(base, a.float() @ b.float().t())
+        _close(base, a.double() @ b.double().t())
         buf = torch.full((m + 8, n + 16), 222.0, device='cuda', dtype=out_dtype)
         d = buf[:m, :n]
         if majors == 'nn':

@@ -11,8 +11,8 @@ from tools.bringup import make_inputs  # noqa: E402
 import deepgemm_b200 as dg  # noqa: E402
 from deepgemm_b200 import _lib  # noqa: E402
 
-NAMES = ['entry', 'setup_done', 'first_tma', 'first_data', 'x4', 'last_mma', 'acc_ready', 'stores_issued',
-         'teardown_begin', 'exit', 'cs_outbox', 'cs_bar', 'cs_sent', 'cs_recv']
+NAMES = ['entry', 'setup_done', 'first_tma', 'first_data', 'producer_start', 'last_mma', 'acc_ready', 'stores_issued',
+         'teardown_begin', 'exit', 'cs_outbox', 'cs_bar', 'cs_sent', 'cs_recv', 'first_tile_known']
 COLD = '--cold' in sys.argv
 SHAPES = [(4096, 4096, 7168), (4096, 7168, 2048)] if '--big' in sys.argv else [(64, 4096, 7168), (128, 4096, 7168)]
 for arg in sys.argv[1:]:

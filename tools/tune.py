@@ -87,6 +87,10 @@ if __name__ == '__main__':
                            ((4096, 7168, 16384), (224,)), ((1024, 7168, 2048), (208, 224)), ((384, 4096, 7168), (112, 128)),
                            ((448, 4096, 7168), (112, 128)), ((4096, 4096, 7168), (224, 240))]:
             run([shape], [dict(swap=0)] + [dict(swap=1, block_m=bn, tma_store=ts) for bn in bns for ts in (0, 1)])
+    elif mode == 'ab_small':
+        # default configuration only, on the latency-bound shapes: used to A/B two builds of the library (DGB200_LIB)
+        run([(64, 4096, 7168), (128, 4096, 7168), (64, 7168, 2048), (128, 7168, 2048), (128, 24576, 1536), (64, 2112, 7168),
+             (256, 4096, 7168), (512, 4096, 7168), (512, 7168, 2048)], [{}])
     elif mode == 'small3':
         # short K with many weight panels at small M: single CTAs (192 / 56 independent tiles) vs pairs vs 2 single-CTA slices
         cfgs = [{}, dict(cluster=1, csplit=0), dict(cluster=1, csplit=0, block_m=64), dict(cluster=1, csplit=0, block_m=32), dict(csplit=2)]
