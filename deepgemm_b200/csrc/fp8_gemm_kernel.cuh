@@ -369,38 +369,33 @@ __device__ __forceinline__ float as_f32(float v) { return v; }
 __device__ __forceinline__ float as_f32(uint32_t v) { return __uint_as_float(v); }
 
 // kRows consecutive output rows of one warp-wide column group (row r at `row + r * row_bytes`), the first `valid` of them
-// written. Accumulating into C reads ALL the rows first and only then adds and stores: written as one read-modify-write
-// per row the loads serialise behind the (possibly aliasing) stores, one DRAM round trip per row -- the k-grouped
-// weight-gradient GEMM ran 4.5x slower than the reference that way.
+// written. Accumulating into C:
+//  * FP32: a memory-side add, `red.global.add.f32` (one per element, 128 contiguous bytes per warp instruction): the add
+//    happens in L2, nothing comes back to the SM -- the same thing the reference's TMA reduce-add does
+//    (epilogue/sm100_store_cd.cuh:126-128, `cp.reduce.async.bulk ... add.f32`), incl. its flush of subnormals.
+//  * BF16: round the accumulator, then one BF16 add (the reference's `add.noftz.bf16` reduce); all rows are READ first and
+//    only then added and stored -- as one read-modify-write per row the loads serialise behind the (possibly aliasing)
+//    stores, one DRAM round trip per row (the k-grouped weight-gradient GEMM ran 4.5x slower than the reference that way).
 template <typename out_t, uint32_t kRows, bool kAccumulate, typename value_t>
 __device__ __forceinline__ void store_rows(char* row, size_t row_bytes, const value_t* v, uint32_t valid) {
-    if constexpr (kAccumulate) {
-        out_t prev[kRows];
+    if constexpr (kAccumulate && std::is_same_v<out_t, float>) {
         if (valid >= kRows) {
 #pragma unroll
-            for (uint32_t j = 0; j < kRows; ++j) prev[j] = *reinterpret_cast<const out_t*>(row + j * row_bytes);
-#pragma unroll
-            for (uint32_t j = 0; j < kRows; ++j) {
-                const float x = as_f32(v[j]);
-                if constexpr (std::is_same_v<out_t, float>)
-                    *reinterpret_cast<float*>(row + j * row_bytes) = x + prev[j];
-                else   // the reference's memory-side reduce on a BF16 tile (epilogue/sm100_store_cd.cuh:126-128): round, then one BF16 add
-                    *reinterpret_cast<__nv_bfloat16*>(row + j * row_bytes) = __hadd(__float2bfloat16_rn(x), prev[j]);
-            }
+            for (uint32_t j = 0; j < kRows; ++j)
+                asm volatile("red.global.add.f32 [%0], %1;" ::"l"(row + j * row_bytes), "f"(as_f32(v[j])) : "memory");
         } else {
 #pragma unroll
             for (uint32_t j = 0; j < kRows; ++j)
-                if (j < valid) prev[j] = *reinterpret_cast<const out_t*>(row + j * row_bytes);
-#pragma unroll
-            for (uint32_t j = 0; j < kRows; ++j)
-                if (j < valid) {
-                    const float x = as_f32(v[j]);
-                    if constexpr (std::is_same_v<out_t, float>)
-                        *reinterpret_cast<float*>(row + j * row_bytes) = x + prev[j];
-                    else
-                        *reinterpret_cast<__nv_bfloat16*>(row + j * row_bytes) = __hadd(__float2bfloat16_rn(x), prev[j]);
-                }
+                if (j < valid) asm volatile("red.global.add.f32 [%0], %1;" ::"l"(row + j * row_bytes), "f"(as_f32(v[j])) : "memory");
         }
+    } else if constexpr (kAccumulate) {
+        __nv_bfloat16 prev[kRows];
+#pragma unroll
+        for (uint32_t j = 0; j < kRows; ++j)
+            if (j < valid) prev[j] = *reinterpret_cast<const __nv_bfloat16*>(row + j * row_bytes);
+#pragma unroll
+        for (uint32_t j = 0; j < kRows; ++j)
+            if (j < valid) *reinterpret_cast<__nv_bfloat16*>(row + j * row_bytes) = __hadd(__float2bfloat16_rn(as_f32(v[j])), prev[j]);
     } else {
         if (valid >= kRows) {
 #pragma unroll
@@ -505,14 +500,17 @@ fp8_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
     const uint32_t warp_idx = __shfl_sync(0xffffffffu, threadIdx.x / 32, 0);
     const uint32_t lane = lane_id();
 #ifdef DGB_WARM_PARAMS
-    // Experiment: the kernel parameter block (5 tensor maps + GemmParams, ~14 lines of 64 B) is freshly written by every
-    // launch, so the first instruction that needs a line waits for it from memory, one line after the other along the
-    // producer's dependent path. Here every warp touches one line at entry so that the misses overlap.
+    // Experiment: the kernel parameter block (5 tensor maps + 3 lines of GemmParams) is freshly written by every launch, so
+    // the first instruction that needs a line waits for it from memory -- one miss after the other along the producer's
+    // dependent path (first tile known ~600 cycles after the producer starts). Line 0 of GemmParams is read by everyone right
+    // below; here every thread also reads one field of lines 1 and 2, and idle warps fetch the tensor-map descriptors.
+    asm volatile("" ::"r"(p.num_splits), "r"(p.num_n_units));
     if (lane == 0) {
-        constexpr uint32_t kParamLines = (sizeof(GemmParams) + 63) / 64;
-        const char* line = warp_idx < kParamLines ? reinterpret_cast<const char*>(&p) + 64 * warp_idx
-                                                  : reinterpret_cast<const char*>(&map_x) + 64 * (warp_idx - kParamLines);
-        if (warp_idx < kParamLines + 8) (void)*reinterpret_cast<const volatile uint32_t*>(line);
+        if (warp_idx == 4) prefetch_tensormap(&map_w);
+        if (warp_idx == 5) prefetch_tensormap(&map_x);
+        if (warp_idx == 6 && !kBf16AB) prefetch_tensormap(&map_sfw);
+        if (warp_idx == 7 && !kBf16AB) prefetch_tensormap(&map_sfx);
+        if (warp_idx == 8 && kTmaStore) prefetch_tensormap(&map_d);
     }
 #endif
     if (threadIdx.x == 0) DGB_STAMP(0);

@@ -30,6 +30,15 @@ def dg():
     return deepgemm_b200
 
 
+@pytest.fixture
+def no_split_k(dg):
+    """Cluster split-K (dense, K-major, M <= ~256) adds the K slices in slice order: within FP32 rounding of the one-pass
+    kernel, not bit-identical to it. Bit-for-bit comparisons switch it off, as `set_split_k(False)` does for a user."""
+    dg.set_split_k(False)
+    yield
+    dg.set_split_k(True)
+
+
 def _close(d, ref, what=''):
     """`ref` is the FP64 product of the (exact) BF16 inputs. Stated tolerance: FP32 outputs within 3e-5 x max|D| (FP32
     accumulation of up to 7168 terms in the tensor core's own order), BF16 outputs within one BF16 rounding step of it."""
@@ -67,6 +76,38 @@ def test_bf16_gemm_nt_matches_fp32_matmul(dg, m, n, k, out_dtype):
     assert bool((err <= mag * 2.0 ** -6 + 1e-5 * mag.max()).all())
 
 
+@pytest.mark.parametrize('m,n,k', [(64, 4096, 7168), (128, 2112, 7168), (17, 576, 4096), (192, 4096, 7168), (256, 2112, 7168)])
+def test_bf16_cluster_split_k_stays_within_fp32_rounding(dg, m, n, k):
+    """Default configuration at small / medium M: K slices reduced through distributed shared memory (as for FP8 operands)."""
+    from deepgemm_b200 import _lib
+    a = torch.randn((m, k), device='cuda', dtype=torch.bfloat16)
+    b = torch.randn((n, k), device='cuda', dtype=torch.bfloat16)
+    ref = a.double() @ b.double().t()
+    for out_dtype in (torch.bfloat16, torch.float32):
+        d = torch.empty((m, n), device='cuda', dtype=out_dtype)
+        dg.bf16_gemm_nt(a, b, d)
+        cfg = _lib.last_config()
+        _close(d, ref, f'{m}x{n}x{k} {cfg}')
+        dg.set_split_k(False)
+        try:
+            one = torch.empty_like(d)
+            dg.bf16_gemm_nt(a, b, one)
+        finally:
+            dg.set_split_k(True)
+        if cfg['cluster_split']:
+            frac = float((one != d).float().mean())
+            assert frac < (0.01 if out_dtype == torch.bfloat16 else 1.0), frac      # BF16: a rounding step on a few outputs at most
+        else:
+            assert torch.equal(one, d)
+        c = torch.randn((m, n), device='cuda').to(out_dtype)
+        acc = c.clone()
+        dg.bf16_gemm_nt(a, b, acc, c=acc)
+        want = ref.to(torch.bfloat16).double() + c.double() if out_dtype == torch.bfloat16 else ref + c.double()
+        err = (acc.double() - want).abs()
+        mag = ref.abs() + c.double().abs()
+        assert bool((err <= mag * 2.0 ** -6 + 3e-5 * float(mag.max())).all())
+
+
 def test_bf16_gemm_every_tile_config_gives_identical_bits(dg, monkeypatch):
     m, n, k = 500, 1024, 1024
     a = torch.randn((m, k), device='cuda', dtype=torch.bfloat16)
@@ -83,7 +124,7 @@ def test_bf16_gemm_every_tile_config_gives_identical_bits(dg, monkeypatch):
         monkeypatch.delenv('DGB200_STAGES', raising=False)
 
 
-def test_bf16_transposed_wrappers_on_k_major_views(dg):
+def test_bf16_transposed_wrappers_on_k_major_views(dg, no_split_k):
     a = torch.randn((256, 512), device='cuda', dtype=torch.bfloat16)
     b = torch.randn((384, 512), device='cuda', dtype=torch.bfloat16)
     d0 = torch.empty((256, 384), device='cuda', dtype=torch.bfloat16)
@@ -98,7 +139,7 @@ def test_bf16_transposed_wrappers_on_k_major_views(dg):
 
 @pytest.mark.parametrize('m,n,k', [(128, 128, 128), (64, 4096, 7168), (304, 2112, 1536), (4096, 4096, 2048), (96, 136, 200), (8, 576, 512)])
 @pytest.mark.parametrize('majors', ['nn', 'tn', 'tt'])
-def test_bf16_gemm_mn_major_operands_give_the_k_major_bits(dg, m, n, k, majors):
+def test_bf16_gemm_mn_major_operands_give_the_k_major_bits(dg, no_split_k, m, n, k, majors):
     """Genuinely MN-major operands (bf16_gemm_{nn,tn,tt}, gemm.hpp:440-462): the same products summed in the same order, so the
     output must equal the K-major launch bit for bit."""
     gen = torch.Generator(device='cuda').manual_seed(m * 3 + n + k)
@@ -265,7 +306,7 @@ def test_m_grouped_bf16_masked(dg):
 
 
 @pytest.mark.parametrize('m,n,k', [(128, 2112, 7168), (4096, 7168, 2048), (64, 576, 7168)])
-def test_bf16_matches_the_reference_kernel_bit_for_bit(dg, m, n, k):
+def test_bf16_matches_the_reference_kernel_bit_for_bit(dg, no_split_k, m, n, k):
     path = os.path.join(HERE, 'golden', 'gpu_digests.json')
     key = f'bf16_{m}x{n}x{k}'
     digests = json.load(open(path)) if os.path.exists(path) else {}
