@@ -95,6 +95,8 @@ struct GemmParams {
     uint32_t x_swizzle;         // MN-major tokens: swizzle width in bytes (128 / 64 / 32) = rows of one TMA box
     uint32_t sf_k_span;         // k-grouped: K elements covered by one packed SF word (4 * gran_k)
     uint32_t k_shift;           // k-grouped: log2(bytes per operand element); the group sizes arrive in elements, K is walked in bytes
+    uint32_t grid_tiles;        // dense, one wave: exactly one tile per cluster, addressed by the 2-D grid (blockIdx.x / cluster =
+                                // n-unit, blockIdx.y = m-block) -- the first tile is known without the ~500 cycles of index arithmetic
     uint64_t d_batch_stride;    // batched: elements between consecutive batches of D (0 otherwise)
     // Head-split output remap (fp8_gemm_nt_skip_head_mid, attention.hpp:19-74 / epilogue/transform.cuh:15-22): output
     // column n is stored at n + (n + head_right) / head_lr * head_mid, i.e. every (left | right) head of the GEMM's N
@@ -246,7 +248,12 @@ struct Scheduler {
                 return false;
             }
 
-            split(local, num_m, m_blk, n_unit);
+            if (kGemmType == kDense && !kSplitK && kPairs == 1 && p.grid_tiles) {
+                if (iter != 1) return false;                                 // (iter was advanced above) one tile per cluster
+                m_blk = blockIdx.y, n_unit = cluster_id;
+            } else {
+                split(local, num_m, m_blk, n_unit);
+            }
             m_blk = m_blk * kPairs + (cta_rank >> 1);                        // this pair's m-block inside the group
             uint32_t height = p.block_m;
             t.x_row = m_blk * p.block_m;
@@ -460,7 +467,7 @@ __device__ __forceinline__ void splitk_finalize(const float* ws, size_t slice_el
 
 #define DGB_STAMP(i)                                                            \
     do {                                                                        \
-        if (p.debug_ts != nullptr && blockIdx.x == 0) p.debug_ts[i] = clock64(); \
+        if (p.debug_ts != nullptr && blockIdx.x == 0 && blockIdx.y == 0) p.debug_ts[i] = clock64(); \
     } while (0)
 
 // kXMn / kWMn: the token / weight operand is MN-major in global memory (its M / N extent is contiguous, K strided):
@@ -499,20 +506,6 @@ fp8_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
 
     const uint32_t warp_idx = __shfl_sync(0xffffffffu, threadIdx.x / 32, 0);
     const uint32_t lane = lane_id();
-#ifdef DGB_WARM_PARAMS
-    // Experiment: the kernel parameter block (5 tensor maps + 3 lines of GemmParams) is freshly written by every launch, so
-    // the first instruction that needs a line waits for it from memory -- one miss after the other along the producer's
-    // dependent path (first tile known ~600 cycles after the producer starts). Line 0 of GemmParams is read by everyone right
-    // below; here every thread also reads one field of lines 1 and 2, and idle warps fetch the tensor-map descriptors.
-    asm volatile("" ::"r"(p.num_splits), "r"(p.num_n_units));
-    if (lane == 0) {
-        if (warp_idx == 4) prefetch_tensormap(&map_w);
-        if (warp_idx == 5) prefetch_tensormap(&map_x);
-        if (warp_idx == 6 && !kBf16AB) prefetch_tensormap(&map_sfw);
-        if (warp_idx == 7 && !kBf16AB) prefetch_tensormap(&map_sfx);
-        if (warp_idx == 8 && kTmaStore) prefetch_tensormap(&map_d);
-    }
-#endif
     if (threadIdx.x == 0) DGB_STAMP(0);
     if (threadIdx.x == 0 && p.debug_ts != nullptr) p.debug_ts[16 + 2 * blockIdx.x] = globaltimer_ns();   // per-CTA entry
     constexpr int kCtaGroup = kCSplit ? kCluster / kCSplit : (kCluster >= 2 ? 2 : 1);   // CTAs per UMMA (cta_group)
@@ -1107,6 +1100,7 @@ fp8_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
                     tmem_ld_32x32b_x16(taddr + u * kSwapStoreCols + 16, *reinterpret_cast<uint32_t(*)[16]>(&v[16]));
                     tmem_ld_wait();
                     if (u + 2 >= num_units) release_accumulator();
+#ifndef DGB_EXP_NO_STAGE
 #pragma unroll
                     for (uint32_t piece = 0; piece < 4; ++piece)
                         st_shared_v4(row_off + ((piece ^ sw) << 4), pack_bf16x2(v[8 * piece + 0], v[8 * piece + 1]),
@@ -1114,10 +1108,13 @@ fp8_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
                                      pack_bf16x2(v[8 * piece + 6], v[8 * piece + 7]));
                     fence_proxy_async_smem();
                     __syncwarp();
+#ifndef DGB_EXP_NO_STORE
                     if (lane == 0 && t.n0 + quad * 32 < p.n) {
                         tma_store_2d(&map_d, buf, t.d_row + u * kSwapStoreCols, t.n0 + quad * 32);
                         tma_store_commit();
                     }
+#endif
+#endif
                 }
                 continue;
             }

@@ -91,6 +91,10 @@ if __name__ == '__main__':
         # default configuration only, on the latency-bound shapes: used to A/B two builds of the library (DGB200_LIB)
         run([(64, 4096, 7168), (128, 4096, 7168), (64, 7168, 2048), (128, 7168, 2048), (128, 24576, 1536), (64, 2112, 7168),
              (256, 4096, 7168), (512, 4096, 7168), (512, 7168, 2048)], [{}])
+    elif mode == 'swap_exp':
+        # the transposed-output kernel at the reference's own tiling (256 x 224) beside the default orientation at equal depth
+        run([(4096, 7168, 2048)], [dict(swap=1, block_m=224, tma_store=1), dict(swap=0), dict(swap=0, block_m=224), dict(swap=0, block_m=224, stages=6),
+                                   dict(swap=0, block_m=208, stages=6), dict(swap=1, block_m=224, tma_store=1, stages=5)])
     elif mode == 'small3':
         # short K with many weight panels at small M: single CTAs (192 / 56 independent tiles) vs pairs vs 2 single-CTA slices
         cfgs = [{}, dict(cluster=1, csplit=0), dict(cluster=1, csplit=0, block_m=64), dict(cluster=1, csplit=0, block_m=32), dict(csplit=2)]
