@@ -380,9 +380,9 @@ Config choose_config(const Problem& pb, int num_sms_override = 0) {
     };
     c.tma_store = 0;
     if (pb.swapped) {
-        // transposed output: per-warp 32 x 32 staging (16 KB), tile width a multiple of 32 columns. DGB200_TMA_STORE pins it.
+        // transposed output: per-warp 32 x 64 staging (32 KB), tile width a multiple of 32 columns (>= 64). DGB200_TMA_STORE pins it.
         const int want = env_int("DGB200_TMA_STORE", -1);
-        c.tma_store = pb.tma_store_ok && c.block_m % (int)kSwapStoreCols == 0 && c.cluster <= 2 && (want >= 0 ? want != 0 : c.block_m >= kTmaStoreMinBlockM);
+        c.tma_store = pb.tma_store_ok && c.block_m % 32 == 0 && c.block_m >= (int)kSwapStoreCols && c.cluster <= 2 && (want >= 0 ? want != 0 : c.block_m >= kTmaStoreMinBlockM);
     } else if (pb.tma_store_ok && c.cluster == 2 && !c.csplit && c.num_splits == 1) {
         // Measured (tools/tune.py store): the staged epilogue wins 1-4 % on tall tiles with a long enough K loop to hide it
         // behind (4096 x 4096 x 7168, 4096 x 7168 x 2048, 4096 x 24576 x 1536 at 240 rows); it loses when it costs a pipeline
@@ -421,7 +421,7 @@ int want_swapped_orientation(const GemmCall& c, int num_sms_override = 0) {
     const int default_tiles = ceil_div(c.m, dflt.block_m) * ceil_div(c.n, 2 * (int)kBlockN);
     if (default_tiles <= pairs || num_kb < 8) return 0;                       // already one round of pairs
     const int token_units = ceil_div(c.m, 2 * (int)kBlockN);
-    for (int bn = 128; bn <= 224; bn += (int)kSwapStoreCols)                   // the narrowest tiles that still make one round
+    for (int bn = 128; bn <= 224; bn += 32)                                    // the narrowest tiles that still make one round
         if (token_units * ceil_div(c.n, bn) <= pairs) return bn;
     return 0;
 }
@@ -513,9 +513,9 @@ int run_gemm(const GemmCall& c) {
                                 kBlockN, 1, CU_TENSOR_MAP_SWIZZLE_NONE)) return e;
     }
     if (cfg.tma_store && c.swap_d) {
-        // transposed output: D [tokens = c.n rows, weights = c.m columns]; box 32 columns (64 B swizzle atom) x 32 rows (one warp)
+        // transposed output: D [tokens = c.n rows, weights = c.m columns]; box 64 columns (128 B swizzle atom) x 32 rows (one warp)
         if (int e = make_map_2d(&maps.d, c.d, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, c.m, c.n, (uint64_t)c.ldd * 2, kSwapStoreCols, 32,
-                                CU_TENSOR_MAP_SWIZZLE_64B)) return e;
+                                CU_TENSOR_MAP_SWIZZLE_128B)) return e;
     } else if (cfg.tma_store) {
         // D [rows, N] BF16: box 64 columns (one 128 B swizzle atom) x 16 rows; rows / columns past the end are clipped
         if (int e = make_map_2d(&maps.d, c.d, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, c.n, c.m, (uint64_t)c.ldd * 2, 64, kStoreRows,

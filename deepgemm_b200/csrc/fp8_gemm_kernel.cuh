@@ -59,8 +59,8 @@ constexpr uint32_t kWTileBytes = kBlockN * kBlockK;  // 16 KB
 constexpr uint32_t kStoreRows = 16;                  // output rows per TMA store (one staging buffer = 16 rows x 128 columns bf16)
 constexpr uint32_t kStoreBufBytes = kStoreRows * kBlockN * 2;       // 4 KB: two 128B-swizzled boxes of 16 rows x 64 columns
 constexpr uint32_t kStoreStagingBytes = 2 * kStoreBufBytes;         // two buffers, shared by the eight epilogue warps
-constexpr uint32_t kSwapStoreCols = 32;              // transposed-output staged epilogue: columns per TMA store (64 B swizzle atom)
-constexpr uint32_t kSwapStoreBufBytes = 32 * kSwapStoreCols * 2;    // 2 KB: 32 output rows (one warp's lanes) x 32 columns bf16
+constexpr uint32_t kSwapStoreCols = 64;              // transposed-output staged epilogue: columns per TMA store (one 128 B swizzle atom)
+constexpr uint32_t kSwapStoreBufBytes = 32 * kSwapStoreCols * 2;    // 4 KB: 32 output rows (one warp's lanes) x 64 columns bf16
 constexpr uint32_t kSwapStagingBytes = 8 * kSwapStoreBufBytes;      // one buffer per epilogue warp
 
 struct GemmParams {
@@ -1085,32 +1085,42 @@ fp8_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
             if constexpr (kSwapD && kTmaStore) {
                 // ---------------------------------------------------------------- transposed output, staged TMA stores
                 // lane = output row, TMEM column = output column: no transpose needed. Every warp stages its own 32 rows x
-                // 32 columns (64 B per row, 64B-swizzled, one 2 KB buffer per warp) and stores them with one
+                // 64 columns (128 B per row, 128B-swizzled, one 4 KB buffer per warp) and stores them with one
                 // cp.async.bulk.tensor -- no cross-warp synchronisation at all. The two warps of a lane quadrant take alternate
-                // 32-column units; the tile width is a multiple of 32 (host), rows / columns past the end of D are clipped.
-                const uint32_t num_units = (load_cols + kSwapStoreCols - 1) / kSwapStoreCols;   // (a ragged last tile: the map clips)
+                // 64-column units. Rows of 128 B matter: with 32-column units (64 B rows) the stores alone cost 5.5 us of a
+                // 43.7 us launch (4096 x 7168 x 2048; 38.2 with the stores compiled out, reference 40.9). A tile width that is
+                // not a multiple of 64 (224 = 3.5 units) makes its LAST unit end at the tile edge, re-writing up to 48 columns
+                // of the unit before it with the same values; columns past the end of D are clipped by the map.
+                const uint32_t num_units = (load_cols + kSwapStoreCols - 1) / kSwapStoreCols;
                 const uint32_t buf = staging + (warp_idx - 4) * kSwapStoreBufBytes;
-                const uint32_t row_off = buf + lane * 64, sw = (lane >> 1) & 3;
+                const uint32_t row_off = buf + lane * 128, sw = lane & 7;
                 if (half >= num_units) release_accumulator();
                 for (uint32_t u = half; u < num_units; u += 2) {
+                    const uint32_t c0 = ((u + 1) * kSwapStoreCols <= load_cols || load_cols < kSwapStoreCols) ? u * kSwapStoreCols
+                                                                                                             : load_cols - kSwapStoreCols;
+                    uint32_t packed[32];
+#pragma unroll
+                    for (uint32_t hh = 0; hh < 2; ++hh) {
+                        uint32_t v[32];
+                        tmem_ld_32x32b_x16(taddr + c0 + hh * 32, *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
+                        tmem_ld_32x32b_x16(taddr + c0 + hh * 32 + 16, *reinterpret_cast<uint32_t(*)[16]>(&v[16]));
+                        tmem_ld_wait();
+#pragma unroll
+                        for (uint32_t q = 0; q < 16; ++q) packed[hh * 16 + q] = pack_bf16x2(v[2 * q], v[2 * q + 1]);
+                    }
+                    if (u + 2 >= num_units) release_accumulator();
                     tma_store_wait_read<0>();                       // (only lane 0 owns bulk groups) the buffer has been read out
                     __syncwarp();
-                    uint32_t v[32];
-                    tmem_ld_32x32b_x16(taddr + u * kSwapStoreCols, *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
-                    tmem_ld_32x32b_x16(taddr + u * kSwapStoreCols + 16, *reinterpret_cast<uint32_t(*)[16]>(&v[16]));
-                    tmem_ld_wait();
-                    if (u + 2 >= num_units) release_accumulator();
 #ifndef DGB_EXP_NO_STAGE
 #pragma unroll
-                    for (uint32_t piece = 0; piece < 4; ++piece)
-                        st_shared_v4(row_off + ((piece ^ sw) << 4), pack_bf16x2(v[8 * piece + 0], v[8 * piece + 1]),
-                                     pack_bf16x2(v[8 * piece + 2], v[8 * piece + 3]), pack_bf16x2(v[8 * piece + 4], v[8 * piece + 5]),
-                                     pack_bf16x2(v[8 * piece + 6], v[8 * piece + 7]));
+                    for (uint32_t piece = 0; piece < 8; ++piece)
+                        st_shared_v4(row_off + ((piece ^ sw) << 4), packed[4 * piece + 0], packed[4 * piece + 1], packed[4 * piece + 2],
+                                     packed[4 * piece + 3]);
                     fence_proxy_async_smem();
                     __syncwarp();
 #ifndef DGB_EXP_NO_STORE
                     if (lane == 0 && t.n0 + quad * 32 < p.n) {
-                        tma_store_2d(&map_d, buf, t.d_row + u * kSwapStoreCols, t.n0 + quad * 32);
+                        tma_store_2d(&map_d, buf, t.d_row + c0, t.n0 + quad * 32);
                         tma_store_commit();
                     }
 #endif

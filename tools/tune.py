@@ -95,6 +95,12 @@ if __name__ == '__main__':
         # the transposed-output kernel at the reference's own tiling (256 x 224) beside the default orientation at equal depth
         run([(4096, 7168, 2048)], [dict(swap=1, block_m=224, tma_store=1), dict(swap=0), dict(swap=0, block_m=224), dict(swap=0, block_m=224, stages=6),
                                    dict(swap=0, block_m=208, stages=6), dict(swap=1, block_m=224, tma_store=1, stages=5)])
+    elif mode == 'swap3':
+        # the transposed-output kernel with 64-column staged stores against the default orientation, shapes with N = 7168 / 24576 / 4096
+        for shape, bns in [((4096, 7168, 2048), (224,)), ((4096, 7168, 16384), (224,)), ((1024, 7168, 2048), (224, 208)), ((2048, 7168, 2048), (224,)),
+                           ((512, 7168, 2048), (224, 192)), ((4096, 4096, 7168), (224, 240, 192)), ((4096, 24576, 1536), (224, 240, 192)),
+                           ((4096, 2112, 7168), (192, 224)), ((1024, 4096, 7168), (128, 224)), ((4096, 32768, 512), (224,)), ((2048, 4096, 7168), (224, 192))]:
+            run([shape], [dict(swap=0)] + [dict(swap=1, block_m=bn, tma_store=1) for bn in bns])
     elif mode == 'small3':
         # short K with many weight panels at small M: single CTAs (192 / 56 independent tiles) vs pairs vs 2 single-CTA slices
         cfgs = [{}, dict(cluster=1, csplit=0), dict(cluster=1, csplit=0, block_m=64), dict(cluster=1, csplit=0, block_m=32), dict(csplit=2)]
