@@ -380,9 +380,9 @@ Config choose_config(const Problem& pb, int num_sms_override = 0) {
     };
     c.tma_store = 0;
     if (pb.swapped) {
-        // transposed output: per-warp 32 x 64 staging (32 KB), tile width a multiple of 32 columns (>= 64). DGB200_TMA_STORE pins it.
+        // transposed output: per-warp 32 x 32 staging (16 KB), tile width a multiple of 32 columns. DGB200_TMA_STORE pins it.
         const int want = env_int("DGB200_TMA_STORE", -1);
-        c.tma_store = pb.tma_store_ok && c.block_m % 32 == 0 && c.block_m >= (int)kSwapStoreCols && c.cluster <= 2 && (want >= 0 ? want != 0 : c.block_m >= kTmaStoreMinBlockM);
+        c.tma_store = pb.tma_store_ok && c.block_m % (int)kSwapStoreCols == 0 && c.cluster <= 2 && (want >= 0 ? want != 0 : c.block_m >= kTmaStoreMinBlockM);
     } else if (pb.tma_store_ok && c.cluster == 2 && !c.csplit && c.num_splits == 1) {
         // Measured (tools/tune.py store): the staged epilogue wins 1-4 % on tall tiles with a long enough K loop to hide it
         // behind (4096 x 4096 x 7168, 4096 x 7168 x 2048, 4096 x 24576 x 1536 at 240 rows); it loses when it costs a pipeline
@@ -447,7 +447,8 @@ int run_gemm(const GemmCall& c) {
     // TMA stores need a 16-byte aligned base and row pitch; tiles that must not touch rows past `valid_m` (masked, psum),
     // accumulate into C or remap columns keep the predicated direct stores
     pb.tma_store_ok = (c.type == kDense || c.type == kMContiguous) && !c.bf16_ab && c.d_dtype == DGB200_BF16 && !c.accumulate && !head_split &&
-                      (reinterpret_cast<uintptr_t>(c.d) & 15) == 0 && (c.ldd * 2) % 16 == 0 && c.arrival == nullptr;
+                      (reinterpret_cast<uintptr_t>(c.d) & 15) == 0 && (c.ldd * 2) % 16 == 0 && c.arrival == nullptr &&
+                      (!c.swap_d || c.m % 8 == 0);    // (transposed output: 16-byte pieces must not straddle the last column)
     // split-K needs scratch: [4096 arrival counters][num_splits x m x n fp32 partial tiles]
     if (c.type == kDense && !head_split && !c.swap_d && c.workspace != nullptr && c.n % 4 == 0 && c.workspace_bytes > kSplitKHeaderBytes &&
         (reinterpret_cast<uintptr_t>(c.workspace) & 15) == 0) {
@@ -513,9 +514,7 @@ int run_gemm(const GemmCall& c) {
                                 kBlockN, 1, CU_TENSOR_MAP_SWIZZLE_NONE)) return e;
     }
     if (cfg.tma_store && c.swap_d) {
-        // transposed output: D [tokens = c.n rows, weights = c.m columns]; box 64 columns (128 B swizzle atom) x 32 rows (one warp)
-        if (int e = make_map_2d(&maps.d, c.d, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, c.m, c.n, (uint64_t)c.ldd * 2, kSwapStoreCols, 32,
-                                CU_TENSOR_MAP_SWIZZLE_128B)) return e;
+        // transposed output: staged through shared memory, written with plain 16-byte stores (no tensor map)
     } else if (cfg.tma_store) {
         // D [rows, N] BF16: box 64 columns (one 128 B swizzle atom) x 16 rows; rows / columns past the end are clipped
         if (int e = make_map_2d(&maps.d, c.d, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, c.n, c.m, (uint64_t)c.ldd * 2, 64, kStoreRows,

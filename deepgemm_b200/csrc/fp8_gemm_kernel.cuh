@@ -59,8 +59,8 @@ constexpr uint32_t kWTileBytes = kBlockN * kBlockK;  // 16 KB
 constexpr uint32_t kStoreRows = 16;                  // output rows per TMA store (one staging buffer = 16 rows x 128 columns bf16)
 constexpr uint32_t kStoreBufBytes = kStoreRows * kBlockN * 2;       // 4 KB: two 128B-swizzled boxes of 16 rows x 64 columns
 constexpr uint32_t kStoreStagingBytes = 2 * kStoreBufBytes;         // two buffers, shared by the eight epilogue warps
-constexpr uint32_t kSwapStoreCols = 64;              // transposed-output staged epilogue: columns per TMA store (one 128 B swizzle atom)
-constexpr uint32_t kSwapStoreBufBytes = 32 * kSwapStoreCols * 2;    // 4 KB: 32 output rows (one warp's lanes) x 64 columns bf16
+constexpr uint32_t kSwapStoreCols = 32;              // transposed-output staged epilogue: columns per unit (64 B per output row)
+constexpr uint32_t kSwapStoreBufBytes = 32 * kSwapStoreCols * 2;    // 2 KB: 32 output rows (one warp's lanes) x 32 columns bf16
 constexpr uint32_t kSwapStagingBytes = 8 * kSwapStoreBufBytes;      // one buffer per epilogue warp
 
 struct GemmParams {
@@ -623,7 +623,7 @@ fp8_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
                 prefetch_tensormap(&map_sfx);
                 prefetch_tensormap(&map_sfw);
             }
-            if constexpr (kTmaStore) prefetch_tensormap(&map_d);
+            if constexpr (kTmaStore && !kSwapD) prefetch_tensormap(&map_d);
         }
         __syncwarp();
     } else if (warp_idx == 1) {
@@ -1083,48 +1083,40 @@ fp8_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
                     mbar_arrive(tmem_empty_dst + as * 8);
             };
             if constexpr (kSwapD && kTmaStore) {
-                // ---------------------------------------------------------------- transposed output, staged TMA stores
-                // lane = output row, TMEM column = output column: no transpose needed. Every warp stages its own 32 rows x
-                // 64 columns (128 B per row, 128B-swizzled, one 4 KB buffer per warp) and stores them with one
-                // cp.async.bulk.tensor -- no cross-warp synchronisation at all. The two warps of a lane quadrant take alternate
-                // 64-column units. Rows of 128 B matter: with 32-column units (64 B rows) the stores alone cost 5.5 us of a
-                // 43.7 us launch (4096 x 7168 x 2048; 38.2 with the stores compiled out, reference 40.9). A tile width that is
-                // not a multiple of 64 (224 = 3.5 units) makes its LAST unit end at the tile edge, re-writing up to 48 columns
-                // of the unit before it with the same values; columns past the end of D are clipped by the map.
+                // ---------------------------------------------------------------- transposed output, staged through shared memory
+                // lane = output row, TMEM column = output column. Every warp turns its own 32 rows x 32 columns around in a
+                // private 2 KB buffer: each thread writes the 64 bytes of ITS row (4 x 16 B, XOR-swizzled), then lane L reads
+                // the 16 bytes (row 8i + L/4, piece L%4) back and the warp stores 8 rows x 64 contiguous bytes per instruction
+                // -- no cross-warp synchronisation, both shared-memory phases conflict-free. The two warps of a lane quadrant
+                // take alternate 32-column units. (Per-warp TMA stores out of the same buffers cost 5.5 us of a 43.7 us launch
+                // at 4096 x 7168 x 2048 -- 38.2 with the stores compiled out --, 64-column units 7.8 us: kept out.)
                 const uint32_t num_units = (load_cols + kSwapStoreCols - 1) / kSwapStoreCols;
                 const uint32_t buf = staging + (warp_idx - 4) * kSwapStoreBufBytes;
-                const uint32_t row_off = buf + lane * 128, sw = lane & 7;
+                const uint32_t row_off = buf + lane * 64, sw = (lane >> 1) & 3;
+                const uint32_t rd_row = lane >> 2, rd_piece = lane & 3;                // read phase: row 8i + rd_row, 16-byte piece rd_piece
+                const uint32_t rd_off = buf + rd_row * 64 + ((rd_piece ^ ((rd_row >> 1) & 3)) << 4);   // (+ 512 i: the swizzle term repeats every 8 rows)
+                const uint32_t tok0 = t.n0 + quad * 32 + rd_row;
                 if (half >= num_units) release_accumulator();
                 for (uint32_t u = half; u < num_units; u += 2) {
-                    const uint32_t c0 = ((u + 1) * kSwapStoreCols <= load_cols || load_cols < kSwapStoreCols) ? u * kSwapStoreCols
-                                                                                                             : load_cols - kSwapStoreCols;
-                    uint32_t packed[32];
-#pragma unroll
-                    for (uint32_t hh = 0; hh < 2; ++hh) {
-                        uint32_t v[32];
-                        tmem_ld_32x32b_x16(taddr + c0 + hh * 32, *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
-                        tmem_ld_32x32b_x16(taddr + c0 + hh * 32 + 16, *reinterpret_cast<uint32_t(*)[16]>(&v[16]));
-                        tmem_ld_wait();
-#pragma unroll
-                        for (uint32_t q = 0; q < 16; ++q) packed[hh * 16 + q] = pack_bf16x2(v[2 * q], v[2 * q + 1]);
-                    }
+                    uint32_t v[32];
+                    tmem_ld_32x32b_x16(taddr + u * kSwapStoreCols, *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
+                    tmem_ld_32x32b_x16(taddr + u * kSwapStoreCols + 16, *reinterpret_cast<uint32_t(*)[16]>(&v[16]));
+                    tmem_ld_wait();
                     if (u + 2 >= num_units) release_accumulator();
-                    tma_store_wait_read<0>();                       // (only lane 0 owns bulk groups) the buffer has been read out
-                    __syncwarp();
-#ifndef DGB_EXP_NO_STAGE
 #pragma unroll
-                    for (uint32_t piece = 0; piece < 8; ++piece)
-                        st_shared_v4(row_off + ((piece ^ sw) << 4), packed[4 * piece + 0], packed[4 * piece + 1], packed[4 * piece + 2],
-                                     packed[4 * piece + 3]);
-                    fence_proxy_async_smem();
+                    for (uint32_t piece = 0; piece < 4; ++piece)
+                        st_shared_v4(row_off + ((piece ^ sw) << 4), pack_bf16x2(v[8 * piece + 0], v[8 * piece + 1]),
+                                     pack_bf16x2(v[8 * piece + 2], v[8 * piece + 3]), pack_bf16x2(v[8 * piece + 4], v[8 * piece + 5]),
+                                     pack_bf16x2(v[8 * piece + 6], v[8 * piece + 7]));
                     __syncwarp();
-#ifndef DGB_EXP_NO_STORE
-                    if (lane == 0 && t.n0 + quad * 32 < p.n) {
-                        tma_store_2d(&map_d, buf, t.d_row + c0, t.n0 + quad * 32);
-                        tma_store_commit();
+                    const uint32_t col = t.d_row + u * kSwapStoreCols + rd_piece * 8;   // output column of this lane's piece (D has a multiple of 8 columns)
+                    __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(d) + static_cast<size_t>(tok0) * p.ld_d + col;
+#pragma unroll
+                    for (uint32_t i = 0; i < 4; ++i) {
+                        const uint4 x = ld_shared_u4(rd_off + i * 512);
+                        if (tok0 + 8 * i < p.n && col < p.m) *reinterpret_cast<uint4*>(dst + static_cast<size_t>(8 * i) * p.ld_d) = x;
                     }
-#endif
-#endif
+                    __syncwarp();                                    // the buffer is rewritten by the next unit
                 }
                 continue;
             }
@@ -1200,9 +1192,13 @@ fp8_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
                     named_bar_sync(3, kNumEpilogueThreads);
                     if (issuer_warp && lane == 0) {
                         const uint32_t row = t.d_row + u * kStoreRows;
+#ifndef DGB_EXP_NO_STORE
                         if (t.n0 < p.n) tma_store_2d(&map_d, buf, t.n0, row);
                         if (t.n0 + 64 < p.n) tma_store_2d(&map_d, buf + kStoreBufBytes / 2, t.n0 + 64, row);
                         tma_store_commit();
+#else
+                        (void)row;
+#endif
                     }
                 }
                 if (num_units == 0) release_accumulator();
@@ -1233,7 +1229,7 @@ fp8_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
                     store_out<out_t>(reinterpret_cast<out_t*>(d_col + r * row_bytes), 0.0f, false);
         }
         if constexpr (kTmaStore) {
-            if (warp_idx == 4 || kSwapD) tma_store_wait_all();   // the staging buffers must outlive every store that reads them
+            if (!kSwapD && warp_idx == 4) tma_store_wait_all();   // the staging buffers must outlive every store that reads them
         }
     }
 

@@ -176,11 +176,11 @@ def test_transposed_output_orientation_gives_identical_bits(dg, m, n, k, out_dty
     assert torch.equal(accs[0], accs[1])
 
 
-@pytest.mark.parametrize('m,n,k,bn', [(512, 7168, 2048, 224), (300, 1000, 512, 96), (100, 520, 768, 64), (4096, 2048, 512, 224), (640, 1536, 256, 128),
+@pytest.mark.parametrize('m,n,k,bn', [(512, 7168, 2048, 224), (300, 1000, 512, 96), (100, 520, 768, 32), (4096, 2048, 512, 224), (640, 1536, 256, 128),
                                       (257, 4104, 384, 160)])
 def test_transposed_output_with_staged_tma_stores(dg, m, n, k, bn, monkeypatch):
-    """Second orientation + per-warp staged TMA stores (32 rows x 64 columns per store; a width that is not a multiple of 64
-    ends its last store at the tile edge): same bits, nothing outside D."""
+    """Second orientation + per-warp staging through shared memory (32 rows x 32 columns turned around, written as 8 rows x 64
+    contiguous bytes per instruction): same bits, nothing outside D."""
     from deepgemm_b200 import _lib
     _, _, qa, qb = _quant_dense(m, n, k, seed=m + bn)
     monkeypatch.setenv('DGB200_SPLITS', '1')

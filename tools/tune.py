@@ -101,6 +101,9 @@ if __name__ == '__main__':
                            ((512, 7168, 2048), (224, 192)), ((4096, 4096, 7168), (224, 240, 192)), ((4096, 24576, 1536), (224, 240, 192)),
                            ((4096, 2112, 7168), (192, 224)), ((1024, 4096, 7168), (128, 224)), ((4096, 32768, 512), (224,)), ((2048, 4096, 7168), (224, 192))]:
             run([shape], [dict(swap=0)] + [dict(swap=1, block_m=bn, tma_store=1) for bn in bns])
+    elif mode == 'store_exp':
+        # default orientation, dominant shapes, staged vs direct epilogue (run against a build without the stores to see their cost)
+        run([(4096, 4096, 7168), (4096, 7168, 2048)], [dict(swap=0), dict(swap=0, tma_store=0), dict(swap=0, tma_store=1, block_m=224)])
     elif mode == 'small3':
         # short K with many weight panels at small M: single CTAs (192 / 56 independent tiles) vs pairs vs 2 single-CTA slices
         cfgs = [{}, dict(cluster=1, csplit=0), dict(cluster=1, csplit=0, block_m=64), dict(cluster=1, csplit=0, block_m=32), dict(csplit=2)]
