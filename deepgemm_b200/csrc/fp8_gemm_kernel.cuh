@@ -1192,13 +1192,9 @@ fp8_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
                     named_bar_sync(3, kNumEpilogueThreads);
                     if (issuer_warp && lane == 0) {
                         const uint32_t row = t.d_row + u * kStoreRows;
-#ifndef DGB_EXP_NO_STORE
                         if (t.n0 < p.n) tma_store_2d(&map_d, buf, t.n0, row);
                         if (t.n0 + 64 < p.n) tma_store_2d(&map_d, buf + kStoreBufBytes / 2, t.n0 + 64, row);
                         tma_store_commit();
-#else
-                        (void)row;
-#endif
                     }
                 }
                 if (num_units == 0) release_accumulator();
