@@ -160,7 +160,8 @@ struct Problem {
     int n, k, groups;
     int alignment;     // contiguous layouts: group start alignment
     int max_splits = 1;  // > 1 only for dense problems whose caller supplied a split-K workspace
-    bool x_mn = false;   // MN-major tokens: the token tile is loaded in 32/64/128-row swizzle atoms
+    bool x_mn = false;   // MN-major tokens: the token tile is loaded in 32/64/128-byte swizzle atoms
+    int el = 1;          // operand bytes per element (2: BF16 operands)
     bool any_mn = false; // any MN-major operand: no weight multicast
     bool tma_store_ok = false;   // the output may leave through the staged TMA-store epilogue (plain BF16 tiles)
     bool swapped = false;        // transposed-output orientation: `m` is the weight count (tiled freely), `n` the token count (lanes)
@@ -228,8 +229,14 @@ Config choose_config(const Problem& pb, int num_sms_override = 0) {
     c.swap_d = pb.swapped;
     std::vector<int> candidates;
     if (pb.type == kDense || pb.type == kMMasked || pb.type == kKGrouped || pb.type == kKGroupedPsum || pb.type == kBatched) {
-        const int step = pb.x_mn ? 32 * std::min(c.cluster, 2) : 16;   // MN-major tokens: load_m is a multiple of 32
-        for (int bm = step; bm <= (int)kMaxBlockM; bm += step) candidates.push_back(bm);
+        const int step = pb.x_mn ? 32 / pb.el * std::min(c.cluster, 2) : 16;   // MN-major tokens: a CTA's rows are whole 32-byte atoms
+        for (int bm = step; bm <= (int)kMaxBlockM; bm += step) {
+            // ... and narrow atoms are slow (k-grouped FP8, 4096 x 7168: 192-row tiles = 32 B atoms 280 us, 128-row = 64 B atoms
+            // 262; BF16 160 / 224 rows = 64 / 32 B atoms 421 / 411 us against 356 at 192): keep the heights whose atoms are
+            // at least 64 bytes wide, plus the shortest tile that covers a small problem
+            if (pb.x_mn && (bm / std::min(c.cluster, 2) * pb.el) % 64 != 0 && bm < align_up(pb.m, step)) continue;
+            candidates.push_back(bm);
+        }
     } else {
         // a tile must not straddle two groups: block_m has to divide the group alignment
         for (int bm = 16; bm <= (int)kMaxBlockM; bm += 16)
@@ -442,7 +449,7 @@ int run_gemm(const GemmCall& c) {
     const bool batched = c.type == kBatched;
     const bool head_split = c.head_mid > 0;
     Problem pb{c.type, c.m, c.expected_m, c.n, c.k, c.groups, c.alignment};
-    pb.x_mn = c.x_mn, pb.any_mn = c.x_mn || c.w_mn;
+    pb.x_mn = c.x_mn, pb.any_mn = c.x_mn || c.w_mn, pb.el = c.bf16_ab ? 2 : 1;
     pb.swapped = c.swap_d, pb.forced_block_m = c.forced_block_m, pb.plain_only = c.bf16_ab && !(c.type == kDense && !c.x_mn && !c.w_mn);   // BF16: cluster split-K is built for dense K-major only
     // TMA stores need a 16-byte aligned base and row pitch; tiles that must not touch rows past `valid_m` (masked, psum),
     // accumulate into C or remap columns keep the predicated direct stores
