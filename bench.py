@@ -419,6 +419,56 @@ def run_dense(args, rank, world, device):
     return out, probs
 
 
+def next_rows_block(device, dg):
+    """SURVEY section 8(f4) and the k-grouped row beside the reference's own kernels (same tensors, kernel time by the profiler):
+    BF16-operand dense GEMMs, the k-grouped weight-gradient form for both operand types."""
+    from deepgemm_b200.utils import per_channel_cast_to_fp8
+    try:
+        ref = import_reference()
+    except Exception as e:  # noqa: BLE001
+        return {'unavailable': f'{type(e).__name__}: {e}'[:300]}
+    rows = []
+    gen = torch.Generator(device=device).manual_seed(7)
+    for (m, n, k) in [(64, 4096, 7168), (4096, 4096, 7168)]:
+        a = torch.randn((m, k), device=device, dtype=torch.bfloat16, generator=gen)
+        b = torch.randn((n, k), device=device, dtype=torch.bfloat16, generator=gen)
+        d0, d1 = torch.empty((m, n), device=device, dtype=torch.bfloat16), torch.empty((m, n), device=device, dtype=torch.bfloat16)
+        ref.bf16_gemm_nt(a, b, d0)
+        dg.set_split_k(False)
+        try:
+            dg.bf16_gemm_nt(a, b, d1)
+            torch.cuda.synchronize()
+            bitwise = bool(torch.equal(d0, d1))
+        finally:
+            dg.set_split_k(True)
+        rows.append({'op': 'bf16_gemm_nt', 'm': m, 'n': n, 'k': k, 'bitwise_equal': bitwise,
+                     'ours_kineto_us': kineto_us(lambda: dg.bf16_gemm_nt(a, b, d1), 'fp8_gemm_kernel'),
+                     'ref_kineto_us': kineto_us(lambda: ref.bf16_gemm_nt(a, b, d0), 'sm100_bf16')})
+    g, m, n, ks = 4, 4096, 7168, [1024, 2048, 512, 4096]
+    a = torch.randn((sum(ks), m), device=device, dtype=torch.bfloat16, generator=gen)
+    b = torch.randn((sum(ks), n), device=device, dtype=torch.bfloat16, generator=gen)
+    c = torch.randn((g, m, n), device=device, dtype=torch.float32, generator=gen)
+    layout = torch.tensor(ks, device=device, dtype=torch.int32)
+    d0, d1 = c.clone(), c.clone()
+    ref.k_grouped_bf16_gemm_tn_contiguous(a, b, d0, ks, layout, c=d0)
+    dg.k_grouped_bf16_gemm_tn_contiguous(a, b, d1, ks, layout, c=d1)
+    torch.cuda.synchronize()
+    rows.append({'op': 'k_grouped_bf16_gemm_tn_contiguous', 'groups': g, 'm': m, 'n': n, 'ks': ks, 'bitwise_equal': bool(torch.equal(d0, d1)),
+                 'ours_kineto_us': kineto_us(lambda: dg.k_grouped_bf16_gemm_tn_contiguous(a, b, d1, ks, layout, c=d1), 'fp8_gemm_kernel', 5),
+                 'ref_kineto_us': kineto_us(lambda: ref.k_grouped_bf16_gemm_tn_contiguous(a, b, d0, ks, layout, c=d0), 'sm100_bf16', 5)})
+    qa, qb = per_channel_cast_to_fp8(a, True), per_channel_cast_to_fp8(b, True)
+    del a, b
+    d0.copy_(c), d1.copy_(c)
+    ref.k_grouped_fp8_gemm_tn_contiguous(qa, qb, d0, ks, layout, c=d0)
+    dg.k_grouped_fp8_gemm_tn_contiguous(qa, qb, d1, ks, layout, c=d1)
+    torch.cuda.synchronize()
+    rows.append({'op': 'k_grouped_fp8_gemm_tn_contiguous', 'groups': g, 'm': m, 'n': n, 'ks': ks, 'bitwise_equal': bool(torch.equal(d0, d1)),
+                 'ours_kineto_us': kineto_us(lambda: dg.k_grouped_fp8_gemm_tn_contiguous(qa, qb, d1, ks, layout, c=d1), 'fp8_gemm_kernel', 5),
+                 'ref_kineto_us': kineto_us(lambda: ref.k_grouped_fp8_gemm_tn_contiguous(qa, qb, d0, ks, layout, c=d0), 'sm100_fp8', 5)})
+    return {'method': 'kernel time by torch.profiler (GEMM kernels selected by name; the k-grouped FP8 calls also run their scale-factor packing '
+                      'kernels, not counted), L2 flushed before every launch; bitwise_equal with set_split_k(False)', 'rows': rows}
+
+
 def add_dense_extras(out, probs, args, rank, world, device):
     """Outside the timed regions: the comparisons the north star is about (reference-kernel A/B, configs 3 / 4, config 5)."""
     import deepgemm_b200 as dg
@@ -435,6 +485,9 @@ def add_dense_extras(out, probs, args, rank, world, device):
     torch.cuda.empty_cache()
     if rank == 0:
         out['decode_chain'] = guarded(lambda: decode_chain_block(device, dg))
+    torch.cuda.empty_cache()
+    if rank == 0:
+        out['next_rows'] = guarded(lambda: next_rows_block(device, dg))
     torch.cuda.empty_cache()
     barrier(world)
     weights = None

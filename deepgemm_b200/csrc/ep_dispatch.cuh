@@ -620,7 +620,15 @@ combine_gather_kernel(Peers ctrl_bufs, Peers d_bufs, const void* __restrict__ id
             }
             const uint32_t owner = static_cast<uint32_t>(load_id<id_t>(ids, t)) / epr;
             const uint4* src = reinterpret_cast<const uint4*>(d_bufs.base[owner] + static_cast<int64_t>(row) * ldd_bytes);
+            // remote reads are a round trip over NVLink (~2-3 us): 8 x 16 B in flight per lane, an 8 KB row in two trips
             uint32_t c = lane;
+            for (; c + 224 < chunks; c += 256) {
+                uint4 v[8];
+#pragma unroll
+                for (uint32_t j = 0; j < 8; ++j) v[j] = __ldcv(src + c + 32 * j);
+#pragma unroll
+                for (uint32_t j = 0; j < 8; ++j) dst[c + 32 * j] = v[j];
+            }
             for (; c + 96 < chunks; c += 128) {
                 const uint4 v0 = __ldcv(src + c), v1 = __ldcv(src + c + 32), v2 = __ldcv(src + c + 64), v3 = __ldcv(src + c + 96);
                 dst[c] = v0, dst[c + 32] = v1, dst[c + 64] = v2, dst[c + 96] = v3;

@@ -46,8 +46,41 @@ dense(600, 768, 1024, {'DGB200_CLUSTER': '4', 'DGB200_SPLITS': '1'})   # weight-
 dense(256, 384, 512, majors='mm', fp32=True, c=True)                    # MN-major operands (wgrad form)
 dense(200, 256, 512, {'DGB200_CLUSTER': '1', 'DGB200_SPLITS': '1'})    # single-CTA MMA, plain prologue
 
+KNOBS = KNOBS + ('DGB200_SWAP', 'DGB200_GRID_TILES')
+dense(300, 1000, 512, {'DGB200_SWAP': '1', 'DGB200_TMA_STORE': '1', 'DGB200_BLOCK_M': '96', 'DGB200_SPLITS': '1'})    # transposed output, staged
+dense(120, 2000, 640, {'DGB200_SWAP': '1', 'DGB200_TMA_STORE': '0', 'DGB200_BLOCK_M': '48', 'DGB200_SPLITS': '1'})    # transposed output, direct
+dense(700, 4096, 256, {'DGB200_GRID_TILES': '0', 'DGB200_SPLITS': '1'})                                              # persistent walk of a one-wave problem
 for kk in KNOBS:
     os.environ.pop(kk, None)
+
+# BF16 operands: dense nt (cluster split-K at this size), tn with FP32 accumulation (memory-side add), grouped, k-grouped, einsum
+ab, bb = torch.randn((48, 1024), device='cuda', dtype=torch.bfloat16), torch.randn((384, 1024), device='cuda', dtype=torch.bfloat16)
+db = torch.zeros((48, 384), device='cuda', dtype=torch.bfloat16)
+dg.bf16_gemm_nt(ab, bb, db)
+print('bf16 nt', _lib.last_config(), flush=True)
+akm, bkn = torch.randn((512, 160), device='cuda', dtype=torch.bfloat16), torch.randn((512, 264), device='cuda', dtype=torch.bfloat16)
+dacc = torch.zeros((160, 264), device='cuda', dtype=torch.float32)
+dg.bf16_gemm_tn(akm, bkn, dacc, c=dacc)
+gb = torch.randn((3, 256, 512), device='cuda', dtype=torch.bfloat16)
+agr = torch.randn((3 * 128, 512), device='cuda', dtype=torch.bfloat16)
+dgr = torch.zeros((3 * 128, 256), device='cuda', dtype=torch.bfloat16)
+lay = torch.arange(3, device='cuda', dtype=torch.int32).repeat_interleave(128)
+lay[100:128] = -1
+dg.m_grouped_bf16_gemm_nt_contiguous(agr, gb, dgr, lay)
+dg.m_grouped_bf16_gemm_nn_contiguous(agr, gb.transpose(1, 2).contiguous(), dgr, lay)
+dmk = torch.zeros((3, 128, 256), device='cuda', dtype=torch.bfloat16)
+dg.m_grouped_bf16_gemm_nt_masked(agr.view(3, 128, 512), gb, dmk, torch.tensor([7, 128, 0], device='cuda', dtype=torch.int32), 64)
+ksb = [128, 0, 384]
+akb, bkb = torch.randn((sum(ksb), 192), device='cuda', dtype=torch.bfloat16), torch.randn((sum(ksb), 136), device='cuda', dtype=torch.bfloat16)
+dkb = torch.zeros((3, 192, 136), device='cuda', dtype=torch.float32)
+dg.k_grouped_bf16_gemm_tn_contiguous(akb, bkb, dkb, ksb, torch.tensor(ksb, device='cuda', dtype=torch.int32), c=dkb)
+xe, ye = torch.randn((40, 4, 256), device='cuda', dtype=torch.bfloat16), torch.randn((4, 128, 256), device='cuda', dtype=torch.bfloat16)
+ze = torch.zeros((40, 4, 128), device='cuda', dtype=torch.bfloat16)
+dg.einsum('bhr,hdr->bhd', xe, ye, ze)
+ze2 = torch.zeros((40, 4, 256), device='cuda', dtype=torch.bfloat16)
+dg.einsum('bhd,hdr->bhr', ze, ye, ze2)
+torch.cuda.synchronize()
+print('bf16 family done', flush=True)
 
 # skip_head_mid, bmm / einsum, quantiser
 a = torch.randn((77, 384), device='cuda', dtype=torch.bfloat16)
