@@ -638,17 +638,28 @@ combine_gather_kernel(Peers ctrl_bufs, Peers d_bufs, const void* __restrict__ id
         }
         for (uint32_t c = lane; c < chunks; c += 32) {               // 8 BF16 outputs per lane and pass
             float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-            for (uint32_t j = 0; j < topk; ++j) {
-                const int32_t row = __ldg(token_row + t * topk + j);
-                if (row < 0) continue;
-                const uint32_t owner = static_cast<uint32_t>(load_id<id_t>(ids, t * topk + j)) / epr;
-                const float w = weights != nullptr ? __ldg(weights + t * topk + j) : 1.0f;
-                const uint4 v = __ldcv(reinterpret_cast<const uint4*>(d_bufs.base[owner] + static_cast<int64_t>(row) * ldd_bytes) + c);
-                const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+            for (uint32_t j0 = 0; j0 < topk; j0 += 8) {              // up to 8 slots at a time: their remote reads travel together
+                uint4 v[8];
+                float w[8];
 #pragma unroll
-                for (uint32_t q = 0; q < 4; ++q) {
-                    acc[2 * q] = __fadd_rn(acc[2 * q], __fmul_rn(w, __uint_as_float(u[q] << 16)));
-                    acc[2 * q + 1] = __fadd_rn(acc[2 * q + 1], __fmul_rn(w, __uint_as_float(u[q] & 0xFFFF0000u)));
+                for (uint32_t jj = 0; jj < 8; ++jj) {
+                    const uint32_t j = j0 + jj;
+                    const int32_t row = j < topk ? __ldg(token_row + t * topk + j) : -1;
+                    w[jj] = 0.f, v[jj] = make_uint4(0u, 0u, 0u, 0u);
+                    if (row < 0) continue;
+                    const uint32_t owner = static_cast<uint32_t>(load_id<id_t>(ids, t * topk + j)) / epr;
+                    w[jj] = weights != nullptr ? __ldg(weights + t * topk + j) : 1.0f;
+                    v[jj] = __ldcv(reinterpret_cast<const uint4*>(d_bufs.base[owner] + static_cast<int64_t>(row) * ldd_bytes) + c);
+                }
+#pragma unroll
+                for (uint32_t jj = 0; jj < 8; ++jj) {                // slot order, as before: a slot that was not routed adds nothing
+                    if (j0 + jj >= topk || __ldg(token_row + t * topk + j0 + jj) < 0) continue;
+                    const uint32_t u[4] = {v[jj].x, v[jj].y, v[jj].z, v[jj].w};
+#pragma unroll
+                    for (uint32_t q = 0; q < 4; ++q) {
+                        acc[2 * q] = __fadd_rn(acc[2 * q], __fmul_rn(w[jj], __uint_as_float(u[q] << 16)));
+                        acc[2 * q + 1] = __fadd_rn(acc[2 * q + 1], __fmul_rn(w[jj], __uint_as_float(u[q] & 0xFFFF0000u)));
+                    }
                 }
             }
             uint32_t o[4];
