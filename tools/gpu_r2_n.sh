@@ -1,0 +1,5 @@
+#!/usr/bin/env bash
+cd "${GRAFT_REPO_ROOT:-/root/repo}"
+OUT=gpurun_out/r2; mkdir -p $OUT
+timeout 600 python tools/tune.py swap_small > $OUT/tune_n_swap_small.log 2>&1
+grep -v -i warn $OUT/tune_n_swap_small.log | tail -60

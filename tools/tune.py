@@ -104,6 +104,11 @@ if __name__ == '__main__':
     elif mode == 'store_exp':
         # default orientation, dominant shapes, staged vs direct epilogue (run against a build without the stores to see their cost)
         run([(4096, 4096, 7168), (4096, 7168, 2048)], [dict(swap=0), dict(swap=0, tma_store=0), dict(swap=0, tma_store=1, block_m=224)])
+    elif mode == 'swap_small':
+        # small M, many weight panels: single-CTA transposed-output tiles (tokens on the lanes) of a width that fills one wave
+        for shape, bns in [((64, 7168, 2048), (48, 64, 96)), ((128, 7168, 2048), (48, 64, 96)), ((128, 24576, 1536), (160, 176, 192, 224)),
+                           ((64, 24576, 1536), (160, 176, 192)), ((64, 32768, 512), (224, 240)), ((128, 7168, 16384), (48, 64))]:
+            run([shape], [dict(swap=0)] + [dict(swap=1, block_m=bn, tma_store=ts) for bn in bns for ts in ((0, 1) if bn % 32 == 0 else (0,))])
     elif mode == 'small3':
         # short K with many weight panels at small M: single CTAs (192 / 56 independent tiles) vs pairs vs 2 single-CTA slices
         cfgs = [{}, dict(cluster=1, csplit=0), dict(cluster=1, csplit=0, block_m=64), dict(cluster=1, csplit=0, block_m=32), dict(csplit=2)]
