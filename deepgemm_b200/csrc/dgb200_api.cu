@@ -16,6 +16,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <unistd.h>   // environ
 #include <mutex>
 #include <string>
 #include <unordered_map>
@@ -95,8 +96,28 @@ int effective_num_sms() {
 
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 inline int align_up(int a, int b) { return ceil_div(a, b) * b; }
+// Developer knobs are environment variables read per call. A launch consults ~20 of them, and every
+// getenv() walks the whole environment: several microseconds of a host path that bounds small-M GEMMs in plain stream
+// order. So the public entry points open an EnvScope: ONE pass over `environ` finds out whether any DGB200_* variable is
+// set at all (in production: none), and the lookups below answer "unset" without searching.
+thread_local int t_env_state = 0;           // 0: no scope open (plain getenv) | 1: scope, no DGB200_* variable | 2: scope, some are set
+struct EnvScope {
+    int saved;
+    EnvScope() : saved(t_env_state) {
+        if (saved != 0) return;              // nested: the outer scope has looked already
+        int state = 1;
+        for (char** e = ::environ; e != nullptr && *e != nullptr; ++e)
+            if ((*e)[0] == 'D' && strncmp(*e, "DGB200_", 7) == 0) {
+                state = 2;
+                break;
+            }
+        t_env_state = state;
+    }
+    ~EnvScope() { t_env_state = saved; }
+};
+inline const char* env_str(const char* name) { return t_env_state == 1 ? nullptr : getenv(name); }
 inline int env_int(const char* name, int dflt) {
-    const char* v = getenv(name);
+    const char* v = env_str(name);
     return v && *v ? atoi(v) : dflt;
 }
 
@@ -267,7 +288,7 @@ Config choose_config(const Problem& pb, int num_sms_override = 0) {
     }
     if (pb.forced_block_m > 0) c.block_m = pb.forced_block_m, c.num_splits = 1;
     if (int v = env_int("DGB200_BLOCK_M", 0)) c.block_m = v;
-    if (const char* v = getenv("DGB200_SPLITS")) c.num_splits = std::max(1, std::min(atoi(v), max_splits));
+    if (const char* v = env_str("DGB200_SPLITS")) c.num_splits = std::max(1, std::min(atoi(v), max_splits));
     c.kb_per_split = ceil_div(num_kb, c.num_splits);
     c.num_splits = ceil_div(num_kb, c.kb_per_split);
 
@@ -278,7 +299,7 @@ Config choose_config(const Problem& pb, int num_sms_override = 0) {
     // heights, the taller ones first).
     c.num_tall = 0, c.block_m_low = 0;
     if (pb.type == kDense && !pb.swapped && !pb.x_mn && c.num_splits == 1 && c.cluster == 2 && pb.m >= 1024 && c.block_m >= 160 &&
-        !getenv("DGB200_BLOCK_M") && env_int("DGB200_BALANCE", 1)) {
+        !env_str("DGB200_BLOCK_M") && env_int("DGB200_BALANCE", 1)) {
         const int units = c.num_sms / 2, n_units = ceil_div(pb.n, (int)kBlockN * 2);
         const double overhead_rows = kTileOverhead / (2.0 * num_kb);      // per-tile fixed cost in units of token rows
         double best_ms = 1e300;
@@ -307,9 +328,9 @@ Config choose_config(const Problem& pb, int num_sms_override = 0) {
     // the partial tiles are reduced through distributed shared memory. Every weight byte then crosses L2 -> SM once
     // (instead of once per m-block) and all SMs stream from HBM even when there are few output tiles.
     c.csplit = 0, c.grid = 0, c.grid_y = 1;
-    const char* splits_env = getenv("DGB200_SPLITS");
-    const bool pinned = getenv("DGB200_BLOCK_M") || getenv("DGB200_CLUSTER") || (splits_env && atoi(splits_env) <= 1);
-    if (pb.type == kDense && !pb.swapped && !pb.plain_only && !pb.any_mn && c.cluster == 2 && pb.m > 0 && rt().split_k && !(pinned && !getenv("DGB200_CSPLIT"))) {
+    const char* splits_env = env_str("DGB200_SPLITS");
+    const bool pinned = env_str("DGB200_BLOCK_M") || env_str("DGB200_CLUSTER") || (splits_env && atoi(splits_env) <= 1);
+    if (pb.type == kDense && !pb.swapped && !pb.plain_only && !pb.any_mn && c.cluster == 2 && pb.m > 0 && rt().split_k && !(pinned && !env_str("DGB200_CSPLIT"))) {
         const int want = env_int("DGB200_CSPLIT", -1);            // -1: heuristic, 0: off, 2/4: forced
         int pick = 0, pick_bm = 0;
         for (int sp : {4, 2}) {
@@ -418,7 +439,7 @@ Config choose_config(const Problem& pb, int num_sms_override = 0) {
 int want_swapped_orientation(const GemmCall& c, int num_sms_override = 0) {
     const int want = env_int("DGB200_SWAP", -1);
     if (want >= 0) return want != 0 ? -1 : 0;
-    if (getenv("DGB200_BLOCK_M") || getenv("DGB200_CLUSTER") || getenv("DGB200_SPLITS")) return 0;   // pinned configurations
+    if (env_str("DGB200_BLOCK_M") || env_str("DGB200_CLUSTER") || env_str("DGB200_SPLITS")) return 0;   // pinned configurations
     if (c.d_dtype != DGB200_BF16 || c.accumulate || c.m <= (int)kBlockN || (reinterpret_cast<uintptr_t>(c.d) & 15) != 0 || (c.ldd * 2) % 16 != 0)
         return 0;
     Problem pb{kDense, c.m, c.m, c.n, c.k, 1, 1};
@@ -435,6 +456,7 @@ int want_swapped_orientation(const GemmCall& c, int num_sms_override = 0) {
 
 // ------------------------------------------------------------------------------------------------ launch
 int run_gemm(const GemmCall& c) {
+    EnvScope env_scope;
     if (int e = ensure_device()) return e;
     DGB_REQUIRE(c.gran_k_a == 32 || c.gran_k_a == 128);
     DGB_REQUIRE(c.gran_k_b == 32 || c.gran_k_b == 128);
@@ -730,6 +752,7 @@ int dgb200_fp8_gemm_nt(const void* a, const int32_t* sfa, const void* b, const i
                        int k, int64_t lda, int64_t ldb, int64_t ldd, int major_a, int major_b, int sfa_stride,
                        int sfb_stride, int gran_k_a, int gran_k_b, int d_dtype, int accumulate, void* workspace,
                        int64_t workspace_bytes, void* stream) {
+    EnvScope env_scope;
     DGB_REQUIRE(m >= 0 && n >= 0 && k >= 0);
     if (m == 0 || n == 0) return DGB200_OK;  // gemm.hpp:22-23
     DGB_REQUIRE(k > 0);                      // k == 0 (D = C or 0) is handled by the host wrapper, gemm.hpp:36-40
@@ -1114,6 +1137,7 @@ int dgb200_k_grouped_fp8_gemm_tn_contiguous(const void* a, const int32_t* sfa, c
 
 int dgb200_plan(int gemm_type, int m, int n, int k, int num_groups, int expected_m, int alignment, int num_sms,
                 dgb200_config* out) {
+    EnvScope env_scope;
     DGB_REQUIRE(out != nullptr && num_sms >= 2);
     DGB_REQUIRE(gemm_type >= kDense && gemm_type <= kMContiguousPsum);
     DGB_REQUIRE(m > 0 && n > 0 && k > 0 && num_groups > 0);
