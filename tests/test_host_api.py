@@ -227,3 +227,25 @@ def test_plan_picks_pair_split_k_and_the_staged_epilogue_where_measured(lib):
     sw = lib.plan(0, 512, 7168, 2048)      # 28 x 5 tiles = two rounds of pairs; 2 x 32 tiles of 256 tokens x 224 weights = one
     assert (sw['swap_ab'], sw['block_m'], sw['cluster'], sw['tma_store'], sw['num_tiles']) == (1, 224, 2, 1, 64)
     assert lib.plan(0, 256, 7168, 2048)['swap_ab'] == 0 and lib.plan(0, 1024, 7168, 2048)['swap_ab'] == 0
+
+
+def test_prepacked_scale_factor_pair_memo_notices_a_changed_layout():
+    """The per-call fast path remembers the last validated pair of pre-packed scale-factor tensors by identity; shapes and
+    strides are still compared on every call, so an in-place transpose (or any other tensor) goes through the full checks."""
+    import torch
+    from deepgemm_b200 import layout
+    m, n, k = 64, 256, 1024
+    sfa = torch.zeros((k // 512, m), dtype=torch.int32).t()
+    sfb = torch.zeros((k // 512, n), dtype=torch.int32).t()
+    first = layout.transform_sf_pair_into_required_layout(sfa, sfb, m, n, k, None, None, None, None, None)
+    again = layout.transform_sf_pair_into_required_layout(sfa, sfb, m, n, k, None, None, None, None, None)
+    assert again is first and first[0] is sfa and first[1] is sfb and first[2:] == (128, 128)
+    with pytest.raises(RuntimeError):
+        layout.transform_sf_pair_into_required_layout(sfa, sfb, m + 4, n, k, None, None, None, None, None)     # other problem size
+    other = torch.zeros((m, k // 512), dtype=torch.int32)                                                         # K-major storage: not TMA-ready
+    with pytest.raises(RuntimeError):
+        layout.transform_sf_pair_into_required_layout(other, sfb, m, n, k, None, None, None, None, None)
+    assert layout.transform_sf_pair_into_required_layout(sfa, sfb, m, n, k, None, None, None, None, None)[0] is sfa
+    sfa.t_()                                                                                                       # same object, new layout
+    with pytest.raises(RuntimeError):
+        layout.transform_sf_pair_into_required_layout(sfa, sfb, m, n, k, None, None, None, None, None)
