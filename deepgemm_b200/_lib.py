@@ -93,6 +93,7 @@ SIGNATURES = {
     'dgb200_per_token_cast_to_fp8': (_I, [_P, _L, _P, _L, _P, _I, _I, _I, _I, _P]),
     'dgb200_bf16_gemm_nt': (_I, [_P, _P, _P, _I, _I, _I, _L, _L, _L, _I, _I, _I, _I, _P]),
     'dgb200_m_grouped_bf16_gemm_nt_contiguous': (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _L, _L, _L, _I, _I, _I, _I, _P]),
+    'dgb200_bf16_bmk_bnk_mn': (_I, [_P, _P, _P, _I, _I, _I, _I, _P]),
     'dgb200_bf16_bmm': (_I, [_P, _P, _P, _I, _I, _I, _I, _L, _L, _L, _L, _L, _L, _I, _P]),
     'dgb200_k_grouped_bf16_gemm_tn_contiguous': (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
     'dgb200_m_grouped_bf16_gemm_nt_masked': (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),

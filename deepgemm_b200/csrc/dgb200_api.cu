@@ -249,7 +249,7 @@ Config choose_config(const Problem& pb, int num_sms_override = 0) {
     if (pb.plain_only && c.num_sms >= 2) c.cluster = 2;
     c.swap_d = pb.swapped;
     std::vector<int> candidates;
-    if (pb.type == kDense || pb.type == kMMasked || pb.type == kKGrouped || pb.type == kKGroupedPsum || pb.type == kBatched) {
+    if (pb.type == kDense || pb.type == kMMasked || pb.type == kKGrouped || pb.type == kKGroupedPsum || pb.type == kBatched || pb.type == kBatchReduce) {
         const int step = pb.x_mn ? 32 / pb.el * std::min(c.cluster, 2) : 16;   // MN-major tokens: a CTA's rows are whole 32-byte atoms
         for (int bm = step; bm <= (int)kMaxBlockM; bm += step) {
             // ... and narrow atoms are slow (k-grouped FP8, 4096 x 7168: 192-row tiles = 32 B atoms 280 us, 128-row = 64 B atoms
@@ -468,11 +468,14 @@ int run_gemm(const GemmCall& c) {
     }
     const bool k_grouped = c.type == kKGrouped || c.type == kKGroupedPsum;
 
-    const bool batched = c.type == kBatched;
+    const bool batched = c.type == kBatched || c.type == kBatchReduce;   // rank-3 tensor maps (batch = third coordinate)
     const bool head_split = c.head_mid > 0;
     Problem pb{c.type, c.m, c.expected_m, c.n, c.k, c.groups, c.alignment};
     pb.x_mn = c.x_mn, pb.any_mn = c.x_mn || c.w_mn, pb.el = c.bf16_ab ? 2 : 1;
-    pb.swapped = c.swap_d, pb.forced_block_m = c.forced_block_m, pb.plain_only = c.bf16_ab && !(c.type == kDense && !c.x_mn && !c.w_mn);   // BF16: cluster split-K is built for dense K-major only
+    pb.swapped = c.swap_d, pb.forced_block_m = c.forced_block_m;
+    if (c.type == kBatchReduce)     // few, tall output tiles; the parallelism comes from the batch chunks
+        pb.forced_block_m = align_up(ceil_div(c.m, ceil_div(c.m, (int)kMaxBlockM)), 16);
+    pb.plain_only = c.bf16_ab && !(c.type == kDense && !c.x_mn && !c.w_mn);   // BF16: cluster split-K is built for dense K-major only
     // TMA stores need a 16-byte aligned base and row pitch; tiles that must not touch rows past `valid_m` (masked, psum),
     // accumulate into C or remap columns keep the predicated direct stores
     pb.tma_store_ok = (c.type == kDense || c.type == kMContiguous) && !c.bf16_ab && c.d_dtype == DGB200_BF16 && !c.accumulate && !head_split &&
@@ -599,7 +602,14 @@ int run_gemm(const GemmCall& c) {
     p.zero_padding = c.zero_padding;
     p.x_swizzle = x_swizzle;
     p.sf_k_span = 4 * c.gran_k_a;
-    p.d_batch_stride = batched ? static_cast<uint64_t>(c.batch_stride_d) : 0;
+    p.d_batch_stride = c.type == kBatched ? static_cast<uint64_t>(c.batch_stride_d) : 0;
+    if (c.type == kBatchReduce) {
+        // cut the batches into chunks so that every CTA pair gets about one tile (at least 2 batches per chunk)
+        const int per_chunk = p.num_m_blocks * p.num_n_units, pairs = std::max(1, cfg.num_sms / cfg.cluster);
+        const int want_chunks = std::max(1, std::min(ceil_div(c.groups, 2), std::max(1, pairs / per_chunk)));
+        p.kb_per_split = ceil_div(c.groups, want_chunks);                  // batches per chunk
+        p.num_splits = ceil_div(c.groups, (int)p.kb_per_split);            // chunks
+    }
     p.head_lr = head_split ? c.head_left + c.head_right : 1, p.head_mid = head_split ? c.head_mid : 0, p.head_right = c.head_right;
 
     g_last_config = dgb200_config{cfg.block_m, cfg.cluster, cfg.stages, cfg.num_sms, cfg.smem_bytes, 0, cfg.num_splits, cfg.csplit,
@@ -610,6 +620,7 @@ int run_gemm(const GemmCall& c) {
                 cfg.smem_bytes, cfg.csplit ? -cfg.num_splits : cfg.num_splits, cfg.tma_store);
 
     if (c.bf16_ab) return (c.x_mn || c.w_mn || batched) ? dispatch_bf16_mn(c, cfg, maps, p) : dispatch_bf16(c, cfg, maps, p);
+    if (c.type == kBatchReduce) return fail(DGB200_ERR_UNSUPPORTED, "the batch-reduction GEMM is built for BF16 operands only");
     switch (c.type) {
         case kDense:
             if (c.swap_d) return dispatch_dense_swap(c, cfg, maps, p);
@@ -904,6 +915,22 @@ int dgb200_bf16_bmm(const void* a, const void* b, void* d, int batch, int m, int
     c.expected_m = m, c.alignment = 1, c.zero_padding = 0;
     c.stream = static_cast<cudaStream_t>(stream);
     bf16_common(c, k, lda, ldb);
+    return run_gemm(c);
+}
+
+int dgb200_bf16_bmk_bnk_mn(const void* a, const void* b, float* d, int batch, int m, int n, int k, void* stream) {
+    DGB_REQUIRE(batch >= 0 && m >= 0 && n >= 0 && k >= 0);
+    if (batch == 0 || m == 0 || n == 0 || k == 0) return DGB200_OK;       // nothing to add
+    DGB_REQUIRE(k % 64 == 0);                                            // whole 128-byte k-blocks per batch
+    GemmCall c{};
+    c.type = kBatchReduce;
+    c.a = a, c.b = b, c.d = d, c.grouped_layout = nullptr;
+    c.m = m, c.n = n, c.groups = batch, c.a_rows = m, c.ldd = n;
+    c.batch_stride_a = static_cast<int64_t>(m) * k, c.batch_stride_b = static_cast<int64_t>(n) * k, c.batch_stride_d = 0;
+    c.d_dtype = DGB200_FP32, c.accumulate = 1;
+    c.expected_m = m, c.alignment = 1, c.zero_padding = 0;
+    c.stream = static_cast<cudaStream_t>(stream);
+    bf16_common(c, k, k, k);
     return run_gemm(c);
 }
 

@@ -43,6 +43,8 @@ enum GemmType : int {
     kKGrouped = 4,      // D[g] += A[k_g, :M]^T B[k_g, :N], grouped_layout[g] = K of group g        (gemm.hpp:299, sched :259-283)
     kKGroupedPsum = 5,  // same, grouped_layout[g] = end K of group g, starts aligned to m_alignment
     kBatched = 6,       // D[b] = A[b] B[b]^T with arbitrary batch strides (3-D tensor maps)      (einsum.hpp:137-175, fp8_bmm)
+    kBatchReduce = 7,   // D += sum_b A[b] B[b]^T: the K loop walks (batch, k-block); the batches are cut into chunks over the
+                        // grid and every chunk adds its partial tile into the FP32 D            (einsum.hpp:22-60, 'bmk,bnk->mn')
 };
 
 constexpr uint32_t kBlockN = 128;        // weight rows per CTA == TMEM lanes
@@ -281,6 +283,27 @@ struct Scheduler {
                 t.valid_m = min(t.valid_m, 16 * (groups + 1));
                 t.store_m = t.valid_m;
             }
+        } else if constexpr (kGemmType == kBatchReduce) {
+            // tile = (batch chunk, m-block, n-unit); num_splits chunks of kb_per_split batches each. The k-blocks of a tile are
+            // VIRTUAL: kb counts (batch, k-block) pairs, so the MMA and re-tiling roles need not know; only the producer
+            // turns kb back into coordinates.
+            const uint32_t per_chunk = p.num_m_blocks * num_n_units;
+            if (idx >= per_chunk * p.num_splits) return false;
+            const uint32_t chunk = idx < per_chunk ? 0u : idx / per_chunk;
+            split(idx - chunk * per_chunk, p.num_m_blocks, m_blk, n_unit);
+            t.batch = chunk * p.kb_per_split;
+            const uint32_t batches = min(p.num_groups - t.batch, p.kb_per_split);
+            t.kb_begin = 0, t.kb_end = batches * num_kb_total;
+            t.last_umma = kBlockK / kUmmaK;                       // (the host requires whole k-blocks per batch)
+            t.x_row = m_blk * p.block_m;
+            t.d_row = t.x_row;
+            t.sfx_col = t.x_row, t.sfx_row = 0;
+            t.valid_m = min(p.block_m, p.m - t.x_row);
+            t.store_m = t.valid_m;
+            t.n0 = (n_unit * kCtaGroup + (cta_rank & 1)) * kBlockN;
+            t.w_row = t.n0;
+            t.sfw_col = t.n0, t.sfw_row = 0;
+            return true;
         } else if constexpr (kGemmType == kBatched) {
             // every batch is a full [m, n] problem; batches are walked in order (tensor-map coordinate 2 = batch)
             const uint32_t per_batch = p.num_m_blocks * num_n_units;
@@ -684,6 +707,7 @@ fp8_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
             uint16_t w_mask = 0;
             for (uint32_t q = 0; q < kPairs; ++q) w_mask |= static_cast<uint16_t>(1u << (2 * q + (cta_rank & 1)));
             uint32_t fresh = num_stages;          // slots never used yet: nothing to wait for (a TRYWAIT costs ~90 cycles)
+            uint32_t br_batch = 0, br_k0 = 0;     // kBatchReduce: the producer's position inside the current tile
             uint32_t landed_group = 0xffffffffu;
             while (sched.next(t)) {
                 if (kGemmType == kMContiguousPsum && t.valid_m == 0) continue;
@@ -717,7 +741,14 @@ fp8_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
                     if (first) DGB_STAMP(14);
                     const bool load_sfw = !kBf16AB && ((kb & sfw_mask) == 0 || first), load_sfx = !kBf16AB && ((kb & sfx_mask) == 0 || first);
                     mbar_arrive_expect_tx(full, ab_bytes + (load_sfw ? sfw_tx : 0u) + (load_sfx ? sfx_tx : 0u));
-                    if constexpr (kGemmType == kBatched) {
+                    if constexpr (kGemmType == kBatchReduce) {
+                        // virtual k-block -> (batch, byte offset inside the batch's K), kept incrementally
+                        if (first) br_batch = t.batch, br_k0 = 0;
+                        tma_load_3d(&map_w, full, slot, br_k0, t.w_row, br_batch, p.w_hint);
+                        tma_load_3d(&map_x, full, slot + off_x, br_k0, x_row, br_batch, p.x_hint);
+                        br_k0 += kBlockK;
+                        if (br_k0 >= p.k) br_k0 = 0, ++br_batch;
+                    } else if constexpr (kGemmType == kBatched) {
                         // 3-D maps {inner, outer, batch}: boxes are one batch deep, so the tiles land exactly like 2-D ones
                         if constexpr (kWMn) {
                             for (uint32_t j = 0; j < kEl; ++j)

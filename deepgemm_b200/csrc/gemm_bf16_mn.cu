@@ -37,6 +37,9 @@ int dispatch_bf16_mn(const GemmCall& c, const Config& cfg, const Maps& maps, con
                 return c.w_mn ? launch<kBatched, __nv_bfloat16, false, false, true>(c, cfg, maps, p)
                               : launch<kBatched, __nv_bfloat16, false, false, false>(c, cfg, maps, p);
             break;
+        case kBatchReduce:   // einsum 'bmk,bnk->mn' (einsum.hpp:22-60): FP32 D accumulated in place
+            if (!c.x_mn && !c.w_mn && c.d_dtype == DGB200_FP32 && c.accumulate) return launch<kBatchReduce, float, true, false, false>(c, cfg, maps, p);
+            break;
         case kKGrouped:
             if (c.x_mn && c.w_mn) return launch<kKGrouped, float, true, true, true>(c, cfg, maps, p);
             break;

@@ -336,13 +336,36 @@ def k_grouped_bf16_gemm_tn_contiguous(a: torch.Tensor, b: torch.Tensor, d: torch
                                                          num_groups, m, n, sum_k, int(use_psum_layout), _stream()))
 
 
+def _bmk_bnk_mn(a: torch.Tensor, b: torch.Tensor, d: torch.Tensor, c: Optional[torch.Tensor]) -> None:
+    """D[m,n] (+)= sum_b A[b] @ B[b].T (csrc/apis/einsum.hpp:22-60). FP32 D is accumulated in place (`c` must be `d`); a BF16 D
+    goes through a zeroed FP32 workspace and one cast, exactly as the reference does."""
+    _require(d.dtype in (torch.float32, torch.bfloat16), 'd is float or bfloat16')
+    if d.dtype == torch.bfloat16:
+        _require(c is None, 'c is not supported with a BF16 output')                 # einsum.hpp:30
+        ws = torch.zeros(d.shape, dtype=torch.float32, device=d.device)
+        _bmk_bnk_mn(a, b, ws, ws)
+        d.copy_(ws)
+        return
+    _require(c is not None and c.data_ptr() == d.data_ptr() and c.shape == d.shape and c.stride() == d.stride(),
+             'FP32 output: c must be d (accumulated in place)')                       # einsum.hpp:26
+    _require(a.is_contiguous() and b.is_contiguous() and d.is_contiguous(), 'a, b, d are contiguous')
+    _require(a.dim() == 3 and b.dim() == 3 and d.dim() == 2, 'a, b are 3-D, d is 2-D')
+    (s, m, k), (s_, n, k_) = a.shape, b.shape
+    _require(s == s_ and k == k_ and d.shape == (m, n), 'shapes agree')
+    _require(k % 64 == 0, 'k % 64 == 0')
+    _require(a.data_ptr() % 16 == 0 and b.data_ptr() % 16 == 0, '16-byte aligned operands')
+    check(lib().dgb200_bf16_bmk_bnk_mn(a.data_ptr(), b.data_ptr(), d.data_ptr(), s, m, n, k, _stream()))
+
+
 def einsum(expr: str, a: torch.Tensor, b: torch.Tensor, d: torch.Tensor, c: Optional[torch.Tensor] = None,
            use_cublaslt: bool = False) -> None:
-    """The BF16 contractions of the reference that run on its BF16 GEMM kernel (csrc/apis/einsum.hpp:62-136): 'bhr,hdr->bhd'
-    and 'bhd,hdr->bhr', each one batched GEMM over permuted views (batch = h, m = b), no copies. 'bmk,bnk->mn' (a separate
-    batch-reduction kernel in the reference, impls/sm100_bmk_bnk_mn.cuh) is not built."""
+    """The BF16 contractions of the reference (csrc/apis/einsum.hpp:22-136): 'bhr,hdr->bhd' and 'bhd,hdr->bhr', each one batched
+    GEMM over permuted views (batch = h, m = b), no copies; 'bmk,bnk->mn', the batch-reduction form (a separate kernel in the
+    reference, impls/sm100_bmk_bnk_mn.cuh; here a scheduler type of the same kernel)."""
     _require(a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16, 'a, b are bfloat16')
     _require(not use_cublaslt, 'use_cublaslt is not available in this library')
+    if expr == 'bmk,bnk->mn':
+        return _bmk_bnk_mn(a, b, d, c)
     if expr not in ('bhr,hdr->bhd', 'bhd,hdr->bhr'):
         raise RuntimeError(f'Unsupported einsum expression: {expr}')
     _require(c is None, 'c is not supported for this expression')                     # einsum.hpp:127,130

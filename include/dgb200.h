@@ -158,6 +158,11 @@ int dgb200_k_grouped_bf16_gemm_tn_contiguous(const void* a, const void* b, float
                                              int num_groups, int m, int n, int sum_k, int use_psum_layout, void* stream);
 /* Batched BF16 GEMM D[i] = A[i] B[i]^T behind einsum('bhr,hdr->bhd' / 'bhd,hdr->bhr'), csrc/apis/einsum.hpp:62-108: a K-major,
  * b K-major [batch, n, k] or MN-major [batch, k, n], d BF16; pitches and batch strides in elements (as dgb200_fp8_bmm). */
+/* Batch-reduction GEMM d[m, n] += sum_i a[i] b[i]^T behind einsum('bmk,bnk->mn'), csrc/apis/einsum.hpp:22-60
+ * (sm100_bmn_bnk_mn_gemm): a [batch, m, k], b [batch, n, k] BF16 contiguous, d FP32 [m, n] contiguous, accumulated in place;
+ * k % 64 == 0. The batches are cut into chunks over the grid, every chunk adds its partial tile with memory-side FP32 adds
+ * (the order of those adds is not fixed: results agree to FP32 rounding from run to run, as the reference's do). */
+int dgb200_bf16_bmk_bnk_mn(const void* a, const void* b, float* d, int batch, int m, int n, int k, void* stream);
 int dgb200_bf16_bmm(const void* a, const void* b, void* d, int batch, int m, int n, int k, int64_t lda, int64_t ldb,
                     int64_t ldd, int64_t batch_stride_a, int64_t batch_stride_b, int64_t batch_stride_d, int major_b,
                     void* stream);

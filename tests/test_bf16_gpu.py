@@ -257,7 +257,30 @@ def test_bf16_einsum(dg, h, r, dd, bsz):
     dg.einsum('bhd,hdr->bhr', x2, y, z2)
     _close(z2, torch.einsum('bhd,hdr->bhr', x2.float(), y.float()), 'bhd,hdr->bhr')
     with pytest.raises(RuntimeError):
-        dg.einsum('bmk,bnk->mn', x, x, z)
+        dg.einsum('bmk,bhk->mh', x, x, z)
+
+
+@pytest.mark.parametrize('s', [1, 129, 4096])
+@pytest.mark.parametrize('m,n,k', [(128, 384, 128), (256, 256, 256), (384, 128, 384), (72, 200, 64)])
+def test_bf16_einsum_bmk_bnk_mn(dg, s, m, n, k):
+    """The batch-reduction form, tests/test_einsum.py:16-35: FP32 D accumulated in place, BF16 D through an FP32 workspace.
+    Tolerance: the reference's own (calc_diff < 1e-5); partial tiles are added with memory-side FP32 adds in no fixed order."""
+    from deepgemm_b200.testing import calc_diff
+    gen = torch.Generator(device='cuda').manual_seed(s + m + k)
+    a = torch.randn((s, m, k), device='cuda', dtype=torch.bfloat16, generator=gen)
+    b = torch.randn((s, n, k), device='cuda', dtype=torch.bfloat16, generator=gen)
+    prod = torch.bmm(a.double(), b.double().mT).sum(0)
+    for dtype in (torch.float32, torch.bfloat16):
+        d = torch.randn((m, n), device='cuda', dtype=dtype, generator=gen)
+        c = d if dtype == torch.float32 else None
+        ref = (d.double() if dtype == torch.float32 else 0) + prod
+        dg.einsum('bmk,bnk->mn', a, b, d, c=c)
+        assert calc_diff(d, ref) < 1e-5, (s, m, n, k, dtype)
+        scale = float(ref.abs().max().clamp(min=1.0))
+        tol = 3e-5 * scale if dtype == torch.float32 else 2.0 ** -7 * scale
+        assert float((d.double() - ref).abs().max()) <= tol
+    with pytest.raises(RuntimeError):
+        dg.einsum('bmk,bnk->mn', a, b, torch.empty((m, n), device='cuda'), c=None)          # FP32 needs c is d
 
 
 @pytest.mark.parametrize('use_psum', [False, True])

@@ -54,3 +54,18 @@ ref.k_grouped_bf16_gemm_tn_contiguous(a, b, d0, ks, layout, c=d0)
 dg.k_grouped_bf16_gemm_tn_contiguous(a, b, d1, ks, layout, c=d1)
 torch.cuda.synchronize()
 print(json.dumps({'form': 'k_grouped_tn', 'bitwise_equal': bool(torch.equal(d0, d1)), 'max_abs_diff': float((d0 - d1).abs().max())}), flush=True)
+
+# the batch-reduction einsum against the reference's dedicated kernel (tests/test_einsum.py:16-35)
+for s_ in (129, 4096, 8192):
+    for (m, n, k) in [(128, 384, 128), (256, 256, 256), (384, 128, 384)]:
+        a = torch.randn((s_, m, k), device='cuda', dtype=torch.bfloat16)
+        b = torch.randn((s_, n, k), device='cuda', dtype=torch.bfloat16)
+        d0, d1 = torch.zeros((m, n), device='cuda'), torch.zeros((m, n), device='cuda')
+        ref.einsum('bmk,bnk->mn', a, b, d0, c=d0)
+        dg.einsum('bmk,bnk->mn', a, b, d1, c=d1)
+        torch.cuda.synchronize()
+        err = float((d0 - d1).abs().max() / d0.abs().max())
+        t_ref = bench_kineto(lambda: ref.einsum('bmk,bnk->mn', a, b, d0, c=d0), 'bmn_bnk_mn_gemm_impl', num_tests=10)
+        t_our = bench_kineto(lambda: dg.einsum('bmk,bnk->mn', a, b, d1, c=d1), 'fp8_gemm_kernel', num_tests=10)
+        print(json.dumps({'form': 'bmk,bnk->mn', 's': s_, 'm': m, 'n': n, 'k': k, 'max_rel_diff_vs_ref': err, 'ours_us': round(t_our * 1e6, 1),
+                          'ref_us': round(t_ref * 1e6, 1)}), flush=True)

@@ -79,6 +79,9 @@ ze = torch.zeros((40, 4, 128), device='cuda', dtype=torch.bfloat16)
 dg.einsum('bhr,hdr->bhd', xe, ye, ze)
 ze2 = torch.zeros((40, 4, 256), device='cuda', dtype=torch.bfloat16)
 dg.einsum('bhd,hdr->bhr', ze, ye, ze2)
+abr, bbr = torch.randn((37, 136, 128), device='cuda', dtype=torch.bfloat16), torch.randn((37, 264, 128), device='cuda', dtype=torch.bfloat16)
+dbr = torch.zeros((136, 264), device='cuda', dtype=torch.float32)
+dg.einsum('bmk,bnk->mn', abr, bbr, dbr, c=dbr)
 torch.cuda.synchronize()
 print('bf16 family done', flush=True)
 
