@@ -277,7 +277,8 @@ def test_bf16_einsum_bmk_bnk_mn(dg, s, m, n, k):
         dg.einsum('bmk,bnk->mn', a, b, d, c=c)
         assert calc_diff(d, ref) < 1e-5, (s, m, n, k, dtype)
         scale = float(ref.abs().max().clamp(min=1.0))
-        tol = 3e-5 * scale if dtype == torch.float32 else 2.0 ** -7 * scale
+        # up to 1.5 M products per output, accumulated in FP32 in chunks: the error grows with the length of the sum
+        tol = 2e-4 * scale if dtype == torch.float32 else 2.0 ** -7 * scale
         assert float((d.double() - ref).abs().max()) <= tol
     with pytest.raises(RuntimeError):
         dg.einsum('bmk,bnk->mn', a, b, torch.empty((m, n), device='cuda'), c=None)          # FP32 needs c is d
