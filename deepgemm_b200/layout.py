@@ -181,26 +181,29 @@ def get_default_recipe(sfa_dtype: torch.dtype, sfb_dtype: torch.dtype) -> Tuple[
     return (1, 128, 128) if sfb_dtype == torch.float32 else (1, 1, 128)
 
 
-_pair_memo = None   # the last validated pair of PRE-PACKED scale-factor tensors (weak references + the metadata that was checked)
+_pair_memo = {}   # (id(sfa), id(sfb)) -> the last validation of that pair of PRE-PACKED scale-factor tensors (weak references +
+                  # the metadata that was checked); a model has one pair per GEMM call site
 
 
 def transform_sf_pair_into_required_layout(sfa, sfb, m, n, k, recipe, recipe_a, recipe_b, num_groups_a, num_groups_b,
                                            disable_ue8m0_cast=False, psum_layout=None):
     """csrc/apis/layout.hpp:63-90. Returns (sfa, sfb, gran_k_a, gran_k_b).
 
-    An inference loop calls the GEMM with the same pre-packed scale-factor tensors over and over (weights always, activations
-    under CUDA graphs / static buffers); re-running the chain of layout checks costs ~4 us of a ~10 us kernel. The last
-    validated pair is remembered by identity, and a repeat call only confirms that shapes and strides are still the ones that
-    were checked (an in-place transpose or resize would change them)."""
-    global _pair_memo
-    memo = _pair_memo
+    An inference loop calls the GEMMs with the same pre-packed scale-factor tensors over and over (weights always, activations
+    under CUDA graphs / static buffers); re-running the chain of layout checks costs ~4 us of a ~10 us kernel. Validated pairs
+    are remembered by identity, and a repeat call only confirms that shapes and strides are still the ones that were checked
+    (an in-place transpose or resize would change them)."""
+    key = (id(sfa), id(sfb))
+    memo = _pair_memo.get(key)
     args = (m, n, k, recipe, recipe_a, recipe_b, num_groups_a, num_groups_b)
     if (memo is not None and psum_layout is None and memo[0]() is sfa and memo[1]() is sfb and memo[2] == args
             and sfa.shape == memo[3] and sfa.stride() == memo[4] and sfb.shape == memo[5] and sfb.stride() == memo[6]):
         return memo[7]
     out = _transform_sf_pair(sfa, sfb, m, n, k, recipe, recipe_a, recipe_b, num_groups_a, num_groups_b, disable_ue8m0_cast, psum_layout)
     if out[0] is sfa and out[1] is sfb and psum_layout is None:        # both were pre-packed: nothing was computed, only checked
-        _pair_memo = (weakref.ref(sfa), weakref.ref(sfb), args, sfa.shape, sfa.stride(), sfb.shape, sfb.stride(), out)
+        if len(_pair_memo) >= 1024:
+            _pair_memo.clear()
+        _pair_memo[key] = (weakref.ref(sfa), weakref.ref(sfb), args, sfa.shape, sfa.stride(), sfb.shape, sfb.stride(), out)
     return out
 
 
