@@ -46,7 +46,8 @@ struct Control {
     uint32_t overflow;            // set when a dispatch would not fit `capacity`
     uint32_t num_routed;          // local tokens with a valid expert in the last dispatch
     uint32_t grid_bar;            // fused dispatch: grid barrier arrivals (reset by the last CTA of every launch)
-    uint32_t pad[26];
+    uint32_t pad[2];
+    uint64_t dbg_ns[12];          // globaltimer stamps of the last fused dispatch [0..7] and combine [8..10] (development: tools/ep_phases.py)
     uint32_t counts_flag[kMaxWorld * 8];   // [s*8]: epoch of the counts source rank s published here (32 B apart)
     uint32_t data_flag[kMaxWorld * 8];     // [s*8]: epoch of the rows source rank s finished writing here
     uint32_t gemm_flag[kMaxWorld * 8];     // [o*8]: epoch of the grouped GEMM owner rank o has finished (combine)
@@ -427,6 +428,8 @@ dispatch_fused_kernel(Peers peers, Layout l, const uint8_t* __restrict__ x, int6
     const uint32_t num_slices = (num_entries + slice_len - 1) / slice_len;
     const bool ranker = cta < num_slices;
     const uint32_t slice_begin = cta * slice_len, slice_end = min(num_entries, slice_begin + slice_len);
+    const bool stamper = cta == 0 && tid == 0;
+    if (stamper) ctrl->dbg_ns[0] = ep_globaltimer();
 
     // ---- phase 1: stable rank of every entry inside (its expert, this slice) + the slice's histogram
     if (ranker) {
@@ -455,6 +458,7 @@ dispatch_fused_kernel(Peers peers, Layout l, const uint8_t* __restrict__ x, int6
         for (uint32_t e = tid; e < num_experts; e += blockDim.x) hist[cta * num_experts + e] = static_cast<int32_t>(s_cnt[e]);
     }
     grid_barrier(&ctrl->grid_bar, grid);
+    if (stamper) ctrl->dbg_ns[1] = ep_globaltimer();
 
     // ---- phase 2a (CTA 0): my counts -> every peer; theirs -> destination rows of my tokens + the local psum layout
     if (cta == 0) {
@@ -470,8 +474,10 @@ dispatch_fused_kernel(Peers peers, Layout l, const uint8_t* __restrict__ x, int6
         __threadfence_system();
         __syncthreads();
         if (tid < world) st_release_sys(&reinterpret_cast<Control*>(peers.base[tid])->counts_flag[rank * 8], epoch);
+        if (stamper) ctrl->dbg_ns[2] = ep_globaltimer();
         if (tid < world) wait_flag(&ctrl->counts_flag[tid * 8], epoch);
         __syncthreads();
+        if (stamper) ctrl->dbg_ns[3] = ep_globaltimer();
         const int32_t* table = reinterpret_cast<const int32_t*>(mine + l.table_off) + table_half;
         for (uint32_t e = tid; e < num_experts; e += blockDim.x) {
             uint32_t total = 0, before = 0;
@@ -517,6 +523,7 @@ dispatch_fused_kernel(Peers peers, Layout l, const uint8_t* __restrict__ x, int6
         }
     }
     grid_barrier(&ctrl->grid_bar, 2 * grid);
+    if (stamper) ctrl->dbg_ns[4] = ep_globaltimer();
 
     // ---- phase 3: scatter, one warp per entry (grid-strided so that consecutive warps write consecutive rows' worth of bytes)
     {
@@ -559,6 +566,7 @@ dispatch_fused_kernel(Peers peers, Layout l, const uint8_t* __restrict__ x, int6
     }
 
     // ---- phase 4: the last CTA tells every peer that all of this rank's rows have landed and waits for theirs
+    if (stamper) ctrl->dbg_ns[5] = ep_globaltimer();
     __threadfence_system();
     __syncthreads();
     __shared__ uint32_t s_last;
@@ -572,9 +580,11 @@ dispatch_fused_kernel(Peers peers, Layout l, const uint8_t* __restrict__ x, int6
             __threadfence_system();
         }
         __syncthreads();
+        if (tid == 0) ctrl->dbg_ns[6] = ep_globaltimer();
         if (tid < world) st_release_sys(&reinterpret_cast<Control*>(peers.base[tid])->data_flag[rank * 8], epoch);
         if (tid < world) wait_flag(&ctrl->data_flag[tid * 8], epoch);
         __syncthreads();
+        if (tid == 0) ctrl->dbg_ns[7] = ep_globaltimer();
         __threadfence_system();
     }
 }
@@ -605,8 +615,12 @@ combine_gather_kernel(Peers ctrl_bufs, Peers d_bufs, const void* __restrict__ id
     asm volatile("griddepcontrol.wait;" ::: "memory");
     const Control* ctrl = reinterpret_cast<const Control*>(ctrl_bufs.base[rank]);
     const uint32_t epoch = ctrl->epoch;
+    uint64_t* dbg = const_cast<uint64_t*>(ctrl->dbg_ns);
+    const bool stamper = blockIdx.x == 0 && threadIdx.x == 0;
+    if (stamper) dbg[8] = ep_globaltimer();
     if (threadIdx.x < world) wait_flag(&ctrl->gemm_flag[threadIdx.x * 8], epoch);   // every owner's GEMM of this step is done
     __syncthreads();
+    if (stamper) dbg[9] = ep_globaltimer();
     const uint32_t epr = num_experts / world;
     const uint32_t lane = threadIdx.x % 32, warps_per_cta = blockDim.x / 32;
     const uint32_t chunks = row_bytes / 16;
@@ -671,6 +685,7 @@ combine_gather_kernel(Peers ctrl_bufs, Peers d_bufs, const void* __restrict__ id
             dst[c] = make_uint4(o[0], o[1], o[2], o[3]);
         }
     }
+    if (stamper) dbg[10] = ep_globaltimer();
 }
 
 }  // namespace ep

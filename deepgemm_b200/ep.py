@@ -214,6 +214,10 @@ class EpBuffer:
     def num_rows(self) -> int:
         return int(self._ctrl[self.off_rows // 4].item())
 
+    def debug_timestamps(self):
+        """globaltimer stamps (ns) of the last fused dispatch [0..7] and combine [8..10] on this rank (development; synchronises)."""
+        return self._bytes[32:128].view(torch.int64).tolist()
+
     def overflowed(self) -> bool:
         return bool(self._ctrl[self.off_overflow // 4].item())
 
