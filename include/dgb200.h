@@ -266,7 +266,7 @@ typedef struct dgb200_config {
     int num_tiles;   /* upper bound on (cluster) tiles */
     int num_splits;  /* split-K slices (1 = none) */
     int cluster_split; /* != 0: the slices are the CTAs of one cluster, reduced through distributed shared memory */
-    int tma_store;   /* != 0: output tiles are staged in shared memory and written with TMA stores */
+    int tma_store;   /* != 0: output tiles are staged in shared memory (TMA stores; plain coalesced stores in the transposed orientation) */
     int swap_ab;     /* != 0: transposed-output orientation (tokens on the TMEM lanes, block_m = weight rows per tile) */
 } dgb200_config;
 /* Pure function (no CUDA): the configuration the heuristics pick for a problem on `num_sms` SMs.
