@@ -109,6 +109,10 @@ if __name__ == '__main__':
         for shape, bns in [((64, 7168, 2048), (48, 64, 96)), ((128, 7168, 2048), (48, 64, 96)), ((128, 24576, 1536), (160, 176, 192, 224)),
                            ((64, 24576, 1536), (160, 176, 192)), ((64, 32768, 512), (224, 240)), ((128, 7168, 16384), (48, 64))]:
             run([shape], [dict(swap=0)] + [dict(swap=1, block_m=bn, tma_store=ts) for bn in bns for ts in ((0, 1) if bn % 32 == 0 else (0,))])
+    elif mode == 'swap_mid':
+        # mid M at N = 4096, K = 7168: tokens on the lanes of a CTA pair (256 per tile), narrow weight tiles so that all SMs work
+        for m_ in (224, 256, 320, 384, 448):
+            run([(m_, 4096, 7168)], [dict(swap=0)] + [dict(swap=1, block_m=bn, tma_store=ts) for bn in (48, 56, 64, 96, 112) for ts in ((0, 1) if bn % 32 == 0 else (0,))])
     elif mode == 'small3':
         # short K with many weight panels at small M: single CTAs (192 / 56 independent tiles) vs pairs vs 2 single-CTA slices
         cfgs = [{}, dict(cluster=1, csplit=0), dict(cluster=1, csplit=0, block_m=64), dict(cluster=1, csplit=0, block_m=32), dict(csplit=2)]
