@@ -258,6 +258,9 @@ def dense_step_setup(device, gemm, transform):
     return probs
 
 
+RETIMED = None   # set by time_dense_step when the timed region had to be measured a second time
+
+
 def time_dense_step(args, world, device, probs, gemm, on_first_call=None):
     """W warm-up steps, then exactly K timed steps; every launch preceded by an L2 flush and bracketed by CUDA events.
     Returns (per-shape mean ms, per-step ms lists, clock summary, wall seconds)."""
@@ -274,10 +277,7 @@ def time_dense_step(args, world, device, probs, gemm, on_first_call=None):
             elif on_first_call is not None:
                 on_first_call(p)
 
-    # the clock sampler starts before the warm-up: its start-up noise and the idle->busy clock ramp fall outside the timed region
-    with ClockSampler(torch.cuda.current_device()) as clocks:
-        for _ in range(args.warmup):
-            step()
+    def timed_region(clocks):
         torch.cuda.synchronize()
         barrier(world)
         events = [[(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in probs]
@@ -287,9 +287,38 @@ def time_dense_step(args, world, device, probs, gemm, on_first_call=None):
         for s in range(args.steps):
             step(events[s])
         torch.cuda.synchronize()
-        wall = time.perf_counter() - t0
+        wall_ = time.perf_counter() - t0
+        ms = [[e[i][0].elapsed_time(e[i][1]) for i in range(len(probs))] for e in events]
+        return ms, wall_
+
+    def stalled(ms):
+        """A launch that took more than 3x the median of its shape: the host stalled between the event and the launch (the
+        events bracket one kernel each, so the GPU sat idle inside the bracket). Seen once with 4 ranks on one box."""
+        worst = 0.0
+        for i in range(len(probs)):
+            col = sorted(st[i] for st in ms)
+            worst = max(worst, col[-1] / max(col[len(col) // 2], 1e-9))
+        return worst
+
+    global RETIMED
+    RETIMED = None
+    # the clock sampler starts before the warm-up: its start-up noise and the idle->busy clock ramp fall outside the timed region
+    with ClockSampler(torch.cuda.current_device()) as clocks:
+        for _ in range(args.warmup):
+            step()
+        per_step_ms, wall = timed_region(clocks)
+        ratio = allreduce_max(stalled(per_step_ms), world, device)
+        if os.environ.get('BENCH_FORCE_RETIME'):      # (test hook for the second-attempt path)
+            ratio = 99.0
+        if ratio > 3.0:
+            # like a throttled run: rejected and re-measured ONCE, by every rank together; both attempts are reported
+            first = sum(sum(st[i] for st in per_step_ms) / args.steps for i in range(len(probs)))
+            per_step_ms, wall = timed_region(clocks)
+            RETIMED = {'reason': 'a launch took %.1fx the median of its shape on some rank (host stall inside an event bracket); the K timed '
+                                 'steps were measured again once' % ratio,
+                       'first_attempt_ms_per_step_this_rank': round(first, 4),
+                       'second_attempt_worst_over_median': round(allreduce_max(stalled(per_step_ms), world, device), 2)}
     barrier(world)
-    per_step_ms = [[e[i][0].elapsed_time(e[i][1]) for i in range(len(probs))] for e in events]
     per_shape_ms = [sum(st[i] for st in per_step_ms) / args.steps for i in range(len(probs))]
     return per_shape_ms, per_step_ms, clocks.summary(), wall
 
@@ -354,6 +383,7 @@ def run_dense(args, rank, world, device):
 
     launches0 = _lib.launch_count()
     per_shape_ms, per_step_ms, clock_summary, t_wall = time_dense_step(args, world, device, probs, dg.fp8_gemm_nt, note_tile)
+    retimed = RETIMED
     launches = (_lib.launch_count() - launches0) * args.steps // (args.steps + args.warmup)
     step_ms = allreduce_max(sum(per_shape_ms), world, device)
     flops = sum(2.0 * p['m'] * p['n'] * p['k'] for p in probs)
@@ -406,7 +436,8 @@ def run_dense(args, rank, world, device):
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'fp8_e4m3 (fp32 accumulate, bf16 out)',
         'data': 'synthetic', 'impl': 'deepgemm_b200',
         'config': {'workload': 'dense fp8_gemm_nt M in {64,128,512,4096} N=4096 K=7168, 1x128/128x128 UE8M0 SF',
-                   'l2': 'flushed (512 MB write) before every timed launch', 'parallelism': f'replicas x{world}'},
+                   'l2': 'flushed (512 MB write) before every timed launch', 'parallelism': f'replicas x{world}',
+                   **({'retimed': retimed} if retimed else {})},
         'per_shape': per_shape, 'roofline': roofline, 'clocks': clock_summary,
         'e2e': {'value': round(e2e_value, 3), 'unit': 'TFLOPS', 'ms_per_step': round(e2e_ms, 4),
                 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h),
@@ -979,6 +1010,7 @@ def run_reference_arm_gpu(args, rank, world, device):
     ref = import_reference()
     probs = dense_step_setup(device, ref.fp8_gemm_nt, ref.transform_sf_into_required_layout)
     per_shape_ms, per_step_ms, clock_summary, _ = time_dense_step(args, world, device, probs, ref.fp8_gemm_nt)
+    retimed = RETIMED
     step_ms = allreduce_max(sum(per_shape_ms), world, device)
     flops = sum(2.0 * p['m'] * p['n'] * p['k'] for p in probs)
     value = flops * world / (step_ms * 1e-3) / 1e12
@@ -994,7 +1026,8 @@ def run_reference_arm_gpu(args, rank, world, device):
         'dtype': 'fp8_e4m3 (fp32 accumulate, bf16 out)', 'data': 'synthetic',
         'reference': 'deepseek-ai/DeepGEMM, unmodified, oracle/_ref: deep_gemm.fp8_gemm_nt -> sm100_fp8_fp4_gemm_1d1d (NVCC JIT on this box)',
         'config': {'workload': 'dense fp8_gemm_nt M in {64,128,512,4096} N=4096 K=7168, 1x128/128x128 UE8M0 SF',
-                   'l2': 'flushed (512 MB write) before every timed launch', 'parallelism': f'replicas x{world}'},
+                   'l2': 'flushed (512 MB write) before every timed launch', 'parallelism': f'replicas x{world}',
+                   **({'retimed': retimed} if retimed else {})},
         'per_shape': [{'m': p['m'], 'n': p['n'], 'k': p['k'], 'us': round(ms * 1e3, 2),
                        'tflops': round(2.0 * p['m'] * p['n'] * p['k'] / (ms * 1e-3) / 1e12, 1)} for p, ms in zip(probs, per_shape_ms)],
         'clocks': clock_summary,
