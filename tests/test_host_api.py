@@ -249,3 +249,12 @@ def test_prepacked_scale_factor_pair_memo_notices_a_changed_layout():
     sfa.t_()                                                                                                       # same object, new layout
     with pytest.raises(RuntimeError):
         layout.transform_sf_pair_into_required_layout(sfa, sfb, m, n, k, None, None, None, None, None)
+
+
+def test_tools_and_bench_compile():
+    """bench.py, __graft_entry__.py and every helper under tools/ at least parse (they only run on the GPU box)."""
+    import glob
+    files = [os.path.join(REPO, 'bench.py'), os.path.join(REPO, '__graft_entry__.py')] + sorted(glob.glob(os.path.join(REPO, 'tools', '*.py')))
+    assert len(files) > 10
+    for f in files:
+        compile(open(f).read(), f, 'exec')
