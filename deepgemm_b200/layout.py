@@ -198,12 +198,13 @@ def transform_sf_pair_into_required_layout(sfa, sfb, m, n, k, recipe, recipe_a, 
     args = (m, n, k, recipe, recipe_a, recipe_b, num_groups_a, num_groups_b)
     if (memo is not None and psum_layout is None and memo[0]() is sfa and memo[1]() is sfb and memo[2] == args
             and sfa.shape == memo[3] and sfa.stride() == memo[4] and sfb.shape == memo[5] and sfb.stride() == memo[6]):
-        return memo[7]
+        return sfa, sfb, memo[7], memo[8]
     out = _transform_sf_pair(sfa, sfb, m, n, k, recipe, recipe_a, recipe_b, num_groups_a, num_groups_b, disable_ue8m0_cast, psum_layout)
     if out[0] is sfa and out[1] is sfb and psum_layout is None:        # both were pre-packed: nothing was computed, only checked
         if len(_pair_memo) >= 1024:
             _pair_memo.clear()
-        _pair_memo[key] = (weakref.ref(sfa), weakref.ref(sfb), args, sfa.shape, sfa.stride(), sfb.shape, sfb.stride(), out)
+        # (weak references only: the memo must not keep a caller's tensors alive)
+        _pair_memo[key] = (weakref.ref(sfa), weakref.ref(sfb), args, sfa.shape, sfa.stride(), sfb.shape, sfb.stride(), out[2], out[3])
     return out
 
 

@@ -239,7 +239,15 @@ def test_prepacked_scale_factor_pair_memo_notices_a_changed_layout():
     sfb = torch.zeros((k // 512, n), dtype=torch.int32).t()
     first = layout.transform_sf_pair_into_required_layout(sfa, sfb, m, n, k, None, None, None, None, None)
     again = layout.transform_sf_pair_into_required_layout(sfa, sfb, m, n, k, None, None, None, None, None)
-    assert again is first and first[0] is sfa and first[1] is sfb and first[2:] == (128, 128)
+    assert again == first and again[0] is sfa and again[1] is sfb and first[2:] == (128, 128)
+    import gc
+    import weakref
+    probe = torch.zeros((k // 512, m), dtype=torch.int32).t()
+    layout.transform_sf_pair_into_required_layout(probe, sfb, m, n, k, None, None, None, None, None)
+    alive = weakref.ref(probe)
+    del probe
+    gc.collect()
+    assert alive() is None, 'the memo keeps a validated tensor alive' 
     with pytest.raises(RuntimeError):
         layout.transform_sf_pair_into_required_layout(sfa, sfb, m + 4, n, k, None, None, None, None, None)     # other problem size
     other = torch.zeros((m, k // 512), dtype=torch.int32)                                                         # K-major storage: not TMA-ready
