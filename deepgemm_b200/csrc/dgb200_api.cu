@@ -303,7 +303,9 @@ Config choose_config(const Problem& pb, int num_sms_override = 0) {
         const int units = c.num_sms / 2, n_units = ceil_div(pb.n, (int)kBlockN * 2);
         const double overhead_rows = kTileOverhead / (2.0 * num_kb);      // per-tile fixed cost in units of token rows
         double best_ms = 1e300;
+        const int force_nb = env_int("DGB200_M_BLOCKS", 0);      // (development: pin the number of m-blocks)
         for (int nb = ceil_div(pb.m, (int)kMaxBlockM); nb <= ceil_div(pb.m, 160) && nb * n_units <= 64 * units; ++nb) {
+            if (force_nb && nb != force_nb) continue;
             const int hi = align_up(ceil_div(pb.m, nb), 16), lo = hi - 16;
             if (hi > (int)kMaxBlockM || lo < 16) continue;
             // tall blocks: smallest count with tall * hi + (nb - tall) * lo >= m
@@ -316,7 +318,11 @@ Config choose_config(const Problem& pb, int num_sms_override = 0) {
                 for (int mb = 0; mb < nb; ++mb) {
                     const int row0 = mb < tall ? mb * hi : tall * hi + (mb - tall) * lo;
                     const int h = std::max(0, std::min(mb < tall ? hi : lo, pb.m - row0));
-                    for (int j = 0; j < width; ++j, ++idx) load[idx % units] += align_up(std::max(h, 1), 16) + overhead_rows;
+                    // taller tiles are worth more than their rows: fewer operand bytes per FLOP, which under the power cap is
+                    // clock (measured, tools/tune.py mblocks / mblocks2: 4096 x 4096 x 7168 76.1 us with 18 m-blocks of 240 / 224
+                    // rows against 76.9 with 23 of 192 / 176; 3000 x 4096 x 7168 58.6 against 60.6) -- ~1 % per 24 rows below 240
+                    const double rows = align_up(std::max(h, 1), 16);
+                    for (int j = 0; j < width; ++j, ++idx) load[idx % units] += rows * (1.0 + 0.10 * (240.0 - rows) / 240.0) + overhead_rows;
                 }
             }
             const double ms = *std::max_element(load.begin(), load.end());
@@ -415,10 +421,10 @@ Config choose_config(const Problem& pb, int num_sms_override = 0) {
         // Measured (tools/tune.py store): the staged epilogue wins 1-4 % on tall tiles with a long enough K loop to hide it
         // behind (4096 x 4096 x 7168, 4096 x 7168 x 2048, 4096 x 24576 x 1536 at 240 rows); it loses when it costs a pipeline
         // stage, on short tiles, and when the kernel is epilogue-bound (K = 512: 8 warps of direct stores move more bytes per
-        // cycle than one TMA issuer).
+        // cycle than one TMA issuer; K = 1536 at 240 rows: 106.7 us staged, 104.2 direct) -- hence K >= 2048.
         const int want = env_int("DGB200_TMA_STORE", -1);
         c.tma_store = want >= 0 ? (want != 0)
-                                : (c.block_m >= kTmaStoreMinBlockM && num_kb >= 12 && max_stages((int)kStoreStagingBytes) == max_stages(0));
+                                : (c.block_m >= kTmaStoreMinBlockM && num_kb >= 16 && max_stages((int)kStoreStagingBytes) == max_stages(0));
     }
     const int store_bytes = c.tma_store ? (pb.swapped ? (int)kSwapStagingBytes : (int)kStoreStagingBytes) : 0;
     int stages = max_stages(store_bytes);

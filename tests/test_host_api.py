@@ -194,11 +194,14 @@ def test_ep_buffer_layout_and_argument_checks(lib):
 
 
 def test_dense_plan_balances_rounds_of_cta_pairs(lib):
-    """M = N = 4096 on 74 CTA pairs: 240-row tiles are 288 tiles = 3.89 rounds; the planner picks 23 m-blocks (368 tiles,
-    4.97 rounds) of 192 / 176 rows instead."""
+    """M = N = 4096 on 74 CTA pairs: uniform 240-row tiles would leave a 16-row m-block behind (17 x 240 + 16); the planner
+    makes 18 m-blocks of 240 / 224 rows (288 tiles, 3.89 rounds). It weighs rows by tile height (taller tiles move fewer
+    operand bytes per FLOP, which is clock under the power cap): 23 m-blocks of 192 / 176 rows fill 4.97 rounds more evenly
+    but measured 1 % slower. M = 6144 keeps shorter tiles: 32 m-blocks of 192 rows are 6.92 rounds."""
     cfg = lib.plan(0, 4096, 4096, 7168)
-    assert cfg['block_m'] == 192 and cfg['cluster'] == 2 and cfg['num_splits'] == 1
-    assert cfg['num_tiles'] == 23 * 16                  # 3 x 192 + 20 x 176 rows = 4096, times 16 column pairs
+    assert cfg['block_m'] == 240 and cfg['cluster'] == 2 and cfg['num_splits'] == 1
+    assert cfg['num_tiles'] == 18 * 16                  # 4 x 240 + 14 x 224 rows = 4096, times 16 column pairs
+    assert lib.plan(0, 8192, 4096, 7168)['block_m'] == 224          # 37 m-blocks of 224 / 208 rows: 8 rounds
     small = lib.plan(0, 512, 4096, 7168)
     assert small['block_m'] == 128                       # below 1024 rows the tile height is chosen by the cost model alone
 
@@ -219,7 +222,7 @@ def test_plan_picks_pair_split_k_and_the_staged_epilogue_where_measured(lib):
     c = lib.plan(0, 64, 4096, 7168)
     assert (c['cluster'], c['cluster_split']) == (4, 4)                          # small M: four single-CTA slices
     big = lib.plan(0, 4096, 7168, 2048)
-    assert big['tma_store'] == 1 and big['block_m'] >= 176 and big['num_stages'] == 7
+    assert big['tma_store'] == 1 and big['block_m'] >= 176 and big['num_stages'] >= 6
     assert lib.plan(0, 4096, 32768, 512)['tma_store'] == 0                       # epilogue-bound: direct stores
     assert lib.plan(0, 512, 4096, 7168)['tma_store'] == 0                        # 128-row tiles: the staging would cost a stage
     assert lib.plan(1, 32768, 4096, 7168, 256, 128, 128)['tma_store'] == 0       # contiguous, 128-row tiles

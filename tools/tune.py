@@ -11,7 +11,7 @@ import deepgemm_b200 as dg  # noqa: E402
 from deepgemm_b200 import _lib  # noqa: E402
 from deepgemm_b200.testing import bench_kineto  # noqa: E402
 
-KEYS = ('DGB200_BLOCK_M', 'DGB200_CLUSTER', 'DGB200_STAGES', 'DGB200_SWIZZLE_GROUP', 'DGB200_CSPLIT', 'DGB200_SPLITS', 'DGB200_PSPLIT',
+KEYS = ('DGB200_M_BLOCKS', 'DGB200_BLOCK_M', 'DGB200_CLUSTER', 'DGB200_STAGES', 'DGB200_SWIZZLE_GROUP', 'DGB200_CSPLIT', 'DGB200_SPLITS', 'DGB200_PSPLIT',
         'DGB200_PSPLIT_BM', 'DGB200_TMA_STORE', 'DGB200_SWAP')
 
 
@@ -113,6 +113,22 @@ if __name__ == '__main__':
         # mid M at N = 4096, K = 7168: tokens on the lanes of a CTA pair (256 per tile), narrow weight tiles so that all SMs work
         for m_ in (224, 256, 320, 384, 448):
             run([(m_, 4096, 7168)], [dict(swap=0)] + [dict(swap=1, block_m=bn, tma_store=ts) for bn in (48, 56, 64, 96, 112) for ts in ((0, 1) if bn % 32 == 0 else (0,))])
+    elif mode == 'mblocks':
+        # dense, tensor-bound: the number of m-blocks (two heights each) behind the wave-balancing choice
+        run([(4096, 4096, 7168)], [{}] + [dict(m_blocks=nb) for nb in (18, 19, 20, 21, 22, 23, 24, 25)] + [{}])
+        run([(4096, 7168, 2048)], [{}] + [dict(m_blocks=nb) for nb in (18, 19, 20, 21, 22, 23)])
+        run([(2048, 4096, 7168)], [{}] + [dict(m_blocks=nb) for nb in (9, 10, 11, 12, 13)])
+    elif mode == 'mblocks2':
+        run([(4096, 24576, 1536)], [{}] + [dict(m_blocks=nb) for nb in (18, 19, 20)])
+        run([(3000, 4096, 7168)], [{}] + [dict(m_blocks=nb) for nb in (13, 14, 18)])
+        run([(6144, 4096, 7168)], [{}] + [dict(m_blocks=nb) for nb in (27, 28, 32)])
+        run([(8192, 4096, 7168)], [{}] + [dict(m_blocks=nb) for nb in (35, 36, 37)])
+        run([(4096, 7168, 16384)], [{}] + [dict(m_blocks=nb) for nb in (18, 21)], with_ref=False)
+    elif mode == 'tall':
+        # the wave balancer's choice on tall dense problems (default configuration; + the direct epilogue where K is short)
+        run([(4096, 4096, 7168), (4096, 7168, 2048), (3000, 4096, 7168), (2048, 4096, 7168), (6144, 4096, 7168), (8192, 4096, 7168),
+             (4096, 2112, 7168), (1024, 4096, 7168)], [{}])
+        run([(4096, 24576, 1536), (4096, 32768, 512), (4096, 7168, 16384)], [{}, dict(tma_store=0)])
     elif mode == 'small3':
         # short K with many weight panels at small M: single CTAs (192 / 56 independent tiles) vs pairs vs 2 single-CTA slices
         cfgs = [{}, dict(cluster=1, csplit=0), dict(cluster=1, csplit=0, block_m=64), dict(cluster=1, csplit=0, block_m=32), dict(csplit=2)]
